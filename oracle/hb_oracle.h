@@ -1,0 +1,110 @@
+/*
+ * hb_oracle.h -- CPU oracle for the hibayes Gibbs hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+ * arm may load this library; the product (hibayes_b200/) never links or calls it.
+ *
+ * PARITY UNPINNED: the reference (YinLiLin/hibayes @ 98328fe) ships no tests and
+ * no golden vectors for this path, cannot be built here (needs R, Rcpp,
+ * RcppArmadillo, bigmemory, libRmath -- none present), and its random numbers
+ * come from libR's sequential stream (third party, version unpinned;
+ * DESCRIPTION:35 "R (>= 3.3.0)").  This oracle is therefore a literal
+ * restatement of the reference arithmetic (file:line cited at each function)
+ * driven by the position-addressed Philox stream of hibayes_b200/csrc/hb_rng.h
+ * instead of libR.  The samplers are pinned to the distributions R documents by
+ * tests/test_samplers.py (scipy.stats), Philox by the Random123 known-answer
+ * vectors, and the whole chain by statistical recovery tests on the bundled
+ * inst/extdata/demo data (tests/golden/).
+ */
+#ifndef HB_ORACLE_H
+#define HB_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HBO_NA (__builtin_nan(""))
+
+typedef struct {
+  /* data */
+  int n, m;
+  const double* y;       /* n */
+  const void* X;         /* n x m column-major */
+  int x_is_int8;         /* 0: double, 1: int8 */
+  const char* model;     /* "BayesRR","BayesA","BayesB","BayesBpi","BayesC","BayesCpi","BayesL","BayesR" */
+  int n_fold;
+  const double* Pi;      /* n_fold */
+  const double* fold;    /* n_fold or NULL */
+  int nc;
+  const double* C;       /* n x nc column-major or NULL */
+  int nr;
+  const int32_t* Rlev;   /* n x nr column-major 0-based level codes or NULL */
+  const int32_t* nlev;   /* nr */
+  int niter, nburn, thin;
+  double dfvr, s2vr, vg, dfvg, s2vg, ve, dfve, s2ve; /* NaN = not given */
+  const int32_t* windindx; /* m, 1-based window ids, or NULL */
+  uint64_t seed;
+  /* single-step epsilon term (Bayes.cpp:254-275,554-584); ne = 0 disables */
+  int ne, qe;
+  const double* epsl_y_J;     /* n */
+  const int32_t* epsl_index;  /* ne, 1-based */
+  const int32_t* Gi_colptr;   /* qe+1, CSC of epsl_Gi */
+  const int32_t* Gi_rowidx;
+  const double* Gi_val;
+} hbo_bayes_args;
+
+typedef struct {
+  double Vg, Ve, h2, mu, Veps, J;
+  double* beta;        /* nc */
+  double* alpha;       /* m */
+  double* pi;          /* n_fold */
+  double* pip;         /* m */
+  double* gwas;        /* nw (max window id) or NULL */
+  double* g;           /* n   (the reference returns u here, Bayes.cpp:1023) */
+  double* e;           /* n */
+  double* vr;          /* nr */
+  double* estR;        /* sum(nlev) */
+  double* epsilon;     /* qe */
+  /* MCMC stores, n_records columns each (NULL to skip) */
+  double* mu_store; double* vara_store; double* vare_store; double* hsq_store;
+  double* pi_store;    /* n_fold x n_records col-major */
+  double* alpha_store; /* m x n_records col-major */
+  double* beta_store;  /* nc x n_records */
+  /* diagnostics for parity tests */
+  int32_t* tracker_final; /* m */
+  double* nzrate_count;   /* m: raw counts before /nzct */
+  double* wppa_count;     /* nw */
+  int32_t* nnz_trace;     /* niter */
+  double* vara_trace;     /* niter */
+  double* vare_trace;     /* niter */
+  double* varg_trace;     /* niter */
+  int n_records_done;
+  int nzct;
+  int iters_done;
+  double seconds_sweep;   /* wall seconds inside the SNP sweeps */
+} hbo_bayes_out;
+
+/* returns 0 on success, else nonzero and hbo_last_error() holds the message
+ * (same texts as the Rcpp::exception()s in Bayes.cpp:92-117,325,356). */
+int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o);
+const char* hbo_last_error(void);
+
+/* helpers exposed for unit tests */
+double hbo_var(const double* x, int n);             /* Armadillo var(), norm_type 0 */
+double hbo_qnorm(double p);
+void hbo_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+double hbo_draw_gamma(uint64_t seed, uint32_t dom, uint32_t iter, uint32_t idx, uint32_t slot, double shape);
+double hbo_draw_chisq(uint64_t seed, uint32_t dom, uint32_t iter, uint32_t idx, uint32_t slot, double df);
+void hbo_draw_uz(uint64_t seed, uint32_t dom, uint32_t iter, uint32_t idx, uint32_t slot, uint32_t attempt, double* u, double* z);
+double hbo_invgauss(double mu, double lambda, double u, double z);
+
+/* CPU timing of the reference's level-1 path: per-SNP ddot + 2 daxpy on a
+ * column-major fp64 X (Bayes.cpp:756,787-789), `threads` OpenMP threads split
+ * each vector op.  Returns SNP-updates per second. */
+double hbo_time_sweep_fp64(int n, int m_cpu, int sweeps, int threads, uint64_t seed, double* checksum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,198 @@
+"""ctypes loader for the CPU oracle (oracle/libhb_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm
+import this module; nothing under hibayes_b200/ does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libhb_oracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.hbo_bayes.restype = C.c_int
+        _LIB.hbo_last_error.restype = C.c_char_p
+        _LIB.hbo_var.restype = C.c_double
+        _LIB.hbo_var.argtypes = [C.c_void_p, C.c_int]
+        _LIB.hbo_qnorm.restype = C.c_double
+        _LIB.hbo_qnorm.argtypes = [C.c_double]
+        _LIB.hbo_draw_gamma.restype = C.c_double
+        _LIB.hbo_draw_gamma.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double]
+        _LIB.hbo_draw_chisq.restype = C.c_double
+        _LIB.hbo_draw_chisq.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double]
+        _LIB.hbo_draw_uz.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _LIB.hbo_invgauss.restype = C.c_double
+        _LIB.hbo_invgauss.argtypes = [C.c_double] * 4
+        _LIB.hbo_time_sweep_fp64.restype = C.c_double
+        _LIB.hbo_time_sweep_fp64.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_double)]
+    return _LIB
+
+
+class Args(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("m", C.c_int), ("y", C.c_void_p), ("X", C.c_void_p), ("x_is_int8", C.c_int),
+        ("model", C.c_char_p), ("n_fold", C.c_int), ("Pi", C.c_void_p), ("fold", C.c_void_p),
+        ("nc", C.c_int), ("C", C.c_void_p), ("nr", C.c_int), ("Rlev", C.c_void_p), ("nlev", C.c_void_p),
+        ("niter", C.c_int), ("nburn", C.c_int), ("thin", C.c_int),
+        ("dfvr", C.c_double), ("s2vr", C.c_double), ("vg", C.c_double), ("dfvg", C.c_double),
+        ("s2vg", C.c_double), ("ve", C.c_double), ("dfve", C.c_double), ("s2ve", C.c_double),
+        ("windindx", C.c_void_p), ("seed", C.c_uint64),
+        ("ne", C.c_int), ("qe", C.c_int), ("epsl_y_J", C.c_void_p), ("epsl_index", C.c_void_p),
+        ("Gi_colptr", C.c_void_p), ("Gi_rowidx", C.c_void_p), ("Gi_val", C.c_void_p),
+    ]
+
+
+class Out(C.Structure):
+    _fields_ = [
+        ("Vg", C.c_double), ("Ve", C.c_double), ("h2", C.c_double), ("mu", C.c_double),
+        ("Veps", C.c_double), ("J", C.c_double),
+        ("beta", C.c_void_p), ("alpha", C.c_void_p), ("pi", C.c_void_p), ("pip", C.c_void_p),
+        ("gwas", C.c_void_p), ("g", C.c_void_p), ("e", C.c_void_p), ("vr", C.c_void_p),
+        ("estR", C.c_void_p), ("epsilon", C.c_void_p),
+        ("mu_store", C.c_void_p), ("vara_store", C.c_void_p), ("vare_store", C.c_void_p),
+        ("hsq_store", C.c_void_p), ("pi_store", C.c_void_p), ("alpha_store", C.c_void_p),
+        ("beta_store", C.c_void_p),
+        ("tracker_final", C.c_void_p), ("nzrate_count", C.c_void_p), ("wppa_count", C.c_void_p),
+        ("nnz_trace", C.c_void_p), ("vara_trace", C.c_void_p), ("vare_trace", C.c_void_p),
+        ("varg_trace", C.c_void_p),
+        ("n_records_done", C.c_int), ("nzct", C.c_int), ("iters_done", C.c_int),
+        ("seconds_sweep", C.c_double),
+    ]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _nan(v):
+    return float("nan") if v is None else float(v)
+
+
+def bayes(y, X, model, Pi, fold=None, C_=None, R=None, niter=200, nburn=100, thin=5,
+          dfvr=None, s2vr=None, vg=None, dfvg=None, s2vg=None, ve=None, dfve=None, s2ve=None,
+          windindx=None, seed=666666, epsl_y_J=None, epsl_Gi=None, epsl_index=None,
+          store_alpha=False):
+    """Oracle twin of hibayes' C++ Bayes() (Bayes.cpp:60-88 argument list).
+
+    X: (n, m) array, float64 or int8 (Fortran order is used internally).
+    R: (n, nr) integer level codes (0-based) for environmental random effects.
+    epsl_Gi: scipy.sparse matrix (qe x qe); epsl_index 1-based.
+    Returns a dict named like the reference's Rcpp::List plus diagnostics.
+    """
+    L = lib()
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    n = y.shape[0]
+    X = np.asarray(X)
+    if X.dtype == np.int8:
+        Xf = np.asfortranarray(X)
+        is8 = 1
+    else:
+        Xf = np.asfortranarray(X, dtype=np.float64)
+        is8 = 0
+    m = Xf.shape[1]
+    Pi = np.ascontiguousarray(Pi, dtype=np.float64)
+    F = Pi.shape[0]
+    fold_a = None if fold is None else np.ascontiguousarray(fold, dtype=np.float64)
+    a = Args()
+    a.n, a.m, a.y, a.X, a.x_is_int8 = n, m, _ptr(y), _ptr(Xf), is8
+    a.model = model.encode()
+    a.n_fold, a.Pi, a.fold = F, _ptr(Pi), _ptr(fold_a)
+    keep = [y, Xf, Pi, fold_a]
+    nc = 0
+    if C_ is not None:
+        Cf = np.asfortranarray(C_, dtype=np.float64)
+        nc = Cf.shape[1]
+        a.C = _ptr(Cf)
+        keep.append(Cf)
+    a.nc = nc
+    nr, n_levels = 0, 0
+    if R is not None:
+        Rf = np.asfortranarray(R, dtype=np.int32)
+        nr = Rf.shape[1]
+        nlev = np.ascontiguousarray(Rf.max(axis=0) + 1, dtype=np.int32)
+        n_levels = int(nlev.sum())
+        a.Rlev, a.nlev = _ptr(Rf), _ptr(nlev)
+        keep += [Rf, nlev]
+    a.nr = nr
+    a.niter, a.nburn, a.thin = niter, nburn, thin
+    a.dfvr, a.s2vr, a.vg, a.dfvg = _nan(dfvr), _nan(s2vr), _nan(vg), _nan(dfvg)
+    a.s2vg, a.ve, a.dfve, a.s2ve = _nan(s2vg), _nan(ve), _nan(dfve), _nan(s2ve)
+    nw = 0
+    if windindx is not None:
+        w = np.ascontiguousarray(windindx, dtype=np.int32)
+        nw = int(w.max())
+        a.windindx = _ptr(w)
+        keep.append(w)
+    a.seed = seed
+    ne = qe = 0
+    if epsl_index is not None:
+        import scipy.sparse as sp
+        ei = np.ascontiguousarray(epsl_index, dtype=np.int32)
+        G = sp.csc_matrix(epsl_Gi)
+        G.sort_indices()
+        cp = np.ascontiguousarray(G.indptr, dtype=np.int32)
+        ri = np.ascontiguousarray(G.indices, dtype=np.int32)
+        gv = np.ascontiguousarray(G.data, dtype=np.float64)
+        yj = np.ascontiguousarray(epsl_y_J, dtype=np.float64)
+        ne, qe = ei.shape[0], G.shape[0]
+        a.epsl_y_J, a.epsl_index, a.Gi_colptr, a.Gi_rowidx, a.Gi_val = _ptr(yj), _ptr(ei), _ptr(cp), _ptr(ri), _ptr(gv)
+        keep += [ei, cp, ri, gv, yj]
+    a.ne, a.qe = ne, qe
+    nrec = max((niter - nburn) // thin, 0)
+    o = Out()
+    res = {
+        "beta": np.zeros(nc), "alpha": np.zeros(m), "pi": np.zeros(F), "pip": np.zeros(m),
+        "gwas": np.zeros(nw), "g": np.zeros(n), "e": np.zeros(n), "Vr": np.zeros(nr),
+        "r": np.zeros(n_levels), "epsilon": np.zeros(qe),
+    }
+    mc = {
+        "mu": np.zeros(nrec), "Vg": np.zeros(nrec), "Ve": np.zeros(nrec), "h2": np.zeros(nrec),
+        "pi": np.zeros((F, nrec), order="F"), "beta": np.zeros((nc, nrec), order="F"),
+    }
+    if store_alpha:
+        mc["alpha"] = np.zeros((m, nrec), order="F")
+    dg = {
+        "tracker": np.zeros(m, dtype=np.int32), "nzrate_count": np.zeros(m), "wppa_count": np.zeros(nw),
+        "nnz_trace": np.zeros(niter, dtype=np.int32), "vara_trace": np.zeros(niter),
+        "vare_trace": np.zeros(niter), "varg_trace": np.zeros(niter),
+    }
+    o.beta, o.alpha, o.pi, o.pip = _ptr(res["beta"]), _ptr(res["alpha"]), _ptr(res["pi"]), _ptr(res["pip"])
+    o.gwas = _ptr(res["gwas"]) if nw else None
+    o.g, o.e, o.vr, o.estR, o.epsilon = _ptr(res["g"]), _ptr(res["e"]), _ptr(res["Vr"]), _ptr(res["r"]), _ptr(res["epsilon"])
+    o.mu_store, o.vara_store, o.vare_store, o.hsq_store = _ptr(mc["mu"]), _ptr(mc["Vg"]), _ptr(mc["Ve"]), _ptr(mc["h2"])
+    o.pi_store, o.beta_store = _ptr(mc["pi"]), _ptr(mc["beta"])
+    o.alpha_store = _ptr(mc["alpha"]) if store_alpha else None
+    o.tracker_final, o.nzrate_count = _ptr(dg["tracker"]), _ptr(dg["nzrate_count"])
+    o.wppa_count = _ptr(dg["wppa_count"]) if nw else None
+    o.nnz_trace, o.vara_trace, o.vare_trace, o.varg_trace = (_ptr(dg["nnz_trace"]), _ptr(dg["vara_trace"]),
+                                                             _ptr(dg["vare_trace"]), _ptr(dg["varg_trace"]))
+    rc = L.hbo_bayes(C.byref(a), C.byref(o))
+    if rc != 0:
+        raise RuntimeError(L.hbo_last_error().decode())
+    res.update({"Vg": o.Vg, "Ve": o.Ve, "h2": o.h2, "mu": o.mu, "Veps": o.Veps, "J": o.J})
+    res["MCMCsamples"] = mc
+    dg.update({"n_records": o.n_records_done, "nzct": o.nzct, "iters_done": o.iters_done,
+               "seconds_sweep": o.seconds_sweep})
+    res["diag"] = dg
+    return res
+
+
+def time_sweep_fp64(n, m_cpu, sweeps, threads, seed=1):
+    cs = C.c_double(0)
+    v = lib().hbo_time_sweep_fp64(n, m_cpu, sweeps, threads, seed, C.byref(cs))
+    return v, cs.value
