@@ -167,7 +167,7 @@ HB_HD double hb_qnorm(double p) {
     den = HB_H(den, r, 7.868691311456132591e-4);
     den = HB_H(den, r, 0.0148753612908506148525);
     den = HB_H(den, r, 0.13692988092273580531);
-    den = HB_H(den, r, 0.59983224201105211);
+    den = HB_H(den, r, 0.59983220655588793769);
     den = HB_H(den, r, 1.0);
     val = num / den;
   }
