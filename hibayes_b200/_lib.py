@@ -1,0 +1,125 @@
+"""ctypes binding of libhibayes_b200.so (the C ABI declared in include/hibayes_b200.h)."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+MAX_FOLD = 8
+
+# every symbol include/hibayes_b200.h declares
+SYMBOLS = [
+    "hb_last_error", "hb_device_count", "hb_engine_create", "hb_engine_destroy", "hb_engine_load_geno_i8",
+    "hb_engine_load_geno_f64", "hb_engine_synth_geno", "hb_synth_geno_host", "hb_engine_col_stats",
+    "hb_engine_set_snp_info", "hb_engine_build_gram", "hb_engine_set_residual", "hb_engine_get_residual",
+    "hb_engine_set_u", "hb_engine_get_u", "hb_engine_set_effects", "hb_engine_get_effects", "hb_engine_get_tracker",
+    "hb_engine_set_vargL", "hb_engine_sweep", "hb_engine_set_windows", "hb_engine_accumulate_pip",
+    "hb_engine_get_pip_counts", "hb_engine_accumulate_effects", "hb_engine_get_effect_sums", "hb_engine_predict",
+    "hb_engine_last_sweep_ms", "hb_engine_describe", "hb_bayes",
+]
+
+
+class EngineConfig(C.Structure):
+    _fields_ = [("device", C.c_int), ("n", C.c_int), ("m", C.c_int), ("tile_snps", C.c_int), ("lag_tiles", C.c_int),
+                ("n_slabs", C.c_int), ("seed", C.c_uint64), ("rank", C.c_int), ("world", C.c_int)]
+
+
+class SweepIn(C.Structure):
+    _fields_ = [("iter", C.c_int), ("model_index", C.c_int), ("n_fold", C.c_int),
+                ("fold", C.c_double * MAX_FOLD), ("logpi", C.c_double * MAX_FOLD), ("vara_fold", C.c_double * MAX_FOLD),
+                ("vare", C.c_double), ("dfvara", C.c_double), ("s2varg", C.c_double),
+                ("lambda_", C.c_double), ("lambda2", C.c_double), ("mu_shift", C.c_double), ("rnorm2_bound", C.c_double)]
+
+
+class SweepOut(C.Structure):
+    _fields_ = [("count", C.c_double * MAX_FOLD), ("varg_acc", C.c_double), ("sum_vargL", C.c_double),
+                ("sum_r", C.c_double), ("sum_r2", C.c_double), ("sum_u", C.c_double), ("var_u", C.c_double),
+                ("n_changed", C.c_int), ("status", C.c_int)]
+
+
+class BayesArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("m", C.c_int), ("y", C.c_void_p), ("X", C.c_void_p), ("x_type", C.c_int),
+        ("model", C.c_char_p), ("n_fold", C.c_int), ("Pi", C.c_void_p), ("fold", C.c_void_p),
+        ("nc", C.c_int), ("C", C.c_void_p), ("nr", C.c_int), ("Rlev", C.c_void_p), ("nlev", C.c_void_p),
+        ("niter", C.c_int), ("nburn", C.c_int), ("thin", C.c_int),
+        ("dfvr", C.c_double), ("s2vr", C.c_double), ("vg", C.c_double), ("dfvg", C.c_double),
+        ("s2vg", C.c_double), ("ve", C.c_double), ("dfve", C.c_double), ("s2ve", C.c_double),
+        ("windindx", C.c_void_p), ("outfreq", C.c_int), ("verbose", C.c_int), ("seed", C.c_uint64),
+        ("ne", C.c_int), ("qe", C.c_int), ("epsl_y_J", C.c_void_p), ("epsl_index", C.c_void_p),
+        ("Gi_colptr", C.c_void_p), ("Gi_rowidx", C.c_void_p), ("Gi_val", C.c_void_p),
+        ("device", C.c_int), ("tile_snps", C.c_int), ("lag_tiles", C.c_int), ("n_slabs", C.c_int),
+    ]
+
+
+class BayesOut(C.Structure):
+    _fields_ = [
+        ("Vg", C.c_double), ("Ve", C.c_double), ("h2", C.c_double), ("mu", C.c_double),
+        ("Veps", C.c_double), ("J", C.c_double),
+        ("beta", C.c_void_p), ("alpha", C.c_void_p), ("pi", C.c_void_p), ("pip", C.c_void_p),
+        ("gwas", C.c_void_p), ("g", C.c_void_p), ("e", C.c_void_p), ("vr", C.c_void_p),
+        ("estR", C.c_void_p), ("epsilon", C.c_void_p),
+        ("mu_store", C.c_void_p), ("vara_store", C.c_void_p), ("vare_store", C.c_void_p),
+        ("hsq_store", C.c_void_p), ("pi_store", C.c_void_p), ("alpha_store", C.c_void_p),
+        ("beta_store", C.c_void_p),
+        ("tracker_final", C.c_void_p), ("nzrate_count", C.c_void_p), ("wppa_count", C.c_void_p),
+        ("nnz_trace", C.c_void_p), ("vara_trace", C.c_void_p), ("vare_trace", C.c_void_p),
+        ("varg_trace", C.c_void_p),
+        ("n_records_done", C.c_int), ("nzct", C.c_int), ("iters_done", C.c_int),
+        ("seconds_sweep", C.c_double), ("seconds_setup", C.c_double),
+    ]
+
+
+def library_path():
+    return os.path.join(_HERE, "libhibayes_b200.so")
+
+
+def load_library():
+    """Loads libhibayes_b200.so; raises if it is missing (build with `python __graft_entry__.py`)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError("hibayes_b200: %s not built -- run `python __graft_entry__.py` (nvcc, sm_100a); "
+                           "there is no CPU fallback" % path)
+    L = C.CDLL(path)
+    L.hb_last_error.restype = C.c_char_p
+    for name in SYMBOLS:
+        getattr(L, name)  # raises AttributeError if the ABI is incomplete
+    L.hb_engine_create.argtypes = [C.POINTER(EngineConfig), C.POINTER(C.c_void_p)]
+    L.hb_engine_destroy.argtypes = [C.c_void_p]
+    L.hb_engine_destroy.restype = None
+    L.hb_engine_load_geno_i8.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.hb_engine_load_geno_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.hb_engine_synth_geno.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
+    L.hb_synth_geno_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int64]
+    L.hb_engine_col_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb_engine_set_snp_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb_engine_build_gram.argtypes = [C.c_void_p]
+    for f in ("set_residual", "get_residual", "set_u", "get_u", "set_effects", "get_effects", "get_tracker", "set_vargL",
+              "get_effect_sums", "set_windows"):
+        getattr(L, "hb_engine_" + f).argtypes = [C.c_void_p, C.c_void_p]
+    L.hb_engine_sweep.argtypes = [C.c_void_p, C.POINTER(SweepIn), C.POINTER(SweepOut)]
+    L.hb_engine_accumulate_pip.argtypes = [C.c_void_p]
+    L.hb_engine_accumulate_effects.argtypes = [C.c_void_p]
+    L.hb_engine_get_pip_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.hb_engine_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb_engine_last_sweep_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.hb_engine_describe.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                     C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.hb_bayes.argtypes = [C.POINTER(BayesArgs), C.POINTER(BayesOut)]
+    _LIB = L
+    return L
+
+
+def last_error():
+    return load_library().hb_last_error().decode()
+
+
+def device_count():
+    return load_library().hb_device_count()
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(last_error())

@@ -1,0 +1,258 @@
+"""Python mirror of the reference interface for the hot path, on top of the C ABI.
+
+`Bayes()` has the argument list of the reference's C++ `Bayes()` (/root/reference/src/Bayes.cpp:60-88,
+what R's ibrm() calls at R/bayes.r:294-296) and returns a dict named like its Rcpp::List
+(:919-1040).  `Engine` exposes the device engine (hb_engine_*) used by the host driver, the
+parity tests and bench.py.  Nothing here computes: every call goes to libhibayes_b200.so.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+
+MODEL_INDEX = {"BayesRR": 1, "BayesA": 2, "BayesB": 3, "BayesBpi": 3, "BayesC": 4, "BayesCpi": 4, "BSLMM": 4, "BayesL": 5}
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _nan(v):
+    return float("nan") if v is None else float(v)
+
+
+def synth_geno_host(n, m, seed, row_offset=0):
+    """The synthetic genotype matrix of hb_engine_synth_geno, generated on the host (int8, F order)."""
+    L = _lib.load_library()
+    X = np.empty((n, m), dtype=np.int8, order="F")
+    _lib.check(L.hb_synth_geno_host(X.ctypes.data, n, m, seed, row_offset))
+    return X
+
+
+def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, niter=50000, nburn=20000, thin=5,
+          epsl_y_J=None, epsl_Gi=None, epsl_index=None, dfvr=None, s2vr=None, vg=None, dfvg=None, s2vg=None,
+          ve=None, dfve=None, s2ve=None, windindx=None, outfreq=100, threads=0, verbose=False,
+          seed=666666, device=0, tile_snps=0, lag_tiles=0, n_slabs=0, store_alpha=False):
+    """GPU twin of hibayes' Bayes().  R: (n, nr) integer level codes (0-based) standing for the
+    CharacterMatrix of environmental random effects; seed: the Philox run key the Rcpp shim
+    derives from R's RNG state (the reference takes no seed argument, Bayes.cpp:60-88)."""
+    if Ki is not None or Kival is not None:
+        raise NotImplementedError("BSLMM polygenic term (Ki/Kival) is not part of this build")
+    L = _lib.load_library()
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    n = y.shape[0]
+    X = np.asarray(X)
+    if X.shape[0] != n:
+        raise RuntimeError("Number of individuals not equals.")  # Bayes.cpp:96
+    if X.dtype == np.int8:
+        Xf, xt = np.asfortranarray(X), 1
+    else:
+        Xf, xt = np.asfortranarray(X, dtype=np.float64), 0
+    m = Xf.shape[1]
+    Pi = np.ascontiguousarray(Pi, dtype=np.float64)
+    F = Pi.shape[0]
+    fold_a = None if fold is None else np.ascontiguousarray(fold, dtype=np.float64)
+    if fold_a is not None and fold_a.shape[0] != F:
+        raise RuntimeError("length of Pi and fold not equals.")  # :115-117
+    a = _lib.BayesArgs()
+    a.n, a.m, a.y, a.X, a.x_type = n, m, _ptr(y), _ptr(Xf), xt
+    a.model = model.encode()
+    a.n_fold, a.Pi, a.fold = F, _ptr(Pi), _ptr(fold_a)
+    keep = [y, Xf, Pi, fold_a]
+    nc = 0
+    if C_ is not None:
+        Cf = np.asfortranarray(C_, dtype=np.float64)
+        if Cf.shape[0] != n:
+            raise RuntimeError("Number of individuals does not match for covariates.")
+        nc = Cf.shape[1]
+        a.C = _ptr(Cf)
+        keep.append(Cf)
+    a.nc = nc
+    nr, n_levels = 0, 0
+    if R is not None:
+        Rf = np.asfortranarray(R, dtype=np.int32)
+        if Rf.shape[0] != n:
+            raise RuntimeError("Number of individuals does not match for environmental random effects.")
+        nr = Rf.shape[1]
+        nlev = np.ascontiguousarray(Rf.max(axis=0) + 1, dtype=np.int32)
+        n_levels = int(nlev.sum())
+        a.Rlev, a.nlev = _ptr(Rf), _ptr(nlev)
+        keep += [Rf, nlev]
+    a.nr = nr
+    a.niter, a.nburn, a.thin = niter, nburn, thin
+    a.dfvr, a.s2vr, a.vg, a.dfvg = _nan(dfvr), _nan(s2vr), _nan(vg), _nan(dfvg)
+    a.s2vg, a.ve, a.dfve, a.s2ve = _nan(s2vg), _nan(ve), _nan(dfve), _nan(s2ve)
+    nw = 0
+    if windindx is not None:
+        w = np.ascontiguousarray(windindx, dtype=np.int32)
+        nw = int(w.max())
+        a.windindx = _ptr(w)
+        keep.append(w)
+    a.outfreq, a.verbose, a.seed = outfreq, int(bool(verbose)), seed
+    ne = qe = 0
+    if epsl_index is not None:
+        import scipy.sparse as sp
+        ei = np.ascontiguousarray(epsl_index, dtype=np.int32)
+        G = sp.csc_matrix(epsl_Gi)
+        G.sort_indices()
+        cp = np.ascontiguousarray(G.indptr, dtype=np.int32)
+        ri = np.ascontiguousarray(G.indices, dtype=np.int32)
+        gv = np.ascontiguousarray(G.data, dtype=np.float64)
+        yj = np.ascontiguousarray(epsl_y_J, dtype=np.float64)
+        ne, qe = ei.shape[0], G.shape[0]
+        a.epsl_y_J, a.epsl_index, a.Gi_colptr, a.Gi_rowidx, a.Gi_val = _ptr(yj), _ptr(ei), _ptr(cp), _ptr(ri), _ptr(gv)
+        keep += [ei, cp, ri, gv, yj]
+    a.ne, a.qe = ne, qe
+    a.device, a.tile_snps, a.lag_tiles, a.n_slabs = device, tile_snps, lag_tiles, n_slabs
+    nrec = max((niter - nburn) // thin, 0)
+    o = _lib.BayesOut()
+    res = {
+        "beta": np.zeros(nc), "alpha": np.zeros(m), "pi": np.zeros(F), "pip": np.zeros(m),
+        "gwas": np.zeros(nw), "g": np.zeros(n), "e": np.zeros(n), "Vr": np.zeros(nr),
+        "r": np.zeros(n_levels), "epsilon": np.zeros(qe),
+    }
+    mc = {
+        "mu": np.zeros(nrec), "Vg": np.zeros(nrec), "Ve": np.zeros(nrec), "h2": np.zeros(nrec),
+        "pi": np.zeros((F, nrec), order="F"), "beta": np.zeros((nc, nrec), order="F"),
+    }
+    if store_alpha:
+        mc["alpha"] = np.zeros((m, nrec), order="F")
+    dg = {
+        "tracker": np.zeros(m, dtype=np.int32), "nzrate_count": np.zeros(m), "wppa_count": np.zeros(nw),
+        "nnz_trace": np.zeros(niter, dtype=np.int32), "vara_trace": np.zeros(niter),
+        "vare_trace": np.zeros(niter), "varg_trace": np.zeros(niter),
+    }
+    o.beta, o.alpha, o.pi, o.pip = _ptr(res["beta"]), _ptr(res["alpha"]), _ptr(res["pi"]), _ptr(res["pip"])
+    o.gwas = _ptr(res["gwas"]) if nw else None
+    o.g, o.e, o.vr, o.estR, o.epsilon = _ptr(res["g"]), _ptr(res["e"]), _ptr(res["Vr"]), _ptr(res["r"]), _ptr(res["epsilon"])
+    o.mu_store, o.vara_store, o.vare_store, o.hsq_store = _ptr(mc["mu"]), _ptr(mc["Vg"]), _ptr(mc["Ve"]), _ptr(mc["h2"])
+    o.pi_store, o.beta_store = _ptr(mc["pi"]), _ptr(mc["beta"])
+    o.alpha_store = _ptr(mc["alpha"]) if store_alpha else None
+    o.tracker_final, o.nzrate_count = _ptr(dg["tracker"]), _ptr(dg["nzrate_count"])
+    o.wppa_count = _ptr(dg["wppa_count"]) if nw else None
+    o.nnz_trace, o.vara_trace, o.vare_trace, o.varg_trace = (_ptr(dg["nnz_trace"]), _ptr(dg["vara_trace"]),
+                                                             _ptr(dg["vare_trace"]), _ptr(dg["varg_trace"]))
+    _lib.check(L.hb_bayes(C.byref(a), C.byref(o)))
+    res.update({"Vg": o.Vg, "Ve": o.Ve, "h2": o.h2, "mu": o.mu, "Veps": o.Veps, "J": o.J})
+    res["MCMCsamples"] = mc
+    dg.update({"n_records": o.n_records_done, "nzct": o.nzct, "iters_done": o.iters_done,
+               "seconds_sweep": o.seconds_sweep, "seconds_setup": o.seconds_setup})
+    res["diag"] = dg
+    return res
+
+
+class Engine:
+    """Thin handle on hb_engine_* (one per GPU)."""
+
+    def __init__(self, n, m, device=0, tile_snps=0, lag_tiles=0, n_slabs=0, seed=0, rank=0, world=1):
+        self.L = _lib.load_library()
+        cfg = _lib.EngineConfig(device, n, m, tile_snps, lag_tiles, n_slabs, seed, rank, world)
+        self.h = C.c_void_p()
+        _lib.check(self.L.hb_engine_create(C.byref(cfg), C.byref(self.h)))
+        self.n, self.m = n, m
+
+    def close(self):
+        if self.h:
+            self.L.hb_engine_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def describe(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        g, h = C.c_uint64(), C.c_uint64()
+        _lib.check(self.L.hb_engine_describe(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(g), C.byref(h)))
+        return {"n_slabs": a.value, "rows_per_slab": b.value, "tile_snps": c.value, "lag_tiles": d.value,
+                "geno_bytes": g.value, "gram_bytes": h.value}
+
+    def load_geno(self, X):
+        X = np.asarray(X)
+        if X.dtype == np.int8:
+            Xf = np.asfortranarray(X)
+            _lib.check(self.L.hb_engine_load_geno_i8(self.h, Xf.ctypes.data, Xf.shape[0]))
+        else:
+            Xf = np.asfortranarray(X, dtype=np.float64)
+            _lib.check(self.L.hb_engine_load_geno_f64(self.h, Xf.ctypes.data, Xf.shape[0]))
+
+    def synth_geno(self, seed, row_offset=0):
+        _lib.check(self.L.hb_engine_synth_geno(self.h, seed, row_offset))
+
+    def col_stats(self):
+        xpx, sumx = np.zeros(self.m), np.zeros(self.m)
+        _lib.check(self.L.hb_engine_col_stats(self.h, xpx.ctypes.data, sumx.ctypes.data))
+        return xpx, sumx
+
+    def set_snp_info(self, xpx, active):
+        xpx = np.ascontiguousarray(xpx, dtype=np.float64)
+        active = np.ascontiguousarray(active, dtype=np.uint8)
+        _lib.check(self.L.hb_engine_set_snp_info(self.h, xpx.ctypes.data, active.ctypes.data))
+
+    def build_gram(self):
+        _lib.check(self.L.hb_engine_build_gram(self.h))
+
+    def _set(self, name, arr, dtype=np.float64):
+        arr = np.ascontiguousarray(arr, dtype=dtype)
+        _lib.check(getattr(self.L, "hb_engine_" + name)(self.h, arr.ctypes.data))
+
+    def _get(self, name, count, dtype=np.float64):
+        out = np.zeros(count, dtype=dtype)
+        _lib.check(getattr(self.L, "hb_engine_" + name)(self.h, out.ctypes.data))
+        return out
+
+    def set_residual(self, r): self._set("set_residual", r)
+    def get_residual(self): return self._get("get_residual", self.n)
+    def set_u(self, u): self._set("set_u", u)
+    def get_u(self): return self._get("get_u", self.n)
+    def set_effects(self, g): self._set("set_effects", g)
+    def get_effects(self): return self._get("get_effects", self.m)
+    def get_tracker(self): return self._get("get_tracker", self.m, np.int32)
+    def set_vargL(self, v): self._set("set_vargL", v)
+    def get_effect_sums(self): return self._get("get_effect_sums", self.m)
+
+    def predict(self, alpha):
+        alpha = np.ascontiguousarray(alpha, dtype=np.float64)
+        out = np.zeros(self.n)
+        _lib.check(self.L.hb_engine_predict(self.h, alpha.ctypes.data, out.ctypes.data))
+        return out
+
+    def sweep(self, iter, model_index, vare, logpi, vara_fold, fold=None, dfvara=4.0, s2varg=0.0, lambda_=0.0, lambda2=0.0,
+              mu_shift=0.0, rnorm2_bound=1.0):
+        si = _lib.SweepIn()
+        F = len(logpi)
+        si.iter, si.model_index, si.n_fold = iter, model_index, F
+        for k in range(F):
+            si.logpi[k] = logpi[k]
+            si.vara_fold[k] = vara_fold[k]
+            si.fold[k] = 0.0 if fold is None else fold[k]
+        si.vare, si.dfvara, si.s2varg, si.lambda_, si.lambda2 = vare, dfvara, s2varg, lambda_, lambda2
+        si.mu_shift, si.rnorm2_bound = mu_shift, rnorm2_bound
+        so = _lib.SweepOut()
+        _lib.check(self.L.hb_engine_sweep(self.h, C.byref(si), C.byref(so)))
+        return {"count": list(so.count), "varg_acc": so.varg_acc, "sum_vargL": so.sum_vargL, "sum_r": so.sum_r,
+                "sum_r2": so.sum_r2, "sum_u": so.sum_u, "var_u": so.var_u, "n_changed": so.n_changed, "status": so.status}
+
+    def last_sweep_ms(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        _lib.check(self.L.hb_engine_last_sweep_ms(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def set_windows(self, windindx):
+        if windindx is None:
+            _lib.check(self.L.hb_engine_set_windows(self.h, None))
+        else:
+            self._set("set_windows", windindx, np.int32)
+
+    def accumulate_pip(self): _lib.check(self.L.hb_engine_accumulate_pip(self.h))
+    def accumulate_effects(self): _lib.check(self.L.hb_engine_accumulate_effects(self.h))
+
+    def get_pip_counts(self, nw=0):
+        nz = np.zeros(self.m)
+        wp = np.zeros(nw)
+        _lib.check(self.L.hb_engine_get_pip_counts(self.h, nz.ctypes.data, wp.ctypes.data if nw else None, nw))
+        return nz, wp

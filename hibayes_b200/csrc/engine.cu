@@ -1,0 +1,1305 @@
+// engine.cu -- B200 (sm_100a) device engine for the hibayes single-site Gibbs sweep.
+//
+// Replaces the switch(model_index) block of Bayes() (/root/reference/src/Bayes.cpp:586-816)
+// and the per-iteration reductions (:480,:819,:823) behind the C ABI of
+// include/hibayes_b200.h.  See DESIGN.md for the algorithm; in short:
+//
+//   * X is held once in HBM as raw int8, tile-major  Xp[slab][tile][snp-in-tile][row-in-slab];
+//     every streaming CTA owns one row slab and reads its part of X exactly once per sweep
+//     through a TMA (cp.async.bulk) ring in shared memory.
+//   * per tile of B SNPs each streaming CTA computes the B partial dots x_j'r over its slab
+//     (PRMT + DFMA per genotype, the residual slab lives in registers) and adds them, as
+//     fixed-point int64, to per-SNP accumulators in L2 -> the sum is order-independent.
+//   * one scalar CTA runs the sequential Gibbs chain: it turns the dots of tile t into
+//     conditional draws, resolving the dependence between SNPs with the precomputed exact
+//     Gram band  G = X_t'[X_t .. X_{t+D-1}]  (speculate all, commit up to the first changed
+//     SNP, patch the later right-hand sides, repeat) and publishes the changed effects.
+//   * streaming CTAs apply those residual updates (r -= x_j*delta, u += x_j*delta) D tiles
+//     later, so D tiles are in flight and the chain latency is hidden behind streaming.
+//
+// All random draws are position-addressed (hb_rng.h), so the result does not depend on the
+// decomposition.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/hibayes_b200.h"
+#include "hb_device.cuh"
+#include "hb_rng.h"
+#include "hb_synth.h"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+extern "C" const char* hb_last_error(void) { return g_err; }
+int hb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CU(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return hb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                          cudaGetErrorString(_e));                                           \
+  } while (0)
+
+extern "C" int hb_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) return -1;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------
+// engine state
+// ------------------------------------------------------------------------------------------
+struct SweepOutDev {
+  double count[HB_MAX_FOLD];
+  double varg_acc;
+  double sum_vargL;
+  double sum_r, sum_r2, sum_u, var_u;
+  int n_changed;
+  int status;
+};
+
+struct hb_engine {
+  hb_engine_config cfg;
+  int n, m, B, D, S, R, NRG, CL, T, m_pad, NS, nsm;
+  int NTC, NTCp, block_threads;
+  size_t Npad, slab_stride, stage_bytes, smem_bytes;
+  size_t off_part, off_u, off_bar;
+  uint8_t* Xp = nullptr;
+  double *r = nullptr, *u = nullptr, *xpx = nullptr, *g = nullptr, *vargL = nullptr, *gsum = nullptr;
+  double *nzrate = nullptr, *wppa = nullptr;
+  uint8_t* active = nullptr;
+  int32_t* tracker = nullptr;
+  int32_t* gram = nullptr;
+  bool gram_ready = false, info_ready = false, geno_ready = false;
+  unsigned long long* dacc = nullptr;
+  unsigned int* arrive = nullptr;
+  int* q_snp = nullptr;
+  double* q_delta = nullptr;
+  int* tile_qend = nullptr;
+  int* ctrl = nullptr;  // [0] progress, [1] abort
+  double* prm = nullptr;  // per-SNP sweep parameters, SoA
+  int prm_fold = 0;
+  SweepOutDev* out_dev = nullptr;
+  // windows (CSR)
+  int nw = 0;
+  int *wstart = nullptr, *wmem = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float ms_prep = 0, ms_sweep = 0, ms_tail = 0;
+};
+
+static const double kScaleUp = 2.6815615859885194e154;   // 2^513
+static const double kScaleDn = 2.6815615859885194e154;   // partial = acc * 2^(1026-513)
+
+// ------------------------------------------------------------------------------------------
+// packing, synthetic data, column statistics
+// ------------------------------------------------------------------------------------------
+// One thread per 16-row chunk of one column: gathers 16 int8 genotypes (0 beyond n) and stores
+// them as one 16-byte vector at Xp[slab][tile][col][16*rg ..].
+__global__ void k_pack_i8(const int8_t* __restrict__ src, size_t ld, int n, int col0, int ncols, uint8_t* __restrict__ Xp,
+                          int S, int R, int NRG, int T, int B) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t per_col = (size_t)S * NRG;
+  if (idx >= per_col * ncols) return;
+  int c = (int)(idx / per_col);
+  int ch = (int)(idx % per_col);
+  int s = ch / NRG, rg = ch % NRG;
+  size_t row0 = (size_t)s * R + 16 * rg;
+  const int8_t* col = src + (size_t)c * ld;
+  uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    size_t row = row0 + i;
+    uint32_t x = (row < (size_t)n) ? (uint32_t)(uint8_t)col[row] : 0u;
+    w[i >> 2] |= x << (8 * (i & 3));
+  }
+  int j = col0 + c, t = j / B, cj = j % B;
+  uint4* dst = (uint4*)(Xp + ((((size_t)s * T + t) * B + cj) * R + 16 * rg));
+  *dst = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void k_synth(uint8_t* __restrict__ Xp, int n, int m, int S, int R, int NRG, int T, int B, hb_key_t key,
+                        long long row_offset) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t per_col = (size_t)S * NRG;
+  if (idx >= per_col * (size_t)m) return;
+  int j = (int)(idx / per_col);
+  int ch = (int)(idx % per_col);
+  int s = ch / NRG, rg = ch % NRG;
+  size_t row0 = (size_t)s * R + 16 * rg;
+  double t0, t1;
+  hb_synth_thresholds(key, (uint32_t)j, &t0, &t1);
+  uint32_t w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    size_t lrow = row0 + 4 * k;
+    uint32_t word = 0;
+    if (lrow < (size_t)n) {
+      word = hb_synth_word(key, (uint32_t)j, (uint64_t)(row_offset + (long long)lrow) >> 2, t0, t1);
+      // mask rows beyond n inside the last word
+      for (int b = 0; b < 4; ++b)
+        if (lrow + b >= (size_t)n) word &= ~(0xffu << (8 * b));
+    }
+    w[k] = word;
+  }
+  int t = j / B, cj = j % B;
+  uint4* dst = (uint4*)(Xp + ((((size_t)s * T + t) * B + cj) * R + 16 * rg));
+  *dst = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Column sums: one warp per column; exact integer sums of x and x^2 (Bayes.cpp:310-315).
+__global__ void k_col_stats(const uint8_t* __restrict__ Xp, int m, int S, int R, int NRG, int T, int B,
+                            double* __restrict__ xpx, double* __restrict__ sumx) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= m) return;
+  int j = warp, t = j / B, cj = j % B;
+  long long s1 = 0, s2 = 0;
+  int chunks = S * NRG;
+  for (int ch = lane; ch < chunks; ch += 32) {
+    int s = ch / NRG, rg = ch % NRG;
+    uint4 v = *(const uint4*)(Xp + ((((size_t)s * T + t) * B + cj) * R + 16 * rg));
+    unsigned a = 0, b = 0;
+    a = __dp4a(v.x, 0x01010101u, a); b = __dp4a(v.x, v.x, b);
+    a = __dp4a(v.y, 0x01010101u, a); b = __dp4a(v.y, v.y, b);
+    a = __dp4a(v.z, 0x01010101u, a); b = __dp4a(v.z, v.z, b);
+    a = __dp4a(v.w, 0x01010101u, a); b = __dp4a(v.w, v.w, b);
+    s1 += a; s2 += b;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) { sumx[j] = (double)s1; xpx[j] = (double)s2; }
+}
+
+// ------------------------------------------------------------------------------------------
+// band Gram:  G[t][dt][a][b] = x_{tB+a}' x_{(t+dt)B+b}   (exact int32)
+// v1: dp4a, 64x64 output block per CTA, rows staged 128 at a time.
+// ------------------------------------------------------------------------------------------
+constexpr int GK = 128;  // rows per staging step
+__global__ void __launch_bounds__(256) k_gram_dp4a(const uint8_t* __restrict__ Xp, int32_t* __restrict__ gram, int S, int R,
+                                                   int T, int B, int D, int t_base) {
+  __shared__ uint32_t As[64][GK / 4 + 1];
+  __shared__ uint32_t Bs[64][GK / 4 + 1];
+  const int t = t_base + blockIdx.z;
+  const int nb = B / 64;
+  const int a0 = (blockIdx.y % nb) * 64;
+  const int dt = blockIdx.x / nb, b0 = (blockIdx.x % nb) * 64;
+  const int t2 = t + dt;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  unsigned acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[i][k] = 0u;
+  if (t2 < T) {
+    for (int s = 0; s < S; ++s) {
+      const uint8_t* Abase = Xp + (((size_t)s * T + t) * B + a0) * R;
+      const uint8_t* Bbase = Xp + (((size_t)s * T + t2) * B + b0) * R;
+      for (int r0 = 0; r0 < R; r0 += GK) {
+        const int nwords = min(GK, R - r0) / 4;  // R is a multiple of 16
+        for (int e = tid; e < 64 * (GK / 4); e += 256) {
+          int c = e / (GK / 4), w = e % (GK / 4);
+          uint32_t va = 0, vb = 0;
+          if (w < nwords) {
+            va = *(const uint32_t*)(Abase + (size_t)c * R + r0 + 4 * w);
+            vb = *(const uint32_t*)(Bbase + (size_t)c * R + r0 + 4 * w);
+          }
+          As[c][w] = va;
+          Bs[c][w] = vb;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int w = 0; w < GK / 4; ++w) {
+          uint32_t av[4], bv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) av[i] = As[ty * 4 + i][w];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) bv[k] = Bs[tx + 16 * k][w];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[i][k] = __dp4a(av[i], bv[k], acc[i][k]);
+        }
+        __syncthreads();
+      }
+    }
+  }
+  int32_t* out = gram + (((size_t)t * D + dt) * B) * B;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[(size_t)(a0 + ty * 4 + i) * B + (b0 + tx + 16 * k)] = (int32_t)acc[i][k];
+}
+
+// ------------------------------------------------------------------------------------------
+// per-sweep preparation: everything about SNP j that does not depend on the residual
+// ------------------------------------------------------------------------------------------
+struct PrepParams {
+  int m, m_pad, T, iter, model, F;
+  double fold[HB_MAX_FOLD], logpi[HB_MAX_FOLD], vara_fold[HB_MAX_FOLD];
+  double vare, dfvara, s2varg;
+  hb_key_t key;
+};
+// prm layout (SoA over m_pad): [0] u, [1] z, then for k = 1..F-1: a_k, c_k, v_k, sd_k
+__device__ __forceinline__ size_t prm_idx(int field, size_t m_pad, int j) { return (size_t)field * m_pad + j; }
+
+__global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8_t* __restrict__ active,
+                       const double* __restrict__ g, const double* __restrict__ vargL, double* __restrict__ prm,
+                       unsigned long long* __restrict__ dacc, unsigned int* __restrict__ arrive, int* __restrict__ ctrl,
+                       SweepOutDev* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) {
+    ctrl[0] = 0; ctrl[1] = 0;
+    out->n_changed = 0; out->status = 0; out->varg_acc = 0; out->sum_vargL = 0;
+    for (int k = 0; k < HB_MAX_FOLD; ++k) out->count[k] = 0;
+  }
+  if (j < p.T) arrive[j] = 0;
+  if (j >= p.m_pad) return;
+  dacc[j] = 0ull;
+  if (j >= p.m || !active[j]) return;
+  const double xx = xpx[j];
+  double u, z;
+  hb_draw_uz(p.key, HB_DOM_SNP, (uint32_t)p.iter, (uint32_t)j, HB_SL_MAIN, 0, &u, &z);
+  prm[prm_idx(0, p.m_pad, j)] = u;
+  prm[prm_idx(1, p.m_pad, j)] = z;
+  const double vare = p.vare;
+  if (p.model == HB_MODEL_R) {
+    for (int k = 1; k < p.F; ++k) {
+      double vf = p.vara_fold[k];
+      double v = xx + vare / vf;
+      int f = 2 + 4 * (k - 1);
+      prm[prm_idx(f + 0, p.m_pad, j)] = -0.5 * log(vf * (xx / vare) + 1.0) + p.logpi[k];
+      prm[prm_idx(f + 1, p.m_pad, j)] = 0.5 / (vare * v);
+      prm[prm_idx(f + 2, p.m_pad, j)] = v;
+      prm[prm_idx(f + 3, p.m_pad, j)] = sqrt(vare / v);
+    }
+  } else {
+    double varg = p.vara_fold[1];
+    if (p.model == HB_MODEL_A || p.model == HB_MODEL_B) {
+      double og = g[j];
+      varg = (og * og + p.s2varg * p.dfvara) /
+             hb_draw_chisq(p.key, HB_DOM_SNP, (uint32_t)p.iter, (uint32_t)j, HB_SL_CHI, p.dfvara + 1.0);
+    }
+    double v = (p.model == HB_MODEL_L) ? (xx + 1.0 / vargL[j]) : (xx + vare / varg);
+    double a = 0.0;
+    if (p.model == HB_MODEL_B || p.model == HB_MODEL_C) a = -0.5 * log(varg * (xx / vare) + 1.0) + p.logpi[1];
+    prm[prm_idx(2, p.m_pad, j)] = a;
+    prm[prm_idx(3, p.m_pad, j)] = 0.5 / (vare * v);
+    prm[prm_idx(4, p.m_pad, j)] = v;
+    prm[prm_idx(5, p.m_pad, j)] = sqrt(vare / v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// the sweep kernel
+// ------------------------------------------------------------------------------------------
+struct SweepParams {
+  const uint8_t* Xp;
+  double *r, *u;
+  const double* xpx;
+  const uint8_t* active;
+  double* g;
+  int32_t* tracker;
+  const int32_t* gram;
+  unsigned long long* dacc;
+  unsigned int* arrive;
+  int* q_snp;
+  double* q_delta;
+  int* tile_qend;
+  int* ctrl;
+  const double* prm;
+  SweepOutDev* out;
+  size_t slab_stride, m_pad;
+  int n, m, S, R, NRG, CL, T, B, D, NS, NTC, NTCp;
+  uint32_t stage_bytes, off_part, off_u, off_bar;
+  int model, F;
+  double fold[HB_MAX_FOLD];
+  double logpi0;
+  double dscale, inv_dscale, mu_shift;
+  unsigned arrive_target;
+};
+
+enum { HB_ABORT_TIMEOUT_STREAM = 1, HB_ABORT_TIMEOUT_SCALAR = 2, HB_ABORT_TIMEOUT_TMA = 3, HB_ABORT_OVERFLOW = 4 };
+
+__device__ __forceinline__ bool spin_backoff(long long& spins, int* ctrl, int code) {
+  // returns false when the wait must be abandoned
+  ++spins;
+  if ((spins & 0x3f) == 0) {
+    __nanosleep(64);
+    if ((spins & 0xfff) == 0) {
+      if (*((volatile int*)(ctrl + 1)) != 0) return false;
+      if (spins > hb::kSpinLimit) {
+        atomicCAS(ctrl + 1, 0, code);
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
+__device__ __forceinline__ double byte_as_scaled(uint32_t w, uint32_t sel) {
+  // genotype byte -> mantissa bits 48..55 of a double: value = byte * 2^-1026 (exact, denormal)
+  return __hiloint2double((int)__byte_perm(w, 0u, sel), 0);
+}
+
+__device__ void stream_role(const SweepParams& p, uint8_t* smem) {
+  const int tid = threadIdx.x;
+  const int s = blockIdx.x;
+  const int NS = p.NS, B = p.B, D = p.D, T = p.T, NRG = p.NRG, NTC = p.NTC, NTCp = p.NTCp, R = p.R;
+  uint8_t* stage0 = smem;
+  double* part = (double*)(smem + p.off_part);
+  double* us = (double*)(smem + p.off_u);
+  uint64_t* full = (uint64_t*)(smem + p.off_bar);
+  uint64_t* empty = full + NS;
+  volatile int* ready_tile = (volatile int*)(empty + NS);
+  volatile int* qend_ring = ready_tile + 1;
+  int* ctrl = p.ctrl;
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { hb::mbar_init(full + i, 1); hb::mbar_init(empty + i, 1); }
+    *ready_tile = -1;
+    hb::mbar_fence_init();
+  }
+  __syncthreads();
+  const uint8_t* Xs = p.Xp + (size_t)s * p.slab_stride;
+
+  // ---------------- poller warp: turns the scalar CTA's progress into a shared-memory flag
+  if (tid >= NTCp + 32) {
+    if (tid == NTCp + 32) {
+      long long spins = 0;
+      for (int t = 0; t < T + D; ++t) {
+        int qend = 0;
+        if (t >= D) {
+          const int need = t - D + 1;
+          while (hb::ld_acquire(ctrl) < need)
+            if (!spin_backoff(spins, ctrl, HB_ABORT_TIMEOUT_STREAM)) { *ready_tile = 1 << 30; return; }
+          qend = __ldcg(p.tile_qend + (t - D));
+        }
+        // do not run more than 8 tiles ahead of the compute threads' ring slot reuse:
+        // (t <= progress + D - 1 <= compute tile + D, ring has 16 slots, D <= 8)
+        qend_ring[t & 15] = qend;
+        __threadfence_block();
+        *ready_tile = t;
+      }
+    }
+    return;
+  }
+  // ---------------- producer warp: streams this slab's tiles through the TMA ring
+  if (tid >= NTCp) {
+    if (tid == NTCp) {
+      long long spins = 0;
+      for (int t = 0; t < T; ++t) {
+        const int st = t % NS;
+        if (t >= NS) {
+          const uint32_t par = (uint32_t)((t / NS - 1) & 1);
+          while (!hb::mbar_try_wait(empty + st, par))
+            if (!spin_backoff(spins, ctrl, HB_ABORT_TIMEOUT_TMA)) return;
+        }
+        hb::mbar_arrive_expect_tx(full + st, p.stage_bytes);
+        hb::tma_load_1d(stage0 + (size_t)st * p.stage_bytes, Xs + (size_t)t * p.stage_bytes, p.stage_bytes, full + st);
+      }
+    }
+    return;
+  }
+  // ---------------- compute threads
+  const bool live = tid < NTC;
+  const int rg = live ? (tid % NRG) : 0;
+  const int cl = live ? (tid / NRG) : 0;
+  const size_t row0 = (size_t)s * R + 16 * rg;
+  double rs[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    double v = 0.0;
+    if (live && row0 + i < (size_t)p.n) v = p.r[row0 + i] + p.mu_shift;
+    rs[i] = v * kScaleUp;
+  }
+  for (int i = tid; i < R; i += NTCp) us[i] = p.u[(size_t)s * R + i];
+  const int kmax = B / p.CL;
+  const int npub = min(B, NTCp);
+  int applied = 0;
+  long long spins = 0;
+  bool dead = false;
+
+  for (int t = 0; t < T + D; ++t) {
+    // 1. residual updates published by the scalar CTA for tiles <= t-D
+    if (t >= D && !dead) {
+      while (hb::ld_volatile_shared(ready_tile) < t)
+        if (!spin_backoff(spins, ctrl, HB_ABORT_TIMEOUT_STREAM)) { dead = true; break; }
+      if (*ready_tile == (1 << 30)) dead = true;
+    }
+    if (t >= D && !dead) {
+      const int qend = qend_ring[t & 15];
+      for (int q = applied; q < qend; q += 4) {
+        int js[4];
+        double dl[4];
+        uint4 xv[4];
+        const int nq = min(4, qend - q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (e < nq) {
+            js[e] = __ldcg(p.q_snp + q + e);
+            dl[e] = __ldcg(p.q_delta + q + e);
+          }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (e < nq && live) {
+            const int tj = js[e] / B, cj = js[e] % B;
+            xv[e] = __ldg((const uint4*)(Xs + ((size_t)tj * B + cj) * R + 16 * rg));
+          }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (e < nq && live) {
+            const uint32_t w[4] = {xv[e].x, xv[e].y, xv[e].z, xv[e].w};
+            const double dls = dl[e] * kScaleUp;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const double xd = (double)((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
+              rs[i] = fma(-xd, dls, rs[i]);                       // yadj -= x * delta  (Bayes.cpp:787)
+              if (cl == 0) us[16 * rg + i] = fma(xd, dl[e], us[16 * rg + i]);  // u += x * delta (:789)
+            }
+          }
+      }
+      applied = qend;
+    }
+    if (t >= T) {
+      if (hb::named_bar_or(1, NTCp, dead)) { dead = true; break; }
+      continue;
+    }
+    // 2. wait for the tile in the TMA ring
+    const int st = t % NS;
+    if (!dead) {
+      const uint32_t par = (uint32_t)((t / NS) & 1);
+      while (!hb::mbar_try_wait(full + st, par))
+        if (!spin_backoff(spins, ctrl, HB_ABORT_TIMEOUT_TMA)) { dead = true; break; }
+    }
+    // 3. partial dots of this slab: thread (rg, cl) handles rows 16rg..16rg+15 of columns cl, cl+CL, ...
+    double* pt = part + (size_t)(t & 1) * B * NRG;
+    if (live && !dead) {
+      const uint4* sp = (const uint4*)(stage0 + (size_t)st * p.stage_bytes);
+      for (int k = 0; k < kmax; ++k) {
+        const uint4 v = sp[tid + NTC * k];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        a0 = fma(rs[0], byte_as_scaled(v.x, 0x4044), a0);
+        a1 = fma(rs[1], byte_as_scaled(v.x, 0x4144), a1);
+        a2 = fma(rs[2], byte_as_scaled(v.x, 0x4244), a2);
+        a3 = fma(rs[3], byte_as_scaled(v.x, 0x4344), a3);
+        a0 = fma(rs[4], byte_as_scaled(v.y, 0x4044), a0);
+        a1 = fma(rs[5], byte_as_scaled(v.y, 0x4144), a1);
+        a2 = fma(rs[6], byte_as_scaled(v.y, 0x4244), a2);
+        a3 = fma(rs[7], byte_as_scaled(v.y, 0x4344), a3);
+        a0 = fma(rs[8], byte_as_scaled(v.z, 0x4044), a0);
+        a1 = fma(rs[9], byte_as_scaled(v.z, 0x4144), a1);
+        a2 = fma(rs[10], byte_as_scaled(v.z, 0x4244), a2);
+        a3 = fma(rs[11], byte_as_scaled(v.z, 0x4344), a3);
+        a0 = fma(rs[12], byte_as_scaled(v.w, 0x4044), a0);
+        a1 = fma(rs[13], byte_as_scaled(v.w, 0x4144), a1);
+        a2 = fma(rs[14], byte_as_scaled(v.w, 0x4244), a2);
+        a3 = fma(rs[15], byte_as_scaled(v.w, 0x4344), a3);
+        pt[tid + NTC * k] = ((a0 + a1) + (a2 + a3)) * kScaleDn;
+      }
+    }
+    // 4. all compute threads are done with the stage and have written their partials; the
+    //    barrier also votes on `dead` so that an abort is taken by the whole CTA at once
+    if (hb::named_bar_or(1, NTCp, dead)) { dead = true; break; }
+    if (tid == 0) hb::mbar_arrive(empty + st);
+    // 5. fixed-order sum over row groups, then fixed-point accumulation in L2
+    if (tid < npub) {
+      for (int j = tid; j < B; j += NTCp) {
+        const double* pj = pt + (size_t)j * NRG;
+        double sum = 0.0;
+        for (int q = 0; q < NRG; ++q) sum += pj[q];
+        const double scaled = sum * p.dscale;
+        if (!(fabs(scaled) < 4.0e18)) atomicCAS(ctrl + 1, 0, HB_ABORT_OVERFLOW);
+        const long long fx = __double2ll_rn(scaled);
+        atomicAdd(p.dacc + (size_t)t * B + j, (unsigned long long)fx);
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) {
+        __threadfence();
+        atomicAdd(p.arrive + t, 1u);
+      }
+    }
+  }
+  // write the slab back
+  if (!dead) {
+    hb::named_bar_sync(1, NTCp);
+    if (live && cl == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) p.r[row0 + i] = rs[i] * (1.0 / kScaleUp);
+    }
+    for (int i = tid; i < R; i += NTCp) p.u[(size_t)s * R + i] = us[i];
+  }
+}
+
+// Conditional draw of one SNP given its right-hand side (Bayes.cpp:592-601, 639-664, 756-801).
+__device__ __forceinline__ void eval_snp(int model, int F, double rhs, const double* a, const double* c, const double* v,
+                                         const double* sd, double logpi0, double u, double z, int& cls, double& gnew) {
+  if (model == HB_MODEL_RR || model == HB_MODEL_A || model == HB_MODEL_L) {
+    cls = 1;
+    gnew = rhs / v[0] + sd[0] * z;
+    if (model == HB_MODEL_L && fabs(gnew) < 1e-6) gnew = 1e-6;  // :728
+    return;
+  }
+  double sv[HB_MAX_FOLD];
+  const double rr = rhs * rhs;
+  sv[0] = logpi0;
+  double smax = logpi0;
+#pragma unroll
+  for (int k = 1; k < HB_MAX_FOLD; ++k)
+    if (k < F) {
+      sv[k] = fma(rr, c[k - 1], a[k - 1]);
+      smax = fmax(smax, sv[k]);
+    }
+  double tot = 0.0;
+#pragma unroll
+  for (int k = 0; k < HB_MAX_FOLD; ++k)
+    if (k < F) {
+      sv[k] = exp(sv[k] - smax);
+      tot += sv[k];
+    }
+  const double inv = 1.0 / tot;
+  double acc = 0.0;
+  cls = 0;
+  bool found = false;
+#pragma unroll
+  for (int k = 0; k < HB_MAX_FOLD; ++k)
+    if (k < F && !found) {
+      acc += sv[k] * inv;
+      if (u < acc) { cls = k; found = true; }
+    }
+  gnew = 0.0;
+#pragma unroll
+  for (int k = 1; k < HB_MAX_FOLD; ++k)
+    if (k == cls) gnew = rhs / v[k - 1] + sd[k - 1] * z;
+}
+
+__device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
+  const int B = p.B, D = p.D, T = p.T, F = p.F, model = p.model;
+  const int i = threadIdx.x;
+  if (i >= B) return;
+  const int nwarp = B / 32, warp = i >> 5, lane = i & 31;
+  double* ring = (double*)smem;                         // D * B
+  double* chg_delta = ring + (size_t)D * B;             // B
+  double* cand_delta = chg_delta + B;                   // 2 * nwarp
+  double* red = cand_delta + 2 * 8;                     // B * (HB_MAX_FOLD + 1)
+  int* chg_a = (int*)(red + (size_t)B * (HB_MAX_FOLD + 1));  // B
+  int* cand_idx = chg_a + B;                            // 2 * nwarp
+  volatile int* s_abort = cand_idx + 16;
+  int* ctrl = p.ctrl;
+  for (int d = 0; d < D; ++d) ring[(size_t)d * B + i] = 0.0;
+  double cnt[HB_MAX_FOLD];
+#pragma unroll
+  for (int k = 0; k < HB_MAX_FOLD; ++k) cnt[k] = 0.0;
+  double vacc = 0.0;
+  int qbase = 0;
+  long long spins = 0;
+  const size_t mp = p.m_pad;
+  const bool mixture = (model == HB_MODEL_B || model == HB_MODEL_C || model == HB_MODEL_R);
+  const int nf = mixture ? (model == HB_MODEL_R ? F : 2) : 2;
+  bool dead = false;
+
+  for (int t = 0; t < T && !dead; ++t) {
+    const int j = t * B + i;
+    // per-SNP inputs that do not depend on the dots: fetch before waiting
+    const bool act = (j < p.m) && p.active[j];
+    double xx = 0, gold = 0, u = 0.5, z = 0;
+    double pa[HB_MAX_FOLD - 1], pc[HB_MAX_FOLD - 1], pv[HB_MAX_FOLD - 1], psd[HB_MAX_FOLD - 1];
+#pragma unroll
+    for (int k = 0; k < HB_MAX_FOLD - 1; ++k) { pa[k] = 0; pc[k] = 0; pv[k] = 1; psd[k] = 0; }
+    if (act) {
+      xx = p.xpx[j];
+      gold = p.g[j];
+      u = p.prm[prm_idx(0, mp, j)];
+      z = p.prm[prm_idx(1, mp, j)];
+#pragma unroll
+      for (int k = 0; k < HB_MAX_FOLD - 1; ++k)
+        if (k < nf - 1) {
+          pa[k] = p.prm[prm_idx(2 + 4 * k, mp, j)];
+          pc[k] = p.prm[prm_idx(3 + 4 * k, mp, j)];
+          pv[k] = p.prm[prm_idx(4 + 4 * k, mp, j)];
+          psd[k] = p.prm[prm_idx(5 + 4 * k, mp, j)];
+        }
+    }
+    // wait until every streaming CTA has added its partial dots of tile t
+    if (i == 0) {
+      bool ok = true;
+      while (hb::ld_acquire_u(p.arrive + t) < p.arrive_target)
+        if (!spin_backoff(spins, ctrl, HB_ABORT_TIMEOUT_SCALAR)) { ok = false; break; }
+      *s_abort = (!ok || *((volatile int*)(ctrl + 1)) != 0) ? 1 : 0;
+    }
+    hb::named_bar_sync(2, B);
+    if (*s_abort) { dead = true; break; }
+    const long long fx = (long long)__ldcg(p.dacc + j);
+    double d = (double)fx * p.inv_dscale;
+    const int slot = t % D;
+    d -= ring[(size_t)slot * B + i];
+    ring[(size_t)slot * B + i] = 0.0;
+    // rhs = x_j' yadj (+ xpx_j g_j)    (Bayes.cpp:593-594, 756-757)
+    double rhs = d + ((gold != 0.0) ? xx * gold : 0.0);
+
+    int pos = 0, nchg = 0, round = 0;
+    int cls = 0;
+    double gnew = gold;
+    bool done = !act;     // inactive SNPs are skipped (:589)
+    if (!act) { cls = 0; gnew = gold; }
+    for (;;) {
+      bool changed = false;
+      if (!done) {
+        eval_snp(model, nf, rhs, pa, pc, pv, psd, p.logpi0, u, z, cls, gnew);
+        changed = (gnew != gold);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, changed);
+      int* ci = cand_idx + (round & 1) * 8;
+      double* cd = cand_delta + (round & 1) * 8;
+      if (lane == 0) ci[warp] = bal ? (warp * 32 + __ffs(bal) - 1) : (1 << 30);
+      if (bal && lane == __ffs(bal) - 1) cd[warp] = gnew - gold;
+      hb::named_bar_sync(2, B);
+      int first = 1 << 30;
+      double delta = 0.0;
+      for (int w = 0; w < nwarp; ++w)
+        if (ci[w] < first) { first = ci[w]; delta = cd[w]; }
+      ++round;
+      if (first == (1 << 30)) break;  // nothing left that changes: everything is final
+      if (i <= first) done = true;   // SNPs up to and including `first` are committed
+      if (i == first) {
+        chg_a[nchg] = first;
+        chg_delta[nchg] = delta;
+        p.q_snp[qbase + nchg] = t * B + first;
+        p.q_delta[qbase + nchg] = delta;
+      }
+      ++nchg;
+      if (!done) {
+        // patch the right-hand sides of the later SNPs of this tile:  x_i'(r - x_f delta)
+        const int gfi = p.gram[(((size_t)t * D) * B + first) * B + i];
+        rhs -= (double)gfi * delta;
+      }
+      pos = first + 1;
+      if (pos >= B) break;
+    }
+    // commit this tile
+    if (act) {
+      p.g[j] = gnew;
+      p.tracker[j] = cls;
+      cnt[cls] += 1.0;
+      if (cls > 0) vacc += (model == HB_MODEL_R) ? (gnew * gnew / p.fold[cls]) : (gnew * gnew);
+    }
+    hb::named_bar_sync(2, B);  // chg lists complete and visible
+    // corrections owed to the next D-1 tiles, whose dots were taken before these updates
+    for (int dt = 1; dt < D; ++dt) {
+      if (t + dt >= T) break;
+      double corr = 0.0;
+      const int32_t* gb = p.gram + (((size_t)t * D + dt) * B) * B;
+      for (int c = 0; c < nchg; ++c) corr += (double)gb[(size_t)chg_a[c] * B + i] * chg_delta[c];
+      ring[(size_t)((t + dt) % D) * B + i] += corr;
+    }
+    qbase += nchg;
+    if (i == 0) p.tile_qend[t] = qbase;
+    hb::named_bar_sync(2, B);
+    if (i == 0) {
+      __threadfence();
+      hb::st_release(ctrl, t + 1);
+    }
+  }
+  // fixed-order reduction of the per-thread accumulators
+  double* myred = red + (size_t)i * (HB_MAX_FOLD + 1);
+#pragma unroll
+  for (int k = 0; k < HB_MAX_FOLD; ++k) myred[k] = cnt[k];
+  myred[HB_MAX_FOLD] = vacc;
+  hb::named_bar_sync(2, B);
+  if (i == 0) {
+    for (int k = 0; k <= HB_MAX_FOLD; ++k) {
+      double sacc = 0.0;
+      for (int q = 0; q < B; ++q) sacc += red[(size_t)q * (HB_MAX_FOLD + 1) + k];
+      if (k < HB_MAX_FOLD) p.out->count[k] = sacc; else p.out->varg_acc = sacc;
+    }
+    p.out->n_changed = qbase;
+  }
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_sweep(const __grid_constant__ SweepParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  if ((int)blockIdx.x == p.S) scalar_role(p, smem);
+  else stream_role(p, smem);
+}
+static const void* sweep_kernel_for(int threads) {
+  return threads <= 512 ? (const void*)k_sweep<512> : (const void*)k_sweep<1024>;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-iteration reductions (Bayes.cpp:480, 819, 823) -- one CTA, fixed reduction tree
+// ------------------------------------------------------------------------------------------
+__device__ double block_sum_1024(double v, double* sh) {
+  const int tid = threadIdx.x;
+  sh[tid] = v;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (tid < o) sh[tid] += sh[tid + o];
+    __syncthreads();
+  }
+  double r = sh[0];
+  __syncthreads();
+  return r;
+}
+__global__ void __launch_bounds__(1024) k_tail(const double* __restrict__ r, const double* __restrict__ u, int n,
+                                               SweepOutDev* out, const int* ctrl) {
+  __shared__ double sh[1024];
+  double a = 0, b = 0, c = 0;
+  for (int i = threadIdx.x; i < n; i += 1024) { double x = r[i]; a += x; b += x * x; c += u[i]; }
+  a = block_sum_1024(a, sh); b = block_sum_1024(b, sh); c = block_sum_1024(c, sh);
+  const double mean = c / n;
+  double e = 0, f = 0;
+  for (int i = threadIdx.x; i < n; i += 1024) { double x = mean - u[i]; e += x * x; f += x; }
+  e = block_sum_1024(e, sh); f = block_sum_1024(f, sh);
+  if (threadIdx.x == 0) {
+    out->sum_r = a; out->sum_r2 = b; out->sum_u = c;
+    out->var_u = (n > 1) ? (e - f * f / n) / (n - 1) : 0.0;  // op_var::direct_var
+    out->status = ctrl[1];
+  }
+}
+
+// BayesL: per-SNP variance draw after the sweep (Bayes.cpp:729-730) and sum(vargL) (:739)
+__global__ void k_bayesl_post(int m, int iter, hb_key_t key, const uint8_t* __restrict__ active, const double* __restrict__ g,
+                              double* __restrict__ vargL, double vare, double lambda, double lambda2) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m || !active[j]) return;
+  double uu, zz;
+  hb_draw_uz(key, HB_DOM_SNP, (uint32_t)iter, (uint32_t)j, HB_SL_IG, 0, &uu, &zz);
+  double vargi = 1.0 / hb_invgauss_from_uz(sqrt(vare) * lambda / fabs(g[j]), lambda2, uu, zz);
+  if (vargi >= 0) vargL[j] = vargi;
+}
+__global__ void __launch_bounds__(1024) k_sum(const double* __restrict__ x, int n, double* out) {
+  __shared__ double sh[1024];
+  double a = 0;
+  for (int i = threadIdx.x; i < n; i += 1024) a += x[i];
+  a = block_sum_1024(a, sh);
+  if (threadIdx.x == 0) *out = a;
+}
+
+// PIP / WPPA counters and effect sums
+__global__ void k_pip(int m, const int32_t* __restrict__ tracker, double* __restrict__ nzrate) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < m && tracker[j]) nzrate[j] += 1.0;
+}
+__global__ void k_wppa(int nw, const int* __restrict__ wstart, const int* __restrict__ wmem,
+                       const int32_t* __restrict__ tracker, double* __restrict__ wppa) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  for (int q = wstart[w]; q < wstart[w + 1]; ++q)
+    if (tracker[wmem[q]]) { wppa[w] += 1.0; return; }
+}
+__global__ void k_axpy1(int m, const double* __restrict__ g, double* __restrict__ gsum) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < m) gsum[j] += g[j];
+}
+
+// out[row] = sum_j x[row][j] * alpha[j]  (the X*g of Bayes.cpp:971).  grid (S, nchunk): block
+// (s, c) covers slab s and a contiguous range of tiles and writes partial[c][row]; k_gemv_sum
+// adds the chunks in order, so the result is deterministic.
+__global__ void __launch_bounds__(1024) k_gemv_part(const uint8_t* __restrict__ Xp, const double* __restrict__ alpha, int m,
+                                                    int R, int NRG, int CL, int T, int B, size_t slab_stride, size_t Npad,
+                                                    double* __restrict__ partial) {
+  extern __shared__ double sh[];  // CL * R
+  const int s = blockIdx.x, c = blockIdx.y, nchunk = gridDim.y;
+  const int tid = threadIdx.x, NTC = NRG * CL;
+  const int t_lo = (int)((long long)T * c / nchunk), t_hi = (int)((long long)T * (c + 1) / nchunk);
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+  if (tid < NTC) {
+    const int rg = tid % NRG, cl = tid / NRG;
+    const uint8_t* Xs = Xp + (size_t)s * slab_stride;
+    for (int t = t_lo; t < t_hi; ++t)
+      for (int cj = cl; cj < B; cj += CL) {
+        const int j = t * B + cj;
+        if (j >= m) continue;
+        const double a = alpha[j];
+        if (a == 0.0) continue;
+        const uint4 v = *(const uint4*)(Xs + ((size_t)t * B + cj) * R + 16 * rg);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fma((double)((w[i >> 2] >> (8 * (i & 3))) & 0xffu), a, acc[i]);
+      }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sh[(size_t)cl * R + 16 * rg + i] = acc[i];
+  }
+  __syncthreads();
+  for (int row = tid; row < R; row += blockDim.x) {
+    double v = 0.0;
+    for (int cl = 0; cl < CL; ++cl) v += sh[(size_t)cl * R + row];
+    partial[(size_t)c * Npad + (size_t)s * R + row] = v;
+  }
+}
+__global__ void k_gemv_sum(const double* __restrict__ partial, int nchunk, size_t Npad, int n, double* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n) return;
+  double v = 0.0;
+  for (int c = 0; c < nchunk; ++c) v += partial[(size_t)c * Npad + i];
+  out[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side of the engine
+// ------------------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
+  if (!cfg || !out) return hb_set_error("hb_engine_create: null argument");
+  if (cfg->n <= 0 || cfg->m <= 0) return hb_set_error("hb_engine_create: n and m must be positive");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0 || cfg->device < 0 || cfg->device >= ndev)
+    return hb_set_error("hb_engine_create: CUDA device %d not available (%d visible) -- this engine has no CPU fallback",
+                        cfg->device, ndev);
+  CU(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10)
+    return hb_set_error("hb_engine_create: device sm_%d%d is not a Blackwell (sm_100a) GPU", prop.major, prop.minor);
+  hb_engine* e = new hb_engine();
+  e->cfg = *cfg;
+  e->n = cfg->n; e->m = cfg->m;
+  e->nsm = prop.multiProcessorCount;
+  e->B = cfg->tile_snps > 0 ? cfg->tile_snps : 64;
+  e->D = cfg->lag_tiles > 0 ? cfg->lag_tiles : 4;
+  if (e->B % 64 != 0 || e->B > 256) { delete e; return hb_set_error("tile_snps must be 64, 128, 192 or 256"); }
+  if (e->D > 8) { delete e; return hb_set_error("lag_tiles must be <= 8"); }
+  int S = cfg->n_slabs > 0 ? cfg->n_slabs : e->nsm - 1;
+  S = std::min(S, e->nsm - 1);
+  S = std::min(S, (e->n + 15) / 16);
+  S = std::max(S, 1);
+  e->S = S;
+  e->NRG = (e->n + 16 * S - 1) / (16 * S);
+  e->R = 16 * e->NRG;
+  e->Npad = (size_t)S * e->R;
+  int CL = 16;
+  while (CL > 1 && e->NRG * CL > 928) CL >>= 1;
+  if (e->NRG * CL > 928) { delete e; return hb_set_error("n = %d rows per GPU is beyond this build's slab size (max ~%d)", e->n, 928 * 16 * S); }
+  e->CL = CL;
+  e->NTC = e->NRG * CL;
+  e->NTCp = (e->NTC + 31) & ~31;
+  e->block_threads = std::max(e->NTCp + 64, e->B);
+  e->T = (e->m + e->B - 1) / e->B;
+  e->m_pad = e->T * e->B;
+  e->stage_bytes = (size_t)e->B * e->R;
+  e->slab_stride = (size_t)e->T * e->stage_bytes;
+  const size_t part_bytes = 2 * (size_t)e->B * e->NRG * sizeof(double);
+  const size_t u_bytes = (size_t)e->R * sizeof(double);
+  const size_t fixed = part_bytes + u_bytes + 512;
+  const size_t budget = 200 * 1024;
+  if (fixed + 2 * e->stage_bytes > budget) {
+    delete e;
+    return hb_set_error("tile of %d SNPs x %d rows does not fit the shared-memory ring; lower tile_snps or use more GPUs", e->B, e->R);
+  }
+  e->NS = (int)std::min<size_t>(8, (budget - fixed) / e->stage_bytes);
+  e->off_part = (uint32_t)align_up((size_t)e->NS * e->stage_bytes, 128);
+  e->off_u = e->off_part + part_bytes;
+  e->off_bar = align_up(e->off_u + u_bytes, 16);
+  size_t stream_smem = e->off_bar + 2 * e->NS * 8 + 17 * 4 + 64;
+  size_t scalar_smem = ((size_t)e->D * e->B + e->B + 16 + (size_t)e->B * (HB_MAX_FOLD + 1)) * 8 + (e->B + 32) * 4 + 64;
+  e->smem_bytes = std::max(stream_smem, scalar_smem);
+  CU(cudaFuncSetAttribute(sweep_kernel_for(e->block_threads), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+  int occ = 0;
+  if (e->block_threads <= 512) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep<512>, e->block_threads, e->smem_bytes));
+  else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep<1024>, e->block_threads, e->smem_bytes));
+  if (occ < 1) { delete e; return hb_set_error("sweep kernel does not fit an SM (threads %d, smem %zu)", e->block_threads, e->smem_bytes); }
+  CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&e->ev[i]));
+  const size_t xbytes = (size_t)S * e->slab_stride;
+  CU(cudaMalloc(&e->Xp, xbytes));
+  CU(cudaMemsetAsync(e->Xp, 0, xbytes, e->stream));
+  CU(cudaMalloc(&e->r, e->Npad * 8)); CU(cudaMemsetAsync(e->r, 0, e->Npad * 8, e->stream));
+  CU(cudaMalloc(&e->u, e->Npad * 8)); CU(cudaMemsetAsync(e->u, 0, e->Npad * 8, e->stream));
+  const size_t mp = e->m_pad;
+  CU(cudaMalloc(&e->xpx, mp * 8)); CU(cudaMemsetAsync(e->xpx, 0, mp * 8, e->stream));
+  CU(cudaMalloc(&e->g, mp * 8)); CU(cudaMemsetAsync(e->g, 0, mp * 8, e->stream));
+  CU(cudaMalloc(&e->gsum, mp * 8)); CU(cudaMemsetAsync(e->gsum, 0, mp * 8, e->stream));
+  CU(cudaMalloc(&e->nzrate, mp * 8)); CU(cudaMemsetAsync(e->nzrate, 0, mp * 8, e->stream));
+  CU(cudaMalloc(&e->vargL, mp * 8)); CU(cudaMemsetAsync(e->vargL, 0, mp * 8, e->stream));
+  CU(cudaMalloc(&e->active, mp)); CU(cudaMemsetAsync(e->active, 0, mp, e->stream));
+  CU(cudaMalloc(&e->tracker, mp * 4)); CU(cudaMemsetAsync(e->tracker, 0, mp * 4, e->stream));
+  CU(cudaMalloc(&e->dacc, mp * 8));
+  CU(cudaMalloc(&e->arrive, (size_t)e->T * 4));
+  CU(cudaMalloc(&e->q_snp, mp * 4));
+  CU(cudaMalloc(&e->q_delta, mp * 8));
+  CU(cudaMalloc(&e->tile_qend, (size_t)e->T * 4));
+  CU(cudaMalloc(&e->ctrl, 64)); CU(cudaMemsetAsync(e->ctrl, 0, 64, e->stream));
+  CU(cudaMalloc(&e->out_dev, sizeof(SweepOutDev)));
+  CU(cudaStreamSynchronize(e->stream));
+  *out = e;
+  return 0;
+}
+
+extern "C" void hb_engine_destroy(hb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaFree(e->Xp); cudaFree(e->r); cudaFree(e->u); cudaFree(e->xpx); cudaFree(e->g); cudaFree(e->gsum);
+  cudaFree(e->nzrate); cudaFree(e->wppa); cudaFree(e->vargL); cudaFree(e->active); cudaFree(e->tracker);
+  cudaFree(e->gram); cudaFree(e->dacc); cudaFree(e->arrive); cudaFree(e->q_snp); cudaFree(e->q_delta);
+  cudaFree(e->tile_qend); cudaFree(e->ctrl); cudaFree(e->prm); cudaFree(e->out_dev); cudaFree(e->wstart); cudaFree(e->wmem);
+  for (int i = 0; i < 4; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+extern "C" int hb_engine_describe(hb_engine* e, int* n_slabs, int* rows_per_slab, int* tile_snps, int* lag_tiles,
+                                  uint64_t* geno_bytes, uint64_t* gram_bytes) {
+  if (!e) return hb_set_error("null engine");
+  if (n_slabs) *n_slabs = e->S;
+  if (rows_per_slab) *rows_per_slab = e->R;
+  if (tile_snps) *tile_snps = e->B;
+  if (lag_tiles) *lag_tiles = e->D;
+  if (geno_bytes) *geno_bytes = (uint64_t)e->S * e->slab_stride;
+  if (gram_bytes) *gram_bytes = (uint64_t)e->T * e->D * e->B * e->B * 4;
+  return 0;
+}
+
+static int load_chunked(hb_engine* e, const int8_t* X8, const double* X64, size_t ld) {
+  CU(cudaSetDevice(e->cfg.device));
+  const int n = e->n, m = e->m;
+  size_t cols_per_chunk = std::max<size_t>(1, (size_t)(256u << 20) / (size_t)n);
+  cols_per_chunk = std::min<size_t>(cols_per_chunk, (size_t)m);
+  int8_t* stage = nullptr;
+  CU(cudaMalloc(&stage, cols_per_chunk * (size_t)n));
+  std::vector<int8_t> hbuf;
+  if (X64 || ld != (size_t)n) hbuf.resize(cols_per_chunk * (size_t)n);
+  for (size_t c0 = 0; c0 < (size_t)m; c0 += cols_per_chunk) {
+    const size_t nc = std::min(cols_per_chunk, (size_t)m - c0);
+    const int8_t* src = nullptr;
+    if (X64) {
+      for (size_t c = 0; c < nc; ++c) {
+        const double* col = X64 + (c0 + c) * ld;
+        int8_t* dst = hbuf.data() + c * (size_t)n;
+        for (int i = 0; i < n; ++i) {
+          double v = col[i];
+          if (!(v == 0.0 || v == 1.0 || v == 2.0)) {
+            cudaFree(stage);
+            return hb_set_error("genotype (%d,%zu) = %g: this engine holds genotypes as int8 in {0,1,2}", i, c0 + c, v);
+          }
+          dst[i] = (int8_t)v;
+        }
+      }
+      src = hbuf.data();
+    } else if (ld != (size_t)n) {
+      for (size_t c = 0; c < nc; ++c) memcpy(hbuf.data() + c * (size_t)n, X8 + (c0 + c) * ld, (size_t)n);
+      src = hbuf.data();
+    } else {
+      src = X8 + c0 * ld;
+    }
+    if (!X64) {
+      // validate the value range once on the host: negative or > 2 bytes would silently change the model
+      const int8_t* p8 = src;
+      for (size_t q = 0; q < nc * (size_t)n; ++q)
+        if ((uint8_t)p8[q] > 2) {
+          cudaFree(stage);
+          return hb_set_error("genotype value %d outside {0,1,2} (column %zu)", (int)p8[q], c0 + q / n);
+        }
+    }
+    CU(cudaMemcpyAsync(stage, src, nc * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    const size_t work = (size_t)e->S * e->NRG * nc;
+    k_pack_i8<<<(unsigned)((work + 255) / 256), 256, 0, e->stream>>>(stage, (size_t)n, n, (int)c0, (int)nc, e->Xp, e->S, e->R,
+                                                                    e->NRG, e->T, e->B);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+  }
+  CU(cudaFree(stage));
+  e->geno_ready = true;
+  e->gram_ready = false;
+  return 0;
+}
+
+extern "C" int hb_engine_load_geno_i8(hb_engine* e, const int8_t* X, size_t ld) {
+  if (!e || !X) return hb_set_error("hb_engine_load_geno_i8: null argument");
+  if (ld < (size_t)e->n) return hb_set_error("hb_engine_load_geno_i8: ld < n");
+  return load_chunked(e, X, nullptr, ld);
+}
+extern "C" int hb_engine_load_geno_f64(hb_engine* e, const double* X, size_t ld) {
+  if (!e || !X) return hb_set_error("hb_engine_load_geno_f64: null argument");
+  if (ld < (size_t)e->n) return hb_set_error("hb_engine_load_geno_f64: ld < n");
+  return load_chunked(e, nullptr, X, ld);
+}
+
+extern "C" int hb_engine_synth_geno(hb_engine* e, uint64_t seed, int64_t row_offset) {
+  if (!e) return hb_set_error("null engine");
+  if (row_offset % 4 != 0) return hb_set_error("row_offset must be a multiple of 4");
+  CU(cudaSetDevice(e->cfg.device));
+  const size_t work = (size_t)e->S * e->NRG * (size_t)e->m;
+  const size_t blocks = (work + 255) / 256;
+  if (blocks > 0x7fffffffull) return hb_set_error("synthetic matrix too large for one launch");
+  k_synth<<<(unsigned)blocks, 256, 0, e->stream>>>(e->Xp, e->n, e->m, e->S, e->R, e->NRG, e->T, e->B, hb_make_key(seed),
+                                                  (long long)row_offset);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(e->stream));
+  e->geno_ready = true;
+  e->gram_ready = false;
+  return 0;
+}
+
+extern "C" int hb_synth_geno_host(int8_t* X, int n, int m, uint64_t seed, int64_t row_offset) {
+  if (!X || row_offset % 4 != 0) return hb_set_error("hb_synth_geno_host: bad argument");
+  hb_key_t key = hb_make_key(seed);
+  for (int j = 0; j < m; ++j) {
+    double t0, t1;
+    hb_synth_thresholds(key, (uint32_t)j, &t0, &t1);
+    int8_t* col = X + (size_t)j * n;
+    for (int i = 0; i < n; i += 4) {
+      uint32_t w = hb_synth_word(key, (uint32_t)j, (uint64_t)(row_offset + i) >> 2, t0, t1);
+      for (int b = 0; b < 4 && i + b < n; ++b) col[i + b] = (int8_t)((w >> (8 * b)) & 0xff);
+    }
+  }
+  return 0;
+}
+
+extern "C" int hb_engine_col_stats(hb_engine* e, double* xpx, double* sumx) {
+  if (!e || !xpx || !sumx) return hb_set_error("hb_engine_col_stats: null argument");
+  if (!e->geno_ready) return hb_set_error("hb_engine_col_stats: genotypes not loaded");
+  CU(cudaSetDevice(e->cfg.device));
+  double *dx = nullptr, *ds = nullptr;
+  CU(cudaMalloc(&dx, (size_t)e->m * 8));
+  CU(cudaMalloc(&ds, (size_t)e->m * 8));
+  const size_t threads = (size_t)e->m * 32;
+  k_col_stats<<<(unsigned)((threads + 255) / 256), 256, 0, e->stream>>>(e->Xp, e->m, e->S, e->R, e->NRG, e->T, e->B, dx, ds);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(xpx, dx, (size_t)e->m * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaMemcpyAsync(sumx, ds, (size_t)e->m * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  cudaFree(dx); cudaFree(ds);
+  return 0;
+}
+
+extern "C" int hb_engine_set_snp_info(hb_engine* e, const double* xpx_global, const uint8_t* active) {
+  if (!e || !xpx_global || !active) return hb_set_error("hb_engine_set_snp_info: null argument");
+  CU(cudaSetDevice(e->cfg.device));
+  CU(cudaMemcpyAsync(e->xpx, xpx_global, (size_t)e->m * 8, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->active, active, (size_t)e->m, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  e->info_ready = true;
+  return 0;
+}
+
+extern "C" int hb_engine_build_gram(hb_engine* e) {
+  if (!e) return hb_set_error("null engine");
+  if (!e->geno_ready) return hb_set_error("hb_engine_build_gram: genotypes not loaded");
+  CU(cudaSetDevice(e->cfg.device));
+  const size_t gbytes = (size_t)e->T * e->D * e->B * e->B * 4;
+  if (!e->gram) CU(cudaMalloc(&e->gram, gbytes));
+  const int nb = e->B / 64;
+  // grid.z is limited to 65535 tiles per launch
+  for (int t0 = 0; t0 < e->T; t0 += 65535) {
+    const int nt = std::min(65535, e->T - t0);
+    dim3 grid(e->D * nb, nb, nt);
+    k_gram_dp4a<<<grid, 256, 0, e->stream>>>(e->Xp, e->gram, e->S, e->R, e->T, e->B, e->D, t0);
+    CU(cudaGetLastError());
+  }
+  CU(cudaStreamSynchronize(e->stream));
+  e->gram_ready = true;
+  return 0;
+}
+
+static int copy_vec(hb_engine* e, double* dst_dev, const double* src_host, size_t cnt) {
+  CU(cudaSetDevice(e->cfg.device));
+  CU(cudaMemcpyAsync(dst_dev, src_host, cnt * 8, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+static int fetch_vec(hb_engine* e, double* dst_host, const double* src_dev, size_t cnt) {
+  CU(cudaSetDevice(e->cfg.device));
+  CU(cudaMemcpyAsync(dst_host, src_dev, cnt * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+extern "C" int hb_engine_set_residual(hb_engine* e, const double* y) { if (!e || !y) return hb_set_error("null argument"); return copy_vec(e, e->r, y, e->n); }
+extern "C" int hb_engine_get_residual(hb_engine* e, double* y) { if (!e || !y) return hb_set_error("null argument"); return fetch_vec(e, y, e->r, e->n); }
+extern "C" int hb_engine_set_u(hb_engine* e, const double* u) { if (!e || !u) return hb_set_error("null argument"); return copy_vec(e, e->u, u, e->n); }
+extern "C" int hb_engine_get_u(hb_engine* e, double* u) { if (!e || !u) return hb_set_error("null argument"); return fetch_vec(e, u, e->u, e->n); }
+extern "C" int hb_engine_set_effects(hb_engine* e, const double* g) { if (!e || !g) return hb_set_error("null argument"); return copy_vec(e, e->g, g, e->m); }
+extern "C" int hb_engine_get_effects(hb_engine* e, double* g) { if (!e || !g) return hb_set_error("null argument"); return fetch_vec(e, g, e->g, e->m); }
+extern "C" int hb_engine_set_vargL(hb_engine* e, const double* v) { if (!e || !v) return hb_set_error("null argument"); return copy_vec(e, e->vargL, v, e->m); }
+extern "C" int hb_engine_get_effect_sums(hb_engine* e, double* g) { if (!e || !g) return hb_set_error("null argument"); return fetch_vec(e, g, e->gsum, e->m); }
+extern "C" int hb_engine_get_tracker(hb_engine* e, int32_t* t) {
+  if (!e || !t) return hb_set_error("null argument");
+  CU(cudaSetDevice(e->cfg.device));
+  CU(cudaMemcpyAsync(t, e->tracker, (size_t)e->m * 4, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out* out) {
+  if (!e || !in || !out) return hb_set_error("hb_engine_sweep: null argument");
+  if (!e->geno_ready || !e->info_ready || !e->gram_ready)
+    return hb_set_error("hb_engine_sweep: engine not ready (genotypes %d, snp info %d, gram %d)", (int)e->geno_ready,
+                        (int)e->info_ready, (int)e->gram_ready);
+  if (in->model_index < 1 || in->model_index > 6) return hb_set_error("hb_engine_sweep: bad model_index");
+  const int F = in->n_fold;
+  if (F < 2 || F > HB_MAX_FOLD) return hb_set_error("hb_engine_sweep: n_fold must be in [2, %d]", HB_MAX_FOLD);
+  CU(cudaSetDevice(e->cfg.device));
+  const int nfields = 2 + 4 * (HB_MAX_FOLD - 1);
+  if (!e->prm) CU(cudaMalloc(&e->prm, (size_t)nfields * e->m_pad * 8));
+  PrepParams pp;
+  memset(&pp, 0, sizeof pp);
+  pp.m = e->m; pp.m_pad = e->m_pad; pp.T = e->T; pp.iter = in->iter; pp.model = in->model_index; pp.F = F;
+  for (int k = 0; k < HB_MAX_FOLD; ++k) { pp.fold[k] = in->fold[k]; pp.logpi[k] = in->logpi[k]; pp.vara_fold[k] = in->vara_fold[k]; }
+  pp.vare = in->vare; pp.dfvara = in->dfvara; pp.s2varg = in->s2varg;
+  pp.key = hb_make_key(e->cfg.seed);
+
+  SweepParams sp;
+  memset(&sp, 0, sizeof sp);
+  sp.Xp = e->Xp; sp.r = e->r; sp.u = e->u; sp.xpx = e->xpx; sp.active = e->active; sp.g = e->g; sp.tracker = e->tracker;
+  sp.gram = e->gram; sp.dacc = e->dacc; sp.arrive = e->arrive; sp.q_snp = e->q_snp; sp.q_delta = e->q_delta;
+  sp.tile_qend = e->tile_qend; sp.ctrl = e->ctrl; sp.prm = e->prm; sp.out = e->out_dev;
+  sp.slab_stride = e->slab_stride; sp.m_pad = e->m_pad;
+  sp.n = e->n; sp.m = e->m; sp.S = e->S; sp.R = e->R; sp.NRG = e->NRG; sp.CL = e->CL; sp.T = e->T; sp.B = e->B; sp.D = e->D;
+  sp.NS = e->NS; sp.NTC = e->NTC; sp.NTCp = e->NTCp;
+  sp.stage_bytes = (uint32_t)e->stage_bytes; sp.off_part = (uint32_t)e->off_part; sp.off_u = (uint32_t)e->off_u;
+  sp.off_bar = (uint32_t)e->off_bar;
+  sp.model = in->model_index; sp.F = F;
+  for (int k = 0; k < HB_MAX_FOLD; ++k) sp.fold[k] = in->fold[k];
+  sp.logpi0 = in->logpi[0];
+  sp.mu_shift = in->mu_shift;
+  // fixed-point scale of the dot accumulators: |x_j'r| <= ||x_j|| ||r|| <= 2 sqrt(n) ||r||, with a
+  // factor 16 of head-room for the residual changing during the sweep
+  {
+    const double ntot = (double)e->n * std::max(1, e->cfg.world);
+    double bound = 2.0 * sqrt(ntot * std::max(in->rnorm2_bound, 1e-300)) * 16.0;
+    int ex = (int)floor(log2(4.0e18 / bound));
+    ex = std::max(-900, std::min(ex, 900));
+    sp.dscale = ldexp(1.0, ex);
+    sp.inv_dscale = ldexp(1.0, -ex);
+  }
+  sp.arrive_target = (unsigned)(e->S * (std::min(e->B, e->NTCp) / 32));
+
+  CU(cudaEventRecord(e->ev[0], e->stream));
+  k_prep<<<(e->m_pad + 255) / 256, 256, 0, e->stream>>>(pp, e->xpx, e->active, e->g, e->vargL, e->prm, e->dacc, e->arrive, e->ctrl,
+                                                       e->out_dev);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(e->ev[1], e->stream));
+  {
+    void* args[] = {(void*)&sp};
+    CU(cudaLaunchCooperativeKernel(sweep_kernel_for(e->block_threads), dim3(e->S + 1), dim3(e->block_threads), args, e->smem_bytes, e->stream));
+  }
+  CU(cudaEventRecord(e->ev[2], e->stream));
+  if (in->model_index == HB_MODEL_L) {
+    k_bayesl_post<<<(e->m + 255) / 256, 256, 0, e->stream>>>(e->m, in->iter, pp.key, e->active, e->g, e->vargL, in->vare,
+                                                             in->lambda, in->lambda2);
+    CU(cudaGetLastError());
+    k_sum<<<1, 1024, 0, e->stream>>>(e->vargL, e->m, &e->out_dev->sum_vargL);
+    CU(cudaGetLastError());
+  }
+  k_tail<<<1, 1024, 0, e->stream>>>(e->r, e->u, e->n, e->out_dev, e->ctrl);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(e->ev[3], e->stream));
+  SweepOutDev h;
+  CU(cudaMemcpyAsync(&h, e->out_dev, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaEventElapsedTime(&e->ms_prep, e->ev[0], e->ev[1]));
+  CU(cudaEventElapsedTime(&e->ms_sweep, e->ev[1], e->ev[2]));
+  CU(cudaEventElapsedTime(&e->ms_tail, e->ev[2], e->ev[3]));
+  for (int k = 0; k < HB_MAX_FOLD; ++k) out->count[k] = h.count[k];
+  out->varg_acc = h.varg_acc; out->sum_vargL = h.sum_vargL;
+  out->sum_r = h.sum_r; out->sum_r2 = h.sum_r2; out->sum_u = h.sum_u; out->var_u = h.var_u;
+  out->n_changed = h.n_changed; out->status = h.status;
+  if (h.status != 0)
+    return hb_set_error("sweep kernel aborted with device status %d (%s)", h.status,
+                        h.status == HB_ABORT_OVERFLOW ? "fixed-point dot overflow" : "timeout waiting on a tile signal");
+  return 0;
+}
+
+extern "C" int hb_engine_last_sweep_ms(hb_engine* e, float* a, float* b, float* c) {
+  if (!e) return hb_set_error("null engine");
+  if (a) *a = e->ms_prep;
+  if (b) *b = e->ms_sweep;
+  if (c) *c = e->ms_tail;
+  return 0;
+}
+
+extern "C" int hb_engine_set_windows(hb_engine* e, const int32_t* windindx) {
+  if (!e) return hb_set_error("null engine");
+  CU(cudaSetDevice(e->cfg.device));
+  cudaFree(e->wstart); cudaFree(e->wmem); cudaFree(e->wppa);
+  e->wstart = e->wmem = nullptr; e->wppa = nullptr; e->nw = 0;
+  if (!windindx) return 0;
+  int nw = 0;
+  for (int i = 0; i < e->m; ++i) nw = std::max(nw, (int)windindx[i]);
+  if (nw <= 0) return 0;
+  std::vector<int> ws(nw + 1, 0), wm(e->m), fill(nw, 0);
+  for (int i = 0; i < e->m; ++i) if (windindx[i] >= 1) ws[windindx[i]]++;
+  for (int w = 0; w < nw; ++w) ws[w + 1] += ws[w];
+  for (int i = 0; i < e->m; ++i) if (windindx[i] >= 1) { int w = windindx[i] - 1; wm[ws[w] + fill[w]++] = i; }
+  CU(cudaMalloc(&e->wstart, (nw + 1) * 4));
+  CU(cudaMalloc(&e->wmem, (size_t)e->m * 4));
+  CU(cudaMalloc(&e->wppa, (size_t)nw * 8));
+  CU(cudaMemcpy(e->wstart, ws.data(), (nw + 1) * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(e->wmem, wm.data(), (size_t)e->m * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemset(e->wppa, 0, (size_t)nw * 8));
+  e->nw = nw;
+  return 0;
+}
+extern "C" int hb_engine_accumulate_pip(hb_engine* e) {
+  if (!e) return hb_set_error("null engine");
+  CU(cudaSetDevice(e->cfg.device));
+  k_pip<<<(e->m + 255) / 256, 256, 0, e->stream>>>(e->m, e->tracker, e->nzrate);
+  CU(cudaGetLastError());
+  if (e->nw) {
+    k_wppa<<<(e->nw + 127) / 128, 128, 0, e->stream>>>(e->nw, e->wstart, e->wmem, e->tracker, e->wppa);
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+extern "C" int hb_engine_get_pip_counts(hb_engine* e, double* nzrate, double* wppa, int nw) {
+  if (!e) return hb_set_error("null engine");
+  CU(cudaSetDevice(e->cfg.device));
+  if (nzrate) CU(cudaMemcpyAsync(nzrate, e->nzrate, (size_t)e->m * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (wppa && e->nw) {
+    if (nw != e->nw) return hb_set_error("window count mismatch");
+    CU(cudaMemcpyAsync(wppa, e->wppa, (size_t)nw * 8, cudaMemcpyDeviceToHost, e->stream));
+  }
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+extern "C" int hb_engine_accumulate_effects(hb_engine* e) {
+  if (!e) return hb_set_error("null engine");
+  CU(cudaSetDevice(e->cfg.device));
+  k_axpy1<<<(e->m + 255) / 256, 256, 0, e->stream>>>(e->m, e->g, e->gsum);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int hb_engine_predict(hb_engine* e, const double* alpha, double* out) {
+  if (!e || !alpha || !out) return hb_set_error("hb_engine_predict: null argument");
+  if (!e->geno_ready) return hb_set_error("hb_engine_predict: genotypes not loaded");
+  CU(cudaSetDevice(e->cfg.device));
+  const int nchunk = 32;
+  double *da = nullptr, *dp = nullptr, *dout = nullptr;
+  CU(cudaMalloc(&da, (size_t)e->m * 8));
+  CU(cudaMalloc(&dp, (size_t)nchunk * e->Npad * 8));
+  CU(cudaMalloc(&dout, (size_t)e->n * 8));
+  CU(cudaMemcpyAsync(da, alpha, (size_t)e->m * 8, cudaMemcpyHostToDevice, e->stream));
+  const size_t sh = (size_t)e->CL * e->R * 8;
+  CU(cudaFuncSetAttribute(k_gemv_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+  k_gemv_part<<<dim3(e->S, nchunk), e->NTCp, sh, e->stream>>>(e->Xp, da, e->m, e->R, e->NRG, e->CL, e->T, e->B, e->slab_stride,
+                                                             e->Npad, dp);
+  CU(cudaGetLastError());
+  k_gemv_sum<<<(e->n + 255) / 256, 256, 0, e->stream>>>(dp, nchunk, e->Npad, e->n, dout);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dout, (size_t)e->n * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  cudaFree(da); cudaFree(dp); cudaFree(dout);
+  return 0;
+}

@@ -111,7 +111,7 @@ HB_HD double hb_u01(uint32_t a, uint32_t b) {
 HB_HD double hb_qnorm(double p) {
   double q = p - 0.5, r, val;
   if (fabs(q) <= 0.425) {
-    r = 0.180625 - q * q;
+    r = HB_ADD(0.180625, -HB_MUL(q, q));
     double num = 2509.0809287301226727;
     num = HB_H(num, r, 33430.575583588128105);
     num = HB_H(num, r, 67265.770927008700853);

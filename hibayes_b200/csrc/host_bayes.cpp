@@ -1,0 +1,468 @@
+// host_bayes.cpp -- C++ host orchestration of the individual-level Gibbs sampler.
+//
+// Mirrors Rcpp::List Bayes(...) of the reference (/root/reference/src/Bayes.cpp:60-1094): same
+// argument meaning, checks and error texts (:92-117, :293, :325, :356), same priors (:319-375),
+// same per-iteration order (intercept :480, covariates :484, environmental random effects :496,
+// single-step term :554, SNP sweep :586, variances :819-823, counters :826-845, records
+// :848-882, early break :916) and the same outputs (:919-1040).  The SNP sweep and the
+// reductions around it run on the GPU through hb_engine_*; there is no CPU fallback.
+//
+// The Rcpp file that would replace src/Bayes.cpp unpacks its arguments into hb_bayes_args and
+// calls hb_bayes(); INTEGRATION.md shows it.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../include/hibayes_b200.h"
+#include "hb_rng.h"
+
+int hb_set_error(const char* fmt, ...);
+
+namespace {
+
+inline bool isna(double v) { return v != v; }
+
+// Armadillo arrayops::accumulate / op_var::direct_var (two interleaved accumulators)
+double acc_sum(const double* x, int n) {
+  double a1 = 0.0, a2 = 0.0;
+  int i, j;
+  for (i = 0, j = 1; j < n; i += 2, j += 2) { a1 += x[i]; a2 += x[j]; }
+  if (i < n) a1 += x[i];
+  return a1 + a2;
+}
+double arma_var(const double* x, int n) {
+  if (n < 2) return 0.0;
+  const double mean = acc_sum(x, n) / (double)n;
+  double acc2 = 0.0, acc3 = 0.0;
+  int i, j;
+  for (i = 0, j = 1; j < n; i += 2, j += 2) {
+    double ti = mean - x[i], tj = mean - x[j];
+    acc2 += ti * ti + tj * tj;
+    acc3 += ti + tj;
+  }
+  if (i < n) { double ti = mean - x[i]; acc2 += ti * ti; acc3 += ti; }
+  return (acc2 - acc3 * acc3 / (double)n) / (double)(n - 1);
+}
+double ddot(int n, const double* x, const double* y) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += x[i] * y[i];
+  return s;
+}
+void daxpy(int n, double a, const double* x, double* y) {
+  for (int i = 0; i < n; ++i) y[i] += a * x[i];
+}
+
+struct EngineGuard {
+  hb_engine* e = nullptr;
+  ~EngineGuard() { hb_engine_destroy(e); }
+};
+
+double seconds_since(const std::chrono::steady_clock::time_point& t0) {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // namespace
+
+#define HBCHK(call) do { if ((call) != 0) return 1; } while (0)
+
+extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
+  if (!a || !o) return hb_set_error("hb_bayes: null argument");
+  const int n = a->n, m = a->m;
+  const std::string model = a->model ? a->model : "";
+  const hb_key_t KEY = hb_make_key(a->seed);
+
+  // ---- Bayes.cpp:92-117
+  for (int i = 0; i < n; ++i) if (isna(a->y[i])) return hb_set_error("NAs are not allowed in y.");
+  const int model_index = (model == "BayesRR" ? 1 : (model == "BayesA" ? 2 : (model == "BayesB" || model == "BayesBpi" ? 3 :
+                          (model == "BayesC" || model == "BayesCpi" || model == "BSLMM" ? 4 : (model == "BayesL" ? 5 : 6)))));
+  bool fixpi = (model == "BayesB" || model == "BayesC");
+  const int n_fold = a->n_fold;
+  if (n_fold < 2) return hb_set_error("Pi should be a vector.");
+  if (acc_sum(a->Pi, n_fold) != 1) return hb_set_error("sum of Pi should be 1.");
+  if (a->Pi[0] == 1) return hb_set_error("all markers have no effect size.");
+  for (int i = 0; i < n_fold; ++i)
+    if (a->Pi[i] < 0 || a->Pi[i] > 1) return hb_set_error("elements of Pi should be at the range of [0, 1]");
+  std::vector<double> Pi(a->Pi, a->Pi + n_fold);
+  std::vector<double> fold_(std::max(n_fold, 2), 0.0);
+  if (a->fold) std::copy(a->fold, a->fold + n_fold, fold_.begin());
+  else {
+    if (model == "BayesR") return hb_set_error("'fold' should be provided for BayesR model.");
+    if (n_fold != 2) return hb_set_error("length of Pi and fold not equals.");
+  }
+  if (n_fold > HB_MAX_FOLD) return hb_set_error("this build supports at most %d mixture components", HB_MAX_FOLD);
+
+  const double vary = arma_var(a->y, n);
+  const double h2 = 0.5;
+  const int niter = a->niter, nburn = a->nburn, thin = a->thin;
+  const int n_records = (niter - nburn) / thin;  // :124
+
+  // ---- covariates :126-147
+  const int nc = a->nc;
+  std::vector<double> cpc(nc), beta(nc, 0.0), betasum(nc, 0.0);
+  for (int i = 0; i < nc; ++i) cpc[i] = ddot(n, a->C + (size_t)i * n, a->C + (size_t)i * n);
+  // ---- environmental random effects :149-201
+  const int nr = a->nr;
+  const double dfr = isna(a->dfvr) ? -1 : a->dfvr;
+  const double s2r = isna(a->s2vr) ? 0 : a->s2vr;
+  std::vector<double> vrtmp(nr), vrv(nr, 0.0), vrsum(nr, 0.0);
+  std::vector<int> R_off(nr + 1, 0);
+  int n_levels = 0;
+  for (int i = 0; i < nr; ++i) {
+    vrtmp[i] = vary * (1 - h2) / (nr + 1);
+    n_levels += a->nlev[i];
+    R_off[i + 1] = n_levels;
+  }
+  std::vector<double> estR(n_levels, 0.0), estR_tmp(n_levels, 0.0), r_rhs(n_levels, 0.0), r_cnt(n_levels, 0.0),
+      estRsum(n_levels, 0.0), diff(nr ? n : 0);
+  for (int i = 0; i < nr; ++i)
+    for (int k = 0; k < n; ++k) r_cnt[R_off[i] + a->Rlev[(size_t)i * n + k]] += 1.0;
+  // ---- single-step term :235-275
+  const int ne = a->ne, qe = ne ? a->qe : 0;
+  double veps = 0, vepstmp = 0, JtJ = 0, epsl_J_beta = 0, vepssum = 0, Jsum = 0;
+  std::vector<double> e_estR(qe, 0.0), e_tmp(qe, 0.0), e_rhs(qe, 0.0), e_cnt(qe, 0.0), e_sum(qe, 0.0);
+  if (ne) {
+    if (!a->Gi_colptr) return hb_set_error("variance-covariance matrix should be provided for epsilon term.");
+    JtJ = ddot(n, a->epsl_y_J, a->epsl_y_J);
+    for (int i = 0; i < ne; ++i) e_cnt[a->epsl_index[i] - 1] += 1.0;
+  }
+
+  int NnzSnp = 0;
+  bool have_tracker = false;
+  if (model == "BayesRR" || model == "BayesA" || model == "BayesL") {  // :288-292
+    NnzSnp = m;
+    Pi[0] = 0; Pi[1] = 1;
+    fixpi = true;
+  } else {
+    if (model != "BayesR" && n_fold != 2)
+      return hb_set_error("length of Pi should be 2, the first value is the proportion of non-effect markers.");
+    have_tracker = true;
+  }
+  double dfvara_ = isna(a->dfvg) ? 4 : a->dfvg;
+  if (dfvara_ <= 2) return hb_set_error("dfvg should not be less than 2.");
+  if (niter < nburn) return hb_set_error("Number of total iteration ('niter') shold be larger than burn-in ('nburn').");
+
+  // ---- device engine: load X, column statistics (:310-317), Gram band
+  const auto t_setup = std::chrono::steady_clock::now();
+  EngineGuard guard;
+  hb_engine_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.device = a->device; cfg.n = n; cfg.m = m; cfg.tile_snps = a->tile_snps; cfg.lag_tiles = a->lag_tiles;
+  cfg.n_slabs = a->n_slabs; cfg.seed = a->seed; cfg.rank = 0; cfg.world = 1;
+  HBCHK(hb_engine_create(&cfg, &guard.e));
+  hb_engine* E = guard.e;
+  if (a->x_type == 1) HBCHK(hb_engine_load_geno_i8(E, (const int8_t*)a->X, (size_t)n));
+  else HBCHK(hb_engine_load_geno_f64(E, (const double*)a->X, (size_t)n));
+  std::vector<double> xpx(m), sumx(m), vx(m);
+  HBCHK(hb_engine_col_stats(E, xpx.data(), sumx.data()));
+  std::vector<uint8_t> active(m);
+  int nvar0 = 0;
+  for (int i = 0; i < m; ++i) {
+    // var(x) from exact integer sums; zero exactly when the column is constant
+    const bool constant = ((double)n * xpx[i] == sumx[i] * sumx[i]);
+    vx[i] = constant ? 0.0 : (xpx[i] - sumx[i] * sumx[i] / (double)n) / (double)(n - 1);
+    active[i] = constant ? 0 : 1;
+    nvar0 += constant ? 1 : 0;
+  }
+  const double sumvx = acc_sum(vx.data(), m);
+  HBCHK(hb_engine_set_snp_info(E, xpx.data(), active.data()));
+  HBCHK(hb_engine_build_gram(E));
+  if (a->windindx) HBCHK(hb_engine_set_windows(E, a->windindx));
+  int nw = 0;
+  if (a->windindx) for (int i = 0; i < m; ++i) if (a->windindx[i] > nw) nw = a->windindx[i];
+  o->seconds_setup = seconds_since(t_setup);
+
+  // ---- priors :319-375
+  double vara_ = isna(a->vg) ? ((dfvara_ - 2) / dfvara_) * vary * h2 : a->vg;
+  vepstmp = vara_;
+  double vare_ = isna(a->ve) ? vary * (1 - h2) / (nr + 1) : a->ve;
+  const double dfvare_ = isna(a->dfve) ? -2 : a->dfve;
+  const double s2vara_ = isna(a->s2vg) ? vara_ * (dfvara_ - 2) / dfvara_ : a->s2vg;
+  double varg = vara_ / ((1 - Pi[0]) * sumvx);
+  const double s2varg_ = s2vara_ / ((1 - Pi[0]) * sumvx);
+  const double s2vare_ = isna(a->s2ve) ? 0 : a->s2ve;
+  const double R2 = (dfvara_ - 2) / dfvara_;
+  double lambda2 = 2 * (1 - R2) / (R2)*sumvx;
+  double lambda = sqrt(lambda2);
+  const double shape0 = 1.1;
+  const double rate0 = (shape0 - 1) / lambda2;
+  if (model == "BayesL") {
+    std::vector<double> vargL(m, varg);
+    HBCHK(hb_engine_set_vargL(E, vargL.data()));
+  }
+  std::vector<double> fold_snp_num(n_fold, 0.0), vara_fold(n_fold, 0.0);
+  for (int j = 0; j < n_fold; ++j) vara_fold[j] = (vara_ / ((1 - Pi[0]) * sumvx)) * fold_[j];
+
+  // ---- state :469-471
+  double mu_, mu = acc_sum(a->y, n) / n;
+  std::vector<double> yadj(n), u_host;
+  for (int i = 0; i < n; ++i) yadj[i] = a->y[i] - mu;
+  HBCHK(hb_engine_set_residual(E, yadj.data()));
+  const bool host_effects = (nc > 0 || nr > 0 || ne > 0);
+  if (ne) u_host.assign(n, 0.0);
+  double sum_r = acc_sum(yadj.data(), n), sum_r2 = ddot(n, yadj.data(), yadj.data());
+
+  double musum = 0, varasum = 0, varesum = 0, hsqsum = 0;
+  std::vector<double> pisum(n_fold, 0.0), gtmp;
+  int count = 0, nzct = 0, iter;
+  double t_sweep = 0.0;
+
+  for (iter = 0; iter < niter; ++iter) {
+    const uint32_t it = (uint32_t)iter;
+    // intercept :480-482
+    mu_ = -(sum_r / n + sqrt(vare_ / n) * hb_draw_z(KEY, HB_DOM_ITER, it, HB_IT_MU, 0, 0));
+    mu -= mu_;
+    double mu_shift = mu_;
+    double rnorm2 = sum_r2 + 2.0 * mu_ * sum_r + (double)n * mu_ * mu_;
+    if (host_effects) {
+      HBCHK(hb_engine_get_residual(E, yadj.data()));
+      for (int i = 0; i < n; ++i) yadj[i] += mu_ * 1.0;
+      mu_shift = 0.0;
+      if (ne) HBCHK(hb_engine_get_u(E, u_host.data()));
+      // covariates :484-494
+      for (int i = 0; i < nc; ++i) {
+        const double* dci = a->C + (size_t)i * n;
+        const double oldgi = beta[i], v = cpc[i];
+        double rhs = ddot(n, dci, yadj.data());
+        rhs += v * oldgi;
+        const double gi = rhs / v + sqrt(vare_ / v) * hb_draw_z(KEY, HB_DOM_COV, it, (uint32_t)i, 0, 0);
+        daxpy(n, oldgi - gi, dci, yadj.data());
+        beta[i] = gi;
+      }
+      // environmental random effects :496-516
+      for (int i = 0; i < nr; ++i) {
+        const int off = R_off[i], qr = a->nlev[i];
+        const int32_t* lev = a->Rlev + (size_t)i * n;
+        for (int q = 0; q < qr; ++q) r_rhs[off + q] = 0.0;
+        for (int k = 0; k < n; ++k) r_rhs[off + lev[k]] += yadj[k];
+        for (int q = 0; q < qr; ++q) r_rhs[off + q] += r_cnt[off + q] * estR[off + q];
+        for (int q = 0; q < qr; ++q) {
+          const double l = r_cnt[off + q] + vare_ / vrtmp[i];
+          estR_tmp[off + q] = r_rhs[off + q] / l + sqrt(vare_ / l) * hb_draw_z(KEY, HB_DOM_RAND, it, (uint32_t)(off + q), 0, 0);
+        }
+        for (int k = 0; k < n; ++k) diff[k] = estR[off + lev[k]] - estR_tmp[off + lev[k]];
+        daxpy(n, 1.0, diff.data(), yadj.data());
+        vrtmp[i] = (ddot(qr, estR_tmp.data() + off, estR_tmp.data() + off) + s2r * dfr) /
+                   hb_draw_chisq(KEY, HB_DOM_ITER, it, HB_IT_VR0 + (uint32_t)i, 0, qr + dfr);
+        vrv[i] = arma_var(estR_tmp.data() + off, qr);
+        for (int q = 0; q < qr; ++q) estR[off + q] = estR_tmp[off + q];
+      }
+      // single-step J + epsilon :554-584 (sparse Gauss-Seidel sampler, solver.cpp:131-140)
+      if (ne) {
+        double oldgi = epsl_J_beta, v = JtJ;
+        double rhs = ddot(n, a->epsl_y_J, yadj.data());
+        rhs += v * oldgi;
+        const double gi = rhs / v + sqrt(vare_ / v) * hb_draw_z(KEY, HB_DOM_ITER, it, HB_IT_J, 0, 0);
+        double gi_ = oldgi - gi;
+        daxpy(n, gi_, a->epsl_y_J, yadj.data());
+        gi_ *= -1;
+        daxpy(n, gi_, a->epsl_y_J, u_host.data());
+        epsl_J_beta = gi;
+        const double ratio = vare_ / vepstmp;
+        for (int q = 0; q < qe; ++q) e_rhs[q] = 0.0;
+        for (int i = 0; i < ne; ++i) e_rhs[a->epsl_index[i] - 1] += yadj[n - ne + i];
+        for (int q = 0; q < qe; ++q) e_rhs[q] += e_cnt[q] * e_tmp[q];
+        for (int i = 0; i < qe; ++i) {
+          double aii = e_cnt[i], Ax = 0.0;
+          bool have_diag = false;
+          for (int p = a->Gi_colptr[i]; p < a->Gi_colptr[i + 1]; ++p) {
+            const int rix = a->Gi_rowidx[p];
+            const double aval = a->Gi_val[p] * ratio + (rix == i ? e_cnt[i] : 0.0);
+            if (rix == i) { aii = aval; have_diag = true; }
+            Ax += aval * e_tmp[rix];
+          }
+          if (!have_diag) Ax += e_cnt[i] * e_tmp[i];
+          const double invlhs = 1.0 / aii;
+          const double uu = invlhs * (e_rhs[i] - Ax) + e_tmp[i];
+          e_tmp[i] = uu + sqrt(invlhs * vare_) * hb_draw_z(KEY, HB_DOM_EPS, it, (uint32_t)i, 0, 0);
+        }
+        for (int q = 0; q < qe; ++q) e_estR[q] -= e_tmp[q];
+        for (int i = 0; i < ne; ++i) {
+          const double d = e_estR[a->epsl_index[i] - 1];
+          yadj[n - ne + i] += d;
+          u_host[n - ne + i] -= d;
+        }
+        vepstmp = 0.0;
+        for (int c = 0; c < qe; ++c) {
+          double colsum = 0.0;
+          for (int p = a->Gi_colptr[c]; p < a->Gi_colptr[c + 1]; ++p) colsum += a->Gi_val[p] * e_tmp[a->Gi_rowidx[p]];
+          vepstmp += colsum * e_tmp[c];
+        }
+        vepstmp += s2vara_ * dfvara_;
+        vepstmp /= hb_draw_chisq(KEY, HB_DOM_ITER, it, HB_IT_VEPS, 0, dfvara_ + qe);
+        for (int q = 0; q < qe; ++q) e_estR[q] = e_tmp[q];
+        veps = vepstmp;
+        HBCHK(hb_engine_set_u(E, u_host.data()));
+      }
+      HBCHK(hb_engine_set_residual(E, yadj.data()));
+      rnorm2 = ddot(n, yadj.data(), yadj.data());
+    }
+
+    // SNP sweep :586-816 on the device
+    hb_sweep_in in;
+    memset(&in, 0, sizeof in);
+    in.iter = iter; in.model_index = model_index; in.n_fold = n_fold;
+    for (int j = 0; j < n_fold; ++j) { in.fold[j] = fold_[j]; in.logpi[j] = log(Pi[j]); }
+    if (model_index == 6) for (int j = 0; j < n_fold; ++j) in.vara_fold[j] = vara_fold[j];
+    else in.vara_fold[1] = varg;
+    in.vare = vare_; in.dfvara = dfvara_; in.s2varg = s2varg_;
+    in.lambda = lambda; in.lambda2 = lambda2;
+    in.mu_shift = mu_shift; in.rnorm2_bound = rnorm2;
+    hb_sweep_out so;
+    HBCHK(hb_engine_sweep(E, &in, &so));
+    { float a0, a1, a2; hb_engine_last_sweep_ms(E, &a0, &a1, &a2); t_sweep += 1e-3 * (a0 + a1 + a2); }
+
+    switch (model_index) {
+      case 1:
+        varg = (so.varg_acc + s2varg_ * dfvara_) / hb_draw_chisq(KEY, HB_DOM_ITER, it, HB_IT_VARG, 0, dfvara_ + m - nvar0);  // :603
+        break;
+      case 2:
+        break;
+      case 3:
+      case 4:
+        fold_snp_num[1] = so.count[1];                          // :666-668, :710-712
+        fold_snp_num[0] = m - nvar0 - fold_snp_num[1];
+        NnzSnp = (int)fold_snp_num[1];
+        if (model_index == 4)
+          varg = (so.varg_acc + s2varg_ * dfvara_) / hb_draw_chisq(KEY, HB_DOM_ITER, it, HB_IT_VARG, 0, dfvara_ + NnzSnp);  // :713
+        break;
+      case 5: {
+        const double shape = shape0 + m - nvar0;                 // :738-741
+        const double rate = rate0 + so.sum_vargL / 2;
+        lambda2 = hb_draw_gamma(KEY, HB_DOM_ITER, it, HB_IT_LAMBDA, 0, shape) * (1 / rate);
+        lambda = sqrt(lambda2);
+        break;
+      }
+      case 6:
+        for (int j = 0; j < n_fold; ++j) fold_snp_num[j] = so.count[j];
+        fold_snp_num[0] += nvar0;                                // snptracker == 0 also for skipped SNPs (:803-805)
+        NnzSnp = m - (int)fold_snp_num[0];                       // :806
+        varg = (so.varg_acc + s2varg_ * dfvara_) / hb_draw_chisq(KEY, HB_DOM_ITER, it, HB_IT_VARG, 0, dfvara_ + NnzSnp);  // :807
+        for (int j = 0; j < n_fold; ++j) vara_fold[j] = varg * fold_[j];
+        fold_snp_num[0] -= nvar0;                                // :813
+        break;
+    }
+    if ((model_index == 3 || model_index == 4 || model_index == 6) && !fixpi) {  // rdirichlet_sample, stats.cpp:69-76
+      for (int j = 0; j < n_fold; ++j)
+        Pi[j] = hb_draw_gamma(KEY, HB_DOM_ITER, it, HB_IT_PI0 + (uint32_t)j, 0, fold_snp_num[j] + 1);
+      const double tot = acc_sum(Pi.data(), n_fold);
+      for (int j = 0; j < n_fold; ++j) Pi[j] /= tot;
+    }
+    sum_r = so.sum_r; sum_r2 = so.sum_r2;
+    vara_ = so.var_u;                                                                                    // :819
+    vare_ = (so.sum_r2 + s2vare_ * dfvare_) / hb_draw_chisq(KEY, HB_DOM_ITER, it, HB_IT_VARE, 0, n + dfvare_);  // :823
+
+    if (o->nnz_trace) o->nnz_trace[iter] = NnzSnp;
+    if (o->vara_trace) o->vara_trace[iter] = vara_;
+    if (o->vare_trace) o->vare_trace[iter] = vare_;
+    if (o->varg_trace) o->varg_trace[iter] = varg;
+
+    if (iter >= nburn) {  // :826-845
+      if (have_tracker || a->windindx) HBCHK(hb_engine_accumulate_pip(E));
+      nzct++;
+    }
+    if (iter >= nburn && (iter + 1 - nburn) % thin == 0) {  // :848-882
+      musum += mu;
+      if (o->mu_store) o->mu_store[count] = mu;
+      if (!fixpi) {
+        for (int j = 0; j < n_fold; ++j) pisum[j] += Pi[j];
+        if (o->pi_store) for (int j = 0; j < n_fold; ++j) o->pi_store[(size_t)count * n_fold + j] = Pi[j];
+      }
+      varasum += vara_; varesum += vare_;
+      if (o->vara_store) o->vara_store[count] = vara_;
+      if (o->vare_store) o->vare_store[count] = vare_;
+      HBCHK(hb_engine_accumulate_effects(E));
+      if (o->alpha_store) HBCHK(hb_engine_get_effects(E, o->alpha_store + (size_t)count * m));
+      for (int i = 0; i < nc; ++i) betasum[i] += beta[i];
+      if (nc && o->beta_store) memcpy(o->beta_store + (size_t)count * nc, beta.data(), sizeof(double) * nc);
+      double vt = vara_ + vare_;
+      for (int i = 0; i < nr; ++i) { vt += vrv[i]; vrsum[i] += vrv[i]; }
+      for (int q = 0; q < n_levels; ++q) estRsum[q] += estR[q];
+      if (ne) {
+        vepssum += veps; Jsum += epsl_J_beta;
+        for (int q = 0; q < qe; ++q) e_sum[q] += e_estR[q];
+      }
+      hsqsum += vara_ / vt;
+      if (o->hsq_store) o->hsq_store[count] = vara_ / vt;
+      count++;
+    }
+    if (a->verbose && a->outfreq > 0 && (iter + 1) % a->outfreq == 0) {  // :884-914 (abridged)
+      printf(" %d %d ", iter + 1, NnzSnp);
+      for (int j = 0; j < n_fold; ++j) printf("%.4f ", Pi[j]);
+      printf("%.4f %.4f %.4f\n", vara_, vare_, vara_ / (vara_ + vare_));
+    }
+    if (count == n_records) { ++iter; break; }  // :916
+  }
+  o->iters_done = iter;
+  o->n_records_done = count;
+  o->nzct = nzct;
+  o->seconds_sweep = t_sweep;
+
+  // ---- posterior summaries :919-1040
+  const double rc = (double)count;
+  o->Vg = varasum / rc; o->Ve = varesum / rc; o->h2 = hsqsum / rc;
+  const double Mu = musum / rc;
+  o->mu = Mu;
+  std::vector<double> alpha(m, 0.0);
+  HBCHK(hb_engine_get_effect_sums(E, alpha.data()));
+  for (int i = 0; i < m; ++i) alpha[i] /= rc;
+  if (o->alpha) memcpy(o->alpha, alpha.data(), sizeof(double) * m);
+  if (o->e) {
+    std::vector<double> xg(n);
+    HBCHK(hb_engine_predict(E, alpha.data(), xg.data()));
+    for (int i = 0; i < n; ++i) o->e[i] = a->y[i] - Mu * 1.0;
+    for (int i = 0; i < nc; ++i) {
+      const double b = betasum[i] / rc;
+      for (int k = 0; k < n; ++k) o->e[k] -= a->C[(size_t)i * n + k] * b;
+    }
+    for (int i = 0; i < n; ++i) o->e[i] -= xg[i];
+  }
+  if (o->beta) for (int i = 0; i < nc; ++i) o->beta[i] = betasum[i] / rc;
+  if (o->pi) {
+    if (!fixpi) for (int j = 0; j < n_fold; ++j) o->pi[j] = pisum[j] / rc;
+    else for (int j = 0; j < n_fold; ++j) o->pi[j] = Pi[j];
+  }
+  if (fixpi && o->pi_store)
+    for (int c = 0; c < count; ++c) { o->pi_store[(size_t)c * n_fold] = Pi[0]; o->pi_store[(size_t)c * n_fold + 1] = Pi[1]; }
+  if (ne) {
+    o->Veps = vepssum / rc; o->J = Jsum / rc;
+    if (o->e) {
+      for (int k = 0; k < n; ++k) o->e[k] -= o->J * a->epsl_y_J[k];
+      for (int i = 0; i < ne; ++i) o->e[n - ne + i] -= e_sum[a->epsl_index[i] - 1] / rc;
+    }
+    if (o->epsilon) for (int q = 0; q < qe; ++q) o->epsilon[q] = e_sum[q] / rc;
+  }
+  if (nr) {
+    for (int i = 0; i < nr; ++i) if (o->vr) o->vr[i] = vrsum[i] / rc;
+    for (int q = 0; q < n_levels; ++q) estRsum[q] /= rc;
+    if (o->estR) memcpy(o->estR, estRsum.data(), sizeof(double) * n_levels);
+    if (o->e)
+      for (int i = 0; i < nr; ++i)
+        for (int k = 0; k < n; ++k) o->e[k] -= estRsum[R_off[i] + a->Rlev[(size_t)i * n + k]];
+  }
+  if (o->g) HBCHK(hb_engine_get_u(E, o->g));  // the reference returns u as "g" (:1023)
+  std::vector<double> nzrate(m, 0.0), wppa(nw, 0.0);
+  HBCHK(hb_engine_get_pip_counts(E, nzrate.data(), nw ? wppa.data() : nullptr, nw));
+  if (o->nzrate_count) memcpy(o->nzrate_count, nzrate.data(), sizeof(double) * m);
+  if (o->tracker_final) HBCHK(hb_engine_get_tracker(E, o->tracker_final));
+  if (o->pip) {  // :1026-1032
+    if (!have_tracker) for (int i = 0; i < m; ++i) o->pip[i] = 1.0;
+    else for (int i = 0; i < m; ++i) {
+      double r = nzrate[i] / nzct;
+      if (r == 1) r = (nzct - 1) / (double)nzct;
+      o->pip[i] = r;
+    }
+  }
+  if (nw) {
+    if (o->wppa_count) memcpy(o->wppa_count, wppa.data(), sizeof(double) * nw);
+    if (o->gwas) for (int w = 0; w < nw; ++w) {
+      double r = wppa[w] / nzct;
+      if (r == 1) r = (nzct - 1) / (double)nzct;
+      o->gwas[w] = r;
+    }
+  }
+  return 0;
+}

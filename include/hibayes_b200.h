@@ -1,0 +1,177 @@
+/*
+ * hibayes_b200.h -- C ABI of the B200-native single-site Gibbs engine that replaces the
+ * per-SNP sweep of hibayes' Bayes() / SBayesD() / SBayesS().
+ *
+ * Two layers, both plain C (pointers + sizes, caller-owned memory, int status codes,
+ * nothing thrown across the boundary; hb_last_error() gives the message):
+ *
+ *   1. hb_bayes()        -- drop-in for the body of  Rcpp::List Bayes(...)
+ *                           (/root/reference/src/Bayes.cpp:60-88 signature, :919-1040 return
+ *                           list).  The Rcpp shim _hibayes_Bayes (src/RcppExports.cpp:16-50)
+ *                           unpacks its 27 SEXPs exactly as today and forwards plain pointers;
+ *                           see INTEGRATION.md for the stub.
+ *   2. hb_engine_*()     -- the device engine the host driver is written against: load the
+ *                           genotype matrix once, then one hb_engine_sweep() per MCMC iteration
+ *                           replaces the switch(model_index) block Bayes.cpp:586-816 and the
+ *                           reductions at :480,:819,:823; non-SNP effects stay on the host and
+ *                           exchange the residual through hb_engine_{get,set}_residual().
+ *
+ * All functions return 0 on success.  A handle is not thread-safe; calls are synchronous.
+ */
+#ifndef HIBAYES_B200_H
+#define HIBAYES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_MAX_FOLD 8
+
+/* model_index as decoded at Bayes.cpp:97 / SBayesD.cpp:28 */
+enum {
+  HB_MODEL_RR = 1, HB_MODEL_A = 2, HB_MODEL_B = 3, HB_MODEL_C = 4, HB_MODEL_L = 5, HB_MODEL_R = 6
+};
+
+const char* hb_last_error(void);
+/* number of CUDA devices visible; <0 on driver error */
+int hb_device_count(void);
+
+/* ------------------------------------------------------------------ engine layer */
+typedef struct hb_engine hb_engine;
+
+typedef struct {
+  int device;        /* CUDA ordinal */
+  int n;             /* individuals held by this engine (rows of X, y) */
+  int m;             /* SNPs (columns of X) */
+  int tile_snps;     /* B: SNPs per tile step; 0 = default (64) */
+  int lag_tiles;     /* D: tiles in flight between a dot and its residual update; 0 = default */
+  int n_slabs;       /* row slabs = streaming CTAs; 0 = default (SM count - 1, fewer for small n) */
+  uint64_t seed;     /* Philox run key (hb_rng.h) */
+  /* row sharding across ranks (one engine per GPU); world = 1 for a single GPU */
+  int rank, world;
+} hb_engine_config;
+
+int hb_engine_create(const hb_engine_config* cfg, hb_engine** out);
+void hb_engine_destroy(hb_engine* e);
+
+/* Genotypes: column-major n x m host matrix, leading dimension ld (>= n), values {0,1,2}
+ * (what read_bed.cpp:116-120 produces after imputation).  Borrowed for the call only.
+ * Replaces the `arma::mat& X` argument, Bayes.cpp:62.  _f64 accepts the R numeric matrix. */
+int hb_engine_load_geno_i8(hb_engine* e, const int8_t* X, size_t ld);
+int hb_engine_load_geno_f64(hb_engine* e, const double* X, size_t ld);
+/* Synthetic genotypes generated on the device: p_j ~ U(0.05,0.5),
+ * x_ij ~ Binomial(2,p_j), addressed by (seed, global row, column) so that any row sharding
+ * yields the same matrix; row_offset is this rank's first global row.
+ * hb_synth_geno_host() writes the same matrix on the host (column-major int8). */
+int hb_engine_synth_geno(hb_engine* e, uint64_t seed, int64_t row_offset);
+int hb_synth_geno_host(int8_t* X, int n, int m, uint64_t seed, int64_t row_offset);
+
+/* Column statistics, Bayes.cpp:310-317: xpx_j = sum x^2, sumx_j = sum x (exact integers
+ * returned as doubles; the caller forms var(x_j)).  Local rows only when world > 1. */
+int hb_engine_col_stats(hb_engine* e, double* xpx, double* sumx);
+/* Marks SNPs the sweep skips (vx == 0, Bayes.cpp:589) and sets the global xpx. */
+int hb_engine_set_snp_info(hb_engine* e, const double* xpx_global, const uint8_t* active);
+/* One-off band Gram blocks X_t' [X_t .. X_{t+D-1}] (exact int32) used to chain the tiles. */
+int hb_engine_build_gram(hb_engine* e);
+
+int hb_engine_set_residual(hb_engine* e, const double* yadj); /* n doubles */
+int hb_engine_get_residual(hb_engine* e, double* yadj);
+int hb_engine_set_u(hb_engine* e, const double* u);
+int hb_engine_get_u(hb_engine* e, double* u);
+int hb_engine_set_effects(hb_engine* e, const double* g);      /* m doubles */
+int hb_engine_get_effects(hb_engine* e, double* g);
+int hb_engine_get_tracker(hb_engine* e, int32_t* tracker);     /* m, class label per SNP */
+int hb_engine_set_vargL(hb_engine* e, const double* vargL);    /* BayesL per-SNP variances */
+
+typedef struct {
+  int iter;                    /* MCMC iteration (draw address) */
+  int model_index;             /* HB_MODEL_* */
+  int n_fold;                  /* mixture components (2 for B/C, F for R) */
+  double fold[HB_MAX_FOLD];    /* BayesR fold_ (Bayes.cpp:108-114) */
+  double logpi[HB_MAX_FOLD];   /* log(Pi) */
+  double vara_fold[HB_MAX_FOLD]; /* BayesR: varg*fold_k; C/RR: [1] = varg */
+  double vare;                 /* residual variance */
+  double dfvara, s2varg;       /* per-SNP inv-chi^2 prior (BayesA/B, :613,:636) */
+  double lambda, lambda2;      /* BayesL (:729) */
+  double mu_shift;             /* added to every residual entry before the sweep (:482) */
+  double rnorm2_bound;         /* >= yadj'yadj at sweep start; sizes the fixed-point dot scale */
+} hb_sweep_in;
+
+typedef struct {
+  double count[HB_MAX_FOLD];   /* SNPs per class after the sweep (fold_snp_num, :803-805) */
+  double varg_acc;             /* model 4: sum g^2 (:698); 6: sum g^2/fold (:791); 1: g'g (:603) */
+  double sum_vargL;            /* model 5: sum(vargL) (:739) */
+  double sum_r, sum_r2;        /* sum(yadj), yadj'yadj (:480,:823) */
+  double sum_u, var_u;         /* var(u) with n-1 (:819) */
+  int n_changed;               /* SNPs whose effect changed (= residual updates applied) */
+  int status;                  /* 0 ok; else device-side abort code */
+} hb_sweep_out;
+
+int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out* out);
+
+/* PIP / WPPA counters on the device, Bayes.cpp:826-845 (windindx 1-based, 0/NULL = none) */
+int hb_engine_set_windows(hb_engine* e, const int32_t* windindx);
+int hb_engine_accumulate_pip(hb_engine* e);
+int hb_engine_get_pip_counts(hb_engine* e, double* nzrate, double* wppa, int nw);
+/* running sum of g over recorded iterations (posterior mean of alpha, :970) */
+int hb_engine_accumulate_effects(hb_engine* e);
+int hb_engine_get_effect_sums(hb_engine* e, double* gsum);
+
+/* out[i] = sum_j X[i][j] * alpha[j] over the resident genotypes (the X*g of Bayes.cpp:971) */
+int hb_engine_predict(hb_engine* e, const double* alpha, double* out);
+
+/* timing of the last sweep's kernels in ms (prep, sweep, tail) measured with CUDA events */
+int hb_engine_last_sweep_ms(hb_engine* e, float* prep_ms, float* sweep_ms, float* tail_ms);
+/* description of the layout chosen: slabs, rows per slab, tile, lag, bytes of X on device */
+int hb_engine_describe(hb_engine* e, int* n_slabs, int* rows_per_slab, int* tile_snps, int* lag_tiles,
+                       uint64_t* geno_bytes, uint64_t* gram_bytes);
+
+/* ------------------------------------------------------------------ host driver layer */
+#define HB_NA (__builtin_nan(""))
+
+typedef struct {
+  int n, m;
+  const double* y;          /* n                                   (arma::vec& y) */
+  const void* X;            /* n x m column-major                  (arma::mat& X) */
+  int x_type;               /* 0: double, 1: int8 */
+  const char* model;        /* std::string model */
+  int n_fold;
+  const double* Pi;         /* arma::vec Pi */
+  const double* fold;       /* Nullable<arma::vec> fold, NULL = R_NilValue */
+  int nc; const double* C;  /* Nullable<arma::mat> C, n x nc column-major */
+  int nr; const int32_t* Rlev; const int32_t* nlev; /* Nullable<CharacterMatrix> R as 0-based level codes */
+  int niter, nburn, thin;
+  double dfvr, s2vr, vg, dfvg, s2vg, ve, dfve, s2ve; /* Nullable<double>: NaN = R_NilValue */
+  const int32_t* windindx;  /* Nullable<arma::uvec>, 1-based, m entries */
+  int outfreq; int verbose;
+  uint64_t seed;            /* derived by the Rcpp shim from R's RNG state */
+  /* single-step term: epsl_y_J, epsl_Gi (CSC), epsl_index (1-based) */
+  int ne, qe;
+  const double* epsl_y_J; const int32_t* epsl_index;
+  const int32_t* Gi_colptr; const int32_t* Gi_rowidx; const double* Gi_val;
+  /* engine knobs (0 = defaults) */
+  int device, tile_snps, lag_tiles, n_slabs;
+} hb_bayes_args;
+
+typedef struct {
+  double Vg, Ve, h2, mu, Veps, J;
+  double* beta; double* alpha; double* pi; double* pip; double* gwas;
+  double* g; double* e; double* vr; double* estR; double* epsilon;
+  double* mu_store; double* vara_store; double* vare_store; double* hsq_store;
+  double* pi_store; double* alpha_store; double* beta_store;
+  int32_t* tracker_final; double* nzrate_count; double* wppa_count;
+  int32_t* nnz_trace; double* vara_trace; double* vare_trace; double* varg_trace;
+  int n_records_done, nzct, iters_done;
+  double seconds_sweep;     /* device time inside hb_engine_sweep, seconds */
+  double seconds_setup;     /* load + stats + gram */
+} hb_bayes_out;
+
+int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIBAYES_B200_H */
