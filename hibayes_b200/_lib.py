@@ -10,7 +10,7 @@ MAX_FOLD = 8
 SYMBOLS = [
     "hb_last_error", "hb_device_count", "hb_engine_create", "hb_engine_destroy", "hb_engine_load_geno_i8",
     "hb_engine_load_geno_f64", "hb_engine_synth_geno", "hb_synth_geno_host", "hb_engine_col_stats",
-    "hb_engine_set_snp_info", "hb_engine_build_gram", "hb_engine_set_residual", "hb_engine_get_residual",
+    "hb_engine_set_snp_info", "hb_engine_build_gram", "hb_engine_get_gram", "hb_engine_set_residual", "hb_engine_get_residual",
     "hb_engine_set_u", "hb_engine_get_u", "hb_engine_set_effects", "hb_engine_get_effects", "hb_engine_get_tracker",
     "hb_engine_set_vargL", "hb_engine_sweep", "hb_engine_set_windows", "hb_engine_accumulate_pip",
     "hb_engine_get_pip_counts", "hb_engine_accumulate_effects", "hb_engine_get_effect_sums", "hb_engine_predict",
@@ -96,6 +96,7 @@ def load_library():
     L.hb_engine_col_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_engine_set_snp_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_engine_build_gram.argtypes = [C.c_void_p]
+    L.hb_engine_get_gram.argtypes = [C.c_void_p, C.c_void_p]
     for f in ("set_residual", "get_residual", "set_u", "get_u", "set_effects", "get_effects", "get_tracker", "set_vargL",
               "get_effect_sums", "set_windows"):
         getattr(L, "hb_engine_" + f).argtypes = [C.c_void_p, C.c_void_p]

@@ -196,6 +196,14 @@ class Engine:
     def build_gram(self):
         _lib.check(self.L.hb_engine_build_gram(self.h))
 
+    def get_gram(self):
+        d = self.describe()
+        B, D = d["tile_snps"], d["lag_tiles"]
+        T = (self.m + B - 1) // B
+        out = np.zeros((T, D, B, B), dtype=np.int32)
+        _lib.check(self.L.hb_engine_get_gram(self.h, out.ctypes.data))
+        return out
+
     def _set(self, name, arr, dtype=np.float64):
         arr = np.ascontiguousarray(arr, dtype=dtype)
         _lib.check(getattr(self.L, "hb_engine_" + name)(self.h, arr.ctypes.data))

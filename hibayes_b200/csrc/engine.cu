@@ -248,6 +248,107 @@ __global__ void __launch_bounds__(256) k_gram_dp4a(const uint8_t* __restrict__ X
     for (int k = 0; k < 4; ++k) out[(size_t)(a0 + ty * 4 + i) * B + (b0 + tx + 16 * k)] = (int32_t)acc[i][k];
 }
 
+// v2: the same band Gram on the integer tensor-core path (mma.sync m16n8k32 u8 -> s32, exact).
+// This is the one dense contraction of the code base (SURVEY.md K6 / tXXmat family); it runs once
+// per data set.  CTA = 64x64 outputs of block (t, dt), 4 warps of 32x32; rows staged 128 at a
+// time through a double-buffered cp.async pipeline; fragments come from ldmatrix.
+constexpr int GI_RK = 128;            // rows (bytes) per stage
+constexpr int GI_STRIDE = GI_RK + 16; // padded row stride: conflict-free ldmatrix
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const uint32_t d = hb::smem_u32(dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(hb::smem_u32(p)));
+}
+__device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(128) k_gram_imma(const uint8_t* __restrict__ Xp, int32_t* __restrict__ gram, int S, int R,
+                                                   int T, int B, int D, int t_base) {
+  __shared__ __align__(16) uint8_t As[2][64 * GI_STRIDE];
+  __shared__ __align__(16) uint8_t Bs[2][64 * GI_STRIDE];
+  const int t = t_base + blockIdx.z;
+  const int nb = B / 64;
+  const int a0 = (blockIdx.y % nb) * 64;
+  const int dt = blockIdx.x / nb, b0 = (blockIdx.x % nb) * 64;
+  const int t2 = t + dt;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  int acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[i][j][k] = 0;
+  int32_t* out = gram + (((size_t)t * D + dt) * B) * B;
+  if (t2 < T) {
+    const int cps = (R + GI_RK - 1) / GI_RK;  // chunks per slab
+    const int nchunks = S * cps;
+    auto issue = [&](int ch, int buf) {
+      const int s = ch / cps, r0 = (ch % cps) * GI_RK;
+      const uint8_t* Abase = Xp + (((size_t)s * T + t) * B + a0) * R + r0;
+      const uint8_t* Bbase = Xp + (((size_t)s * T + t2) * B + b0) * R + r0;
+      // 64 columns x 8 vectors of 16 B per operand = 512 vectors; 128 threads -> 4 + 4 each
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int v = tid + 128 * q;
+        const int c = v >> 3, w = v & 7;
+        const bool ok = r0 + 16 * w < R;
+        cp_async16(&As[buf][c * GI_STRIDE + 16 * w], Abase + (size_t)c * R + (ok ? 16 * w : 0), ok);
+        cp_async16(&Bs[buf][c * GI_STRIDE + 16 * w], Bbase + (size_t)c * R + (ok ? 16 * w : 0), ok);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int buf = ch & 1;
+      if (ch + 1 < nchunks) {
+        issue(ch + 1, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+#pragma unroll
+      for (int ks = 0; ks < GI_RK / 32; ++ks) {
+        uint32_t af[2][4], bf[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int row = wm + 16 * i + (lane & 7) + 8 * ((lane >> 3) & 1);
+          ldmatrix_x4(af[i], &As[buf][row * GI_STRIDE + 32 * ks + 16 * (lane >> 4)]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int row = wn + 16 * j + (lane & 7) + 8 * (lane >> 4);
+          ldmatrix_x4(bf[j], &Bs[buf][row * GI_STRIDE + 32 * ks + 16 * ((lane >> 3) & 1)]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) imma_16832(acc[i][j], af[i], bf[j >> 1][2 * (j & 1)], bf[j >> 1][2 * (j & 1) + 1]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int row = a0 + wm + 16 * i + (lane >> 2);
+      const int col = b0 + wn + 8 * j + 2 * (lane & 3);
+      *(int2*)&out[(size_t)row * B + col] = make_int2(acc[i][j][0], acc[i][j][1]);
+      *(int2*)&out[(size_t)(row + 8) * B + col] = make_int2(acc[i][j][2], acc[i][j][3]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // per-sweep preparation: everything about SNP j that does not depend on the residual
 // ------------------------------------------------------------------------------------------
@@ -1105,7 +1206,8 @@ extern "C" int hb_engine_build_gram(hb_engine* e) {
   for (int t0 = 0; t0 < e->T; t0 += 65535) {
     const int nt = std::min(65535, e->T - t0);
     dim3 grid(e->D * nb, nb, nt);
-    k_gram_dp4a<<<grid, 256, 0, e->stream>>>(e->Xp, e->gram, e->S, e->R, e->T, e->B, e->D, t0);
+    if (getenv("HB_GRAM_DP4A")) k_gram_dp4a<<<grid, 256, 0, e->stream>>>(e->Xp, e->gram, e->S, e->R, e->T, e->B, e->D, t0);
+    else k_gram_imma<<<grid, 128, 0, e->stream>>>(e->Xp, e->gram, e->S, e->R, e->T, e->B, e->D, t0);
     CU(cudaGetLastError());
   }
   CU(cudaStreamSynchronize(e->stream));
@@ -1278,6 +1380,14 @@ extern "C" int hb_engine_accumulate_effects(hb_engine* e) {
   CU(cudaSetDevice(e->cfg.device));
   k_axpy1<<<(e->m + 255) / 256, 256, 0, e->stream>>>(e->m, e->g, e->gsum);
   CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int hb_engine_get_gram(hb_engine* e, int32_t* out) {
+  if (!e || !out) return hb_set_error("hb_engine_get_gram: null argument");
+  if (!e->gram_ready) return hb_set_error("hb_engine_get_gram: gram not built");
+  CU(cudaSetDevice(e->cfg.device));
+  CU(cudaMemcpy(out, e->gram, (size_t)e->T * e->D * e->B * e->B * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 

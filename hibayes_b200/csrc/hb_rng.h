@@ -234,12 +234,17 @@ HB_HD double hb_draw_chisq(hb_key_t key, uint32_t domain, uint32_t iter, uint32_
   return 2.0 * hb_draw_gamma(key, domain, iter, index, slot, 0.5 * df);
 }
 
-/* inverse-Gaussian(mu, lambda) from one (U,Z) pair  (stats.cpp:55-67) */
+/* inverse-Gaussian(mu, lambda) from one (U,Z) pair  (stats.cpp:55-67).  The reference's formula
+ * cancels catastrophically for large mu, so it is evaluated with explicit, unfused operations:
+ * host and device then round identically. */
 HB_HD double hb_invgauss_from_uz(double mu, double lambda, double u, double z) {
-  double y = z * z;
-  double x = mu + 0.5 * mu * mu * y / lambda -
-             0.5 * (mu / lambda) * sqrt(4.0 * mu * lambda * y + mu * mu * y * y);
-  return (u <= mu / (mu + x)) ? x : (mu * mu / x);
+  double y = HB_MUL(z, z);
+  double mu2 = HB_MUL(mu, mu);
+  double t1 = HB_MUL(HB_MUL(0.5, mu2), y) / lambda;                      /* 0.5*mu*mu*y/lambda */
+  double rad = HB_ADD(HB_MUL(HB_MUL(HB_MUL(4.0, mu), lambda), y), HB_MUL(HB_MUL(mu2, y), y));
+  double t2 = HB_MUL(HB_MUL(0.5, mu / lambda), sqrt(rad));
+  double x = HB_ADD(HB_ADD(mu, t1), -t2);
+  return (u <= mu / HB_ADD(mu, x)) ? x : (mu2 / x);
 }
 
 #endif /* HB_RNG_H */

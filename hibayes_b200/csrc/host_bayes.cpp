@@ -447,7 +447,10 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
   std::vector<double> nzrate(m, 0.0), wppa(nw, 0.0);
   HBCHK(hb_engine_get_pip_counts(E, nzrate.data(), nw ? wppa.data() : nullptr, nw));
   if (o->nzrate_count) memcpy(o->nzrate_count, nzrate.data(), sizeof(double) * m);
-  if (o->tracker_final) HBCHK(hb_engine_get_tracker(E, o->tracker_final));
+  if (o->tracker_final) {
+    if (have_tracker) HBCHK(hb_engine_get_tracker(E, o->tracker_final));
+    else memset(o->tracker_final, 0, sizeof(int32_t) * m);  // BayesRR/A/L keep no snptracker (:288-296)
+  }
   if (o->pip) {  // :1026-1032
     if (!have_tracker) for (int i = 0; i < m; ++i) o->pip[i] = 1.0;
     else for (int i = 0; i < m; ++i) {

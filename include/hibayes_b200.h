@@ -76,6 +76,8 @@ int hb_engine_col_stats(hb_engine* e, double* xpx, double* sumx);
 int hb_engine_set_snp_info(hb_engine* e, const double* xpx_global, const uint8_t* active);
 /* One-off band Gram blocks X_t' [X_t .. X_{t+D-1}] (exact int32) used to chain the tiles. */
 int hb_engine_build_gram(hb_engine* e);
+/* copies the band out: int32 [tiles][lag][tile_snps][tile_snps] (tests, diagnostics) */
+int hb_engine_get_gram(hb_engine* e, int32_t* out);
 
 int hb_engine_set_residual(hb_engine* e, const double* yadj); /* n doubles */
 int hb_engine_get_residual(hb_engine* e, double* yadj);
