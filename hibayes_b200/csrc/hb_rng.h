@@ -234,17 +234,29 @@ HB_HD double hb_draw_chisq(hb_key_t key, uint32_t domain, uint32_t iter, uint32_
   return 2.0 * hb_draw_gamma(key, domain, iter, index, slot, 0.5 * df);
 }
 
-/* inverse-Gaussian(mu, lambda) from one (U,Z) pair  (stats.cpp:55-67).  The reference's formula
- * cancels catastrophically for large mu, so it is evaluated with explicit, unfused operations:
- * host and device then round identically. */
+/* inverse-Gaussian(mu, lambda) from one (U,Z) pair  (stats.cpp:55-67).
+ * The reference writes the smaller root of the Michael-Schucany-Haas quadratic as
+ *     x = mu + 0.5*mu*mu*y/lambda - (0.5*mu/lambda)*sqrt(4*mu*lambda*y + mu*mu*y*y),   y = z*z,
+ * which cancels catastrophically once w = mu*y/(2*lambda) >> 1 (BayesL reaches w ~ 1e5 through the
+ * |g| >= 1e-6 clamp, Bayes.cpp:728): one ulp on mu then moves x by ~1e-6 and no two BLAS builds of
+ * the reference agree with each other.  With  (1+w)^2 - (w^2+2w) = 1  the same root is
+ *     x = mu * (1 + w - sqrt(w*w + 2*w)) = mu / (1 + w + sqrt(w*(w+2))),
+ * algebraically identical and well conditioned; oracle and device both use this form (the
+ * accept/flip step `u <= mu/(mu+x) ? x : mu*mu/x` is the reference's, stats.cpp:60-66).
+ * Explicit unfused operations keep host and device rounding identical. */
 HB_HD double hb_invgauss_from_uz(double mu, double lambda, double u, double z) {
   double y = HB_MUL(z, z);
-  double mu2 = HB_MUL(mu, mu);
-  double t1 = HB_MUL(HB_MUL(0.5, mu2), y) / lambda;                      /* 0.5*mu*mu*y/lambda */
-  double rad = HB_ADD(HB_MUL(HB_MUL(HB_MUL(4.0, mu), lambda), y), HB_MUL(HB_MUL(mu2, y), y));
-  double t2 = HB_MUL(HB_MUL(0.5, mu / lambda), sqrt(rad));
-  double x = HB_ADD(HB_ADD(mu, t1), -t2);
-  return (u <= mu / HB_ADD(mu, x)) ? x : (mu2 / x);
+  double w = HB_MUL(mu, y) / HB_MUL(2.0, lambda);
+  double root = sqrt(HB_MUL(w, HB_ADD(w, 2.0)));
+  double x = mu / HB_ADD(HB_ADD(1.0, w), root);
+  return (u <= mu / HB_ADD(mu, x)) ? x : (HB_MUL(mu, mu) / x);
+}
+
+/* the reference's literal expression (stats.cpp:57-59), kept for the tests that show the two forms
+ * agree wherever the literal one is well conditioned */
+HB_HD double hb_invgauss_literal_root(double mu, double lambda, double z) {
+  double y = z * z;
+  return mu + 0.5 * mu * mu * y / lambda - (0.5 * mu / lambda) * sqrt(4.0 * mu * lambda * y + mu * mu * y * y);
 }
 
 #endif /* HB_RNG_H */

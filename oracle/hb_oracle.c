@@ -97,6 +97,7 @@ void hbo_draw_uz(uint64_t seed, uint32_t dom, uint32_t iter, uint32_t idx, uint3
   hb_draw_uz(hb_make_key(seed), dom, iter, idx, slot, attempt, u, z);
 }
 double hbo_invgauss(double mu, double lambda, double u, double z) { return hb_invgauss_from_uz(mu, lambda, u, z); }
+double hbo_invgauss_literal_root(double mu, double lambda, double z) { return hb_invgauss_literal_root(mu, lambda, z); }
 
 /* column accessor: the reference holds X as arma::mat (fp64); an int8 source is
  * widened into a scratch column so the arithmetic is identical. */

@@ -98,6 +98,8 @@ double hbo_draw_gamma(uint64_t seed, uint32_t dom, uint32_t iter, uint32_t idx, 
 double hbo_draw_chisq(uint64_t seed, uint32_t dom, uint32_t iter, uint32_t idx, uint32_t slot, double df);
 void hbo_draw_uz(uint64_t seed, uint32_t dom, uint32_t iter, uint32_t idx, uint32_t slot, uint32_t attempt, double* u, double* z);
 double hbo_invgauss(double mu, double lambda, double u, double z);
+/* the reference's literal (cancelling) expression for the smaller root, stats.cpp:57-59 */
+double hbo_invgauss_literal_root(double mu, double lambda, double z);
 
 /* CPU timing of the reference's level-1 path: per-SNP ddot + 2 daxpy on a
  * column-major fp64 X (Bayes.cpp:756,787-789), `threads` OpenMP threads split

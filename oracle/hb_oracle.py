@@ -38,6 +38,8 @@ def lib():
                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]
         _LIB.hbo_invgauss.restype = C.c_double
         _LIB.hbo_invgauss.argtypes = [C.c_double] * 4
+        _LIB.hbo_invgauss_literal_root.restype = C.c_double
+        _LIB.hbo_invgauss_literal_root.argtypes = [C.c_double] * 3
         _LIB.hbo_time_sweep_fp64.restype = C.c_double
         _LIB.hbo_time_sweep_fp64.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_double)]
     return _LIB

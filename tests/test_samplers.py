@@ -74,6 +74,27 @@ def test_inverse_gaussian_distribution(oracle):
     assert stats.kstest(x, "invgauss", args=(mu / lam, 0, lam)).pvalue > 1e-3
 
 
+def test_inverse_gaussian_stable_form_equals_reference_expression(oracle):
+    """hb_rng.h evaluates the smaller root of stats.cpp:57-59 as mu/(1+w+sqrt(w(w+2))); where the
+    reference's own expression is well conditioned (w = mu*z^2/(2*lambda) <~ 1) the two agree to
+    rounding, and the stable form stays accurate where the literal one cancels."""
+    L = oracle.lib()
+    rng = np.random.default_rng(3)
+    for _ in range(2000):
+        mu, lam, z = rng.uniform(0.1, 3), rng.uniform(1, 50), rng.normal()
+        lit = L.hbo_invgauss_literal_root(mu, lam, z)
+        got = L.hbo_invgauss(mu, lam, 0.0, z)      # u = 0 always takes the root itself
+        assert abs(got / lit - 1) < 1e-12
+    # ill-conditioned corner reached through the |g| >= 1e-6 clamp of Bayes.cpp:728
+    from decimal import Decimal, getcontext
+    getcontext().prec = 60
+    mu, lam, z = 2.8e8, 800.0, 1.3
+    w = Decimal(mu) * Decimal(z) * Decimal(z) / (2 * Decimal(lam))
+    exact = Decimal(mu) / (1 + w + (w * (w + 2)).sqrt())
+    assert abs(Decimal(L.hbo_invgauss(mu, lam, 0.0, z)) / exact - 1) < Decimal(1e-14)
+    assert abs(Decimal(L.hbo_invgauss_literal_root(mu, lam, z)) / exact - 1) > Decimal(1e-9)
+
+
 def test_draws_are_position_addressed(oracle):
     L = oracle.lib()
     a = L.hbo_draw_chisq(5, 1, 2, 33, 0, 5.0)
