@@ -191,7 +191,7 @@ def run_gpu(args):
     for _ in range(args.warmup):
         step()
     # ---- device-timed region: K steps, inputs resident in HBM
-    dev_ms, sweep_ms, changed = [], [], []
+    dev_ms, sweep_ms, changed, rounds = [], [], [], []
     with ClockSampler(local_rank) as clk:
         for _ in range(args.steps):
             so = step()
@@ -199,6 +199,7 @@ def run_gpu(args):
             dev_ms.append(a + b + c)
             sweep_ms.append(b)
             changed.append(so["n_changed"])
+            rounds.append(so["rounds"])
     total_ms = float(sum(dev_ms))
     m_active = int(active.sum())
     value = m_active * args.steps / (total_ms * 1e-3)
@@ -221,7 +222,7 @@ def run_gpu(args):
         "config": {"workload": "ibrm() BayesR sweep, synthetic n=%d x m=%d int8 genotypes, 1 GPU" % (n_total, m),
                    "n": n_total, "m": m, "m_active": m_active, "Pi": PI0, "fold": FOLD,
                    "layout": desc, "l2": "inputs (%.1f GB) larger than L2" % (desc["geno_bytes"] / 1e9),
-                   "changed_snps_per_sweep": float(np.mean(changed)), "setup_s": t_setup, "gram_s": t_gram,
+                   "changed_snps_per_sweep": float(np.mean(changed)), "scalar_rounds_per_sweep": float(np.mean(rounds)), "setup_s": t_setup, "gram_s": t_gram,
                    "frac_of_8TBps": achieved / 8000.0},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "kernel": "k_sweep", "kernel_ms": kern_s * 1e3},

@@ -33,7 +33,7 @@ class SweepIn(C.Structure):
 class SweepOut(C.Structure):
     _fields_ = [("count", C.c_double * MAX_FOLD), ("varg_acc", C.c_double), ("sum_vargL", C.c_double),
                 ("sum_r", C.c_double), ("sum_r2", C.c_double), ("sum_u", C.c_double), ("var_u", C.c_double),
-                ("n_changed", C.c_int), ("status", C.c_int)]
+                ("n_changed", C.c_int), ("status", C.c_int), ("rounds", C.c_int), ("reserved", C.c_int)]
 
 
 class BayesArgs(C.Structure):

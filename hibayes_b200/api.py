@@ -243,7 +243,7 @@ class Engine:
         so = _lib.SweepOut()
         _lib.check(self.L.hb_engine_sweep(self.h, C.byref(si), C.byref(so)))
         return {"count": list(so.count), "varg_acc": so.varg_acc, "sum_vargL": so.sum_vargL, "sum_r": so.sum_r,
-                "sum_r2": so.sum_r2, "sum_u": so.sum_u, "var_u": so.var_u, "n_changed": so.n_changed, "status": so.status}
+                "sum_r2": so.sum_r2, "sum_u": so.sum_u, "var_u": so.var_u, "n_changed": so.n_changed, "status": so.status, "rounds": so.rounds}
 
     def last_sweep_ms(self):
         a, b, c = C.c_float(), C.c_float(), C.c_float()

@@ -33,6 +33,7 @@
 #include "../../include/hibayes_b200.h"
 #include "hb_device.cuh"
 #include "hb_rng.h"
+#include "hb_sweep.cuh"
 #include "hb_synth.h"
 
 // ------------------------------------------------------------------------------------------
@@ -64,21 +65,12 @@ extern "C" int hb_device_count(void) {
 // ------------------------------------------------------------------------------------------
 // engine state
 // ------------------------------------------------------------------------------------------
-struct SweepOutDev {
-  double count[HB_MAX_FOLD];
-  double varg_acc;
-  double sum_vargL;
-  double sum_r, sum_r2, sum_u, var_u;
-  int n_changed;
-  int status;
-};
-
 struct hb_engine {
   hb_engine_config cfg;
   int n, m, B, D, S, R, NRG, CL, T, m_pad, NS, nsm;
-  int NTC, NTCp, block_threads;
+  int NTC, NTCp, NCW, NAW, SUBB, Q, block_threads;
   size_t Npad, slab_stride, stage_bytes, smem_bytes;
-  size_t off_part, off_u, off_bar;
+  size_t off_part, off_rbuf, off_bar;
   uint8_t* Xp = nullptr;
   double *r = nullptr, *u = nullptr, *xpx = nullptr, *g = nullptr, *vargL = nullptr, *gsum = nullptr;
   double *nzrate = nullptr, *wppa = nullptr;
@@ -95,6 +87,8 @@ struct hb_engine {
   double* prm = nullptr;  // per-SNP sweep parameters, SoA
   int prm_fold = 0;
   SweepOutDev* out_dev = nullptr;
+  double* post_partial = nullptr;  // kPostBlocks x (HB_MAX_FOLD+1)
+  double* fold_dev = nullptr;      // HB_MAX_FOLD
   // windows (CSR)
   int nw = 0;
   int *wstart = nullptr, *wmem = nullptr;
@@ -103,8 +97,6 @@ struct hb_engine {
   float ms_prep = 0, ms_sweep = 0, ms_tail = 0;
 };
 
-static const double kScaleUp = 2.6815615859885194e154;   // 2^513
-static const double kScaleDn = 2.6815615859885194e154;   // partial = acc * 2^(1026-513)
 
 // ------------------------------------------------------------------------------------------
 // packing, synthetic data, column statistics
@@ -358,8 +350,6 @@ struct PrepParams {
   double vare, dfvara, s2varg;
   hb_key_t key;
 };
-// prm layout (SoA over m_pad): [0] u, [1] z, then for k = 1..F-1: a_k, c_k, v_k, sd_k
-__device__ __forceinline__ size_t prm_idx(int field, size_t m_pad, int j) { return (size_t)field * m_pad + j; }
 
 __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8_t* __restrict__ active,
                        const double* __restrict__ g, const double* __restrict__ vargL, double* __restrict__ prm,
@@ -368,7 +358,7 @@ __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) {
     ctrl[0] = 0; ctrl[1] = 0;
-    out->n_changed = 0; out->status = 0; out->varg_acc = 0; out->sum_vargL = 0;
+    out->n_changed = 0; out->status = 0; out->rounds = 0; out->varg_acc = 0; out->sum_vargL = 0;
     for (int k = 0; k < HB_MAX_FOLD; ++k) out->count[k] = 0;
   }
   if (j < p.T) arrive[j] = 0;
@@ -388,8 +378,8 @@ __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8
       int f = 2 + 4 * (k - 1);
       prm[prm_idx(f + 0, p.m_pad, j)] = -0.5 * log(vf * (xx / vare) + 1.0) + p.logpi[k];
       prm[prm_idx(f + 1, p.m_pad, j)] = 0.5 / (vare * v);
-      prm[prm_idx(f + 2, p.m_pad, j)] = v;
-      prm[prm_idx(f + 3, p.m_pad, j)] = sqrt(vare / v);
+      prm[prm_idx(f + 2, p.m_pad, j)] = 1.0 / v;
+      prm[prm_idx(f + 3, p.m_pad, j)] = sqrt(vare / v) * z;
     }
   } else {
     double varg = p.vara_fold[1];
@@ -403,445 +393,15 @@ __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8
     if (p.model == HB_MODEL_B || p.model == HB_MODEL_C) a = -0.5 * log(varg * (xx / vare) + 1.0) + p.logpi[1];
     prm[prm_idx(2, p.m_pad, j)] = a;
     prm[prm_idx(3, p.m_pad, j)] = 0.5 / (vare * v);
-    prm[prm_idx(4, p.m_pad, j)] = v;
-    prm[prm_idx(5, p.m_pad, j)] = sqrt(vare / v);
+    prm[prm_idx(4, p.m_pad, j)] = 1.0 / v;
+    prm[prm_idx(5, p.m_pad, j)] = sqrt(vare / v) * z;
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// the sweep kernel
-// ------------------------------------------------------------------------------------------
-struct SweepParams {
-  const uint8_t* Xp;
-  double *r, *u;
-  const double* xpx;
-  const uint8_t* active;
-  double* g;
-  int32_t* tracker;
-  const int32_t* gram;
-  unsigned long long* dacc;
-  unsigned int* arrive;
-  int* q_snp;
-  double* q_delta;
-  int* tile_qend;
-  int* ctrl;
-  const double* prm;
-  SweepOutDev* out;
-  size_t slab_stride, m_pad;
-  int n, m, S, R, NRG, CL, T, B, D, NS, NTC, NTCp;
-  uint32_t stage_bytes, off_part, off_u, off_bar;
-  int model, F;
-  double fold[HB_MAX_FOLD];
-  double logpi0;
-  double dscale, inv_dscale, mu_shift;
-  unsigned arrive_target;
-};
-
-enum { HB_ABORT_TIMEOUT_STREAM = 1, HB_ABORT_TIMEOUT_SCALAR = 2, HB_ABORT_TIMEOUT_TMA = 3, HB_ABORT_OVERFLOW = 4 };
-
-__device__ __forceinline__ bool spin_backoff(long long& spins, int* ctrl, int code) {
-  // returns false when the wait must be abandoned
-  ++spins;
-  if ((spins & 0x3f) == 0) {
-    __nanosleep(64);
-    if ((spins & 0xfff) == 0) {
-      if (*((volatile int*)(ctrl + 1)) != 0) return false;
-      if (spins > hb::kSpinLimit) {
-        atomicCAS(ctrl + 1, 0, code);
-        return false;
-      }
-    }
-  }
-  return true;
-}
-
-__device__ __forceinline__ double byte_as_scaled(uint32_t w, uint32_t sel) {
-  // genotype byte -> mantissa bits 48..55 of a double: value = byte * 2^-1026 (exact, denormal)
-  return __hiloint2double((int)__byte_perm(w, 0u, sel), 0);
-}
-
-__device__ void stream_role(const SweepParams& p, uint8_t* smem) {
-  const int tid = threadIdx.x;
-  const int s = blockIdx.x;
-  const int NS = p.NS, B = p.B, D = p.D, T = p.T, NRG = p.NRG, NTC = p.NTC, NTCp = p.NTCp, R = p.R;
-  uint8_t* stage0 = smem;
-  double* part = (double*)(smem + p.off_part);
-  double* us = (double*)(smem + p.off_u);
-  uint64_t* full = (uint64_t*)(smem + p.off_bar);
-  uint64_t* empty = full + NS;
-  volatile int* ready_tile = (volatile int*)(empty + NS);
-  volatile int* qend_ring = ready_tile + 1;
-  int* ctrl = p.ctrl;
-
-  if (tid == 0) {
-    for (int i = 0; i < NS; ++i) { hb::mbar_init(full + i, 1); hb::mbar_init(empty + i, 1); }
-    *ready_tile = -1;
-    hb::mbar_fence_init();
-  }
-  __syncthreads();
-  const uint8_t* Xs = p.Xp + (size_t)s * p.slab_stride;
-
-  // ---------------- poller warp: turns the scalar CTA's progress into a shared-memory flag
-  if (tid >= NTCp + 32) {
-    if (tid == NTCp + 32) {
-      long long spins = 0;
-      for (int t = 0; t < T + D; ++t) {
-        int qend = 0;
-        if (t >= D) {
-          const int need = t - D + 1;
-          while (hb::ld_acquire(ctrl) < need)
-            if (!spin_backoff(spins, ctrl, HB_ABORT_TIMEOUT_STREAM)) { *ready_tile = 1 << 30; return; }
-          qend = __ldcg(p.tile_qend + (t - D));
-        }
-        // do not run more than 8 tiles ahead of the compute threads' ring slot reuse:
-        // (t <= progress + D - 1 <= compute tile + D, ring has 16 slots, D <= 8)
-        qend_ring[t & 15] = qend;
-        __threadfence_block();
-        *ready_tile = t;
-      }
-    }
-    return;
-  }
-  // ---------------- producer warp: streams this slab's tiles through the TMA ring
-  if (tid >= NTCp) {
-    if (tid == NTCp) {
-      long long spins = 0;
-      for (int t = 0; t < T; ++t) {
-        const int st = t % NS;
-        if (t >= NS) {
-          const uint32_t par = (uint32_t)((t / NS - 1) & 1);
-          while (!hb::mbar_try_wait(empty + st, par))
-            if (!spin_backoff(spins, ctrl, HB_ABORT_TIMEOUT_TMA)) return;
-        }
-        hb::mbar_arrive_expect_tx(full + st, p.stage_bytes);
-        hb::tma_load_1d(stage0 + (size_t)st * p.stage_bytes, Xs + (size_t)t * p.stage_bytes, p.stage_bytes, full + st);
-      }
-    }
-    return;
-  }
-  // ---------------- compute threads
-  const bool live = tid < NTC;
-  const int rg = live ? (tid % NRG) : 0;
-  const int cl = live ? (tid / NRG) : 0;
-  const size_t row0 = (size_t)s * R + 16 * rg;
-  double rs[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    double v = 0.0;
-    if (live && row0 + i < (size_t)p.n) v = p.r[row0 + i] + p.mu_shift;
-    rs[i] = v * kScaleUp;
-  }
-  for (int i = tid; i < R; i += NTCp) us[i] = p.u[(size_t)s * R + i];
-  const int kmax = B / p.CL;
-  const int npub = min(B, NTCp);
-  int applied = 0;
-  long long spins = 0;
-  bool dead = false;
-
-  for (int t = 0; t < T + D; ++t) {
-    // 1. residual updates published by the scalar CTA for tiles <= t-D
-    if (t >= D && !dead) {
-      while (hb::ld_volatile_shared(ready_tile) < t)
-        if (!spin_backoff(spins, ctrl, HB_ABORT_TIMEOUT_STREAM)) { dead = true; break; }
-      if (*ready_tile == (1 << 30)) dead = true;
-    }
-    if (t >= D && !dead) {
-      const int qend = qend_ring[t & 15];
-      for (int q = applied; q < qend; q += 4) {
-        int js[4];
-        double dl[4];
-        uint4 xv[4];
-        const int nq = min(4, qend - q);
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (e < nq) {
-            js[e] = __ldcg(p.q_snp + q + e);
-            dl[e] = __ldcg(p.q_delta + q + e);
-          }
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (e < nq && live) {
-            const int tj = js[e] / B, cj = js[e] % B;
-            xv[e] = __ldg((const uint4*)(Xs + ((size_t)tj * B + cj) * R + 16 * rg));
-          }
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (e < nq && live) {
-            const uint32_t w[4] = {xv[e].x, xv[e].y, xv[e].z, xv[e].w};
-            const double dls = dl[e] * kScaleUp;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const double xd = (double)((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
-              rs[i] = fma(-xd, dls, rs[i]);                       // yadj -= x * delta  (Bayes.cpp:787)
-              if (cl == 0) us[16 * rg + i] = fma(xd, dl[e], us[16 * rg + i]);  // u += x * delta (:789)
-            }
-          }
-      }
-      applied = qend;
-    }
-    if (t >= T) {
-      if (hb::named_bar_or(1, NTCp, dead)) { dead = true; break; }
-      continue;
-    }
-    // 2. wait for the tile in the TMA ring
-    const int st = t % NS;
-    if (!dead) {
-      const uint32_t par = (uint32_t)((t / NS) & 1);
-      while (!hb::mbar_try_wait(full + st, par))
-        if (!spin_backoff(spins, ctrl, HB_ABORT_TIMEOUT_TMA)) { dead = true; break; }
-    }
-    // 3. partial dots of this slab: thread (rg, cl) handles rows 16rg..16rg+15 of columns cl, cl+CL, ...
-    double* pt = part + (size_t)(t & 1) * B * NRG;
-    if (live && !dead) {
-      const uint4* sp = (const uint4*)(stage0 + (size_t)st * p.stage_bytes);
-      for (int k = 0; k < kmax; ++k) {
-        const uint4 v = sp[tid + NTC * k];
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        a0 = fma(rs[0], byte_as_scaled(v.x, 0x4044), a0);
-        a1 = fma(rs[1], byte_as_scaled(v.x, 0x4144), a1);
-        a2 = fma(rs[2], byte_as_scaled(v.x, 0x4244), a2);
-        a3 = fma(rs[3], byte_as_scaled(v.x, 0x4344), a3);
-        a0 = fma(rs[4], byte_as_scaled(v.y, 0x4044), a0);
-        a1 = fma(rs[5], byte_as_scaled(v.y, 0x4144), a1);
-        a2 = fma(rs[6], byte_as_scaled(v.y, 0x4244), a2);
-        a3 = fma(rs[7], byte_as_scaled(v.y, 0x4344), a3);
-        a0 = fma(rs[8], byte_as_scaled(v.z, 0x4044), a0);
-        a1 = fma(rs[9], byte_as_scaled(v.z, 0x4144), a1);
-        a2 = fma(rs[10], byte_as_scaled(v.z, 0x4244), a2);
-        a3 = fma(rs[11], byte_as_scaled(v.z, 0x4344), a3);
-        a0 = fma(rs[12], byte_as_scaled(v.w, 0x4044), a0);
-        a1 = fma(rs[13], byte_as_scaled(v.w, 0x4144), a1);
-        a2 = fma(rs[14], byte_as_scaled(v.w, 0x4244), a2);
-        a3 = fma(rs[15], byte_as_scaled(v.w, 0x4344), a3);
-        pt[tid + NTC * k] = ((a0 + a1) + (a2 + a3)) * kScaleDn;
-      }
-    }
-    // 4. all compute threads are done with the stage and have written their partials; the
-    //    barrier also votes on `dead` so that an abort is taken by the whole CTA at once
-    if (hb::named_bar_or(1, NTCp, dead)) { dead = true; break; }
-    if (tid == 0) hb::mbar_arrive(empty + st);
-    // 5. fixed-order sum over row groups, then fixed-point accumulation in L2
-    if (tid < npub) {
-      for (int j = tid; j < B; j += NTCp) {
-        const double* pj = pt + (size_t)j * NRG;
-        double sum = 0.0;
-        for (int q = 0; q < NRG; ++q) sum += pj[q];
-        const double scaled = sum * p.dscale;
-        if (!(fabs(scaled) < 4.0e18)) atomicCAS(ctrl + 1, 0, HB_ABORT_OVERFLOW);
-        const long long fx = __double2ll_rn(scaled);
-        atomicAdd(p.dacc + (size_t)t * B + j, (unsigned long long)fx);
-      }
-      __syncwarp();
-      if ((tid & 31) == 0) {
-        __threadfence();
-        atomicAdd(p.arrive + t, 1u);
-      }
-    }
-  }
-  // write the slab back
-  if (!dead) {
-    hb::named_bar_sync(1, NTCp);
-    if (live && cl == 0) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) p.r[row0 + i] = rs[i] * (1.0 / kScaleUp);
-    }
-    for (int i = tid; i < R; i += NTCp) p.u[(size_t)s * R + i] = us[i];
-  }
-}
-
-// Conditional draw of one SNP given its right-hand side (Bayes.cpp:592-601, 639-664, 756-801).
-__device__ __forceinline__ void eval_snp(int model, int F, double rhs, const double* a, const double* c, const double* v,
-                                         const double* sd, double logpi0, double u, double z, int& cls, double& gnew) {
-  if (model == HB_MODEL_RR || model == HB_MODEL_A || model == HB_MODEL_L) {
-    cls = 1;
-    gnew = rhs / v[0] + sd[0] * z;
-    if (model == HB_MODEL_L && fabs(gnew) < 1e-6) gnew = 1e-6;  // :728
-    return;
-  }
-  double sv[HB_MAX_FOLD];
-  const double rr = rhs * rhs;
-  sv[0] = logpi0;
-  double smax = logpi0;
-#pragma unroll
-  for (int k = 1; k < HB_MAX_FOLD; ++k)
-    if (k < F) {
-      sv[k] = fma(rr, c[k - 1], a[k - 1]);
-      smax = fmax(smax, sv[k]);
-    }
-  double tot = 0.0;
-#pragma unroll
-  for (int k = 0; k < HB_MAX_FOLD; ++k)
-    if (k < F) {
-      sv[k] = exp(sv[k] - smax);
-      tot += sv[k];
-    }
-  const double inv = 1.0 / tot;
-  double acc = 0.0;
-  cls = 0;
-  bool found = false;
-#pragma unroll
-  for (int k = 0; k < HB_MAX_FOLD; ++k)
-    if (k < F && !found) {
-      acc += sv[k] * inv;
-      if (u < acc) { cls = k; found = true; }
-    }
-  gnew = 0.0;
-#pragma unroll
-  for (int k = 1; k < HB_MAX_FOLD; ++k)
-    if (k == cls) gnew = rhs / v[k - 1] + sd[k - 1] * z;
-}
-
-__device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
-  const int B = p.B, D = p.D, T = p.T, F = p.F, model = p.model;
-  const int i = threadIdx.x;
-  if (i >= B) return;
-  const int nwarp = B / 32, warp = i >> 5, lane = i & 31;
-  double* ring = (double*)smem;                         // D * B
-  double* chg_delta = ring + (size_t)D * B;             // B
-  double* cand_delta = chg_delta + B;                   // 2 * nwarp
-  double* red = cand_delta + 2 * 8;                     // B * (HB_MAX_FOLD + 1)
-  int* chg_a = (int*)(red + (size_t)B * (HB_MAX_FOLD + 1));  // B
-  int* cand_idx = chg_a + B;                            // 2 * nwarp
-  volatile int* s_abort = cand_idx + 16;
-  int* ctrl = p.ctrl;
-  for (int d = 0; d < D; ++d) ring[(size_t)d * B + i] = 0.0;
-  double cnt[HB_MAX_FOLD];
-#pragma unroll
-  for (int k = 0; k < HB_MAX_FOLD; ++k) cnt[k] = 0.0;
-  double vacc = 0.0;
-  int qbase = 0;
-  long long spins = 0;
-  const size_t mp = p.m_pad;
-  const bool mixture = (model == HB_MODEL_B || model == HB_MODEL_C || model == HB_MODEL_R);
-  const int nf = mixture ? (model == HB_MODEL_R ? F : 2) : 2;
-  bool dead = false;
-
-  for (int t = 0; t < T && !dead; ++t) {
-    const int j = t * B + i;
-    // per-SNP inputs that do not depend on the dots: fetch before waiting
-    const bool act = (j < p.m) && p.active[j];
-    double xx = 0, gold = 0, u = 0.5, z = 0;
-    double pa[HB_MAX_FOLD - 1], pc[HB_MAX_FOLD - 1], pv[HB_MAX_FOLD - 1], psd[HB_MAX_FOLD - 1];
-#pragma unroll
-    for (int k = 0; k < HB_MAX_FOLD - 1; ++k) { pa[k] = 0; pc[k] = 0; pv[k] = 1; psd[k] = 0; }
-    if (act) {
-      xx = p.xpx[j];
-      gold = p.g[j];
-      u = p.prm[prm_idx(0, mp, j)];
-      z = p.prm[prm_idx(1, mp, j)];
-#pragma unroll
-      for (int k = 0; k < HB_MAX_FOLD - 1; ++k)
-        if (k < nf - 1) {
-          pa[k] = p.prm[prm_idx(2 + 4 * k, mp, j)];
-          pc[k] = p.prm[prm_idx(3 + 4 * k, mp, j)];
-          pv[k] = p.prm[prm_idx(4 + 4 * k, mp, j)];
-          psd[k] = p.prm[prm_idx(5 + 4 * k, mp, j)];
-        }
-    }
-    // wait until every streaming CTA has added its partial dots of tile t
-    if (i == 0) {
-      bool ok = true;
-      while (hb::ld_acquire_u(p.arrive + t) < p.arrive_target)
-        if (!spin_backoff(spins, ctrl, HB_ABORT_TIMEOUT_SCALAR)) { ok = false; break; }
-      *s_abort = (!ok || *((volatile int*)(ctrl + 1)) != 0) ? 1 : 0;
-    }
-    hb::named_bar_sync(2, B);
-    if (*s_abort) { dead = true; break; }
-    const long long fx = (long long)__ldcg(p.dacc + j);
-    double d = (double)fx * p.inv_dscale;
-    const int slot = t % D;
-    d -= ring[(size_t)slot * B + i];
-    ring[(size_t)slot * B + i] = 0.0;
-    // rhs = x_j' yadj (+ xpx_j g_j)    (Bayes.cpp:593-594, 756-757)
-    double rhs = d + ((gold != 0.0) ? xx * gold : 0.0);
-
-    int pos = 0, nchg = 0, round = 0;
-    int cls = 0;
-    double gnew = gold;
-    bool done = !act;     // inactive SNPs are skipped (:589)
-    if (!act) { cls = 0; gnew = gold; }
-    for (;;) {
-      bool changed = false;
-      if (!done) {
-        eval_snp(model, nf, rhs, pa, pc, pv, psd, p.logpi0, u, z, cls, gnew);
-        changed = (gnew != gold);
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, changed);
-      int* ci = cand_idx + (round & 1) * 8;
-      double* cd = cand_delta + (round & 1) * 8;
-      if (lane == 0) ci[warp] = bal ? (warp * 32 + __ffs(bal) - 1) : (1 << 30);
-      if (bal && lane == __ffs(bal) - 1) cd[warp] = gnew - gold;
-      hb::named_bar_sync(2, B);
-      int first = 1 << 30;
-      double delta = 0.0;
-      for (int w = 0; w < nwarp; ++w)
-        if (ci[w] < first) { first = ci[w]; delta = cd[w]; }
-      ++round;
-      if (first == (1 << 30)) break;  // nothing left that changes: everything is final
-      if (i <= first) done = true;   // SNPs up to and including `first` are committed
-      if (i == first) {
-        chg_a[nchg] = first;
-        chg_delta[nchg] = delta;
-        p.q_snp[qbase + nchg] = t * B + first;
-        p.q_delta[qbase + nchg] = delta;
-      }
-      ++nchg;
-      if (!done) {
-        // patch the right-hand sides of the later SNPs of this tile:  x_i'(r - x_f delta)
-        const int gfi = p.gram[(((size_t)t * D) * B + first) * B + i];
-        rhs -= (double)gfi * delta;
-      }
-      pos = first + 1;
-      if (pos >= B) break;
-    }
-    // commit this tile
-    if (act) {
-      p.g[j] = gnew;
-      p.tracker[j] = cls;
-      cnt[cls] += 1.0;
-      if (cls > 0) vacc += (model == HB_MODEL_R) ? (gnew * gnew / p.fold[cls]) : (gnew * gnew);
-    }
-    hb::named_bar_sync(2, B);  // chg lists complete and visible
-    // corrections owed to the next D-1 tiles, whose dots were taken before these updates
-    for (int dt = 1; dt < D; ++dt) {
-      if (t + dt >= T) break;
-      double corr = 0.0;
-      const int32_t* gb = p.gram + (((size_t)t * D + dt) * B) * B;
-      for (int c = 0; c < nchg; ++c) corr += (double)gb[(size_t)chg_a[c] * B + i] * chg_delta[c];
-      ring[(size_t)((t + dt) % D) * B + i] += corr;
-    }
-    qbase += nchg;
-    if (i == 0) p.tile_qend[t] = qbase;
-    hb::named_bar_sync(2, B);
-    if (i == 0) {
-      __threadfence();
-      hb::st_release(ctrl, t + 1);
-    }
-  }
-  // fixed-order reduction of the per-thread accumulators
-  double* myred = red + (size_t)i * (HB_MAX_FOLD + 1);
-#pragma unroll
-  for (int k = 0; k < HB_MAX_FOLD; ++k) myred[k] = cnt[k];
-  myred[HB_MAX_FOLD] = vacc;
-  hb::named_bar_sync(2, B);
-  if (i == 0) {
-    for (int k = 0; k <= HB_MAX_FOLD; ++k) {
-      double sacc = 0.0;
-      for (int q = 0; q < B; ++q) sacc += red[(size_t)q * (HB_MAX_FOLD + 1) + k];
-      if (k < HB_MAX_FOLD) p.out->count[k] = sacc; else p.out->varg_acc = sacc;
-    }
-    p.out->n_changed = qbase;
-  }
-}
-
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) k_sweep(const __grid_constant__ SweepParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  if ((int)blockIdx.x == p.S) scalar_role(p, smem);
-  else stream_role(p, smem);
-}
-static const void* sweep_kernel_for(int threads) {
-  return threads <= 512 ? (const void*)k_sweep<512> : (const void*)k_sweep<1024>;
+// kernel variants: CTA size (register budget) x number of mixture classes held in registers
+static const void* sweep_kernel_for(int threads, int nf) {
+  if (threads <= 512) return nf <= 2 ? (const void*)k_sweep<512, 2> : nf <= 4 ? (const void*)k_sweep<512, 4> : (const void*)k_sweep<512, HB_MAX_FOLD>;
+  return nf <= 2 ? (const void*)k_sweep<1024, 2> : nf <= 4 ? (const void*)k_sweep<1024, 4> : (const void*)k_sweep<1024, HB_MAX_FOLD>;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -859,6 +419,49 @@ __device__ double block_sum_1024(double v, double* sh) {
   __syncthreads();
   return r;
 }
+// Class counts and the variance accumulator of the sweep (Bayes.cpp:603, 698, 791, 803-805), taken
+// from the committed effects in a fixed order (deterministic): stage 1 = per-block partials, stage 2 =
+// one warp adds the partials in block order.
+constexpr int kPostBlocks = 148, kPostThreads = 256;
+__global__ void __launch_bounds__(kPostThreads) k_post1(int m, int model, const int32_t* __restrict__ tracker,
+                                                        const double* __restrict__ g, const uint8_t* __restrict__ active,
+                                                        const double* __restrict__ fold8, double* __restrict__ partial) {
+  __shared__ double sh[kPostThreads][HB_MAX_FOLD + 1];
+  double cnt[HB_MAX_FOLD + 1];
+#pragma unroll
+  for (int k = 0; k <= HB_MAX_FOLD; ++k) cnt[k] = 0.0;
+  double fold[HB_MAX_FOLD];
+#pragma unroll
+  for (int k = 0; k < HB_MAX_FOLD; ++k) fold[k] = fold8[k];
+  const bool dense = (model == HB_MODEL_RR || model == HB_MODEL_A || model == HB_MODEL_L);
+  for (int j = blockIdx.x * kPostThreads + threadIdx.x; j < m; j += kPostBlocks * kPostThreads) {
+    if (!active[j]) continue;
+    const int cls = dense ? 1 : tracker[j];
+    const double gj = g[j];
+#pragma unroll
+    for (int k = 0; k < HB_MAX_FOLD; ++k)
+      if (k == cls) {
+        cnt[k] += 1.0;
+        if (k > 0) cnt[HB_MAX_FOLD] += (model == HB_MODEL_R) ? (gj * gj / fold[k]) : (gj * gj);
+      }
+  }
+#pragma unroll
+  for (int k = 0; k <= HB_MAX_FOLD; ++k) sh[threadIdx.x][k] = cnt[k];
+  __syncthreads();
+  if (threadIdx.x <= HB_MAX_FOLD) {
+    double a = 0.0;
+    for (int q = 0; q < kPostThreads; ++q) a += sh[q][threadIdx.x];
+    partial[blockIdx.x * (HB_MAX_FOLD + 1) + threadIdx.x] = a;
+  }
+}
+__global__ void k_post2(const double* __restrict__ partial, SweepOutDev* out) {
+  const int k = threadIdx.x;
+  if (k > HB_MAX_FOLD) return;
+  double a = 0.0;
+  for (int b = 0; b < kPostBlocks; ++b) a += partial[b * (HB_MAX_FOLD + 1) + k];
+  if (k < HB_MAX_FOLD) out->count[k] = a; else out->varg_acc = a;
+}
+
 __global__ void __launch_bounds__(1024) k_tail(const double* __restrict__ r, const double* __restrict__ u, int n,
                                                SweepOutDev* out, const int* ctrl) {
   __shared__ double sh[1024];
@@ -978,9 +581,9 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   e->cfg = *cfg;
   e->n = cfg->n; e->m = cfg->m;
   e->nsm = prop.multiProcessorCount;
-  e->B = cfg->tile_snps > 0 ? cfg->tile_snps : 64;
+  e->B = cfg->tile_snps > 0 ? cfg->tile_snps : 256;
   e->D = cfg->lag_tiles > 0 ? cfg->lag_tiles : 4;
-  if (e->B % 64 != 0 || e->B > 256) { delete e; return hb_set_error("tile_snps must be 64, 128, 192 or 256"); }
+  if (e->B % 64 != 0 || e->B > 512) { delete e; return hb_set_error("tile_snps must be a multiple of 64, at most 512"); }
   if (e->D > 8) { delete e; return hb_set_error("lag_tiles must be <= 8"); }
   int S = cfg->n_slabs > 0 ? cfg->n_slabs : e->nsm - 1;
   S = std::min(S, e->nsm - 1);
@@ -990,37 +593,48 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   e->NRG = (e->n + 16 * S - 1) / (16 * S);
   e->R = 16 * e->NRG;
   e->Npad = (size_t)S * e->R;
+  // compute threads: (row group of 16 rows) x (column lane); at most 12 warps
   int CL = 16;
-  while (CL > 1 && e->NRG * CL > 928) CL >>= 1;
-  if (e->NRG * CL > 928) { delete e; return hb_set_error("n = %d rows per GPU is beyond this build's slab size (max ~%d)", e->n, 928 * 16 * S); }
+  while (CL > 1 && e->NRG * CL > 384) CL >>= 1;
+  if (e->NRG * CL > 384) { delete e; return hb_set_error("n = %d rows per GPU is beyond this build's slab size (max ~%d)", e->n, 384 * 16 * S); }
   e->CL = CL;
   e->NTC = e->NRG * CL;
   e->NTCp = (e->NTC + 31) & ~31;
-  e->block_threads = std::max(e->NTCp + 64, e->B);
+  e->NCW = e->NTCp / 32;
+  e->NAW = (e->R / 4 + 31) / 32;       // AXPY threads own 4 rows each
+  e->block_threads = std::max(32 * (e->NCW + 2 + e->NAW), 2 * e->B);
+  if (e->block_threads > 1024) { delete e; return hb_set_error("slab of %d rows needs %d threads per CTA; use more GPUs", e->R, e->block_threads); }
   e->T = (e->m + e->B - 1) / e->B;
   e->m_pad = e->T * e->B;
-  e->stage_bytes = (size_t)e->B * e->R;
-  e->slab_stride = (size_t)e->T * e->stage_bytes;
-  const size_t part_bytes = 2 * (size_t)e->B * e->NRG * sizeof(double);
-  const size_t u_bytes = (size_t)e->R * sizeof(double);
-  const size_t fixed = part_bytes + u_bytes + 512;
+  e->slab_stride = (size_t)e->T * e->B * e->R;
+  // shared memory of a streaming CTA: NS sub-stages of SUBB columns + 2 partial buffers (same size as a
+  // sub-stage: SUBB x NRG doubles) + 2 residual-slab buffers + barriers
   const size_t budget = 200 * 1024;
-  if (fixed + 2 * e->stage_bytes > budget) {
+  const size_t rbuf_bytes = 2 * (size_t)e->R * sizeof(double);
+  int SUBB = 64;
+  while (SUBB > 16 && (4 * (size_t)SUBB * e->R + rbuf_bytes + 512 > budget)) SUBB >>= 1;
+  if (SUBB < CL || 4 * (size_t)SUBB * e->R + rbuf_bytes + 512 > budget) {
     delete e;
-    return hb_set_error("tile of %d SNPs x %d rows does not fit the shared-memory ring; lower tile_snps or use more GPUs", e->B, e->R);
+    return hb_set_error("slab of %d rows does not fit the shared-memory ring; use more GPUs", e->R);
   }
-  e->NS = (int)std::min<size_t>(8, (budget - fixed) / e->stage_bytes);
-  e->off_part = (uint32_t)align_up((size_t)e->NS * e->stage_bytes, 128);
-  e->off_u = e->off_part + part_bytes;
-  e->off_bar = align_up(e->off_u + u_bytes, 16);
-  size_t stream_smem = e->off_bar + 2 * e->NS * 8 + 17 * 4 + 64;
-  size_t scalar_smem = ((size_t)e->D * e->B + e->B + 16 + (size_t)e->B * (HB_MAX_FOLD + 1)) * 8 + (e->B + 32) * 4 + 64;
+  e->SUBB = SUBB;
+  e->Q = e->B / SUBB;
+  e->stage_bytes = (size_t)SUBB * e->R;
+  const size_t part_bytes = 2 * (size_t)SUBB * e->NRG * sizeof(double);
+  e->NS = (int)std::min<size_t>(8, (budget - part_bytes - rbuf_bytes - 512) / e->stage_bytes);
+  e->off_part = align_up((size_t)e->NS * e->stage_bytes, 128);
+  e->off_rbuf = e->off_part + part_bytes;
+  e->off_bar = align_up(e->off_rbuf + rbuf_bytes, 16);
+  const size_t stream_smem = e->off_bar + (2 * (size_t)e->NS + 8) * 8 + 64;
+  const size_t scalar_smem = hbk::scalar_smem_bytes(e->B, e->D);
   e->smem_bytes = std::max(stream_smem, scalar_smem);
-  CU(cudaFuncSetAttribute(sweep_kernel_for(e->block_threads), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
-  int occ = 0;
-  if (e->block_threads <= 512) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep<512>, e->block_threads, e->smem_bytes));
-  else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep<1024>, e->block_threads, e->smem_bytes));
-  if (occ < 1) { delete e; return hb_set_error("sweep kernel does not fit an SM (threads %d, smem %zu)", e->block_threads, e->smem_bytes); }
+  for (int nf : {2, 4, HB_MAX_FOLD}) {
+    const void* fn = sweep_kernel_for(e->block_threads, nf);
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, e->block_threads, e->smem_bytes));
+    if (occ < 1) { delete e; return hb_set_error("sweep kernel does not fit an SM (threads %d, smem %zu)", e->block_threads, e->smem_bytes); }
+  }
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&e->ev[i]));
   const size_t xbytes = (size_t)S * e->slab_stride;
@@ -1043,6 +657,8 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   CU(cudaMalloc(&e->tile_qend, (size_t)e->T * 4));
   CU(cudaMalloc(&e->ctrl, 64)); CU(cudaMemsetAsync(e->ctrl, 0, 64, e->stream));
   CU(cudaMalloc(&e->out_dev, sizeof(SweepOutDev)));
+  CU(cudaMalloc(&e->post_partial, (size_t)kPostBlocks * (HB_MAX_FOLD + 1) * 8));
+  CU(cudaMalloc(&e->fold_dev, HB_MAX_FOLD * 8));
   CU(cudaStreamSynchronize(e->stream));
   *out = e;
   return 0;
@@ -1054,7 +670,7 @@ extern "C" void hb_engine_destroy(hb_engine* e) {
   cudaFree(e->Xp); cudaFree(e->r); cudaFree(e->u); cudaFree(e->xpx); cudaFree(e->g); cudaFree(e->gsum);
   cudaFree(e->nzrate); cudaFree(e->wppa); cudaFree(e->vargL); cudaFree(e->active); cudaFree(e->tracker);
   cudaFree(e->gram); cudaFree(e->dacc); cudaFree(e->arrive); cudaFree(e->q_snp); cudaFree(e->q_delta);
-  cudaFree(e->tile_qend); cudaFree(e->ctrl); cudaFree(e->prm); cudaFree(e->out_dev); cudaFree(e->wstart); cudaFree(e->wmem);
+  cudaFree(e->tile_qend); cudaFree(e->ctrl); cudaFree(e->prm); cudaFree(e->out_dev); cudaFree(e->post_partial); cudaFree(e->fold_dev); cudaFree(e->wstart); cudaFree(e->wmem);
   for (int i = 0; i < 4; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -1252,8 +868,7 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   const int F = in->n_fold;
   if (F < 2 || F > HB_MAX_FOLD) return hb_set_error("hb_engine_sweep: n_fold must be in [2, %d]", HB_MAX_FOLD);
   CU(cudaSetDevice(e->cfg.device));
-  const int nfields = 2 + 4 * (HB_MAX_FOLD - 1);
-  if (!e->prm) CU(cudaMalloc(&e->prm, (size_t)nfields * e->m_pad * 8));
+  if (!e->prm) CU(cudaMalloc(&e->prm, (size_t)kPrmFields * e->m_pad * 8));
   PrepParams pp;
   memset(&pp, 0, sizeof pp);
   pp.m = e->m; pp.m_pad = e->m_pad; pp.T = e->T; pp.iter = in->iter; pp.model = in->model_index; pp.F = F;
@@ -1268,8 +883,8 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   sp.tile_qend = e->tile_qend; sp.ctrl = e->ctrl; sp.prm = e->prm; sp.out = e->out_dev;
   sp.slab_stride = e->slab_stride; sp.m_pad = e->m_pad;
   sp.n = e->n; sp.m = e->m; sp.S = e->S; sp.R = e->R; sp.NRG = e->NRG; sp.CL = e->CL; sp.T = e->T; sp.B = e->B; sp.D = e->D;
-  sp.NS = e->NS; sp.NTC = e->NTC; sp.NTCp = e->NTCp;
-  sp.stage_bytes = (uint32_t)e->stage_bytes; sp.off_part = (uint32_t)e->off_part; sp.off_u = (uint32_t)e->off_u;
+  sp.NS = e->NS; sp.NTC = e->NTC; sp.NCW = e->NCW; sp.NAW = e->NAW; sp.SUBB = e->SUBB; sp.Q = e->Q;
+  sp.stage_bytes = (uint32_t)e->stage_bytes; sp.off_part = (uint32_t)e->off_part; sp.off_rbuf = (uint32_t)e->off_rbuf;
   sp.off_bar = (uint32_t)e->off_bar;
   sp.model = in->model_index; sp.F = F;
   for (int k = 0; k < HB_MAX_FOLD; ++k) sp.fold[k] = in->fold[k];
@@ -1285,7 +900,9 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
     sp.dscale = ldexp(1.0, ex);
     sp.inv_dscale = ldexp(1.0, -ex);
   }
-  sp.arrive_target = (unsigned)(e->S * (std::min(e->B, e->NTCp) / 32));
+  sp.arrive_target = (unsigned)e->S;
+  sp.rowbuf = (uint32_t)hbk::scalar_rowbuf_bytes(e->B, e->D);
+  { const char* dbg = getenv("HB_DEBUG"); sp.dbg = dbg ? atoi(dbg) : 0; }
 
   CU(cudaEventRecord(e->ev[0], e->stream));
   k_prep<<<(e->m_pad + 255) / 256, 256, 0, e->stream>>>(pp, e->xpx, e->active, e->g, e->vargL, e->prm, e->dacc, e->arrive, e->ctrl,
@@ -1294,9 +911,14 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   CU(cudaEventRecord(e->ev[1], e->stream));
   {
     void* args[] = {(void*)&sp};
-    CU(cudaLaunchCooperativeKernel(sweep_kernel_for(e->block_threads), dim3(e->S + 1), dim3(e->block_threads), args, e->smem_bytes, e->stream));
+    CU(cudaLaunchCooperativeKernel(sweep_kernel_for(e->block_threads, in->model_index == HB_MODEL_R ? F : 2), dim3(e->S + 1), dim3(e->block_threads), args, e->smem_bytes, e->stream));
   }
   CU(cudaEventRecord(e->ev[2], e->stream));
+  CU(cudaMemcpyAsync(e->fold_dev, in->fold, HB_MAX_FOLD * 8, cudaMemcpyHostToDevice, e->stream));
+  k_post1<<<kPostBlocks, kPostThreads, 0, e->stream>>>(e->m, in->model_index, e->tracker, e->g, e->active, e->fold_dev, e->post_partial);
+  CU(cudaGetLastError());
+  k_post2<<<1, 32, 0, e->stream>>>(e->post_partial, e->out_dev);
+  CU(cudaGetLastError());
   if (in->model_index == HB_MODEL_L) {
     k_bayesl_post<<<(e->m + 255) / 256, 256, 0, e->stream>>>(e->m, in->iter, pp.key, e->active, e->g, e->vargL, in->vare,
                                                              in->lambda, in->lambda2);
@@ -1316,7 +938,15 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   for (int k = 0; k < HB_MAX_FOLD; ++k) out->count[k] = h.count[k];
   out->varg_acc = h.varg_acc; out->sum_vargL = h.sum_vargL;
   out->sum_r = h.sum_r; out->sum_r2 = h.sum_r2; out->sum_u = h.sum_u; out->var_u = h.var_u;
-  out->n_changed = h.n_changed; out->status = h.status;
+  out->n_changed = h.n_changed; out->status = h.status; out->rounds = h.rounds; out->reserved = 0;
+  if (getenv("HB_PHASES")) {
+    static const char* nm[8] = {"wait_dots", "guess", "wait_prev", "compact", "chain", "verify", "corr1", "commit"};
+    for (int g = 0; g < 2; ++g) {
+      fprintf(stderr, "[hb phases grp %d]", g);
+      for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%.0f", nm[k], (double)h.phase_clk[g][k] / std::max(1, (sp.dbg & 8) ? e->T : e->T / 2));
+      fprintf(stderr, " (cycles per tile)\n");
+    }
+  }
   if (h.status != 0)
     return hb_set_error("sweep kernel aborted with device status %d (%s)", h.status,
                         h.status == HB_ABORT_OVERFLOW ? "fixed-point dot overflow" : "timeout waiting on a tile signal");

@@ -150,7 +150,10 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
   EngineGuard guard;
   hb_engine_config cfg;
   memset(&cfg, 0, sizeof cfg);
-  cfg.device = a->device; cfg.n = n; cfg.m = m; cfg.tile_snps = a->tile_snps; cfg.lag_tiles = a->lag_tiles;
+  cfg.device = a->device; cfg.n = n; cfg.m = m; cfg.lag_tiles = a->lag_tiles;
+  // every SNP changes in every sweep of the dense models (RR/A/L): their tiles chain as a full triangular
+  // recurrence, which favours short tiles; the mixture models change few SNPs per tile and favour long ones
+  cfg.tile_snps = a->tile_snps ? a->tile_snps : ((model_index == 1 || model_index == 2 || model_index == 5) ? 64 : 256);
   cfg.n_slabs = a->n_slabs; cfg.seed = a->seed; cfg.rank = 0; cfg.world = 1;
   HBCHK(hb_engine_create(&cfg, &guard.e));
   hb_engine* E = guard.e;

@@ -110,6 +110,8 @@ typedef struct {
   double sum_u, var_u;         /* var(u) with n-1 (:819) */
   int n_changed;               /* SNPs whose effect changed (= residual updates applied) */
   int status;                  /* 0 ok; else device-side abort code */
+  int rounds;                  /* speculation rounds of the scalar chain summed over tiles (>= tiles) */
+  int reserved;
 } hb_sweep_out;
 
 int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out* out);
