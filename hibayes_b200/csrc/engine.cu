@@ -68,9 +68,9 @@ extern "C" int hb_device_count(void) {
 struct hb_engine {
   hb_engine_config cfg;
   int n, m, B, D, S, R, NRG, CL, T, m_pad, NS, nsm;
-  int NTC, NTCp, NCW, NAW, SUBB, Q, block_threads;
+  int NTC, NTCp, NCW, NAW, SUBB, NG, RL, block_threads;
   size_t Npad, slab_stride, stage_bytes, smem_bytes;
-  size_t off_part, off_rbuf, off_bar;
+  size_t off_rbuf, off_bar;
   uint8_t* Xp = nullptr;
   double *r = nullptr, *u = nullptr, *xpx = nullptr, *g = nullptr, *vargL = nullptr, *gsum = nullptr;
   double *nzrate = nullptr, *wppa = nullptr;
@@ -399,9 +399,13 @@ __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8
 }
 
 // kernel variants: CTA size (register budget) x number of mixture classes held in registers
-static const void* sweep_kernel_for(int threads, int nf) {
-  if (threads <= 512) return nf <= 2 ? (const void*)k_sweep<512, 2> : nf <= 4 ? (const void*)k_sweep<512, 4> : (const void*)k_sweep<512, HB_MAX_FOLD>;
-  return nf <= 2 ? (const void*)k_sweep<1024, 2> : nf <= 4 ? (const void*)k_sweep<1024, 4> : (const void*)k_sweep<1024, HB_MAX_FOLD>;
+template <int RL>
+static const void* sweep_kernel_rl(int nf) {
+  return nf <= 2 ? (const void*)k_sweep<512, 2, RL> : nf <= 4 ? (const void*)k_sweep<512, 4, RL> : (const void*)k_sweep<512, HB_MAX_FOLD, RL>;
+}
+static const void* sweep_kernel_for(int threads, int nf, int rl) {
+  (void)threads;   // every variant is built for CTAs of up to 512 threads
+  return rl == 8 ? sweep_kernel_rl<8>(nf) : rl == 16 ? sweep_kernel_rl<16>(nf) : sweep_kernel_rl<24>(nf);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -583,53 +587,50 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   e->nsm = prop.multiProcessorCount;
   e->B = cfg->tile_snps > 0 ? cfg->tile_snps : 256;
   e->D = cfg->lag_tiles > 0 ? cfg->lag_tiles : 4;
-  if (e->B % 64 != 0 || e->B > 512) { delete e; return hb_set_error("tile_snps must be a multiple of 64, at most 512"); }
+  if (e->B != 64 && e->B != 128 && e->B != 256) { delete e; return hb_set_error("tile_snps must be 64, 128 or 256"); }
   if (e->D > 8) { delete e; return hb_set_error("lag_tiles must be <= 8"); }
-  int S = cfg->n_slabs > 0 ? cfg->n_slabs : e->nsm - 1;
-  S = std::min(S, e->nsm - 1);
-  S = std::min(S, (e->n + 15) / 16);
-  S = std::max(S, 1);
-  e->S = S;
-  e->NRG = (e->n + 16 * S - 1) / (16 * S);
-  e->R = 16 * e->NRG;
-  e->Npad = (size_t)S * e->R;
-  // compute threads: (row group of 16 rows) x (column lane); at most 12 warps
-  int CL = 16;
-  while (CL > 1 && e->NRG * CL > 384) CL >>= 1;
-  if (e->NRG * CL > 384) { delete e; return hb_set_error("n = %d rows per GPU is beyond this build's slab size (max ~%d)", e->n, 384 * 16 * S); }
-  e->CL = CL;
-  e->NTC = e->NRG * CL;
+  e->NG = 1;   // scalar CTAs
+  // Row slabs: one streaming CTA per slab, R = 16 lanes x RL rows (RL = 8, 16 or 24); the smallest R whose
+  // slab count fits the SMs left beside the scalar CTAs keeps the most SMs streaming.
+  int s_max = e->nsm - e->NG;
+  if (cfg->n_slabs > 0) s_max = std::min(s_max, cfg->n_slabs);
+  s_max = std::max(s_max, 1);
+  e->RL = 0;
+  for (int rl : {8, 16, 24})
+    if (((size_t)e->n + 16 * rl - 1) / (16 * rl) <= (size_t)s_max) { e->RL = rl; break; }
+  if (!e->RL && cfg->n_slabs > 0 && ((size_t)e->n + 383) / 384 <= (size_t)(e->nsm - e->NG)) e->RL = 24;   // n_slabs is a hint
+  if (!e->RL) {
+    delete e;
+    return hb_set_error("n = %d rows per GPU exceeds this build's %d slabs x 384 rows; shard the individuals over more GPUs", cfg->n, s_max);
+  }
+  e->R = 16 * e->RL;
+  e->S = (e->n + e->R - 1) / e->R;
+  e->NRG = e->R / 16;
+  e->Npad = (size_t)e->S * e->R;
+  e->CL = 16;                          // column lanes of the prediction kernel (k_gemv_part)
+  e->NTC = e->NRG * e->CL;
   e->NTCp = (e->NTC + 31) & ~31;
-  e->NCW = e->NTCp / 32;
-  e->NAW = (e->R / 4 + 31) / 32;       // AXPY threads own 4 rows each
+  e->NCW = e->B / 32;                  // compute warps: 32 columns of the tile each
+  e->NAW = e->R / 128;                 // AXPY threads own 4 rows each
   e->block_threads = std::max(32 * (e->NCW + 2 + e->NAW), 2 * e->B);
-  if (e->block_threads > 1024) { delete e; return hb_set_error("slab of %d rows needs %d threads per CTA; use more GPUs", e->R, e->block_threads); }
   e->T = (e->m + e->B - 1) / e->B;
   e->m_pad = e->T * e->B;
   e->slab_stride = (size_t)e->T * e->B * e->R;
-  // shared memory of a streaming CTA: NS sub-stages of SUBB columns + 2 partial buffers (same size as a
-  // sub-stage: SUBB x NRG doubles) + 2 residual-slab buffers + barriers
-  const size_t budget = 200 * 1024;
+  // shared memory of a streaming CTA: NS sub-stages of B/4 columns + 2 residual-slab buffers + barriers
+  e->SUBB = e->B / 4;
+  e->stage_bytes = (size_t)e->SUBB * e->R;
   const size_t rbuf_bytes = 2 * (size_t)e->R * sizeof(double);
-  int SUBB = 64;
-  while (SUBB > 16 && (4 * (size_t)SUBB * e->R + rbuf_bytes + 512 > budget)) SUBB >>= 1;
-  if (SUBB < CL || 4 * (size_t)SUBB * e->R + rbuf_bytes + 512 > budget) {
-    delete e;
-    return hb_set_error("slab of %d rows does not fit the shared-memory ring; use more GPUs", e->R);
-  }
-  e->SUBB = SUBB;
-  e->Q = e->B / SUBB;
-  e->stage_bytes = (size_t)SUBB * e->R;
-  const size_t part_bytes = 2 * (size_t)SUBB * e->NRG * sizeof(double);
-  e->NS = (int)std::min<size_t>(8, (budget - part_bytes - rbuf_bytes - 512) / e->stage_bytes);
-  e->off_part = align_up((size_t)e->NS * e->stage_bytes, 128);
-  e->off_rbuf = e->off_part + part_bytes;
+  const size_t bar_bytes = (2 * 16 + 4 + hbk::kDotBars) * 8 + 64;
+  const size_t budget = 226 * 1024;
+  e->NS = (int)std::min<size_t>(16, (budget - rbuf_bytes - bar_bytes - 256) / e->stage_bytes);
+  if (e->NS < 2) { delete e; return hb_set_error("sub-stage of %zu bytes does not fit shared memory", e->stage_bytes); }
+  e->off_rbuf = align_up((size_t)e->NS * e->stage_bytes, 128);
   e->off_bar = align_up(e->off_rbuf + rbuf_bytes, 16);
-  const size_t stream_smem = e->off_bar + (2 * (size_t)e->NS + 8) * 8 + 64;
+  const size_t stream_smem = e->off_bar + bar_bytes;
   const size_t scalar_smem = hbk::scalar_smem_bytes(e->B, e->D);
   e->smem_bytes = std::max(stream_smem, scalar_smem);
   for (int nf : {2, 4, HB_MAX_FOLD}) {
-    const void* fn = sweep_kernel_for(e->block_threads, nf);
+    const void* fn = sweep_kernel_for(e->block_threads, nf, e->RL);
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, e->block_threads, e->smem_bytes));
@@ -637,7 +638,7 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   }
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&e->ev[i]));
-  const size_t xbytes = (size_t)S * e->slab_stride;
+  const size_t xbytes = (size_t)e->S * e->slab_stride;
   CU(cudaMalloc(&e->Xp, xbytes));
   CU(cudaMemsetAsync(e->Xp, 0, xbytes, e->stream));
   CU(cudaMalloc(&e->r, e->Npad * 8)); CU(cudaMemsetAsync(e->r, 0, e->Npad * 8, e->stream));
@@ -882,9 +883,9 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   sp.gram = e->gram; sp.dacc = e->dacc; sp.arrive = e->arrive; sp.q_snp = e->q_snp; sp.q_delta = e->q_delta;
   sp.tile_qend = e->tile_qend; sp.ctrl = e->ctrl; sp.prm = e->prm; sp.out = e->out_dev;
   sp.slab_stride = e->slab_stride; sp.m_pad = e->m_pad;
-  sp.n = e->n; sp.m = e->m; sp.S = e->S; sp.R = e->R; sp.NRG = e->NRG; sp.CL = e->CL; sp.T = e->T; sp.B = e->B; sp.D = e->D;
-  sp.NS = e->NS; sp.NTC = e->NTC; sp.NCW = e->NCW; sp.NAW = e->NAW; sp.SUBB = e->SUBB; sp.Q = e->Q;
-  sp.stage_bytes = (uint32_t)e->stage_bytes; sp.off_part = (uint32_t)e->off_part; sp.off_rbuf = (uint32_t)e->off_rbuf;
+  sp.n = e->n; sp.m = e->m; sp.S = e->S; sp.R = e->R; sp.T = e->T; sp.B = e->B; sp.D = e->D;
+  sp.NS = e->NS; sp.NCW = e->NCW; sp.NAW = e->NAW; sp.SUBB = e->SUBB; sp.NG = e->NG;
+  sp.stage_bytes = (uint32_t)e->stage_bytes; sp.off_rbuf = (uint32_t)e->off_rbuf;
   sp.off_bar = (uint32_t)e->off_bar;
   sp.model = in->model_index; sp.F = F;
   for (int k = 0; k < HB_MAX_FOLD; ++k) sp.fold[k] = in->fold[k];
@@ -911,7 +912,7 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   CU(cudaEventRecord(e->ev[1], e->stream));
   {
     void* args[] = {(void*)&sp};
-    CU(cudaLaunchCooperativeKernel(sweep_kernel_for(e->block_threads, in->model_index == HB_MODEL_R ? F : 2), dim3(e->S + 1), dim3(e->block_threads), args, e->smem_bytes, e->stream));
+    CU(cudaLaunchCooperativeKernel(sweep_kernel_for(e->block_threads, in->model_index == HB_MODEL_R ? F : 2, e->RL), dim3(e->S + e->NG), dim3(e->block_threads), args, e->smem_bytes, e->stream));
   }
   CU(cudaEventRecord(e->ev[2], e->stream));
   CU(cudaMemcpyAsync(e->fold_dev, in->fold, HB_MAX_FOLD * 8, cudaMemcpyHostToDevice, e->stream));

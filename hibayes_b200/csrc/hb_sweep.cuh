@@ -59,9 +59,9 @@ struct SweepParams {
   const double* prm;
   SweepOutDev* out;
   size_t slab_stride, m_pad;
-  int n, m, S, R, NRG, CL, T, B, D, NS;
-  int NTC, NCW, NAW, SUBB, Q;
-  uint32_t stage_bytes, off_part, off_rbuf, off_bar;
+  int n, m, S, R, T, B, D, NS;
+  int NCW, NAW, SUBB, NG;
+  uint32_t stage_bytes, off_rbuf, off_bar;
   int model, F;
   double fold[HB_MAX_FOLD];
   double logpi0;
@@ -82,7 +82,8 @@ namespace hbk {
 
 constexpr double kTwo513 = 2.6815615859885194e154;     // 2^513
 constexpr double kTwoM513 = 3.7291703656001034e-155;   // 2^-513
-constexpr long long kTimeoutNs = 4000000000ll;          // every wait is bounded: a lost signal aborts, it never hangs
+constexpr long long kTimeoutNs = 4000000000ll;
+constexpr int kDotBars = 16;          // every wait is bounded: a lost signal aborts, it never hangs
 
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -127,28 +128,34 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // ------------------------------------------------------------------------------------------
 // streaming CTA
 // ------------------------------------------------------------------------------------------
+// Layout of one CTA (slab of R = 16*RL rows, tile of B = 32*NCW SNP columns, sub-stage = B/4 columns):
+//   compute warp w, half-warp h, lane l: rows [RL*l, RL*l + RL) of the slab, held in registers for the
+//   whole tile; in every sub-stage q it takes the four columns 8w + 4h + {0..3} and keeps one running
+//   dot per column (16 per tile).  After the tile's four sub-stages the 16 lanes of a half-warp hold
+//   16 x 16 partial dots; a transposed shuffle reduction (8+4+2+1 exchanges, fixed tree) leaves lane l
+//   with the complete slab dot of accumulator l, i.e. of column 64*(l>>2)... (see col_of_acc) -- no
+//   shared-memory partials, no cross-warp reduction.  The lane adds it, as fixed-point int64, to the
+//   per-SNP accumulator in L2 (order-independent => deterministic).
+template <int RL>
 __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s = blockIdx.x;
-  const int NS = p.NS, B = p.B, D = p.D, T = p.T, NRG = p.NRG, NTC = p.NTC, R = p.R, NCW = p.NCW, NAW = p.NAW;
-  const int SUBB = p.SUBB, Q = p.Q;
+  const int NS = p.NS, B = p.B, D = p.D, T = p.T, R = p.R, NCW = p.NCW, NAW = p.NAW;
+  const int SUBB = p.SUBB;
+  constexpr int Q = 4;
   uint8_t* stage0 = smem;
-  double* part = (double*)(smem + p.off_part);   // 2 x SUBB x NRG
   double* rbuf = (double*)(smem + p.off_rbuf);   // 2 x R   (residual slab * 2^513)
   uint64_t* full = (uint64_t*)(smem + p.off_bar);
   uint64_t* empty = full + NS;
-  uint64_t* pfull = empty + NS;
-  uint64_t* pempty = pfull + 2;
-  uint64_t* rfull = pempty + 2;
+  uint64_t* rfull = empty + NS;
   uint64_t* rempty = rfull + 2;
+  uint64_t* dfull = rempty + 2;                  // kDotBars barriers: dots of tile t added to L2 by every compute warp
   int* ctrl = p.ctrl;
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { hb::mbar_init(full + i, 1); hb::mbar_init(empty + i, NCW); }
-    for (int i = 0; i < 2; ++i) {
-      hb::mbar_init(pfull + i, NCW); hb::mbar_init(pempty + i, 1);
-      hb::mbar_init(rfull + i, NAW); hb::mbar_init(rempty + i, NCW);
-    }
+    for (int i = 0; i < 2; ++i) { hb::mbar_init(rfull + i, NAW); hb::mbar_init(rempty + i, NCW); }
+    for (int i = 0; i < kDotBars; ++i) hb::mbar_init(dfull + i, NCW);
     hb::mbar_fence_init();
   }
   __syncthreads();
@@ -156,92 +163,99 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
   const int nsub = T * Q;
 
   if (warp < NCW) {
-    // ---------------- compute warps: partial dots of this slab
-    const bool live = tid < NTC;
-    const int rg = live ? (tid % NRG) : 0;
-    const int KC = SUBB / p.CL;
-    double rs[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) rs[i] = 0.0;
+    // ---------------- compute warps
+    const int h = lane >> 4, l = lane & 15;
+    const uint32_t lane_off = (uint32_t)((8 * warp + 4 * h) * R + RL * l);
+    double rs[RL];
+    int st = 0;
+    uint32_t st_par = 0;
     for (int t = 0; t < T; ++t) {
       if (!mbar_wait(rfull + (t & 1), (uint32_t)((t >> 1) & 1), ctrl, HB_ABORT_TIMEOUT_PIPE)) return;
-      if (live) {
-        const double2* rb = (const double2*)(rbuf + (size_t)(t & 1) * R + 16 * rg);
+      {
+        const double2* rb = (const double2*)(rbuf + (size_t)(t & 1) * R + RL * l);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const double2 v = rb[i]; rs[2 * i] = v.x; rs[2 * i + 1] = v.y; }
+        for (int i = 0; i < RL / 2; ++i) { const double2 v = rb[i]; rs[2 * i] = v.x; rs[2 * i + 1] = v.y; }
       }
       __syncwarp();
       if (lane == 0) hb::mbar_arrive(rempty + (t & 1));
+      double acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+#pragma unroll
       for (int q = 0; q < Q; ++q) {
-        const int gsub = t * Q + q, st = gsub % NS;
-        if (!mbar_wait(full + st, (uint32_t)((gsub / NS) & 1), ctrl, HB_ABORT_TIMEOUT_TMA)) return;
-        if (gsub >= 2 && !mbar_wait(pempty + (gsub & 1), (uint32_t)(((gsub >> 1) - 1) & 1), ctrl, HB_ABORT_TIMEOUT_PIPE)) return;
-        double* pt = part + (size_t)(gsub & 1) * SUBB * NRG;
-        if (live && !(p.dbg & 2)) {
-          const uint4* sp = (const uint4*)(stage0 + (size_t)st * p.stage_bytes);
-#pragma unroll 2
-          for (int k = 0; k < KC; ++k) {
-            const uint4 v = sp[tid + NTC * k];
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            a0 = fma(rs[0], byte_as_scaled(v.x, 0x4044), a0);
-            a1 = fma(rs[1], byte_as_scaled(v.x, 0x4144), a1);
-            a2 = fma(rs[2], byte_as_scaled(v.x, 0x4244), a2);
-            a3 = fma(rs[3], byte_as_scaled(v.x, 0x4344), a3);
-            a0 = fma(rs[4], byte_as_scaled(v.y, 0x4044), a0);
-            a1 = fma(rs[5], byte_as_scaled(v.y, 0x4144), a1);
-            a2 = fma(rs[6], byte_as_scaled(v.y, 0x4244), a2);
-            a3 = fma(rs[7], byte_as_scaled(v.y, 0x4344), a3);
-            a0 = fma(rs[8], byte_as_scaled(v.z, 0x4044), a0);
-            a1 = fma(rs[9], byte_as_scaled(v.z, 0x4144), a1);
-            a2 = fma(rs[10], byte_as_scaled(v.z, 0x4244), a2);
-            a3 = fma(rs[11], byte_as_scaled(v.z, 0x4344), a3);
-            a0 = fma(rs[12], byte_as_scaled(v.w, 0x4044), a0);
-            a1 = fma(rs[13], byte_as_scaled(v.w, 0x4144), a1);
-            a2 = fma(rs[14], byte_as_scaled(v.w, 0x4244), a2);
-            a3 = fma(rs[15], byte_as_scaled(v.w, 0x4344), a3);
-            pt[tid + NTC * k] = ((a0 + a1) + (a2 + a3)) * kTwo513;
+        if (!mbar_wait(full + st, st_par, ctrl, HB_ABORT_TIMEOUT_TMA)) return;
+        if (!(p.dbg & 2)) {
+          const uint8_t* sp = stage0 + (size_t)st * p.stage_bytes + lane_off;
+#pragma unroll
+          for (int wd = 0; wd < RL / 8; ++wd) {
+            uint2 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = *(const uint2*)(sp + k * R + 8 * wd);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              double a = acc[4 * q + k];
+              a = fma(rs[8 * wd + 0], byte_as_scaled(v[k].x, 0x4044), a);
+              a = fma(rs[8 * wd + 1], byte_as_scaled(v[k].x, 0x4144), a);
+              a = fma(rs[8 * wd + 2], byte_as_scaled(v[k].x, 0x4244), a);
+              a = fma(rs[8 * wd + 3], byte_as_scaled(v[k].x, 0x4344), a);
+              a = fma(rs[8 * wd + 4], byte_as_scaled(v[k].y, 0x4044), a);
+              a = fma(rs[8 * wd + 5], byte_as_scaled(v[k].y, 0x4144), a);
+              a = fma(rs[8 * wd + 6], byte_as_scaled(v[k].y, 0x4244), a);
+              a = fma(rs[8 * wd + 7], byte_as_scaled(v[k].y, 0x4344), a);
+              acc[4 * q + k] = a;
+            }
           }
         }
         __syncwarp();
-        if (lane == 0) { hb::mbar_arrive(pfull + (gsub & 1)); hb::mbar_arrive(empty + st); }
+        if (lane == 0) hb::mbar_arrive(empty + st);
+        if (++st == NS) { st = 0; st_par ^= 1u; }
       }
+      // transposed reduction over the 16 lanes of the half-warp: afterwards lane l holds accumulator l
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) {
+        const bool up = (l & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+          const double keep = up ? acc[i + o] : acc[i];
+          const double send = up ? acc[i] : acc[i + o];
+          acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      {
+        // accumulator l = 4*q + k  <->  column 64q' ... of the tile: sub-stage q, column 8w + 4h + k of it
+        const int col = (l >> 2) * SUBB + 8 * warp + 4 * h + (l & 3);
+        const double scaled = (acc[0] * kTwo513) * p.dscale;
+        if (!(fabs(scaled) < 4.0e18)) atomicCAS(ctrl + 1, 0, HB_ABORT_OVERFLOW);
+        const long long fx = __double2ll_rn(scaled);
+        atomicAdd(p.dacc + (size_t)t * B + col, (unsigned long long)fx);
+      }
+      __syncwarp();
+      if (lane == 0) hb::mbar_arrive(dfull + (t % kDotBars));
     }
     return;
   }
   if (warp == NCW) {
     // ---------------- TMA producer: streams this slab's sub-stages through the ring
     if (lane == 0) {
+      int st = 0;
+      uint32_t par = 1;   // parity of the previous phase of empty[st]
       for (int gsub = 0; gsub < nsub; ++gsub) {
-        const int st = gsub % NS;
-        if (gsub >= NS && !mbar_wait(empty + st, (uint32_t)((gsub / NS - 1) & 1), ctrl, HB_ABORT_TIMEOUT_TMA)) return;
+        if (gsub >= NS && !mbar_wait(empty + st, par, ctrl, HB_ABORT_TIMEOUT_TMA)) return;
         hb::mbar_arrive_expect_tx(full + st, p.stage_bytes);
         hb::tma_load_1d(stage0 + (size_t)st * p.stage_bytes, Xs + (size_t)gsub * p.stage_bytes, p.stage_bytes, full + st);
+        if (++st == NS) { st = 0; par ^= 1u; }
       }
     }
     return;
   }
   if (warp == NCW + 1) {
-    // ---------------- reducer warp: row-group sum in fixed order, fixed-point accumulation in L2
-    for (int gsub = 0; gsub < nsub; ++gsub) {
-      const int t = gsub / Q, q = gsub - t * Q;
-      if (!mbar_wait(pfull + (gsub & 1), (uint32_t)((gsub >> 1) & 1), ctrl, HB_ABORT_TIMEOUT_PIPE)) return;
-      const double* pt = part + (size_t)(gsub & 1) * SUBB * NRG;
-      for (int c = lane; c < SUBB; c += 32) {
-        const double* pj = pt + (size_t)c * NRG;
-        double sum = 0.0;
-        for (int k = 0; k < NRG; ++k) sum += pj[k];
-        const double scaled = sum * p.dscale;
-        if (!(fabs(scaled) < 4.0e18)) atomicCAS(ctrl + 1, 0, HB_ABORT_OVERFLOW);
-        const long long fx = __double2ll_rn(scaled);
-        atomicAdd(p.dacc + (size_t)t * B + q * SUBB + c, (unsigned long long)fx);
-      }
-      __syncwarp();
-      if (lane == 0) {
-        hb::mbar_arrive(pempty + (gsub & 1));
-        if (q == Q - 1) {
-          __threadfence();
-          atomicAdd(p.arrive + t, 1u);
-        }
+    // ---------------- committer: once every compute warp has added its dots of tile t, make them visible
+    // device-wide and count the slab in (the fence stalls only this warp)
+    if (lane == 0) {
+      for (int t = 0; t < T; ++t) {
+        if (!mbar_wait(dfull + (t % kDotBars), (uint32_t)((t / kDotBars) & 1), ctrl, HB_ABORT_TIMEOUT_PIPE)) return;
+        __threadfence();
+        atomicAdd(p.arrive + t, 1u);
       }
     }
     return;
@@ -277,28 +291,34 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
         ok = __shfl_sync(0xffffffffu, ok, 0);
         if (!ok) return;
         const int qend = __ldcg(p.tile_qend + (t - D));
-        for (int q0 = applied; q0 < ((p.dbg & 1) ? applied : qend); q0 += 4) {
-          int js[4];
-          double dl[4];
-          uint32_t xw[4];
-          const int nq = min(4, qend - q0);
+        // the tile's changes: 32 queue entries per coalesced read, then the genotype words of eight
+        // changed SNPs in flight at a time (all from L2: the columns were streamed D tiles ago)
+        for (int q0 = applied; q0 < ((p.dbg & 1) ? applied : qend); q0 += 32) {
+          const int nq = min(32, qend - q0);
+          int jl = 0;
+          double dll = 0.0;
+          if (lane < nq) { jl = __ldcg(p.q_snp + q0 + lane); dll = __ldcg(p.q_delta + q0 + lane); }
+          for (int e0 = 0; e0 < nq; e0 += 8) {
+            uint32_t xw[8];
+            double dl[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (e < nq) { js[e] = __ldcg(p.q_snp + q0 + e); dl[e] = __ldcg(p.q_delta + q0 + e); }
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (e < nq && has) xw[e] = __ldg((const uint32_t*)(Xs + (size_t)js[e] * R + row0));
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (e < nq && has) {
-              const double ds = dl[e] * kTwo513;
-              const double x0 = byte_as_scaled(xw[e], 0x4044), x1 = byte_as_scaled(xw[e], 0x4144);
-              const double x2 = byte_as_scaled(xw[e], 0x4244), x3 = byte_as_scaled(xw[e], 0x4344);
-              rm[0] = fma(-x0, ds, rm[0]); um[0] = fma(x0, ds, um[0]);   // yadj -= x*delta (Bayes.cpp:787), u += x*delta (:789)
-              rm[1] = fma(-x1, ds, rm[1]); um[1] = fma(x1, ds, um[1]);
-              rm[2] = fma(-x2, ds, rm[2]); um[2] = fma(x2, ds, um[2]);
-              rm[3] = fma(-x3, ds, rm[3]); um[3] = fma(x3, ds, um[3]);
+            for (int e = 0; e < 8; ++e) {
+              const int js = __shfl_sync(0xffffffffu, jl, (e0 + e) & 31);
+              dl[e] = __shfl_sync(0xffffffffu, dll, (e0 + e) & 31);
+              xw[e] = (e0 + e < nq && has) ? __ldg((const uint32_t*)(Xs + (size_t)js * R + row0)) : 0u;
             }
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (e0 + e < nq) {
+                const double ds = dl[e] * kTwo513;
+                const double x0 = byte_as_scaled(xw[e], 0x4044), x1 = byte_as_scaled(xw[e], 0x4144);
+                const double x2 = byte_as_scaled(xw[e], 0x4244), x3 = byte_as_scaled(xw[e], 0x4344);
+                rm[0] = fma(-x0, ds, rm[0]); um[0] = fma(x0, ds, um[0]);   // yadj -= x*delta (Bayes.cpp:787), u += x*delta (:789)
+                rm[1] = fma(-x1, ds, rm[1]); um[1] = fma(x1, ds, um[1]);
+                rm[2] = fma(-x2, ds, rm[2]); um[2] = fma(x2, ds, um[2]);
+                rm[3] = fma(-x3, ds, rm[3]); um[3] = fma(x3, ds, um[3]);
+              }
+          }
         }
         applied = qend;
       }
@@ -483,6 +503,23 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
   const int B = p.B, D = p.D, T = p.T, F = p.F, model = p.model;
   const int tid = threadIdx.x;
   const int ngrp = (p.dbg & 8) ? 1 : 2;   // timing experiment: one thread group does every tile
+  if (p.dbg & 48) {
+    // timing experiments: the streaming side alone.  16: every tile is published (without changes) as soon
+    // as its dots have arrived; 32: all tiles are published up front.
+    if (tid == 0) {
+      if (p.dbg & 32) { for (int t = 0; t < T; ++t) p.tile_qend[t] = 0; __threadfence(); hb::st_release(p.ctrl, T); }
+      else for (int t = 0; t < T; ++t) {
+        Waiter w;
+        while (hb::ld_relaxed_u(p.arrive + t) < p.arrive_target)
+          if (!w.keep_waiting(p.ctrl, HB_ABORT_TIMEOUT_SCALAR)) return;
+        p.tile_qend[t] = 0;
+        __threadfence();
+        hb::st_release(p.ctrl, t + 1);
+      }
+      p.out->n_changed = 0; p.out->rounds = 0;
+    }
+    return;
+  }
   if (tid >= ngrp * B) return;
   const int grp = tid / B, i = tid - grp * B, warp = i >> 5, lane = i & 31, nwarp = B / 32;
   // ---- shared memory carve-up
@@ -765,9 +802,9 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
 
 }  // namespace hbk
 
-template <int MAXT, int NF>
+template <int MAXT, int NF, int RL>
 __global__ void __launch_bounds__(MAXT, 1) k_sweep(const __grid_constant__ SweepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  if ((int)blockIdx.x == p.S) hbk::scalar_role<NF>(p, smem);
-  else hbk::stream_role(p, smem);
+  if ((int)blockIdx.x >= p.S) hbk::scalar_role<NF>(p, smem);
+  else hbk::stream_role<RL>(p, smem);
 }

@@ -105,7 +105,7 @@ def test_config1_matches_committed_golden():
     assert abs(got["Ve"] / gold["Ve"] - 1) < RTOL
 
 
-@pytest.mark.parametrize("tile,lag,slabs", [(64, 1, 0), (64, 2, 0), (64, 8, 0), (128, 3, 0), (64, 4, 5), (64, 4, 2), (256, 4, 0), (256, 1, 3), (512, 2, 0)])
+@pytest.mark.parametrize("tile,lag,slabs", [(64, 1, 0), (64, 2, 0), (64, 8, 0), (128, 3, 0), (64, 4, 5), (64, 4, 2), (256, 4, 0), (256, 1, 3), (128, 8, 0)])
 def test_result_does_not_depend_on_tiling(oracle, tile, lag, slabs):
     y, X = synth(1500, 1000, seed=21, n_causal=15)
     kw = dict(niter=12, nburn=4, thin=2, seed=31337)
