@@ -83,6 +83,8 @@ struct hb_engine {
   int* q_snp = nullptr;
   double* q_delta = nullptr;
   int* tile_qend = nullptr;
+  double* corr = nullptr;
+  int* hq = nullptr;
   int* ctrl = nullptr;  // [0] progress, [1] abort
   double* prm = nullptr;  // per-SNP sweep parameters, SoA
   int prm_fold = 0;
@@ -354,16 +356,21 @@ struct PrepParams {
 __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8_t* __restrict__ active,
                        const double* __restrict__ g, const double* __restrict__ vargL, double* __restrict__ prm,
                        unsigned long long* __restrict__ dacc, unsigned int* __restrict__ arrive, int* __restrict__ ctrl,
-                       SweepOutDev* __restrict__ out) {
+                       SweepOutDev* __restrict__ out, int* __restrict__ tile_qend, int* __restrict__ hq,
+                       unsigned long long* __restrict__ corr, int B, int DC) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) {
     ctrl[0] = 0; ctrl[1] = 0;
     out->n_changed = 0; out->status = 0; out->rounds = 0; out->varg_acc = 0; out->sum_vargL = 0;
     for (int k = 0; k < HB_MAX_FOLD; ++k) out->count[k] = 0;
   }
-  if (j < p.T) arrive[j] = 0;
+  if (j < p.T) { arrive[j] = 0; tile_qend[j] = -1; hq[j] = -1; }
   if (j >= p.m_pad) return;
   dacc[j] = 0ull;
+  {
+    const int t = j / B, i = j - t * B;
+    for (int d = 0; d < DC; ++d) corr[((size_t)t * DC + d) * B + i] = hbk::kCorrEmpty;
+  }
   if (j >= p.m || !active[j]) return;
   const double xx = xpx[j];
   double u, z;
@@ -589,7 +596,9 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   e->D = cfg->lag_tiles > 0 ? cfg->lag_tiles : 4;
   if (e->B != 64 && e->B != 128 && e->B != 256) { delete e; return hb_set_error("tile_snps must be 64, 128 or 256"); }
   if (e->D > 8) { delete e; return hb_set_error("lag_tiles must be <= 8"); }
-  e->NG = 1;   // scalar CTAs
+  e->NG = 4;   // scalar CTAs (two workers each)
+  if (const char* ng = getenv("HB_NG")) e->NG = std::max(1, std::min(16, atoi(ng)));
+  e->NG = std::min(e->NG, std::max(1, e->nsm / 8));
   // Row slabs: one streaming CTA per slab, R = 16 lanes x RL rows (RL = 8, 16 or 24); the smallest R whose
   // slab count fits the SMs left beside the scalar CTAs keeps the most SMs streaming.
   int s_max = e->nsm - e->NG;
@@ -656,6 +665,8 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   CU(cudaMalloc(&e->q_snp, mp * 4));
   CU(cudaMalloc(&e->q_delta, mp * 8));
   CU(cudaMalloc(&e->tile_qend, (size_t)e->T * 4));
+  CU(cudaMalloc(&e->hq, (size_t)e->T * 4));
+  CU(cudaMalloc(&e->corr, std::max<size_t>(1, (size_t)e->m_pad * (e->D - 1)) * 8));
   CU(cudaMalloc(&e->ctrl, 64)); CU(cudaMemsetAsync(e->ctrl, 0, 64, e->stream));
   CU(cudaMalloc(&e->out_dev, sizeof(SweepOutDev)));
   CU(cudaMalloc(&e->post_partial, (size_t)kPostBlocks * (HB_MAX_FOLD + 1) * 8));
@@ -671,7 +682,7 @@ extern "C" void hb_engine_destroy(hb_engine* e) {
   cudaFree(e->Xp); cudaFree(e->r); cudaFree(e->u); cudaFree(e->xpx); cudaFree(e->g); cudaFree(e->gsum);
   cudaFree(e->nzrate); cudaFree(e->wppa); cudaFree(e->vargL); cudaFree(e->active); cudaFree(e->tracker);
   cudaFree(e->gram); cudaFree(e->dacc); cudaFree(e->arrive); cudaFree(e->q_snp); cudaFree(e->q_delta);
-  cudaFree(e->tile_qend); cudaFree(e->ctrl); cudaFree(e->prm); cudaFree(e->out_dev); cudaFree(e->post_partial); cudaFree(e->fold_dev); cudaFree(e->wstart); cudaFree(e->wmem);
+  cudaFree(e->tile_qend); cudaFree(e->hq); cudaFree(e->corr); cudaFree(e->ctrl); cudaFree(e->prm); cudaFree(e->out_dev); cudaFree(e->post_partial); cudaFree(e->fold_dev); cudaFree(e->wstart); cudaFree(e->wmem);
   for (int i = 0; i < 4; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -881,7 +892,7 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   memset(&sp, 0, sizeof sp);
   sp.Xp = e->Xp; sp.r = e->r; sp.u = e->u; sp.xpx = e->xpx; sp.active = e->active; sp.g = e->g; sp.tracker = e->tracker;
   sp.gram = e->gram; sp.dacc = e->dacc; sp.arrive = e->arrive; sp.q_snp = e->q_snp; sp.q_delta = e->q_delta;
-  sp.tile_qend = e->tile_qend; sp.ctrl = e->ctrl; sp.prm = e->prm; sp.out = e->out_dev;
+  sp.tile_qend = e->tile_qend; sp.corr = e->corr; sp.hq = e->hq; sp.ctrl = e->ctrl; sp.prm = e->prm; sp.out = e->out_dev;
   sp.slab_stride = e->slab_stride; sp.m_pad = e->m_pad;
   sp.n = e->n; sp.m = e->m; sp.S = e->S; sp.R = e->R; sp.T = e->T; sp.B = e->B; sp.D = e->D;
   sp.NS = e->NS; sp.NCW = e->NCW; sp.NAW = e->NAW; sp.SUBB = e->SUBB; sp.NG = e->NG;
@@ -907,7 +918,7 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
 
   CU(cudaEventRecord(e->ev[0], e->stream));
   k_prep<<<(e->m_pad + 255) / 256, 256, 0, e->stream>>>(pp, e->xpx, e->active, e->g, e->vargL, e->prm, e->dacc, e->arrive, e->ctrl,
-                                                       e->out_dev);
+                                                       e->out_dev, e->tile_qend, e->hq, (unsigned long long*)e->corr, e->B, e->D - 1);
   CU(cudaGetLastError());
   CU(cudaEventRecord(e->ev[1], e->stream));
   {

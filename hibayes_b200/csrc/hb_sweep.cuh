@@ -54,7 +54,9 @@ struct SweepParams {
   unsigned int* arrive;
   int* q_snp;
   double* q_delta;
-  int* tile_qend;
+  int* tile_qend;   // per tile: end of its entries in the queue, -1 until published (release)
+  double* corr;     // [T][D-1][B] corrections owed to tile t by tile t-dt, each value its own flag
+  int* hq;          // per tile: queue position after the tile, -1 until known
   int* ctrl;  // [0] tiles committed by the scalar CTA, [1] abort code
   const double* prm;
   SweepOutDev* out;
@@ -169,6 +171,19 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
     double rs[RL];
     int st = 0;
     uint32_t st_par = 0;
+    // dots of the previous sub-stage, reduced; their addition to L2 is issued after the next loads
+    double pend = 0.0;
+    size_t pend_idx = 0;
+    bool have_pend = false;
+    const bool red_lane = (l & 3) == 0;
+    auto flush = [&]() {
+      if (have_pend && red_lane) {
+        const double scaled = (pend * kTwo513) * p.dscale;
+        if (!(fabs(scaled) < 4.0e18)) atomicCAS(ctrl + 1, 0, HB_ABORT_OVERFLOW);
+        atomicAdd(p.dacc + pend_idx, (unsigned long long)__double2ll_rn(scaled));
+      }
+      have_pend = false;
+    };
     for (int t = 0; t < T; ++t) {
       if (!mbar_wait(rfull + (t & 1), (uint32_t)((t >> 1) & 1), ctrl, HB_ABORT_TIMEOUT_PIPE)) return;
       {
@@ -178,57 +193,58 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
       }
       __syncwarp();
       if (lane == 0) hb::mbar_arrive(rempty + (t & 1));
-      double acc[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-#pragma unroll
+#pragma unroll 1
       for (int q = 0; q < Q; ++q) {
         if (!mbar_wait(full + st, st_par, ctrl, HB_ABORT_TIMEOUT_TMA)) return;
-        if (!(p.dbg & 2)) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        {
           const uint8_t* sp = stage0 + (size_t)st * p.stage_bytes + lane_off;
+          uint2 v0 = *(const uint2*)(sp), v1 = *(const uint2*)(sp + R), v2 = *(const uint2*)(sp + 2 * R),
+                v3 = *(const uint2*)(sp + 3 * R);
+          flush();   // the previous sub-stage's dots go out while these loads are in flight
 #pragma unroll
           for (int wd = 0; wd < RL / 8; ++wd) {
-            uint2 v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = *(const uint2*)(sp + k * R + 8 * wd);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              double a = acc[4 * q + k];
-              a = fma(rs[8 * wd + 0], byte_as_scaled(v[k].x, 0x4044), a);
-              a = fma(rs[8 * wd + 1], byte_as_scaled(v[k].x, 0x4144), a);
-              a = fma(rs[8 * wd + 2], byte_as_scaled(v[k].x, 0x4244), a);
-              a = fma(rs[8 * wd + 3], byte_as_scaled(v[k].x, 0x4344), a);
-              a = fma(rs[8 * wd + 4], byte_as_scaled(v[k].y, 0x4044), a);
-              a = fma(rs[8 * wd + 5], byte_as_scaled(v[k].y, 0x4144), a);
-              a = fma(rs[8 * wd + 6], byte_as_scaled(v[k].y, 0x4244), a);
-              a = fma(rs[8 * wd + 7], byte_as_scaled(v[k].y, 0x4344), a);
-              acc[4 * q + k] = a;
+            uint2 n0 = v0, n1 = v1, n2 = v2, n3 = v3;
+            if (wd + 1 < RL / 8) {
+              n0 = *(const uint2*)(sp + 8 * (wd + 1)); n1 = *(const uint2*)(sp + R + 8 * (wd + 1));
+              n2 = *(const uint2*)(sp + 2 * R + 8 * (wd + 1)); n3 = *(const uint2*)(sp + 3 * R + 8 * (wd + 1));
             }
+            if (!(p.dbg & 2)) {
+#define HB_ROW4(i, W, SEL)                                               \
+  a0 = fma(rs[8 * wd + (i)], byte_as_scaled(v0.W, SEL), a0);            \
+  a1 = fma(rs[8 * wd + (i)], byte_as_scaled(v1.W, SEL), a1);            \
+  a2 = fma(rs[8 * wd + (i)], byte_as_scaled(v2.W, SEL), a2);            \
+  a3 = fma(rs[8 * wd + (i)], byte_as_scaled(v3.W, SEL), a3);
+              HB_ROW4(0, x, 0x4044) HB_ROW4(1, x, 0x4144) HB_ROW4(2, x, 0x4244) HB_ROW4(3, x, 0x4344)
+              HB_ROW4(4, y, 0x4044) HB_ROW4(5, y, 0x4144) HB_ROW4(6, y, 0x4244) HB_ROW4(7, y, 0x4344)
+#undef HB_ROW4
+            }
+            v0 = n0; v1 = n1; v2 = n2; v3 = n3;
           }
         }
         __syncwarp();
         if (lane == 0) hb::mbar_arrive(empty + st);
         if (++st == NS) { st = 0; st_par ^= 1u; }
-      }
-      // transposed reduction over the 16 lanes of the half-warp: afterwards lane l holds accumulator l
-#pragma unroll
-      for (int o = 8; o >= 1; o >>= 1) {
-        const bool up = (l & o) != 0;
-#pragma unroll
-        for (int i = 0; i < o; ++i) {
-          const double keep = up ? acc[i + o] : acc[i];
-          const double send = up ? acc[i] : acc[i + o];
-          acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        // transposed reduction of the four dots over the 16 lanes of the half-warp (fixed tree):
+        // lanes 4c .. 4c+3 end up with the slab dot of column c of this warp's four
+        {
+          const bool up8 = (l & 8) != 0, up4 = (l & 4) != 0;
+          const double k0 = up8 ? a2 : a0, s0 = up8 ? a0 : a2;
+          const double k1 = up8 ? a3 : a1, s1 = up8 ? a1 : a3;
+          const double b0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
+          const double b1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
+          const double k2 = up4 ? b1 : b0, s2 = up4 ? b0 : b1;
+          double c0 = k2 + __shfl_xor_sync(0xffffffffu, s2, 4);
+          c0 += __shfl_xor_sync(0xffffffffu, c0, 2);
+          c0 += __shfl_xor_sync(0xffffffffu, c0, 1);
+          pend = c0;
+          // lanes with bit 3 set hold columns 2,3; bit 2 selects the odd one
+          const int kcol = ((l >> 3) & 1) * 2 + ((l >> 2) & 1);
+          pend_idx = (size_t)t * B + q * SUBB + 8 * warp + 4 * h + kcol;
+          have_pend = true;
         }
       }
-      {
-        // accumulator l = 4*q + k  <->  column 64q' ... of the tile: sub-stage q, column 8w + 4h + k of it
-        const int col = (l >> 2) * SUBB + 8 * warp + 4 * h + (l & 3);
-        const double scaled = (acc[0] * kTwo513) * p.dscale;
-        if (!(fabs(scaled) < 4.0e18)) atomicCAS(ctrl + 1, 0, HB_ABORT_OVERFLOW);
-        const long long fx = __double2ll_rn(scaled);
-        atomicAdd(p.dacc + (size_t)t * B + col, (unsigned long long)fx);
-      }
+      flush();
       __syncwarp();
       if (lane == 0) hb::mbar_arrive(dfull + (t % kDotBars));
     }
@@ -278,19 +294,18 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
     int applied = 0;
     for (int t = 0; t < T + D; ++t) {
       if (t >= D) {
-        // residual updates published by the scalar CTA for tile t-D
-        const int need = t - D + 1;
-        int ok = 1;
+        // residual updates published by the scalar workers for tile t-D
+        int qend = 0;
         if (lane == 0) {
-          if (hb::ld_acquire(ctrl) < need) {
+          qend = hb::ld_acquire(p.tile_qend + (t - D));
+          if (qend < 0) {
             Waiter w;
-            while (hb::ld_acquire(ctrl) < need)
-              if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_STREAM)) { ok = 0; break; }
+            while ((qend = hb::ld_acquire(p.tile_qend + (t - D))) < 0)
+              if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_STREAM)) break;
           }
         }
-        ok = __shfl_sync(0xffffffffu, ok, 0);
-        if (!ok) return;
-        const int qend = __ldcg(p.tile_qend + (t - D));
+        qend = __shfl_sync(0xffffffffu, qend, 0);
+        if (qend < 0) return;
         // the tile's changes: 32 queue entries per coalesced read, then the genotype words of eight
         // changed SNPs in flight at a time (all from L2: the columns were streamed D tiles ago)
         for (int q0 = applied; q0 < ((p.dbg & 1) ? applied : qend); q0 += 32) {
@@ -402,10 +417,12 @@ struct CandSet {
   int *idx, *cls;
 };
 
-// Shared memory of the scalar CTA.  Each thread group owns two row buffers into which the Gram rows of
-// its tile's candidates are gathered by TMA bulk copies (one 4B-byte row per candidate and band block).
+// Shared memory of a scalar CTA: two workers (thread groups of B threads), each with its candidate arrays
+// and two row buffers into which the Gram rows of its tile's candidates are gathered by TMA bulk copies
+// (one 4B-byte row per candidate and band block).
 __host__ __device__ inline size_t scalar_fixed_bytes(int B, int D) {
-  size_t b = (2 * (size_t)D * B + 12 * (size_t)B) * 8 + (4 * (size_t)B + 64 + 16) * 4 + 32 + 18 * 8;   // ring, candidates, ints, barriers, timers
+  (void)D;
+  size_t b = (12 * (size_t)B) * 8 + (4 * (size_t)B + 64 + 16) * 4 + 32 + 18 * 8;   // candidates, ints, barriers, timers
   return (b + 127) / 128 * 128;
 }
 // largest row buffer (multiple of 1 KB, at most 44 KB) that still fits the 227 KB of an SM
@@ -418,6 +435,26 @@ __host__ inline size_t scalar_rowbuf_bytes(int B, int D) {
 }
 __host__ inline size_t scalar_smem_bytes(int B, int D) {
   return scalar_fixed_bytes(B, D) + 4 * scalar_rowbuf_bytes(B, D);
+}
+
+// A correction slot that has not been written yet holds this NaN payload (k_prep fills the array).
+constexpr unsigned long long kCorrEmpty = 0x7ff8dead0badf00dull;
+// thread-private hand-off: spin on one 8-byte word until its producer has stored a value
+__device__ __forceinline__ bool poll_corr(const double* slot, double& v, int* ctrl) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(slot) : "memory");
+  if (w == kCorrEmpty) {
+    Waiter wt;
+    do {
+      if (!wt.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) return false;
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(slot) : "memory");
+    } while (w == kCorrEmpty);
+  }
+  v = __longlong_as_double((long long)w);
+  return true;
+}
+__device__ __forceinline__ void post_corr(double* slot, double v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(slot), "l"(__double_as_longlong(v)) : "memory");
 }
 
 // TMA gather of the Gram rows of the k candidates from one band block into a row buffer (one warp)
@@ -500,46 +537,37 @@ __device__ __forceinline__ double band_correction(const CandSet& cs, int k, cons
 
 template <int NF>
 __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
+  // The scalar CTAs hold 2 workers each (thread groups of B threads, one thread per SNP of a tile); worker w
+  // owns tiles w, w + W, w + 2W, ...  A tile goes through three phases:
+  //   P  (any time after its dots arrived)  inputs, corrections owed by the tiles t-D+1 .. t-2, speculated
+  //      classes, candidate list, TMA gather of the candidates' Gram rows
+  //   S  (serial: starts when tile t-1 has handed over its corrections for tile t)  exact right-hand sides,
+  //      candidate chain, verification; ends by handing the corrections for tile t+1 to the next worker
+  //   C  commit: effects, classes, residual-update queue for the streaming CTAs, corrections for t+2 .. t+D-1
+  // Workers exchange data through global memory only: every correction value is its own flag (poll_corr).
   const int B = p.B, D = p.D, T = p.T, F = p.F, model = p.model;
   const int tid = threadIdx.x;
-  const int ngrp = (p.dbg & 8) ? 1 : 2;   // timing experiment: one thread group does every tile
-  if (p.dbg & 48) {
-    // timing experiments: the streaming side alone.  16: every tile is published (without changes) as soon
-    // as its dots have arrived; 32: all tiles are published up front.
-    if (tid == 0) {
-      if (p.dbg & 32) { for (int t = 0; t < T; ++t) p.tile_qend[t] = 0; __threadfence(); hb::st_release(p.ctrl, T); }
-      else for (int t = 0; t < T; ++t) {
-        Waiter w;
-        while (hb::ld_relaxed_u(p.arrive + t) < p.arrive_target)
-          if (!w.keep_waiting(p.ctrl, HB_ABORT_TIMEOUT_SCALAR)) return;
-        p.tile_qend[t] = 0;
-        __threadfence();
-        hb::st_release(p.ctrl, t + 1);
-      }
-      p.out->n_changed = 0; p.out->rounds = 0;
-    }
-    return;
-  }
+  const int ngrp = 2;
   if (tid >= ngrp * B) return;
   const int grp = tid / B, i = tid - grp * B, warp = i >> 5, lane = i & 31, nwarp = B / 32;
+  const int worker = ((int)blockIdx.x - p.S) * ngrp + grp, nworker = p.NG * ngrp;
+  int* ctrl = p.ctrl;
   // ---- shared memory carve-up
-  double* ring;      // [2 groups][D][B]  corrections owed to the tiles in flight, one array per writing group
-  CandSet cs;        // this group's candidate arrays
-  int *wcnt, *wbad;  // 16 per group
-  volatile int* ctl; // [0] tiles final (+ next-tile corrections in place), [1] qbase, [2],[3] per-group abort, [4] rounds, [5] tiles published
-  uint64_t* rbar;    // this group's two row-buffer barriers
+  CandSet cs;        // this worker's candidate arrays
+  int *wcnt, *wbad;  // 16 per worker
+  volatile int* gctl; // per worker: [0] abort flag, [1] qbase
+  uint64_t* rbar;    // this worker's two row-buffer barriers
   int32_t *rows0, *rows1;
   long long* phase;
   {
     double* d = (double*)smem;
-    ring = d; d += 2 * (size_t)D * B;
     double* cbase = d + (size_t)grp * 6 * B; d += 12 * (size_t)B;
     cs.rhs0 = cbase; cs.iv = cbase + B; cs.sdz = cbase + 2 * B; cs.gold = cbase + 3 * B;
     cs.delta = cbase + 4 * B; cs.gnew = cbase + 5 * B;
     int* ip = (int*)d;
     cs.idx = ip + (size_t)grp * 2 * B; cs.cls = cs.idx + B; ip += 4 * (size_t)B;
     wcnt = ip + grp * 16; wbad = ip + 32 + grp * 16; ip += 64;
-    ctl = ip; ip += 16;
+    gctl = ip + grp * 8; ip += 16;
     rbar = (uint64_t*)ip + 2 * grp;
     phase = (long long*)((uint64_t*)ip + 4);
     uint8_t* rb = smem + scalar_fixed_bytes(B, D);
@@ -547,11 +575,8 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
     rows1 = (int32_t*)(rb + (size_t)(2 * grp + 1) * p.rowbuf);
   }
   const int KROW = (int)(p.rowbuf / ((size_t)B * 4));
-  double* ring_mine = ring + (size_t)grp * D * B;
-  int* ctrl = p.ctrl;
   const int gbar = 2 + grp;
-  for (int d = 0; d < D; ++d) ring_mine[(size_t)d * B + i] = 0.0;
-  if (tid < 8) ctl[tid] = 0;
+  if (i < 8) gctl[i] = 0;
   if (i == 0) { hb::mbar_init(rbar, 1); hb::mbar_init(rbar + 1, 1); hb::mbar_fence_init(); }
   hb::named_bar_sync(1, ngrp * B);
 
@@ -559,16 +584,31 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
   const bool dense = (model == HB_MODEL_RR || model == HB_MODEL_A || model == HB_MODEL_L);
   const int nf = (model == HB_MODEL_R) ? F : 2;
   const int NONE = 1 << 30;
+  const int DC = D - 1;   // correction slots per tile
   unsigned n0 = 0, n1 = 0;   // gathers issued so far into rows0 / rows1 (parity of the phase to wait for)
   bool dead = false;
+  int rounds_total = 0;
 
   long long* pc = phase + grp * 9;   // [8] = last time stamp
   if (i == 0) { for (int k = 0; k < 8; ++k) pc[k] = 0; pc[8] = clock64(); }
 #define HB_PHASE(n) do { if (i == 0) { const long long _now = clock64(); pc[n] += _now - pc[8]; pc[8] = _now; } } while (0)
-  for (int t = grp; t < T; t += ngrp) {
+  for (int t = worker; t < T; t += nworker) {
     const int j = t * B + i;
-    const int slot = t % D;
-    // ---- phase 1 (overlaps the other group's serial phase): inputs, speculation, Gram-row gather
+    if (p.dbg & 48) {
+      // timing experiments, the streaming side alone: 16 publishes every tile (without changes) as soon as
+      // its dots have arrived, 32 publishes it at once
+      if (i == 0) {
+        bool ok = true;
+        if (!(p.dbg & 32)) {
+          Waiter w;
+          while (hb::ld_relaxed_u(p.arrive + t) < p.arrive_target)
+            if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) { ok = false; break; }
+        }
+        if (ok) { __threadfence(); hb::st_release(p.tile_qend + t, 0); }
+      }
+      continue;
+    }
+    // ---- phase P: inputs, speculation, Gram-row gather
     const bool act = (j < p.m) && p.active[j];
     const double xx = p.xpx[j];
     const double gold = p.g[j];
@@ -592,20 +632,26 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
           if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) { ok = false; break; }
       }
       hb::fence_acq_rel_gpu();
-      ctl[2 + grp] = (!ok || *((volatile int*)(ctrl + 1)) != 0) ? 1 : 0;
+      gctl[0] = (!ok || *((volatile int*)(ctrl + 1)) != 0) ? 1 : 0;
     }
     hb::named_bar_sync(gbar, B);
-    if (ctl[2 + grp]) break;
+    if (gctl[0]) { dead = true; break; }
     HB_PHASE(0);
     const double base0 = (double)(long long)__ldcg(p.dacc + j) * p.inv_dscale;
     // rhs = x_j' yadj (+ xpx_j g_j)    (Bayes.cpp:593-594, 756-757)
     const double addback = (act && (dense || gold != 0.0)) ? xx * gold : 0.0;
+    // corrections owed by the tiles t-D+1 .. t-2 (oldest first); the one of tile t-1 comes in phase S
+    double cold = 0.0;
+    for (int dt = min(DC, t); dt >= 2; --dt) {
+      double v;
+      if (!poll_corr(p.corr + ((size_t)t * DC + (dt - 1)) * B + i, v, ctrl)) { dead = true; v = 0.0; }
+      cold += v;
+    }
     int cls = 0;
     double gnew = gold;
     if (act) {
-      // the corrections of the previous tile may still be missing here: this is only the speculation
-      const double rguess = ((base0 - ring[(size_t)slot * B + i]) - ring[(size_t)(D + slot) * B + i]) + addback;
-      eval_snp<NF>(model, nf, rguess, q, p.logpi0, cls, gnew);
+      // the corrections of the previous tile are still missing here: this is only the speculation
+      eval_snp<NF>(model, nf, (base0 - cold) + addback, q, p.logpi0, cls, gnew);
     }
     int k = 0, myrank = 0;
     bool cand = false, fast = false;
@@ -649,24 +695,11 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
     };
     compact();
     HB_PHASE(1);
-    // ---- wait until the previous tile is final and its corrections for this tile are in the ring
-    if (i == 0) {
-      bool ok = true;
-      if (ctl[0] < t) {
-        Waiter w;
-        while (ctl[0] < t)
-          if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) { ok = false; break; }
-      }
-      __threadfence_block();
-      ctl[2 + grp] = (!ok || *((volatile int*)(ctrl + 1)) != 0) ? 1 : 0;
-    }
-    hb::named_bar_sync(gbar, B);
-    if (ctl[2 + grp]) break;
+    // ---- phase S: the previous tile is final once its corrections for this tile are here
+    double c1 = 0.0;
+    if (t >= 1 && D > 1 && !poll_corr(p.corr + ((size_t)t * DC) * B + i, c1, ctrl)) dead = true;
     HB_PHASE(2);
-    // ---- serial phase
-    const double rhs0 = ((base0 - ring[(size_t)slot * B + i]) - ring[(size_t)(D + slot) * B + i]) + addback;
-    ring[(size_t)slot * B + i] = 0.0;
-    ring[(size_t)(D + slot) * B + i] = 0.0;
+    const double rhs0 = ((base0 - cold) - c1) + addback;
     int nrounds = 0;
     bool rows1_pending = false;
     for (;;) {
@@ -719,6 +752,7 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
       compact();
     }
     if (dead) break;
+    rounds_total += nrounds;
     // ---- the tile is final.  First what the next tile waits for: its corrections (dt = 1)
     if (has1) {
       double corr;
@@ -728,18 +762,28 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
       } else {
         corr = band_correction(cs, k, G0 + (size_t)B * B, B, i);
       }
-      ring_mine[(size_t)((t + 1) % D) * B + i] += corr;
-    }
-    const int qbase = ctl[1];
-    hb::named_bar_sync(gbar, B);
-    if (i == 0) {
-      ctl[1] = qbase + k;
-      ctl[4] = ctl[4] + nrounds;
-      __threadfence_block();
-      ctl[0] = t + 1;          // hand over to the other group
+      post_corr(p.corr + ((size_t)(t + 1) * DC) * B + i, corr);
     }
     HB_PHASE(6);
-    // ---- commit (overlaps the other group's serial phase)
+    // ---- phase C: commit.  Position of this tile's changes in the residual-update queue
+    if (i == 0) {
+      int qb = 0;
+      bool ok = true;
+      if (t > 0) {
+        qb = hb::ld_relaxed(p.hq + (t - 1));
+        if (qb < 0) {
+          Waiter w;
+          while ((qb = hb::ld_relaxed(p.hq + (t - 1))) < 0)
+            if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) { ok = false; break; }
+        }
+      }
+      if (ok) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.hq + t), "r"(qb + k) : "memory");
+      gctl[1] = qb;
+      gctl[0] = ok ? 0 : 1;
+    }
+    hb::named_bar_sync(gbar, B);
+    if (gctl[0]) { dead = true; break; }
+    const int qbase = gctl[1];
     if (cand) gnew = cs.gnew[myrank];
     if (act) {
       p.g[j] = gnew;
@@ -753,6 +797,7 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
     for (int dt = 2; dt < D; dt += 2) {
       if (t + dt >= T) break;
       const bool two = (dt + 1 < D) && (t + dt + 1 < T);
+      double ca, cb = 0.0;
       if (fast) {
         if (warp == 0) {
           issue_gather(rows0, G0 + (size_t)dt * B * B, cs, k, B, rbar, lane);
@@ -761,42 +806,31 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
         ++n0;
         if (two) ++n1;
         if (!hbk::mbar_wait(rbar, (n0 - 1) & 1, ctrl, HB_ABORT_TIMEOUT_SCALAR)) dead = true;
-        if (!dead) ring_mine[(size_t)((t + dt) % D) * B + i] += band_correction_rows(cs, k, rows0, B, i);
+        ca = dead ? 0.0 : band_correction_rows(cs, k, rows0, B, i);
         if (two) {
           if (!hbk::mbar_wait(rbar + 1, (n1 - 1) & 1, ctrl, HB_ABORT_TIMEOUT_SCALAR)) dead = true;
-          if (!dead) ring_mine[(size_t)((t + dt + 1) % D) * B + i] += band_correction_rows(cs, k, rows1, B, i);
+          cb = dead ? 0.0 : band_correction_rows(cs, k, rows1, B, i);
         }
         if (dt + 2 < D) hb::named_bar_sync(gbar, B);   // every thread is done with the row buffers before they are refilled
       } else {
-        ring_mine[(size_t)((t + dt) % D) * B + i] += band_correction(cs, k, G0 + (size_t)dt * B * B, B, i);
-        if (two) ring_mine[(size_t)((t + dt + 1) % D) * B + i] += band_correction(cs, k, G0 + (size_t)(dt + 1) * B * B, B, i);
+        ca = band_correction(cs, k, G0 + (size_t)dt * B * B, B, i);
+        if (two) cb = band_correction(cs, k, G0 + (size_t)(dt + 1) * B * B, B, i);
       }
+      post_corr(p.corr + ((size_t)(t + dt) * DC + (dt - 1)) * B + i, ca);
+      if (two) post_corr(p.corr + ((size_t)(t + dt + 1) * DC + dt) * B + i, cb);
     }
+    // publish the tile's residual updates to the streaming CTAs
+    __threadfence();
     hb::named_bar_sync(gbar, B);
-    if (i == 0) {
-      // publish to the streaming CTAs, in tile order
-      bool ok = true;
-      if (ctl[5] < t) {
-        Waiter w;
-        while (ctl[5] < t)
-          if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) { ok = false; break; }
-      }
-      if (ok) {
-        p.tile_qend[t] = qbase + k;
-        __threadfence();
-        hb::st_release(ctrl, t + 1);
-        ctl[5] = t + 1;
-      }
-    }
+    if (i == 0) hb::st_release(p.tile_qend + t, qbase + k);
+    if (i == 0 && t == T - 1) p.out->n_changed = qbase + k;
     HB_PHASE(7);
   }
   if (dead) atomicCAS(ctrl + 1, 0, HB_ABORT_TIMEOUT_SCALAR);
-  if (i == 0)
-    for (int k = 0; k < 8; ++k) p.out->phase_clk[grp][k] = pc[k];
-  hb::named_bar_sync(1, ngrp * B);
-  if (tid == 0) {
-    p.out->n_changed = ctl[1];
-    p.out->rounds = ctl[4];
+  if (i == 0) {
+    if (worker < 2)
+      for (int k = 0; k < 8; ++k) p.out->phase_clk[worker][k] = pc[k];
+    atomicAdd(&p.out->rounds, rounds_total);
   }
 }
 
