@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(128) k_gram_imma(const uint8_t* __restrict__ X
 // per-sweep preparation: everything about SNP j that does not depend on the residual
 // ------------------------------------------------------------------------------------------
 struct PrepParams {
-  int m, m_pad, T, iter, model, F;
+  int m, m_pad, T, iter, model, F, use_thr;
   double fold[HB_MAX_FOLD], logpi[HB_MAX_FOLD], vara_fold[HB_MAX_FOLD];
   double vare, dfvara, s2varg;
   hb_key_t key;
@@ -388,6 +388,15 @@ __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8
       prm[prm_idx(f + 2, p.m_pad, j)] = 1.0 / v;
       prm[prm_idx(f + 3, p.m_pad, j)] = sqrt(vare / v) * z;
     }
+    if (p.use_thr) {
+      double a[HB_MAX_FOLD - 1], c[HB_MAX_FOLD - 1], TL[HB_MAX_FOLD - 1], TH[HB_MAX_FOLD - 1];
+      for (int k = 1; k < p.F; ++k) { a[k - 1] = prm[prm_idx(2 + 4 * (k - 1), p.m_pad, j)]; c[k - 1] = prm[prm_idx(3 + 4 * (k - 1), p.m_pad, j)]; }
+      hbk::solve_thresholds<HB_MAX_FOLD>(p.F, u, a, c, p.logpi[0], TL, TH);
+      for (int b = 0; b < p.F - 1; ++b) {
+        prm[prm_idx(kThrField0 + 2 * b, p.m_pad, j)] = TL[b];
+        prm[prm_idx(kThrField0 + 2 * b + 1, p.m_pad, j)] = TH[b];
+      }
+    }
   } else {
     double varg = p.vara_fold[1];
     if (p.model == HB_MODEL_A || p.model == HB_MODEL_B) {
@@ -402,6 +411,12 @@ __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8
     prm[prm_idx(3, p.m_pad, j)] = 0.5 / (vare * v);
     prm[prm_idx(4, p.m_pad, j)] = 1.0 / v;
     prm[prm_idx(5, p.m_pad, j)] = sqrt(vare / v) * z;
+    if (p.use_thr && (p.model == HB_MODEL_B || p.model == HB_MODEL_C)) {
+      double a1[1] = {a}, c1[1] = {0.5 / (vare * v)}, TL[1], TH[1];
+      hbk::solve_thresholds<2>(2, u, a1, c1, p.logpi[0], TL, TH);
+      prm[prm_idx(kThrField0, p.m_pad, j)] = TL[0];
+      prm[prm_idx(kThrField0 + 1, p.m_pad, j)] = TH[0];
+    }
   }
 }
 
@@ -887,6 +902,14 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   for (int k = 0; k < HB_MAX_FOLD; ++k) { pp.fold[k] = in->fold[k]; pp.logpi[k] = in->logpi[k]; pp.vara_fold[k] = in->vara_fold[k]; }
   pp.vare = in->vare; pp.dfvara = in->dfvara; pp.s2varg = in->s2varg;
   pp.key = hb_make_key(e->cfg.seed);
+  // class decisions by thresholds need class-ordered variances (every cumulative probability then decreases in rhs^2)
+  {
+    bool ordered = true;
+    if (in->model_index == HB_MODEL_R)
+      for (int k = 2; k < F; ++k) ordered = ordered && (in->vara_fold[k] >= in->vara_fold[k - 1]) && (in->vara_fold[k - 1] > 0);
+    const bool mixture = in->model_index == HB_MODEL_B || in->model_index == HB_MODEL_C || in->model_index == HB_MODEL_R;
+    pp.use_thr = (mixture && ordered && !getenv("HB_NO_THR")) ? 1 : 0;
+  }
 
   SweepParams sp;
   memset(&sp, 0, sizeof sp);
@@ -898,7 +921,7 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   sp.NS = e->NS; sp.NCW = e->NCW; sp.NAW = e->NAW; sp.SUBB = e->SUBB; sp.NG = e->NG;
   sp.stage_bytes = (uint32_t)e->stage_bytes; sp.off_rbuf = (uint32_t)e->off_rbuf;
   sp.off_bar = (uint32_t)e->off_bar;
-  sp.model = in->model_index; sp.F = F;
+  sp.model = in->model_index; sp.F = F; sp.use_thr = pp.use_thr;
   for (int k = 0; k < HB_MAX_FOLD; ++k) sp.fold[k] = in->fold[k];
   sp.logpi0 = in->logpi[0];
   sp.mu_shift = in->mu_shift;
@@ -952,10 +975,10 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   out->sum_r = h.sum_r; out->sum_r2 = h.sum_r2; out->sum_u = h.sum_u; out->var_u = h.var_u;
   out->n_changed = h.n_changed; out->status = h.status; out->rounds = h.rounds; out->reserved = 0;
   if (getenv("HB_PHASES")) {
-    static const char* nm[8] = {"wait_dots", "guess", "wait_prev", "compact", "chain", "verify", "corr1", "commit"};
+    static const char* nm[8] = {"wait_dots", "guess", "wait_prev", "rows0", "chain", "verify", "post", "commit"};
     for (int g = 0; g < 2; ++g) {
       fprintf(stderr, "[hb phases grp %d]", g);
-      for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%.0f", nm[k], (double)h.phase_clk[g][k] / std::max(1, (sp.dbg & 8) ? e->T : e->T / 2));
+      for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%.0f", nm[k], (double)h.phase_clk[g][k] / std::max(1, e->T / (2 * e->NG)));
       fprintf(stderr, " (cycles per tile)\n");
     }
   }

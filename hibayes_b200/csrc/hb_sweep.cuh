@@ -70,15 +70,18 @@ struct SweepParams {
   double dscale, inv_dscale, mu_shift;
   unsigned arrive_target;
   uint32_t rowbuf;   // bytes of one Gram-row buffer of the scalar CTA
+  int use_thr;   // class decisions of the mixture models by certified thresholds on rhs^2 (k_prep), no exp in the chain
   int dbg;   // timing experiments only (HB_DEBUG env): 1 skip AXPY, 2 skip dot FMAs, 4 skip chain+verify
 };
 
 enum { HB_ABORT_TIMEOUT_STREAM = 1, HB_ABORT_TIMEOUT_SCALAR = 2, HB_ABORT_TIMEOUT_TMA = 3, HB_ABORT_OVERFLOW = 4,
        HB_ABORT_TIMEOUT_PIPE = 5 };
 
-// prm layout (SoA over m_pad): [0] u, [1] z, then for k = 1..F-1: a_k, c_k, 1/v_k, sd_k*z
+// prm layout (SoA over m_pad): [0] u, [1] z, then for k = 1..F-1: a_k, c_k, 1/v_k, sd_k*z; then for every class
+// boundary b = 0..F-2 the certified thresholds TL_b, TH_b on rhs^2 (solve_thresholds)
 __host__ __device__ __forceinline__ size_t prm_idx(int field, size_t m_pad, int j) { return (size_t)field * m_pad + j; }
-constexpr int kPrmFields = 2 + 4 * (HB_MAX_FOLD - 1);
+constexpr int kThrField0 = 2 + 4 * (HB_MAX_FOLD - 1);
+constexpr int kPrmFields = kThrField0 + 2 * (HB_MAX_FOLD - 1);
 
 namespace hbk {
 
@@ -368,24 +371,16 @@ struct SnpPrm {
   double a[NF - 1], c[NF - 1], iv[NF - 1], sdz[NF - 1];
 };
 
-// Conditional draw of one SNP given its right-hand side (Bayes.cpp:592-601, 639-664, 756-801).
-// `nf` = number of mixture classes in play (2 for B/C, F for R); dense models always return class 1.
+// Cumulative class probabilities of one SNP given rr = rhs^2 (Bayes.cpp:759-770 in soft-max form).
 template <int NF>
-__device__ __forceinline__ void eval_snp(int model, int nf, double rhs, const SnpPrm<NF>& q, double logpi0, int& cls, double& gnew) {
-  if (model == HB_MODEL_RR || model == HB_MODEL_A || model == HB_MODEL_L) {
-    cls = 1;
-    gnew = fma(rhs, q.iv[0], q.sdz[0]);
-    if (model == HB_MODEL_L && fabs(gnew) < 1e-6) gnew = 1e-6;  // :728
-    return;
-  }
+__device__ __forceinline__ void class_cum(int nf, double rr, const double* a, const double* c, double logpi0, double* cum) {
   double sv[NF];
-  const double rr = rhs * rhs;
   sv[0] = logpi0;
   double smax = logpi0;
 #pragma unroll
   for (int k = 1; k < NF; ++k)
     if (k < nf) {
-      sv[k] = fma(rr, q.c[k - 1], q.a[k - 1]);
+      sv[k] = fma(rr, c[k - 1], a[k - 1]);
       smax = fmax(smax, sv[k]);
     }
   double tot = 0.0;
@@ -397,18 +392,123 @@ __device__ __forceinline__ void eval_snp(int model, int nf, double rhs, const Sn
     }
   const double inv = 1.0 / tot;
   double acc = 0.0;
-  cls = 0;
+#pragma unroll
+  for (int k = 0; k < NF; ++k)
+    if (k < nf) {
+      acc = fma(sv[k], inv, acc);
+      cum[k] = acc;
+    }
+}
+// inverse-CDF class draw with one uniform (Bayes.cpp:773-781): first k with u < cum_k, 0 if none
+template <int NF>
+__device__ __forceinline__ int class_from_cum(int nf, double u, const double* cum) {
+  int cls = 0;
   bool found = false;
 #pragma unroll
   for (int k = 0; k < NF; ++k)
-    if (k < nf && !found) {
-      acc += sv[k] * inv;
-      if (q.u < acc) { cls = k; found = true; }
-    }
+    if (k < nf && !found && u < cum[k]) { cls = k; found = true; }
+  return cls;
+}
+
+// Conditional draw of one SNP given its right-hand side (Bayes.cpp:592-601, 639-664, 756-801).
+// `nf` = number of mixture classes in play (2 for B/C, F for R); dense models always return class 1.
+template <int NF>
+__device__ __forceinline__ void eval_snp(int model, int nf, double rhs, const SnpPrm<NF>& q, double logpi0, int& cls, double& gnew) {
+  if (model == HB_MODEL_RR || model == HB_MODEL_A || model == HB_MODEL_L) {
+    cls = 1;
+    gnew = fma(rhs, q.iv[0], q.sdz[0]);
+    if (model == HB_MODEL_L && fabs(gnew) < 1e-6) gnew = 1e-6;  // :728
+    return;
+  }
+  double cum[NF];
+  class_cum<NF>(nf, rhs * rhs, q.a, q.c, logpi0, cum);
+  cls = class_from_cum<NF>(nf, q.u, cum);
   gnew = 0.0;
 #pragma unroll
   for (int k = 1; k < NF; ++k)
     if (k == cls) gnew = fma(rhs, q.iv[k - 1], q.sdz[k - 1]);
+}
+
+// Class as a step function of rr = rhs^2.  With class-ordered slopes c_1 <= c_2 <= ... every cumulative
+// probability cum_b(rr) decreases in rr, so "first b with u < cum_b" equals "first b with rr below the root
+// theta_b of cum_b = u".  k_prep brackets each root as [TL_b, TH_b] and certifies both ends with class_cum
+// itself; inside a bracket (or where certification failed: TL = -1, TH = inf) the caller evaluates exactly.
+// Returns the class, or -1 when rr falls inside a bracket.
+template <int NF>
+__device__ __forceinline__ int thr_class(int nf, double rr, const double* TL, const double* TH) {
+#pragma unroll
+  for (int b = 0; b < NF - 1; ++b)
+    if (b < nf - 1) {
+      if (rr <= TL[b]) return b;
+      if (!(rr >= TH[b])) return -1;
+    }
+  return nf - 1;
+}
+
+// Brackets of the class boundaries of one SNP (device, k_prep).  phi_b(rr) = log S_hi - log S_lo - log((1-u)/u)
+// with S_lo = sum_{l<=b} e^{s_l}, S_hi = sum_{l>b} e^{s_l}, s_0 = log pi_0, s_l = a_l + c_l rr, is increasing;
+// safeguarded Newton finds its root, the bracket is widened by 1e-9 relative and both ends are certified with
+// a margin far above the rounding error of class_cum.
+template <int NF>
+__device__ void solve_thresholds(int nf, double u, const double* a, const double* c, double logpi0, double* TL, double* TH) {
+  const double INF = __longlong_as_double(0x7ff0000000000000ll);
+  const double lam = log1p(-u) - log(u);
+  const bool u_ok = (u < 1.0 - 1e-12) && (u > 1e-300);
+  for (int b = 0; b < nf - 1; ++b) {
+    TL[b] = -1.0;
+    TH[b] = INF;
+    if (!u_ok) continue;
+    auto phi = [&](double rr, double& dphi) {
+      double mlo = logpi0, mhi = -INF;
+      for (int l = 1; l < nf; ++l) {
+        const double sl = fma(rr, c[l - 1], a[l - 1]);
+        if (l <= b) mlo = fmax(mlo, sl); else mhi = fmax(mhi, sl);
+      }
+      double Slo = exp(logpi0 - mlo), Clo = 0.0, Shi = 0.0, Chi = 0.0;
+      for (int l = 1; l < nf; ++l) {
+        const double sl = fma(rr, c[l - 1], a[l - 1]);
+        if (l <= b) { const double e = exp(sl - mlo); Slo += e; Clo += c[l - 1] * e; }
+        else { const double e = exp(sl - mhi); Shi += e; Chi += c[l - 1] * e; }
+      }
+      dphi = Chi / Shi - Clo / Slo;
+      return (mhi + log(Shi)) - (mlo + log(Slo)) - lam;
+    };
+    double df, f = phi(0.0, df);
+    double theta = 0.0;
+    bool have = false;
+    if (f > 1e-9) {
+      // never at or below class b: certify at rr = 0 (cum_b decreases from there)
+      double cum[NF];
+      class_cum<NF>(nf, 0.0, a, c, logpi0, cum);
+      if (cum[b] < u * (1.0 - 1e-11)) { TL[b] = -1.0; TH[b] = -1.0; }
+      continue;
+    }
+    if (f < -1e-9) {
+      double lo = 0.0, hi = INF, rr = 0.0;
+      for (int it = 0; it < 60; ++it) {
+        if (!(df > 0.0)) break;
+        double rn = rr - f / df;
+        if (!(rn > lo) || !(rn < hi)) rn = (hi < INF) ? 0.5 * (lo + hi) : fmax(2.0 * rr, rr + 1.0);
+        rr = rn;
+        f = phi(rr, df);
+        if (f < 0.0) lo = rr; else hi = rr;
+        if (fabs(f) < 1e-12) { have = true; theta = rr; break; }
+        if (hi < INF && (hi - lo) <= 1e-13 * hi) { have = true; theta = 0.5 * (lo + hi); f = phi(theta, df); break; }
+      }
+    }
+    if (!have || !(df > 0.0)) continue;
+    const double w = 1e-9 * theta + 2e-10 / df;
+    const double tl = theta - w, th = theta + w;
+    double cum[NF];
+    class_cum<NF>(nf, th, a, c, logpi0, cum);
+    if (!(cum[b] < u * (1.0 - 1e-11))) continue;
+    if (tl >= 0.0) {
+      class_cum<NF>(nf, tl, a, c, logpi0, cum);
+      if (!(cum[b] > u * (1.0 + 1e-11))) continue;
+      TL[b] = tl;
+    }
+    TH[b] = th;
+  }
 }
 
 // candidate arrays of one thread group (B entries each)
@@ -535,6 +635,51 @@ __device__ __forceinline__ double band_correction(const CandSet& cs, int k, cons
   return corr;
 }
 
+// exact int32 -> double for 0 <= g < 2^31 on the full-rate pipe (one DADD instead of a quarter-rate I2F)
+__device__ __forceinline__ double gram_as_double(int g) {
+  return __hiloint2double(0x43300000, g) - 4503599627370496.0;
+}
+
+// Candidate chain of the mixture models (one warp, rows in shared memory).  Lane s tracks
+//   e_s = rhs_s/v_s + sd_s z_s - gold_s        (its effect change if nothing before it in the tile changed)
+// and every earlier candidate s' lowers it by (G[c_s'][c_s]/v_s) delta_s'; when the chain reaches lane s its
+// e_s is final (= delta_s).  One shuffle and one fma per candidate on the dependent path.
+__device__ void chain_candidates(const CandSet& cs, int k, const int32_t* rows, int B, int lane) {
+  for (int sb = 0; sb < k; sb += 32) {
+    const int sidx = sb + lane;
+    const bool valid = sidx < k;
+    const int ci = valid ? cs.idx[sidx] : 0;
+    const double iv = valid ? cs.iv[sidx] : 0.0, gold = valid ? cs.gold[sidx] : 0.0;
+    const double niv = -iv;
+    double e = valid ? fma(cs.rhs0[sidx], iv, cs.sdz[sidx]) - gold : 0.0;
+    // candidates of earlier chunks: their changes are final
+    for (int sp = 0; sp < sb; sp += 8) {
+      double gv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) gv[q] = valid ? gram_as_double(rows[(size_t)(sp + q) * B + ci]) * niv : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) e = fma(gv[q], cs.delta[sp + q], e);
+    }
+    const int nl = min(32, k - sb);
+    // -G[c_(sb+lp)][c_s]/v_s for the next four steps (software pipeline: loads and conversions stay off the chain)
+    auto hload = [&](int lp) -> double {
+      double h = 0.0;
+      if (valid && lp < lane && lp < nl) h = gram_as_double(rows[(size_t)(sb + lp) * B + ci]) * niv;
+      return h;
+    };
+    double h0 = hload(0), h1 = hload(1), h2 = hload(2), h3 = hload(3);
+#pragma unroll 4
+    for (int lp = 0; lp < nl; ++lp) {
+      const double hcur = h0;
+      h0 = h1; h1 = h2; h2 = h3; h3 = hload(lp + 4);
+      const double d = __shfl_sync(0xffffffffu, e, lp);
+      e = fma(hcur, d, e);   // hcur = 0 for the lanes at or before lp: their e is final
+    }
+    if (valid) { cs.delta[sidx] = e; cs.gnew[sidx] = (cs.cls[sidx] > 0) ? gold + e : 0.0; }
+    __syncwarp();
+  }
+}
+
 template <int NF>
 __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
   // The scalar CTAs hold 2 workers each (thread groups of B threads, one thread per SNP of a tile); worker w
@@ -583,6 +728,7 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
   const size_t mp = p.m_pad;
   const bool dense = (model == HB_MODEL_RR || model == HB_MODEL_A || model == HB_MODEL_L);
   const int nf = (model == HB_MODEL_R) ? F : 2;
+  const bool use_thr = p.use_thr && !dense;
   const int NONE = 1 << 30;
   const int DC = D - 1;   // correction slots per tile
   unsigned n0 = 0, n1 = 0;   // gathers issued so far into rows0 / rows1 (parity of the phase to wait for)
@@ -612,18 +758,38 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
     const bool act = (j < p.m) && p.active[j];
     const double xx = p.xpx[j];
     const double gold = p.g[j];
-    SnpPrm<NF> q;
-    q.u = p.prm[prm_idx(0, mp, j)];
+    double TL[NF - 1], TH[NF - 1];
+    double div0 = 0.0, dsdz0 = 0.0;   // dense models: 1/v and sd*z
+    if (use_thr) {
 #pragma unroll
-    for (int k = 0; k < NF - 1; ++k) {
-      q.a[k] = 0; q.c[k] = 0; q.iv[k] = 0; q.sdz[k] = 0;
-      if (k < nf - 1) {
-        q.a[k] = p.prm[prm_idx(2 + 4 * k, mp, j)];
-        q.c[k] = p.prm[prm_idx(3 + 4 * k, mp, j)];
-        q.iv[k] = p.prm[prm_idx(4 + 4 * k, mp, j)];
-        q.sdz[k] = p.prm[prm_idx(5 + 4 * k, mp, j)];
+      for (int b = 0; b < NF - 1; ++b) {
+        TL[b] = -1.0; TH[b] = -1.0;
+        if (b < nf - 1) {
+          TL[b] = p.prm[prm_idx(kThrField0 + 2 * b, mp, j)];
+          TH[b] = p.prm[prm_idx(kThrField0 + 2 * b + 1, mp, j)];
+        }
       }
+    } else if (dense) {
+      div0 = p.prm[prm_idx(4, mp, j)];
+      dsdz0 = p.prm[prm_idx(5, mp, j)];
     }
+    // class of this SNP given its right-hand side: thresholds, or the exact evaluation (rare with thresholds)
+    auto classify = [&](double rhs) -> int {
+      if (dense) return 1;
+      const double rr = rhs * rhs;
+      if (use_thr) {
+        const int c0 = thr_class<NF>(nf, rr, TL, TH);
+        if (c0 >= 0) return c0;
+      }
+      double a[NF - 1], c[NF - 1], cum[NF];
+#pragma unroll
+      for (int kk = 0; kk < NF - 1; ++kk) {
+        a[kk] = 0.0; c[kk] = 0.0;
+        if (kk < nf - 1) { a[kk] = p.prm[prm_idx(2 + 4 * kk, mp, j)]; c[kk] = p.prm[prm_idx(3 + 4 * kk, mp, j)]; }
+      }
+      class_cum<NF>(nf, rr, a, c, p.logpi0, cum);
+      return class_from_cum<NF>(nf, p.prm[prm_idx(0, mp, j)], cum);
+    };
     if (i == 0) {
       bool ok = true;
       if (hb::ld_relaxed_u(p.arrive + t) < p.arrive_target) {
@@ -649,10 +815,8 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
     }
     int cls = 0;
     double gnew = gold;
-    if (act) {
-      // the corrections of the previous tile are still missing here: this is only the speculation
-      eval_snp<NF>(model, nf, (base0 - cold) + addback, q, p.logpi0, cls, gnew);
-    }
+    // the corrections of the previous tile are still missing here: this is only the speculation
+    if (act) cls = classify((base0 - cold) + addback);
     int k = 0, myrank = 0;
     bool cand = false, fast = false;
     const bool has1 = (D > 1 && t + 1 < T);
@@ -676,9 +840,8 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
         cs.gold[myrank] = gold;
         cs.cls[myrank] = cls;
         double iv = 0.0, sdz = 0.0;
-#pragma unroll
-        for (int kk = 1; kk < NF; ++kk)
-          if (kk == cls) { iv = q.iv[kk - 1]; sdz = q.sdz[kk - 1]; }
+        if (dense) { iv = div0; sdz = dsdz0; }
+        else if (cls > 0) { iv = p.prm[prm_idx(4 * cls, mp, j)]; sdz = p.prm[prm_idx(4 * cls + 1, mp, j)]; }   // 1/v_k, sd_k z of class k
         cs.iv[myrank] = iv;
         cs.sdz[myrank] = sdz;
       }
@@ -702,25 +865,39 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
     const double rhs0 = ((base0 - cold) - c1) + addback;
     int nrounds = 0;
     bool rows1_pending = false;
+    double corr1 = 0.0;
     for (;;) {
       ++nrounds;
       if (cand) cs.rhs0[myrank] = rhs0;
       hb::named_bar_sync(gbar, B);
       if (fast && !hbk::mbar_wait(rbar, (n0 - 1) & 1, ctrl, HB_ABORT_TIMEOUT_SCALAR)) dead = true;
-      rows1_pending = fast && has1;
       HB_PHASE(3);
       if (warp == 0 && k > 0 && !dead) {
-        if (fast) solve_candidates<true>(cs, k, G0, rows0, B, model, lane);
+        if (fast && !dense) chain_candidates(cs, k, rows0, B, lane);
+        else if (fast) solve_candidates<true>(cs, k, G0, rows0, B, model, lane);
         else solve_candidates<false>(cs, k, G0, rows0, B, model, lane);
       }
+      if (fast && has1 && !hbk::mbar_wait(rbar + 1, (n1 - 1) & 1, ctrl, HB_ABORT_TIMEOUT_SCALAR)) dead = true;
+      rows1_pending = false;
       hb::named_bar_sync(gbar, B);
       HB_PHASE(4);
-      // exact right-hand side of every SNP of the tile:  x_i'(r - sum_{c<i} x_c delta_c), ascending c
+      // exact right-hand side of every SNP of the tile:  x_i'(r - sum_{c<i} x_c delta_c), ascending c; in the
+      // same pass the corrections this tile owes to the next one (all k changes)
       double rhs = rhs0;
+      corr1 = 0.0;
       if (fast) {
         if (!dead) {
+          if (has1) {
 #pragma unroll 4
-          for (int sidx = 0; sidx < myrank; ++sidx) rhs = fma(-(double)rows0[(size_t)sidx * B + i], cs.delta[sidx], rhs);
+            for (int sidx = 0; sidx < k; ++sidx) {
+              const double d = cs.delta[sidx];
+              if (sidx < myrank) rhs = fma(-gram_as_double(rows0[(size_t)sidx * B + i]), d, rhs);
+              corr1 = fma(gram_as_double(rows1[(size_t)sidx * B + i]), d, corr1);
+            }
+          } else {
+#pragma unroll 4
+            for (int sidx = 0; sidx < myrank; ++sidx) rhs = fma(-gram_as_double(rows0[(size_t)sidx * B + i]), cs.delta[sidx], rhs);
+          }
         }
       } else {
         for (int sb = 0; sb < myrank; sb += 8) {
@@ -731,10 +908,17 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
           for (int e = 0; e < 8; ++e)
             if (sb + e < myrank) rhs = fma(-(double)gv[e], cs.delta[sb + e], rhs);
         }
+        if (has1) corr1 = band_correction(cs, k, G0 + (size_t)B * B, B, i);
       }
       int cls2 = 0;
       double gnew2 = gold;
-      if (act) eval_snp<NF>(model, nf, rhs, q, p.logpi0, cls2, gnew2);
+      if (act) {
+        cls2 = classify(rhs);
+        if (dense) {
+          gnew2 = fma(rhs, div0, dsdz0);
+          if (model == HB_MODEL_L && fabs(gnew2) < 1e-6) gnew2 = 1e-6;  // :728
+        }
+      }
       const bool bad = act && (cls2 != cls);
       const unsigned bal2 = __ballot_sync(0xffffffffu, bad);
       if (lane == 0) wbad[warp] = bal2 ? (warp * 32 + __ffs(bal2) - 1) : NONE;
@@ -754,16 +938,7 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
     if (dead) break;
     rounds_total += nrounds;
     // ---- the tile is final.  First what the next tile waits for: its corrections (dt = 1)
-    if (has1) {
-      double corr;
-      if (fast) {
-        if (!hbk::mbar_wait(rbar + 1, (n1 - 1) & 1, ctrl, HB_ABORT_TIMEOUT_SCALAR)) dead = true;
-        corr = dead ? 0.0 : band_correction_rows(cs, k, rows1, B, i);
-      } else {
-        corr = band_correction(cs, k, G0 + (size_t)B * B, B, i);
-      }
-      post_corr(p.corr + ((size_t)(t + 1) * DC) * B + i, corr);
-    }
+    if (has1) post_corr(p.corr + ((size_t)(t + 1) * DC) * B + i, corr1);
     HB_PHASE(6);
     // ---- phase C: commit.  Position of this tile's changes in the residual-update queue
     if (i == 0) {
