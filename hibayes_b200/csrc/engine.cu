@@ -70,7 +70,7 @@ struct hb_engine {
   int n, m, B, D, S, R, NRG, CL, T, m_pad, NS, nsm;
   int NTC, NTCp, NCW, NAW, SUBB, NG, RL, block_threads;
   size_t Npad, slab_stride, stage_bytes, smem_bytes;
-  size_t off_rbuf, off_bar;
+  size_t off_rbuf, off_bar, off_qbuf;
   uint8_t* Xp = nullptr;
   double *r = nullptr, *u = nullptr, *xpx = nullptr, *g = nullptr, *vargL = nullptr, *gsum = nullptr;
   double *nzrate = nullptr, *wppa = nullptr;
@@ -79,12 +79,13 @@ struct hb_engine {
   int32_t* gram = nullptr;
   bool gram_ready = false, info_ready = false, geno_ready = false;
   unsigned long long* dacc = nullptr;
-  unsigned int* arrive = nullptr;
   int* q_snp = nullptr;
   double* q_delta = nullptr;
-  int* tile_qend = nullptr;
+  int* tile_cnt = nullptr;
   double* corr = nullptr;
-  int* hq = nullptr;
+  double xpx_max = 0.0;
+  unsigned long long* trace = nullptr;
+  int KROW = 0;
   int* ctrl = nullptr;  // [0] progress, [1] abort
   double* prm = nullptr;  // per-SNP sweep parameters, SoA
   int prm_fold = 0;
@@ -355,8 +356,8 @@ struct PrepParams {
 
 __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8_t* __restrict__ active,
                        const double* __restrict__ g, const double* __restrict__ vargL, double* __restrict__ prm,
-                       unsigned long long* __restrict__ dacc, unsigned int* __restrict__ arrive, int* __restrict__ ctrl,
-                       SweepOutDev* __restrict__ out, int* __restrict__ tile_qend, int* __restrict__ hq,
+                       unsigned long long* __restrict__ dacc, int* __restrict__ ctrl, SweepOutDev* __restrict__ out,
+                       int* __restrict__ tile_cnt, int* __restrict__ q_snp, unsigned long long* __restrict__ q_delta,
                        unsigned long long* __restrict__ corr, int B, int DC) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) {
@@ -364,9 +365,11 @@ __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8
     out->n_changed = 0; out->status = 0; out->rounds = 0; out->varg_acc = 0; out->sum_vargL = 0;
     for (int k = 0; k < HB_MAX_FOLD; ++k) out->count[k] = 0;
   }
-  if (j < p.T) { arrive[j] = 0; tile_qend[j] = -1; hq[j] = -1; }
+  if (j < p.T) tile_cnt[j] = -1;
   if (j >= p.m_pad) return;
   dacc[j] = 0ull;
+  q_snp[j] = -1;
+  q_delta[j] = hbk::kCorrEmpty;
   {
     const int t = j / B, i = j - t * B;
     for (int d = 0; d < DC; ++d) corr[((size_t)t * DC + d) * B + i] = hbk::kCorrEmpty;
@@ -422,12 +425,13 @@ __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8
 
 // kernel variants: CTA size (register budget) x number of mixture classes held in registers
 template <int RL>
-static const void* sweep_kernel_rl(int nf) {
-  return nf <= 2 ? (const void*)k_sweep<512, 2, RL> : nf <= 4 ? (const void*)k_sweep<512, 4, RL> : (const void*)k_sweep<512, HB_MAX_FOLD, RL>;
+static const void* sweep_kernel_rl(int nf, bool dense) {
+  if (dense) return (const void*)k_sweep<512, 2, RL, true>;
+  return nf <= 2 ? (const void*)k_sweep<512, 2, RL, false> : nf <= 4 ? (const void*)k_sweep<512, 4, RL, false> : (const void*)k_sweep<512, HB_MAX_FOLD, RL, false>;
 }
-static const void* sweep_kernel_for(int threads, int nf, int rl) {
-  (void)threads;   // every variant is built for CTAs of up to 512 threads
-  return rl == 8 ? sweep_kernel_rl<8>(nf) : rl == 16 ? sweep_kernel_rl<16>(nf) : sweep_kernel_rl<24>(nf);
+// kernel variants: rows per lane x number of mixture classes held in registers x dense/mixture chain
+static const void* sweep_kernel_for(int nf, int rl, bool dense) {
+  return rl == 8 ? sweep_kernel_rl<8>(nf, dense) : rl == 16 ? sweep_kernel_rl<16>(nf, dense) : sweep_kernel_rl<24>(nf, dense);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -611,7 +615,7 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   e->D = cfg->lag_tiles > 0 ? cfg->lag_tiles : 4;
   if (e->B != 64 && e->B != 128 && e->B != 256) { delete e; return hb_set_error("tile_snps must be 64, 128 or 256"); }
   if (e->D > 8) { delete e; return hb_set_error("lag_tiles must be <= 8"); }
-  e->NG = 4;   // scalar CTAs (two workers each)
+  e->NG = 8;   // scalar CTAs (one worker each)
   if (const char* ng = getenv("HB_NG")) e->NG = std::max(1, std::min(16, atoi(ng)));
   e->NG = std::min(e->NG, std::max(1, e->nsm / 8));
   // Row slabs: one streaming CTA per slab, R = 16 lanes x RL rows (RL = 8, 16 or 24); the smallest R whose
@@ -636,7 +640,7 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   e->NTCp = (e->NTC + 31) & ~31;
   e->NCW = e->B / 32;                  // compute warps: 32 columns of the tile each
   e->NAW = e->R / 128;                 // AXPY threads own 4 rows each
-  e->block_threads = std::max(32 * (e->NCW + 2 + e->NAW), 2 * e->B);
+  e->block_threads = std::max(32 * (e->NCW + 1 + e->NAW), 2 * e->B);
   e->T = (e->m + e->B - 1) / e->B;
   e->m_pad = e->T * e->B;
   e->slab_stride = (size_t)e->T * e->B * e->R;
@@ -644,17 +648,24 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   e->SUBB = e->B / 4;
   e->stage_bytes = (size_t)e->SUBB * e->R;
   const size_t rbuf_bytes = 2 * (size_t)e->R * sizeof(double);
-  const size_t bar_bytes = (2 * 16 + 4 + hbk::kDotBars) * 8 + 64;
+  const size_t bar_bytes = (2 * 16 + 4) * 8 + 64;
   const size_t budget = 226 * 1024;
-  e->NS = (int)std::min<size_t>(16, (budget - rbuf_bytes - bar_bytes - 256) / e->stage_bytes);
+  const size_t qbuf_bytes = (size_t)e->B * 12 + 16;   // the current tile's residual updates
+  // sub-stages in flight: enough to cover the HBM latency at full bandwidth and no more -- every byte queued
+  // beyond that only delays the latency-critical reads of the scalar CTAs (4 x 24 KB x 131 SMs = 12 MB in flight)
+  int ns_cap = 4;
+  if (const char* nsv = getenv("HB_NS")) ns_cap = std::max(2, std::min(16, atoi(nsv)));
+  e->NS = (int)std::min<size_t>(ns_cap, (budget - rbuf_bytes - bar_bytes - qbuf_bytes - 256) / e->stage_bytes);
   if (e->NS < 2) { delete e; return hb_set_error("sub-stage of %zu bytes does not fit shared memory", e->stage_bytes); }
   e->off_rbuf = align_up((size_t)e->NS * e->stage_bytes, 128);
   e->off_bar = align_up(e->off_rbuf + rbuf_bytes, 16);
-  const size_t stream_smem = e->off_bar + bar_bytes;
-  const size_t scalar_smem = hbk::scalar_smem_bytes(e->B, e->D);
+  e->off_qbuf = align_up(e->off_bar + bar_bytes, 16);
+  const size_t stream_smem = e->off_qbuf + qbuf_bytes;
+  const size_t scalar_smem = hbk::scalar_smem_bytes(e->B);
+  e->KROW = hbk::scalar_krow(e->B);
   e->smem_bytes = std::max(stream_smem, scalar_smem);
-  for (int nf : {2, 4, HB_MAX_FOLD}) {
-    const void* fn = sweep_kernel_for(e->block_threads, nf, e->RL);
+  for (int v = 0; v < 4; ++v) {
+    const void* fn = sweep_kernel_for(v == 0 ? 2 : v == 1 ? 4 : HB_MAX_FOLD, e->RL, v == 3);
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, e->block_threads, e->smem_bytes));
@@ -676,11 +687,9 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   CU(cudaMalloc(&e->active, mp)); CU(cudaMemsetAsync(e->active, 0, mp, e->stream));
   CU(cudaMalloc(&e->tracker, mp * 4)); CU(cudaMemsetAsync(e->tracker, 0, mp * 4, e->stream));
   CU(cudaMalloc(&e->dacc, mp * 8));
-  CU(cudaMalloc(&e->arrive, (size_t)e->T * 4));
   CU(cudaMalloc(&e->q_snp, mp * 4));
   CU(cudaMalloc(&e->q_delta, mp * 8));
-  CU(cudaMalloc(&e->tile_qend, (size_t)e->T * 4));
-  CU(cudaMalloc(&e->hq, (size_t)e->T * 4));
+  CU(cudaMalloc(&e->tile_cnt, (size_t)e->T * 4));
   CU(cudaMalloc(&e->corr, std::max<size_t>(1, (size_t)e->m_pad * (e->D - 1)) * 8));
   CU(cudaMalloc(&e->ctrl, 64)); CU(cudaMemsetAsync(e->ctrl, 0, 64, e->stream));
   CU(cudaMalloc(&e->out_dev, sizeof(SweepOutDev)));
@@ -696,8 +705,8 @@ extern "C" void hb_engine_destroy(hb_engine* e) {
   cudaSetDevice(e->cfg.device);
   cudaFree(e->Xp); cudaFree(e->r); cudaFree(e->u); cudaFree(e->xpx); cudaFree(e->g); cudaFree(e->gsum);
   cudaFree(e->nzrate); cudaFree(e->wppa); cudaFree(e->vargL); cudaFree(e->active); cudaFree(e->tracker);
-  cudaFree(e->gram); cudaFree(e->dacc); cudaFree(e->arrive); cudaFree(e->q_snp); cudaFree(e->q_delta);
-  cudaFree(e->tile_qend); cudaFree(e->hq); cudaFree(e->corr); cudaFree(e->ctrl); cudaFree(e->prm); cudaFree(e->out_dev); cudaFree(e->post_partial); cudaFree(e->fold_dev); cudaFree(e->wstart); cudaFree(e->wmem);
+  cudaFree(e->gram); cudaFree(e->dacc); cudaFree(e->q_snp); cudaFree(e->q_delta);
+  cudaFree(e->tile_cnt); cudaFree(e->corr); cudaFree(e->ctrl); cudaFree(e->prm); cudaFree(e->out_dev); cudaFree(e->post_partial); cudaFree(e->fold_dev); cudaFree(e->wstart); cudaFree(e->wmem);
   for (int i = 0; i < 4; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -831,6 +840,8 @@ extern "C" int hb_engine_col_stats(hb_engine* e, double* xpx, double* sumx) {
 extern "C" int hb_engine_set_snp_info(hb_engine* e, const double* xpx_global, const uint8_t* active) {
   if (!e || !xpx_global || !active) return hb_set_error("hb_engine_set_snp_info: null argument");
   CU(cudaSetDevice(e->cfg.device));
+  e->xpx_max = 0.0;
+  for (int q = 0; q < e->m; ++q) e->xpx_max = std::max(e->xpx_max, xpx_global[q]);
   CU(cudaMemcpyAsync(e->xpx, xpx_global, (size_t)e->m * 8, cudaMemcpyHostToDevice, e->stream));
   CU(cudaMemcpyAsync(e->active, active, (size_t)e->m, cudaMemcpyHostToDevice, e->stream));
   CU(cudaStreamSynchronize(e->stream));
@@ -914,39 +925,41 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   SweepParams sp;
   memset(&sp, 0, sizeof sp);
   sp.Xp = e->Xp; sp.r = e->r; sp.u = e->u; sp.xpx = e->xpx; sp.active = e->active; sp.g = e->g; sp.tracker = e->tracker;
-  sp.gram = e->gram; sp.dacc = e->dacc; sp.arrive = e->arrive; sp.q_snp = e->q_snp; sp.q_delta = e->q_delta;
-  sp.tile_qend = e->tile_qend; sp.corr = e->corr; sp.hq = e->hq; sp.ctrl = e->ctrl; sp.prm = e->prm; sp.out = e->out_dev;
+  sp.gram = e->gram; sp.dacc = e->dacc; sp.q_snp = e->q_snp; sp.q_delta = e->q_delta;
+  if (getenv("HB_TRACE") && !e->trace) { CU(cudaMalloc(&e->trace, (size_t)e->T * 64)); CU(cudaMemset(e->trace, 0, (size_t)e->T * 64)); }
+  sp.trace = e->trace;
+  sp.tile_cnt = e->tile_cnt; sp.corr = e->corr; sp.ctrl = e->ctrl; sp.prm = e->prm; sp.out = e->out_dev;
   sp.slab_stride = e->slab_stride; sp.m_pad = e->m_pad;
   sp.n = e->n; sp.m = e->m; sp.S = e->S; sp.R = e->R; sp.T = e->T; sp.B = e->B; sp.D = e->D;
-  sp.NS = e->NS; sp.NCW = e->NCW; sp.NAW = e->NAW; sp.SUBB = e->SUBB; sp.NG = e->NG;
-  sp.stage_bytes = (uint32_t)e->stage_bytes; sp.off_rbuf = (uint32_t)e->off_rbuf;
+  sp.NS = e->NS; sp.NCW = e->NCW; sp.NAW = e->NAW; sp.SUBB = e->SUBB; sp.NG = e->NG; sp.KROW = e->KROW;
+  sp.stage_bytes = (uint32_t)e->stage_bytes; sp.off_rbuf = (uint32_t)e->off_rbuf; sp.off_qbuf = (uint32_t)e->off_qbuf;
   sp.off_bar = (uint32_t)e->off_bar;
   sp.model = in->model_index; sp.F = F; sp.use_thr = pp.use_thr;
   for (int k = 0; k < HB_MAX_FOLD; ++k) sp.fold[k] = in->fold[k];
   sp.logpi0 = in->logpi[0];
   sp.mu_shift = in->mu_shift;
-  // fixed-point scale of the dot accumulators: |x_j'r| <= ||x_j|| ||r|| <= 2 sqrt(n) ||r||, with a
-  // factor 16 of head-room for the residual changing during the sweep
+  // fixed-point scale of the dot accumulators: |x_j'r| <= ||x_j|| ||r|| <= sqrt(max_j xpx_j) ||r|| for the whole
+  // dot and for every slab's part of it, with a factor 8 of head-room for the residual changing during the
+  // sweep; the sums must stay below 2^54 (the low byte of an accumulator counts the slabs that have arrived)
   {
-    const double ntot = (double)e->n * std::max(1, e->cfg.world);
-    double bound = 2.0 * sqrt(ntot * std::max(in->rnorm2_bound, 1e-300)) * 16.0;
-    int ex = (int)floor(log2(4.0e18 / bound));
+    const double xmax = e->xpx_max > 0 ? e->xpx_max : 4.0 * (double)e->n * std::max(1, e->cfg.world);
+    double bound = sqrt(xmax * std::max(in->rnorm2_bound, 1e-300)) * 8.0;
+    int ex = (int)floor(log2(hbk::kFixLimit / bound));
     ex = std::max(-900, std::min(ex, 900));
     sp.dscale = ldexp(1.0, ex);
     sp.inv_dscale = ldexp(1.0, -ex);
   }
-  sp.arrive_target = (unsigned)e->S;
-  sp.rowbuf = (uint32_t)hbk::scalar_rowbuf_bytes(e->B, e->D);
   { const char* dbg = getenv("HB_DEBUG"); sp.dbg = dbg ? atoi(dbg) : 0; }
 
+  const bool dense_model = in->model_index == HB_MODEL_RR || in->model_index == HB_MODEL_A || in->model_index == HB_MODEL_L;
   CU(cudaEventRecord(e->ev[0], e->stream));
-  k_prep<<<(e->m_pad + 255) / 256, 256, 0, e->stream>>>(pp, e->xpx, e->active, e->g, e->vargL, e->prm, e->dacc, e->arrive, e->ctrl,
-                                                       e->out_dev, e->tile_qend, e->hq, (unsigned long long*)e->corr, e->B, e->D - 1);
+  k_prep<<<(e->m_pad + 255) / 256, 256, 0, e->stream>>>(pp, e->xpx, e->active, e->g, e->vargL, e->prm, e->dacc, e->ctrl, e->out_dev,
+                                                       e->tile_cnt, e->q_snp, (unsigned long long*)e->q_delta, (unsigned long long*)e->corr, e->B, e->D - 1);
   CU(cudaGetLastError());
   CU(cudaEventRecord(e->ev[1], e->stream));
   {
     void* args[] = {(void*)&sp};
-    CU(cudaLaunchCooperativeKernel(sweep_kernel_for(e->block_threads, in->model_index == HB_MODEL_R ? F : 2, e->RL), dim3(e->S + e->NG), dim3(e->block_threads), args, e->smem_bytes, e->stream));
+    CU(cudaLaunchCooperativeKernel(sweep_kernel_for(in->model_index == HB_MODEL_R ? F : 2, e->RL, dense_model), dim3(e->S + e->NG), dim3(e->block_threads), args, e->smem_bytes, e->stream));
   }
   CU(cudaEventRecord(e->ev[2], e->stream));
   CU(cudaMemcpyAsync(e->fold_dev, in->fold, HB_MAX_FOLD * 8, cudaMemcpyHostToDevice, e->stream));
@@ -974,11 +987,18 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   out->varg_acc = h.varg_acc; out->sum_vargL = h.sum_vargL;
   out->sum_r = h.sum_r; out->sum_r2 = h.sum_r2; out->sum_u = h.sum_u; out->var_u = h.var_u;
   out->n_changed = h.n_changed; out->status = h.status; out->rounds = h.rounds; out->reserved = 0;
+  if (e->trace && getenv("HB_TRACE")) {
+    // event stamps of the tiles of this sweep -> file (ns): see tools/trace_report.py
+    std::vector<unsigned long long> tr((size_t)e->T * 8);
+    CU(cudaMemcpy(tr.data(), e->trace, tr.size() * 8, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(getenv("HB_TRACE"), "wb")) { fwrite(tr.data(), 8, tr.size(), f); fclose(f); }
+  }
   if (getenv("HB_PHASES")) {
-    static const char* nm[8] = {"wait_dots", "guess", "wait_prev", "rows0", "chain", "verify", "post", "commit"};
+    static const char* nm[16] = {"wait_dots", "guess", "wait_prev", "bar_rhs0", "chain", "first", "post", "commit",
+                                 "bar_chain", "loop", "bar_part", "classify", "bar_bad", "-", "-", "-"};
     for (int g = 0; g < 2; ++g) {
-      fprintf(stderr, "[hb phases grp %d]", g);
-      for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%.0f", nm[k], (double)h.phase_clk[g][k] / std::max(1, e->T / (2 * e->NG)));
+      fprintf(stderr, "[hb phases worker %d]", g);
+      for (int k = 0; k < 13; ++k) fprintf(stderr, " %s=%.0f", nm[k], (double)h.phase_clk[g][k] / std::max(1, e->T / e->NG));
       fprintf(stderr, " (cycles per tile)\n");
     }
   }

@@ -2,27 +2,29 @@
 //
 // One cooperative launch per MCMC iteration replaces the switch(model_index) block of Bayes()
 // (/root/reference/src/Bayes.cpp:586-816): grid = S streaming CTAs (one row slab each, one per SM)
-// + 1 scalar CTA.  X is read from HBM exactly once per sweep.
+// + NG scalar CTAs.  X is read from HBM exactly once per sweep.
 //
 // Streaming CTA (warp-specialised):
-//   TMA warp      cp.async.bulk ring: sub-stages of SUBB SNP columns x R rows (raw int8)
-//   compute warps x_j'r over the slab: the residual slab lives in registers (16 rows / thread),
-//                 one PRMT + one DFMA per genotype, per-thread partials -> shared memory
-//   reducer warp  fixed-order sum of the partials over row groups, fixed-point int64 atomicAdd to
-//                 the per-SNP accumulators in L2 (order-independent => deterministic), tile arrival
-//   AXPY warps    own the master copy of the slab's residual/u rows in registers; D tiles later
-//                 they apply the effect changes the scalar CTA published (r -= x*delta, u += x*delta,
+//   TMA warp      cp.async.bulk ring: sub-stages of B/4 SNP columns x R rows (raw int8)
+//   compute warps x_j'r over the slab: a lane keeps RL residual rows in registers for a whole tile and one
+//                 running dot per column (PRMT + DFMA per genotype); a transposed shuffle reduction over
+//                 the 16 lanes of a half-warp completes the slab dots, which are added as fixed-point
+//                 integers (with an arrival count in the low byte) to the per-SNP accumulators in L2:
+//                 order-independent, hence deterministic, and complete exactly when the count says so
+//   AXPY warps    own the master copy of the slab's residual/u rows in registers; D tiles later they apply
+//                 the effect changes the scalar CTAs published (r -= x*delta, u += x*delta,
 //                 Bayes.cpp:787-789, in SNP order) and republish the slab for the compute warps
 //
-// Scalar CTA (two thread groups ping-pong over the tiles, one thread per SNP of a tile of B SNPs):
-//   turns the reduced dots of tile t into the conditional draws of Bayes.cpp:756-801.  The chain
-//   x_j'r depends on every earlier change; inside a tile that dependence is the exact integer Gram
-//   block G = X_t'X_t, across the D-1 tiles still in flight it is the Gram band.  Classes are
-//   speculated for the whole tile, the changed SNPs ("candidates") are chained by one warp as a
-//   small triangular recurrence in SNP order, every SNP is then re-evaluated with its exact
-//   right-hand side and the first SNP whose class differs from the speculation restarts the round
-//   (everything before it is final).  Random draws are position-addressed (hb_rng.h), so
-//   re-evaluation reuses the same uniform/normal and the result equals the one-SNP-at-a-time sweep.
+// Scalar CTAs (one worker each, tiles round-robin, one thread pair per SNP of a tile of B SNPs):
+//   turn the reduced dots of tile t into the conditional draws of Bayes.cpp:756-801.  The chain x_j'r
+//   depends on every earlier change; inside a tile that dependence is the exact integer Gram block
+//   G = X_t'X_t, across the D-1 tiles still in flight it is the Gram band.  Classes are speculated for the
+//   whole tile, the changed SNPs ("candidates") are chained by one warp as a small triangular recurrence
+//   in SNP order, every SNP is then re-evaluated with its exact right-hand side and the first SNP whose
+//   class differs from the speculation restarts the round.  Random draws are position-addressed
+//   (hb_rng.h), so re-evaluation reuses the same uniform/normal and the result equals the
+//   one-SNP-at-a-time sweep.  Workers hand over through global memory; every handed-over value is its own
+//   flag (a NaN payload / -1 means "not yet written"), so no hand-over needs a fence or a second round trip.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -39,7 +41,7 @@ struct SweepOutDev {
   int status;
   int rounds;        // speculation rounds summed over tiles (diagnostic)
   int pad;
-  long long phase_clk[2][8];   // scalar CTA: SM cycles per phase, per thread group (diagnostic)
+  long long phase_clk[2][16];  // scalar workers 0 and 1: SM cycles per phase (diagnostic)
 };
 
 struct SweepParams {
@@ -50,28 +52,25 @@ struct SweepParams {
   double* g;
   int32_t* tracker;
   const int32_t* gram;
-  unsigned long long* dacc;
-  unsigned int* arrive;
-  int* q_snp;
-  double* q_delta;
-  int* tile_qend;   // per tile: end of its entries in the queue, -1 until published (release)
-  double* corr;     // [T][D-1][B] corrections owed to tile t by tile t-dt, each value its own flag
-  int* hq;          // per tile: queue position after the tile, -1 until known
-  int* ctrl;  // [0] tiles committed by the scalar CTA, [1] abort code
+  unsigned long long* dacc;   // per SNP: sum over slabs of (fixed-point dot << 8) + 1
+  int* q_snp;                 // [T][B] changed SNPs of tile t (global index), -1 = not yet written
+  double* q_delta;            // [T][B] their effect changes, kCorrEmpty = not yet written
+  int* tile_cnt;              // per tile: number of changes, -1 until known
+  double* corr;               // [T][D-1][B] corrections owed to tile t by tile t-dt, kCorrEmpty = not yet written
+  int* ctrl;                  // [1] abort code
+  unsigned long long* trace;  // diagnostics (HB_TRACE): [T][8] globaltimer stamps of a tile's events, or null
   const double* prm;
   SweepOutDev* out;
   size_t slab_stride, m_pad;
   int n, m, S, R, T, B, D, NS;
-  int NCW, NAW, SUBB, NG;
-  uint32_t stage_bytes, off_rbuf, off_bar;
+  int NCW, NAW, SUBB, NG, KROW;
+  uint32_t stage_bytes, off_rbuf, off_bar, off_qbuf;
   int model, F;
   double fold[HB_MAX_FOLD];
   double logpi0;
   double dscale, inv_dscale, mu_shift;
-  unsigned arrive_target;
-  uint32_t rowbuf;   // bytes of one Gram-row buffer of the scalar CTA
   int use_thr;   // class decisions of the mixture models by certified thresholds on rhs^2 (k_prep), no exp in the chain
-  int dbg;   // timing experiments only (HB_DEBUG env): 1 skip AXPY, 2 skip dot FMAs, 4 skip chain+verify
+  int dbg;       // timing experiments only (HB_DEBUG env): 1 skip AXPY, 2 skip dot FMAs, 16/32 streaming side alone
 };
 
 enum { HB_ABORT_TIMEOUT_STREAM = 1, HB_ABORT_TIMEOUT_SCALAR = 2, HB_ABORT_TIMEOUT_TMA = 3, HB_ABORT_OVERFLOW = 4,
@@ -87,8 +86,10 @@ namespace hbk {
 
 constexpr double kTwo513 = 2.6815615859885194e154;     // 2^513
 constexpr double kTwoM513 = 3.7291703656001034e-155;   // 2^-513
-constexpr long long kTimeoutNs = 4000000000ll;
-constexpr int kDotBars = 16;          // every wait is bounded: a lost signal aborts, it never hangs
+constexpr long long kTimeoutNs = 4000000000ll;          // every wait is bounded: a lost signal aborts, it never hangs
+constexpr double kFixLimit = 1.8e16;                    // |fixed-point partial dot| < 2^54: 8 bits left for the count
+// A slot that has not been written yet holds this NaN payload (k_prep fills the arrays).
+constexpr unsigned long long kCorrEmpty = 0x7ff8dead0badf00dull;
 
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -100,8 +101,8 @@ struct Waiter {
   unsigned long long t0 = 0;
   unsigned spins = 0;
   // returns false when the wait must be abandoned (abort flag raised somewhere, or timeout)
-  __device__ __forceinline__ bool keep_waiting(int* ctrl, int code) {
-    if ((++spins & 0xff) == 0) {
+  __device__ __noinline__ bool keep_waiting(int* ctrl, int code) {
+    if ((++spins & 0x3f) == 0) {
       __nanosleep(32);
       if (*((volatile int*)(ctrl + 1)) != 0) return false;
       const unsigned long long now = gtimer();
@@ -123,24 +124,51 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* c
   return true;
 }
 
+#define HB_TRACE(t, ev) do { if (p.trace) p.trace[(size_t)(t) * 8 + (ev)] = gtimer(); } while (0)
+
 __device__ __forceinline__ double byte_as_scaled(uint32_t w, uint32_t sel) {
   // genotype byte -> mantissa bits 48..55 of a double: value = byte * 2^-1026 (exact, denormal)
   return __hiloint2double((int)__byte_perm(w, 0u, sel), 0);
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const void* p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
+}
+__device__ __forceinline__ void st_relaxed_u64(void* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_s32(int* p, int v) {
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// thread-private hand-over: spin on one 8-byte word until its producer has stored a value
+__device__ __noinline__ bool poll_corr_slow(const double* slot, double& v, int* ctrl) {
+  unsigned long long w;
+  Waiter wt;
+  do {
+    if (!wt.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) return false;
+    w = ld_relaxed_u64(slot);
+  } while (w == kCorrEmpty);
+  v = __longlong_as_double((long long)w);
+  return true;
+}
+__device__ __forceinline__ bool poll_corr(const double* slot, double& v, int* ctrl) {
+  const unsigned long long w = ld_relaxed_u64(slot);
+  if (w == kCorrEmpty) return poll_corr_slow(slot, v, ctrl);
+  v = __longlong_as_double((long long)w);
+  return true;
+}
+__device__ __forceinline__ void post_corr(double* slot, double v) { st_relaxed_u64(slot, (unsigned long long)__double_as_longlong(v)); }
 
 // ------------------------------------------------------------------------------------------
 // streaming CTA
 // ------------------------------------------------------------------------------------------
 // Layout of one CTA (slab of R = 16*RL rows, tile of B = 32*NCW SNP columns, sub-stage = B/4 columns):
-//   compute warp w, half-warp h, lane l: rows [RL*l, RL*l + RL) of the slab, held in registers for the
-//   whole tile; in every sub-stage q it takes the four columns 8w + 4h + {0..3} and keeps one running
-//   dot per column (16 per tile).  After the tile's four sub-stages the 16 lanes of a half-warp hold
-//   16 x 16 partial dots; a transposed shuffle reduction (8+4+2+1 exchanges, fixed tree) leaves lane l
-//   with the complete slab dot of accumulator l, i.e. of column 64*(l>>2)... (see col_of_acc) -- no
-//   shared-memory partials, no cross-warp reduction.  The lane adds it, as fixed-point int64, to the
-//   per-SNP accumulator in L2 (order-independent => deterministic).
+//   compute warp w, half-warp h, lane l: rows [RL*l, RL*l + RL) of the slab; in sub-stage q it takes the four
+//   columns 8w + 4h + {0..3} and keeps one running dot per column (16 per tile).  After the tile's four
+//   sub-stages the 16 lanes of a half-warp hold 16 x 16 partial dots; a transposed shuffle reduction (8+4+2+1
+//   exchanges, fixed tree) leaves lane l with the complete slab dot of accumulator l.
 template <int RL>
 __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -154,13 +182,14 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
   uint64_t* empty = full + NS;
   uint64_t* rfull = empty + NS;
   uint64_t* rempty = rfull + 2;
-  uint64_t* dfull = rempty + 2;                  // kDotBars barriers: dots of tile t added to L2 by every compute warp
+  double* qd = (double*)(smem + p.off_qbuf);     // the current tile's residual updates: B deltas, B SNPs, count
+  int* qj = (int*)(qd + B);
+  int* qcnt = qj + B;
   int* ctrl = p.ctrl;
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { hb::mbar_init(full + i, 1); hb::mbar_init(empty + i, NCW); }
     for (int i = 0; i < 2; ++i) { hb::mbar_init(rfull + i, NAW); hb::mbar_init(rempty + i, NCW); }
-    for (int i = 0; i < kDotBars; ++i) hb::mbar_init(dfull + i, NCW);
     hb::mbar_fence_init();
   }
   __syncthreads();
@@ -171,22 +200,12 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
     // ---------------- compute warps
     const int h = lane >> 4, l = lane & 15;
     const uint32_t lane_off = (uint32_t)((8 * warp + 4 * h) * R + RL * l);
+    // accumulator l = 4*q + k  <->  column q*SUBB + 8w + 4h + k of the tile
+    const int my_col = (l >> 2) * SUBB + 8 * warp + 4 * h + (l & 3);
+    const double to_fix = p.dscale;
     double rs[RL];
     int st = 0;
     uint32_t st_par = 0;
-    // dots of the previous sub-stage, reduced; their addition to L2 is issued after the next loads
-    double pend = 0.0;
-    size_t pend_idx = 0;
-    bool have_pend = false;
-    const bool red_lane = (l & 3) == 0;
-    auto flush = [&]() {
-      if (have_pend && red_lane) {
-        const double scaled = (pend * kTwo513) * p.dscale;
-        if (!(fabs(scaled) < 4.0e18)) atomicCAS(ctrl + 1, 0, HB_ABORT_OVERFLOW);
-        atomicAdd(p.dacc + pend_idx, (unsigned long long)__double2ll_rn(scaled));
-      }
-      have_pend = false;
-    };
     for (int t = 0; t < T; ++t) {
       if (!mbar_wait(rfull + (t & 1), (uint32_t)((t >> 1) & 1), ctrl, HB_ABORT_TIMEOUT_PIPE)) return;
       {
@@ -196,7 +215,8 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
       }
       __syncwarp();
       if (lane == 0) hb::mbar_arrive(rempty + (t & 1));
-#pragma unroll 1
+      double acc[16];
+#pragma unroll
       for (int q = 0; q < Q; ++q) {
         if (!mbar_wait(full + st, st_par, ctrl, HB_ABORT_TIMEOUT_TMA)) return;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -204,7 +224,6 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
           const uint8_t* sp = stage0 + (size_t)st * p.stage_bytes + lane_off;
           uint2 v0 = *(const uint2*)(sp), v1 = *(const uint2*)(sp + R), v2 = *(const uint2*)(sp + 2 * R),
                 v3 = *(const uint2*)(sp + 3 * R);
-          flush();   // the previous sub-stage's dots go out while these loads are in flight
 #pragma unroll
           for (int wd = 0; wd < RL / 8; ++wd) {
             uint2 n0 = v0, n1 = v1, n2 = v2, n3 = v3;
@@ -228,28 +247,26 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
         __syncwarp();
         if (lane == 0) hb::mbar_arrive(empty + st);
         if (++st == NS) { st = 0; st_par ^= 1u; }
-        // transposed reduction of the four dots over the 16 lanes of the half-warp (fixed tree):
-        // lanes 4c .. 4c+3 end up with the slab dot of column c of this warp's four
-        {
-          const bool up8 = (l & 8) != 0, up4 = (l & 4) != 0;
-          const double k0 = up8 ? a2 : a0, s0 = up8 ? a0 : a2;
-          const double k1 = up8 ? a3 : a1, s1 = up8 ? a1 : a3;
-          const double b0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
-          const double b1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
-          const double k2 = up4 ? b1 : b0, s2 = up4 ? b0 : b1;
-          double c0 = k2 + __shfl_xor_sync(0xffffffffu, s2, 4);
-          c0 += __shfl_xor_sync(0xffffffffu, c0, 2);
-          c0 += __shfl_xor_sync(0xffffffffu, c0, 1);
-          pend = c0;
-          // lanes with bit 3 set hold columns 2,3; bit 2 selects the odd one
-          const int kcol = ((l >> 3) & 1) * 2 + ((l >> 2) & 1);
-          pend_idx = (size_t)t * B + q * SUBB + 8 * warp + 4 * h + kcol;
-          have_pend = true;
+        acc[4 * q + 0] = a0; acc[4 * q + 1] = a1; acc[4 * q + 2] = a2; acc[4 * q + 3] = a3;
+      }
+      // transposed reduction over the 16 lanes of the half-warp: afterwards lane l holds accumulator l
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) {
+        const bool up = (l & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+          const double keep = up ? acc[i + o] : acc[i];
+          const double send = up ? acc[i] : acc[i + o];
+          acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
       }
-      flush();
-      __syncwarp();
-      if (lane == 0) hb::mbar_arrive(dfull + (t % kDotBars));
+      {
+        const double scaled = (acc[0] * kTwo513) * to_fix;
+        if (!(fabs(scaled) < kFixLimit)) atomicCAS(ctrl + 1, 0, HB_ABORT_OVERFLOW);
+        const unsigned long long fx = (unsigned long long)__double2ll_rn(scaled);
+        atomicAdd(p.dacc + (size_t)t * B + my_col, (fx << 8) + 1ull);   // fire and forget: the count validates the sum
+        if (s == 0 && tid == 0) HB_TRACE(t, 7);
+      }
     }
     return;
   }
@@ -267,22 +284,10 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
     }
     return;
   }
-  if (warp == NCW + 1) {
-    // ---------------- committer: once every compute warp has added its dots of tile t, make them visible
-    // device-wide and count the slab in (the fence stalls only this warp)
-    if (lane == 0) {
-      for (int t = 0; t < T; ++t) {
-        if (!mbar_wait(dfull + (t % kDotBars), (uint32_t)((t / kDotBars) & 1), ctrl, HB_ABORT_TIMEOUT_PIPE)) return;
-        __threadfence();
-        atomicAdd(p.arrive + t, 1u);
-      }
-    }
-    return;
-  }
-  if (warp < NCW + 2 + NAW) {
+  if (warp < NCW + 1 + NAW) {
     // ---------------- AXPY warps: master copy of the slab's residual and u rows (4 rows / thread,
     // held as value * 2^-513 so that the denormal genotype factors stay exact)
-    const int a = tid - 32 * (NCW + 2);
+    const int a = tid - 32 * (NCW + 1);
     const int row0 = 4 * a;
     const bool has = row0 < R;
     double rm[4], um[4];
@@ -294,51 +299,75 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
       rm[i] = rv * kTwoM513;
       um[i] = uv * kTwoM513;
     }
-    int applied = 0;
     for (int t = 0; t < T + D; ++t) {
       if (t >= D) {
-        // residual updates published by the scalar workers for tile t-D
-        int qend = 0;
-        if (lane == 0) {
-          qend = hb::ld_acquire(p.tile_qend + (t - D));
-          if (qend < 0) {
-            Waiter w;
-            while ((qend = hb::ld_acquire(p.tile_qend + (t - D))) < 0)
-              if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_STREAM)) break;
-          }
-        }
-        qend = __shfl_sync(0xffffffffu, qend, 0);
-        if (qend < 0) return;
-        // the tile's changes: 32 queue entries per coalesced read, then the genotype words of eight
-        // changed SNPs in flight at a time (all from L2: the columns were streamed D tiles ago)
-        for (int q0 = applied; q0 < ((p.dbg & 1) ? applied : qend); q0 += 32) {
-          const int nq = min(32, qend - q0);
-          int jl = 0;
-          double dll = 0.0;
-          if (lane < nq) { jl = __ldcg(p.q_snp + q0 + lane); dll = __ldcg(p.q_delta + q0 + lane); }
-          for (int e0 = 0; e0 < nq; e0 += 8) {
-            uint32_t xw[8];
-            double dl[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int js = __shfl_sync(0xffffffffu, jl, (e0 + e) & 31);
-              dl[e] = __shfl_sync(0xffffffffu, dll, (e0 + e) & 31);
-              xw[e] = (e0 + e < nq && has) ? __ldg((const uint32_t*)(Xs + (size_t)js * R + row0)) : 0u;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              if (e0 + e < nq) {
-                const double ds = dl[e] * kTwo513;
-                const double x0 = byte_as_scaled(xw[e], 0x4044), x1 = byte_as_scaled(xw[e], 0x4144);
-                const double x2 = byte_as_scaled(xw[e], 0x4244), x3 = byte_as_scaled(xw[e], 0x4344);
-                rm[0] = fma(-x0, ds, rm[0]); um[0] = fma(x0, ds, um[0]);   // yadj -= x*delta (Bayes.cpp:787), u += x*delta (:789)
-                rm[1] = fma(-x1, ds, rm[1]); um[1] = fma(x1, ds, um[1]);
-                rm[2] = fma(-x2, ds, rm[2]); um[2] = fma(x2, ds, um[2]);
-                rm[3] = fma(-x3, ds, rm[3]); um[3] = fma(x3, ds, um[3]);
+        // residual updates published by the scalar workers for tile t-D.  The first AXPY warp fetches them into
+        // shared memory (one polite poller per CTA); an entry is valid once it differs from its "not yet
+        // written" pattern, so no fence is needed on either side.
+        const int tt = t - D;
+        const size_t qb = (size_t)tt * B;
+        if (a < 32) {
+          int cnt = -1;
+          if (lane == 0) {
+            cnt = hb::ld_relaxed(p.tile_cnt + tt);
+            if (cnt < 0) {
+              Waiter w;
+              for (;;) {
+                __nanosleep(100);
+                cnt = hb::ld_relaxed(p.tile_cnt + tt);
+                if (cnt >= 0) break;
+                if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_STREAM)) { cnt = -2; break; }
               }
+            }
           }
+          cnt = __shfl_sync(0xffffffffu, cnt, 0);
+          if (p.dbg & 1) cnt = min(cnt, 0);
+          for (int q0 = 0; q0 < cnt; q0 += 32) {
+            int jl = -1;
+            unsigned long long dw = kCorrEmpty;
+            if (q0 + lane < cnt) {
+              Waiter w;
+              for (;;) {
+                if (jl < 0) jl = hb::ld_relaxed(p.q_snp + qb + q0 + lane);
+                if (dw == kCorrEmpty) dw = ld_relaxed_u64(p.q_delta + qb + q0 + lane);
+                if (jl >= 0 && dw != kCorrEmpty) break;
+                if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_STREAM)) { cnt = -2; break; }
+              }
+              qj[q0 + lane] = jl;
+              qd[q0 + lane] = __longlong_as_double((long long)dw);
+            }
+          }
+          cnt = __reduce_min_sync(0xffffffffu, cnt);
+          if (lane == 0) *qcnt = cnt;
+          if (s == 0 && lane == 0) HB_TRACE(tt, 6);
         }
-        applied = qend;
+        hb::named_bar_sync(2, 32 * NAW);
+        const int cnt = *(volatile int*)qcnt;
+        if (cnt < 0) return;
+        // the genotype words of eight changed SNPs in flight at a time (from L2: streamed D tiles ago)
+        for (int e0 = 0; e0 < cnt; e0 += 8) {
+          uint32_t xw[8];
+          double dl[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const bool v = e0 + e < cnt;
+            const int js = v ? qj[e0 + e] : 0;
+            dl[e] = v ? qd[e0 + e] : 0.0;
+            xw[e] = (v && has) ? __ldg((const uint32_t*)(Xs + (size_t)js * R + row0)) : 0u;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (e0 + e < cnt) {
+              const double ds = dl[e] * kTwo513;
+              const double x0 = byte_as_scaled(xw[e], 0x4044), x1 = byte_as_scaled(xw[e], 0x4144);
+              const double x2 = byte_as_scaled(xw[e], 0x4244), x3 = byte_as_scaled(xw[e], 0x4344);
+              rm[0] = fma(-x0, ds, rm[0]); um[0] = fma(x0, ds, um[0]);   // yadj -= x*delta (Bayes.cpp:787), u += x*delta (:789)
+              rm[1] = fma(-x1, ds, rm[1]); um[1] = fma(x1, ds, um[1]);
+              rm[2] = fma(-x2, ds, rm[2]); um[2] = fma(x2, ds, um[2]);
+              rm[3] = fma(-x3, ds, rm[3]); um[3] = fma(x3, ds, um[3]);
+            }
+        }
+        hb::named_bar_sync(3, 32 * NAW);   // everybody has read the entries before they are overwritten
       }
       if (t < T) {
         if (t >= 2 && !mbar_wait(rempty + (t & 1), (uint32_t)(((t >> 1) - 1) & 1), ctrl, HB_ABORT_TIMEOUT_PIPE)) return;
@@ -363,14 +392,8 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
 }
 
 // ------------------------------------------------------------------------------------------
-// scalar CTA
+// class decisions
 // ------------------------------------------------------------------------------------------
-template <int NF>
-struct SnpPrm {
-  double u;
-  double a[NF - 1], c[NF - 1], iv[NF - 1], sdz[NF - 1];
-};
-
 // Cumulative class probabilities of one SNP given rr = rhs^2 (Bayes.cpp:759-770 in soft-max form).
 template <int NF>
 __device__ __forceinline__ void class_cum(int nf, double rr, const double* a, const double* c, double logpi0, double* cum) {
@@ -408,25 +431,6 @@ __device__ __forceinline__ int class_from_cum(int nf, double u, const double* cu
   for (int k = 0; k < NF; ++k)
     if (k < nf && !found && u < cum[k]) { cls = k; found = true; }
   return cls;
-}
-
-// Conditional draw of one SNP given its right-hand side (Bayes.cpp:592-601, 639-664, 756-801).
-// `nf` = number of mixture classes in play (2 for B/C, F for R); dense models always return class 1.
-template <int NF>
-__device__ __forceinline__ void eval_snp(int model, int nf, double rhs, const SnpPrm<NF>& q, double logpi0, int& cls, double& gnew) {
-  if (model == HB_MODEL_RR || model == HB_MODEL_A || model == HB_MODEL_L) {
-    cls = 1;
-    gnew = fma(rhs, q.iv[0], q.sdz[0]);
-    if (model == HB_MODEL_L && fabs(gnew) < 1e-6) gnew = 1e-6;  // :728
-    return;
-  }
-  double cum[NF];
-  class_cum<NF>(nf, rhs * rhs, q.a, q.c, logpi0, cum);
-  cls = class_from_cum<NF>(nf, q.u, cum);
-  gnew = 0.0;
-#pragma unroll
-  for (int k = 1; k < NF; ++k)
-    if (k == cls) gnew = fma(rhs, q.iv[k - 1], q.sdz[k - 1]);
 }
 
 // Class as a step function of rr = rhs^2.  With class-ordered slopes c_1 <= c_2 <= ... every cumulative
@@ -511,68 +515,108 @@ __device__ void solve_thresholds(int nf, double u, const double* a, const double
   }
 }
 
-// candidate arrays of one thread group (B entries each)
+// ------------------------------------------------------------------------------------------
+// scalar CTAs
+// ------------------------------------------------------------------------------------------
+// candidate arrays of a worker (B entries each)
 struct CandSet {
   double *rhs0, *iv, *sdz, *gold, *delta, *gnew;
   int *idx, *cls;
 };
 
-// Shared memory of a scalar CTA: two workers (thread groups of B threads), each with its candidate arrays
-// and two row buffers into which the Gram rows of its tile's candidates are gathered by TMA bulk copies
-// (one 4B-byte row per candidate and band block).
-__host__ __device__ inline size_t scalar_fixed_bytes(int B, int D) {
-  (void)D;
-  size_t b = (12 * (size_t)B) * 8 + (4 * (size_t)B + 64 + 16) * 4 + 32 + 18 * 8;   // candidates, ints, barriers, timers
+__device__ __forceinline__ CandSet make_candset(uint8_t* smem, int B) {
+  CandSet cs;
+  double* d = (double*)smem;
+  cs.rhs0 = d; cs.iv = d + B; cs.sdz = d + 2 * B; cs.gold = d + 3 * B; cs.delta = d + 4 * B; cs.gnew = d + 5 * B;
+  int* ip = (int*)(d + 8 * (size_t)B);
+  cs.idx = ip; cs.cls = ip + B;
+  return cs;
+}
+
+// Shared memory of a scalar CTA: candidate arrays, two partial-sum arrays, and two buffers with the Gram rows of
+// the tile's candidates (converted to double while they are gathered): rows0 = diagonal block, rows1 = block
+// towards the next tile.
+__host__ __device__ inline size_t scalar_fixed_bytes(int B) {
+  size_t b = (8 * (size_t)B) * 8 + (3 * (size_t)B + 64 + 16) * 4 + 18 * 8 + 64;   // candidates + partials, ints, timers
   return (b + 127) / 128 * 128;
 }
-// largest row buffer (multiple of 1 KB, at most 44 KB) that still fits the 227 KB of an SM
-__host__ inline size_t scalar_rowbuf_bytes(int B, int D) {
-  const size_t cap = 227 * 1024 - 1024;
-  const size_t fixed = scalar_fixed_bytes(B, D);
-  size_t rb = fixed < cap ? (cap - fixed) / 4 : 0;
-  rb = rb / 1024 * 1024;
-  return rb > 44 * 1024 ? 44 * 1024 : rb;
+__host__ inline int scalar_krow(int B) {
+  const size_t cap = 226 * 1024;
+  const size_t fixed = scalar_fixed_bytes(B);
+  size_t rows = (cap - fixed) / (2 * (size_t)B * 8);
+  if (rows > (size_t)B) rows = (size_t)B;
+  return (int)rows;
 }
-__host__ inline size_t scalar_smem_bytes(int B, int D) {
-  return scalar_fixed_bytes(B, D) + 4 * scalar_rowbuf_bytes(B, D);
+__host__ inline size_t scalar_smem_bytes(int B) { return scalar_fixed_bytes(B) + 2 * (size_t)scalar_krow(B) * B * 8; }
+
+// exact int32 -> double for 0 <= g < 2^31 on the full-rate pipe (one DADD instead of a quarter-rate I2F)
+__device__ __forceinline__ double gram_as_double(int g) {
+  return __hiloint2double(0x43300000, g) - 4503599627370496.0;
 }
 
-// A correction slot that has not been written yet holds this NaN payload (k_prep fills the array).
-constexpr unsigned long long kCorrEmpty = 0x7ff8dead0badf00dull;
-// thread-private hand-off: spin on one 8-byte word until its producer has stored a value
-__device__ __forceinline__ bool poll_corr(const double* slot, double& v, int* ctrl) {
-  unsigned long long w;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(slot) : "memory");
-  if (w == kCorrEmpty) {
-    Waiter wt;
-    do {
-      if (!wt.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) return false;
-      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(slot) : "memory");
-    } while (w == kCorrEmpty);
+// Gathers the Gram rows of the k candidates from one band block into a row buffer as doubles: thread i takes
+// column i of every row (coalesced), sixteen loads in flight.
+__device__ __forceinline__ void gather_rows(double* dst, const int32_t* __restrict__ blk, const int* idx, int k, int B, int i) {
+  for (int sb = 0; sb < k; sb += 16) {
+    int gv[16];
+    const int nb = min(16, k - sb);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) gv[e] = (e < nb) ? __ldcg(blk + (size_t)idx[sb + e] * B + i) : 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      if (e < nb) dst[(size_t)(sb + e) * B + i] = gram_as_double(gv[e]);
   }
-  v = __longlong_as_double((long long)w);
-  return true;
-}
-__device__ __forceinline__ void post_corr(double* slot, double v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(slot), "l"(__double_as_longlong(v)) : "memory");
 }
 
-// TMA gather of the Gram rows of the k candidates from one band block into a row buffer (one warp)
-__device__ __forceinline__ void issue_gather(int32_t* dst, const int32_t* __restrict__ blk, const CandSet& cs, int k, int B,
-                                             uint64_t* bar, int lane) {
-  hb::fence_proxy_async();
-  if (lane == 0) hb::mbar_arrive_expect_tx(bar, (uint32_t)(k * B * 4));
-  __syncwarp();
-  for (int sidx = lane; sidx < k; sidx += 32)
-    hb::tma_load_1d(dst + (size_t)sidx * B, blk + (size_t)cs.idx[sidx] * B, (uint32_t)(B * 4), bar);
-}
-
-// Chains the k candidates of a tile in SNP order (one warp).  Candidate s has right-hand side
-//   rhs_s = rhs0_s - sum_{s' < s} G[c_s'][c_s] * delta_s'      (ascending s', one fma each)
-// and effect  gnew_s = class > 0 ? rhs_s/v + sd*z : 0,  delta_s = gnew_s - gold_s.
-// ROWS: G rows of the candidates are in shared memory (rows[s'][.]); otherwise they are read from global.
+// Candidate chain of the mixture models (one warp).  Lane s tracks
+//   e_s = rhs_s/v_s + sd_s z_s - gold_s        (its effect change if nothing before it in the tile changed)
+// and every earlier candidate s' lowers it by (G[c_s'][c_s]/v_s) delta_s'; when the chain reaches lane s its
+// e_s is final (= delta_s).  One shuffle and one fma per candidate on the dependent path.
+// ROWS: the candidates' Gram rows are in shared memory (doubles); otherwise they are read from global.
 template <bool ROWS>
-__device__ void solve_candidates(const CandSet& cs, int k, const int32_t* __restrict__ G, const int32_t* rows, int B, int model,
+__device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const int32_t* __restrict__ G, const double* rows, int B, int lane) {
+  for (int sb = 0; sb < k; sb += 32) {
+    const int sidx = sb + lane;
+    const bool valid = sidx < k;
+    const int ci = valid ? cs.idx[sidx] : 0;
+    const double iv = valid ? cs.iv[sidx] : 0.0, gold = valid ? cs.gold[sidx] : 0.0;
+    const double niv = -iv;
+    double e = valid ? fma(cs.rhs0[sidx], iv, cs.sdz[sidx]) - gold : 0.0;
+    auto gval = [&](int sp) -> double {
+      return ROWS ? rows[(size_t)sp * B + ci] : gram_as_double(__ldcg(G + (size_t)cs.idx[sp] * B + ci));
+    };
+    // candidates of earlier chunks: their changes are final
+    for (int sp = 0; sp < sb; sp += 8) {
+      double gv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) gv[q] = valid ? gval(sp + q) * niv : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) e = fma(gv[q], cs.delta[sp + q], e);
+    }
+    const int nl = min(32, k - sb);
+    // -G[c_(sb+lp)][c_s]/v_s for the next four steps (software pipeline: loads stay off the chain)
+    auto hload = [&](int lp) -> double {
+      double h = 0.0;
+      if (valid && lp < lane && lp < nl) h = gval(sb + lp) * niv;
+      return h;
+    };
+    double h0 = hload(0), h1 = hload(1), h2 = hload(2), h3 = hload(3);
+#pragma unroll 4
+    for (int lp = 0; lp < nl; ++lp) {
+      const double hcur = h0;
+      h0 = h1; h1 = h2; h2 = h3; h3 = hload(lp + 4);
+      const double d = __shfl_sync(0xffffffffu, e, lp);
+      e = fma(hcur, d, e);   // hcur = 0 for the lanes at or before lp: their e is final
+    }
+    if (valid) { cs.delta[sidx] = e; cs.gnew[sidx] = (cs.cls[sidx] > 0) ? gold + e : 0.0; }
+    __syncwarp();
+  }
+}
+
+// Candidate chain of the dense models (RR/A/L; BayesL clamps the effect, Bayes.cpp:728, so the right-hand side
+// itself is chained):  rhs_s = rhs0_s - sum_{s' < s} G[c_s'][c_s] * delta_s', gnew_s = rhs_s/v + sd*z.
+template <bool ROWS>
+__device__ void solve_candidates(const CandSet& cs, int k, const int32_t* __restrict__ G, const double* rows, int B, int model,
                                  int lane) {
   for (int sb = 0; sb < k; sb += 32) {
     const int sidx = sb + lane;
@@ -581,22 +625,19 @@ __device__ void solve_candidates(const CandSet& cs, int k, const int32_t* __rest
     double rhs = valid ? cs.rhs0[sidx] : 0.0;
     const double iv = valid ? cs.iv[sidx] : 0.0, sdz = valid ? cs.sdz[sidx] : 0.0, gold = valid ? cs.gold[sidx] : 0.0;
     const int cls = valid ? cs.cls[sidx] : 0;
-    // candidates of earlier chunks: their deltas are final
+    auto gval = [&](int sp) -> double {
+      return ROWS ? rows[(size_t)sp * B + ci] : gram_as_double(__ldcg(G + (size_t)cs.idx[sp] * B + ci));
+    };
     for (int sp = 0; sp < sb; sp += 8) {
-      int gv[8];
+      double gv[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) gv[e] = !valid ? 0 : ROWS ? rows[(size_t)(sp + e) * B + ci] : __ldg(G + (size_t)cs.idx[sp + e] * B + ci);
+      for (int e = 0; e < 8; ++e) gv[e] = valid ? gval(sp + e) : 0.0;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) rhs = fma(-(double)gv[e], cs.delta[sp + e], rhs);
+      for (int e = 0; e < 8; ++e) rhs = fma(-gv[e], cs.delta[sp + e], rhs);
     }
     const int nl = min(32, k - sb);
     double mydelta = 0.0, mygnew = gold;
-    // G[c_(sb+lp)][c_s] for the next four steps (software pipeline: the load latency stays off the chain)
-    auto gload = [&](int lp) -> double {
-      int gv = 0;
-      if (valid && lp < lane && lp < nl) gv = ROWS ? rows[(size_t)(sb + lp) * B + ci] : __ldg(G + (size_t)cs.idx[sb + lp] * B + ci);
-      return (double)gv;
-    };
+    auto gload = [&](int lp) -> double { return (valid && lp < lane && lp < nl) ? gval(sb + lp) : 0.0; };
     double g0 = gload(0), g1 = gload(1), g2 = gload(2), g3 = gload(3);
 #pragma unroll 4
     for (int lp = 0; lp < nl; ++lp) {
@@ -614,164 +655,145 @@ __device__ void solve_candidates(const CandSet& cs, int k, const int32_t* __rest
   }
 }
 
-// corr_i = sum_s G[c_s][i] * delta_s over the k candidates (ascending s), rows in shared memory
-__device__ __forceinline__ double band_correction_rows(const CandSet& cs, int k, const int32_t* rows, int B, int i) {
-  double corr = 0.0;
-#pragma unroll 4
-  for (int sidx = 0; sidx < k; ++sidx) corr = fma((double)rows[(size_t)sidx * B + i], cs.delta[sidx], corr);
-  return corr;
-}
-// same from global memory (tiles with more candidates than a row buffer holds)
+// corr_i = sum_s G[c_s][i] * delta_s over the k candidates (ascending s), read from global memory
 __device__ __forceinline__ double band_correction(const CandSet& cs, int k, const int32_t* __restrict__ gb, int B, int i) {
   double corr = 0.0;
   for (int sb = 0; sb < k; sb += 16) {
     int gv[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) gv[e] = (sb + e < k) ? __ldg(gb + (size_t)cs.idx[sb + e] * B + i) : 0;
+    for (int e = 0; e < 16; ++e) gv[e] = (sb + e < k) ? __ldcg(gb + (size_t)cs.idx[sb + e] * B + i) : 0;
 #pragma unroll
     for (int e = 0; e < 16; ++e)
-      if (sb + e < k) corr = fma((double)gv[e], cs.delta[sb + e], corr);
+      if (sb + e < k) corr = fma(gram_as_double(gv[e]), cs.delta[sb + e], corr);
   }
   return corr;
 }
 
-// exact int32 -> double for 0 <= g < 2^31 on the full-rate pipe (one DADD instead of a quarter-rate I2F)
-__device__ __forceinline__ double gram_as_double(int g) {
-  return __hiloint2double(0x43300000, g) - 4503599627370496.0;
-}
-
-// Candidate chain of the mixture models (one warp, rows in shared memory).  Lane s tracks
-//   e_s = rhs_s/v_s + sd_s z_s - gold_s        (its effect change if nothing before it in the tile changed)
-// and every earlier candidate s' lowers it by (G[c_s'][c_s]/v_s) delta_s'; when the chain reaches lane s its
-// e_s is final (= delta_s).  One shuffle and one fma per candidate on the dependent path.
-__device__ void chain_candidates(const CandSet& cs, int k, const int32_t* rows, int B, int lane) {
-  for (int sb = 0; sb < k; sb += 32) {
-    const int sidx = sb + lane;
-    const bool valid = sidx < k;
-    const int ci = valid ? cs.idx[sidx] : 0;
-    const double iv = valid ? cs.iv[sidx] : 0.0, gold = valid ? cs.gold[sidx] : 0.0;
-    const double niv = -iv;
-    double e = valid ? fma(cs.rhs0[sidx], iv, cs.sdz[sidx]) - gold : 0.0;
-    // candidates of earlier chunks: their changes are final
-    for (int sp = 0; sp < sb; sp += 8) {
-      double gv[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) gv[q] = valid ? gram_as_double(rows[(size_t)(sp + q) * B + ci]) * niv : 0.0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) e = fma(gv[q], cs.delta[sp + q], e);
-    }
-    const int nl = min(32, k - sb);
-    // -G[c_(sb+lp)][c_s]/v_s for the next four steps (software pipeline: loads and conversions stay off the chain)
-    auto hload = [&](int lp) -> double {
-      double h = 0.0;
-      if (valid && lp < lane && lp < nl) h = gram_as_double(rows[(size_t)(sb + lp) * B + ci]) * niv;
-      return h;
-    };
-    double h0 = hload(0), h1 = hload(1), h2 = hload(2), h3 = hload(3);
-#pragma unroll 4
-    for (int lp = 0; lp < nl; ++lp) {
-      const double hcur = h0;
-      h0 = h1; h1 = h2; h2 = h3; h3 = hload(lp + 4);
-      const double d = __shfl_sync(0xffffffffu, e, lp);
-      e = fma(hcur, d, e);   // hcur = 0 for the lanes at or before lp: their e is final
-    }
-    if (valid) { cs.delta[sidx] = e; cs.gnew[sidx] = (cs.cls[sidx] > 0) ? gold + e : 0.0; }
-    __syncwarp();
+// Tiles with more candidates than a row buffer holds (k > KROW): chain and sums straight from the Gram band in
+// global memory.  Rare and slow; kept out of line so that the common path stays compact in the instruction cache.
+__device__ __noinline__ void slow_chain_and_sums(int k, int myrank, const int32_t* __restrict__ G0, int B,
+                                                 int i, int h, bool has1, bool dense, int model, int nthreads, double* prhs,
+                                                 double* pcorr) {
+  extern __shared__ __align__(128) uint8_t smem_slow[];
+  const CandSet cs = make_candset(smem_slow, B);
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < 32 && k > 0) {
+    if (dense) solve_candidates<false>(cs, k, G0, nullptr, B, model, lane);
+    else chain_candidates<false>(cs, k, G0, nullptr, B, lane);
   }
+  hb::named_bar_sync(1, nthreads);
+  *prhs = 0.0;
+  *pcorr = 0.0;
+  if (h == 0) *prhs = band_correction(cs, myrank, G0, B, i);
+  else if (has1) *pcorr = band_correction(cs, k, G0 + (size_t)B * B, B, i);
 }
 
+// exact class of SNP j given rr = rhs^2 (reads its a_k, c_k and uniform from the parameter table)
 template <int NF>
+__device__ __noinline__ int classify_exact(const double* __restrict__ prm, size_t mp, int j, int nf, double rr, double logpi0) {
+  double a[NF - 1], c[NF - 1], cum[NF];
+#pragma unroll
+  for (int kk = 0; kk < NF - 1; ++kk) {
+    a[kk] = 0.0; c[kk] = 0.0;
+    if (kk < nf - 1) { a[kk] = __ldcg(prm + prm_idx(2 + 4 * kk, mp, j)); c[kk] = __ldcg(prm + prm_idx(3 + 4 * kk, mp, j)); }
+  }
+  class_cum<NF>(nf, rr, a, c, logpi0, cum);
+  return class_from_cum<NF>(nf, __ldcg(prm + prm_idx(0, mp, j)), cum);
+}
+
+template <int NF, bool DENSE>
 __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
-  // The scalar CTAs hold 2 workers each (thread groups of B threads, one thread per SNP of a tile); worker w
-  // owns tiles w, w + W, w + 2W, ...  A tile goes through three phases:
+  // Worker w (= scalar CTA w) owns tiles w, w + NG, w + 2 NG, ...  Two threads per SNP of the tile: the
+  // primary half (h = 0) and the secondary half (h = 1) split the gathers and the correction sums.
+  // A tile goes through three phases:
   //   P  (any time after its dots arrived)  inputs, corrections owed by the tiles t-D+1 .. t-2, speculated
-  //      classes, candidate list, TMA gather of the candidates' Gram rows
+  //      classes, candidate list, gather of the candidates' Gram rows
   //   S  (serial: starts when tile t-1 has handed over its corrections for tile t)  exact right-hand sides,
   //      candidate chain, verification; ends by handing the corrections for tile t+1 to the next worker
-  //   C  commit: effects, classes, residual-update queue for the streaming CTAs, corrections for t+2 .. t+D-1
-  // Workers exchange data through global memory only: every correction value is its own flag (poll_corr).
+  //   C  commit: effects, classes, the tile's residual updates for the streaming CTAs, corrections for
+  //      t+2 .. t+D-1
   const int B = p.B, D = p.D, T = p.T, F = p.F, model = p.model;
   const int tid = threadIdx.x;
-  const int ngrp = 2;
-  if (tid >= ngrp * B) return;
-  const int grp = tid / B, i = tid - grp * B, warp = i >> 5, lane = i & 31, nwarp = B / 32;
-  const int worker = ((int)blockIdx.x - p.S) * ngrp + grp, nworker = p.NG * ngrp;
+  if (tid >= 2 * B) return;
+  const int h = tid / B, i = tid - h * B, warp = i >> 5, lane = i & 31, nwarp = B / 32;
+  const bool prim = (h == 0);
+  const int worker = (int)blockIdx.x - p.S, nworker = p.NG;
   int* ctrl = p.ctrl;
   // ---- shared memory carve-up
-  CandSet cs;        // this worker's candidate arrays
-  int *wcnt, *wbad;  // 16 per worker
-  volatile int* gctl; // per worker: [0] abort flag, [1] qbase
-  uint64_t* rbar;    // this worker's two row-buffer barriers
-  int32_t *rows0, *rows1;
+  CandSet cs;
+  double *part_rhs, *part_corr;   // secondary half's partial sums
+  int *wcnt, *wbad, *rank_sh;     // rank_sh[i] = number of candidates before SNP i
+  volatile int* gctl;             // [0] abort flag, [1] number of candidates
   long long* phase;
+  double *rows0, *rows1;
   {
+    cs = make_candset(smem, B);
     double* d = (double*)smem;
-    double* cbase = d + (size_t)grp * 6 * B; d += 12 * (size_t)B;
-    cs.rhs0 = cbase; cs.iv = cbase + B; cs.sdz = cbase + 2 * B; cs.gold = cbase + 3 * B;
-    cs.delta = cbase + 4 * B; cs.gnew = cbase + 5 * B;
+    part_rhs = d + 6 * B; part_corr = d + 7 * B;
+    d += 8 * (size_t)B;
     int* ip = (int*)d;
-    cs.idx = ip + (size_t)grp * 2 * B; cs.cls = cs.idx + B; ip += 4 * (size_t)B;
-    wcnt = ip + grp * 16; wbad = ip + 32 + grp * 16; ip += 64;
-    gctl = ip + grp * 8; ip += 16;
-    rbar = (uint64_t*)ip + 2 * grp;
-    phase = (long long*)((uint64_t*)ip + 4);
-    uint8_t* rb = smem + scalar_fixed_bytes(B, D);
-    rows0 = (int32_t*)(rb + (size_t)(2 * grp) * p.rowbuf);
-    rows1 = (int32_t*)(rb + (size_t)(2 * grp + 1) * p.rowbuf);
+    rank_sh = ip + 2 * B; ip += 3 * (size_t)B;
+    wcnt = ip; wbad = ip + 32; ip += 64;
+    gctl = ip; ip += 16;
+    phase = (long long*)ip;
+    uint8_t* rb = smem + scalar_fixed_bytes(B);
+    rows0 = (double*)rb;
+    rows1 = rows0 + (size_t)p.KROW * B;
   }
-  const int KROW = (int)(p.rowbuf / ((size_t)B * 4));
-  const int gbar = 2 + grp;
-  if (i < 8) gctl[i] = 0;
-  if (i == 0) { hb::mbar_init(rbar, 1); hb::mbar_init(rbar + 1, 1); hb::mbar_fence_init(); }
-  hb::named_bar_sync(1, ngrp * B);
+  const int KROW = p.KROW;
+  const int NT2 = 2 * B;   // threads of the worker
+  if (tid < 8) gctl[tid] = 0;
+  if (tid < 32) wbad[tid] = 1 << 30;
+  hb::named_bar_sync(1, NT2);
 
   const size_t mp = p.m_pad;
-  const bool dense = (model == HB_MODEL_RR || model == HB_MODEL_A || model == HB_MODEL_L);
+  constexpr bool dense = DENSE;   // RR / A / L: every SNP changes in every sweep
   const int nf = (model == HB_MODEL_R) ? F : 2;
   const bool use_thr = p.use_thr && !dense;
   const int NONE = 1 << 30;
   const int DC = D - 1;   // correction slots per tile
-  unsigned n0 = 0, n1 = 0;   // gathers issued so far into rows0 / rows1 (parity of the phase to wait for)
   bool dead = false;
-  int rounds_total = 0;
+  int rounds_total = 0, changed_total = 0;
 
-  long long* pc = phase + grp * 9;   // [8] = last time stamp
-  if (i == 0) { for (int k = 0; k < 8; ++k) pc[k] = 0; pc[8] = clock64(); }
-#define HB_PHASE(n) do { if (i == 0) { const long long _now = clock64(); pc[n] += _now - pc[8]; pc[8] = _now; } } while (0)
+  long long* pc = phase;   // [16] = last time stamp
+  if (tid == 0) { for (int k = 0; k < 16; ++k) pc[k] = 0; pc[16] = clock64(); }
+#define HB_PHASE(n) do { if (tid == 0) { const long long _now = clock64(); pc[n] += _now - pc[16]; pc[16] = _now; } } while (0)
   for (int t = worker; t < T; t += nworker) {
     const int j = t * B + i;
     if (p.dbg & 48) {
       // timing experiments, the streaming side alone: 16 publishes every tile (without changes) as soon as
       // its dots have arrived, 32 publishes it at once
-      if (i == 0) {
-        bool ok = true;
-        if (!(p.dbg & 32)) {
-          Waiter w;
-          while (hb::ld_relaxed_u(p.arrive + t) < p.arrive_target)
-            if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) { ok = false; break; }
-        }
-        if (ok) { __threadfence(); hb::st_release(p.tile_qend + t, 0); }
+      if (!(p.dbg & 32) && prim) {
+        Waiter w;
+        while ((ld_relaxed_u64(p.dacc + j) & 0xffull) != (unsigned long long)p.S)
+          if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) break;
       }
+      hb::named_bar_sync(1, NT2);
+      if (tid == 0) st_relaxed_s32(p.tile_cnt + t, 0);
       continue;
     }
-    // ---- phase P: inputs, speculation, Gram-row gather
-    const bool act = (j < p.m) && p.active[j];
-    const double xx = p.xpx[j];
-    const double gold = p.g[j];
+    // ---- phase P: inputs, speculation, gather of the Gram rows.  The primary half decides, the secondary half
+    // only helps with gathers and sums.
+    bool act = false;
+    double xx = 0.0, gold = 0.0;
     double TL[NF - 1], TH[NF - 1];
-    double div0 = 0.0, dsdz0 = 0.0;   // dense models: 1/v and sd*z
-    if (use_thr) {
+    double civ[NF - 1], csdz[NF - 1];   // 1/v_k and sd_k z of every class (dense models: [0])
 #pragma unroll
-      for (int b = 0; b < NF - 1; ++b) {
-        TL[b] = -1.0; TH[b] = -1.0;
+    for (int b = 0; b < NF - 1; ++b) { TL[b] = -1.0; TH[b] = -1.0; civ[b] = 0.0; csdz[b] = 0.0; }
+    if (prim) {
+      act = (j < p.m) && __ldcg(p.active + j);
+      xx = __ldcg(p.xpx + j);
+      gold = __ldcg(p.g + j);
+#pragma unroll
+      for (int b = 0; b < NF - 1; ++b)
         if (b < nf - 1) {
-          TL[b] = p.prm[prm_idx(kThrField0 + 2 * b, mp, j)];
-          TH[b] = p.prm[prm_idx(kThrField0 + 2 * b + 1, mp, j)];
+          if (use_thr) {
+            TL[b] = __ldcg(p.prm + prm_idx(kThrField0 + 2 * b, mp, j));
+            TH[b] = __ldcg(p.prm + prm_idx(kThrField0 + 2 * b + 1, mp, j));
+          }
+          civ[b] = __ldcg(p.prm + prm_idx(4 + 4 * b, mp, j));
+          csdz[b] = __ldcg(p.prm + prm_idx(5 + 4 * b, mp, j));
         }
-      }
-    } else if (dense) {
-      div0 = p.prm[prm_idx(4, mp, j)];
-      dsdz0 = p.prm[prm_idx(5, mp, j)];
     }
     // class of this SNP given its right-hand side: thresholds, or the exact evaluation (rare with thresholds)
     auto classify = [&](double rhs) -> int {
@@ -781,239 +803,218 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
         const int c0 = thr_class<NF>(nf, rr, TL, TH);
         if (c0 >= 0) return c0;
       }
-      double a[NF - 1], c[NF - 1], cum[NF];
-#pragma unroll
-      for (int kk = 0; kk < NF - 1; ++kk) {
-        a[kk] = 0.0; c[kk] = 0.0;
-        if (kk < nf - 1) { a[kk] = p.prm[prm_idx(2 + 4 * kk, mp, j)]; c[kk] = p.prm[prm_idx(3 + 4 * kk, mp, j)]; }
-      }
-      class_cum<NF>(nf, rr, a, c, p.logpi0, cum);
-      return class_from_cum<NF>(nf, p.prm[prm_idx(0, mp, j)], cum);
+      return classify_exact<NF>(p.prm, mp, j, nf, rr, p.logpi0);
     };
-    if (i == 0) {
-      bool ok = true;
-      if (hb::ld_relaxed_u(p.arrive + t) < p.arrive_target) {
-        Waiter w;
-        while (hb::ld_relaxed_u(p.arrive + t) < p.arrive_target)
-          if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) { ok = false; break; }
-      }
-      hb::fence_acq_rel_gpu();
-      gctl[0] = (!ok || *((volatile int*)(ctrl + 1)) != 0) ? 1 : 0;
+    // corrections owed by the tiles t-D+1 .. t-1: whatever has been posted by now goes into the speculation
+    // (no waiting here); phase S takes them all, summed oldest first
+    double cspec = 0.0;
+    const int dmax = min(DC, t);
+    if (prim) {
+      unsigned long long cw[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) cw[q] = (q + 1 <= dmax) ? ld_relaxed_u64(p.corr + ((size_t)t * DC + q) * B + i) : kCorrEmpty;
+#pragma unroll
+      for (int q = 7; q >= 0; --q)
+        if (cw[q] != kCorrEmpty) cspec += __longlong_as_double((long long)cw[q]);
     }
-    hb::named_bar_sync(gbar, B);
-    if (gctl[0]) { dead = true; break; }
+    // the dots: complete when the arrival count in the low byte equals the number of slabs.  One thread waits
+    // politely for the tile's first SNP, then every primary thread takes its own accumulator.
+    if (tid == 0) {
+      Waiter wt;
+      while ((ld_relaxed_u64(p.dacc + j) & 0xffull) != (unsigned long long)p.S) {
+        __nanosleep(100);
+        if (!wt.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) break;
+      }
+    }
+    hb::named_bar_sync(1, NT2);
+    double base0 = 0.0;
+    if (prim) {
+      unsigned long long w = ld_relaxed_u64(p.dacc + j);
+      if ((w & 0xffull) != (unsigned long long)p.S) {
+        Waiter wt;
+        do {
+          __nanosleep(50);
+          if (!wt.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) { dead = true; break; }
+          w = ld_relaxed_u64(p.dacc + j);
+        } while ((w & 0xffull) != (unsigned long long)p.S);
+      }
+      base0 = (double)((long long)w >> 8) * p.inv_dscale;
+    }
     HB_PHASE(0);
-    const double base0 = (double)(long long)__ldcg(p.dacc + j) * p.inv_dscale;
+    if (tid == 0) HB_TRACE(t, 0);
     // rhs = x_j' yadj (+ xpx_j g_j)    (Bayes.cpp:593-594, 756-757)
     const double addback = (act && (dense || gold != 0.0)) ? xx * gold : 0.0;
-    // corrections owed by the tiles t-D+1 .. t-2 (oldest first); the one of tile t-1 comes in phase S
-    double cold = 0.0;
-    for (int dt = min(DC, t); dt >= 2; --dt) {
-      double v;
-      if (!poll_corr(p.corr + ((size_t)t * DC + (dt - 1)) * B + i, v, ctrl)) { dead = true; v = 0.0; }
-      cold += v;
-    }
     int cls = 0;
     double gnew = gold;
     // the corrections of the previous tile are still missing here: this is only the speculation
-    if (act) cls = classify((base0 - cold) + addback);
+    if (act) cls = classify((base0 - cspec) + addback);
     int k = 0, myrank = 0;
     bool cand = false, fast = false;
     const bool has1 = (D > 1 && t + 1 < T);
     const int32_t* G0 = p.gram + ((size_t)t * D) * B * B;
-    // candidate list of the speculated classes; used as is by the first round of the serial phase
+    // candidate list of the speculated classes and their Gram rows
     auto compact = [&]() {
       cand = act && (cls > 0 || gold != 0.0);
-      const unsigned bal = __ballot_sync(0xffffffffu, cand);
-      if (lane == 0) wcnt[warp] = __popc(bal);
-      hb::named_bar_sync(gbar, B);
-      int pre = 0;
-      k = 0;
-      for (int w = 0; w < nwarp; ++w) {
-        const int c = wcnt[w];
-        if (w < warp) pre += c;
-        k += c;
+      if (prim) {
+        const unsigned bal = __ballot_sync(0xffffffffu, cand);
+        if (lane == 0) wcnt[warp] = __popc(bal);
+        hb::named_bar_sync(4, B);   // primary half only
+        int pre = 0;
+        k = 0;
+        for (int w = 0; w < nwarp; ++w) {
+          const int c = wcnt[w];
+          if (w < warp) pre += c;
+          k += c;
+        }
+        myrank = pre + __popc(bal & ((1u << lane) - 1u));   // = number of candidates before SNP i
+        rank_sh[i] = myrank;
+        if (i == 0) gctl[1] = k;
+        if (cand) {
+          cs.idx[myrank] = i;
+          cs.gold[myrank] = gold;
+          cs.cls[myrank] = cls;
+          double iv = 0.0, sdz = 0.0;
+#pragma unroll
+          for (int kk = 1; kk < NF; ++kk)
+            if (kk == cls) { iv = civ[kk - 1]; sdz = csdz[kk - 1]; }
+          cs.iv[myrank] = iv;
+          cs.sdz[myrank] = sdz;
+        }
       }
-      myrank = pre + __popc(bal & ((1u << lane) - 1u));   // = number of candidates before SNP i
-      if (cand) {
-        cs.idx[myrank] = i;
-        cs.gold[myrank] = gold;
-        cs.cls[myrank] = cls;
-        double iv = 0.0, sdz = 0.0;
-        if (dense) { iv = div0; sdz = dsdz0; }
-        else if (cls > 0) { iv = p.prm[prm_idx(4 * cls, mp, j)]; sdz = p.prm[prm_idx(4 * cls + 1, mp, j)]; }   // 1/v_k, sd_k z of class k
-        cs.iv[myrank] = iv;
-        cs.sdz[myrank] = sdz;
-      }
-      hb::named_bar_sync(gbar, B);
+      hb::named_bar_sync(1, NT2);
+      if (!prim) { k = gctl[1]; myrank = rank_sh[i]; }
       fast = (k <= KROW);
       if (fast) {
-        if (warp == 0) {
-          issue_gather(rows0, G0, cs, k, B, rbar, lane);
-          if (has1) issue_gather(rows1, G0 + (size_t)B * B, cs, k, B, rbar + 1, lane);
-        }
-        ++n0;
-        if (has1) ++n1;
+        if (prim) gather_rows(rows0, G0, cs.idx, k, B, i);
+        else if (has1) gather_rows(rows1, G0 + (size_t)B * B, cs.idx, k, B, i);
       }
     };
     compact();
     HB_PHASE(1);
+    if (tid == 0) HB_TRACE(t, 1);
     // ---- phase S: the previous tile is final once its corrections for this tile are here
-    double c1 = 0.0;
-    if (t >= 1 && D > 1 && !poll_corr(p.corr + ((size_t)t * DC) * B + i, c1, ctrl)) dead = true;
+    double cold = 0.0, c1 = 0.0;
+    if (prim) {
+      unsigned long long cw[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) cw[q] = (q + 1 <= dmax) ? ld_relaxed_u64(p.corr + ((size_t)t * DC + q) * B + i) : 0ull;
+#pragma unroll
+      for (int q = 7; q >= 0; --q)
+        if (q + 1 <= dmax) {
+          double v = __longlong_as_double((long long)cw[q]);
+          if (cw[q] == kCorrEmpty && !poll_corr_slow(p.corr + ((size_t)t * DC + q) * B + i, v, ctrl)) { dead = true; v = 0.0; }
+          if (q == 0) c1 = v; else cold += v;
+        }
+    }
     HB_PHASE(2);
+    if (tid == 0) HB_TRACE(t, 2);
     const double rhs0 = ((base0 - cold) - c1) + addback;
     int nrounds = 0;
-    bool rows1_pending = false;
     double corr1 = 0.0;
     for (;;) {
       ++nrounds;
-      if (cand) cs.rhs0[myrank] = rhs0;
-      hb::named_bar_sync(gbar, B);
-      if (fast && !hbk::mbar_wait(rbar, (n0 - 1) & 1, ctrl, HB_ABORT_TIMEOUT_SCALAR)) dead = true;
+      if (cand && prim) cs.rhs0[myrank] = rhs0;
+      hb::named_bar_sync(1, NT2);   // rows and right-hand sides of the candidates are in shared memory
       HB_PHASE(3);
-      if (warp == 0 && k > 0 && !dead) {
-        if (fast && !dense) chain_candidates(cs, k, rows0, B, lane);
-        else if (fast) solve_candidates<true>(cs, k, G0, rows0, B, model, lane);
-        else solve_candidates<false>(cs, k, G0, rows0, B, model, lane);
-      }
-      if (fast && has1 && !hbk::mbar_wait(rbar + 1, (n1 - 1) & 1, ctrl, HB_ABORT_TIMEOUT_SCALAR)) dead = true;
-      rows1_pending = false;
-      hb::named_bar_sync(gbar, B);
-      HB_PHASE(4);
-      // exact right-hand side of every SNP of the tile:  x_i'(r - sum_{c<i} x_c delta_c), ascending c; in the
-      // same pass the corrections this tile owes to the next one (all k changes)
-      double rhs = rhs0;
-      corr1 = 0.0;
+      double prhs = 0.0, pcorr = 0.0;
       if (fast) {
-        if (!dead) {
-          if (has1) {
+        if (tid < 32 && k > 0) {
+          if (dense) solve_candidates<true>(cs, k, G0, rows0, B, model, lane);
+          else chain_candidates<true>(cs, k, G0, rows0, B, lane);
+        }
+        HB_PHASE(4);
+        hb::named_bar_sync(1, NT2);
+        HB_PHASE(8);
+        // exact right-hand side of every SNP of the tile:  x_i'(r - sum_{c<i} x_c delta_c), and in the same pass
+        // the corrections this tile owes to the next one (all k changes).  The primary thread takes the even
+        // candidates, the secondary the odd ones.
 #pragma unroll 4
-            for (int sidx = 0; sidx < k; ++sidx) {
-              const double d = cs.delta[sidx];
-              if (sidx < myrank) rhs = fma(-gram_as_double(rows0[(size_t)sidx * B + i]), d, rhs);
-              corr1 = fma(gram_as_double(rows1[(size_t)sidx * B + i]), d, corr1);
-            }
-          } else {
-#pragma unroll 4
-            for (int sidx = 0; sidx < myrank; ++sidx) rhs = fma(-gram_as_double(rows0[(size_t)sidx * B + i]), cs.delta[sidx], rhs);
-          }
+        for (int sidx = h; sidx < k; sidx += 2) {
+          const double d = cs.delta[sidx];
+          if (sidx < myrank) prhs = fma(rows0[(size_t)sidx * B + i], d, prhs);
+          if (has1) pcorr = fma(rows1[(size_t)sidx * B + i], d, pcorr);
         }
       } else {
-        for (int sb = 0; sb < myrank; sb += 8) {
-          int gv[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) gv[e] = (sb + e < myrank) ? __ldg(G0 + (size_t)cs.idx[sb + e] * B + i) : 0;
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (sb + e < myrank) rhs = fma(-(double)gv[e], cs.delta[sb + e], rhs);
-        }
-        if (has1) corr1 = band_correction(cs, k, G0 + (size_t)B * B, B, i);
+        slow_chain_and_sums(k, myrank, G0, B, i, h, has1, dense, model, NT2, &prhs, &pcorr);
+      }
+      if (!prim) { part_rhs[i] = prhs; part_corr[i] = pcorr; }
+      HB_PHASE(9);
+      hb::named_bar_sync(1, NT2);
+      HB_PHASE(10);
+      double rhs = rhs0;
+      if (prim) {
+        rhs = rhs0 - (prhs + part_rhs[i]);
+        corr1 = pcorr + part_corr[i];
       }
       int cls2 = 0;
       double gnew2 = gold;
-      if (act) {
+      if (act && prim) {
         cls2 = classify(rhs);
         if (dense) {
-          gnew2 = fma(rhs, div0, dsdz0);
+          gnew2 = fma(rhs, civ[0], csdz[0]);
           if (model == HB_MODEL_L && fabs(gnew2) < 1e-6) gnew2 = 1e-6;  // :728
         }
       }
-      const bool bad = act && (cls2 != cls);
+      const bool bad = prim && act && (cls2 != cls);
       const unsigned bal2 = __ballot_sync(0xffffffffu, bad);
-      if (lane == 0) wbad[warp] = bal2 ? (warp * 32 + __ffs(bal2) - 1) : NONE;
-      if (__any_sync(0xffffffffu, dead) && lane == 0) wbad[warp] = -1;
-      hb::named_bar_sync(gbar, B);
+      if (prim && lane == 0) wbad[warp] = bal2 ? (warp * 32 + __ffs(bal2) - 1) : NONE;
+      if (dead) wbad[16 + (tid & 15)] = -1;
+      HB_PHASE(11);
+      hb::named_bar_sync(1, NT2);
+      HB_PHASE(12);
       int first = NONE;
       for (int w = 0; w < nwarp; ++w) first = min(first, wbad[w]);
-      cls = cls2;
-      gnew = gnew2;
+      for (int w = 16; w < 32; ++w) first = min(first, wbad[w]);
+      if (prim) { cls = cls2; gnew = gnew2; }
       HB_PHASE(5);
       if (first == NONE) break;   // every class equals its speculation: the tile is final
       if (first < 0) { dead = true; break; }
       // a class differed: everything before it is final; speculate again with the corrected classes
-      if (rows1_pending && !hbk::mbar_wait(rbar + 1, (n1 - 1) & 1, ctrl, HB_ABORT_TIMEOUT_SCALAR)) dead = true;
       compact();
     }
     if (dead) break;
     rounds_total += nrounds;
+    changed_total += k;
     // ---- the tile is final.  First what the next tile waits for: its corrections (dt = 1)
-    if (has1) post_corr(p.corr + ((size_t)(t + 1) * DC) * B + i, corr1);
+    if (has1 && prim) post_corr(p.corr + ((size_t)(t + 1) * DC) * B + i, corr1);
     HB_PHASE(6);
-    // ---- phase C: commit.  Position of this tile's changes in the residual-update queue
-    if (i == 0) {
-      int qb = 0;
-      bool ok = true;
-      if (t > 0) {
-        qb = hb::ld_relaxed(p.hq + (t - 1));
-        if (qb < 0) {
-          Waiter w;
-          while ((qb = hb::ld_relaxed(p.hq + (t - 1))) < 0)
-            if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) { ok = false; break; }
-        }
+    if (tid == 0) HB_TRACE(t, 3);
+    // ---- phase C: commit.  The tile's residual updates go to the streaming CTAs first
+    if (prim) {
+      if (cand) {
+        gnew = cs.gnew[myrank];
+        st_relaxed_u64(p.q_delta + (size_t)t * B + myrank, (unsigned long long)__double_as_longlong(cs.delta[myrank]));
+        st_relaxed_s32(p.q_snp + (size_t)t * B + myrank, j);
+        p.g[j] = gnew;
       }
-      if (ok) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.hq + t), "r"(qb + k) : "memory");
-      gctl[1] = qb;
-      gctl[0] = ok ? 0 : 1;
+      if (i == 0) { st_relaxed_s32(p.tile_cnt + t, k); HB_TRACE(t, 4); }
+      if (act) p.tracker[j] = cls;
     }
-    hb::named_bar_sync(gbar, B);
-    if (gctl[0]) { dead = true; break; }
-    const int qbase = gctl[1];
-    if (cand) gnew = cs.gnew[myrank];
-    if (act) {
-      p.g[j] = gnew;
-      p.tracker[j] = cls;
-    }
-    if (cand) {
-      p.q_snp[qbase + myrank] = j;
-      p.q_delta[qbase + myrank] = cs.delta[myrank];
-    }
-    // corrections owed to the tiles further ahead, whose dots were (or will be) taken before these updates land
-    for (int dt = 2; dt < D; dt += 2) {
+    // corrections owed to the tiles further ahead, whose dots were (or will be) taken before these updates
+    // land: block dt goes to the half with the parity of dt
+    for (int dt = 2 + h; dt < D; dt += 2) {
       if (t + dt >= T) break;
-      const bool two = (dt + 1 < D) && (t + dt + 1 < T);
-      double ca, cb = 0.0;
-      if (fast) {
-        if (warp == 0) {
-          issue_gather(rows0, G0 + (size_t)dt * B * B, cs, k, B, rbar, lane);
-          if (two) issue_gather(rows1, G0 + (size_t)(dt + 1) * B * B, cs, k, B, rbar + 1, lane);
-        }
-        ++n0;
-        if (two) ++n1;
-        if (!hbk::mbar_wait(rbar, (n0 - 1) & 1, ctrl, HB_ABORT_TIMEOUT_SCALAR)) dead = true;
-        ca = dead ? 0.0 : band_correction_rows(cs, k, rows0, B, i);
-        if (two) {
-          if (!hbk::mbar_wait(rbar + 1, (n1 - 1) & 1, ctrl, HB_ABORT_TIMEOUT_SCALAR)) dead = true;
-          cb = dead ? 0.0 : band_correction_rows(cs, k, rows1, B, i);
-        }
-        if (dt + 2 < D) hb::named_bar_sync(gbar, B);   // every thread is done with the row buffers before they are refilled
-      } else {
-        ca = band_correction(cs, k, G0 + (size_t)dt * B * B, B, i);
-        if (two) cb = band_correction(cs, k, G0 + (size_t)(dt + 1) * B * B, B, i);
-      }
-      post_corr(p.corr + ((size_t)(t + dt) * DC + (dt - 1)) * B + i, ca);
-      if (two) post_corr(p.corr + ((size_t)(t + dt + 1) * DC + dt) * B + i, cb);
+      const double cv = band_correction(cs, k, G0 + (size_t)dt * B * B, B, i);
+      post_corr(p.corr + ((size_t)(t + dt) * DC + (dt - 1)) * B + i, cv);
     }
-    // publish the tile's residual updates to the streaming CTAs
-    __threadfence();
-    hb::named_bar_sync(gbar, B);
-    if (i == 0) hb::st_release(p.tile_qend + t, qbase + k);
-    if (i == 0 && t == T - 1) p.out->n_changed = qbase + k;
     HB_PHASE(7);
+    if (tid == 0) HB_TRACE(t, 5);
+    hb::named_bar_sync(1, NT2);   // the candidate arrays are free again
   }
   if (dead) atomicCAS(ctrl + 1, 0, HB_ABORT_TIMEOUT_SCALAR);
-  if (i == 0) {
+  if (tid == 0) {
     if (worker < 2)
-      for (int k = 0; k < 8; ++k) p.out->phase_clk[worker][k] = pc[k];
+      for (int k = 0; k < 16; ++k) p.out->phase_clk[worker][k] = pc[k];
     atomicAdd(&p.out->rounds, rounds_total);
+    atomicAdd(&p.out->n_changed, changed_total);
   }
 }
 
 }  // namespace hbk
 
-template <int MAXT, int NF, int RL>
+template <int MAXT, int NF, int RL, bool DENSE>
 __global__ void __launch_bounds__(MAXT, 1) k_sweep(const __grid_constant__ SweepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  if ((int)blockIdx.x >= p.S) hbk::scalar_role<NF>(p, smem);
+  if ((int)blockIdx.x >= p.S) hbk::scalar_role<NF, DENSE>(p, smem);
   else hbk::stream_role<RL>(p, smem);
 }

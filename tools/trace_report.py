@@ -1,0 +1,23 @@
+"""Reads an HB_TRACE dump ([T][8] globaltimer ns per tile) and prints where a tile's time goes.
+events: 0 dots seen by worker, 1 P done, 2 hand-over from t-1 arrived, 3 S done (hand-over posted), 4 updates published,
+5 C done, 6 AXPY warp of slab 0 fetched the tile's updates, 7 compute warp 0 of slab 0 added its dots of the tile."""
+import sys
+import numpy as np
+a = np.fromfile(sys.argv[1], dtype=np.uint64).reshape(-1, 8).astype(np.int64)
+D = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+T = a.shape[0]
+lo, hi = T // 4, 3 * T // 4
+s = a[lo:hi]
+def d(x, y): return float(np.median(s[:, x] - s[:, y]))
+print("tiles", T, "window", lo, hi)
+print("period (S done t - S done t-1): %.0f ns" % float(np.median(np.diff(a[lo:hi, 3]))))
+print("dots added by slab0 (7) -> dots seen by worker (0): %.0f" % d(0, 7))
+print("dots seen (0) -> P done (1): %.0f" % d(1, 0))
+print("P done (1) -> hand-over arrived (2): %.0f" % d(2, 1))
+print("hand-over arrived (2) -> S done (3): %.0f" % d(3, 2))
+print("S done (3) -> published (4): %.0f" % d(4, 3))
+print("published (4) -> AXPY fetched (6): %.0f" % d(6, 4))
+print("S done (3) -> C done (5): %.0f" % d(5, 3))
+print("S done of t-1 (3) -> hand-over arrived at t (2): %.0f" % float(np.median(a[lo + 1:hi, 2] - a[lo:hi - 1, 3])))
+print("AXPY fetched t (6) -> slab0 added dots of t+D (7): %.0f" % float(np.median(a[lo + D:hi, 7] - a[lo:hi - D, 6])))
+print("published t (4) -> dots of t+D seen (0): %.0f" % float(np.median(a[lo + D:hi, 0] - a[lo:hi - D, 4])))
