@@ -362,7 +362,7 @@ __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) {
     ctrl[0] = 0; ctrl[1] = 0;
-    out->n_changed = 0; out->status = 0; out->rounds = 0; out->varg_acc = 0; out->sum_vargL = 0;
+    out->n_changed = 0; out->status = 0; out->rounds = 0; out->pad = 0; out->varg_acc = 0; out->sum_vargL = 0;
     for (int k = 0; k < HB_MAX_FOLD; ++k) out->count[k] = 0;
   }
   if (j < p.T) tile_cnt[j] = -1;
@@ -994,6 +994,7 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
     if (FILE* f = fopen(getenv("HB_TRACE"), "wb")) { fwrite(tr.data(), 8, tr.size(), f); fclose(f); }
   }
   if (getenv("HB_PHASES")) {
+    fprintf(stderr, "[hb] exact class evaluations this sweep: %d\n", h.pad);
     static const char* nm[16] = {"wait_dots", "guess", "wait_prev", "bar_rhs0", "chain", "first", "post", "commit",
                                  "bar_chain", "loop", "bar_part", "classify", "bar_bad", "-", "-", "-"};
     for (int g = 0; g < 2; ++g) {

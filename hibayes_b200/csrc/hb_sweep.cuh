@@ -451,8 +451,8 @@ __device__ __forceinline__ int thr_class(int nf, double rr, const double* TL, co
 
 // Brackets of the class boundaries of one SNP (device, k_prep).  phi_b(rr) = log S_hi - log S_lo - log((1-u)/u)
 // with S_lo = sum_{l<=b} e^{s_l}, S_hi = sum_{l>b} e^{s_l}, s_0 = log pi_0, s_l = a_l + c_l rr, is increasing;
-// safeguarded Newton finds its root, the bracket is widened by 1e-9 relative and both ends are certified with
-// a margin far above the rounding error of class_cum.
+// safeguarded Newton finds its root; a small bracket around it is certified at both ends with a margin far
+// above the rounding error of class_cum.
 template <int NF>
 __device__ void solve_thresholds(int nf, double u, const double* a, const double* c, double logpi0, double* TL, double* TH) {
   const double INF = __longlong_as_double(0x7ff0000000000000ll);
@@ -480,14 +480,14 @@ __device__ void solve_thresholds(int nf, double u, const double* a, const double
     double df, f = phi(0.0, df);
     double theta = 0.0;
     bool have = false;
-    if (f > 1e-9) {
+    if (f >= 0.0) {
       // never at or below class b: certify at rr = 0 (cum_b decreases from there)
       double cum[NF];
       class_cum<NF>(nf, 0.0, a, c, logpi0, cum);
-      if (cum[b] < u * (1.0 - 1e-11)) { TL[b] = -1.0; TH[b] = -1.0; }
+      if (cum[b] < u - 1e-13) { TL[b] = -1.0; TH[b] = -1.0; }
       continue;
     }
-    if (f < -1e-9) {
+    {
       double lo = 0.0, hi = INF, rr = 0.0;
       for (int it = 0; it < 60; ++it) {
         if (!(df > 0.0)) break;
@@ -501,14 +501,17 @@ __device__ void solve_thresholds(int nf, double u, const double* a, const double
       }
     }
     if (!have || !(df > 0.0)) continue;
-    const double w = 1e-9 * theta + 2e-10 / df;
+    // bracket: 2e-8 in log-odds on either side of the root (the chance that rhs^2 falls inside is ~1e-8 per
+    // decision); the ends are certified with an absolute margin of 1e-13 on the cumulative probability,
+    // two orders above the rounding error of class_cum
+    const double w = 1e-9 * theta + 2e-8 / df;
     const double tl = theta - w, th = theta + w;
     double cum[NF];
     class_cum<NF>(nf, th, a, c, logpi0, cum);
-    if (!(cum[b] < u * (1.0 - 1e-11))) continue;
+    if (!(cum[b] < u - 1e-13)) continue;
     if (tl >= 0.0) {
       class_cum<NF>(nf, tl, a, c, logpi0, cum);
-      if (!(cum[b] > u * (1.0 + 1e-11))) continue;
+      if (!(cum[b] > u + 1e-13)) continue;
       TL[b] = tl;
     }
     TH[b] = th;
@@ -534,7 +537,7 @@ __device__ __forceinline__ CandSet make_candset(uint8_t* smem, int B) {
 }
 
 // Shared memory of a scalar CTA: candidate arrays, two partial-sum arrays, and two buffers with the Gram rows of
-// the tile's candidates (converted to double while they are gathered): rows0 = diagonal block, rows1 = block
+// the tile's candidates (exact int32, as stored): rows0 = diagonal block, rows1 = block
 // towards the next tile.
 __host__ __device__ inline size_t scalar_fixed_bytes(int B) {
   size_t b = (8 * (size_t)B) * 8 + (3 * (size_t)B + 64 + 16) * 4 + 18 * 8 + 64;   // candidates + partials, ints, timers
@@ -543,11 +546,11 @@ __host__ __device__ inline size_t scalar_fixed_bytes(int B) {
 __host__ inline int scalar_krow(int B) {
   const size_t cap = 226 * 1024;
   const size_t fixed = scalar_fixed_bytes(B);
-  size_t rows = (cap - fixed) / (2 * (size_t)B * 8);
+  size_t rows = (cap - fixed) / (2 * (size_t)B * 4);
   if (rows > (size_t)B) rows = (size_t)B;
   return (int)rows;
 }
-__host__ inline size_t scalar_smem_bytes(int B) { return scalar_fixed_bytes(B) + 2 * (size_t)scalar_krow(B) * B * 8; }
+__host__ inline size_t scalar_smem_bytes(int B) { return scalar_fixed_bytes(B) + 2 * (size_t)scalar_krow(B) * B * 4; }
 
 // exact int32 -> double for 0 <= g < 2^31 on the full-rate pipe (one DADD instead of a quarter-rate I2F)
 __device__ __forceinline__ double gram_as_double(int g) {
@@ -556,15 +559,18 @@ __device__ __forceinline__ double gram_as_double(int g) {
 
 // Gathers the Gram rows of the k candidates from one band block into a row buffer as doubles: thread i takes
 // column i of every row (coalesced), sixteen loads in flight.
-__device__ __forceinline__ void gather_rows(double* dst, const int32_t* __restrict__ blk, const int* idx, int k, int B, int i) {
-  for (int sb = 0; sb < k; sb += 16) {
-    int gv[16];
-    const int nb = min(16, k - sb);
+__device__ __noinline__ void gather_rows(int32_t* dst, const int32_t* __restrict__ blk, const int* idx, int k, int B, int i) {
+  // kept small (rolled, 8 loads per round trip) and out of line: this runs off the critical path, and the code of
+  // a tile's phases has to stay inside the instruction cache
+#pragma unroll 1
+  for (int sb = 0; sb < k; sb += 8) {
+    int gv[8];
+    const int nb = min(8, k - sb);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) gv[e] = (e < nb) ? __ldcg(blk + (size_t)idx[sb + e] * B + i) : 0;
+    for (int e = 0; e < 8; ++e) gv[e] = (e < nb) ? __ldcg(blk + (size_t)idx[sb + e] * B + i) : 0;
 #pragma unroll
-    for (int e = 0; e < 16; ++e)
-      if (e < nb) dst[(size_t)(sb + e) * B + i] = gram_as_double(gv[e]);
+    for (int e = 0; e < 8; ++e)
+      if (e < nb) dst[(size_t)(sb + e) * B + i] = gv[e];
   }
 }
 
@@ -574,7 +580,7 @@ __device__ __forceinline__ void gather_rows(double* dst, const int32_t* __restri
 // e_s is final (= delta_s).  One shuffle and one fma per candidate on the dependent path.
 // ROWS: the candidates' Gram rows are in shared memory (doubles); otherwise they are read from global.
 template <bool ROWS>
-__device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const int32_t* __restrict__ G, const double* rows, int B, int lane) {
+__device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const int32_t* __restrict__ G, const int32_t* rows, int B, int lane) {
   for (int sb = 0; sb < k; sb += 32) {
     const int sidx = sb + lane;
     const bool valid = sidx < k;
@@ -583,7 +589,7 @@ __device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const
     const double niv = -iv;
     double e = valid ? fma(cs.rhs0[sidx], iv, cs.sdz[sidx]) - gold : 0.0;
     auto gval = [&](int sp) -> double {
-      return ROWS ? rows[(size_t)sp * B + ci] : gram_as_double(__ldcg(G + (size_t)cs.idx[sp] * B + ci));
+      return gram_as_double(ROWS ? rows[(size_t)sp * B + ci] : __ldcg(G + (size_t)cs.idx[sp] * B + ci));
     };
     // candidates of earlier chunks: their changes are final
     for (int sp = 0; sp < sb; sp += 8) {
@@ -594,19 +600,42 @@ __device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const
       for (int q = 0; q < 8; ++q) e = fma(gv[q], cs.delta[sp + q], e);
     }
     const int nl = min(32, k - sb);
-    // -G[c_(sb+lp)][c_s]/v_s for the next four steps (software pipeline: loads stay off the chain)
-    auto hload = [&](int lp) -> double {
-      double h = 0.0;
-      if (valid && lp < lane && lp < nl) h = gval(sb + lp) * niv;
-      return h;
-    };
-    double h0 = hload(0), h1 = hload(1), h2 = hload(2), h3 = hload(3);
+    if (ROWS) {
+      // two halves of 16 steps: the coefficients -G[c_(sb+lp)][c_s]/v_s of a half go to registers first, then
+      // the steps run fully unrolled: one shuffle and one fma each
+#pragma unroll
+      for (int hc = 0; hc < 2; ++hc) {
+        if (16 * hc < nl) {
+          double hreg[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int lp = 16 * hc + q;
+            const int row = min(sb + lp, k - 1);
+            const double gv = gram_as_double(rows[(size_t)row * B + ci]) * niv;
+            hreg[q] = (valid && lp < lane && lp < nl) ? gv : 0.0;
+          }
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const double d = __shfl_sync(0xffffffffu, e, 16 * hc + q);
+            e = fma(hreg[q], d, e);   // hreg = 0 for the lanes at or before the step: their e is final
+          }
+        }
+      }
+    } else {
+      // -G[c_(sb+lp)][c_s]/v_s for the next four steps (software pipeline: loads stay off the chain)
+      auto hload = [&](int lp) -> double {
+        double h = 0.0;
+        if (valid && lp < lane && lp < nl) h = gval(sb + lp) * niv;
+        return h;
+      };
+      double h0 = hload(0), h1 = hload(1), h2 = hload(2), h3 = hload(3);
 #pragma unroll 4
-    for (int lp = 0; lp < nl; ++lp) {
-      const double hcur = h0;
-      h0 = h1; h1 = h2; h2 = h3; h3 = hload(lp + 4);
-      const double d = __shfl_sync(0xffffffffu, e, lp);
-      e = fma(hcur, d, e);   // hcur = 0 for the lanes at or before lp: their e is final
+      for (int lp = 0; lp < nl; ++lp) {
+        const double hcur = h0;
+        h0 = h1; h1 = h2; h2 = h3; h3 = hload(lp + 4);
+        const double d = __shfl_sync(0xffffffffu, e, lp);
+        e = fma(hcur, d, e);   // hcur = 0 for the lanes at or before lp: their e is final
+      }
     }
     if (valid) { cs.delta[sidx] = e; cs.gnew[sidx] = (cs.cls[sidx] > 0) ? gold + e : 0.0; }
     __syncwarp();
@@ -616,7 +645,7 @@ __device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const
 // Candidate chain of the dense models (RR/A/L; BayesL clamps the effect, Bayes.cpp:728, so the right-hand side
 // itself is chained):  rhs_s = rhs0_s - sum_{s' < s} G[c_s'][c_s] * delta_s', gnew_s = rhs_s/v + sd*z.
 template <bool ROWS>
-__device__ void solve_candidates(const CandSet& cs, int k, const int32_t* __restrict__ G, const double* rows, int B, int model,
+__device__ void solve_candidates(const CandSet& cs, int k, const int32_t* __restrict__ G, const int32_t* rows, int B, int model,
                                  int lane) {
   for (int sb = 0; sb < k; sb += 32) {
     const int sidx = sb + lane;
@@ -626,7 +655,7 @@ __device__ void solve_candidates(const CandSet& cs, int k, const int32_t* __rest
     const double iv = valid ? cs.iv[sidx] : 0.0, sdz = valid ? cs.sdz[sidx] : 0.0, gold = valid ? cs.gold[sidx] : 0.0;
     const int cls = valid ? cs.cls[sidx] : 0;
     auto gval = [&](int sp) -> double {
-      return ROWS ? rows[(size_t)sp * B + ci] : gram_as_double(__ldcg(G + (size_t)cs.idx[sp] * B + ci));
+      return gram_as_double(ROWS ? rows[(size_t)sp * B + ci] : __ldcg(G + (size_t)cs.idx[sp] * B + ci));
     };
     for (int sp = 0; sp < sb; sp += 8) {
       double gv[8];
@@ -656,24 +685,27 @@ __device__ void solve_candidates(const CandSet& cs, int k, const int32_t* __rest
 }
 
 // corr_i = sum_s G[c_s][i] * delta_s over the k candidates (ascending s), read from global memory
-__device__ __forceinline__ double band_correction(const CandSet& cs, int k, const int32_t* __restrict__ gb, int B, int i) {
+__device__ __noinline__ double band_correction_raw(const int* idx, const double* delta, int k, const int32_t* __restrict__ gb, int B, int i) {
   double corr = 0.0;
-  for (int sb = 0; sb < k; sb += 16) {
-    int gv[16];
+#pragma unroll 1
+  for (int sb = 0; sb < k; sb += 8) {
+    int gv[8];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) gv[e] = (sb + e < k) ? __ldcg(gb + (size_t)cs.idx[sb + e] * B + i) : 0;
+    for (int e = 0; e < 8; ++e) gv[e] = (sb + e < k) ? __ldcg(gb + (size_t)idx[sb + e] * B + i) : 0;
 #pragma unroll
-    for (int e = 0; e < 16; ++e)
-      if (sb + e < k) corr = fma(gram_as_double(gv[e]), cs.delta[sb + e], corr);
+    for (int e = 0; e < 8; ++e)
+      if (sb + e < k) corr = fma(gram_as_double(gv[e]), delta[sb + e], corr);
   }
   return corr;
+}
+__device__ __forceinline__ double band_correction(const CandSet& cs, int k, const int32_t* __restrict__ gb, int B, int i) {
+  return band_correction_raw(cs.idx, cs.delta, k, gb, B, i);
 }
 
 // Tiles with more candidates than a row buffer holds (k > KROW): chain and sums straight from the Gram band in
 // global memory.  Rare and slow; kept out of line so that the common path stays compact in the instruction cache.
-__device__ __noinline__ void slow_chain_and_sums(int k, int myrank, const int32_t* __restrict__ G0, int B,
-                                                 int i, int h, bool has1, bool dense, int model, int nthreads, double* prhs,
-                                                 double* pcorr) {
+__device__ __noinline__ double slow_chain_and_sums(int k, int myrank, const int32_t* __restrict__ G0, int B,
+                                                 int i, int h, bool has1, bool dense, int model, int nthreads) {
   extern __shared__ __align__(128) uint8_t smem_slow[];
   const CandSet cs = make_candset(smem_slow, B);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -682,10 +714,9 @@ __device__ __noinline__ void slow_chain_and_sums(int k, int myrank, const int32_
     else chain_candidates<false>(cs, k, G0, nullptr, B, lane);
   }
   hb::named_bar_sync(1, nthreads);
-  *prhs = 0.0;
-  *pcorr = 0.0;
-  if (h == 0) *prhs = band_correction(cs, myrank, G0, B, i);
-  else if (has1) *pcorr = band_correction(cs, k, G0 + (size_t)B * B, B, i);
+  // the primary half returns its right-hand-side sum, the secondary half the corrections for the next tile
+  if (h == 0) return band_correction(cs, myrank, G0, B, i);
+  return has1 ? band_correction(cs, k, G0 + (size_t)B * B, B, i) : 0.0;
 }
 
 // exact class of SNP j given rr = rhs^2 (reads its a_k, c_k and uniform from the parameter table)
@@ -702,7 +733,13 @@ __device__ __noinline__ int classify_exact(const double* __restrict__ prm, size_
 }
 
 template <int NF, bool DENSE>
-__device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
+__device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
+  // the parameters are read all along the serial phase: keep a copy in shared memory instead of going through the
+  // constant cache, which the long code of a tile keeps evicting (a miss there costs a trip to L2)
+  __shared__ SweepParams ps;
+  for (int w = threadIdx.x; w < (int)(sizeof(SweepParams) / 4); w += blockDim.x) ((int*)&ps)[w] = ((const int*)&pin)[w];
+  __syncthreads();
+  const SweepParams& p = ps;
   // Worker w (= scalar CTA w) owns tiles w, w + NG, w + 2 NG, ...  Two threads per SNP of the tile: the
   // primary half (h = 0) and the secondary half (h = 1) split the gathers and the correction sums.
   // A tile goes through three phases:
@@ -722,10 +759,10 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
   // ---- shared memory carve-up
   CandSet cs;
   double *part_rhs, *part_corr;   // secondary half's partial sums
-  int *wcnt, *wbad, *rank_sh;     // rank_sh[i] = number of candidates before SNP i
+  int *wcnt, *rank_sh;            // rank_sh[i] = number of candidates before SNP i
   volatile int* gctl;             // [0] abort flag, [1] number of candidates
   long long* phase;
-  double *rows0, *rows1;
+  int32_t *rows0, *rows1;
   {
     cs = make_candset(smem, B);
     double* d = (double*)smem;
@@ -733,24 +770,22 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
     d += 8 * (size_t)B;
     int* ip = (int*)d;
     rank_sh = ip + 2 * B; ip += 3 * (size_t)B;
-    wcnt = ip; wbad = ip + 32; ip += 64;
+    wcnt = ip; ip += 64;
     gctl = ip; ip += 16;
     phase = (long long*)ip;
     uint8_t* rb = smem + scalar_fixed_bytes(B);
-    rows0 = (double*)rb;
+    rows0 = (int32_t*)rb;
     rows1 = rows0 + (size_t)p.KROW * B;
   }
   const int KROW = p.KROW;
   const int NT2 = 2 * B;   // threads of the worker
   if (tid < 8) gctl[tid] = 0;
-  if (tid < 32) wbad[tid] = 1 << 30;
   hb::named_bar_sync(1, NT2);
 
   const size_t mp = p.m_pad;
   constexpr bool dense = DENSE;   // RR / A / L: every SNP changes in every sweep
   const int nf = (model == HB_MODEL_R) ? F : 2;
   const bool use_thr = p.use_thr && !dense;
-  const int NONE = 1 << 30;
   const int DC = D - 1;   // correction slots per tile
   bool dead = false;
   int rounds_total = 0, changed_total = 0;
@@ -803,6 +838,7 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
         const int c0 = thr_class<NF>(nf, rr, TL, TH);
         if (c0 >= 0) return c0;
       }
+      atomicAdd(&p.out->pad, 1);   // diagnostic: exact evaluations
       return classify_exact<NF>(p.prm, mp, j, nf, rr, p.logpi0);
     };
     // corrections owed by the tiles t-D+1 .. t-1: whatever has been posted by now goes into the speculation
@@ -931,11 +967,13 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
 #pragma unroll 4
         for (int sidx = h; sidx < k; sidx += 2) {
           const double d = cs.delta[sidx];
-          if (sidx < myrank) prhs = fma(rows0[(size_t)sidx * B + i], d, prhs);
-          if (has1) pcorr = fma(rows1[(size_t)sidx * B + i], d, pcorr);
+          const double g0 = gram_as_double(rows0[(size_t)sidx * B + i]), g1 = gram_as_double(rows1[(size_t)sidx * B + i]);
+          prhs = fma(sidx < myrank ? g0 : 0.0, d, prhs);
+          pcorr = fma(has1 ? g1 : 0.0, d, pcorr);
         }
       } else {
-        slow_chain_and_sums(k, myrank, G0, B, i, h, has1, dense, model, NT2, &prhs, &pcorr);
+        const double sv = slow_chain_and_sums(k, myrank, G0, B, i, h, has1, dense, model, NT2);
+        if (prim) prhs = sv; else pcorr = sv;
       }
       if (!prim) { part_rhs[i] = prhs; part_corr[i] = pcorr; }
       HB_PHASE(9);
@@ -956,20 +994,15 @@ __device__ void scalar_role(const SweepParams& p, uint8_t* smem) {
         }
       }
       const bool bad = prim && act && (cls2 != cls);
-      const unsigned bal2 = __ballot_sync(0xffffffffu, bad);
-      if (prim && lane == 0) wbad[warp] = bal2 ? (warp * 32 + __ffs(bal2) - 1) : NONE;
-      if (dead) wbad[16 + (tid & 15)] = -1;
       HB_PHASE(11);
-      hb::named_bar_sync(1, NT2);
+      // one barrier tells everybody whether any class differs from its speculation (or a wait was abandoned)
+      const bool redo = hb::named_bar_or(1, NT2, bad || dead);
       HB_PHASE(12);
-      int first = NONE;
-      for (int w = 0; w < nwarp; ++w) first = min(first, wbad[w]);
-      for (int w = 16; w < 32; ++w) first = min(first, wbad[w]);
       if (prim) { cls = cls2; gnew = gnew2; }
       HB_PHASE(5);
-      if (first == NONE) break;   // every class equals its speculation: the tile is final
-      if (first < 0) { dead = true; break; }
-      // a class differed: everything before it is final; speculate again with the corrected classes
+      if (!redo) break;   // the tile is final
+      if (hb::named_bar_or(1, NT2, dead)) { dead = true; break; }
+      // a class differed: speculate again with the corrected classes
       compact();
     }
     if (dead) break;
