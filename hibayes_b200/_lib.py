@@ -3,6 +3,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+ALLREDUCE_F64 = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_size_t)
+ALLREDUCE_I32_DEV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
+ALLGATHER_BYTES = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
 _LIB = None
 MAX_FOLD = 8
 
@@ -15,7 +18,12 @@ SYMBOLS = [
     "hb_engine_set_vargL", "hb_engine_sweep", "hb_engine_set_windows", "hb_engine_accumulate_pip",
     "hb_engine_get_pip_counts", "hb_engine_accumulate_effects", "hb_engine_get_effect_sums", "hb_engine_predict",
     "hb_engine_last_sweep_ms", "hb_engine_describe", "hb_bayes",
+    "hb_engine_ipc_handle", "hb_engine_set_peers", "hb_engine_gram_device", "hb_engine_u_centered_sums",
 ]
+
+ALLREDUCE_F64 = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_size_t)
+ALLREDUCE_I32_DEV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
+ALLGATHER_BYTES = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
 
 
 class EngineConfig(C.Structure):
@@ -48,6 +56,9 @@ class BayesArgs(C.Structure):
         ("ne", C.c_int), ("qe", C.c_int), ("epsl_y_J", C.c_void_p), ("epsl_index", C.c_void_p),
         ("Gi_colptr", C.c_void_p), ("Gi_rowidx", C.c_void_p), ("Gi_val", C.c_void_p),
         ("device", C.c_int), ("tile_snps", C.c_int), ("lag_tiles", C.c_int), ("n_slabs", C.c_int),
+        ("rank", C.c_int), ("world", C.c_int), ("n_total", C.c_longlong), ("comm_ctx", C.c_void_p),
+        ("allreduce_sum_f64", ALLREDUCE_F64), ("allreduce_sum_i32_dev", ALLREDUCE_I32_DEV),
+        ("allgather_bytes", ALLGATHER_BYTES),
     ]
 
 
@@ -109,6 +120,10 @@ def load_library():
     L.hb_engine_describe.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.hb_bayes.argtypes = [C.POINTER(BayesArgs), C.POINTER(BayesOut)]
+    L.hb_engine_ipc_handle.argtypes = [C.c_void_p, C.c_void_p]
+    L.hb_engine_set_peers.argtypes = [C.c_void_p, C.c_void_p]
+    L.hb_engine_gram_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.hb_engine_u_centered_sums.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _LIB = L
     return L
 

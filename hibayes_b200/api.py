@@ -34,7 +34,7 @@ def synth_geno_host(n, m, seed, row_offset=0):
 def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, niter=50000, nburn=20000, thin=5,
           epsl_y_J=None, epsl_Gi=None, epsl_index=None, dfvr=None, s2vr=None, vg=None, dfvg=None, s2vg=None,
           ve=None, dfve=None, s2ve=None, windindx=None, outfreq=100, threads=0, verbose=False,
-          seed=666666, device=0, tile_snps=0, lag_tiles=0, n_slabs=0, store_alpha=False):
+          seed=666666, device=0, tile_snps=0, lag_tiles=0, n_slabs=0, store_alpha=False, comm=None):
     """GPU twin of hibayes' Bayes().  R: (n, nr) integer level codes (0-based) standing for the
     CharacterMatrix of environmental random effects; seed: the Philox run key the Rcpp shim
     derives from R's RNG state (the reference takes no seed argument, Bayes.cpp:60-88)."""
@@ -106,6 +106,10 @@ def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, nite
         keep += [ei, cp, ri, gv, yj]
     a.ne, a.qe = ne, qe
     a.device, a.tile_snps, a.lag_tiles, a.n_slabs = device, tile_snps, lag_tiles, n_slabs
+    if comm is not None and comm.world > 1:
+        a.rank, a.world, a.n_total = comm.rank, comm.world, comm.total_rows(n)
+        a.allreduce_sum_f64, a.allreduce_sum_i32_dev, a.allgather_bytes = comm.callbacks()
+        keep.append(comm)
     nrec = max((niter - nburn) // thin, 0)
     o = _lib.BayesOut()
     res = {

@@ -84,6 +84,10 @@ struct hb_engine {
   int* tile_cnt = nullptr;
   double* corr = nullptr;
   double xpx_max = 0.0;
+  unsigned long long* acc2 = nullptr;          // [2][m_pad] second-level dot accumulators (row-sharded runs), by sweep parity
+  unsigned long long* peer_acc2[8] = {nullptr};  // every rank's acc2 (IPC mappings; [rank] = acc2)
+  bool peers_ready = false;
+  unsigned sweep_no = 0;
   unsigned long long* trace = nullptr;
   int KROW = 0;
   int* ctrl = nullptr;  // [0] progress, [1] abort
@@ -358,7 +362,7 @@ __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8
                        const double* __restrict__ g, const double* __restrict__ vargL, double* __restrict__ prm,
                        unsigned long long* __restrict__ dacc, int* __restrict__ ctrl, SweepOutDev* __restrict__ out,
                        int* __restrict__ tile_cnt, int* __restrict__ q_snp, unsigned long long* __restrict__ q_delta,
-                       unsigned long long* __restrict__ corr, int B, int DC) {
+                       unsigned long long* __restrict__ corr, int B, int DC, unsigned long long* __restrict__ acc2_next) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) {
     ctrl[0] = 0; ctrl[1] = 0;
@@ -368,6 +372,7 @@ __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8
   if (j < p.T) tile_cnt[j] = -1;
   if (j >= p.m_pad) return;
   dacc[j] = 0ull;
+  if (acc2_next) acc2_next[j] = 0ull;   // the buffer of the sweep after this one (see hb_engine_sweep)
   q_snp[j] = -1;
   q_delta[j] = hbk::kCorrEmpty;
   {
@@ -690,6 +695,12 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   CU(cudaMalloc(&e->q_snp, mp * 4));
   CU(cudaMalloc(&e->q_delta, mp * 8));
   CU(cudaMalloc(&e->tile_cnt, (size_t)e->T * 4));
+  if (cfg->world > 1) {
+    if (cfg->world > 8 || cfg->rank < 0 || cfg->rank >= cfg->world) { hb_engine_destroy(e); return hb_set_error("hb_engine_create: bad rank/world (at most 8 ranks)"); }
+    CU(cudaMalloc(&e->acc2, 2 * mp * 8));
+    CU(cudaMemsetAsync(e->acc2, 0, 2 * mp * 8, e->stream));
+    e->peer_acc2[cfg->rank] = e->acc2;
+  }
   CU(cudaMalloc(&e->corr, std::max<size_t>(1, (size_t)e->m_pad * (e->D - 1)) * 8));
   CU(cudaMalloc(&e->ctrl, 64)); CU(cudaMemsetAsync(e->ctrl, 0, 64, e->stream));
   CU(cudaMalloc(&e->out_dev, sizeof(SweepOutDev)));
@@ -706,7 +717,9 @@ extern "C" void hb_engine_destroy(hb_engine* e) {
   cudaFree(e->Xp); cudaFree(e->r); cudaFree(e->u); cudaFree(e->xpx); cudaFree(e->g); cudaFree(e->gsum);
   cudaFree(e->nzrate); cudaFree(e->wppa); cudaFree(e->vargL); cudaFree(e->active); cudaFree(e->tracker);
   cudaFree(e->gram); cudaFree(e->dacc); cudaFree(e->q_snp); cudaFree(e->q_delta);
-  cudaFree(e->tile_cnt); cudaFree(e->corr); cudaFree(e->ctrl); cudaFree(e->prm); cudaFree(e->out_dev); cudaFree(e->post_partial); cudaFree(e->fold_dev); cudaFree(e->wstart); cudaFree(e->wmem);
+  cudaFree(e->tile_cnt); cudaFree(e->corr); cudaFree(e->trace);
+  for (int g = 0; g < 8; ++g) if (e->peer_acc2[g] && e->peer_acc2[g] != e->acc2) cudaIpcCloseMemHandle(e->peer_acc2[g]);
+  cudaFree(e->acc2); cudaFree(e->ctrl); cudaFree(e->prm); cudaFree(e->out_dev); cudaFree(e->post_partial); cudaFree(e->fold_dev); cudaFree(e->wstart); cudaFree(e->wmem);
   for (int i = 0; i < 4; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -928,6 +941,13 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   sp.gram = e->gram; sp.dacc = e->dacc; sp.q_snp = e->q_snp; sp.q_delta = e->q_delta;
   if (getenv("HB_TRACE") && !e->trace) { CU(cudaMalloc(&e->trace, (size_t)e->T * 64)); CU(cudaMemset(e->trace, 0, (size_t)e->T * 64)); }
   sp.trace = e->trace;
+  sp.world = std::max(1, e->cfg.world); sp.rank = e->cfg.rank;
+  if (sp.world > 1) {
+    if (!e->peers_ready) return hb_set_error("hb_engine_sweep: world = %d but hb_engine_set_peers has not been called", sp.world);
+    // second-level accumulators alternate between two buffers: a rank that is one sweep ahead adds into the buffer
+    // this rank has already cleared (k_prep of the previous sweep), never into the one still in use
+    for (int g = 0; g < sp.world; ++g) sp.peer_acc[g] = e->peer_acc2[g] + (size_t)(e->sweep_no & 1) * e->m_pad;
+  }
   sp.tile_cnt = e->tile_cnt; sp.corr = e->corr; sp.ctrl = e->ctrl; sp.prm = e->prm; sp.out = e->out_dev;
   sp.slab_stride = e->slab_stride; sp.m_pad = e->m_pad;
   sp.n = e->n; sp.m = e->m; sp.S = e->S; sp.R = e->R; sp.T = e->T; sp.B = e->B; sp.D = e->D;
@@ -954,7 +974,8 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   const bool dense_model = in->model_index == HB_MODEL_RR || in->model_index == HB_MODEL_A || in->model_index == HB_MODEL_L;
   CU(cudaEventRecord(e->ev[0], e->stream));
   k_prep<<<(e->m_pad + 255) / 256, 256, 0, e->stream>>>(pp, e->xpx, e->active, e->g, e->vargL, e->prm, e->dacc, e->ctrl, e->out_dev,
-                                                       e->tile_cnt, e->q_snp, (unsigned long long*)e->q_delta, (unsigned long long*)e->corr, e->B, e->D - 1);
+                                                       e->tile_cnt, e->q_snp, (unsigned long long*)e->q_delta, (unsigned long long*)e->corr, e->B, e->D - 1,
+                                                       e->acc2 ? e->acc2 + (size_t)((e->sweep_no + 1) & 1) * e->m_pad : nullptr);
   CU(cudaGetLastError());
   CU(cudaEventRecord(e->ev[1], e->stream));
   {
@@ -977,6 +998,7 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   k_tail<<<1, 1024, 0, e->stream>>>(e->r, e->u, e->n, e->out_dev, e->ctrl);
   CU(cudaGetLastError());
   CU(cudaEventRecord(e->ev[3], e->stream));
+  e->sweep_no++;
   SweepOutDev h;
   CU(cudaMemcpyAsync(&h, e->out_dev, sizeof h, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
@@ -1097,5 +1119,60 @@ extern "C" int hb_engine_predict(hb_engine* e, const double* alpha, double* out)
   CU(cudaMemcpyAsync(out, dout, (size_t)e->n * 8, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   cudaFree(da); cudaFree(dp); cudaFree(dout);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// row sharding over several GPUs (one process and one engine per GPU)
+// ------------------------------------------------------------------------------------------
+extern "C" int hb_engine_ipc_handle(hb_engine* e, void* handle64) {
+  if (!e || !handle64) return hb_set_error("hb_engine_ipc_handle: null argument");
+  if (!e->acc2) return hb_set_error("hb_engine_ipc_handle: engine was created with world = 1");
+  CU(cudaSetDevice(e->cfg.device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, e->acc2));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+extern "C" int hb_engine_set_peers(hb_engine* e, const void* handles) {
+  if (!e || !handles) return hb_set_error("hb_engine_set_peers: null argument");
+  if (!e->acc2) return hb_set_error("hb_engine_set_peers: engine was created with world = 1");
+  CU(cudaSetDevice(e->cfg.device));
+  for (int g = 0; g < e->cfg.world; ++g) {
+    if (g == e->cfg.rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + 64 * (size_t)g, 64);
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    e->peer_acc2[g] = (unsigned long long*)ptr;
+  }
+  e->peers_ready = true;
+  return 0;
+}
+extern "C" int hb_engine_gram_device(hb_engine* e, void** ptr, uint64_t* count) {
+  if (!e || !ptr || !count) return hb_set_error("hb_engine_gram_device: null argument");
+  if (!e->gram_ready) return hb_set_error("hb_engine_gram_device: gram not built");
+  *ptr = e->gram;
+  *count = (uint64_t)e->T * e->D * e->B * e->B;
+  return 0;
+}
+// sum over the local rows of (mean - u)^2 and (mean - u): the two accumulators of Armadillo's var(), Bayes.cpp:819
+__global__ void __launch_bounds__(1024) k_centered(const double* __restrict__ u, int n, double mean, double* out2) {
+  __shared__ double sh[1024];
+  double e = 0, f = 0;
+  for (int i = threadIdx.x; i < n; i += 1024) { double x = mean - u[i]; e += x * x; f += x; }
+  e = block_sum_1024(e, sh); f = block_sum_1024(f, sh);
+  if (threadIdx.x == 0) { out2[0] = e; out2[1] = f; }
+}
+extern "C" int hb_engine_u_centered_sums(hb_engine* e, double mean, double* ss, double* s1) {
+  if (!e || !ss || !s1) return hb_set_error("hb_engine_u_centered_sums: null argument");
+  CU(cudaSetDevice(e->cfg.device));
+  k_centered<<<1, 1024, 0, e->stream>>>(e->u, e->n, mean, e->post_partial);
+  CU(cudaGetLastError());
+  double h[2];
+  CU(cudaMemcpyAsync(h, e->post_partial, 16, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  *ss = h[0]; *s1 = h[1];
   return 0;
 }

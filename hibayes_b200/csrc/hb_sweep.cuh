@@ -53,6 +53,9 @@ struct SweepParams {
   int32_t* tracker;
   const int32_t* gram;
   unsigned long long* dacc;   // per SNP: sum over slabs of (fixed-point dot << 8) + 1
+  unsigned long long* peer_acc[8];   // row-sharded runs: every rank's second-level accumulators (this sweep's buffer):
+                                     // sum over ranks of (local fixed-point dot << 4) + 1; [rank] is the local one
+  int world, rank;
   int* q_snp;                 // [T][B] changed SNPs of tile t (global index), -1 = not yet written
   double* q_delta;            // [T][B] their effect changes, kCorrEmpty = not yet written
   int* tile_cnt;              // per tile: number of changes, -1 until known
@@ -874,7 +877,25 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
           w = ld_relaxed_u64(p.dacc + j);
         } while ((w & 0xffull) != (unsigned long long)p.S);
       }
-      base0 = (double)((long long)w >> 8) * p.inv_dscale;
+      long long fx = (long long)w >> 8;
+      if (p.world > 1) {
+        // rows are sharded over the ranks: add this rank's exact integer part of the dot to every rank's
+        // accumulator over NVLink (peer atomics), then wait until all parts have arrived here.  Integer sums do
+        // not depend on the order, so every rank ends up with the same dot and takes the same decisions.
+        const unsigned long long part = ((unsigned long long)fx << 4) + 1ull;
+        for (int g = 0; g < p.world; ++g)
+          asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p.peer_acc[g] + j), "l"(part) : "memory");
+        unsigned long long w2;
+        Waiter wt;
+        for (;;) {
+          asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w2) : "l"(p.peer_acc[p.rank] + j) : "memory");
+          if ((w2 & 0xfull) == (unsigned long long)p.world) break;
+          __nanosleep(200);
+          if (!wt.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) { dead = true; break; }
+        }
+        fx = (long long)w2 >> 4;
+      }
+      base0 = (double)fx * p.inv_dscale;
     }
     HB_PHASE(0);
     if (tid == 0) HB_TRACE(t, 0);

@@ -72,6 +72,20 @@ double seconds_since(const std::chrono::steady_clock::time_point& t0) {
 extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
   if (!a || !o) return hb_set_error("hb_bayes: null argument");
   const int n = a->n, m = a->m;
+  const int world = a->world > 1 ? a->world : 1;
+  const double ntot = world > 1 ? (double)a->n_total : (double)n;   // individuals over all ranks
+  if (world > 1) {
+    if (!a->allreduce_sum_f64 || !a->allreduce_sum_i32_dev || !a->allgather_bytes || a->n_total < n)
+      return hb_set_error("hb_bayes: world = %d needs n_total and the three collectives", world);
+    if (a->nc || a->nr || a->ne)
+      return hb_set_error("hb_bayes: covariates, environmental random effects and the single-step term are not sharded in this build");
+  }
+  // sum over ranks, in place (no-op on one rank)
+  auto allsum = [&](double* buf, size_t cnt) -> int {
+    if (world <= 1) return 0;
+    if (a->allreduce_sum_f64(a->comm_ctx, buf, cnt) != 0) return hb_set_error("hb_bayes: all-reduce failed");
+    return 0;
+  };
   const std::string model = a->model ? a->model : "";
   const hb_key_t KEY = hb_make_key(a->seed);
 
@@ -95,7 +109,16 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
   }
   if (n_fold > HB_MAX_FOLD) return hb_set_error("this build supports at most %d mixture components", HB_MAX_FOLD);
 
-  const double vary = arma_var(a->y, n);
+  double vary = arma_var(a->y, n), ymean = acc_sum(a->y, n) / (double)n;
+  if (world > 1) {   // the same two-pass variance over all ranks
+    double s0 = acc_sum(a->y, n);
+    HBCHK(allsum(&s0, 1));
+    ymean = s0 / ntot;
+    double acc[2] = {0.0, 0.0};
+    for (int i = 0; i < n; ++i) { const double t = ymean - a->y[i]; acc[0] += t * t; acc[1] += t; }
+    HBCHK(allsum(acc, 2));
+    vary = (acc[0] - acc[1] * acc[1] / ntot) / (ntot - 1.0);
+  }
   const double h2 = 0.5;
   const int niter = a->niter, nburn = a->nburn, thin = a->thin;
   const int n_records = (niter - nburn) / thin;  // :124
@@ -154,25 +177,39 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
   // every SNP changes in every sweep of the dense models (RR/A/L): their tiles chain as a full triangular
   // recurrence, which favours short tiles; the mixture models change few SNPs per tile and favour long ones
   cfg.tile_snps = a->tile_snps ? a->tile_snps : ((model_index == 1 || model_index == 2 || model_index == 5) ? 64 : 256);
-  cfg.n_slabs = a->n_slabs; cfg.seed = a->seed; cfg.rank = 0; cfg.world = 1;
+  cfg.n_slabs = a->n_slabs; cfg.seed = a->seed; cfg.rank = world > 1 ? a->rank : 0; cfg.world = world;
   HBCHK(hb_engine_create(&cfg, &guard.e));
   hb_engine* E = guard.e;
   if (a->x_type == 1) HBCHK(hb_engine_load_geno_i8(E, (const int8_t*)a->X, (size_t)n));
   else HBCHK(hb_engine_load_geno_f64(E, (const double*)a->X, (size_t)n));
   std::vector<double> xpx(m), sumx(m), vx(m);
   HBCHK(hb_engine_col_stats(E, xpx.data(), sumx.data()));
+  HBCHK(allsum(xpx.data(), m));   // exact: integer-valued doubles
+  HBCHK(allsum(sumx.data(), m));
   std::vector<uint8_t> active(m);
   int nvar0 = 0;
   for (int i = 0; i < m; ++i) {
     // var(x) from exact integer sums; zero exactly when the column is constant
-    const bool constant = ((double)n * xpx[i] == sumx[i] * sumx[i]);
-    vx[i] = constant ? 0.0 : (xpx[i] - sumx[i] * sumx[i] / (double)n) / (double)(n - 1);
+    const bool constant = (ntot * xpx[i] == sumx[i] * sumx[i]);
+    vx[i] = constant ? 0.0 : (xpx[i] - sumx[i] * sumx[i] / ntot) / (ntot - 1.0);
     active[i] = constant ? 0 : 1;
     nvar0 += constant ? 1 : 0;
   }
   const double sumvx = acc_sum(vx.data(), m);
   HBCHK(hb_engine_set_snp_info(E, xpx.data(), active.data()));
   HBCHK(hb_engine_build_gram(E));
+  if (world > 1) {
+    // the Gram band is a sum over individuals as well (exact int32), and the ranks exchange the IPC handles of
+    // their dot accumulators so that the sweep kernels can add to each other over NVLink
+    void* gptr = nullptr;
+    uint64_t gcnt = 0;
+    HBCHK(hb_engine_gram_device(E, &gptr, &gcnt));
+    if (a->allreduce_sum_i32_dev(a->comm_ctx, gptr, (size_t)gcnt) != 0) return hb_set_error("hb_bayes: Gram all-reduce failed");
+    std::vector<char> mine(64), all(64 * (size_t)world);
+    HBCHK(hb_engine_ipc_handle(E, mine.data()));
+    if (a->allgather_bytes(a->comm_ctx, mine.data(), all.data(), 64) != 0) return hb_set_error("hb_bayes: all-gather failed");
+    HBCHK(hb_engine_set_peers(E, all.data()));
+  }
   if (a->windindx) HBCHK(hb_engine_set_windows(E, a->windindx));
   int nw = 0;
   if (a->windindx) for (int i = 0; i < m; ++i) if (a->windindx[i] > nw) nw = a->windindx[i];
@@ -200,13 +237,14 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
   for (int j = 0; j < n_fold; ++j) vara_fold[j] = (vara_ / ((1 - Pi[0]) * sumvx)) * fold_[j];
 
   // ---- state :469-471
-  double mu_, mu = acc_sum(a->y, n) / n;
+  double mu_, mu = ymean;
   std::vector<double> yadj(n), u_host;
   for (int i = 0; i < n; ++i) yadj[i] = a->y[i] - mu;
   HBCHK(hb_engine_set_residual(E, yadj.data()));
   const bool host_effects = (nc > 0 || nr > 0 || ne > 0);
   if (ne) u_host.assign(n, 0.0);
   double sum_r = acc_sum(yadj.data(), n), sum_r2 = ddot(n, yadj.data(), yadj.data());
+  if (world > 1) { double b2[2] = {sum_r, sum_r2}; HBCHK(allsum(b2, 2)); sum_r = b2[0]; sum_r2 = b2[1]; }
 
   double musum = 0, varasum = 0, varesum = 0, hsqsum = 0;
   std::vector<double> pisum(n_fold, 0.0), gtmp;
@@ -216,10 +254,10 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
   for (iter = 0; iter < niter; ++iter) {
     const uint32_t it = (uint32_t)iter;
     // intercept :480-482
-    mu_ = -(sum_r / n + sqrt(vare_ / n) * hb_draw_z(KEY, HB_DOM_ITER, it, HB_IT_MU, 0, 0));
+    mu_ = -(sum_r / ntot + sqrt(vare_ / ntot) * hb_draw_z(KEY, HB_DOM_ITER, it, HB_IT_MU, 0, 0));
     mu -= mu_;
     double mu_shift = mu_;
-    double rnorm2 = sum_r2 + 2.0 * mu_ * sum_r + (double)n * mu_ * mu_;
+    double rnorm2 = sum_r2 + 2.0 * mu_ * sum_r + ntot * mu_ * mu_;
     if (host_effects) {
       HBCHK(hb_engine_get_residual(E, yadj.data()));
       for (int i = 0; i < n; ++i) yadj[i] += mu_ * 1.0;
@@ -356,7 +394,18 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
     }
     sum_r = so.sum_r; sum_r2 = so.sum_r2;
     vara_ = so.var_u;                                                                                    // :819
-    vare_ = (so.sum_r2 + s2vare_ * dfvare_) / hb_draw_chisq(KEY, HB_DOM_ITER, it, HB_IT_VARE, 0, n + dfvare_);  // :823
+    if (world > 1) {
+      // per-iteration scalars are sums over the ranks' rows; var(u) with Armadillo's two accumulators about the
+      // global mean
+      double b3[3] = {so.sum_r, so.sum_r2, so.sum_u};
+      HBCHK(allsum(b3, 3));
+      sum_r = b3[0]; sum_r2 = b3[1];
+      double acc[2];
+      HBCHK(hb_engine_u_centered_sums(E, b3[2] / ntot, &acc[0], &acc[1]));
+      HBCHK(allsum(acc, 2));
+      vara_ = (acc[0] - acc[1] * acc[1] / ntot) / (ntot - 1.0);
+    }
+    vare_ = (sum_r2 + s2vare_ * dfvare_) / hb_draw_chisq(KEY, HB_DOM_ITER, it, HB_IT_VARE, 0, ntot + dfvare_);  // :823
 
     if (o->nnz_trace) o->nnz_trace[iter] = NnzSnp;
     if (o->vara_trace) o->vara_trace[iter] = vara_;

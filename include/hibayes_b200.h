@@ -46,7 +46,7 @@ typedef struct {
   int device;        /* CUDA ordinal */
   int n;             /* individuals held by this engine (rows of X, y) */
   int m;             /* SNPs (columns of X) */
-  int tile_snps;     /* B: SNPs per tile step; 0 = default (64) */
+  int tile_snps;     /* B: SNPs per tile step (64, 128 or 256); 0 = default (256) */
   int lag_tiles;     /* D: tiles in flight between a dot and its residual update; 0 = default */
   int n_slabs;       /* row slabs = streaming CTAs; 0 = default (SM count - 1, fewer for small n) */
   uint64_t seed;     /* Philox run key (hb_rng.h) */
@@ -127,6 +127,20 @@ int hb_engine_get_effect_sums(hb_engine* e, double* gsum);
 /* out[i] = sum_j X[i][j] * alpha[j] over the resident genotypes (the X*g of Bayes.cpp:971) */
 int hb_engine_predict(hb_engine* e, const double* alpha, double* out);
 
+/* Row sharding over the GPUs of one node: one process and one engine per GPU, created with
+ * (rank, world) and this rank's rows.  The x_j'r of Bayes.cpp:593 becomes a sum over ranks: inside the sweep
+ * kernel every rank adds its exact fixed-point part of a tile's dots to every rank's accumulators with NVLink
+ * peer atomics, so all ranks see identical dots and take identical decisions (no broadcast, no host round trip).
+ * hb_engine_ipc_handle() exports this rank's accumulators (64-byte CUDA IPC handle); the caller exchanges the
+ * handles (e.g. torch.distributed.all_gather) and passes all `world` of them, rank-ordered, to
+ * hb_engine_set_peers().  Set-up sums (xpx, sumx, the Gram band) and the per-iteration scalars of hb_sweep_out
+ * are all-reduced by the caller (NCCL): hb_engine_gram_device() exposes the int32 band on the device for that,
+ * hb_engine_u_centered_sums() gives the two accumulators of var(u) (Bayes.cpp:819) about a global mean. */
+int hb_engine_ipc_handle(hb_engine* e, void* handle64);
+int hb_engine_set_peers(hb_engine* e, const void* handles);
+int hb_engine_gram_device(hb_engine* e, void** device_ptr, uint64_t* n_int32);
+int hb_engine_u_centered_sums(hb_engine* e, double mean_u, double* sum_sq, double* sum_dev);
+
 /* timing of the last sweep's kernels in ms (prep, sweep, tail) measured with CUDA events */
 int hb_engine_last_sweep_ms(hb_engine* e, float* prep_ms, float* sweep_ms, float* tail_ms);
 /* description of the layout chosen: slabs, rows per slab, tile, lag, bytes of X on device */
@@ -158,6 +172,15 @@ typedef struct {
   const int32_t* Gi_colptr; const int32_t* Gi_rowidx; const double* Gi_val;
   /* engine knobs (0 = defaults) */
   int device, tile_snps, lag_tiles, n_slabs;
+  /* Row sharding (world > 1): y, X hold this rank's n individuals; n_total is the sum over ranks.  The caller
+   * supplies the collectives (torch.distributed / NCCL / MPI): all three return 0 on success and are called by
+   * every rank in the same order.  world <= 1: leave everything 0 / NULL. */
+  int rank, world;
+  long long n_total;
+  void* comm_ctx;
+  int (*allreduce_sum_f64)(void* ctx, double* host_buf, size_t count);        /* in place, host memory */
+  int (*allreduce_sum_i32_dev)(void* ctx, void* device_buf, size_t count);    /* in place, device memory */
+  int (*allgather_bytes)(void* ctx, const void* mine, void* all, size_t bytes_per_rank); /* rank-ordered */
 } hb_bayes_args;
 
 typedef struct {
