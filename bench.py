@@ -2,14 +2,22 @@
 """bench.py -- Gibbs SNP-updates/s of the BayesR sweep (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one MCMC iteration's SNP sweep over the whole synthetic genotype matrix
-(n=50 000 x m=1 000 000 int8 per SURVEY.md 8d, generated on the device) followed by the
-per-iteration reductions -- what replaces Bayes.cpp:586-823.  `value` times K steps on the device
-(CUDA events on the engine's stream, inputs resident in HBM); `e2e` times the same K steps through
-the host-facing C ABI with the residual crossing PCIe in both directions every step.
-`--impl reference` times the reference's own CPU data path (per-SNP ddot + 2 daxpy on a column-major
-fp64 matrix, Bayes.cpp:751-802) with all host threads on a bounded column sample of the workload.
+A "step" is one MCMC iteration's SNP sweep over the whole synthetic genotype matrix (n = 50 000
+individuals x m = 1 000 000 SNPs, int8, generated on the device) followed by the per-iteration reductions -- what
+replaces Bayes.cpp:586-823 -- driven by the host-side scalar updates of a BayesR chain.
+
+`value`     K steps timed with inputs resident in HBM (barrier + synchronize on both sides, max over ranks).
+`e2e`       the same K steps through the host-facing C ABI with HOST buffers: every step uploads the residual
+            (what the host driver does after its non-SNP effects) and downloads residual and genetic values.
+N > 1       weak scaling over individuals: every rank holds n = 50 000 rows of an N x 50 000-row matrix (the
+            reference's C3 shape is 8 x 25 000); a unit of `value` is one SNP update over one rank's 50 000-row
+            shard, so N ranks sweeping m SNPs do N x m units per step.  The dots of a tile are exchanged inside the
+            sweep kernel (NVLink peer atomics), scalars of the iteration by one small all-reduce.
+`--impl reference`  the reference's own CPU data path (per-SNP ddot + 2 daxpy on a column-major fp64 matrix,
+            Bayes.cpp:751-802, all host threads) on a bounded column sample of the same workload (oracle port: the
+            reference itself needs R/Rcpp/Armadillo and cannot be built here).
 """
 import argparse
 import json
@@ -29,16 +37,26 @@ METRIC = "gibbs_snp_updates_per_sec_bayesr_n50k"
 UNIT = "SNP-updates/s"
 PI0 = [0.95, 0.02, 0.02, 0.01]
 FOLD = [0.0, 1e-4, 1e-3, 1e-2]
+KERNELS_PER_STEP = 5   # k_prep, k_sweep, k_post1, k_post2, k_tail
 
 
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         try:
-            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy bandwidth)"
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic():
+    """dram bytes per k_sweep launch at the bench shape, from the committed ncu capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r01_sweep_traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -62,7 +80,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.1)
 
     def __enter__(self):
         self.th.start()
@@ -85,11 +103,11 @@ def cpu_reference(n, m_cpu, sweeps, threads):
 
 
 class Chain:
-    """Host-side scalar updates of the BayesR chain around hb_engine_sweep (Bayes.cpp:480-482,
-    803-823); numpy's generator stands in for the host draws -- only the workload matters here."""
+    """Host-side scalar updates of the BayesR chain around hb_engine_sweep (Bayes.cpp:480-482, 803-823); numpy's
+    generator stands in for the host draws (same seed on every rank) -- only the workload matters here."""
 
-    def __init__(self, n, m_active, vary, sumvx, seed):
-        self.n, self.m_active = n, m_active
+    def __init__(self, n_total, vary, sumvx, seed):
+        self.n = n_total
         self.rng = np.random.default_rng(seed)
         self.df = 4.0
         vara = (self.df - 2) / self.df * vary * 0.5
@@ -97,7 +115,7 @@ class Chain:
         self.varg = vara / ((1 - PI0[0]) * sumvx)
         self.s2varg = vara * (self.df - 2) / self.df / ((1 - PI0[0]) * sumvx)
         self.pi = np.array(PI0)
-        self.sum_r, self.sum_r2 = 0.0, vary * (n - 1)
+        self.sum_r, self.sum_r2 = 0.0, vary * (n_total - 1)
         self.it = 0
 
     def sweep_args(self):
@@ -107,13 +125,13 @@ class Chain:
                     vara_fold=[self.varg * f for f in FOLD], fold=FOLD, dfvara=self.df, s2varg=self.s2varg,
                     mu_shift=mu_, rnorm2_bound=rn2)
 
-    def update(self, so):
+    def update(self, so, sum_r, sum_r2):
         cnt = np.array(so["count"][:4])
         nnz = cnt[1:].sum()
         self.varg = (so["varg_acc"] + self.s2varg * self.df) / self.rng.chisquare(self.df + nnz)
         self.pi = self.rng.dirichlet(cnt + 1)
-        self.vare = so["sum_r2"] / self.rng.chisquare(self.n - 2)
-        self.sum_r, self.sum_r2 = so["sum_r"], so["sum_r2"]
+        self.vare = sum_r2 / self.rng.chisquare(self.n - 2)
+        self.sum_r, self.sum_r2 = sum_r, sum_r2
         self.it += 1
 
 
@@ -123,20 +141,20 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     n, m_cpu = args.n, args.m_cpu
-    # each "step" = one sweep over the m_cpu-column sample; hbo_time_sweep_fp64 runs one untimed
-    # warm-up sweep itself, then `steps` timed sweeps
+    # each "step" = one sweep over the m_cpu-column sample; hbo_time_sweep_fp64 runs one untimed warm-up sweep
+    # itself, then `steps` timed sweeps
     t0 = time.time()
     val = cpu_reference(n, m_cpu, max(1, args.steps), threads)
     wall = time.time() - t0
+    sample = ("n=%d x m=%d fp64 column-major, %d timed sweeps, OpenMP ddot/daxpy (oracle port; the reference needs "
+              "R/Rcpp/Armadillo and cannot be built here)" % (n, m_cpu, max(1, args.steps)))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * m_cpu / val, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BayesR sweep n=%d x m=1000000 (CPU sample: first %d columns, fp64 column-major X)" % (n, m_cpu),
-                   "n": n, "m_sample": m_cpu},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "n=%d x m=%d fp64, %d sweeps, OpenMP ddot/daxpy (reference not buildable: needs R/Rcpp)"
-                                   % (n, m_cpu, max(1, args.steps))},
+        "config": {"workload": "ibrm() BayesR sweep, synthetic n=%d x m=%d (CPU sample: first %d columns)" % (n, args.m, m_cpu),
+                   "n": n, "m": args.m, "m_sample": m_cpu},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
     }
@@ -148,96 +166,146 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
+    comm = None
     if world > 1:
         import torch
         import torch.distributed as dist
+        from hibayes_b200.sharded import Comm
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl")
-    n_total, m = args.n, args.m
-    # rows are sharded across ranks (weak scaling: n rows per GPU)
-    n_local = n_total
+        comm = Comm()
+
+    def allsum(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        return comm.allreduce_f64(a) if comm else a
+
+    def barrier():
+        if comm:
+            comm.dist.barrier()
+
+    n_local, m = args.n, args.m
+    n_total = n_local * world
     t_setup = time.time()
     eng = hb.Engine(n_local, m, device=local_rank, tile_snps=args.tile, lag_tiles=args.lag, seed=args.seed, rank=rank, world=world)
     eng.synth_geno(args.seed, row_offset=rank * n_local)
     xpx, sumx = eng.col_stats()
-    if world > 1:
-        raise NotImplementedError("multi-GPU row sharding lands with the NVLink exchange (DESIGN.md)")
-    vx = (xpx - sumx * sumx / n_local) / (n_local - 1)
-    active = (n_local * xpx != sumx * sumx)
+    xpx, sumx = allsum(xpx), allsum(sumx)
+    vx = (xpx - sumx * sumx / n_total) / (n_total - 1)
+    active = (n_total * xpx != sumx * sumx)
     eng.set_snp_info(xpx, active.astype(np.uint8))
     t_gram = time.time()
     eng.build_gram()
+    if comm:
+        ptr, cnt = eng.gram_device()
+        comm.allreduce_i32_device(ptr, cnt)
+        eng.set_peers(comm.allgather_bytes(eng.ipc_handle()))
     t_gram = time.time() - t_gram
     rng = np.random.default_rng(args.seed)
     beta = np.zeros(m)
     causal = rng.choice(m, size=min(1000, m), replace=False)
     beta[causal] = rng.standard_normal(causal.size)
     gv = eng.predict(beta)
-    gv *= math.sqrt(0.5 / gv.var())
-    y = gv + rng.normal(scale=math.sqrt(0.5), size=n_local)
-    r = y - y.mean()
+    s1 = allsum(np.array([gv.sum(), (gv * gv).sum()]))
+    gvar = s1[1] / n_total - (s1[0] / n_total) ** 2
+    gv *= math.sqrt(0.5 / gvar)
+    y = gv + np.random.default_rng(args.seed + 1 + rank).normal(scale=math.sqrt(0.5), size=n_local)
+    s2 = allsum(np.array([y.sum(), (y * y).sum()]))
+    ymean = s2[0] / n_total
+    vary = (s2[1] - n_total * ymean * ymean) / (n_total - 1)
+    r = y - ymean
     eng.set_residual(r)
-    chain = Chain(n_local, int(active.sum()), float(y.var(ddof=1)), float(vx.sum()), args.seed)
-    chain.sum_r, chain.sum_r2 = float(r.sum()), float(r @ r)
+    chain = Chain(n_total, float(vary), float(vx.sum()), args.seed)
+    s3 = allsum(np.array([r.sum(), r @ r]))
+    chain.sum_r, chain.sum_r2 = float(s3[0]), float(s3[1])
     t_setup = time.time() - t_setup
     desc = eng.describe()
 
     def step():
         so = eng.sweep(**chain.sweep_args())
-        chain.update(so)
+        s = allsum(np.array([so["sum_r"], so["sum_r2"]]))
+        chain.update(so, float(s[0]), float(s[1]))
         return so
 
+    import torch
     for _ in range(args.warmup):
         step()
-    # ---- device-timed region: K steps, inputs resident in HBM
-    dev_ms, sweep_ms, changed, rounds = [], [], [], []
+    # ---- timed region: K steps, inputs resident in HBM
+    sweep_ms, dev_ms, changed, rounds = [], [], [], []
     with ClockSampler(local_rank) as clk:
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
         for _ in range(args.steps):
             so = step()
             a, b, c = eng.last_sweep_ms()
-            dev_ms.append(a + b + c)
             sweep_ms.append(b)
+            dev_ms.append(a + b + c)
             changed.append(so["n_changed"])
             rounds.append(so["rounds"])
-    total_ms = float(sum(dev_ms))
+        torch.cuda.synchronize()
+        barrier()
+        wall = time.perf_counter() - t0
+    wall = float(np.max(allsum_max(comm, wall)))
     m_active = int(active.sum())
-    value = m_active * args.steps / (total_ms * 1e-3)
-    # ---- end-to-end region: same steps through the host-facing ABI, residual over PCIe each step
+    value = world * m_active * args.steps / wall
+    # ---- end-to-end region: same steps through the host-facing ABI, residual over PCIe in both directions
+    barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        eng.set_residual(r)                 # H2D: n doubles (what the host driver does after non-SNP effects)
+        eng.set_residual(r)                 # H2D: n doubles
         so = step()
         r = eng.get_residual()              # D2H: n doubles
         _ = eng.get_u()                     # D2H: n doubles
-    e2e_s = time.perf_counter() - t0
-    e2e = m_active * args.steps / e2e_s
+    torch.cuda.synchronize()
+    barrier()
+    e2e_s = float(np.max(allsum_max(comm, time.perf_counter() - t0)))
+    e2e = world * m_active * args.steps / e2e_s
     peak, peak_src = _peaks()
     kern_s = float(np.mean(sweep_ms)) * 1e-3
-    achieved = n_local * m / kern_s / 1e9
+    achieved = n_local * m / kern_s / 1e9   # algorithmic bytes: n per SNP update (one read of the int8 column)
+    tr = _traffic()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "ibrm() BayesR sweep, synthetic n=%d x m=%d int8 genotypes, 1 GPU" % (n_total, m),
-                   "n": n_total, "m": m, "m_active": m_active, "Pi": PI0, "fold": FOLD,
-                   "layout": desc, "l2": "inputs (%.1f GB) larger than L2" % (desc["geno_bytes"] / 1e9),
-                   "changed_snps_per_sweep": float(np.mean(changed)), "scalar_rounds_per_sweep": float(np.mean(rounds)), "setup_s": t_setup, "gram_s": t_gram,
+        "config": {"workload": "ibrm() BayesR sweep, synthetic int8 genotypes, n=%d individuals per GPU x m=%d SNPs, %d GPU(s)"
+                               % (n_local, m, world),
+                   "n_per_gpu": n_local, "n_total": n_total, "m": m, "m_active": m_active, "Pi": PI0, "fold": FOLD,
+                   "unit_of_value": "one SNP update over one rank's %d-row shard" % n_local,
+                   "layout": desc, "l2": "inputs (%.1f GB per GPU) larger than L2" % (desc["geno_bytes"] / 1e9),
+                   "changed_snps_per_sweep": float(np.mean(changed)), "scalar_rounds_per_sweep": float(np.mean(rounds)),
+                   "device_ms_per_step": float(np.mean(dev_ms)), "setup_s": t_setup, "gram_s": t_gram,
                    "frac_of_8TBps": achieved / 8000.0},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "k_sweep", "kernel_ms": kern_s * 1e3},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n_local, "d2h_bytes_per_step": 16 * n_local + 128},
-        "gpu_launches": 3 * args.steps,
+                     "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_source": (tr or {}).get("source"),
+                     "peak_source": peak_src, "kernel": "k_sweep", "kernel_ms": kern_s * 1e3,
+                     "algorithmic_bytes_per_launch": n_local * m},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n_local, "d2h_bytes_per_step": 16 * n_local + 160},
+        "gpu_launches": KERNELS_PER_STEP * args.steps,
         "clocks": clk.summary(),
     }
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        val = cpu_reference(n_total, args.m_cpu, 1, threads)
+        val = cpu_reference(n_local, args.m_cpu, 1, threads)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "n=%d x m=%d fp64 column-major, 1 warm + 1 timed sweep" % (n_total, args.m_cpu)}
+                                "sample": "n=%d x m=%d fp64 column-major (first columns of the workload), 1 warm + 1 timed sweep, "
+                                          "OpenMP ddot/daxpy" % (n_local, args.m_cpu)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     eng.close()
+    if comm:
+        comm.dist.barrier()
+        comm.dist.destroy_process_group()
+
+
+def allsum_max(comm, x):
+    """max over ranks of a host scalar"""
+    if not comm:
+        return np.array([x])
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    comm.dist.all_reduce(t, op=comm.dist.ReduceOp.MAX)
+    return t.cpu().numpy()
 
 
 def main():

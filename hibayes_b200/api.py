@@ -200,6 +200,24 @@ class Engine:
     def build_gram(self):
         _lib.check(self.L.hb_engine_build_gram(self.h))
 
+    def ipc_handle(self):
+        buf = C.create_string_buffer(64)
+        _lib.check(self.L.hb_engine_ipc_handle(self.h, buf))
+        return buf.raw
+
+    def set_peers(self, handles):
+        _lib.check(self.L.hb_engine_set_peers(self.h, C.c_char_p(handles)))
+
+    def gram_device(self):
+        ptr, cnt = C.c_void_p(), C.c_uint64()
+        _lib.check(self.L.hb_engine_gram_device(self.h, C.byref(ptr), C.byref(cnt)))
+        return ptr.value, cnt.value
+
+    def u_centered_sums(self, mean):
+        a, b = C.c_double(), C.c_double()
+        _lib.check(self.L.hb_engine_u_centered_sums(self.h, mean, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def get_gram(self):
         d = self.describe()
         B, D = d["tile_snps"], d["lag_tiles"]
