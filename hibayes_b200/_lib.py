@@ -19,7 +19,27 @@ SYMBOLS = [
     "hb_engine_get_pip_counts", "hb_engine_accumulate_effects", "hb_engine_get_effect_sums", "hb_engine_predict",
     "hb_engine_last_sweep_ms", "hb_engine_describe", "hb_bayes",
     "hb_engine_ipc_handle", "hb_engine_set_peers", "hb_engine_gram_device", "hb_engine_u_centered_sums",
+    "hb_ld_engine_create", "hb_ld_engine_destroy", "hb_ld_engine_load_dense", "hb_ld_engine_set_state",
+    "hb_ld_engine_set_vargL", "hb_ld_engine_get", "hb_ld_engine_sweep", "hb_sbayesd",
 ]
+
+
+class SBayesArgs(C.Structure):
+    _fields_ = [("m", C.c_int), ("sumstat", C.c_void_p), ("ldm", C.c_void_p), ("model", C.c_char_p), ("n_fold", C.c_int),
+                ("Pi", C.c_void_p), ("fold", C.c_void_p), ("niter", C.c_int), ("nburn", C.c_int), ("thin", C.c_int),
+                ("vg", C.c_double), ("dfvg", C.c_double), ("s2vg", C.c_double), ("ve", C.c_double), ("dfve", C.c_double),
+                ("s2ve", C.c_double), ("windindx", C.c_void_p), ("outfreq", C.c_int), ("verbose", C.c_int),
+                ("seed", C.c_uint64), ("device", C.c_int)]
+
+
+class SBayesOut(C.Structure):
+    _fields_ = [("Vg", C.c_double), ("Ve", C.c_double), ("h2", C.c_double), ("alpha", C.c_void_p), ("pi", C.c_void_p),
+                ("pip", C.c_void_p), ("gwas", C.c_void_p), ("vara_store", C.c_void_p), ("vare_store", C.c_void_p),
+                ("hsq_store", C.c_void_p), ("pi_store", C.c_void_p), ("alpha_store", C.c_void_p),
+                ("tracker_final", C.c_void_p), ("nzrate_count", C.c_void_p), ("wppa_count", C.c_void_p),
+                ("nnz_trace", C.c_void_p), ("vara_trace", C.c_void_p), ("vare_trace", C.c_void_p), ("varg_trace", C.c_void_p),
+                ("r_hat_final", C.c_void_p), ("n_records_done", C.c_int), ("nzct", C.c_int), ("iters_done", C.c_int),
+                ("n_used", C.c_int), ("seconds_sweep", C.c_double)]
 
 ALLREDUCE_F64 = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_size_t)
 ALLREDUCE_I32_DEV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
@@ -120,6 +140,7 @@ def load_library():
     L.hb_engine_describe.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.hb_bayes.argtypes = [C.POINTER(BayesArgs), C.POINTER(BayesOut)]
+    L.hb_sbayesd.argtypes = [C.POINTER(SBayesArgs), C.POINTER(SBayesOut)]
     L.hb_engine_ipc_handle.argtypes = [C.c_void_p, C.c_void_p]
     L.hb_engine_set_peers.argtypes = [C.c_void_p, C.c_void_p]
     L.hb_engine_gram_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]

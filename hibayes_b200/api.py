@@ -147,6 +147,55 @@ def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, nite
     return res
 
 
+def SBayesD(sumstat, ldm, model, Pi, niter=50000, nburn=20000, thin=5, fold=None, windindx=None, vg=None, dfvg=None,
+            s2vg=None, ve=None, dfve=None, s2ve=None, outfreq=100, threads=0, verbose=False, seed=666666, device=0):
+    """GPU twin of hibayes' SBayesD() (/root/reference/src/SBayesD.cpp:5-24; what sbrm() calls at R/sbayes.r:215 for a
+    dense LD matrix).  sumstat: m x 4 (MAF, BETA, SE, N = columns 4,5,6,8 of the COJO file, R/sbayes.r:209), NaN = NA;
+    ldm: m x m.  Returns a dict named like the Rcpp::List (:532-578)."""
+    L = _lib.load_library()
+    ss = np.asfortranarray(sumstat, dtype=np.float64)
+    ld = np.asfortranarray(ldm, dtype=np.float64)
+    if ss.shape[0] != ld.shape[0]:
+        raise RuntimeError("Number of SNPs not equals.")  # SBayesD.cpp:29-31
+    m = ld.shape[0]
+    Pi = np.ascontiguousarray(Pi, dtype=np.float64)
+    F = Pi.shape[0]
+    fo = None if fold is None else np.ascontiguousarray(fold, dtype=np.float64)
+    if fo is not None and fo.shape[0] != F:
+        raise RuntimeError("length of Pi and fold not equals.")
+    a = _lib.SBayesArgs()
+    a.m, a.sumstat, a.ldm, a.model, a.n_fold, a.Pi, a.fold = m, ss.ctypes.data, ld.ctypes.data, model.encode(), F, Pi.ctypes.data, _ptr(fo)
+    a.niter, a.nburn, a.thin = niter, nburn, thin
+    a.vg, a.dfvg, a.s2vg, a.ve, a.dfve, a.s2ve = _nan(vg), _nan(dfvg), _nan(s2vg), _nan(ve), _nan(dfve), _nan(s2ve)
+    nw, w = 0, None
+    if windindx is not None:
+        w = np.ascontiguousarray(windindx, dtype=np.int32)
+        nw = int(w.max())
+        a.windindx = w.ctypes.data
+    a.outfreq, a.verbose, a.seed, a.device = outfreq, int(bool(verbose)), seed, device
+    o = _lib.SBayesOut()
+    nrec = max((niter - nburn) // thin, 0)
+    res = {"alpha": np.zeros(m), "pi": np.zeros(F), "pip": np.zeros(m), "gwas": np.zeros(nw)}
+    mc = {"Vg": np.zeros(nrec), "Ve": np.zeros(nrec), "h2": np.zeros(nrec), "pi": np.zeros((F, nrec), order="F")}
+    dg = {"tracker": np.zeros(m, dtype=np.int32), "nzrate_count": np.zeros(m), "wppa_count": np.zeros(nw),
+          "nnz_trace": np.zeros(niter, dtype=np.int32), "vara_trace": np.zeros(niter), "vare_trace": np.zeros(niter),
+          "varg_trace": np.zeros(niter), "r_hat": np.zeros(m)}
+    o.alpha, o.pi, o.pip = _ptr(res["alpha"]), _ptr(res["pi"]), _ptr(res["pip"])
+    o.gwas = _ptr(res["gwas"]) if nw else None
+    o.vara_store, o.vare_store, o.hsq_store, o.pi_store = _ptr(mc["Vg"]), _ptr(mc["Ve"]), _ptr(mc["h2"]), _ptr(mc["pi"])
+    o.tracker_final, o.nzrate_count = _ptr(dg["tracker"]), _ptr(dg["nzrate_count"])
+    o.wppa_count = _ptr(dg["wppa_count"]) if nw else None
+    o.nnz_trace, o.vara_trace, o.vare_trace, o.varg_trace = (_ptr(dg["nnz_trace"]), _ptr(dg["vara_trace"]),
+                                                             _ptr(dg["vare_trace"]), _ptr(dg["varg_trace"]))
+    o.r_hat_final = _ptr(dg["r_hat"])
+    _lib.check(L.hb_sbayesd(C.byref(a), C.byref(o)))
+    res.update({"Vg": o.Vg, "Ve": o.Ve, "h2": o.h2, "MCMCsamples": mc})
+    dg.update({"n_records": o.n_records_done, "nzct": o.nzct, "iters_done": o.iters_done, "n_used": o.n_used,
+               "seconds_sweep": o.seconds_sweep})
+    res["diag"] = dg
+    return res
+
+
 class Engine:
     """Thin handle on hb_engine_* (one per GPU)."""
 

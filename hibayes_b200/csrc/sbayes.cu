@@ -1,0 +1,371 @@
+// sbayes.cu -- device engine for the dense-LD summary-statistics sweep of SBayesD()
+// (/root/reference/src/SBayesD.cpp:253-456).
+//
+// The reference walks the SNPs in order: rhs = r_hat[i] (+ xpx_i g_i), the same conditional draw as Bayes(), and,
+// only if the effect changed, r_hat += (g_old - g_new) * n * LD[:, i] (a length-m daxpy on column i, :351-356).
+// Here one cooperative launch does a whole sweep, tile by tile (B = 256 SNPs):
+//   phase A (CTA 0)   the tile's decisions.  The dependence of r_hat[i] on the earlier changes of the same tile is
+//                     n * LD[i, c] -- the LD block itself plays the role the Gram block plays in the genotype sweep
+//                     (hb_sweep.cuh): classes are speculated, the changed SNPs are chained by one warp in SNP order,
+//                     every SNP is re-evaluated with its exact right-hand side, a mismatch restarts the round.
+//   phase B (all CTAs) the column updates of the tile's changed SNPs, applied to every row of r_hat in SNP order
+//                     (coalesced over rows; deterministic).
+// Two grid barriers per tile.  This is the first correct path for this row of SURVEY.md 8(a14): HBM traffic is the
+// columns of the changed SNPs (m * 8 bytes each), the decisions of a tile are not yet overlapped with the updates
+// of the previous one.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/hibayes_b200.h"
+#include "hb_rng.h"
+
+namespace cg = cooperative_groups;
+int hb_set_error(const char* fmt, ...);
+#define CU(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return hb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                          cudaGetErrorString(_e));                                           \
+  } while (0)
+
+constexpr int LB = 256;   // SNPs per tile = threads per CTA
+
+struct LdOutDev {
+  double count[HB_MAX_FOLD];
+  double varg_acc, sum_vargL, d_minus, d_plus;
+  int n_changed, rounds;
+};
+
+struct LdParams {
+  const double* ldm;
+  int m;
+  double nscale;
+  double *r_hat, *g, *vargL;
+  const double *xpx, *xy;
+  const uint8_t* ifest;
+  int32_t* tracker;
+  int iter, model, F;
+  double logpi[HB_MAX_FOLD], vara_fold[HB_MAX_FOLD], fold[HB_MAX_FOLD];
+  double vare, dfvara, s2varg, lambda, lambda2;
+  hb_key_t key;
+  int* q_idx;      // [LB] global SNP index of the tile's changed SNPs
+  double* q_dn;    // [LB] (g_old - g_new) * n
+  int* q_cnt;
+  LdOutDev* out;
+};
+
+// cumulative class probabilities (soft-max form of SBayesD.cpp:403-415) and the inverse-CDF class (:419-425)
+__device__ __forceinline__ int ld_class(int nf, double rr, const double* a, const double* c, double logpi0, double u) {
+  double sv[HB_MAX_FOLD];
+  sv[0] = logpi0;
+  double smax = logpi0;
+  for (int k = 1; k < nf; ++k) { sv[k] = fma(rr, c[k], a[k]); smax = fmax(smax, sv[k]); }
+  double tot = 0.0;
+  for (int k = 0; k < nf; ++k) { sv[k] = exp(sv[k] - smax); tot += sv[k]; }
+  const double inv = 1.0 / tot;
+  double acc = 0.0;
+  for (int k = 0; k < nf; ++k) { acc = fma(sv[k], inv, acc); if (u < acc) return k; }
+  return 0;
+}
+
+__device__ double block_sum_256(double v, double* sh) {
+  const int tid = threadIdx.x;
+  sh[tid] = v;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) sh[tid] += sh[tid + o];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParams p) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double c_rhs0[LB], c_iv[LB], c_sdz[LB], c_gold[LB], c_delta[LB], c_gnew[LB], red[LB];
+  __shared__ int c_idx[LB], c_cls[LB], wcnt[LB / 32], s_flag;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = p.m, model = p.model, F = p.F;
+  const bool dense = (model == HB_MODEL_RR || model == HB_MODEL_A || model == HB_MODEL_L);
+  const int nf = (model == HB_MODEL_R) ? F : 2;
+  const int T = (m + LB - 1) / LB;
+  const double nscale = p.nscale, vare = p.vare;
+  int rounds = 0, changed = 0;
+  for (int t = 0; t < T; ++t) {
+    if (blockIdx.x == 0) {
+      // ---------------- phase A: the tile's decisions
+      const int j = t * LB + tid;
+      const bool act = j < m && p.ifest[j];
+      double xx = 0, gold = 0, rbase = 0, uu = 0.5, zz = 0;
+      double a[HB_MAX_FOLD], c[HB_MAX_FOLD], iv[HB_MAX_FOLD], sdz[HB_MAX_FOLD];
+      for (int k = 0; k < HB_MAX_FOLD; ++k) { a[k] = 0; c[k] = 0; iv[k] = 0; sdz[k] = 0; }
+      if (act) {
+        xx = p.xpx[j];
+        gold = p.g[j];
+        rbase = __ldcg(p.r_hat + j);
+        if (gold != 0.0) rbase += xx * gold;   // :334-335 (every model)
+        hb_draw_uz(p.key, HB_DOM_SNP, (uint32_t)p.iter, (uint32_t)j, HB_SL_MAIN, 0, &uu, &zz);
+        if (model == HB_MODEL_R) {
+          for (int k = 1; k < F; ++k) {
+            const double vf = p.vara_fold[k], v = xx + vare / vf;
+            a[k] = -0.5 * log(vf * (xx / vare) + 1.0) + p.logpi[k];
+            c[k] = 0.5 / (vare * v);
+            iv[k] = 1.0 / v;
+            sdz[k] = sqrt(vare / v) * zz;
+          }
+        } else {
+          double varg = p.vara_fold[1];
+          if (model == HB_MODEL_A || model == HB_MODEL_B)   // :277, :298
+            varg = (gold * gold + p.s2varg * p.dfvara) /
+                   hb_draw_chisq(p.key, HB_DOM_SNP, (uint32_t)p.iter, (uint32_t)j, HB_SL_CHI, p.dfvara + 1.0);
+          const double v = (model == HB_MODEL_L) ? (xx + 1.0 / p.vargL[j]) : (xx + vare / varg);
+          if (model == HB_MODEL_B || model == HB_MODEL_C) a[1] = -0.5 * log(varg * (xx / vare) + 1.0) + p.logpi[1];
+          c[1] = 0.5 / (vare * v);
+          iv[1] = 1.0 / v;
+          sdz[1] = sqrt(vare / v) * zz;
+        }
+      }
+      auto classify = [&](double rhs) -> int { return dense ? 1 : ld_class(nf, rhs * rhs, a, c, p.logpi[0], uu); };
+      int cls = act ? classify(rbase) : 0;
+      int k = 0, myrank = 0;
+      bool cand = false;
+      double gnew = gold;
+      for (;;) {
+        ++rounds;
+        // candidate list of the current classes
+        cand = act && (dense || cls > 0 || gold != 0.0);
+        const unsigned bal = __ballot_sync(0xffffffffu, cand);
+        if (lane == 0) wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int pre = 0;
+        k = 0;
+        for (int w = 0; w < LB / 32; ++w) { if (w < warp) pre += wcnt[w]; k += wcnt[w]; }
+        myrank = pre + __popc(bal & ((1u << lane) - 1u));
+        if (cand) {
+          c_idx[myrank] = j; c_gold[myrank] = gold; c_cls[myrank] = cls;
+          c_iv[myrank] = iv[cls]; c_sdz[myrank] = sdz[cls]; c_rhs0[myrank] = rbase;
+        }
+        __syncthreads();
+        // chain of the candidates in SNP order (one warp): rhs_s = rhs0_s - sum_{s' < s} n LD[c_s, c_s'] delta_s'
+        if (warp == 0) {
+          for (int sb = 0; sb < k; sb += 32) {
+            const int sidx = sb + lane;
+            const bool valid = sidx < k;
+            const int ji = valid ? c_idx[sidx] : 0;
+            double rhs = valid ? c_rhs0[sidx] : 0.0;
+            const double siv = valid ? c_iv[sidx] : 0.0, ssdz = valid ? c_sdz[sidx] : 0.0, sgold = valid ? c_gold[sidx] : 0.0;
+            const int scls = valid ? c_cls[sidx] : 0;
+            for (int sp = 0; sp < sb; ++sp)
+              if (valid) rhs = fma(-(nscale * p.ldm[(size_t)c_idx[sp] * m + ji]), c_delta[sp], rhs);
+            const int nl = min(32, k - sb);
+            double mydelta = 0.0, mygnew = sgold;
+            for (int lp = 0; lp < nl; ++lp) {
+              double gn = (scls > 0) ? fma(rhs, siv, ssdz) : 0.0;
+              if (model == HB_MODEL_L && fabs(gn) < 1e-6) gn = 1e-6;   // :373
+              const double dl = gn - sgold;
+              const double d = __shfl_sync(0xffffffffu, dl, lp);
+              const int jc = __shfl_sync(0xffffffffu, ji, lp);
+              if (lane == lp) { mydelta = dl; mygnew = gn; }
+              if (valid && lane > lp) rhs = fma(-(nscale * p.ldm[(size_t)jc * m + ji]), d, rhs);
+            }
+            if (valid) { c_delta[sidx] = mydelta; c_gnew[sidx] = mygnew; }
+            __syncwarp();
+          }
+        }
+        __syncthreads();
+        // exact right-hand side of every SNP of the tile and its class
+        double rhs = rbase;
+        if (act)
+          for (int s = 0; s < myrank; ++s) rhs = fma(-(nscale * p.ldm[(size_t)c_idx[s] * m + j]), c_delta[s], rhs);
+        const int cls2 = act ? classify(rhs) : 0;
+        if (tid == 0) s_flag = 0;
+        __syncthreads();
+        if (act && cls2 != cls) s_flag = 1;
+        __syncthreads();
+        const bool redo = s_flag != 0;
+        __syncthreads();
+        cls = cls2;
+        if (!redo) break;
+      }
+      // commit the tile
+      if (cand) gnew = c_gnew[myrank];
+      if (act) {
+        p.g[j] = gnew;
+        p.tracker[j] = cls;
+        if (model == HB_MODEL_L) {   // :374-375
+          double u2, z2;
+          hb_draw_uz(p.key, HB_DOM_SNP, (uint32_t)p.iter, (uint32_t)j, HB_SL_IG, 0, &u2, &z2);
+          const double vargi = 1.0 / hb_invgauss_from_uz(sqrt(vare) * p.lambda / fabs(gnew), p.lambda2, u2, z2);
+          if (vargi > 0) p.vargL[j] = vargi;
+        }
+      }
+      // the reference updates r_hat only when the effect changed (:351; models 1 and 2 always, :263, :284)
+      const bool upd = cand && (model == HB_MODEL_RR || model == HB_MODEL_A || gnew != gold);
+      const unsigned balu = __ballot_sync(0xffffffffu, upd);
+      if (lane == 0) wcnt[warp] = __popc(balu);
+      __syncthreads();
+      int pre = 0, ku = 0;
+      for (int w = 0; w < LB / 32; ++w) { if (w < warp) pre += wcnt[w]; ku += wcnt[w]; }
+      if (upd) {
+        const int r = pre + __popc(balu & ((1u << lane) - 1u));
+        p.q_idx[r] = j;
+        p.q_dn[r] = (gold - gnew) * nscale;   // gi_ = (g[i] - gi) * n
+      }
+      if (tid == 0) *p.q_cnt = ku;
+      changed += ku;
+      __threadfence();
+    }
+    grid.sync();
+    // ---------------- phase B: r_hat += sum_s dn_s * LD[:, c_s], columns in SNP order
+    {
+      const int ku = *(volatile int*)p.q_cnt;
+      for (int row = blockIdx.x * LB + tid; row < m; row += gridDim.x * LB) {
+        double acc = __ldcg(p.r_hat + row);
+        for (int s = 0; s < ku; ++s) acc = fma(__ldcg(p.q_dn + s), p.ldm[(size_t)__ldcg(p.q_idx + s) * m + row], acc);
+        p.r_hat[row] = acc;
+      }
+    }
+    grid.sync();
+  }
+  // ---------------- end of the sweep: the sums the host needs (:269, :353, :445-447, :460-467)
+  if (blockIdx.x == 0) {
+    double cnt[HB_MAX_FOLD], vacc = 0, sl = 0, dm = 0, dp = 0;
+    for (int k = 0; k < HB_MAX_FOLD; ++k) cnt[k] = 0;
+    for (int j = tid; j < m; j += LB) {
+      const double gj = p.g[j], xyj = p.xy[j], rh = __ldcg(p.r_hat + j);
+      dm += gj * (xyj - rh);
+      dp += gj * (xyj + rh);
+      if (model == HB_MODEL_L) sl += p.vargL[j];
+      if (model == HB_MODEL_RR) vacc += gj * gj;
+      if (p.ifest[j] && !dense) {
+        const int cl = p.tracker[j];
+        for (int k = 0; k < HB_MAX_FOLD; ++k) if (k == cl) cnt[k] += 1.0;
+        if (cl > 0) vacc += (model == HB_MODEL_R) ? gj * gj / p.fold[cl] : gj * gj;
+      }
+    }
+    for (int k = 0; k < HB_MAX_FOLD; ++k) { const double v = block_sum_256(cnt[k], red); if (tid == 0) p.out->count[k] = v; }
+    vacc = block_sum_256(vacc, red); sl = block_sum_256(sl, red); dm = block_sum_256(dm, red); dp = block_sum_256(dp, red);
+    if (tid == 0) {
+      p.out->varg_acc = vacc; p.out->sum_vargL = sl; p.out->d_minus = dm; p.out->d_plus = dp;
+      p.out->n_changed = changed; p.out->rounds = rounds;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+struct hb_ld_engine {
+  int device = 0, m = 0, grid = 1;
+  uint64_t seed = 0;
+  double *ldm = nullptr, *r_hat = nullptr, *g = nullptr, *vargL = nullptr, *xpx = nullptr, *xy = nullptr, *q_dn = nullptr;
+  uint8_t* ifest = nullptr;
+  int32_t* tracker = nullptr;
+  int *q_idx = nullptr, *q_cnt = nullptr;
+  LdOutDev* out = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  float ms_sweep = 0;
+  bool ld_ready = false, state_ready = false;
+};
+
+extern "C" int hb_ld_engine_create(int device, int m, uint64_t seed, hb_ld_engine** out) {
+  if (!out || m <= 0) return hb_set_error("hb_ld_engine_create: bad argument");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return hb_set_error("hb_ld_engine_create: CUDA device %d not available (%d visible) -- no CPU fallback", device, ndev);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  hb_ld_engine* e = new hb_ld_engine();
+  e->device = device; e->m = m; e->seed = seed;
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ld_sweep, LB, 0));
+  e->grid = std::max(1, std::min(prop.multiProcessorCount * std::max(1, per_sm), (m + LB - 1) / LB));
+  CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&e->ev[0])); CU(cudaEventCreate(&e->ev[1]));
+  const size_t mm = (size_t)m;
+  CU(cudaMalloc(&e->ldm, mm * mm * 8));
+  CU(cudaMalloc(&e->r_hat, mm * 8)); CU(cudaMalloc(&e->g, mm * 8)); CU(cudaMalloc(&e->vargL, mm * 8));
+  CU(cudaMalloc(&e->xpx, mm * 8)); CU(cudaMalloc(&e->xy, mm * 8)); CU(cudaMalloc(&e->ifest, mm));
+  CU(cudaMalloc(&e->tracker, mm * 4)); CU(cudaMalloc(&e->q_idx, LB * 4)); CU(cudaMalloc(&e->q_dn, LB * 8));
+  CU(cudaMalloc(&e->q_cnt, 4)); CU(cudaMalloc(&e->out, sizeof(LdOutDev)));
+  CU(cudaMemsetAsync(e->g, 0, mm * 8, e->stream)); CU(cudaMemsetAsync(e->tracker, 0, mm * 4, e->stream));
+  CU(cudaMemsetAsync(e->vargL, 0, mm * 8, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  *out = e;
+  return 0;
+}
+extern "C" void hb_ld_engine_destroy(hb_ld_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaFree(e->ldm); cudaFree(e->r_hat); cudaFree(e->g); cudaFree(e->vargL); cudaFree(e->xpx); cudaFree(e->xy);
+  cudaFree(e->ifest); cudaFree(e->tracker); cudaFree(e->q_idx); cudaFree(e->q_dn); cudaFree(e->q_cnt); cudaFree(e->out);
+  if (e->ev[0]) cudaEventDestroy(e->ev[0]);
+  if (e->ev[1]) cudaEventDestroy(e->ev[1]);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+extern "C" int hb_ld_engine_load_dense(hb_ld_engine* e, const double* ldm) {
+  if (!e || !ldm) return hb_set_error("hb_ld_engine_load_dense: null argument");
+  CU(cudaSetDevice(e->device));
+  CU(cudaMemcpy(e->ldm, ldm, (size_t)e->m * e->m * 8, cudaMemcpyHostToDevice));
+  e->ld_ready = true;
+  return 0;
+}
+extern "C" int hb_ld_engine_set_state(hb_ld_engine* e, const double* xpx, const uint8_t* ifest, const double* xy, const double* r_hat) {
+  if (!e || !xpx || !ifest || !xy || !r_hat) return hb_set_error("hb_ld_engine_set_state: null argument");
+  CU(cudaSetDevice(e->device));
+  const size_t mm = (size_t)e->m;
+  CU(cudaMemcpy(e->xpx, xpx, mm * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(e->ifest, ifest, mm, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(e->xy, xy, mm * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(e->r_hat, r_hat, mm * 8, cudaMemcpyHostToDevice));
+  e->state_ready = true;
+  return 0;
+}
+extern "C" int hb_ld_engine_set_vargL(hb_ld_engine* e, const double* v) {
+  if (!e || !v) return hb_set_error("null argument");
+  CU(cudaSetDevice(e->device));
+  CU(cudaMemcpy(e->vargL, v, (size_t)e->m * 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+extern "C" int hb_ld_engine_get(hb_ld_engine* e, double* g, int32_t* tracker, double* r_hat) {
+  if (!e) return hb_set_error("null engine");
+  CU(cudaSetDevice(e->device));
+  if (g) CU(cudaMemcpy(g, e->g, (size_t)e->m * 8, cudaMemcpyDeviceToHost));
+  if (tracker) CU(cudaMemcpy(tracker, e->tracker, (size_t)e->m * 4, cudaMemcpyDeviceToHost));
+  if (r_hat) CU(cudaMemcpy(r_hat, e->r_hat, (size_t)e->m * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int hb_ld_engine_sweep(hb_ld_engine* e, const hb_ld_sweep_in* in, hb_ld_sweep_out* out) {
+  if (!e || !in || !out) return hb_set_error("hb_ld_engine_sweep: null argument");
+  if (!e->ld_ready || !e->state_ready) return hb_set_error("hb_ld_engine_sweep: LD matrix or state not loaded");
+  if (in->model_index < 1 || in->model_index > 6 || in->n_fold < 2 || in->n_fold > HB_MAX_FOLD) return hb_set_error("hb_ld_engine_sweep: bad model or n_fold");
+  CU(cudaSetDevice(e->device));
+  LdParams p;
+  memset(&p, 0, sizeof p);
+  p.ldm = e->ldm; p.m = e->m; p.nscale = in->nscale; p.r_hat = e->r_hat; p.g = e->g; p.vargL = e->vargL; p.xpx = e->xpx;
+  p.xy = e->xy; p.ifest = e->ifest; p.tracker = e->tracker; p.iter = in->iter; p.model = in->model_index; p.F = in->n_fold;
+  for (int k = 0; k < HB_MAX_FOLD; ++k) { p.logpi[k] = in->logpi[k]; p.vara_fold[k] = in->vara_fold[k]; p.fold[k] = in->fold[k]; }
+  p.vare = in->vare; p.dfvara = in->dfvara; p.s2varg = in->s2varg; p.lambda = in->lambda; p.lambda2 = in->lambda2;
+  p.key = hb_make_key(e->seed); p.q_idx = e->q_idx; p.q_dn = e->q_dn; p.q_cnt = e->q_cnt; p.out = e->out;
+  void* args[] = {(void*)&p};
+  CU(cudaEventRecord(e->ev[0], e->stream));
+  CU(cudaLaunchCooperativeKernel((const void*)k_ld_sweep, dim3(e->grid), dim3(LB), args, 0, e->stream));
+  CU(cudaEventRecord(e->ev[1], e->stream));
+  LdOutDev h;
+  CU(cudaMemcpyAsync(&h, e->out, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaEventElapsedTime(&e->ms_sweep, e->ev[0], e->ev[1]));
+  for (int k = 0; k < HB_MAX_FOLD; ++k) out->count[k] = h.count[k];
+  out->varg_acc = h.varg_acc; out->sum_vargL = h.sum_vargL; out->g_xy_minus_rhat = h.d_minus; out->g_xy_plus_rhat = h.d_plus;
+  out->n_changed = h.n_changed; out->status = 0; out->rounds = h.rounds; out->sweep_ms = e->ms_sweep;
+  return 0;
+}

@@ -198,6 +198,64 @@ typedef struct {
 
 int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o);
 
+/* ------------------------------------------------------------------ SBayesD (dense LD, summary statistics) */
+/* Device engine for the LD-column sweep of SBayesD(), /root/reference/src/SBayesD.cpp:253-456: r_hat lives on the
+ * device, one hb_ld_engine_sweep() per MCMC iteration replaces the switch(model_index) block and returns the sums
+ * the host needs for the variance draws (:460-467). */
+typedef struct hb_ld_engine hb_ld_engine;
+int hb_ld_engine_create(int device, int m, uint64_t seed, hb_ld_engine** out);
+void hb_ld_engine_destroy(hb_ld_engine* e);
+int hb_ld_engine_load_dense(hb_ld_engine* e, const double* ldm);   /* m x m column-major (arma::mat ldm, :7) */
+/* xpx_j = n * LD_jj (:93-96), ifest (:100-103), xy (:104), initial r_hat (:105) */
+int hb_ld_engine_set_state(hb_ld_engine* e, const double* xpx, const uint8_t* ifest, const double* xy, const double* r_hat);
+int hb_ld_engine_set_vargL(hb_ld_engine* e, const double* vargL);
+int hb_ld_engine_get(hb_ld_engine* e, double* g, int32_t* tracker, double* r_hat);   /* any of them may be NULL */
+
+typedef struct {
+  int iter, model_index, n_fold;
+  double fold[HB_MAX_FOLD], logpi[HB_MAX_FOLD], vara_fold[HB_MAX_FOLD];   /* as hb_sweep_in */
+  double vare, dfvara, s2varg, lambda, lambda2;
+  double nscale;               /* n = int(mean(N)), :34 */
+} hb_ld_sweep_in;
+typedef struct {
+  double count[HB_MAX_FOLD];   /* estimated SNPs per class */
+  double varg_acc;             /* model 1: g'g (:269); 4: sum g^2 (:345); 6: sum g^2/fold (:432) */
+  double sum_vargL;            /* model 5 (:386) */
+  double g_xy_minus_rhat;      /* g'(xy - r_hat), :460 */
+  double g_xy_plus_rhat;       /* g'(xy + r_hat), :466 */
+  int n_changed, status, rounds, reserved;
+  float sweep_ms;              /* device time of the sweep kernel */
+} hb_ld_sweep_out;
+int hb_ld_engine_sweep(hb_ld_engine* e, const hb_ld_sweep_in* in, hb_ld_sweep_out* out);
+
+/* Host driver: drop-in for the body of  Rcpp::List SBayesD(...)  (SBayesD.cpp:5-24 signature, :532-578 return list). */
+typedef struct {
+  int m;
+  const double* sumstat;    /* m x 4 column-major: MAF, BETA, SE, N (R/sbayes.r:209); NaN = NA */
+  const double* ldm;        /* m x m column-major */
+  const char* model;
+  int n_fold;
+  const double* Pi;
+  const double* fold;       /* NULL = R_NilValue */
+  int niter, nburn, thin;
+  double vg, dfvg, s2vg, ve, dfve, s2ve;   /* NaN = R_NilValue */
+  const int32_t* windindx;  /* m, 1-based, or NULL */
+  int outfreq, verbose;
+  uint64_t seed;
+  int device;
+} hb_sbayes_args;
+typedef struct {
+  double Vg, Ve, h2;
+  double* alpha; double* pi; double* pip; double* gwas;
+  double* vara_store; double* vare_store; double* hsq_store; double* pi_store; double* alpha_store;
+  int32_t* tracker_final; double* nzrate_count; double* wppa_count;
+  int32_t* nnz_trace; double* vara_trace; double* vare_trace; double* varg_trace;
+  double* r_hat_final;
+  int n_records_done, nzct, iters_done, n_used;
+  double seconds_sweep;
+} hb_sbayes_out;
+int hb_sbayesd(const hb_sbayes_args* a, hb_sbayes_out* o);
+
 #ifdef __cplusplus
 }
 #endif

@@ -805,3 +805,302 @@ double hbo_time_sweep_fp64(int n, int m_cpu, int sweeps, int threads, uint64_t s
   free(X); free(yadj); free(u); free(g); free(xpx);
   return (double)updates / t_total;
 }
+
+/* ============================================================================================
+ * SBayesD -- literal restatement of /root/reference/src/SBayesD.cpp:5-609 (dense LD matrix).
+ * Same random-number addresses as hbo_bayes (hb_rng.h); per-iteration extras: HB_IT_VARA for the
+ * genetic variance (:461) and HB_IT_VARE for the residual variance (:467).
+ * ============================================================================================ */
+#define HB_ORACLE_MAX_FOLD 16
+int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o) {
+  if (!a || !o) return fail("null argument");
+  KEY = hb_make_key(a->seed);
+  const int m = a->m;
+  const char* model = a->model;
+  /* :28 (no BSLMM here) */
+  const int model_index = !strcmp(model, "BayesRR") ? 1 : !strcmp(model, "BayesA") ? 2 :
+                          (!strcmp(model, "BayesB") || !strcmp(model, "BayesBpi")) ? 3 :
+                          (!strcmp(model, "BayesC") || !strcmp(model, "BayesCpi")) ? 4 : !strcmp(model, "BayesL") ? 5 : 6;
+  const double* ss = a->sumstat;
+#define SS(k, c) ss[(size_t)(c) * m + (k)]
+  /* :33-34  int n = mean(finite N) */
+  int n;
+  { double acc = 0.0; int cnt = 0;
+    for (int k = 0; k < m; ++k) if (isfinite(SS(k, 3))) { acc += SS(k, 3); cnt++; }
+    if (!cnt) return fail("Lack of SE.");
+    n = (int)(acc / cnt); }
+  int fixpi = (!strcmp(model, "BayesB") || !strcmp(model, "BayesC"));
+  const int n_fold = a->n_fold;
+  if (n_fold < 2) return fail("Pi should be a vector.");
+  if (acc_sum(a->Pi, n_fold) != 1) return fail("sum of Pi should be 1.");
+  if (a->Pi[0] == 1) return fail("all markers have no effect size.");
+  for (int i = 0; i < n_fold; ++i)
+    if (a->Pi[i] < 0 || a->Pi[i] > 1) return fail("elements of Pi should be at the range of [0, 1]");
+  double Pi[HB_ORACLE_MAX_FOLD], fold_[HB_ORACLE_MAX_FOLD];
+  if (n_fold > HB_ORACLE_MAX_FOLD) return fail("too many mixture components");
+  for (int i = 0; i < n_fold; ++i) { Pi[i] = a->Pi[i]; fold_[i] = a->fold ? a->fold[i] : 0.0; }
+  if (!a->fold) {
+    if (!strcmp(model, "BayesR")) return fail("'fold' should be provided for BayesR model.");
+    if (n_fold != 2) return fail("length of Pi and fold not equals.");
+  }
+  const int niter = a->niter, nburn = a->nburn, thin = a->thin;
+  const int n_records = (niter - nburn) / thin;
+  int count = 0, nzct = 0, NnzSnp = 0, have_tracker = 0;
+  if (!strcmp(model, "BayesRR") || !strcmp(model, "BayesA") || !strcmp(model, "BayesL")) {
+    NnzSnp = m; Pi[0] = 0; Pi[1] = 1; fixpi = 1;
+  } else {
+    if (strcmp(model, "BayesR") && n_fold != 2)
+      return fail("length of Pi should be 2, the first value is the proportion of non-effect markers.");
+    have_tracker = 1;
+  }
+  double* xy = calloc(m, 8); double* r_hat = calloc(m, 8); double* tmp = calloc(m, 8); double* yyi = calloc(m, 8);
+  double* g = calloc(m, 8); double* xpx = calloc(m, 8); double* vx = calloc(m, 8); double* snptracker = calloc(m, 8);
+  double* nzrate = calloc(m, 8); double* gsum = calloc(m, 8); double* vargL = calloc(m, 8);
+  uint8_t* ifest = malloc(m);
+  const double* ldm = a->ldm;
+  for (int i = 0; i < m; ++i) { vx[i] = ldm[(size_t)i * m + i]; xpx[i] = vx[i] * n; }   /* :92-96 */
+  int count_y = 0, nvar0 = 0;
+  for (int k = 0; k < m; ++k) {   /* :100-112 */
+    ifest[k] = 1;
+    if (isnan(SS(k, 1)) || isnan(SS(k, 2)) || isnan(SS(k, 3))) { ifest[k] = 0; nvar0++; }
+    else {
+      xy[k] = xpx[k] * SS(k, 1);
+      r_hat[k] = xy[k];
+      yyi[k] = xpx[k] * (SS(k, 1) * SS(k, 1) + (SS(k, 3) - 2) * SS(k, 2) * SS(k, 2));
+      count_y++;
+    }
+  }
+  if (count_y == 0) return fail("Lack of SE.");
+  const double yy = acc_sum(yyi, m) / count_y;
+  const double vary = yy / (n - 1);
+  const double h2 = 0.5;
+  const double dfvara_ = isnan(a->dfvg) ? 4 : a->dfvg;
+  if (dfvara_ <= 2) return fail("dfvg should not be less than 2.");
+  double vara_ = isnan(a->vg) ? ((dfvara_ - 2) / dfvara_) * vary * h2 : a->vg;
+  double vare_ = isnan(a->ve) ? vary * (1 - h2) : a->ve;
+  const double dfvare_ = isnan(a->dfve) ? -2 : a->dfve;
+  const double s2vara_ = isnan(a->s2vg) ? vara_ * (dfvara_ - 2) / dfvara_ : a->s2vg;
+  const double sumvx = acc_sum(vx, m);
+  double varg = vara_ / ((1 - Pi[0]) * sumvx);
+  const double s2varg_ = s2vara_ / ((1 - Pi[0]) * sumvx);
+  const double s2vare_ = isnan(a->s2ve) ? 0 : a->s2ve;
+  if (niter < nburn) return fail("Number of total iteration ('niter') shold be larger than burn-in ('nburn').");
+  const double R2 = (dfvara_ - 2) / dfvara_;
+  double lambda2 = 2 * (1 - R2) / (R2)*sumvx;
+  double lambda = sqrt(lambda2);
+  const double shape0 = 1.1, rate0 = (shape0 - 1) / lambda2;
+  if (model_index == 5) for (int i = 0; i < m; ++i) vargL[i] = varg;
+  double fold_snp_num[HB_ORACLE_MAX_FOLD] = {0}, logpi[HB_ORACLE_MAX_FOLD], s[HB_ORACLE_MAX_FOLD], stemp[HB_ORACLE_MAX_FOLD];
+  double vara_fold[HB_ORACLE_MAX_FOLD], vare_vara_fold[HB_ORACLE_MAX_FOLD] = {0}, pisum[HB_ORACLE_MAX_FOLD] = {0};
+  for (int j = 0; j < n_fold; ++j) vara_fold[j] = (vara_ / ((1 - Pi[0]) * sumvx)) * fold_[j];
+  int nw = 0;
+  double* wppai = NULL;
+  if (a->windindx) { for (int i = 0; i < m; ++i) if (a->windindx[i] > nw) nw = a->windindx[i]; wppai = calloc(nw > 0 ? nw : 1, 8); }
+  double varasum = 0, varesum = 0, hsqsum = 0;
+  int iter;
+  for (iter = 0; iter < niter; ++iter) {
+    const uint32_t it = (uint32_t)iter;
+    double xx, gi, gi_, rhs, lhs, logdetV, acceptProb, uhat, v, vargi;
+    int indistflag;
+    switch (model_index) {
+      case 1: /* :254-270 */
+        for (int i = 0; i < m; ++i) {
+          if (!ifest[i]) continue;
+          xx = xpx[i]; gi = g[i]; rhs = r_hat[i];
+          if (gi) rhs += xx * gi;
+          v = xx + vare_ / varg;
+          gi = norm_at(HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, rhs / v, sqrt(vare_ / v));
+          gi_ = (g[i] - gi) * n;
+          daxpy(m, gi_, ldm + (size_t)i * m, r_hat);
+          g[i] = gi;
+        }
+        varg = (ddot(m, g, g) + s2varg_ * dfvara_) / chisq_at(HB_DOM_ITER, it, HB_IT_VARG, 0, dfvara_ + count_y);
+        break;
+      case 2: /* :273-289 */
+        for (int i = 0; i < m; ++i) {
+          if (!ifest[i]) continue;
+          xx = xpx[i]; gi = g[i];
+          varg = (gi * gi + s2varg_ * dfvara_) / chisq_at(HB_DOM_SNP, it, (uint32_t)i, HB_SL_CHI, dfvara_ + 1);
+          rhs = r_hat[i];
+          if (gi) rhs += xx * gi;
+          v = xx + vare_ / varg;
+          gi = norm_at(HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, rhs / v, sqrt(vare_ / v));
+          gi_ = (g[i] - gi) * n;
+          daxpy(m, gi_, ldm + (size_t)i * m, r_hat);
+          g[i] = gi;
+        }
+        break;
+      case 3: case 4: /* :290-364 */
+        for (int j = 0; j < n_fold; ++j) logpi[j] = log(Pi[j]);
+        s[0] = logpi[0];
+        vargi = 0;
+        for (int i = 0; i < m; ++i) {
+          if (!ifest[i]) continue;
+          xx = xpx[i]; gi = g[i];
+          if (model_index == 3)
+            varg = (gi * gi + s2varg_ * dfvara_) / chisq_at(HB_DOM_SNP, it, (uint32_t)i, HB_SL_CHI, dfvara_ + 1);
+          rhs = r_hat[i];
+          if (gi) rhs += xx * gi;
+          lhs = xx / vare_;
+          logdetV = log(varg * lhs + 1);
+          uhat = rhs / (xx + vare_ / varg);
+          s[1] = -0.5 * (logdetV - (rhs * uhat / vare_)) + logpi[1];
+          acceptProb = 1 / (exp(s[0] - s[0]) + exp(s[1] - s[0]));
+          double rval, zval;
+          hb_draw_uz(KEY, HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, 0, &rval, &zval);
+          indistflag = rval < acceptProb ? 0 : 1;
+          snptracker[i] = indistflag;
+          if (indistflag == 0) gi = 0;
+          else {
+            v = xx + vare_ / varg;
+            gi = rhs / v + sqrt(vare_ / v) * zval;
+            if (model_index == 4) vargi += gi * gi;
+          }
+          if (gi != g[i]) {
+            gi_ = (g[i] - gi) * n;
+            daxpy(m, gi_, ldm + (size_t)i * m, r_hat);
+            g[i] = gi;
+          }
+        }
+        fold_snp_num[1] = acc_sum(snptracker, m);
+        fold_snp_num[0] = m - nvar0 - fold_snp_num[1];
+        NnzSnp = (int)fold_snp_num[1];
+        if (model_index == 4)
+          varg = (vargi + s2varg_ * dfvara_) / chisq_at(HB_DOM_ITER, it, HB_IT_VARG, 0, dfvara_ + NnzSnp);
+        if (!fixpi) {
+          for (int j = 0; j < n_fold; ++j) Pi[j] = hb_draw_gamma(KEY, HB_DOM_ITER, it, HB_IT_PI0 + (uint32_t)j, 0, fold_snp_num[j] + 1);
+          const double tot = acc_sum(Pi, n_fold);
+          for (int j = 0; j < n_fold; ++j) Pi[j] /= tot;
+        }
+        break;
+      case 5: /* :365-389 */
+        for (int i = 0; i < m; ++i) {
+          if (!ifest[i]) continue;
+          xx = xpx[i]; gi = g[i]; rhs = r_hat[i];
+          if (gi) rhs += xx * gi;
+          v = xx + 1 / vargL[i];
+          gi = norm_at(HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, rhs / v, sqrt(vare_ / v));
+          if (fabs(gi) < 1e-6) gi = 1e-6;
+          { double uu, zz;
+            hb_draw_uz(KEY, HB_DOM_SNP, it, (uint32_t)i, HB_SL_IG, 0, &uu, &zz);
+            vargi = 1 / hb_invgauss_from_uz(sqrt(vare_) * lambda / fabs(gi), lambda2, uu, zz); }
+          if (vargi > 0) vargL[i] = vargi;
+          if (gi != g[i]) {
+            gi_ = (g[i] - gi) * n;
+            daxpy(m, gi_, ldm + (size_t)i * m, r_hat);
+            g[i] = gi;
+          }
+        }
+        { const double shape = shape0 + count_y, rate = rate0 + acc_sum(vargL, m) / 2;
+          lambda2 = hb_draw_gamma(KEY, HB_DOM_ITER, it, HB_IT_LAMBDA, 0, shape) * (1 / rate);
+          lambda = sqrt(lambda2); }
+        break;
+      default: /* 6: BayesR :390-455 */
+        for (int j = 0; j < n_fold; ++j) logpi[j] = log(Pi[j]);
+        s[0] = logpi[0];
+        varg = 0;
+        for (int j = 1; j < n_fold; ++j) vare_vara_fold[j] = vare_ / vara_fold[j];
+        for (int i = 0; i < m; ++i) {
+          if (!ifest[i]) continue;
+          xx = xpx[i]; gi = g[i]; rhs = r_hat[i];
+          if (gi) rhs += xx * gi;
+          lhs = xx / vare_;
+          for (int j = 1; j < n_fold; ++j) {
+            logdetV = log(vara_fold[j] * lhs + 1);
+            uhat = rhs / (xx + vare_vara_fold[j]);
+            s[j] = -0.5 * (logdetV - (rhs * uhat / vare_)) + logpi[j];
+          }
+          for (int j = 0; j < n_fold; ++j) {
+            double temp = 0.0;
+            for (int k = 0; k < n_fold; ++k) temp += exp(s[k] - s[j]);
+            stemp[j] = 1 / temp;
+          }
+          acceptProb = 0; indistflag = 0;
+          double rval, zval;
+          hb_draw_uz(KEY, HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, 0, &rval, &zval);
+          for (int j = 0; j < n_fold; ++j) { acceptProb += stemp[j]; if (rval < acceptProb) { indistflag = j; break; } }
+          snptracker[i] = indistflag;
+          if (indistflag == 0) gi = 0;
+          else {
+            v = xx + vare_vara_fold[indistflag];
+            gi = rhs / v + sqrt(vare_ / v) * zval;
+            varg += (gi * gi / fold_[indistflag]);
+          }
+          if (gi != g[i]) {
+            gi_ = (g[i] - gi) * n;
+            daxpy(m, gi_, ldm + (size_t)i * m, r_hat);
+            g[i] = gi;
+          }
+        }
+        for (int j = 0; j < n_fold; ++j) { double c = 0; for (int i = 0; i < m; ++i) c += (snptracker[i] == j); fold_snp_num[j] = c; }
+        NnzSnp = m - (int)fold_snp_num[0];
+        varg = (varg + s2varg_ * dfvara_) / chisq_at(HB_DOM_ITER, it, HB_IT_VARG, 0, dfvara_ + NnzSnp);
+        for (int j = 0; j < n_fold; ++j) vara_fold[j] = varg * fold_[j];
+        fold_snp_num[0] -= nvar0;
+        if (!fixpi) {
+          for (int j = 0; j < n_fold; ++j) Pi[j] = hb_draw_gamma(KEY, HB_DOM_ITER, it, HB_IT_PI0 + (uint32_t)j, 0, fold_snp_num[j] + 1);
+          const double tot = acc_sum(Pi, n_fold);
+          for (int j = 0; j < n_fold; ++j) Pi[j] /= tot;
+        }
+        break;
+    }
+    /* :458-468 */
+    for (int i = 0; i < m; ++i) tmp[i] = xy[i] - r_hat[i];
+    vara_ = (ddot(m, g, tmp) + s2vara_ * dfvara_) / chisq_at(HB_DOM_ITER, it, HB_IT_VARA, 0, n + dfvara_);
+    for (int i = 0; i < m; ++i) tmp[i] = xy[i] + r_hat[i];
+    vare_ = (yy - ddot(m, g, tmp) + s2vare_ * dfvare_) / chisq_at(HB_DOM_ITER, it, HB_IT_VARE, 0, n + dfvare_);
+    if (vare_ < 0) vare_ = vara_ * 0.5;
+    if (o->nnz_trace) o->nnz_trace[iter] = NnzSnp;
+    if (o->vara_trace) o->vara_trace[iter] = vara_;
+    if (o->vare_trace) o->vare_trace[iter] = vare_;
+    if (o->varg_trace) o->varg_trace[iter] = varg;
+    if (iter >= nburn) {   /* :470-491 */
+      if (have_tracker) for (int i = 0; i < m; ++i) if (snptracker[i]) nzrate[i] += 1;
+      if (wppai)
+        for (int w = 0; w < nw; ++w) {
+          int any = 0;
+          for (int i = 0; i < m && !any; ++i) if (a->windindx[i] == w + 1 && snptracker[i]) any = 1;
+          if (any) wppai[w] += 1;
+        }
+      nzct++;
+    }
+    if (iter >= nburn && (iter + 1 - nburn) % thin == 0) {   /* :493-505 */
+      if (!fixpi) {
+        for (int j = 0; j < n_fold; ++j) pisum[j] += Pi[j];
+        if (o->pi_store) for (int j = 0; j < n_fold; ++j) o->pi_store[(size_t)count * n_fold + j] = Pi[j];
+      }
+      varasum += vara_; varesum += vare_;
+      if (o->vara_store) o->vara_store[count] = vara_;
+      if (o->vare_store) o->vare_store[count] = vare_;
+      for (int i = 0; i < m; ++i) gsum[i] += g[i];
+      if (o->alpha_store) memcpy(o->alpha_store + (size_t)count * m, g, 8 * (size_t)m);
+      hsqsum += vara_ / (vara_ + vare_);
+      if (o->hsq_store) o->hsq_store[count] = vara_ / (vara_ + vare_);
+      count++;
+    }
+    if (count == n_records) { ++iter; break; }
+  }
+  o->iters_done = iter; o->n_records_done = count; o->nzct = nzct; o->n_used = n;
+  o->Vg = varasum / count; o->Ve = varesum / count; o->h2 = hsqsum / count;
+  if (o->alpha) for (int i = 0; i < m; ++i) o->alpha[i] = gsum[i] / count;
+  if (o->pi) for (int j = 0; j < n_fold; ++j) o->pi[j] = fixpi ? Pi[j] : pisum[j] / count;
+  if (fixpi && o->pi_store) for (int c = 0; c < count; ++c) { o->pi_store[(size_t)c * n_fold] = Pi[0]; o->pi_store[(size_t)c * n_fold + 1] = Pi[1]; }
+  if (o->nzrate_count) memcpy(o->nzrate_count, nzrate, 8 * (size_t)m);
+  if (o->tracker_final) for (int i = 0; i < m; ++i) o->tracker_final[i] = have_tracker ? (int32_t)snptracker[i] : 0;
+  if (o->pip)
+    for (int i = 0; i < m; ++i) {
+      if (!have_tracker) { o->pip[i] = 1.0; continue; }
+      double r = nzrate[i] / nzct;
+      if (r == 1) r = (nzct - 1) / (double)nzct;
+      o->pip[i] = r;
+    }
+  if (wppai) {
+    if (o->wppa_count) memcpy(o->wppa_count, wppai, 8 * (size_t)nw);
+    if (o->gwas) for (int w = 0; w < nw; ++w) { double r = wppai[w] / nzct; if (r == 1) r = (nzct - 1) / (double)nzct; o->gwas[w] = r; }
+  }
+  if (o->r_hat_final) memcpy(o->r_hat_final, r_hat, 8 * (size_t)m);
+  free(xy); free(r_hat); free(tmp); free(yyi); free(g); free(xpx); free(vx); free(snptracker); free(nzrate); free(gsum);
+  free(vargL); free(ifest); free(wppai);
+#undef SS
+  return 0;
+}

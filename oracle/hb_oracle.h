@@ -110,3 +110,33 @@ double hbo_time_sweep_fp64(int n, int m_cpu, int sweeps, int threads, uint64_t s
 }
 #endif
 #endif
+
+/* ---- SBayesD: dense-LD summary-statistics Gibbs sampler (/root/reference/src/SBayesD.cpp:5-609) ---- */
+typedef struct {
+  int m;
+  const double* sumstat;  /* m x 4 column-major: MAF, BETA, SE, N (R/sbayes.r:209); NaN = NA */
+  const double* ldm;      /* m x m column-major */
+  const char* model;
+  int n_fold;
+  const double* Pi;
+  const double* fold;     /* n_fold or NULL */
+  int niter, nburn, thin;
+  double vg, dfvg, s2vg, ve, dfve, s2ve;   /* NaN = not given */
+  const int32_t* windindx;                 /* m, 1-based, or NULL */
+  uint64_t seed;
+} hbo_sbayes_args;
+
+typedef struct {
+  double Vg, Ve, h2;
+  double* alpha;       /* m */
+  double* pi;          /* n_fold */
+  double* pip;         /* m */
+  double* gwas;        /* nw or NULL */
+  double* vara_store; double* vare_store; double* hsq_store; double* pi_store; double* alpha_store; /* NULL to skip */
+  int32_t* tracker_final; double* nzrate_count; double* wppa_count;
+  int32_t* nnz_trace; double* vara_trace; double* vare_trace; double* varg_trace;   /* niter each */
+  double* r_hat_final;  /* m */
+  int n_records_done, nzct, iters_done, n_used;   /* n_used = int(mean(N)) */
+} hbo_sbayes_out;
+
+int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o);

@@ -198,3 +198,73 @@ def time_sweep_fp64(n, m_cpu, sweeps, threads, seed=1):
     cs = C.c_double(0)
     v = lib().hbo_time_sweep_fp64(n, m_cpu, sweeps, threads, seed, C.byref(cs))
     return v, cs.value
+
+
+class _SBayesArgs(C.Structure):
+    _fields_ = [("m", C.c_int), ("sumstat", C.c_void_p), ("ldm", C.c_void_p), ("model", C.c_char_p), ("n_fold", C.c_int),
+                ("Pi", C.c_void_p), ("fold", C.c_void_p), ("niter", C.c_int), ("nburn", C.c_int), ("thin", C.c_int),
+                ("vg", C.c_double), ("dfvg", C.c_double), ("s2vg", C.c_double), ("ve", C.c_double), ("dfve", C.c_double),
+                ("s2ve", C.c_double), ("windindx", C.c_void_p), ("seed", C.c_uint64)]
+
+
+class _SBayesOut(C.Structure):
+    _fields_ = [("Vg", C.c_double), ("Ve", C.c_double), ("h2", C.c_double), ("alpha", C.c_void_p), ("pi", C.c_void_p),
+                ("pip", C.c_void_p), ("gwas", C.c_void_p), ("vara_store", C.c_void_p), ("vare_store", C.c_void_p),
+                ("hsq_store", C.c_void_p), ("pi_store", C.c_void_p), ("alpha_store", C.c_void_p),
+                ("tracker_final", C.c_void_p), ("nzrate_count", C.c_void_p), ("wppa_count", C.c_void_p),
+                ("nnz_trace", C.c_void_p), ("vara_trace", C.c_void_p), ("vare_trace", C.c_void_p), ("varg_trace", C.c_void_p),
+                ("r_hat_final", C.c_void_p), ("n_records_done", C.c_int), ("nzct", C.c_int), ("iters_done", C.c_int),
+                ("n_used", C.c_int)]
+
+
+def sbayes_buffers(m, F, niter, nburn, thin, nw, out_struct):
+    """Output arrays shared by the oracle wrapper and the GPU wrapper (same field names in both structs)."""
+    nrec = max((niter - nburn) // thin, 0)
+    res = {"alpha": np.zeros(m), "pi": np.zeros(F), "pip": np.zeros(m), "gwas": np.zeros(nw)}
+    mc = {"Vg": np.zeros(nrec), "Ve": np.zeros(nrec), "h2": np.zeros(nrec), "pi": np.zeros((F, nrec), order="F")}
+    dg = {"tracker": np.zeros(m, dtype=np.int32), "nzrate_count": np.zeros(m), "wppa_count": np.zeros(nw),
+          "nnz_trace": np.zeros(niter, dtype=np.int32), "vara_trace": np.zeros(niter), "vare_trace": np.zeros(niter),
+          "varg_trace": np.zeros(niter), "r_hat": np.zeros(m)}
+    o = out_struct
+    o.alpha, o.pi, o.pip = res["alpha"].ctypes.data, res["pi"].ctypes.data, res["pip"].ctypes.data
+    o.gwas = res["gwas"].ctypes.data if nw else None
+    o.vara_store, o.vare_store, o.hsq_store, o.pi_store = (mc["Vg"].ctypes.data, mc["Ve"].ctypes.data, mc["h2"].ctypes.data,
+                                                           mc["pi"].ctypes.data)
+    o.tracker_final, o.nzrate_count = dg["tracker"].ctypes.data, dg["nzrate_count"].ctypes.data
+    o.wppa_count = dg["wppa_count"].ctypes.data if nw else None
+    o.nnz_trace, o.vara_trace, o.vare_trace, o.varg_trace = (dg["nnz_trace"].ctypes.data, dg["vara_trace"].ctypes.data,
+                                                             dg["vare_trace"].ctypes.data, dg["varg_trace"].ctypes.data)
+    o.r_hat_final = dg["r_hat"].ctypes.data
+    return res, mc, dg
+
+
+def sbayesd(sumstat, ldm, model, Pi, fold=None, niter=200, nburn=100, thin=5, windindx=None, vg=None, dfvg=None, s2vg=None,
+            ve=None, dfve=None, s2ve=None, seed=666666):
+    """CPU oracle of SBayesD(): sumstat m x 4 (MAF, BETA, SE, N), ldm m x m."""
+    L = lib()
+    ss = np.asfortranarray(sumstat, dtype=np.float64)
+    ld = np.asfortranarray(ldm, dtype=np.float64)
+    m = ld.shape[0]
+    Pi = np.ascontiguousarray(Pi, dtype=np.float64)
+    F = Pi.shape[0]
+    fo = None if fold is None else np.ascontiguousarray(fold, dtype=np.float64)
+    a = _SBayesArgs()
+    a.m, a.sumstat, a.ldm, a.model, a.n_fold, a.Pi, a.fold = m, ss.ctypes.data, ld.ctypes.data, model.encode(), F, Pi.ctypes.data, _ptr(fo)
+    a.niter, a.nburn, a.thin = niter, nburn, thin
+    a.vg, a.dfvg, a.s2vg, a.ve, a.dfve, a.s2ve = _nan(vg), _nan(dfvg), _nan(s2vg), _nan(ve), _nan(dfve), _nan(s2ve)
+    nw = 0
+    w = None
+    if windindx is not None:
+        w = np.ascontiguousarray(windindx, dtype=np.int32)
+        nw = int(w.max())
+        a.windindx = w.ctypes.data
+    a.seed = seed
+    o = _SBayesOut()
+    res, mc, dg = sbayes_buffers(m, F, niter, nburn, thin, nw, o)
+    L.hbo_sbayesd.restype = C.c_int
+    if L.hbo_sbayesd(C.byref(a), C.byref(o)) != 0:
+        raise RuntimeError(L.hbo_last_error().decode())
+    res.update({"Vg": o.Vg, "Ve": o.Ve, "h2": o.h2, "MCMCsamples": mc})
+    dg.update({"n_records": o.n_records_done, "nzct": o.nzct, "iters_done": o.iters_done, "n_used": o.n_used})
+    res["diag"] = dg
+    return res

@@ -1,0 +1,80 @@
+"""SBayesD: the oracle on CPU, and the CUDA path against it."""
+import numpy as np
+import pytest
+
+from tests.util_demo import load_demo_T1, synth
+from tests.util_sumstat import make_sumstat
+
+MODELS = [
+    ("BayesCpi", [0.95, 0.05], None),
+    ("BayesC", [0.95, 0.05], None),
+    ("BayesB", [0.95, 0.05], None),
+    ("BayesBpi", [0.95, 0.05], None),
+    ("BayesR", [0.95, 0.02, 0.02, 0.01], [0, 1e-4, 1e-3, 1e-2]),
+    ("BayesRR", [0.95, 0.05], None),
+    ("BayesA", [0.95, 0.05], None),
+    ("BayesL", [0.95, 0.05], None),
+]
+RTOL = 1e-5
+
+
+def test_oracle_sbayesd_runs_and_respects_the_quirks(oracle):
+    y, X = synth(800, 300, seed=12, n_causal=10)
+    ss, ld = make_sumstat(y, X, n_na=7, seed=3)
+    wind = (np.arange(300) // 25) + 1
+    r = oracle.sbayesd(ss, ld, "BayesCpi", [0.9, 0.1], niter=60, nburn=20, thin=5, windindx=wind, seed=5)
+    na = np.isnan(ss[:, 1])
+    assert r["diag"]["n_used"] == 800 and r["diag"]["n_records"] == 8
+    assert np.all(r["alpha"][na] == 0) and np.all(r["pip"][na] == 0)          # SNPs with NA statistics are skipped (:100-103)
+    assert 0 < r["h2"] < 1 and r["Vg"] > 0 and r["Ve"] > 0
+    assert r["gwas"].shape == (12,) and np.all((r["gwas"] >= 0) & (r["gwas"] < 1))
+    # effects explain the marginal statistics: r_hat = xy - n LD g  (SBayesD.cpp:105, 351-356)
+    n = r["diag"]["n_used"]
+    # dense models keep every SNP in
+    r2 = oracle.sbayesd(ss, ld, "BayesRR", [0.9, 0.1], niter=30, nburn=10, thin=5, seed=5)
+    assert np.all(r2["pip"] == 1.0)
+    with pytest.raises(RuntimeError, match="fold"):
+        oracle.sbayesd(ss, ld, "BayesR", [0.9, 0.05, 0.05], niter=10, nburn=5, thin=1)
+
+
+def _compare(got, ref):
+    assert np.array_equal(got["diag"]["tracker"], ref["diag"]["tracker"])
+    assert np.array_equal(got["diag"]["nnz_trace"], ref["diag"]["nnz_trace"])
+    assert np.array_equal(got["diag"]["nzrate_count"], ref["diag"]["nzrate_count"])
+    assert np.array_equal(got["pip"], ref["pip"])
+    assert got["diag"]["n_records"] == ref["diag"]["n_records"] and got["diag"]["iters_done"] == ref["diag"]["iters_done"]
+    for k in ("Vg", "Ve", "h2"):
+        assert abs(got[k] / ref[k] - 1) < RTOL, (k, got[k], ref[k])
+    scale = np.abs(ref["alpha"]).max() + 1e-300
+    assert np.abs(got["alpha"] - ref["alpha"]).max() < RTOL * scale
+    assert np.allclose(got["pi"], ref["pi"], rtol=RTOL)
+    assert np.allclose(got["diag"]["r_hat"], ref["diag"]["r_hat"], rtol=RTOL, atol=RTOL * np.abs(ref["diag"]["r_hat"]).max())
+    assert np.allclose(got["diag"]["vare_trace"], ref["diag"]["vare_trace"], rtol=RTOL)
+    assert np.allclose(got["diag"]["vara_trace"], ref["diag"]["vara_trace"], rtol=RTOL)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,Pi,fold", MODELS)
+def test_sbayesd_demo_all_models(oracle, model, Pi, fold):
+    """sbrm()-style inputs from the bundled demo genotypes (300 x 1000): every model string against the oracle."""
+    import hibayes_b200 as hb
+    y, X = load_demo_T1()
+    ss, ld = make_sumstat(y, X)
+    kw = dict(niter=60, nburn=30, thin=5, seed=666666)
+    ref = oracle.sbayesd(ss, ld, model, Pi, fold=fold, **kw)
+    got = hb.SBayesD(ss, ld, model, Pi, fold=fold, **kw)
+    _compare(got, ref)
+
+
+@pytest.mark.gpu
+def test_sbayesd_na_rows_windows_ragged(oracle):
+    import hibayes_b200 as hb
+    y, X = synth(1200, 777, seed=31, n_causal=12)   # m not a multiple of the tile
+    ss, ld = make_sumstat(y, X, n_na=20, seed=2)
+    wind = (np.arange(777) // 40) + 1
+    kw = dict(niter=40, nburn=10, thin=3, windindx=wind, seed=11)
+    ref = oracle.sbayesd(ss, ld, "BayesR", [0.9, 0.05, 0.03, 0.02], fold=[0, 1e-4, 1e-3, 1e-2], **kw)
+    got = hb.SBayesD(ss, ld, "BayesR", [0.9, 0.05, 0.03, 0.02], fold=[0, 1e-4, 1e-3, 1e-2], **kw)
+    _compare(got, ref)
+    assert np.array_equal(got["diag"]["wppa_count"], ref["diag"]["wppa_count"])
+    assert np.array_equal(got["gwas"], ref["gwas"])
