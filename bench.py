@@ -249,6 +249,7 @@ def run_gpu(args):
     m_active = int(active.sum())
     value = world * m_active * args.steps / wall
     # ---- end-to-end region: same steps through the host-facing ABI, residual over PCIe in both directions
+    r = eng.get_residual()                  # the chain's current residual (not the one from before the sweeps)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):

@@ -1016,7 +1016,7 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
     if (FILE* f = fopen(getenv("HB_TRACE"), "wb")) { fwrite(tr.data(), 8, tr.size(), f); fclose(f); }
   }
   if (getenv("HB_PHASES")) {
-    fprintf(stderr, "[hb] exact class evaluations this sweep: %d\n", h.pad);
+    fprintf(stderr, "[hb] tiles re-speculated before the chain: %d, rounds %d (tiles %d)\n", h.pad, h.rounds, e->T);
     static const char* nm[16] = {"wait_dots", "guess", "wait_prev", "bar_rhs0", "chain", "first", "post", "commit",
                                  "bar_chain", "loop", "bar_part", "classify", "bar_bad", "-", "-", "-"};
     for (int g = 0; g < 2; ++g) {

@@ -791,7 +791,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
   const bool use_thr = p.use_thr && !dense;
   const int DC = D - 1;   // correction slots per tile
   bool dead = false;
-  int rounds_total = 0, changed_total = 0;
+  int rounds_total = 0, changed_total = 0, respec = 0;
 
   long long* pc = phase;   // [16] = last time stamp
   if (tid == 0) { for (int k = 0; k < 16; ++k) pc[k] = 0; pc[16] = clock64(); }
@@ -841,7 +841,6 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
         const int c0 = thr_class<NF>(nf, rr, TL, TH);
         if (c0 >= 0) return c0;
       }
-      atomicAdd(&p.out->pad, 1);   // diagnostic: exact evaluations
       return classify_exact<NF>(p.prm, mp, j, nf, rr, p.logpi0);
     };
     // corrections owed by the tiles t-D+1 .. t-1: whatever has been posted by now goes into the speculation
@@ -971,7 +970,19 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     for (;;) {
       ++nrounds;
       if (cand && prim) cs.rhs0[myrank] = rhs0;
-      hb::named_bar_sync(1, NT2);   // rows and right-hand sides of the candidates are in shared memory
+      // The speculation of phase P may have missed corrections that arrived later: with the complete right-hand
+      // side (still without the changes inside this tile) the classes are re-decided first, and if any differs
+      // the candidate list and its rows are rebuilt before the chain runs (instead of after a wasted round).
+      // The barrier that publishes the candidates' right-hand sides carries the verdict.
+      int cls0 = cls;
+      if (nrounds == 1 && prim && act) cls0 = classify(rhs0);
+      if (hb::named_bar_or(1, NT2, cls0 != cls)) {
+        cls = cls0;
+        compact();
+        if (cand && prim) cs.rhs0[myrank] = rhs0;
+        hb::named_bar_sync(1, NT2);
+        ++respec;
+      }
       HB_PHASE(3);
       double prhs = 0.0, pcorr = 0.0;
       if (fast) {
@@ -1060,6 +1071,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     if (worker < 2)
       for (int k = 0; k < 16; ++k) p.out->phase_clk[worker][k] = pc[k];
     atomicAdd(&p.out->rounds, rounds_total);
+    atomicAdd(&p.out->pad, respec);   // diagnostic: tiles whose candidate list was rebuilt before the chain
     atomicAdd(&p.out->n_changed, changed_total);
   }
 }

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+HB_PHASES=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29718 bench.py --gpus 8 --steps 10 --warmup 5 > gpurun_out/scale_n8b.json 2> gpurun_out/scale_n8b.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/scale_n8b.json').read().strip().splitlines()[-1]); print('N',d['n_gpus'],'value',d['value'],'ms',d['ms_per_step'],'kernel_ms',d['roofline']['kernel_ms'],'rounds',d['config']['scalar_rounds_per_sweep'],'e2e',d['e2e']['value'])"
+grep "re-spec" gpurun_out/scale_n8b.err | tail -3
