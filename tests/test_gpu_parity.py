@@ -161,3 +161,50 @@ def test_sweep_is_deterministic_run_to_run():
     a = hb.Bayes(y, X, "BayesR", [0.95, 0.02, 0.02, 0.01], fold=[0, 1e-4, 1e-3, 1e-2], **kw)
     b = hb.Bayes(y, X, "BayesR", [0.95, 0.02, 0.02, 0.01], fold=[0, 1e-4, 1e-3, 1e-2], **kw)
     assert np.array_equal(a["alpha"], b["alpha"]) and np.array_equal(a["g"], b["g"]) and a["Ve"] == b["Ve"]
+
+
+def test_large_shape_invariants():
+    """Size-independent properties at a shape the oracle cannot run (n = 50 000 rows as in the metric, m = 32 768):
+    the residual and genetic values the sweeps leave behind equal y - mu - X g and X g recomputed from the final
+    effects, class counts add up, and two runs agree bit for bit."""
+    n, m = 50000, 32768
+    e = hb.Engine(n, m, seed=77)
+    e.synth_geno(20260101)
+    xpx, sumx = e.col_stats()
+    active = (n * xpx != sumx * sumx)
+    e.set_snp_info(xpx, active.astype(np.uint8))
+    e.build_gram()
+    rng = np.random.default_rng(1)
+    beta = np.zeros(m)
+    idx = rng.choice(m, 100, replace=False)
+    beta[idx] = rng.standard_normal(100)
+    gv = e.predict(beta)
+    y = gv * np.sqrt(0.5 / gv.var()) + rng.normal(scale=np.sqrt(0.5), size=n)
+    r0 = y - y.mean()
+    vx = (xpx - sumx * sumx / n) / (n - 1)
+    varg = 0.25 * y.var() / (0.05 * vx.sum())
+    fold = [0.0, 1e-4, 1e-3, 1e-2]
+    logpi = list(np.log([0.95, 0.02, 0.02, 0.01]))
+
+    def run():
+        e.set_residual(r0)
+        e.set_u(np.zeros(n))
+        e.set_effects(np.zeros(m))
+        outs = []
+        for it in range(3):
+            outs.append(e.sweep(iter=it, model_index=6, vare=0.5 * y.var(), logpi=logpi, vara_fold=[varg * f for f in fold], fold=fold,
+                                rnorm2_bound=float(r0 @ r0) * 2))
+        return outs, e.get_residual(), e.get_u(), e.get_effects(), e.get_tracker()
+
+    o1, r1, u1, g1, t1 = run()
+    o2, r2, u2, g2, t2 = run()
+    assert np.array_equal(t1, t2) and np.array_equal(g1, g2) and np.array_equal(r1, r2) and np.array_equal(u1, u2)
+    xg = e.predict(g1)
+    scale = np.abs(r0).max()
+    assert np.abs(u1 - xg).max() < 1e-9 * scale                      # u = X g         (Bayes.cpp:789)
+    assert np.abs(r1 - (r0 - xg)).max() < 1e-9 * scale               # yadj = y - mu - X g (:787)
+    cnt = np.array(o1[-1]["count"][:4])
+    assert cnt.sum() == active.sum() and np.array_equal(cnt, np.bincount(t1[active], minlength=4))
+    assert abs(o1[-1]["sum_r2"] - r1 @ r1) < 1e-9 * (r1 @ r1)
+    assert np.all((g1 != 0) == (t1 > 0))
+    e.close()
