@@ -20,7 +20,7 @@ SYMBOLS = [
     "hb_engine_last_sweep_ms", "hb_engine_describe", "hb_bayes",
     "hb_engine_ipc_handle", "hb_engine_set_peers", "hb_engine_gram_device", "hb_engine_u_centered_sums",
     "hb_ld_engine_create", "hb_ld_engine_destroy", "hb_ld_engine_load_dense", "hb_ld_engine_set_state",
-    "hb_ld_engine_set_vargL", "hb_ld_engine_get", "hb_ld_engine_sweep", "hb_sbayesd",
+    "hb_ld_engine_set_vargL", "hb_ld_engine_set_sparse_info", "hb_ld_engine_get", "hb_ld_engine_sweep", "hb_sbayesd", "hb_sbayess",
 ]
 
 
@@ -29,7 +29,8 @@ class SBayesArgs(C.Structure):
                 ("Pi", C.c_void_p), ("fold", C.c_void_p), ("niter", C.c_int), ("nburn", C.c_int), ("thin", C.c_int),
                 ("vg", C.c_double), ("dfvg", C.c_double), ("s2vg", C.c_double), ("ve", C.c_double), ("dfve", C.c_double),
                 ("s2ve", C.c_double), ("windindx", C.c_void_p), ("outfreq", C.c_int), ("verbose", C.c_int),
-                ("seed", C.c_uint64), ("device", C.c_int)]
+                ("seed", C.c_uint64), ("device", C.c_int),
+                ("ld_colptr", C.c_void_p), ("ld_rowidx", C.c_void_p), ("ld_val", C.c_void_p)]
 
 
 class SBayesOut(C.Structure):
@@ -141,6 +142,7 @@ def load_library():
                                      C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.hb_bayes.argtypes = [C.POINTER(BayesArgs), C.POINTER(BayesOut)]
     L.hb_sbayesd.argtypes = [C.POINTER(SBayesArgs), C.POINTER(SBayesOut)]
+    L.hb_sbayess.argtypes = [C.POINTER(SBayesArgs), C.POINTER(SBayesOut)]
     L.hb_engine_ipc_handle.argtypes = [C.c_void_p, C.c_void_p]
     L.hb_engine_set_peers.argtypes = [C.c_void_p, C.c_void_p]
     L.hb_engine_gram_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]

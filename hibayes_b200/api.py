@@ -147,31 +147,44 @@ def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, nite
     return res
 
 
-def SBayesD(sumstat, ldm, model, Pi, niter=50000, nburn=20000, thin=5, fold=None, windindx=None, vg=None, dfvg=None,
-            s2vg=None, ve=None, dfve=None, s2ve=None, outfreq=100, threads=0, verbose=False, seed=666666, device=0):
-    """GPU twin of hibayes' SBayesD() (/root/reference/src/SBayesD.cpp:5-24; what sbrm() calls at R/sbayes.r:215 for a
-    dense LD matrix).  sumstat: m x 4 (MAF, BETA, SE, N = columns 4,5,6,8 of the COJO file, R/sbayes.r:209), NaN = NA;
-    ldm: m x m.  Returns a dict named like the Rcpp::List (:532-578)."""
+def _sbayes(sparse, sumstat, ldm, model, Pi, niter, nburn, thin, fold, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, outfreq, verbose,
+            seed, device):
     L = _lib.load_library()
     ss = np.asfortranarray(sumstat, dtype=np.float64)
-    ld = np.asfortranarray(ldm, dtype=np.float64)
-    if ss.shape[0] != ld.shape[0]:
+    a = _lib.SBayesArgs()
+    keep = [ss]
+    if sparse:
+        import scipy.sparse as sp
+        G = sp.csc_matrix(ldm)
+        G.sort_indices()
+        G.eliminate_zeros()
+        cp = np.ascontiguousarray(G.indptr, dtype=np.int32)
+        ri = np.ascontiguousarray(G.indices, dtype=np.int32)
+        gv = np.ascontiguousarray(G.data, dtype=np.float64)
+        a.ld_colptr, a.ld_rowidx, a.ld_val = _ptr(cp), _ptr(ri), _ptr(gv)
+        keep += [cp, ri, gv]
+        m = G.shape[0]
+    else:
+        ld = np.asfortranarray(ldm, dtype=np.float64)
+        a.ldm = _ptr(ld)
+        keep.append(ld)
+        m = ld.shape[0]
+    if ss.shape[0] != m:
         raise RuntimeError("Number of SNPs not equals.")  # SBayesD.cpp:29-31
-    m = ld.shape[0]
     Pi = np.ascontiguousarray(Pi, dtype=np.float64)
     F = Pi.shape[0]
     fo = None if fold is None else np.ascontiguousarray(fold, dtype=np.float64)
     if fo is not None and fo.shape[0] != F:
         raise RuntimeError("length of Pi and fold not equals.")
-    a = _lib.SBayesArgs()
-    a.m, a.sumstat, a.ldm, a.model, a.n_fold, a.Pi, a.fold = m, ss.ctypes.data, ld.ctypes.data, model.encode(), F, Pi.ctypes.data, _ptr(fo)
+    a.m, a.sumstat, a.model, a.n_fold, a.Pi, a.fold = m, _ptr(ss), model.encode(), F, _ptr(Pi), _ptr(fo)
     a.niter, a.nburn, a.thin = niter, nburn, thin
     a.vg, a.dfvg, a.s2vg, a.ve, a.dfve, a.s2ve = _nan(vg), _nan(dfvg), _nan(s2vg), _nan(ve), _nan(dfve), _nan(s2ve)
-    nw, w = 0, None
+    nw = 0
     if windindx is not None:
         w = np.ascontiguousarray(windindx, dtype=np.int32)
         nw = int(w.max())
-        a.windindx = w.ctypes.data
+        a.windindx = _ptr(w)
+        keep.append(w)
     a.outfreq, a.verbose, a.seed, a.device = outfreq, int(bool(verbose)), seed, device
     o = _lib.SBayesOut()
     nrec = max((niter - nburn) // thin, 0)
@@ -188,12 +201,29 @@ def SBayesD(sumstat, ldm, model, Pi, niter=50000, nburn=20000, thin=5, fold=None
     o.nnz_trace, o.vara_trace, o.vare_trace, o.varg_trace = (_ptr(dg["nnz_trace"]), _ptr(dg["vara_trace"]),
                                                              _ptr(dg["vare_trace"]), _ptr(dg["varg_trace"]))
     o.r_hat_final = _ptr(dg["r_hat"])
-    _lib.check(L.hb_sbayesd(C.byref(a), C.byref(o)))
+    _lib.check((L.hb_sbayess if sparse else L.hb_sbayesd)(C.byref(a), C.byref(o)))
     res.update({"Vg": o.Vg, "Ve": o.Ve, "h2": o.h2, "MCMCsamples": mc})
     dg.update({"n_records": o.n_records_done, "nzct": o.nzct, "iters_done": o.iters_done, "n_used": o.n_used,
                "seconds_sweep": o.seconds_sweep})
     res["diag"] = dg
     return res
+
+
+def SBayesD(sumstat, ldm, model, Pi, niter=50000, nburn=20000, thin=5, fold=None, windindx=None, vg=None, dfvg=None,
+            s2vg=None, ve=None, dfve=None, s2ve=None, outfreq=100, threads=0, verbose=False, seed=666666, device=0):
+    """GPU twin of hibayes' SBayesD() (/root/reference/src/SBayesD.cpp:5-24; what sbrm() calls at R/sbayes.r:215 for a
+    dense LD matrix).  sumstat: m x 4 (MAF, BETA, SE, N = columns 4,5,6,8 of the COJO file, R/sbayes.r:209), NaN = NA;
+    ldm: m x m.  Returns a dict named like the Rcpp::List (:532-578)."""
+    return _sbayes(False, sumstat, ldm, model, Pi, niter, nburn, thin, fold, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, outfreq,
+                   verbose, seed, device)
+
+
+def SBayesS(sumstat, ldm, model, Pi, niter=50000, nburn=20000, thin=5, fold=None, windindx=None, vg=None, dfvg=None,
+            s2vg=None, ve=None, dfve=None, s2ve=None, outfreq=100, threads=0, verbose=False, seed=666666, device=0):
+    """GPU twin of hibayes' SBayesS() (/root/reference/src/SBayesS.cpp:21-40; sbrm() with a sparse LD matrix,
+    R/sbayes.r:213): ldm is a scipy sparse matrix (dgCMatrix in R)."""
+    return _sbayes(True, sumstat, ldm, model, Pi, niter, nburn, thin, fold, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, outfreq,
+                   verbose, seed, device)
 
 
 class Engine:

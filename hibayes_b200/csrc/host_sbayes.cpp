@@ -33,8 +33,9 @@ struct LdGuard {
 
 #define HBCHK(call) do { if ((call) != 0) return 1; } while (0)
 
-extern "C" int hb_sbayesd(const hb_sbayes_args* a, hb_sbayes_out* o) {
-  if (!a || !o) return hb_set_error("hb_sbayesd: null argument");
+static int sbayes_host(const hb_sbayes_args* a, hb_sbayes_out* o, bool sparse) {
+  if (!a || !o) return hb_set_error("hb_sbayes: null argument");
+  if (sparse ? !(a->ld_colptr && a->ld_rowidx && a->ld_val) : !a->ldm) return hb_set_error("hb_sbayes: LD matrix missing");
   const int m = a->m;
   const std::string model = a->model ? a->model : "";
   const hb_key_t KEY = hb_make_key(a->seed);
@@ -74,7 +75,22 @@ extern "C" int hb_sbayesd(const hb_sbayes_args* a, hb_sbayes_out* o) {
   std::vector<double> xy(m, 0.0), r_hat(m, 0.0), yyi(m, 0.0), xpx(m), vx(m), g(m, 0.0), gsum(m, 0.0), nzrate(m, 0.0);
   std::vector<uint8_t> ifest(m, 1);
   std::vector<int32_t> tracker(m, 0);
-  for (int i = 0; i < m; ++i) { vx[i] = a->ldm[(size_t)i * m + i]; xpx[i] = vx[i] * n; }   // :92-96
+  std::vector<double> varediff(sparse ? m : 0), dense;
+  if (sparse) {
+    // SBayesS.cpp:109-113, 131-141; the device engine works on a dense copy (zeros where nothing is stored)
+    dense.assign((size_t)m * m, 0.0);
+    for (int i = 0; i < m; ++i) {
+      vx[i] = 0.0;
+      for (int q = a->ld_colptr[i]; q < a->ld_colptr[i + 1]; ++q) {
+        dense[(size_t)i * m + a->ld_rowidx[q]] = a->ld_val[q];
+        if (a->ld_rowidx[q] == i) vx[i] = a->ld_val[q];
+      }
+      varediff[i] = (m - (double)(a->ld_colptr[i + 1] - a->ld_colptr[i])) / m;
+      xpx[i] = vx[i] * n;
+    }
+  } else {
+    for (int i = 0; i < m; ++i) { vx[i] = a->ldm[(size_t)i * m + i]; xpx[i] = vx[i] * n; }   // :92-96
+  }
   int count_y = 0, nvar0 = 0;
   for (int k = 0; k < m; ++k) {   // :100-112
     if (isna(SS(k, 1)) || isna(SS(k, 2)) || isna(SS(k, 3))) { ifest[k] = 0; nvar0++; }
@@ -114,7 +130,8 @@ extern "C" int hb_sbayesd(const hb_sbayes_args* a, hb_sbayes_out* o) {
   LdGuard guard;
   HBCHK(hb_ld_engine_create(a->device, m, a->seed, &guard.e));
   hb_ld_engine* E = guard.e;
-  HBCHK(hb_ld_engine_load_dense(E, a->ldm));
+  HBCHK(hb_ld_engine_load_dense(E, sparse ? dense.data() : a->ldm));
+  if (sparse) { HBCHK(hb_ld_engine_set_sparse_info(E, varediff.data(), vx.data())); std::vector<double>().swap(dense); }
   HBCHK(hb_ld_engine_set_state(E, xpx.data(), ifest.data(), xy.data(), r_hat.data()));
   if (model_index == 5) { std::vector<double> vl(m, varg); HBCHK(hb_ld_engine_set_vargL(E, vl.data())); }
 
@@ -129,6 +146,7 @@ extern "C" int hb_sbayesd(const hb_sbayes_args* a, hb_sbayes_out* o) {
     if (model_index == 6) for (int j = 0; j < n_fold; ++j) in.vara_fold[j] = vara_fold[j];
     else in.vara_fold[1] = varg;
     in.vare = vare_; in.dfvara = dfvara_; in.s2varg = s2varg_; in.lambda = lambda; in.lambda2 = lambda2; in.nscale = n;
+    in.sparse_mode = sparse ? 1 : 0; in.vara = vara_; in.vary = vary;
     hb_ld_sweep_out so;
     HBCHK(hb_ld_engine_sweep(E, &in, &so));
     t_sweep += 1e-3 * so.sweep_ms;
@@ -233,3 +251,6 @@ extern "C" int hb_sbayesd(const hb_sbayes_args* a, hb_sbayes_out* o) {
   if (o->r_hat_final) HBCHK(hb_ld_engine_get(E, nullptr, nullptr, o->r_hat_final));
   return 0;
 }
+
+extern "C" int hb_sbayesd(const hb_sbayes_args* a, hb_sbayes_out* o) { return sbayes_host(a, o, false); }
+extern "C" int hb_sbayess(const hb_sbayes_args* a, hb_sbayes_out* o) { return sbayes_host(a, o, true); }

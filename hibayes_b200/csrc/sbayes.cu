@@ -55,6 +55,13 @@ struct LdParams {
   double logpi[HB_MAX_FOLD], vara_fold[HB_MAX_FOLD], fold[HB_MAX_FOLD];
   double vare, dfvara, s2varg, lambda, lambda2;
   hb_key_t key;
+  // SBayesS (sparse-LD variant): per-SNP residual variance varei = varediff_j * vara + vare, re-draws of too large
+  // effects for BayesC/Cpi and BayesR (SBayesS.cpp:131-141, 285, 388-398)
+  int sparse;
+  const double *varediff, *vx;
+  double vara, vary;
+  uint8_t* looped;   // [m] the re-draw loop ran for this SNP in this sweep
+  double* last2;     // [m] square of its last re-draw
   int* q_idx;      // [LB] global SNP index of the tile's changed SNPs
   double* q_dn;    // [LB] (g_old - g_new) * n
   int* q_cnt;
@@ -90,26 +97,30 @@ __device__ double block_sum_256(double v, double* sh) {
 
 __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParams p) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double c_rhs0[LB], c_iv[LB], c_sdz[LB], c_gold[LB], c_delta[LB], c_gnew[LB], red[LB];
+  __shared__ double c_rhs0[LB], c_iv[LB], c_sdz[LB], c_gold[LB], c_delta[LB], c_gnew[LB], red[LB], c_sd[LB], c_vx[LB];
   __shared__ int c_idx[LB], c_cls[LB], wcnt[LB / 32], s_flag;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = p.m, model = p.model, F = p.F;
   const bool dense = (model == HB_MODEL_RR || model == HB_MODEL_A || model == HB_MODEL_L);
   const int nf = (model == HB_MODEL_R) ? F : 2;
   const int T = (m + LB - 1) / LB;
-  const double nscale = p.nscale, vare = p.vare;
+  const double nscale = p.nscale;
+  const bool redraw = p.sparse && (model == HB_MODEL_C || model == HB_MODEL_R);
   int rounds = 0, changed = 0;
   for (int t = 0; t < T; ++t) {
     if (blockIdx.x == 0) {
       // ---------------- phase A: the tile's decisions
       const int j = t * LB + tid;
       const bool act = j < m && p.ifest[j];
-      double xx = 0, gold = 0, rbase = 0, uu = 0.5, zz = 0;
+      double xx = 0, gold = 0, rbase = 0, uu = 0.5, zz = 0, vare = p.vare, vxj = 0;
+      double sd[HB_MAX_FOLD];
+      for (int k = 0; k < HB_MAX_FOLD; ++k) sd[k] = 0;
       double a[HB_MAX_FOLD], c[HB_MAX_FOLD], iv[HB_MAX_FOLD], sdz[HB_MAX_FOLD];
       for (int k = 0; k < HB_MAX_FOLD; ++k) { a[k] = 0; c[k] = 0; iv[k] = 0; sdz[k] = 0; }
       if (act) {
         xx = p.xpx[j];
         gold = p.g[j];
+        if (p.sparse) { vare = p.varediff[j] * p.vara + p.vare; vxj = p.vx[j]; }   // varei
         rbase = __ldcg(p.r_hat + j);
         if (gold != 0.0) rbase += xx * gold;   // :334-335 (every model)
         hb_draw_uz(p.key, HB_DOM_SNP, (uint32_t)p.iter, (uint32_t)j, HB_SL_MAIN, 0, &uu, &zz);
@@ -119,7 +130,8 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
             a[k] = -0.5 * log(vf * (xx / vare) + 1.0) + p.logpi[k];
             c[k] = 0.5 / (vare * v);
             iv[k] = 1.0 / v;
-            sdz[k] = sqrt(vare / v) * zz;
+            sd[k] = sqrt(vare / v);
+            sdz[k] = sd[k] * zz;
           }
         } else {
           double varg = p.vara_fold[1];
@@ -130,7 +142,8 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
           if (model == HB_MODEL_B || model == HB_MODEL_C) a[1] = -0.5 * log(varg * (xx / vare) + 1.0) + p.logpi[1];
           c[1] = 0.5 / (vare * v);
           iv[1] = 1.0 / v;
-          sdz[1] = sqrt(vare / v) * zz;
+          sd[1] = sqrt(vare / v);
+          sdz[1] = sd[1] * zz;
         }
       }
       auto classify = [&](double rhs) -> int { return dense ? 1 : ld_class(nf, rhs * rhs, a, c, p.logpi[0], uu); };
@@ -151,7 +164,7 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
         myrank = pre + __popc(bal & ((1u << lane) - 1u));
         if (cand) {
           c_idx[myrank] = j; c_gold[myrank] = gold; c_cls[myrank] = cls;
-          c_iv[myrank] = iv[cls]; c_sdz[myrank] = sdz[cls]; c_rhs0[myrank] = rbase;
+          c_iv[myrank] = iv[cls]; c_sdz[myrank] = sdz[cls]; c_rhs0[myrank] = rbase; c_sd[myrank] = sd[cls]; c_vx[myrank] = vxj;
         }
         __syncthreads();
         // chain of the candidates in SNP order (one warp): rhs_s = rhs0_s - sum_{s' < s} n LD[c_s, c_s'] delta_s'
@@ -163,6 +176,7 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
             double rhs = valid ? c_rhs0[sidx] : 0.0;
             const double siv = valid ? c_iv[sidx] : 0.0, ssdz = valid ? c_sdz[sidx] : 0.0, sgold = valid ? c_gold[sidx] : 0.0;
             const int scls = valid ? c_cls[sidx] : 0;
+            const double ssd = valid ? c_sd[sidx] : 0.0, svx = valid ? c_vx[sidx] : 0.0;
             for (int sp = 0; sp < sb; ++sp)
               if (valid) rhs = fma(-(nscale * p.ldm[(size_t)c_idx[sp] * m + ji]), c_delta[sp], rhs);
             const int nl = min(32, k - sb);
@@ -170,6 +184,18 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
             for (int lp = 0; lp < nl; ++lp) {
               double gn = (scls > 0) ? fma(rhs, siv, ssdz) : 0.0;
               if (model == HB_MODEL_L && fabs(gn) < 1e-6) gn = 1e-6;   // :373
+              if (redraw && lane == lp && scls > 0 && gn * gn * svx > p.vary) {   // SBayesS.cpp:388-398, 489-499
+                int ii = 0;
+                double l2 = 0.0;
+                while (gn * gn * svx > p.vary) {
+                  gn = fma(rhs, siv, ssd * hb_draw_z(p.key, HB_DOM_SNP, (uint32_t)p.iter, (uint32_t)ji, HB_SL_RETRY, (uint32_t)(ii + 1)));
+                  l2 = gn * gn;
+                  ++ii;
+                  if (ii > 100) gn = 0.0;
+                }
+                p.looped[ji] = 1;
+                p.last2[ji] = l2;
+              }
               const double dl = gn - sgold;
               const double d = __shfl_sync(0xffffffffu, dl, lp);
               const int jc = __shfl_sync(0xffffffffu, ji, lp);
@@ -203,7 +229,7 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
         if (model == HB_MODEL_L) {   // :374-375
           double u2, z2;
           hb_draw_uz(p.key, HB_DOM_SNP, (uint32_t)p.iter, (uint32_t)j, HB_SL_IG, 0, &u2, &z2);
-          const double vargi = 1.0 / hb_invgauss_from_uz(sqrt(vare) * p.lambda / fabs(gnew), p.lambda2, u2, z2);
+          const double vargi = 1.0 / hb_invgauss_from_uz(sqrt(vare) * p.lambda / fabs(gnew), p.lambda2, u2, z2);   // varei in SBayesS
           if (vargi > 0) p.vargL[j] = vargi;
         }
       }
@@ -251,6 +277,25 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
         if (cl > 0) vacc += (model == HB_MODEL_R) ? gj * gj / p.fold[cl] : gj * gj;
       }
     }
+    if (p.sparse && model == HB_MODEL_C) {
+      // SBayesS.cpp:392 overwrites the running sum of squares inside the re-draw loop: the sum restarts at the last
+      // SNP whose loop ran, from the square of its last re-draw
+      int lastj = -1;
+      for (int j = tid; j < m; j += LB) if (p.looped[j]) lastj = j;
+      __shared__ int s_last;
+      if (tid == 0) s_last = -1;
+      __syncthreads();
+      atomicMax(&s_last, lastj);
+      __syncthreads();
+      lastj = s_last;
+      if (lastj >= 0) {
+        vacc = 0.0;
+        for (int j = tid; j < m; j += LB)
+          if (j >= lastj && p.ifest[j] && p.tracker[j] > 0) vacc += p.g[j] * p.g[j];
+        if (tid == 0) vacc += p.last2[lastj];
+      }
+      __syncthreads();
+    }
     for (int k = 0; k < HB_MAX_FOLD; ++k) { const double v = block_sum_256(cnt[k], red); if (tid == 0) p.out->count[k] = v; }
     vacc = block_sum_256(vacc, red); sl = block_sum_256(sl, red); dm = block_sum_256(dm, red); dp = block_sum_256(dp, red);
     if (tid == 0) {
@@ -265,7 +310,9 @@ struct hb_ld_engine {
   int device = 0, m = 0, grid = 1;
   uint64_t seed = 0;
   double *ldm = nullptr, *r_hat = nullptr, *g = nullptr, *vargL = nullptr, *xpx = nullptr, *xy = nullptr, *q_dn = nullptr;
-  uint8_t* ifest = nullptr;
+  uint8_t *ifest = nullptr, *looped = nullptr;
+  double *varediff = nullptr, *vx = nullptr, *last2 = nullptr;
+  bool sparse_ready = false;
   int32_t* tracker = nullptr;
   int *q_idx = nullptr, *q_cnt = nullptr;
   LdOutDev* out = nullptr;
@@ -306,6 +353,7 @@ extern "C" void hb_ld_engine_destroy(hb_ld_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaFree(e->ldm); cudaFree(e->r_hat); cudaFree(e->g); cudaFree(e->vargL); cudaFree(e->xpx); cudaFree(e->xy);
+  cudaFree(e->looped); cudaFree(e->varediff); cudaFree(e->vx); cudaFree(e->last2);
   cudaFree(e->ifest); cudaFree(e->tracker); cudaFree(e->q_idx); cudaFree(e->q_dn); cudaFree(e->q_cnt); cudaFree(e->out);
   if (e->ev[0]) cudaEventDestroy(e->ev[0]);
   if (e->ev[1]) cudaEventDestroy(e->ev[1]);
@@ -328,6 +376,16 @@ extern "C" int hb_ld_engine_set_state(hb_ld_engine* e, const double* xpx, const 
   CU(cudaMemcpy(e->xy, xy, mm * 8, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(e->r_hat, r_hat, mm * 8, cudaMemcpyHostToDevice));
   e->state_ready = true;
+  return 0;
+}
+extern "C" int hb_ld_engine_set_sparse_info(hb_ld_engine* e, const double* varediff, const double* vx) {
+  if (!e || !varediff || !vx) return hb_set_error("hb_ld_engine_set_sparse_info: null argument");
+  CU(cudaSetDevice(e->device));
+  const size_t mm = (size_t)e->m;
+  if (!e->varediff) { CU(cudaMalloc(&e->varediff, mm * 8)); CU(cudaMalloc(&e->vx, mm * 8)); CU(cudaMalloc(&e->last2, mm * 8)); CU(cudaMalloc(&e->looped, mm)); }
+  CU(cudaMemcpy(e->varediff, varediff, mm * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(e->vx, vx, mm * 8, cudaMemcpyHostToDevice));
+  e->sparse_ready = true;
   return 0;
 }
 extern "C" int hb_ld_engine_set_vargL(hb_ld_engine* e, const double* v) {
@@ -355,6 +413,12 @@ extern "C" int hb_ld_engine_sweep(hb_ld_engine* e, const hb_ld_sweep_in* in, hb_
   p.xy = e->xy; p.ifest = e->ifest; p.tracker = e->tracker; p.iter = in->iter; p.model = in->model_index; p.F = in->n_fold;
   for (int k = 0; k < HB_MAX_FOLD; ++k) { p.logpi[k] = in->logpi[k]; p.vara_fold[k] = in->vara_fold[k]; p.fold[k] = in->fold[k]; }
   p.vare = in->vare; p.dfvara = in->dfvara; p.s2varg = in->s2varg; p.lambda = in->lambda; p.lambda2 = in->lambda2;
+  p.sparse = in->sparse_mode ? 1 : 0; p.vara = in->vara; p.vary = in->vary;
+  if (p.sparse) {
+    if (!e->sparse_ready) return hb_set_error("hb_ld_engine_sweep: sparse_mode without hb_ld_engine_set_sparse_info");
+    p.varediff = e->varediff; p.vx = e->vx; p.looped = e->looped; p.last2 = e->last2;
+    CU(cudaMemsetAsync(e->looped, 0, (size_t)e->m, e->stream));
+  }
   p.key = hb_make_key(e->seed); p.q_idx = e->q_idx; p.q_dn = e->q_dn; p.q_cnt = e->q_cnt; p.out = e->out;
   void* args[] = {(void*)&p};
   CU(cudaEventRecord(e->ev[0], e->stream));

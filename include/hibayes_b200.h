@@ -209,6 +209,7 @@ int hb_ld_engine_load_dense(hb_ld_engine* e, const double* ldm);   /* m x m colu
 /* xpx_j = n * LD_jj (:93-96), ifest (:100-103), xy (:104), initial r_hat (:105) */
 int hb_ld_engine_set_state(hb_ld_engine* e, const double* xpx, const uint8_t* ifest, const double* xy, const double* r_hat);
 int hb_ld_engine_set_vargL(hb_ld_engine* e, const double* vargL);
+int hb_ld_engine_set_sparse_info(hb_ld_engine* e, const double* varediff, const double* vx);
 int hb_ld_engine_get(hb_ld_engine* e, double* g, int32_t* tracker, double* r_hat);   /* any of them may be NULL */
 
 typedef struct {
@@ -216,6 +217,10 @@ typedef struct {
   double fold[HB_MAX_FOLD], logpi[HB_MAX_FOLD], vara_fold[HB_MAX_FOLD];   /* as hb_sweep_in */
   double vare, dfvara, s2varg, lambda, lambda2;
   double nscale;               /* n = int(mean(N)), :34 */
+  /* SBayesS (SBayesS.cpp:131-141, 285, 388-398): per-SNP residual variance varediff_j * vara + vare and the re-draw
+   * of effects with g^2 vx_j > vary; needs hb_ld_engine_set_sparse_info() */
+  int sparse_mode;
+  double vara, vary;
 } hb_ld_sweep_in;
 typedef struct {
   double count[HB_MAX_FOLD];   /* estimated SNPs per class */
@@ -243,6 +248,8 @@ typedef struct {
   int outfreq, verbose;
   uint64_t seed;
   int device;
+  /* hb_sbayess(): the LD matrix as arma::sp_mat / dgCMatrix (CSC, m columns); ldm = NULL */
+  const int32_t* ld_colptr; const int32_t* ld_rowidx; const double* ld_val;
 } hb_sbayes_args;
 typedef struct {
   double Vg, Ve, h2;
@@ -255,6 +262,10 @@ typedef struct {
   double seconds_sweep;
 } hb_sbayes_out;
 int hb_sbayesd(const hb_sbayes_args* a, hb_sbayes_out* o);
+/* drop-in for the body of  Rcpp::List SBayesS(...)  (/root/reference/src/SBayesS.cpp:21-40): sparse LD matrix.  The
+ * device copy of the LD matrix is dense in this build (the column updates then add zeros where the sparse matrix
+ * has no entry: same results); m is therefore limited by m*m*8 bytes of HBM. */
+int hb_sbayess(const hb_sbayes_args* a, hb_sbayes_out* o);
 
 #ifdef __cplusplus
 }

@@ -812,8 +812,12 @@ double hbo_time_sweep_fp64(int n, int m_cpu, int sweeps, int threads, uint64_t s
  * genetic variance (:461) and HB_IT_VARE for the residual variance (:467).
  * ============================================================================================ */
 #define HB_ORACLE_MAX_FOLD 16
-int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o) {
+/* sparse = 1: SBayesS.cpp -- the LD matrix is a sparse column-compressed matrix, the residual variance of SNP i is
+ * inflated to varei = varediff_i * vara + vare (:131-141, :285), and BayesC/Cpi and BayesR re-draw effects that would
+ * explain more than the phenotypic variance (:388-398, :489-499; note `vargi = gi * gi` inside that loop, kept). */
+static int sbayes_impl(const hbo_sbayes_args* a, hbo_sbayes_out* o, int sparse) {
   if (!a || !o) return fail("null argument");
+  if (sparse ? !(a->ld_colptr && a->ld_rowidx && a->ld_val) : !a->ldm) return fail("LD matrix missing");
   KEY = hb_make_key(a->seed);
   const int m = a->m;
   const char* model = a->model;
@@ -858,7 +862,22 @@ int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o) {
   double* nzrate = calloc(m, 8); double* gsum = calloc(m, 8); double* vargL = calloc(m, 8);
   uint8_t* ifest = malloc(m);
   const double* ldm = a->ldm;
-  for (int i = 0; i < m; ++i) { vx[i] = ldm[(size_t)i * m + i]; xpx[i] = vx[i] * n; }   /* :92-96 */
+  double* varediff = calloc(m, 8);
+  for (int i = 0; i < m; ++i) {   /* :92-96 (SBayesS :109-113, :131-141) */
+    if (sparse) {
+      vx[i] = 0.0;
+      for (int q = a->ld_colptr[i]; q < a->ld_colptr[i + 1]; ++q) if (a->ld_rowidx[q] == i) vx[i] = a->ld_val[q];
+      varediff[i] = (m - (double)(a->ld_colptr[i + 1] - a->ld_colptr[i])) / m;
+    } else vx[i] = ldm[(size_t)i * m + i];
+    xpx[i] = vx[i] * n;
+  }
+#define LD_UPDATE(i, gi_) do { if (sparse) { for (int q_ = a->ld_colptr[i]; q_ < a->ld_colptr[(i) + 1]; ++q_) r_hat[a->ld_rowidx[q_]] += (gi_) * a->ld_val[q_]; } \
+                               else daxpy(m, (gi_), ldm + (size_t)(i) * m, r_hat); } while (0)
+#define VAREI(i) (sparse ? varediff[i] * vara_ + vare_ : vare_)
+/* SBayesS.cpp:388-398 / :489-499 */
+#define REDRAW_LOOP(i) do { if (sparse && (gi * gi * vx[i]) > vary) { int ii = 0; \
+    while ((gi * gi * vx[i]) > vary) { gi = rhs / v + sqrt(varei / v) * hb_draw_z(KEY, HB_DOM_SNP, it, (uint32_t)(i), HB_SL_RETRY, (uint32_t)(ii + 1)); \
+      vargi = gi * gi; ii++; if (ii > 100) gi = 0; } } } while (0)
   int count_y = 0, nvar0 = 0;
   for (int k = 0; k < m; ++k) {   /* :100-112 */
     ifest[k] = 1;
@@ -906,12 +925,13 @@ int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o) {
       case 1: /* :254-270 */
         for (int i = 0; i < m; ++i) {
           if (!ifest[i]) continue;
+          const double varei = VAREI(i);
           xx = xpx[i]; gi = g[i]; rhs = r_hat[i];
           if (gi) rhs += xx * gi;
-          v = xx + vare_ / varg;
-          gi = norm_at(HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, rhs / v, sqrt(vare_ / v));
+          v = xx + varei / varg;
+          gi = norm_at(HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, rhs / v, sqrt(varei / v));
           gi_ = (g[i] - gi) * n;
-          daxpy(m, gi_, ldm + (size_t)i * m, r_hat);
+          LD_UPDATE(i, gi_);
           g[i] = gi;
         }
         varg = (ddot(m, g, g) + s2varg_ * dfvara_) / chisq_at(HB_DOM_ITER, it, HB_IT_VARG, 0, dfvara_ + count_y);
@@ -919,14 +939,15 @@ int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o) {
       case 2: /* :273-289 */
         for (int i = 0; i < m; ++i) {
           if (!ifest[i]) continue;
+          const double varei = VAREI(i);
           xx = xpx[i]; gi = g[i];
           varg = (gi * gi + s2varg_ * dfvara_) / chisq_at(HB_DOM_SNP, it, (uint32_t)i, HB_SL_CHI, dfvara_ + 1);
           rhs = r_hat[i];
           if (gi) rhs += xx * gi;
-          v = xx + vare_ / varg;
-          gi = norm_at(HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, rhs / v, sqrt(vare_ / v));
+          v = xx + varei / varg;
+          gi = norm_at(HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, rhs / v, sqrt(varei / v));
           gi_ = (g[i] - gi) * n;
-          daxpy(m, gi_, ldm + (size_t)i * m, r_hat);
+          LD_UPDATE(i, gi_);
           g[i] = gi;
         }
         break;
@@ -936,15 +957,16 @@ int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o) {
         vargi = 0;
         for (int i = 0; i < m; ++i) {
           if (!ifest[i]) continue;
+          const double varei = VAREI(i);
           xx = xpx[i]; gi = g[i];
           if (model_index == 3)
             varg = (gi * gi + s2varg_ * dfvara_) / chisq_at(HB_DOM_SNP, it, (uint32_t)i, HB_SL_CHI, dfvara_ + 1);
           rhs = r_hat[i];
           if (gi) rhs += xx * gi;
-          lhs = xx / vare_;
+          lhs = xx / varei;
           logdetV = log(varg * lhs + 1);
-          uhat = rhs / (xx + vare_ / varg);
-          s[1] = -0.5 * (logdetV - (rhs * uhat / vare_)) + logpi[1];
+          uhat = rhs / (xx + varei / varg);
+          s[1] = -0.5 * (logdetV - (rhs * uhat / varei)) + logpi[1];
           acceptProb = 1 / (exp(s[0] - s[0]) + exp(s[1] - s[0]));
           double rval, zval;
           hb_draw_uz(KEY, HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, 0, &rval, &zval);
@@ -952,13 +974,13 @@ int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o) {
           snptracker[i] = indistflag;
           if (indistflag == 0) gi = 0;
           else {
-            v = xx + vare_ / varg;
-            gi = rhs / v + sqrt(vare_ / v) * zval;
-            if (model_index == 4) vargi += gi * gi;
+            v = xx + varei / varg;
+            gi = rhs / v + sqrt(varei / v) * zval;
+            if (model_index == 4) { REDRAW_LOOP(i); vargi += gi * gi; }
           }
           if (gi != g[i]) {
             gi_ = (g[i] - gi) * n;
-            daxpy(m, gi_, ldm + (size_t)i * m, r_hat);
+            LD_UPDATE(i, gi_);
             g[i] = gi;
           }
         }
@@ -976,18 +998,19 @@ int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o) {
       case 5: /* :365-389 */
         for (int i = 0; i < m; ++i) {
           if (!ifest[i]) continue;
+          const double varei = VAREI(i);
           xx = xpx[i]; gi = g[i]; rhs = r_hat[i];
           if (gi) rhs += xx * gi;
           v = xx + 1 / vargL[i];
-          gi = norm_at(HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, rhs / v, sqrt(vare_ / v));
+          gi = norm_at(HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, rhs / v, sqrt(varei / v));
           if (fabs(gi) < 1e-6) gi = 1e-6;
           { double uu, zz;
             hb_draw_uz(KEY, HB_DOM_SNP, it, (uint32_t)i, HB_SL_IG, 0, &uu, &zz);
-            vargi = 1 / hb_invgauss_from_uz(sqrt(vare_) * lambda / fabs(gi), lambda2, uu, zz); }
+            vargi = 1 / hb_invgauss_from_uz(sqrt(varei) * lambda / fabs(gi), lambda2, uu, zz); }
           if (vargi > 0) vargL[i] = vargi;
           if (gi != g[i]) {
             gi_ = (g[i] - gi) * n;
-            daxpy(m, gi_, ldm + (size_t)i * m, r_hat);
+            LD_UPDATE(i, gi_);
             g[i] = gi;
           }
         }
@@ -1002,13 +1025,14 @@ int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o) {
         for (int j = 1; j < n_fold; ++j) vare_vara_fold[j] = vare_ / vara_fold[j];
         for (int i = 0; i < m; ++i) {
           if (!ifest[i]) continue;
+          const double varei = VAREI(i);
           xx = xpx[i]; gi = g[i]; rhs = r_hat[i];
           if (gi) rhs += xx * gi;
-          lhs = xx / vare_;
+          lhs = xx / varei;
           for (int j = 1; j < n_fold; ++j) {
             logdetV = log(vara_fold[j] * lhs + 1);
-            uhat = rhs / (xx + vare_vara_fold[j]);
-            s[j] = -0.5 * (logdetV - (rhs * uhat / vare_)) + logpi[j];
+            uhat = rhs / (xx + varei / vara_fold[j]);
+            s[j] = -0.5 * (logdetV - (rhs * uhat / varei)) + logpi[j];
           }
           for (int j = 0; j < n_fold; ++j) {
             double temp = 0.0;
@@ -1022,13 +1046,14 @@ int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o) {
           snptracker[i] = indistflag;
           if (indistflag == 0) gi = 0;
           else {
-            v = xx + vare_vara_fold[indistflag];
-            gi = rhs / v + sqrt(vare_ / v) * zval;
+            v = xx + varei / vara_fold[indistflag];
+            gi = rhs / v + sqrt(varei / v) * zval;
+            REDRAW_LOOP(i);
             varg += (gi * gi / fold_[indistflag]);
           }
           if (gi != g[i]) {
             gi_ = (g[i] - gi) * n;
-            daxpy(m, gi_, ldm + (size_t)i * m, r_hat);
+            LD_UPDATE(i, gi_);
             g[i] = gi;
           }
         }
@@ -1100,7 +1125,13 @@ int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o) {
   }
   if (o->r_hat_final) memcpy(o->r_hat_final, r_hat, 8 * (size_t)m);
   free(xy); free(r_hat); free(tmp); free(yyi); free(g); free(xpx); free(vx); free(snptracker); free(nzrate); free(gsum);
-  free(vargL); free(ifest); free(wppai);
+  free(vargL); free(ifest); free(wppai); free(varediff);
 #undef SS
+#undef LD_UPDATE
+#undef VAREI
+#undef REDRAW_LOOP
   return 0;
 }
+
+int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o) { return sbayes_impl(a, o, 0); }
+int hbo_sbayess(const hbo_sbayes_args* a, hbo_sbayes_out* o) { return sbayes_impl(a, o, 1); }

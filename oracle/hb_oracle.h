@@ -115,7 +115,7 @@ double hbo_time_sweep_fp64(int n, int m_cpu, int sweeps, int threads, uint64_t s
 typedef struct {
   int m;
   const double* sumstat;  /* m x 4 column-major: MAF, BETA, SE, N (R/sbayes.r:209); NaN = NA */
-  const double* ldm;      /* m x m column-major */
+  const double* ldm;      /* m x m column-major (SBayesD) or NULL */
   const char* model;
   int n_fold;
   const double* Pi;
@@ -124,6 +124,8 @@ typedef struct {
   double vg, dfvg, s2vg, ve, dfve, s2ve;   /* NaN = not given */
   const int32_t* windindx;                 /* m, 1-based, or NULL */
   uint64_t seed;
+  /* SBayesS: the LD matrix as arma::sp_mat / dgCMatrix (CSC, row indices ascending); ldm = NULL */
+  const int32_t* ld_colptr; const int32_t* ld_rowidx; const double* ld_val;
 } hbo_sbayes_args;
 
 typedef struct {
@@ -140,3 +142,5 @@ typedef struct {
 } hbo_sbayes_out;
 
 int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o);
+/* SBayesS: sparse-LD variant (/root/reference/src/SBayesS.cpp:21-679) */
+int hbo_sbayess(const hbo_sbayes_args* a, hbo_sbayes_out* o);

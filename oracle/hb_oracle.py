@@ -204,7 +204,8 @@ class _SBayesArgs(C.Structure):
     _fields_ = [("m", C.c_int), ("sumstat", C.c_void_p), ("ldm", C.c_void_p), ("model", C.c_char_p), ("n_fold", C.c_int),
                 ("Pi", C.c_void_p), ("fold", C.c_void_p), ("niter", C.c_int), ("nburn", C.c_int), ("thin", C.c_int),
                 ("vg", C.c_double), ("dfvg", C.c_double), ("s2vg", C.c_double), ("ve", C.c_double), ("dfve", C.c_double),
-                ("s2ve", C.c_double), ("windindx", C.c_void_p), ("seed", C.c_uint64)]
+                ("s2ve", C.c_double), ("windindx", C.c_void_p), ("seed", C.c_uint64),
+                ("ld_colptr", C.c_void_p), ("ld_rowidx", C.c_void_p), ("ld_val", C.c_void_p)]
 
 
 class _SBayesOut(C.Structure):
@@ -238,33 +239,59 @@ def sbayes_buffers(m, F, niter, nburn, thin, nw, out_struct):
     return res, mc, dg
 
 
-def sbayesd(sumstat, ldm, model, Pi, fold=None, niter=200, nburn=100, thin=5, windindx=None, vg=None, dfvg=None, s2vg=None,
-            ve=None, dfve=None, s2ve=None, seed=666666):
-    """CPU oracle of SBayesD(): sumstat m x 4 (MAF, BETA, SE, N), ldm m x m."""
+def _sbayes(sumstat, ldm, sparse, model, Pi, fold, niter, nburn, thin, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, seed):
     L = lib()
     ss = np.asfortranarray(sumstat, dtype=np.float64)
-    ld = np.asfortranarray(ldm, dtype=np.float64)
-    m = ld.shape[0]
+    keep = [ss]
+    a = _SBayesArgs()
+    if sparse:
+        import scipy.sparse as sp
+        G = sp.csc_matrix(ldm)
+        G.sort_indices()
+        G.eliminate_zeros()
+        cp = np.ascontiguousarray(G.indptr, dtype=np.int32)
+        ri = np.ascontiguousarray(G.indices, dtype=np.int32)
+        gv = np.ascontiguousarray(G.data, dtype=np.float64)
+        a.ld_colptr, a.ld_rowidx, a.ld_val = cp.ctypes.data, ri.ctypes.data, gv.ctypes.data
+        keep += [cp, ri, gv]
+        m = G.shape[0]
+    else:
+        ld = np.asfortranarray(ldm, dtype=np.float64)
+        a.ldm = ld.ctypes.data
+        keep.append(ld)
+        m = ld.shape[0]
     Pi = np.ascontiguousarray(Pi, dtype=np.float64)
     F = Pi.shape[0]
     fo = None if fold is None else np.ascontiguousarray(fold, dtype=np.float64)
-    a = _SBayesArgs()
-    a.m, a.sumstat, a.ldm, a.model, a.n_fold, a.Pi, a.fold = m, ss.ctypes.data, ld.ctypes.data, model.encode(), F, Pi.ctypes.data, _ptr(fo)
+    a.m, a.sumstat, a.model, a.n_fold, a.Pi, a.fold = m, ss.ctypes.data, model.encode(), F, Pi.ctypes.data, _ptr(fo)
     a.niter, a.nburn, a.thin = niter, nburn, thin
     a.vg, a.dfvg, a.s2vg, a.ve, a.dfve, a.s2ve = _nan(vg), _nan(dfvg), _nan(s2vg), _nan(ve), _nan(dfve), _nan(s2ve)
     nw = 0
-    w = None
     if windindx is not None:
         w = np.ascontiguousarray(windindx, dtype=np.int32)
         nw = int(w.max())
         a.windindx = w.ctypes.data
+        keep.append(w)
     a.seed = seed
     o = _SBayesOut()
     res, mc, dg = sbayes_buffers(m, F, niter, nburn, thin, nw, o)
-    L.hbo_sbayesd.restype = C.c_int
-    if L.hbo_sbayesd(C.byref(a), C.byref(o)) != 0:
+    fn = L.hbo_sbayess if sparse else L.hbo_sbayesd
+    fn.restype = C.c_int
+    if fn(C.byref(a), C.byref(o)) != 0:
         raise RuntimeError(L.hbo_last_error().decode())
     res.update({"Vg": o.Vg, "Ve": o.Ve, "h2": o.h2, "MCMCsamples": mc})
     dg.update({"n_records": o.n_records_done, "nzct": o.nzct, "iters_done": o.iters_done, "n_used": o.n_used})
     res["diag"] = dg
     return res
+
+
+def sbayesd(sumstat, ldm, model, Pi, fold=None, niter=200, nburn=100, thin=5, windindx=None, vg=None, dfvg=None, s2vg=None,
+            ve=None, dfve=None, s2ve=None, seed=666666):
+    """CPU oracle of SBayesD(): sumstat m x 4 (MAF, BETA, SE, N), ldm m x m dense."""
+    return _sbayes(sumstat, ldm, False, model, Pi, fold, niter, nburn, thin, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, seed)
+
+
+def sbayess(sumstat, ldm, model, Pi, fold=None, niter=200, nburn=100, thin=5, windindx=None, vg=None, dfvg=None, s2vg=None,
+            ve=None, dfve=None, s2ve=None, seed=666666):
+    """CPU oracle of SBayesS(): ldm a scipy sparse matrix (or anything csc_matrix() accepts)."""
+    return _sbayes(sumstat, ldm, True, model, Pi, fold, niter, nburn, thin, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, seed)

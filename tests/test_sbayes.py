@@ -78,3 +78,57 @@ def test_sbayesd_na_rows_windows_ragged(oracle):
     _compare(got, ref)
     assert np.array_equal(got["diag"]["wppa_count"], ref["diag"]["wppa_count"])
     assert np.array_equal(got["gwas"], ref["gwas"])
+
+
+def _sparse_ld(ld, n, chisq=10.0):
+    """ldmat(..., chisq=) style sparsification (tXXmat.cpp:146-153): keep r^2 * n > chisq and the diagonal."""
+    import scipy.sparse as sp
+    d = np.sqrt(np.clip(np.diag(ld), 1e-300, None))
+    r2 = (ld / d[:, None] / d[None, :]) ** 2
+    keep = (r2 * n > chisq) | np.eye(ld.shape[0], dtype=bool)
+    return sp.csc_matrix(np.where(keep, ld, 0.0))
+
+
+def test_oracle_sbayess_differs_from_dense_only_through_its_own_rules(oracle):
+    y, X = synth(900, 250, seed=4, n_causal=8)
+    ss, ld = make_sumstat(y, X)
+    import scipy.sparse as sp
+    kw = dict(niter=30, nburn=10, thin=5, seed=3)
+    full = oracle.sbayess(ss, sp.csc_matrix(ld), "BayesCpi", [0.9, 0.1], **kw)
+    dense = oracle.sbayesd(ss, ld, "BayesCpi", [0.9, 0.1], **kw)
+    # a sparse matrix that stores every entry has varediff = 0: SBayesS then equals SBayesD unless a re-draw happens
+    assert np.array_equal(full["diag"]["tracker"], dense["diag"]["tracker"])
+    assert np.allclose(full["alpha"], dense["alpha"], rtol=1e-12, atol=1e-15)
+    sparse = oracle.sbayess(ss, _sparse_ld(ld, 900), "BayesCpi", [0.9, 0.1], **kw)
+    assert sparse["Ve"] > 0 and not np.allclose(sparse["alpha"], dense["alpha"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,Pi,fold", MODELS)
+def test_sbayess_all_models(oracle, model, Pi, fold):
+    """Every model string with a sparsified LD matrix (n > m so that the thresholded matrix stays well conditioned)."""
+    import hibayes_b200 as hb
+    y, X = synth(1500, 400, seed=23, n_causal=10)
+    ss, ld = make_sumstat(y, X)
+    sld = _sparse_ld(ld, len(y))
+    kw = dict(niter=60, nburn=30, thin=5, seed=4242)
+    ref = oracle.sbayess(ss, sld, model, Pi, fold=fold, **kw)
+    assert np.all(np.isfinite(ref["alpha"])) and np.isfinite(ref["Ve"])
+    got = hb.SBayesS(ss, sld, model, Pi, fold=fold, **kw)
+    _compare(got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,Pi,fold", [("BayesCpi", [0.5, 0.5], None), ("BayesR", [0.4, 0.2, 0.2, 0.2], [0, 1e-3, 1e-2, 1e-1])])
+def test_sbayess_redraw_loop(oracle, model, Pi, fold):
+    """Inflated marginal effects make g^2 vx exceed the phenotypic variance: the re-draw loop of SBayesS.cpp:388-398
+    (including its give-up after 100 tries and the overwritten sum of squares) must agree with the oracle."""
+    import hibayes_b200 as hb
+    y, X = synth(600, 200, seed=9, n_causal=5)
+    ss, ld = make_sumstat(y, X)
+    ss[[17, 90, 150], 1] *= 40.0
+    sld = _sparse_ld(ld, 600, chisq=5.0)
+    kw = dict(niter=30, nburn=10, thin=4, seed=77)
+    ref = oracle.sbayess(ss, sld, model, Pi, fold=fold, **kw)
+    got = hb.SBayesS(ss, sld, model, Pi, fold=fold, **kw)
+    _compare(got, ref)
