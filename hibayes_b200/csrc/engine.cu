@@ -617,7 +617,7 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   e->n = cfg->n; e->m = cfg->m;
   e->nsm = prop.multiProcessorCount;
   e->B = cfg->tile_snps > 0 ? cfg->tile_snps : 256;
-  e->D = cfg->lag_tiles > 0 ? cfg->lag_tiles : 4;
+  e->D = cfg->lag_tiles > 0 ? cfg->lag_tiles : 5;
   if (e->B != 64 && e->B != 128 && e->B != 256) { delete e; return hb_set_error("tile_snps must be 64, 128 or 256"); }
   if (e->D > 8) { delete e; return hb_set_error("lag_tiles must be <= 8"); }
   e->NG = 8;   // scalar CTAs (one worker each)

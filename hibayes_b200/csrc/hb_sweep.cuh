@@ -527,7 +527,7 @@ __device__ void solve_thresholds(int nf, double u, const double* a, const double
 // candidate arrays of a worker (B entries each)
 struct CandSet {
   double *rhs0, *iv, *sdz, *gold, *delta, *gnew;
-  int *idx, *cls;
+  int *idx, *cls, *slot;   // slot = row of the candidate in the row buffers
 };
 
 __device__ __forceinline__ CandSet make_candset(uint8_t* smem, int B) {
@@ -535,7 +535,7 @@ __device__ __forceinline__ CandSet make_candset(uint8_t* smem, int B) {
   double* d = (double*)smem;
   cs.rhs0 = d; cs.iv = d + B; cs.sdz = d + 2 * B; cs.gold = d + 3 * B; cs.delta = d + 4 * B; cs.gnew = d + 5 * B;
   int* ip = (int*)(d + 8 * (size_t)B);
-  cs.idx = ip; cs.cls = ip + B;
+  cs.idx = ip; cs.cls = ip + B; cs.slot = ip + 2 * B;
   return cs;
 }
 
@@ -543,7 +543,7 @@ __device__ __forceinline__ CandSet make_candset(uint8_t* smem, int B) {
 // the tile's candidates (exact int32, as stored): rows0 = diagonal block, rows1 = block
 // towards the next tile.
 __host__ __device__ inline size_t scalar_fixed_bytes(int B) {
-  size_t b = (8 * (size_t)B) * 8 + (3 * (size_t)B + 64 + 16) * 4 + 18 * 8 + 64;   // candidates + partials, ints, timers
+  size_t b = (8 * (size_t)B) * 8 + (6 * (size_t)B + 64 + 16) * 4 + 18 * 8 + 64;   // candidates + partials, ints, timers
   return (b + 127) / 128 * 128;
 }
 __host__ inline int scalar_krow(int B) {
@@ -592,7 +592,7 @@ __device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const
     const double niv = -iv;
     double e = valid ? fma(cs.rhs0[sidx], iv, cs.sdz[sidx]) - gold : 0.0;
     auto gval = [&](int sp) -> double {
-      return gram_as_double(ROWS ? rows[(size_t)sp * B + ci] : __ldcg(G + (size_t)cs.idx[sp] * B + ci));
+      return gram_as_double(ROWS ? rows[(size_t)cs.slot[sp] * B + ci] : __ldcg(G + (size_t)cs.idx[sp] * B + ci));
     };
     // candidates of earlier chunks: their changes are final
     for (int sp = 0; sp < sb; sp += 8) {
@@ -614,7 +614,7 @@ __device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const
           for (int q = 0; q < 16; ++q) {
             const int lp = 16 * hc + q;
             const int row = min(sb + lp, k - 1);
-            const double gv = gram_as_double(rows[(size_t)row * B + ci]) * niv;
+            const double gv = gram_as_double(rows[(size_t)cs.slot[row] * B + ci]) * niv;
             hreg[q] = (valid && lp < lane && lp < nl) ? gv : 0.0;
           }
 #pragma unroll
@@ -658,7 +658,7 @@ __device__ void solve_candidates(const CandSet& cs, int k, const int32_t* __rest
     const double iv = valid ? cs.iv[sidx] : 0.0, sdz = valid ? cs.sdz[sidx] : 0.0, gold = valid ? cs.gold[sidx] : 0.0;
     const int cls = valid ? cs.cls[sidx] : 0;
     auto gval = [&](int sp) -> double {
-      return gram_as_double(ROWS ? rows[(size_t)sp * B + ci] : __ldcg(G + (size_t)cs.idx[sp] * B + ci));
+      return gram_as_double(ROWS ? rows[(size_t)cs.slot[sp] * B + ci] : __ldcg(G + (size_t)cs.idx[sp] * B + ci));
     };
     for (int sp = 0; sp < sb; sp += 8) {
       double gv[8];
@@ -763,6 +763,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
   CandSet cs;
   double *part_rhs, *part_corr;   // secondary half's partial sums
   int *wcnt, *rank_sh;            // rank_sh[i] = number of candidates before SNP i
+  int *slot_of, *slot_snp;        // row buffers: slot of SNP i (-1: none), SNP of a slot
   volatile int* gctl;             // [0] abort flag, [1] number of candidates
   long long* phase;
   int32_t *rows0, *rows1;
@@ -772,7 +773,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     part_rhs = d + 6 * B; part_corr = d + 7 * B;
     d += 8 * (size_t)B;
     int* ip = (int*)d;
-    rank_sh = ip + 2 * B; ip += 3 * (size_t)B;
+    rank_sh = ip + 3 * B; slot_of = ip + 4 * B; slot_snp = ip + 5 * B; ip += 6 * (size_t)B;
     wcnt = ip; ip += 64;
     gctl = ip; ip += 16;
     phase = (long long*)ip;
@@ -791,7 +792,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
   const bool use_thr = p.use_thr && !dense;
   const int DC = D - 1;   // correction slots per tile
   bool dead = false;
-  int rounds_total = 0, changed_total = 0, respec = 0;
+  int rounds_total = 0, changed_total = 0, respec = 0, widen = 0;
 
   long long* pc = phase;   // [16] = last time stamp
   if (tid == 0) { for (int k = 0; k < 16; ++k) pc[k] = 0; pc[16] = clock64(); }
@@ -908,9 +909,43 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     bool cand = false, fast = false;
     const bool has1 = (D > 1 && t + 1 < T);
     const int32_t* G0 = p.gram + ((size_t)t * D) * B * B;
-    // candidate list of the speculated classes and their Gram rows
+    // Row buffers: the Gram rows of every SNP that is, or may soon become, a candidate (effect not zero, class not
+    // zero, or right-hand side within 30 % of its first class boundary) are gathered once, as soon as the dots are
+    // there; candidate lists are then rebuilt from these rows without touching memory again.
+    bool extra = false;   // candidate that had no row yet
+    int ns = 0;
+    // `widen`: the wider row set is only worth its gather while speculation keeps missing (chains far from
+    // equilibrium, very large n); every tile that needed a second look switches it on for this worker's next 16 tiles
+    auto select_rows = [&](double rr_spec) {
+      if (prim) {
+        const bool near = widen > 0 && use_thr && TH[0] > 0.0 && TH[0] < 1e300 && rr_spec >= 0.49 * TH[0];
+        const bool want = act && (dense || gold != 0.0 || cls > 0 || near || extra);
+        const unsigned bal = __ballot_sync(0xffffffffu, want);
+        if (lane == 0) wcnt[warp] = __popc(bal);
+        hb::named_bar_sync(4, B);   // primary half only
+        int pre = 0, tot = 0;
+        for (int w = 0; w < nwarp; ++w) {
+          const int c = wcnt[w];
+          if (w < warp) pre += c;
+          tot += c;
+        }
+        const int sl = pre + __popc(bal & ((1u << lane) - 1u));
+        slot_of[i] = want ? sl : -1;
+        if (want) slot_snp[sl] = i;
+        if (i == 0) gctl[2] = tot;
+      }
+      hb::named_bar_sync(1, NT2);
+      ns = gctl[2];
+      fast = (ns <= KROW);
+      if (fast) {
+        if (prim) gather_rows(rows0, G0, slot_snp, ns, B, i);
+        else if (has1) gather_rows(rows1, G0 + (size_t)B * B, slot_snp, ns, B, i);
+      }
+    };
+    // candidate list of the current classes
     auto compact = [&]() {
       cand = act && (cls > 0 || gold != 0.0);
+      bool missing = false;
       if (prim) {
         const unsigned bal = __ballot_sync(0xffffffffu, cand);
         if (lane == 0) wcnt[warp] = __popc(bal);
@@ -929,6 +964,8 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
           cs.idx[myrank] = i;
           cs.gold[myrank] = gold;
           cs.cls[myrank] = cls;
+          cs.slot[myrank] = slot_of[i];
+          missing = slot_of[i] < 0;
           double iv = 0.0, sdz = 0.0;
 #pragma unroll
           for (int kk = 1; kk < NF; ++kk)
@@ -937,14 +974,16 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
           cs.sdz[myrank] = sdz;
         }
       }
-      hb::named_bar_sync(1, NT2);
-      if (!prim) { k = gctl[1]; myrank = rank_sh[i]; }
-      fast = (k <= KROW);
-      if (fast) {
-        if (prim) gather_rows(rows0, G0, cs.idx, k, B, i);
-        else if (has1) gather_rows(rows1, G0 + (size_t)B * B, cs.idx, k, B, i);
+      if (hb::named_bar_or(1, NT2, missing && fast)) {
+        // a candidate without a row (rare): gather again with it included
+        extra = extra || missing;
+        select_rows(0.0);
+        if (prim && cand) cs.slot[myrank] = slot_of[i];
+        hb::named_bar_sync(1, NT2);
       }
+      if (!prim) { k = gctl[1]; myrank = rank_sh[i]; }
     };
+    select_rows(act ? ((base0 - cspec) + addback) * ((base0 - cspec) + addback) : 0.0);
     compact();
     HB_PHASE(1);
     if (tid == 0) HB_TRACE(t, 1);
@@ -966,6 +1005,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     if (tid == 0) HB_TRACE(t, 2);
     const double rhs0 = ((base0 - cold) - c1) + addback;
     int nrounds = 0;
+    bool respec_tile = false;
     double corr1 = 0.0;
     for (;;) {
       ++nrounds;
@@ -982,6 +1022,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
         if (cand && prim) cs.rhs0[myrank] = rhs0;
         hb::named_bar_sync(1, NT2);
         ++respec;
+        respec_tile = true;
       }
       HB_PHASE(3);
       double prhs = 0.0, pcorr = 0.0;
@@ -999,7 +1040,8 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
 #pragma unroll 4
         for (int sidx = h; sidx < k; sidx += 2) {
           const double d = cs.delta[sidx];
-          const double g0 = gram_as_double(rows0[(size_t)sidx * B + i]), g1 = gram_as_double(rows1[(size_t)sidx * B + i]);
+          const int sl = cs.slot[sidx];
+          const double g0 = gram_as_double(rows0[(size_t)sl * B + i]), g1 = gram_as_double(rows1[(size_t)sl * B + i]);
           prhs = fma(sidx < myrank ? g0 : 0.0, d, prhs);
           pcorr = fma(has1 ? g1 : 0.0, d, pcorr);
         }
@@ -1040,6 +1082,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     if (dead) break;
     rounds_total += nrounds;
     changed_total += k;
+    widen = (nrounds > 1 || respec_tile) ? 16 : max(widen - 1, 0);
     // ---- the tile is final.  First what the next tile waits for: its corrections (dt = 1)
     if (has1 && prim) post_corr(p.corr + ((size_t)(t + 1) * DC) * B + i, corr1);
     HB_PHASE(6);

@@ -47,7 +47,7 @@ typedef struct {
   int n;             /* individuals held by this engine (rows of X, y) */
   int m;             /* SNPs (columns of X) */
   int tile_snps;     /* B: SNPs per tile step (64, 128 or 256); 0 = default (256) */
-  int lag_tiles;     /* D: tiles in flight between a dot and its residual update; 0 = default */
+  int lag_tiles;     /* D: tiles in flight between a dot and its residual update (1..8); 0 = default (5) */
   int n_slabs;       /* row slabs = streaming CTAs; 0 = default (SM count - 1, fewer for small n) */
   uint64_t seed;     /* Philox run key (hb_rng.h) */
   /* row sharding across ranks (one engine per GPU); world = 1 for a single GPU */

@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+cp hibayes_b200/libhibayes_b200.so /tmp/lib_cur.so
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/ab.txt
+for v in old new old new; do
+  cp ab/lib_$v.so hibayes_b200/libhibayes_b200.so
+  python bench.py --no-cpu --steps 10 --warmup 5 2>/dev/null | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print('$v ms_per_step',round(d['ms_per_step'],3),'kernel_ms',round(d['roofline']['kernel_ms'],3),'value',round(d['value']/1e6,2))"
+done >> gpurun_out/ab.txt
+cp /tmp/lib_cur.so hibayes_b200/libhibayes_b200.so
+cat gpurun_out/ab.txt
