@@ -1176,3 +1176,23 @@ extern "C" int hb_engine_u_centered_sums(hb_engine* e, double mean, double* ss, 
   *ss = h[0]; *s1 = h[1];
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// host-side access to the class-decision code of the sweep (the same source compiled for the host): lets the CPU
+// tests check the certified thresholds against the exact evaluation without a GPU
+// ------------------------------------------------------------------------------------------
+extern "C" int hb_test_class_thresholds(int n_fold, double u, const double* a, const double* c, double logpi0, double* TL, double* TH) {
+  if (n_fold < 2 || n_fold > HB_MAX_FOLD || !a || !c || !TL || !TH) return hb_set_error("hb_test_class_thresholds: bad argument");
+  hbk::solve_thresholds<HB_MAX_FOLD>(n_fold, u, a, c, logpi0, TL, TH);
+  return 0;
+}
+// class from the thresholds (-1 = inside a bracket) and from the exact cumulative probabilities
+extern "C" int hb_test_class_of(int n_fold, double rr, double u, const double* a, const double* c, double logpi0, const double* TL,
+                                const double* TH, int* by_threshold, int* exact) {
+  if (n_fold < 2 || n_fold > HB_MAX_FOLD || !by_threshold || !exact) return hb_set_error("hb_test_class_of: bad argument");
+  double cum[HB_MAX_FOLD];
+  hbk::class_cum<HB_MAX_FOLD>(n_fold, rr, a, c, logpi0, cum);
+  *exact = hbk::class_from_cum<HB_MAX_FOLD>(n_fold, u, cum);
+  *by_threshold = hbk::thr_class<HB_MAX_FOLD>(n_fold, rr, TL, TH);
+  return 0;
+}

@@ -399,7 +399,7 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
 // ------------------------------------------------------------------------------------------
 // Cumulative class probabilities of one SNP given rr = rhs^2 (Bayes.cpp:759-770 in soft-max form).
 template <int NF>
-__device__ __forceinline__ void class_cum(int nf, double rr, const double* a, const double* c, double logpi0, double* cum) {
+__host__ __device__ __forceinline__ void class_cum(int nf, double rr, const double* a, const double* c, double logpi0, double* cum) {
   double sv[NF];
   sv[0] = logpi0;
   double smax = logpi0;
@@ -427,7 +427,7 @@ __device__ __forceinline__ void class_cum(int nf, double rr, const double* a, co
 }
 // inverse-CDF class draw with one uniform (Bayes.cpp:773-781): first k with u < cum_k, 0 if none
 template <int NF>
-__device__ __forceinline__ int class_from_cum(int nf, double u, const double* cum) {
+__host__ __device__ __forceinline__ int class_from_cum(int nf, double u, const double* cum) {
   int cls = 0;
   bool found = false;
 #pragma unroll
@@ -442,7 +442,7 @@ __device__ __forceinline__ int class_from_cum(int nf, double u, const double* cu
 // itself; inside a bracket (or where certification failed: TL = -1, TH = inf) the caller evaluates exactly.
 // Returns the class, or -1 when rr falls inside a bracket.
 template <int NF>
-__device__ __forceinline__ int thr_class(int nf, double rr, const double* TL, const double* TH) {
+__host__ __device__ __forceinline__ int thr_class(int nf, double rr, const double* TL, const double* TH) {
 #pragma unroll
   for (int b = 0; b < NF - 1; ++b)
     if (b < nf - 1) {
@@ -457,8 +457,8 @@ __device__ __forceinline__ int thr_class(int nf, double rr, const double* TL, co
 // safeguarded Newton finds its root; a small bracket around it is certified at both ends with a margin far
 // above the rounding error of class_cum.
 template <int NF>
-__device__ void solve_thresholds(int nf, double u, const double* a, const double* c, double logpi0, double* TL, double* TH) {
-  const double INF = __longlong_as_double(0x7ff0000000000000ll);
+__host__ __device__ inline void solve_thresholds(int nf, double u, const double* a, const double* c, double logpi0, double* TL, double* TH) {
+  const double INF = HUGE_VAL;
   const double lam = log1p(-u) - log(u);
   const bool u_ok = (u < 1.0 - 1e-12) && (u > 1e-300);
   for (int b = 0; b < nf - 1; ++b) {

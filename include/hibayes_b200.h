@@ -198,6 +198,12 @@ typedef struct {
 
 int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o);
 
+/* Test hooks (host code, no GPU needed): the class-decision code of the sweep compiled for the host.
+ * a[k-1], c[k-1] for k = 1..n_fold-1: class score s_k = a_k + c_k * rhs^2 (Bayes.cpp:759-763); TL/TH: n_fold-1 each. */
+int hb_test_class_thresholds(int n_fold, double u, const double* a, const double* c, double logpi0, double* TL, double* TH);
+int hb_test_class_of(int n_fold, double rr, double u, const double* a, const double* c, double logpi0, const double* TL,
+                     const double* TH, int* by_threshold, int* exact);
+
 /* ------------------------------------------------------------------ SBayesD (dense LD, summary statistics) */
 /* Device engine for the LD-column sweep of SBayesD(), /root/reference/src/SBayesD.cpp:253-456: r_hat lives on the
  * device, one hb_ld_engine_sweep() per MCMC iteration replaces the switch(model_index) block and returns the sums
