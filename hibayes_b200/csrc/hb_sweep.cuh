@@ -156,6 +156,31 @@ __device__ __noinline__ bool poll_corr_slow(const double* slot, double& v, int* 
   v = __longlong_as_double((long long)w);
   return true;
 }
+// The wait on the serial path (corrections of the previous tile): one load at a time would look at the slot once per
+// L2 round trip (~1 us under the streaming load).  Four loads are kept in flight, issued a quarter of a round trip
+// apart, so that the value is seen at most ~0.25 us after it could be (eight in flight measured no better).
+__device__ __noinline__ bool poll_corr_staggered(const double* slot, double& v, int* ctrl) {
+  unsigned long long w[4];
+  const long long t0 = clock64();
+  w[0] = ld_relaxed_u64(slot);
+#pragma unroll
+  for (int q = 1; q < 4; ++q) {
+    while (clock64() - t0 < 450ll * q) {}
+    w[q] = ld_relaxed_u64(slot);
+  }
+  Waiter wt;
+  for (;;) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (w[q] != kCorrEmpty) {
+        v = __longlong_as_double((long long)w[q]);
+        return true;
+      }
+      w[q] = ld_relaxed_u64(slot);
+    }
+    if (!wt.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) return false;
+  }
+}
 __device__ __forceinline__ bool poll_corr(const double* slot, double& v, int* ctrl) {
   const unsigned long long w = ld_relaxed_u64(slot);
   if (w == kCorrEmpty) return poll_corr_slow(slot, v, ctrl);
@@ -310,22 +335,29 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
         const int tt = t - D;
         const size_t qb = (size_t)tt * B;
         if (a < 32) {
-          int cnt = -1;
-          if (lane == 0) {
-            cnt = hb::ld_relaxed(p.tile_cnt + tt);
-            if (cnt < 0) {
-              Waiter w;
-              for (;;) {
-                __nanosleep(100);
-                cnt = hb::ld_relaxed(p.tile_cnt + tt);
-                if (cnt >= 0) break;
-                if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_STREAM)) { cnt = -2; break; }
-              }
+          // the count and the first 32 entries are asked for in the same trip to L2 (entries beyond the count stay
+          // "not yet written" and are ignored)
+          int cnt = -1, jl0 = -1;
+          unsigned long long dw0 = kCorrEmpty;
+          {
+            Waiter w;
+            for (;;) {
+              int c = -1;
+              if (lane == 0) c = hb::ld_relaxed(p.tile_cnt + tt);
+              if (jl0 < 0) jl0 = hb::ld_relaxed(p.q_snp + qb + lane);
+              if (dw0 == kCorrEmpty) dw0 = ld_relaxed_u64(p.q_delta + qb + lane);
+              cnt = __shfl_sync(0xffffffffu, c, 0);
+              if (cnt >= 0 && __all_sync(0xffffffffu, lane >= cnt || (jl0 >= 0 && dw0 != kCorrEmpty))) break;
+              if (cnt < 0) __nanosleep(100);
+              if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_STREAM)) { cnt = -2; break; }
             }
           }
-          cnt = __shfl_sync(0xffffffffu, cnt, 0);
           if (p.dbg & 1) cnt = min(cnt, 0);
-          for (int q0 = 0; q0 < cnt; q0 += 32) {
+          if (lane < cnt) {
+            qj[lane] = jl0;
+            qd[lane] = __longlong_as_double((long long)dw0);
+          }
+          for (int q0 = 32; q0 < cnt; q0 += 32) {
             int jl = -1;
             unsigned long long dw = kCorrEmpty;
             if (q0 + lane < cnt) {
@@ -347,21 +379,19 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
         hb::named_bar_sync(2, 32 * NAW);
         const int cnt = *(volatile int*)qcnt;
         if (cnt < 0) return;
-        // the genotype words of eight changed SNPs in flight at a time (from L2: streamed D tiles ago)
-        for (int e0 = 0; e0 < cnt; e0 += 8) {
-          uint32_t xw[8];
-          double dl[8];
+        // the genotype words of sixteen changed SNPs in flight at a time (from L2: streamed D tiles ago)
+        for (int e0 = 0; e0 < cnt; e0 += 16) {
+          uint32_t xw[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
+          for (int e = 0; e < 16; ++e) {
             const bool v = e0 + e < cnt;
             const int js = v ? qj[e0 + e] : 0;
-            dl[e] = v ? qd[e0 + e] : 0.0;
             xw[e] = (v && has) ? __ldg((const uint32_t*)(Xs + (size_t)js * R + row0)) : 0u;
           }
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
+          for (int e = 0; e < 16; ++e)
             if (e0 + e < cnt) {
-              const double ds = dl[e] * kTwo513;
+              const double ds = qd[e0 + e] * kTwo513;
               const double x0 = byte_as_scaled(xw[e], 0x4044), x1 = byte_as_scaled(xw[e], 0x4144);
               const double x2 = byte_as_scaled(xw[e], 0x4244), x3 = byte_as_scaled(xw[e], 0x4344);
               rm[0] = fma(-x0, ds, rm[0]); um[0] = fma(x0, ds, um[0]);   // yadj -= x*delta (Bayes.cpp:787), u += x*delta (:789)
@@ -443,13 +473,19 @@ __host__ __device__ __forceinline__ int class_from_cum(int nf, double u, const d
 // Returns the class, or -1 when rr falls inside a bracket.
 template <int NF>
 __host__ __device__ __forceinline__ int thr_class(int nf, double rr, const double* TL, const double* TH) {
+  // Level b is looked at only while all earlier levels were passed (rr >= TH): below TL[b] the class is b, between
+  // TL[b] and TH[b] (or NaN) it is undecided.  Written without branches: the compares of all levels are independent.
+  int c = 0;
+  bool live = true, und = false;
 #pragma unroll
   for (int b = 0; b < NF - 1; ++b)
     if (b < nf - 1) {
-      if (rr <= TL[b]) return b;
-      if (!(rr >= TH[b])) return -1;
+      const bool le = rr <= TL[b], ge = rr >= TH[b];
+      und = und || (live && !le && !ge);
+      live = live && ge && !le;
+      c += live ? 1 : 0;
     }
-  return nf - 1;
+  return und ? -1 : c;
 }
 
 // Brackets of the class boundaries of one SNP (device, k_prep).  phi_b(rr) = log S_hi - log S_lo - log((1-u)/u)
@@ -542,9 +578,11 @@ __device__ __forceinline__ CandSet make_candset(uint8_t* smem, int B) {
 // Shared memory of a scalar CTA: candidate arrays, two partial-sum arrays, and two buffers with the Gram rows of
 // the tile's candidates (exact int32, as stored): rows0 = diagonal block, rows1 = block
 // towards the next tile.
+constexpr size_t kChainCoefBytes = 32 * 32 * 8 + 32 * 33 * 8;   // coefficients H (32x32) + solved chain matrix M (32x33, padded rows)
 __host__ __device__ inline size_t scalar_fixed_bytes(int B) {
   size_t b = (8 * (size_t)B) * 8 + (6 * (size_t)B + 64 + 16) * 4 + 18 * 8 + 64;   // candidates + partials, ints, timers
-  return (b + 127) / 128 * 128;
+  b = (b + 127) / 128 * 128;
+  return b + kChainCoefBytes;   // + the chain's coefficient matrix (last kChainCoefBytes of the fixed part)
 }
 __host__ inline int scalar_krow(int B) {
   const size_t cap = 226 * 1024;
@@ -563,18 +601,15 @@ __device__ __forceinline__ double gram_as_double(int g) {
 // Gathers the Gram rows of the k candidates from one band block into a row buffer as doubles: thread i takes
 // column i of every row (coalesced), sixteen loads in flight.
 __device__ __noinline__ void gather_rows(int32_t* dst, const int32_t* __restrict__ blk, const int* idx, int k, int B, int i) {
-  // kept small (rolled, 8 loads per round trip) and out of line: this runs off the critical path, and the code of
-  // a tile's phases has to stay inside the instruction cache
-#pragma unroll 1
-  for (int sb = 0; sb < k; sb += 8) {
-    int gv[8];
-    const int nb = min(8, k - sb);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) gv[e] = (e < nb) ? __ldcg(blk + (size_t)idx[sb + e] * B + i) : 0;
-#pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if (e < nb) dst[(size_t)(sb + e) * B + i] = gv[e];
+  // all rows in flight at once: asynchronous 4-byte copies global -> shared (a warp's copies of one row coalesce into
+  // one 128-byte request), so the gather costs one trip to L2 instead of one per group of registers.  The Gram band
+  // never changes, so the copy may go through L1.
+  for (int sb = 0; sb < k; ++sb) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + (size_t)sb * B + i);
+    const int32_t* src = blk + (size_t)idx[sb] * B + i;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
   }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 // Candidate chain of the mixture models (one warp).  Lane s tracks
@@ -583,7 +618,8 @@ __device__ __noinline__ void gather_rows(int32_t* dst, const int32_t* __restrict
 // e_s is final (= delta_s).  One shuffle and one fma per candidate on the dependent path.
 // ROWS: the candidates' Gram rows are in shared memory (doubles); otherwise they are read from global.
 template <bool ROWS>
-__device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const int32_t* __restrict__ G, const int32_t* rows, int B, int lane) {
+__device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const int32_t* __restrict__ G, const int32_t* rows, int B, int lane,
+                                                 const double* coef = nullptr) {
   for (int sb = 0; sb < k; sb += 32) {
     const int sidx = sb + lane;
     const bool valid = sidx < k;
@@ -603,7 +639,25 @@ __device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const
       for (int q = 0; q < 8; ++q) e = fma(gv[q], cs.delta[sp + q], e);
     }
     const int nl = min(32, k - sb);
-    if (ROWS) {
+    if (ROWS && sb == 0) {
+      // first 32 candidates: the coefficients -G[c_lp][c_s]/v_s were laid out in shared memory when the candidate
+      // list was built (phase P, off the serial path): coef[32 lp + s], zero for lp >= s.  Two halves of 16 steps,
+      // one shuffle and one fma each; steps beyond the last candidate are skipped.
+#pragma unroll
+      for (int hc = 0; hc < 2; ++hc) {
+        if (16 * hc < nl) {
+          double hreg[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) hreg[q] = coef[(16 * hc + q) * 32 + lane];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            if (16 * hc + q >= nl) break;
+            const double d = __shfl_sync(0xffffffffu, e, 16 * hc + q);
+            e = fma(hreg[q], d, e);   // hreg = 0 for the lanes at or before the step: their e is final
+          }
+        }
+      }
+    } else if (ROWS) {
       // two halves of 16 steps: the coefficients -G[c_(sb+lp)][c_s]/v_s of a half go to registers first, then
       // the steps run fully unrolled: one shuffle and one fma each
 #pragma unroll
@@ -647,6 +701,43 @@ __device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const
 
 // Candidate chain of the dense models (RR/A/L; BayesL clamps the effect, Bayes.cpp:728, so the right-hand side
 // itself is chained):  rhs_s = rhs0_s - sum_{s' < s} G[c_s'][c_s] * delta_s', gnew_s = rhs_s/v + sd*z.
+// The chain of the first 32 candidates is the triangular system (I - H) e = e0 with H[s][lp] = coef[32 lp + s]
+// (strictly lower triangular).  Its inverse M depends only on the candidate list, so one idle warp solves it column
+// by column in phase P (lane c owns column c, forward substitution) ...
+__device__ __forceinline__ void chain_build_matrix(const double* coef, double* M, int kk, int c) {
+  for (int sr = 0; sr < 32; ++sr) {
+    double acc0 = (sr == c) ? 1.0 : 0.0, acc1 = 0.0;
+    if (sr < kk) {
+      int lp = 0;
+      for (; lp + 1 < sr; lp += 2) {
+        acc0 = fma(coef[lp * 32 + sr], M[lp * 33 + c], acc0);
+        acc1 = fma(coef[(lp + 1) * 32 + sr], M[(lp + 1) * 33 + c], acc1);
+      }
+      if (lp < sr) acc0 = fma(coef[lp * 32 + sr], M[lp * 33 + c], acc0);
+    }
+    M[sr * 33 + c] = (sr < kk) ? acc0 + acc1 : 0.0;
+  }
+}
+// ... and on the serial path the chain is one 32x32 matrix-vector product by one warp: lane s takes row s, the
+// right-hand sides e0 come by shuffle, four independent partial sums (no step waits for the one before).
+__device__ __forceinline__ void chain_matvec(const CandSet& cs, int k, const double* M, int lane) {
+  const bool valid = lane < k;
+  const double iv = valid ? cs.iv[lane] : 0.0, gold = valid ? cs.gold[lane] : 0.0;
+  const double e0 = valid ? fma(cs.rhs0[lane], iv, cs.sdz[lane]) - gold : 0.0;
+  const double* row = M + lane * 33;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+  for (int lp = 0; lp < 32; lp += 4) {
+    if (lp >= k) break;
+    a0 = fma(row[lp], __shfl_sync(0xffffffffu, e0, lp), a0);
+    a1 = fma(row[lp + 1], __shfl_sync(0xffffffffu, e0, lp + 1), a1);
+    a2 = fma(row[lp + 2], __shfl_sync(0xffffffffu, e0, lp + 2), a2);
+    a3 = fma(row[lp + 3], __shfl_sync(0xffffffffu, e0, lp + 3), a3);
+  }
+  const double e = (a0 + a1) + (a2 + a3);
+  if (valid) { cs.delta[lane] = e; cs.gnew[lane] = (cs.cls[lane] > 0) ? gold + e : 0.0; }
+  __syncwarp();
+}
 template <bool ROWS>
 __device__ void solve_candidates(const CandSet& cs, int k, const int32_t* __restrict__ G, const int32_t* rows, int B, int model,
                                  int lane) {
@@ -767,6 +858,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
   volatile int* gctl;             // [0] abort flag, [1] number of candidates
   long long* phase;
   int32_t *rows0, *rows1;
+  double *coef, *cmat;            // [32][32] chain coefficients of the first 32 candidates, [32][33] solved chain matrix
   {
     cs = make_candset(smem, B);
     double* d = (double*)smem;
@@ -778,6 +870,8 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     gctl = ip; ip += 16;
     phase = (long long*)ip;
     uint8_t* rb = smem + scalar_fixed_bytes(B);
+    coef = (double*)(rb - kChainCoefBytes);
+    cmat = coef + 32 * 32;
     rows0 = (int32_t*)rb;
     rows1 = rows0 + (size_t)p.KROW * B;
   }
@@ -856,23 +950,16 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
       for (int q = 7; q >= 0; --q)
         if (cw[q] != kCorrEmpty) cspec += __longlong_as_double((long long)cw[q]);
     }
-    // the dots: complete when the arrival count in the low byte equals the number of slabs.  One thread waits
-    // politely for the tile's first SNP, then every primary thread takes its own accumulator.
-    if (tid == 0) {
-      Waiter wt;
-      while ((ld_relaxed_u64(p.dacc + j) & 0xffull) != (unsigned long long)p.S) {
-        __nanosleep(100);
-        if (!wt.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) break;
-      }
-    }
-    hb::named_bar_sync(1, NT2);
+    // the dots: complete when the arrival count in the low byte equals the number of slabs.  Every primary thread
+    // waits politely on its own accumulator (16 cache lines per tile, 8 workers: no hot spot), so that the tile
+    // starts one trip to L2 after its last dot arrived.
     double base0 = 0.0;
     if (prim) {
       unsigned long long w = ld_relaxed_u64(p.dacc + j);
       if ((w & 0xffull) != (unsigned long long)p.S) {
         Waiter wt;
         do {
-          __nanosleep(50);
+          __nanosleep(200);
           if (!wt.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) { dead = true; break; }
           w = ld_relaxed_u64(p.dacc + j);
         } while ((w & 0xffull) != (unsigned long long)p.S);
@@ -942,6 +1029,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
         else if (has1) gather_rows(rows1, G0 + (size_t)B * B, slot_snp, ns, B, i);
       }
     };
+    bool m_ok = false;   // the solved chain matrix matches the current candidate list
     // candidate list of the current classes
     auto compact = [&]() {
       cand = act && (cls > 0 || gold != 0.0);
@@ -982,9 +1070,27 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
         hb::named_bar_sync(1, NT2);
       }
       if (!prim) { k = gctl[1]; myrank = rank_sh[i]; }
+      // coefficients of the chain's first 32 candidates (read by the chain warp after the next barrier)
+      m_ok = false;
+      if (fast && !dense) {
+        const int kk = min(k, 32);
+        for (int e = tid; e < 32 * 32; e += NT2) {
+          const int lp = e >> 5, sc = e & 31;
+          double v = 0.0;
+          if (lp < sc && sc < kk) v = gram_as_double(rows0[(size_t)cs.slot[lp] * B + cs.idx[sc]]) * (-cs.iv[sc]);
+          coef[e] = v;
+        }
+      }
     };
     select_rows(act ? ((base0 - cspec) + addback) * ((base0 - cspec) + addback) : 0.0);
     compact();
+    if (fast && !dense && k > 0 && k <= 32 && !(p.dbg & 128)) {
+      // solve the chain matrix while the tile waits for its turn (first warp of the secondary half; everybody
+      // meets again at the barrier that opens phase S)
+      hb::named_bar_sync(1, NT2);
+      if (!prim && warp == 0) chain_build_matrix(coef, cmat, k, lane);
+      m_ok = true;
+    }
     HB_PHASE(1);
     if (tid == 0) HB_TRACE(t, 1);
     // ---- phase S: the previous tile is final once its corrections for this tile are here
@@ -997,7 +1103,10 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
       for (int q = 7; q >= 0; --q)
         if (q + 1 <= dmax) {
           double v = __longlong_as_double((long long)cw[q]);
-          if (cw[q] == kCorrEmpty && !poll_corr_slow(p.corr + ((size_t)t * DC + q) * B + i, v, ctrl)) { dead = true; v = 0.0; }
+          if (cw[q] == kCorrEmpty) {
+            const double* slot = p.corr + ((size_t)t * DC + q) * B + i;
+            if (!(q == 0 ? poll_corr_staggered(slot, v, ctrl) : poll_corr_slow(slot, v, ctrl))) { dead = true; v = 0.0; }
+          }
           if (q == 0) c1 = v; else cold += v;
         }
     }
@@ -1015,7 +1124,9 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
       // the candidate list and its rows are rebuilt before the chain runs (instead of after a wasted round).
       // The barrier that publishes the candidates' right-hand sides carries the verdict.
       int cls0 = cls;
-      if (nrounds == 1 && prim && act) cls0 = classify(rhs0);
+      // (only while speculation has recently missed on this worker: `widen`; otherwise the final check below is
+      // enough and the serial path saves one classification)
+      if (nrounds == 1 && widen > 0 && prim && act) cls0 = classify(rhs0);
       if (hb::named_bar_or(1, NT2, cls0 != cls)) {
         cls = cls0;
         compact();
@@ -1029,7 +1140,8 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
       if (fast) {
         if (tid < 32 && k > 0) {
           if (dense) solve_candidates<true>(cs, k, G0, rows0, B, model, lane);
-          else chain_candidates<true>(cs, k, G0, rows0, B, lane);
+          else if (m_ok) chain_matvec(cs, k, cmat, lane);
+          else chain_candidates<true>(cs, k, G0, rows0, B, lane, coef);
         }
         HB_PHASE(4);
         hb::named_bar_sync(1, NT2);

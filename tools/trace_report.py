@@ -21,3 +21,13 @@ print("S done (3) -> C done (5): %.0f" % d(5, 3))
 print("S done of t-1 (3) -> hand-over arrived at t (2): %.0f" % float(np.median(a[lo + 1:hi, 2] - a[lo:hi - 1, 3])))
 print("AXPY fetched t (6) -> slab0 added dots of t+D (7): %.0f" % float(np.median(a[lo + D:hi, 7] - a[lo:hi - D, 6])))
 print("published t (4) -> dots of t+D seen (0): %.0f" % float(np.median(a[lo + D:hi, 0] - a[lo:hi - D, 4])))
+# who gates the start of phase S: the tile's own phase P (dots + gather) or the previous tile's hand-over?
+late = (a[lo + 1:hi, 1] - a[lo:hi - 1, 3]).astype(np.float64)
+print("P done of t minus S done of t-1: median %.0f ns, P later in %.1f %% of tiles" % (float(np.median(late)), 100.0 * float(np.mean(late > 0))))
+gate = np.maximum(a[lo + 1:hi, 1], a[lo:hi - 1, 3])
+det = (a[lo + 1:hi, 2] - gate).astype(np.float64)
+print("hand-over seen after max(P done, S done of t-1): median %.0f ns, p10 %.0f, p90 %.0f" % (float(np.median(det)), float(np.percentile(det, 10)), float(np.percentile(det, 90))))
+per = np.diff(a[lo:hi, 3]).astype(np.float64)
+print("period: p10 %.0f p50 %.0f p90 %.0f mean %.0f" % (float(np.percentile(per, 10)), float(np.percentile(per, 50)), float(np.percentile(per, 90)), float(per.mean())))
+dd = (a[lo + D:hi, 0] - a[lo:hi - D, 3]).astype(np.float64)
+print("S done of t -> dots of t+D seen by its worker: median %.0f ns (budget: D periods minus P and S)" % float(np.median(dd)))
