@@ -90,6 +90,8 @@ struct hb_engine {
   unsigned sweep_no = 0;
   unsigned long long* trace = nullptr;
   int KROW = 0;
+  int cluster2 = 0;   // HB_CLUSTER=1: scalar workers in clusters of 2 (hand-over through distributed shared memory)
+  int scalar0 = 0;    // block index of the first scalar CTA
   int* ctrl = nullptr;  // [0] progress, [1] abort
   double* prm = nullptr;  // per-SNP sweep parameters, SoA
   int prm_fold = 0;
@@ -676,6 +678,15 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, e->block_threads, e->smem_bytes));
     if (occ < 1) { delete e; return hb_set_error("sweep kernel does not fit an SM (threads %d, smem %zu)", e->block_threads, e->smem_bytes); }
   }
+  e->scalar0 = e->S;
+  if (const char* cl = getenv("HB_CLUSTER")) {
+    // experimental: the whole grid in clusters of 2 so that the scalar workers 2c, 2c+1 share distributed shared memory
+    const int s0 = (e->S + 1) & ~1;
+    if (atoi(cl) && e->B == 256 && e->block_threads == 512 && e->NG % 2 == 0 && s0 + e->NG <= e->nsm) {
+      e->cluster2 = 1;
+      e->scalar0 = s0;
+    }
+  }
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&e->ev[i]));
   const size_t xbytes = (size_t)e->S * e->slab_stride;
@@ -979,8 +990,44 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   CU(cudaGetLastError());
   CU(cudaEventRecord(e->ev[1], e->stream));
   {
+    const void* fn = sweep_kernel_for(in->model_index == HB_MODEL_R ? F : 2, e->RL, dense_model);
     void* args[] = {(void*)&sp};
-    CU(cudaLaunchCooperativeKernel(sweep_kernel_for(in->model_index == HB_MODEL_R ? F : 2, e->RL, dense_model), dim3(e->S + e->NG), dim3(e->block_threads), args, e->smem_bytes, e->stream));
+    bool launched = false;
+    if (e->cluster2) {
+      sp.cluster2 = 1;
+      sp.scalar0 = e->scalar0;
+      cudaLaunchConfig_t lc;
+      memset(&lc, 0, sizeof lc);
+      lc.gridDim = dim3(e->scalar0 + e->NG);
+      lc.blockDim = dim3(e->block_threads);
+      lc.dynamicSmemBytes = e->smem_bytes;
+      lc.stream = e->stream;
+      cudaLaunchAttribute at[2];
+      memset(at, 0, sizeof at);
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      at[1].id = cudaLaunchAttributeCooperative;
+      at[1].val.cooperative = 1;
+      lc.attrs = at;
+      lc.numAttrs = 2;
+      int ncl = 0;
+      cudaError_t err = cudaOccupancyMaxActiveClusters(&ncl, fn, &lc);
+      if (err == cudaSuccess && 2 * ncl >= (int)lc.gridDim.x) err = cudaLaunchKernelExC(&lc, fn, args);
+      else if (err == cudaSuccess) err = cudaErrorCooperativeLaunchTooLarge;
+      if (err == cudaSuccess) launched = true;
+      else {
+        fprintf(stderr, "[hb] cluster launch not possible (%s, %d clusters of 2 fit, %u blocks wanted): plain launch\n",
+                cudaGetErrorString(err), ncl, lc.gridDim.x);
+        (void)cudaGetLastError();
+        e->cluster2 = 0;
+        e->scalar0 = e->S;
+      }
+    }
+    if (!launched) {
+      sp.cluster2 = 0;
+      sp.scalar0 = e->S;
+      CU(cudaLaunchCooperativeKernel(fn, dim3(e->S + e->NG), dim3(e->block_threads), args, e->smem_bytes, e->stream));
+    }
   }
   CU(cudaEventRecord(e->ev[2], e->stream));
   CU(cudaMemcpyAsync(e->fold_dev, in->fold, HB_MAX_FOLD * 8, cudaMemcpyHostToDevice, e->stream));

@@ -74,6 +74,8 @@ struct SweepParams {
   double dscale, inv_dscale, mu_shift;
   int use_thr;   // class decisions of the mixture models by certified thresholds on rhs^2 (k_prep), no exp in the chain
   int dbg;       // timing experiments only (HB_DEBUG env): 1 skip AXPY, 2 skip dot FMAs, 16/32 streaming side alone
+  int scalar0;   // block index of the first scalar CTA (>= S; blocks S .. scalar0-1 are idle padding)
+  int cluster2;  // launched as clusters of 2 CTAs: worker pairs (0,1), (2,3), ... hand over through distributed shared memory
 };
 
 enum { HB_ABORT_TIMEOUT_STREAM = 1, HB_ABORT_TIMEOUT_SCALAR = 2, HB_ABORT_TIMEOUT_TMA = 3, HB_ABORT_OVERFLOW = 4,
@@ -98,6 +100,29 @@ __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+
+// distributed shared memory of a 2-CTA cluster (hand-over between the two scalar workers of a cluster)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_peer_shared_u64(uint32_t local_addr, uint32_t peer_rank, unsigned long long v) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(peer_rank));
+  asm volatile("st.relaxed.cluster.shared::cluster.b64 [%0], %1;" ::"r"(ra), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_own_shared_cluster_u64(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.cluster.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_own_shared_cluster_u64(uint32_t addr, unsigned long long v) {
+  asm volatile("st.relaxed.cluster.shared::cta.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
 }
 
 struct Waiter {
@@ -578,7 +603,8 @@ __device__ __forceinline__ CandSet make_candset(uint8_t* smem, int B) {
 // Shared memory of a scalar CTA: candidate arrays, two partial-sum arrays, and two buffers with the Gram rows of
 // the tile's candidates (exact int32, as stored): rows0 = diagonal block, rows1 = block
 // towards the next tile.
-constexpr size_t kChainCoefBytes = 32 * 32 * 8 + 32 * 33 * 8;   // coefficients H (32x32) + solved chain matrix M (32x33, padded rows)
+// coefficients H (32x32) + solved chain matrix M (32x33, padded rows) + hand-over buffer of the cluster mode (2 x 256)
+constexpr size_t kChainCoefBytes = 32 * 32 * 8 + 32 * 33 * 8 + 2 * 256 * 8;
 __host__ __device__ inline size_t scalar_fixed_bytes(int B) {
   size_t b = (8 * (size_t)B) * 8 + (6 * (size_t)B + 64 + 16) * 4 + 18 * 8 + 64;   // candidates + partials, ints, timers
   b = (b + 127) / 128 * 128;
@@ -780,14 +806,16 @@ __device__ void solve_candidates(const CandSet& cs, int k, const int32_t* __rest
 
 // corr_i = sum_s G[c_s][i] * delta_s over the k candidates (ascending s), read from global memory
 __device__ __noinline__ double band_correction_raw(const int* idx, const double* delta, int k, const int32_t* __restrict__ gb, int B, int i) {
+  // 32 Gram entries in flight: one trip to L2 for most tiles.  The correction for tile t+2 is the next thing that
+  // tile's phase S waits for after the hand-over, so its latency is on the serial path of every second tile.
   double corr = 0.0;
 #pragma unroll 1
-  for (int sb = 0; sb < k; sb += 8) {
-    int gv[8];
+  for (int sb = 0; sb < k; sb += 32) {
+    int gv[32];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) gv[e] = (sb + e < k) ? __ldcg(gb + (size_t)idx[sb + e] * B + i) : 0;
+    for (int e = 0; e < 32; ++e) gv[e] = (sb + e < k) ? __ldcg(gb + (size_t)idx[sb + e] * B + i) : 0;
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
+    for (int e = 0; e < 32; ++e)
       if (sb + e < k) corr = fma(gram_as_double(gv[e]), delta[sb + e], corr);
   }
   return corr;
@@ -848,7 +876,8 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
   if (tid >= 2 * B) return;
   const int h = tid / B, i = tid - h * B, warp = i >> 5, lane = i & 31, nwarp = B / 32;
   const bool prim = (h == 0);
-  const int worker = (int)blockIdx.x - p.S, nworker = p.NG;
+  const int worker = (int)blockIdx.x - p.scalar0, nworker = p.NG;
+  const bool cl2 = p.cluster2 != 0;   // (only with B = 256: every thread of the block is a worker thread)
   int* ctrl = p.ctrl;
   // ---- shared memory carve-up
   CandSet cs;
@@ -859,6 +888,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
   long long* phase;
   int32_t *rows0, *rows1;
   double *coef, *cmat;            // [32][32] chain coefficients of the first 32 candidates, [32][33] solved chain matrix
+  double* hbuf;                   // [2][256] cluster mode: corrections handed over by the other worker of the cluster
   {
     cs = make_candset(smem, B);
     double* d = (double*)smem;
@@ -872,12 +902,18 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     uint8_t* rb = smem + scalar_fixed_bytes(B);
     coef = (double*)(rb - kChainCoefBytes);
     cmat = coef + 32 * 32;
+    hbuf = cmat + 32 * 33;
     rows0 = (int32_t*)rb;
     rows1 = rows0 + (size_t)p.KROW * B;
   }
   const int KROW = p.KROW;
   const int NT2 = 2 * B;   // threads of the worker
   if (tid < 8) gctl[tid] = 0;
+  if (cl2) {
+    for (int w = tid; w < 2 * 256; w += NT2) ((unsigned long long*)hbuf)[w] = kCorrEmpty;
+    cluster_sync_all();   // both workers' buffers are "empty" before either hands anything over
+  }
+  const uint32_t hbuf_addr = (uint32_t)__cvta_generic_to_shared(hbuf);
   hb::named_bar_sync(1, NT2);
 
   const size_t mp = p.m_pad;
@@ -1025,6 +1061,18 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
       ns = gctl[2];
       fast = (ns <= KROW);
       if (fast) {
+        // The far blocks of the same rows (corrections for tiles t+2 .. t+D-1, computed in phase C) come from HBM:
+        // ask for them in L2 now.  The correction for tile t+2 is the last thing that tile's phase S waits for, and a
+        // miss to HBM under the streaming load costs several microseconds.
+        {
+          const int lpr = B / 32;   // 128-byte lines per row of a block
+          const int nfar = min(D, T - t) - 2;
+          for (int l = tid; l < ns * lpr * nfar; l += NT2) {
+            const int line = l % lpr, sl = (l / lpr) % ns, dt = 2 + l / (lpr * ns);
+            const int32_t* a = G0 + (size_t)dt * B * B + (size_t)slot_snp[sl] * B + line * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          }
+        }
         if (prim) gather_rows(rows0, G0, slot_snp, ns, B, i);
         else if (has1) gather_rows(rows1, G0 + (size_t)B * B, slot_snp, ns, B, i);
       }
@@ -1095,10 +1143,34 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     if (tid == 0) HB_TRACE(t, 1);
     // ---- phase S: the previous tile is final once its corrections for this tile are here
     double cold = 0.0, c1 = 0.0;
+    // cluster mode: the odd worker of a cluster gets the previous tile's corrections in its own shared memory
+    const bool c1_local = cl2 && (worker & 1) && t >= 1 && DC >= 1;
     if (prim) {
       unsigned long long cw[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) cw[q] = (q + 1 <= dmax) ? ld_relaxed_u64(p.corr + ((size_t)t * DC + q) * B + i) : 0ull;
+      for (int q = 0; q < 8; ++q)
+        cw[q] = (q + 1 <= dmax && !(q == 0 && c1_local)) ? ld_relaxed_u64(p.corr + ((size_t)t * DC + q) * B + i) : 0ull;
+      if (c1_local) {
+        // the older corrections first (they arrive earlier; asking again only after the hand-over would add a trip to L2)
+#pragma unroll
+        for (int q = 7; q >= 1; --q)
+          if (q + 1 <= dmax && cw[q] == kCorrEmpty) {
+            double v;
+            if (!poll_corr_slow(p.corr + ((size_t)t * DC + q) * B + i, v, ctrl)) { dead = true; v = 0.0; }
+            cw[q] = (unsigned long long)__double_as_longlong(v);
+          }
+        const uint32_t a = hbuf_addr + (uint32_t)((((t / nworker) & 1) * 256 + i) * 8);
+        unsigned long long w = ld_own_shared_cluster_u64(a);
+        if (w == kCorrEmpty) {
+          Waiter wt;
+          do {
+            if (!wt.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) { dead = true; w = 0ull; break; }
+            w = ld_own_shared_cluster_u64(a);
+          } while (w == kCorrEmpty);
+        }
+        st_own_shared_cluster_u64(a, kCorrEmpty);   // free for the hand-over two rounds of this worker later
+        cw[0] = w;
+      }
 #pragma unroll
       for (int q = 7; q >= 0; --q)
         if (q + 1 <= dmax) {
@@ -1196,7 +1268,13 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     changed_total += k;
     widen = (nrounds > 1 || respec_tile) ? 16 : max(widen - 1, 0);
     // ---- the tile is final.  First what the next tile waits for: its corrections (dt = 1)
-    if (has1 && prim) post_corr(p.corr + ((size_t)(t + 1) * DC) * B + i, corr1);
+    if (has1 && prim) {
+      if (cl2 && !(worker & 1))   // the next tile belongs to the other worker of this cluster
+        st_peer_shared_u64(hbuf_addr + (uint32_t)(((((t + 1) / nworker) & 1) * 256 + i) * 8), cluster_ctarank() ^ 1u,
+                           (unsigned long long)__double_as_longlong(corr1));
+      else
+        post_corr(p.corr + ((size_t)(t + 1) * DC) * B + i, corr1);
+    }
     HB_PHASE(6);
     if (tid == 0) HB_TRACE(t, 3);
     // ---- phase C: commit.  The tile's residual updates go to the streaming CTAs first
@@ -1222,6 +1300,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     hb::named_bar_sync(1, NT2);   // the candidate arrays are free again
   }
   if (dead) atomicCAS(ctrl + 1, 0, HB_ABORT_TIMEOUT_SCALAR);
+  if (cl2) cluster_sync_all();   // nobody leaves while the other worker may still write into this CTA
   if (tid == 0) {
     if (worker < 2)
       for (int k = 0; k < 16; ++k) p.out->phase_clk[worker][k] = pc[k];
@@ -1236,6 +1315,6 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
 template <int MAXT, int NF, int RL, bool DENSE>
 __global__ void __launch_bounds__(MAXT, 1) k_sweep(const __grid_constant__ SweepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  if ((int)blockIdx.x >= p.S) hbk::scalar_role<NF, DENSE>(p, smem);
-  else hbk::stream_role<RL>(p, smem);
+  if ((int)blockIdx.x >= p.scalar0) hbk::scalar_role<NF, DENSE>(p, smem);
+  else if ((int)blockIdx.x < p.S) hbk::stream_role<RL>(p, smem);
 }

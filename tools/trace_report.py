@@ -31,3 +31,10 @@ per = np.diff(a[lo:hi, 3]).astype(np.float64)
 print("period: p10 %.0f p50 %.0f p90 %.0f mean %.0f" % (float(np.percentile(per, 10)), float(np.percentile(per, 50)), float(np.percentile(per, 90)), float(per.mean())))
 dd = (a[lo + D:hi, 0] - a[lo:hi - D, 3]).astype(np.float64)
 print("S done of t -> dots of t+D seen by its worker: median %.0f ns (budget: D periods minus P and S)" % float(np.median(dd)))
+ho = (a[lo + 1:hi, 2] - a[lo:hi - 1, 3]).astype(np.float64)
+tt = np.arange(lo + 1, hi)
+for par, name in ((1, "odd tiles (cluster mode: local hand-over)"), (0, "even tiles")):
+    x = ho[(tt & 1) == par]
+    print("S done of t-1 -> hand-over arrived at t, %s: mean %.0f p10 %.0f p50 %.0f p90 %.0f" % (name, x.mean(), np.percentile(x, 10), np.percentile(x, 50), np.percentile(x, 90)))
+sd = (a[lo:hi, 3] - a[lo:hi, 2]).astype(np.float64)
+print("hand-over arrived -> S done: mean %.0f p10 %.0f p50 %.0f p90 %.0f" % (sd.mean(), np.percentile(sd, 10), np.percentile(sd, 50), np.percentile(sd, 90)))
