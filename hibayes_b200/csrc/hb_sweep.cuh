@@ -1162,8 +1162,11 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
         const uint32_t a = hbuf_addr + (uint32_t)((((t / nworker) & 1) * 256 + i) * 8);
         unsigned long long w = ld_own_shared_cluster_u64(a);
         if (w == kCorrEmpty) {
+          // polite: 8 warps spinning on shared memory would take the issue slots of the warp that is still solving
+          // the chain matrix
           Waiter wt;
           do {
+            __nanosleep(64);
             if (!wt.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) { dead = true; w = 0ull; break; }
             w = ld_own_shared_cluster_u64(a);
           } while (w == kCorrEmpty);
