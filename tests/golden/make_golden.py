@@ -10,6 +10,12 @@ Outputs
   demo_oracle_<model>.npz  outputs of the CPU oracle on BASELINE config 1 (demo data, T1 ~ 1,
                            200 iterations) -- regression pins for the oracle itself; the reference
                            publishes no golden vectors.
+  demo_oracle_sbayesd_<model>.npz
+                           the same for the SBayesD oracle on the reference's COJO file demo.ma with the LD
+                           matrix of the demo genotypes
+  sbayess_inputs.npz, demo_oracle_sbayess_<model>.npz
+                           SBayesS oracle on a small synthetic data set with a thresholded LD matrix (inputs
+                           stored); `python make_golden.py sbayes` rebuilds the SBayes pins only.
 """
 import os
 import sys
@@ -82,5 +88,61 @@ def main():
               (r["Vg"], r["Ve"], r["h2"], r["mu"], np.round(r["pi"], 4), r["diag"]["nnz_trace"][-1]))
 
 
+def demo_sumstat():
+    """sbrm()-style inputs from the bundled files: the reference's own COJO file demo.ma (MAF, BETA, SE, NMISS:
+    R/sbayes.r:209) and the LD matrix of the bundled genotypes, centred X'X / n (tXXmat.cpp:174-179)."""
+    d = np.load(os.path.join(HERE, "demo.npz"))
+    X = d["geno"].astype(np.float64)
+    Xc = X - X.mean(axis=0)
+    ld = Xc.T @ Xc / X.shape[0]
+    ss = np.column_stack([d["ma_maf"], d["ma_beta"], d["ma_se"], d["ma_n"]])
+    return np.asfortranarray(ss), np.asfortranarray(ld)
+
+
+def sparse_ld(ld, n, chisq=3.84):
+    """the chi-square sparsifier of tXXmat.cpp:146-153: an entry stays when r^2 n > chisq"""
+    import scipy.sparse as sp
+    dd = np.sqrt(np.clip(np.diag(ld), 1e-300, None))
+    r2 = (ld / dd[:, None] / dd[None, :]) ** 2
+    keep = (r2 * n > chisq) | np.eye(ld.shape[0], dtype=bool)
+    return sp.csc_matrix(np.where(keep, ld, 0.0))
+
+
+SBAYESS_M = 200
+
+
+def sbayes_main():
+    """regression pins for the SBayesD / SBayesS oracles (demo_oracle_sbayes*.npz)"""
+    from oracle import hb_oracle
+    ss, ld = demo_sumstat()
+    kw = dict(niter=100, nburn=50, thin=5, seed=666666)
+    # SBayesS: a synthetic data set (1500 individuals, 200 SNPs), inputs stored next to the outputs
+    # (sbayess_inputs.npz).  With the bundled demo data a thresholded LD matrix is not positive definite (few animals,
+    # long LD blocks) and the chain diverges -- in the reference as well, nothing in SBayesS.cpp guards against it.
+    from tests.util_demo import synth
+    from tests.util_sumstat import make_sumstat
+    ys, Xs = synth(1500, SBAYESS_M, seed=23, n_causal=10)
+    ss_s, ld_s = make_sumstat(ys, Xs)
+    sld = sparse_ld(ld_s, len(ys))
+    np.savez_compressed(os.path.join(HERE, "sbayess_inputs.npz"), sumstat=ss_s, ld_thresholded=sld.toarray())
+    for tag, fn, ssx, ldm in (("sbayesd", hb_oracle.sbayesd, ss, ld), ("sbayess", hb_oracle.sbayess, ss_s, sld)):
+        for model, Pi, fold in [("BayesCpi", [0.95, 0.05], None),
+                                ("BayesR", [0.95, 0.02, 0.02, 0.01], [0, 1e-4, 1e-3, 1e-2])]:
+            r = fn(ssx, ldm, model, Pi, fold=fold, **kw)
+            assert np.all(np.isfinite(r["alpha"])) and np.isfinite(r["Ve"]), (tag, model)
+            np.savez_compressed(
+                os.path.join(HERE, "demo_oracle_%s_%s.npz" % (tag, model)),
+                Vg=r["Vg"], Ve=r["Ve"], h2=r["h2"], alpha=r["alpha"], pi=r["pi"], pip=r["pip"],
+                tracker=r["diag"]["tracker"], nnz_trace=r["diag"]["nnz_trace"], nzrate_count=r["diag"]["nzrate_count"],
+                vare_trace=r["diag"]["vare_trace"], vara_trace=r["diag"]["vara_trace"], n_used=r["diag"]["n_used"],
+            )
+            print(tag, model, "Vg %.5f Ve %.5f h2 %.4f pi %s nnz_last %d n %d" %
+                  (r["Vg"], r["Ve"], r["h2"], np.round(r["pi"], 4), r["diag"]["nnz_trace"][-1], r["diag"]["n_used"]))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "sbayes":
+        sbayes_main()   # needs only tests/golden/demo.npz
+    else:
+        main()
+        sbayes_main()

@@ -1,4 +1,6 @@
 """SBayesD: the oracle on CPU, and the CUDA path against it."""
+import os
+
 import numpy as np
 import pytest
 
@@ -35,6 +37,49 @@ def test_oracle_sbayesd_runs_and_respects_the_quirks(oracle):
     assert np.all(r2["pip"] == 1.0)
     with pytest.raises(RuntimeError, match="fold"):
         oracle.sbayesd(ss, ld, "BayesR", [0.9, 0.05, 0.05], niter=10, nburn=5, thin=1)
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _check_pin(r, pin):
+    """oracle output against a committed pin (tests/golden/make_golden.py): discrete outputs exactly, the rest to 1e-9"""
+    assert np.array_equal(r["diag"]["tracker"], pin["tracker"])
+    assert np.array_equal(r["diag"]["nnz_trace"], pin["nnz_trace"])
+    assert np.array_equal(r["diag"]["nzrate_count"], pin["nzrate_count"])
+    assert r["diag"]["n_used"] == int(pin["n_used"])
+    for k in ("Vg", "Ve", "h2"):
+        assert abs(r[k] / float(pin[k]) - 1) < 1e-9, (k, r[k], float(pin[k]))
+    assert np.allclose(r["alpha"], pin["alpha"], rtol=1e-9, atol=1e-12 * np.abs(pin["alpha"]).max())
+    assert np.allclose(r["pi"], pin["pi"], rtol=1e-9)
+    assert np.allclose(r["diag"]["vare_trace"], pin["vare_trace"], rtol=1e-9)
+    assert np.allclose(r["diag"]["vara_trace"], pin["vara_trace"], rtol=1e-9)
+
+
+PIN_MODELS = [("BayesCpi", [0.95, 0.05], None), ("BayesR", [0.95, 0.02, 0.02, 0.01], [0, 1e-4, 1e-3, 1e-2])]
+PIN_KW = dict(niter=100, nburn=50, thin=5, seed=666666)
+
+
+@pytest.mark.parametrize("model,Pi,fold", PIN_MODELS)
+def test_oracle_sbayesd_pinned_on_the_reference_cojo_file(oracle, model, Pi, fold):
+    """SBayesD oracle on the reference's own summary statistics (inst/extdata/demo.ma, columns MAF/BETA/SE/NMISS as
+    R/sbayes.r:209 selects them) with the LD matrix of the bundled genotypes (centred X'X/n, tXXmat.cpp:174-179)."""
+    d = np.load(os.path.join(GOLDEN, "demo.npz"))
+    X = d["geno"].astype(np.float64)
+    Xc = X - X.mean(axis=0)
+    ld = np.asfortranarray(Xc.T @ Xc / X.shape[0])
+    ss = np.asfortranarray(np.column_stack([d["ma_maf"], d["ma_beta"], d["ma_se"], d["ma_n"]]))
+    r = oracle.sbayesd(ss, ld, model, Pi, fold=fold, **PIN_KW)
+    _check_pin(r, np.load(os.path.join(GOLDEN, "demo_oracle_sbayesd_%s.npz" % model)))
+
+
+@pytest.mark.parametrize("model,Pi,fold", PIN_MODELS)
+def test_oracle_sbayess_pinned(oracle, model, Pi, fold):
+    """SBayesS oracle on stored inputs (summary statistics + thresholded LD matrix of a synthetic data set)."""
+    import scipy.sparse as sp
+    inp = np.load(os.path.join(GOLDEN, "sbayess_inputs.npz"))
+    r = oracle.sbayess(np.asfortranarray(inp["sumstat"]), sp.csc_matrix(inp["ld_thresholded"]), model, Pi, fold=fold, **PIN_KW)
+    _check_pin(r, np.load(os.path.join(GOLDEN, "demo_oracle_sbayess_%s.npz" % model)))
 
 
 def _compare(got, ref):
