@@ -21,7 +21,15 @@ SYMBOLS = [
     "hb_engine_ipc_handle", "hb_engine_set_peers", "hb_engine_gram_device", "hb_engine_u_centered_sums",
     "hb_test_class_thresholds", "hb_test_class_of", "hb_ld_engine_create", "hb_ld_engine_destroy", "hb_ld_engine_load_dense", "hb_ld_engine_set_state",
     "hb_ld_engine_set_vargL", "hb_ld_engine_set_sparse_info", "hb_ld_engine_get", "hb_ld_engine_sweep", "hb_sbayesd", "hb_sbayess",
+    "hb_engine_load_bed", "hb_ldmat_create", "hb_ldmat_destroy", "hb_ldmat_load_i8", "hb_ldmat_load_bed", "hb_ldmat_stats",
+    "hb_ldmat_dense", "hb_ldmat_sparse", "hb_ldmat_sparse_get", "hb_ldmat_set_panel_cols", "hb_ldmat_last_ms", "hb_bed_decode",
+    "hb_test_bed_decode_snp",
 ]
+
+
+class BedSource(C.Structure):
+    _fields_ = [("file", C.c_void_p), ("len", C.c_size_t), ("nid", C.c_int), ("rows", C.c_void_p), ("impt", C.c_int),
+                ("dominance", C.c_int)]
 
 
 class SBayesArgs(C.Structure):
@@ -147,6 +155,20 @@ def load_library():
     L.hb_engine_set_peers.argtypes = [C.c_void_p, C.c_void_p]
     L.hb_engine_gram_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.hb_engine_u_centered_sums.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.hb_engine_load_bed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.hb_ldmat_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.hb_ldmat_destroy.argtypes = [C.c_void_p]
+    L.hb_ldmat_destroy.restype = None
+    L.hb_ldmat_load_i8.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.hb_ldmat_load_bed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.hb_ldmat_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb_ldmat_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_size_t]
+    L.hb_ldmat_sparse.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_longlong)]
+    L.hb_ldmat_sparse_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb_ldmat_set_panel_cols.argtypes = [C.c_void_p, C.c_int]
+    L.hb_ldmat_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.hb_bed_decode.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.hb_test_bed_decode_snp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     _LIB = L
     return L
 

@@ -31,6 +31,170 @@ def synth_geno_host(n, m, seed, row_offset=0):
     return X
 
 
+class BedGeno:
+    """Genotypes held as the image of a SNP-major PLINK .bed file; accepted by Bayes() and LdMat in place of
+    a matrix, decoded on the device (hb_engine_load_bed / hb_ldmat_load_bed; read_bed<char>() of
+    /root/reference/src/read_bed.cpp:97-232).  rows: 0-based file individuals in the order of y
+    (the `M[index, ]` selection of R/bayes.r:281-291), default all in file order."""
+
+    def __init__(self, image, nid, m, rows=None, impute=True, mode="A"):
+        if mode not in ("A", "D"):
+            raise ValueError("mode must be 'A' or 'D'")  # R/read_plink.r:28 match.arg
+        self.image = np.ascontiguousarray(np.frombuffer(image, dtype=np.uint8) if isinstance(image, (bytes, bytearray)) else image,
+                                          dtype=np.uint8)
+        self.nid, self.m = int(nid), int(m)
+        self.rows = None if rows is None else np.ascontiguousarray(rows, dtype=np.int32)
+        self.impute, self.dominance = bool(impute), mode == "D"
+        self.shape = (self.nid if self.rows is None else self.rows.shape[0], self.m)
+
+    @classmethod
+    def from_file(cls, bfile, nid, m, **kw):
+        path = bfile if bfile.endswith(".bed") else bfile + ".bed"  # read_bed.cpp:99-102
+        return cls(np.fromfile(path, dtype=np.uint8), nid, m, **kw)
+
+    def c_struct(self):
+        b = _lib.BedSource()
+        b.file, b.len, b.nid = self.image.ctypes.data, self.image.shape[0], self.nid
+        b.rows = _ptr(self.rows)
+        b.impt, b.dominance = int(self.impute), int(self.dominance)
+        return b
+
+
+def read_bed(image, nid, m, impute=True, mode="A", device=0):
+    """read_bed() of the reference (R/read_plink.r:60-67 -> src/read_bed.cpp:235) on the device: returns the
+    nid x m int8 matrix a "char" big.matrix would hold (NA = -128) and the per-SNP missing flags."""
+    L = _lib.load_library()
+    g = BedGeno(image, nid, m, impute=impute, mode=mode)
+    out = np.empty((nid, m), dtype=np.int8, order="F")
+    miss = np.zeros(m, dtype=np.uint8)
+    _lib.check(L.hb_bed_decode(device, g.image.ctypes.data, g.image.shape[0], nid, m, int(g.impute), int(g.dominance),
+                               out.ctypes.data, miss.ctypes.data))
+    return out, miss
+
+
+class LdMat:
+    """Device LD builder (hb_ldmat_*): tXXmat_Geno / tXXmat_Chr of /root/reference/src/tXXmat.cpp."""
+
+    def __init__(self, geno, device=0, panel_cols=0):
+        self.L = _lib.load_library()
+        self.h = C.c_void_p()
+        self.n, self.m = geno.shape
+        _lib.check(self.L.hb_ldmat_create(device, self.n, self.m, C.byref(self.h)))
+        if panel_cols:
+            _lib.check(self.L.hb_ldmat_set_panel_cols(self.h, panel_cols))
+        if isinstance(geno, BedGeno):
+            _lib.check(self.L.hb_ldmat_load_bed(self.h, geno.image.ctypes.data, geno.image.shape[0], geno.nid, _ptr(geno.rows),
+                                                int(geno.impute), int(geno.dominance)))
+        else:
+            Xf = np.asfortranarray(geno)
+            if Xf.dtype != np.int8:
+                raise TypeError("LdMat holds int8 genotypes (the reference's 'char' big.matrix)")
+            _lib.check(self.L.hb_ldmat_load_i8(self.h, Xf.ctypes.data, Xf.shape[0]))
+
+    def close(self):
+        if self.h:
+            self.L.hb_ldmat_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self):
+        """BigStat(): dict(mean, sum, xx)."""
+        mean, sm, xx = np.zeros(self.m), np.zeros(self.m), np.zeros(self.m)
+        _lib.check(self.L.hb_ldmat_stats(self.h, mean.ctypes.data, sm.ctypes.data, xx.ctypes.data))
+        return {"mean": mean, "sum": sm, "xx": xx}
+
+    @staticmethod
+    def _chr(chr_, m):
+        if chr_ is None:
+            return None
+        c = np.ascontiguousarray(chr_, dtype=np.int32)
+        if c.shape[0] != m:
+            raise ValueError("chr needs one code per SNP")
+        return c
+
+    def dense(self, chr=None, chisq=None):
+        c = self._chr(chr, self.m)
+        out = np.zeros((self.m, self.m), order="F")
+        _lib.check(self.L.hb_ldmat_dense(self.h, _ptr(c), int(chisq is not None), 0.0 if chisq is None else float(chisq),
+                                         out.ctypes.data, self.m))
+        return out
+
+    def sparse(self, chr=None, chisq=None):
+        import scipy.sparse as sp
+        c = self._chr(chr, self.m)
+        nnz = C.c_longlong(0)
+        _lib.check(self.L.hb_ldmat_sparse(self.h, _ptr(c), int(chisq is not None), 0.0 if chisq is None else float(chisq),
+                                          C.byref(nnz)))
+        colptr = np.zeros(self.m + 1, dtype=np.int64)
+        rowidx = np.zeros(max(nnz.value, 1), dtype=np.int32)
+        val = np.zeros(max(nnz.value, 1))
+        _lib.check(self.L.hb_ldmat_sparse_get(self.h, colptr.ctypes.data, rowidx.ctypes.data, val.ctypes.data))
+        return sp.csc_matrix((val[:nnz.value], rowidx[:nnz.value], colptr), shape=(self.m, self.m))
+
+    def last_ms(self):
+        ms = C.c_float(0)
+        _lib.check(self.L.hb_ldmat_last_ms(self.h, C.byref(ms)))
+        return ms.value
+
+
+def ldmat_plan(m, map_chr=None, chisq=None, ldchr=False):
+    """The branch ldmat() of the reference takes (R/ldm.r:44-94) for its arguments: returns
+    (kernel, chisq) with kernel in {"geno_dense", "geno_sparse", "chr_dense", "chr_sparse"}.
+    map_chr: the chromosome column of `map` (None = no map given)."""
+    if chisq is not None and chisq < 0:
+        chisq = None  # :45-47
+    if map_chr is not None:
+        map_chr = np.asarray(map_chr)
+        if map_chr.shape[0] != m:
+            raise ValueError("map needs one row per SNP")
+        one = len(set(map_chr.tolist())) == 1
+        if one:
+            ldchr = True  # :52
+        if chisq is not None and chisq == 0 and one:
+            chisq = None  # :53-55
+        if any(v is None or (isinstance(v, float) and math.isnan(v)) for v in map_chr.tolist()):
+            raise RuntimeError("NAs are not allowed in chromosome.")  # :60
+        if any(str(v) == "0" for v in map_chr.tolist()):
+            raise RuntimeError("0 is not allowed in chromosome.")  # :63
+    else:
+        if chisq is not None and chisq == 0:
+            chisq = None  # :80-82
+        ldchr = True  # :83
+    if ldchr:
+        # tXXmat_Geno: sparse only for chisq > 0 (tXXmat.cpp:118-121)
+        return ("geno_sparse" if (chisq is not None and chisq > 0) else "geno_dense"), chisq
+    return ("chr_sparse" if chisq is not None else "chr_dense"), chisq  # tXXmat_Chr, :520-523
+
+
+def ldmat(geno, map_chr=None, chisq=None, ldchr=False, device=0):
+    """ldmat() of the reference (R/ldm.r:31-112) without the gwas.geno merge: a dense ndarray for the
+    full matrix, a scipy CSC matrix where the reference returns a dgCMatrix."""
+    m = geno.shape[1]
+    kernel, chisq = ldmat_plan(m, map_chr, chisq, ldchr)
+    chr_codes = None
+    if kernel.startswith("chr"):
+        # non-numeric chromosome names become max+1, max+2, ... (R/ldm.r:67-76); only equality matters
+        names = [str(v) for v in np.asarray(map_chr).tolist()]
+        lut = {s: i for i, s in enumerate(dict.fromkeys(names))}
+        chr_codes = np.array([lut[s] for s in names], dtype=np.int32)
+    h = LdMat(geno, device=device)
+    try:
+        if kernel == "geno_dense":
+            return h.dense()
+        if kernel == "geno_sparse":
+            return h.sparse(chisq=chisq)
+        if kernel == "chr_dense":
+            return h.sparse(chr=chr_codes)
+        return h.sparse(chr=chr_codes, chisq=chisq)
+    finally:
+        h.close()
+
+
 def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, niter=50000, nburn=20000, thin=5,
           epsl_y_J=None, epsl_Gi=None, epsl_index=None, dfvr=None, s2vr=None, vg=None, dfvg=None, s2vg=None,
           ve=None, dfve=None, s2ve=None, windindx=None, outfreq=100, threads=0, verbose=False,
@@ -43,24 +207,32 @@ def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, nite
     L = _lib.load_library()
     y = np.ascontiguousarray(y, dtype=np.float64)
     n = y.shape[0]
-    X = np.asarray(X)
-    if X.shape[0] != n:
-        raise RuntimeError("Number of individuals not equals.")  # Bayes.cpp:96
-    if X.dtype == np.int8:
-        Xf, xt = np.asfortranarray(X), 1
+    bed_src = None
+    if isinstance(X, BedGeno):
+        if X.shape[0] != n:
+            raise RuntimeError("Number of individuals not equals.")  # Bayes.cpp:96
+        bed_src = X.c_struct()
+        Xf, xt, m = bed_src, 2, X.shape[1]
     else:
-        Xf, xt = np.asfortranarray(X, dtype=np.float64), 0
-    m = Xf.shape[1]
+        X = np.asarray(X)
+        if X.shape[0] != n:
+            raise RuntimeError("Number of individuals not equals.")  # Bayes.cpp:96
+        if X.dtype == np.int8:
+            Xf, xt = np.asfortranarray(X), 1
+        else:
+            Xf, xt = np.asfortranarray(X, dtype=np.float64), 0
+        m = Xf.shape[1]
     Pi = np.ascontiguousarray(Pi, dtype=np.float64)
     F = Pi.shape[0]
     fold_a = None if fold is None else np.ascontiguousarray(fold, dtype=np.float64)
     if fold_a is not None and fold_a.shape[0] != F:
         raise RuntimeError("length of Pi and fold not equals.")  # :115-117
     a = _lib.BayesArgs()
-    a.n, a.m, a.y, a.X, a.x_type = n, m, _ptr(y), _ptr(Xf), xt
+    a.n, a.m, a.y, a.x_type = n, m, _ptr(y), xt
+    a.X = C.addressof(bed_src) if bed_src is not None else _ptr(Xf)
     a.model = model.encode()
     a.n_fold, a.Pi, a.fold = F, _ptr(Pi), _ptr(fold_a)
-    keep = [y, Xf, Pi, fold_a]
+    keep = [y, Xf, X, Pi, fold_a]
     nc = 0
     if C_ is not None:
         Cf = np.asfortranarray(C_, dtype=np.float64)
@@ -255,6 +427,10 @@ class Engine:
                 "geno_bytes": g.value, "gram_bytes": h.value}
 
     def load_geno(self, X):
+        if isinstance(X, BedGeno):
+            _lib.check(self.L.hb_engine_load_bed(self.h, X.image.ctypes.data, X.image.shape[0], X.nid, _ptr(X.rows),
+                                                 int(X.impute), int(X.dominance)))
+            return
         X = np.asarray(X)
         if X.dtype == np.int8:
             Xf = np.asfortranarray(X)

@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "../../include/hibayes_b200.h"
+#include "hb_bed.cuh"
 #include "hb_device.cuh"
 #include "hb_rng.h"
 #include "hb_sweep.cuh"
@@ -128,6 +129,31 @@ __global__ void k_pack_i8(const int8_t* __restrict__ src, size_t ld, int n, int 
     size_t row = row0 + i;
     uint32_t x = (row < (size_t)n) ? (uint32_t)(uint8_t)col[row] : 0u;
     w[i >> 2] |= x << (8 * (i & 3));
+  }
+  int j = col0 + c, t = j / B, cj = j % B;
+  uint4* dst = (uint4*)(Xp + ((((size_t)s * T + t) * B + cj) * R + 16 * rg));
+  *dst = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// The same layout straight from a PLINK .bed column (2 bits per genotype, hb_bed.cuh): one thread per
+// 16-row chunk of one SNP; output row i is file individual rows[i] (or i), missing genotypes become the
+// SNP's major genotype (read_bed.cpp:186-229).
+__global__ void k_pack_bed(const uint8_t* __restrict__ bed, size_t bps, const int32_t* __restrict__ rows, int n, int col0,
+                           int ncols, int d, const uint8_t* __restrict__ info, uint8_t* __restrict__ Xp, int S, int R, int NRG,
+                           int T, int B) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t per_col = (size_t)S * NRG;
+  if (idx >= per_col * ncols) return;
+  int c = (int)(idx / per_col);
+  int ch = (int)(idx % per_col);
+  int s = ch / NRG, rg = ch % NRG;
+  size_t row0 = (size_t)s * R + 16 * rg;
+  const uint8_t* src = bed + (size_t)c * bps;
+  uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    size_t row = row0 + i;
+    if (row < (size_t)n) w[i >> 2] |= (uint32_t)hb::bed_value(src, rows, row, d, 1, 0, info[c]) << (8 * (i & 3));
   }
   int j = col0 + c, t = j / B, cj = j % B;
   uint4* dst = (uint4*)(Xp + ((((size_t)s * T + t) * B + cj) * R + 16 * rg));
@@ -811,6 +837,60 @@ extern "C" int hb_engine_load_geno_f64(hb_engine* e, const double* X, size_t ld)
   if (!e || !X) return hb_set_error("hb_engine_load_geno_f64: null argument");
   if (ld < (size_t)e->n) return hb_set_error("hb_engine_load_geno_f64: ld < n");
   return load_chunked(e, nullptr, X, ld);
+}
+
+// PLINK .bed image -> device tiles without the fp64 / big.matrix detour of R/bayes.r:284.
+extern "C" int hb_engine_load_bed(hb_engine* e, const uint8_t* file, size_t len, int nid, const int32_t* rows, int impt,
+                                  int dominance) {
+  if (!e || !file) return hb_set_error("hb_engine_load_bed: null argument");
+  if (nid <= 0) return hb_set_error("hb_engine_load_bed: nid must be positive");
+  const size_t bps = ((size_t)nid + 3) / 4;
+  if (len < 3 || file[0] != 0x6c || file[1] != 0x1b) return hb_set_error("hb_engine_load_bed: not a PLINK .bed image (magic bytes)");
+  if (file[2] != 0x01) return hb_set_error("hb_engine_load_bed: individual-major .bed files are not supported");
+  if (len < 3 + bps * (size_t)e->m) return hb_set_error("hb_engine_load_bed: image has %zu bytes, %zu needed for %d individuals x %d SNPs", len, 3 + bps * (size_t)e->m, nid, e->m);
+  if (!rows && nid != e->n) return hb_set_error("hb_engine_load_bed: the file has %d individuals, the engine %d rows; pass the row selection", nid, e->n);
+  if (rows)
+    for (int i = 0; i < e->n; ++i)
+      if (rows[i] < 0 || rows[i] >= nid) return hb_set_error("hb_engine_load_bed: rows[%d] = %d outside the file's %d individuals", i, rows[i], nid);
+  CU(cudaSetDevice(e->cfg.device));
+  const size_t cols_per_chunk = std::min<size_t>((size_t)e->m, std::max<size_t>(1, (size_t)(256u << 20) / bps));
+  uint8_t *stage = nullptr, *info = nullptr;
+  int32_t* drows = nullptr;
+  std::vector<uint8_t> hinfo(cols_per_chunk);
+  int rc = 0;
+#define TRYB(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { rc = hb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); goto done; } } while (0)
+  TRYB(cudaMalloc(&stage, cols_per_chunk * bps));
+  TRYB(cudaMalloc(&info, cols_per_chunk));
+  if (rows) {
+    TRYB(cudaMalloc(&drows, (size_t)e->n * 4));
+    TRYB(cudaMemcpyAsync(drows, rows, (size_t)e->n * 4, cudaMemcpyHostToDevice, e->stream));
+  }
+  for (size_t c0 = 0; c0 < (size_t)e->m; c0 += cols_per_chunk) {
+    const size_t nc = std::min(cols_per_chunk, (size_t)e->m - c0);
+    TRYB(cudaMemcpyAsync(stage, file + 3 + c0 * bps, nc * bps, cudaMemcpyHostToDevice, e->stream));
+    hb::k_bed_info<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, e->stream>>>(stage, bps, nid, (int)nc, dominance, info);
+    TRYB(cudaGetLastError());
+    if (!impt) {
+      TRYB(cudaMemcpyAsync(hinfo.data(), info, nc, cudaMemcpyDeviceToHost, e->stream));
+      TRYB(cudaStreamSynchronize(e->stream));
+      for (size_t c = 0; c < nc; ++c)
+        if (hinfo[c] & 0x80) {
+          rc = hb_set_error("hb_engine_load_bed: SNP %zu has missing genotypes and impute is off; this engine holds genotypes in {0,1,2}", c0 + c);
+          goto done;
+        }
+    }
+    const size_t work = (size_t)e->S * e->NRG * nc;
+    k_pack_bed<<<(unsigned)((work + 255) / 256), 256, 0, e->stream>>>(stage, bps, drows, e->n, (int)c0, (int)nc, dominance, info,
+                                                                     e->Xp, e->S, e->R, e->NRG, e->T, e->B);
+    TRYB(cudaGetLastError());
+    TRYB(cudaStreamSynchronize(e->stream));
+  }
+  e->geno_ready = true;
+  e->gram_ready = false;
+done:
+#undef TRYB
+  cudaFree(stage); cudaFree(info); cudaFree(drows);
+  return rc;
 }
 
 extern "C" int hb_engine_synth_geno(hb_engine* e, uint64_t seed, int64_t row_offset) {

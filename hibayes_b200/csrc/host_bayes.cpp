@@ -180,7 +180,10 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
   cfg.n_slabs = a->n_slabs; cfg.seed = a->seed; cfg.rank = world > 1 ? a->rank : 0; cfg.world = world;
   HBCHK(hb_engine_create(&cfg, &guard.e));
   hb_engine* E = guard.e;
-  if (a->x_type == 1) HBCHK(hb_engine_load_geno_i8(E, (const int8_t*)a->X, (size_t)n));
+  if (a->x_type == 2) {
+    const hb_bed_source* b = (const hb_bed_source*)a->X;
+    HBCHK(hb_engine_load_bed(E, b->file, b->len, b->nid, b->rows, b->impt, b->dominance));
+  } else if (a->x_type == 1) HBCHK(hb_engine_load_geno_i8(E, (const int8_t*)a->X, (size_t)n));
   else HBCHK(hb_engine_load_geno_f64(E, (const double*)a->X, (size_t)n));
   std::vector<double> xpx(m), sumx(m), vx(m);
   HBCHK(hb_engine_col_stats(E, xpx.data(), sumx.data()));

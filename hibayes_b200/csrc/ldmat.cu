@@ -1,0 +1,605 @@
+// ldmat.cu -- the two stages in front of the Gibbs sweeps on the device:
+//
+//   * hb_ldmat_*      the LD / X'X builder: tXXmat_Geno() and tXXmat_Chr() of
+//                     /root/reference/src/tXXmat.cpp:100-185, 504-605 with BigStat() (:43-77).  The
+//                     reference's O(m^2 n) scalar triple loop becomes an exact int8 x int8 -> int32
+//                     tensor-core Gram (mma.sync m16n8k32; products of genotypes are small integers,
+//                     so the inner product is exact) with the centring, the r^2 n <= chisq filter
+//                     and the fp64 conversion fused into the epilogue, evaluated in the reference's
+//                     operation order (so every off-diagonal entry is bit-identical to the oracle).
+//   * hb_bed_decode   read_bed<char>() of /root/reference/src/read_bed.cpp:97-232 (hb_bed.cuh).
+//
+// Data layout: Xc[Mpad][Kpad] int8, one row per SNP, individuals contiguous (K-major for both mma
+// operands), zero padded to Kpad = 128-multiple of n and Mpad = 64-multiple of m.  The m x m result is
+// produced in column panels of W columns (fp64, column-major, <= 1 GiB) that are either copied to the
+// caller's dense matrix or compacted on the device into CSC (dgCMatrix) pieces.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/hibayes_b200.h"
+#include "hb_bed.cuh"
+#include "hb_device.cuh"
+
+int hb_set_error(const char* fmt, ...);  // engine.cu
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return hb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                          cudaGetErrorString(_e));                                                \
+  } while (0)
+
+struct hb_ldmat {
+  int device = 0, n = 0, m = 0, Kpad = 0, Mpad = 0, panel_cols = 0;
+  int8_t* Xc = nullptr;
+  double *sum = nullptr, *mean = nullptr, *xx = nullptr;
+  int32_t* chr = nullptr;
+  double* pan = nullptr;
+  size_t pan_elems = 0;
+  bool loaded = false, stats_ready = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float ms_gram = 0.f;
+  std::vector<long long> colptr;
+  std::vector<int32_t> rowidx;
+  std::vector<double> val;
+  bool sparse_ready = false;
+};
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+// BigStat (tXXmat.cpp:43-77).  One thread per SNP, individuals in file order: the second pass is a
+// sequential fp64 sum of (x - mean)^2 whose rounding depends on the order, and the sparse branch
+// thresholds on it (:142-143), so the order is kept.  The first pass sums integers (exact).
+__global__ void k_ld_stats(const int8_t* __restrict__ Xc, int Kpad, int n, int m, double* __restrict__ sum,
+                           double* __restrict__ mean, double* __restrict__ xx) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const int8_t* row = Xc + (size_t)j * Kpad;
+  long long s = 0;
+  for (int k0 = 0; k0 < Kpad; k0 += 16) {  // padding bytes are 0
+    const int4 v = *(const int4*)(row + k0);
+    const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s += (int8_t)(w[q]) + (int8_t)(w[q] >> 8) + (int8_t)(w[q] >> 16) + (int8_t)(w[q] >> 24);
+  }
+  const double sm = (double)s;
+  const double mu = __ddiv_rn(sm, (double)n);
+  double p1 = 0.0;
+  for (int k0 = 0; k0 < n; k0 += 16) {
+    const int4 v = *(const int4*)(row + k0);
+    const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      if (k0 + q < n) {
+        const double dv = __dsub_rn((double)(int8_t)(w[q >> 2] >> (8 * (q & 3))), mu);
+        p1 = __dadd_rn(p1, __dmul_rn(dv, dv));
+      }
+    }
+  }
+  sum[j] = sm;
+  mean[j] = mu;
+  xx[j] = __dsqrt_rn(p1);
+}
+
+struct LdEpi {
+  const double *sum, *mean, *xx;
+  const int32_t* chr;  // may be null
+  int n, m, has_chisq;
+  double chisq;
+};
+
+// One LD entry from the exact inner product (tXXmat.cpp:141-148 / :157): the statistics of the SNP
+// with the smaller index play the role of sum1/m1/p1 (outer loop variable j of the reference).
+__device__ __forceinline__ double ld_entry(const LdEpi& e, int i, int j, int G) {
+  if (e.chr && e.chr[i] != e.chr[j]) return 0.0;
+  const int lo = min(i, j), hi = max(i, j);
+  const double ind = (double)e.n;
+  const double p1 = e.xx[lo];
+  if (!e.has_chisq && lo == hi) return __ddiv_rn(__dmul_rn(p1, p1), ind);
+  const double m1 = e.mean[lo], sum1 = e.sum[lo];
+  const double p2 = e.xx[hi], m2 = e.mean[hi], sum2 = e.sum[hi];
+  const double t = __dsub_rn(__dadd_rn(__dmul_rn(sum1, m2), __dmul_rn(sum2, m1)), __dmul_rn(__dmul_rn(ind, m1), m2));
+  const double p12 = __dsub_rn((double)G, t);
+  if (e.has_chisq) {
+    const double r = __ddiv_rn(p12, __dmul_rn(p1, p2));
+    if (__dmul_rn(__dmul_rn(r, r), ind) <= e.chisq) return 0.0;
+  }
+  return __ddiv_rn(p12, ind);
+}
+
+constexpr int LD_RK = 128;              // individuals (bytes) per stage
+constexpr int LD_STRIDE = LD_RK + 16;   // padded shared-memory row: conflict-free ldmatrix
+__device__ __forceinline__ void ld_cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(hb::smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ld_ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(hb::smem_u32(p)));
+}
+__device__ __forceinline__ void ld_imma_s8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// CTA = 64 x 64 entries: rows [64 bx, +64) x panel columns [j0 + 64 by, +64); 4 warps of 32 x 32;
+// 128 individuals per stage through a double-buffered cp.async pipeline, fragments by ldmatrix (the
+// structure of k_gram_imma in engine.cu, which builds the sweep's band Gram).  pan is column-major
+// with leading dimension m.
+__global__ void __launch_bounds__(128) k_ld_panel(const int8_t* __restrict__ Xc, int Kpad, int j0, LdEpi epi,
+                                                  double* __restrict__ pan) {
+  __shared__ __align__(16) uint8_t As[2][64 * LD_STRIDE];
+  __shared__ __align__(16) uint8_t Bs[2][64 * LD_STRIDE];
+  const int a0 = blockIdx.x * 64;
+  const int b0 = j0 + blockIdx.y * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  int acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[i][j][k] = 0;
+  const int nchunks = Kpad / LD_RK;
+  auto issue = [&](int ch, int buf) {
+    const int8_t* Abase = Xc + (size_t)a0 * Kpad + (size_t)ch * LD_RK;
+    const int8_t* Bbase = Xc + (size_t)b0 * Kpad + (size_t)ch * LD_RK;
+    // 64 SNP rows x 8 vectors of 16 B per operand = 512 vectors; 128 threads -> 4 + 4 each
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int v = tid + 128 * q;
+      const int c = v >> 3, w = v & 7;
+      ld_cp_async16(&As[buf][c * LD_STRIDE + 16 * w], Abase + (size_t)c * Kpad + 16 * w);
+      ld_cp_async16(&Bs[buf][c * LD_STRIDE + 16 * w], Bbase + (size_t)c * Kpad + 16 * w);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0, 0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunks) {
+      issue(ch + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < LD_RK / 32; ++ks) {
+      uint32_t af[2][4], bf[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int row = wm + 16 * i + (lane & 7) + 8 * ((lane >> 3) & 1);
+        ld_ldmatrix_x4(af[i], &As[buf][row * LD_STRIDE + 32 * ks + 16 * (lane >> 4)]);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int row = wn + 16 * j + (lane & 7) + 8 * (lane >> 4);
+        ld_ldmatrix_x4(bf[j], &Bs[buf][row * LD_STRIDE + 32 * ks + 16 * ((lane >> 3) & 1)]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ld_imma_s8(acc[i][j], af[i], bf[j >> 1][2 * (j & 1)], bf[j >> 1][2 * (j & 1) + 1]);
+    }
+    __syncthreads();
+  }
+  // epilogue: accumulator element (row, col) per the m16n8 C layout
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int row = a0 + wm + 16 * i + (lane >> 2) + 8 * (k >> 1);
+        const int col = b0 + wn + 8 * j + 2 * (lane & 3) + (k & 1);
+        if (row < epi.m && col < epi.m) pan[(size_t)(col - j0) * epi.m + row] = ld_entry(epi, row, col, acc[i][j][k]);
+      }
+}
+
+// Stored entries per panel column: what an arma::sp_mat keeps is every assigned value != 0.
+__global__ void k_ld_count(const double* __restrict__ pan, int m, int wcols, int* __restrict__ counts) {
+  const int w = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= wcols) return;
+  const double* col = pan + (size_t)w * m;
+  int c = 0;
+  for (int i = lane; i < m; i += 32) c += (col[i] != 0.0) ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) counts[w] = c;
+}
+// Ordered compaction of one panel column per warp (row indices ascending, as in a dgCMatrix).
+__global__ void k_ld_compact(const double* __restrict__ pan, int m, int wcols, const long long* __restrict__ off,
+                             int32_t* __restrict__ rowidx, double* __restrict__ val) {
+  const int w = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= wcols) return;
+  const double* col = pan + (size_t)w * m;
+  long long base = off[w];
+  for (int i0 = 0; i0 < m; i0 += 32) {
+    const int i = i0 + lane;
+    const double v = (i < m) ? col[i] : 0.0;
+    const bool keep = v != 0.0;
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const long long pos = base + __popc(mask & ((1u << lane) - 1u));
+      rowidx[pos] = i;
+      val[pos] = v;
+    }
+    base += __popc(mask);
+  }
+}
+
+// .bed -> Xc rows: one thread per 16 individuals of one SNP (bytes beyond n stay 0).
+__global__ void k_bed_to_rows(const uint8_t* __restrict__ bed, size_t bps, const int32_t* __restrict__ rows, int n, int col0,
+                              int ncols, int d, int impt, int na, const uint8_t* __restrict__ info, int8_t* __restrict__ Xc,
+                              int Kpad) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per_col = (size_t)Kpad / 16;
+  if (idx >= per_col * (size_t)ncols) return;
+  const int c = (int)(idx / per_col);
+  const size_t row0 = (idx % per_col) * 16;
+  const uint8_t* src = bed + (size_t)c * bps;
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const size_t row = row0 + i;
+    if (row < (size_t)n) w[i >> 2] |= (uint32_t)(uint8_t)hb::bed_value(src, rows, row, d, impt, na, info[c]) << (8 * (i & 3));
+  }
+  *(uint4*)(Xc + (size_t)(col0 + c) * Kpad + row0) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// .bed -> plain column-major int8 (the "char" big.matrix read_bed() fills), one thread per genotype.
+__global__ void k_bed_to_colmajor(const uint8_t* __restrict__ bed, size_t bps, int nid, int ncols, int d, int impt, int na,
+                                  const uint8_t* __restrict__ info, int8_t* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)nid * (size_t)ncols) return;
+  const int c = (int)(idx / (size_t)nid);
+  const size_t row = idx % (size_t)nid;
+  out[idx] = (int8_t)hb::bed_value(bed + (size_t)c * bps, nullptr, row, d, impt, na, info[c]);
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+static int check_bed_image(const uint8_t* file, size_t len, long long nid, long long m, size_t* bps_out) {
+  if (!file) return hb_set_error("bed: null file image");
+  if (nid <= 0 || m <= 0) return hb_set_error("bed: need at least one individual and one SNP");
+  const size_t bps = (size_t)((nid + 3) / 4);
+  if (len < 3 || file[0] != 0x6c || file[1] != 0x1b) return hb_set_error("bed: not a PLINK .bed image (magic bytes)");
+  if (file[2] != 0x01) return hb_set_error("bed: individual-major .bed files are not supported (third byte must be 0x01)");
+  if (len < 3 + bps * (size_t)m) return hb_set_error("bed: image has %zu bytes, %zu needed for %lld individuals x %lld SNPs", len, 3 + bps * (size_t)m, nid, m);
+  *bps_out = bps;
+  return 0;
+}
+
+extern "C" int hb_ldmat_create(int device, int n, int m, hb_ldmat** out) {
+  if (!out) return hb_set_error("hb_ldmat_create: null out");
+  *out = nullptr;
+  if (n <= 0 || m <= 0) return hb_set_error("hb_ldmat_create: n and m must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return hb_set_error("hb_ldmat_create: no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return hb_set_error("hb_ldmat_create: device %d out of range", device);
+  CU(cudaSetDevice(device));
+  hb_ldmat* h = new hb_ldmat();
+  h->device = device;
+  h->n = n;
+  h->m = m;
+  h->Kpad = (n + LD_RK - 1) / LD_RK * LD_RK;
+  h->Mpad = (m + 63) / 64 * 64;
+  // panel of at most 1 GiB of fp64
+  long long W = ((1ll << 27) / m) / 64 * 64;
+  h->panel_cols = (int)std::min<long long>(h->Mpad, std::max<long long>(64, W));
+#define LDCK(call)                 \
+  do {                             \
+    if ((call) != cudaSuccess) {   \
+      cudaError_t _e = cudaGetLastError(); \
+      hb_ldmat_destroy(h);         \
+      return hb_set_error("hb_ldmat_create: %s", cudaGetErrorString(_e)); \
+    }                              \
+  } while (0)
+  LDCK(cudaStreamCreate(&h->stream));
+  LDCK(cudaEventCreate(&h->ev0));
+  LDCK(cudaEventCreate(&h->ev1));
+  LDCK(cudaMalloc(&h->Xc, (size_t)h->Mpad * h->Kpad));
+  LDCK(cudaMalloc(&h->sum, (size_t)m * 8));
+  LDCK(cudaMalloc(&h->mean, (size_t)m * 8));
+  LDCK(cudaMalloc(&h->xx, (size_t)m * 8));
+  LDCK(cudaMalloc(&h->chr, (size_t)m * 4));
+#undef LDCK
+  *out = h;
+  return 0;
+}
+
+extern "C" void hb_ldmat_destroy(hb_ldmat* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->Xc); cudaFree(h->sum); cudaFree(h->mean); cudaFree(h->xx); cudaFree(h->chr); cudaFree(h->pan);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int hb_ldmat_set_panel_cols(hb_ldmat* h, int cols) {
+  if (!h) return hb_set_error("hb_ldmat_set_panel_cols: null handle");
+  if (cols < 64 || cols % 64) return hb_set_error("hb_ldmat_set_panel_cols: need a positive multiple of 64");
+  h->panel_cols = std::min(cols, h->Mpad);
+  return 0;
+}
+
+extern "C" int hb_ldmat_load_i8(hb_ldmat* h, const int8_t* X, size_t ld) {
+  if (!h || !X) return hb_set_error("hb_ldmat_load_i8: null argument");
+  if (ld < (size_t)h->n) return hb_set_error("hb_ldmat_load_i8: ld < n");
+  // the int32 accumulators hold sum |x_i x_j| only while max|x|^2 n < 2^31
+  int amax = 0;
+  for (int j = 0; j < h->m; ++j) {
+    const int8_t* col = X + (size_t)j * ld;
+    for (int i = 0; i < h->n; ++i) amax = std::max(amax, std::abs((int)col[i]));
+  }
+  if ((double)amax * amax * h->n >= 2147483648.0)
+    return hb_set_error("hb_ldmat_load_i8: |x| up to %d over %d individuals overflows the exact int32 inner product", amax, h->n);
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemsetAsync(h->Xc, 0, (size_t)h->Mpad * h->Kpad, h->stream));
+  CU(cudaMemcpy2DAsync(h->Xc, (size_t)h->Kpad, X, ld, (size_t)h->n, (size_t)h->m, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->loaded = true;
+  h->stats_ready = false;
+  h->sparse_ready = false;
+  return 0;
+}
+
+extern "C" int hb_ldmat_load_bed(hb_ldmat* h, const uint8_t* file, size_t len, int nid, const int32_t* rows, int impt,
+                                 int dominance) {
+  if (!h) return hb_set_error("hb_ldmat_load_bed: null handle");
+  size_t bps = 0;
+  if (check_bed_image(file, len, nid, h->m, &bps)) return 1;
+  if (!rows && nid != h->n) return hb_set_error("hb_ldmat_load_bed: the file has %d individuals, the handle %d; pass the row selection", nid, h->n);
+  if (rows)
+    for (int i = 0; i < h->n; ++i)
+      if (rows[i] < 0 || rows[i] >= nid) return hb_set_error("hb_ldmat_load_bed: rows[%d] = %d outside the file's %d individuals", i, rows[i], nid);
+  CU(cudaSetDevice(h->device));
+  const int na = -128;  // NA_CHAR of bigmemory (read_bed.cpp:241)
+  const size_t cols_per_chunk = std::min<size_t>((size_t)h->m, std::max<size_t>(1, (size_t)(256u << 20) / bps));
+  uint8_t *stage = nullptr, *info = nullptr;
+  int32_t* drows = nullptr;
+  int rc = 0;
+  auto fail = [&](cudaError_t e, int line) {
+    rc = hb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e), __FILE__, line, cudaGetErrorString(e));
+  };
+#define TRY(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { fail(_e, __LINE__); goto done; } } while (0)
+  TRY(cudaMalloc(&stage, cols_per_chunk * bps));
+  TRY(cudaMalloc(&info, cols_per_chunk));
+  if (rows) {
+    TRY(cudaMalloc(&drows, (size_t)h->n * 4));
+    TRY(cudaMemcpyAsync(drows, rows, (size_t)h->n * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  TRY(cudaMemsetAsync(h->Xc, 0, (size_t)h->Mpad * h->Kpad, h->stream));
+  for (size_t c0 = 0; c0 < (size_t)h->m; c0 += cols_per_chunk) {
+    const size_t nc = std::min(cols_per_chunk, (size_t)h->m - c0);
+    TRY(cudaMemcpyAsync(stage, file + 3 + c0 * bps, nc * bps, cudaMemcpyHostToDevice, h->stream));
+    hb::k_bed_info<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, h->stream>>>(stage, bps, nid, (int)nc, dominance, info);
+    const size_t work = (size_t)(h->Kpad / 16) * nc;
+    k_bed_to_rows<<<(unsigned)((work + 255) / 256), 256, 0, h->stream>>>(stage, bps, drows, h->n, (int)c0, (int)nc, dominance, impt,
+                                                                        na, info, h->Xc, h->Kpad);
+    TRY(cudaGetLastError());
+    TRY(cudaStreamSynchronize(h->stream));
+  }
+  h->loaded = true;
+  h->stats_ready = false;
+  h->sparse_ready = false;
+done:
+#undef TRY
+  cudaFree(stage); cudaFree(info); cudaFree(drows);
+  return rc;
+}
+
+static int ensure_stats(hb_ldmat* h) {
+  if (!h->loaded) return hb_set_error("hb_ldmat: genotypes not loaded");
+  if (h->stats_ready) return 0;
+  CU(cudaSetDevice(h->device));
+  k_ld_stats<<<(h->m + 127) / 128, 128, 0, h->stream>>>(h->Xc, h->Kpad, h->n, h->m, h->sum, h->mean, h->xx);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  h->stats_ready = true;
+  return 0;
+}
+
+extern "C" int hb_ldmat_stats(hb_ldmat* h, double* mean, double* sum, double* xx) {
+  if (!h) return hb_set_error("hb_ldmat_stats: null handle");
+  if (ensure_stats(h)) return 1;
+  if (mean) CU(cudaMemcpy(mean, h->mean, (size_t)h->m * 8, cudaMemcpyDeviceToHost));
+  if (sum) CU(cudaMemcpy(sum, h->sum, (size_t)h->m * 8, cudaMemcpyDeviceToHost));
+  if (xx) CU(cudaMemcpy(xx, h->xx, (size_t)h->m * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// Runs the panels; per panel calls sink(j0, wcols) with the panel (column-major, ld = m) complete on the stream.
+template <class Sink>
+static int run_panels(hb_ldmat* h, const int32_t* chr, int has_chisq, double chisq, Sink sink) {
+  if (ensure_stats(h)) return 1;
+  CU(cudaSetDevice(h->device));
+  if (chr) CU(cudaMemcpyAsync(h->chr, chr, (size_t)h->m * 4, cudaMemcpyHostToDevice, h->stream));
+  const int W = h->panel_cols;
+  const size_t need = (size_t)W * h->m;
+  if (h->pan_elems < need) {
+    cudaFree(h->pan);
+    h->pan = nullptr;
+    h->pan_elems = 0;
+    CU(cudaMalloc(&h->pan, need * 8));
+    h->pan_elems = need;
+  }
+  LdEpi epi{h->sum, h->mean, h->xx, chr ? h->chr : nullptr, h->n, h->m, has_chisq, chisq};
+  h->ms_gram = 0.f;
+  for (int j0 = 0; j0 < h->m; j0 += W) {
+    const int wpad = std::min(W, h->Mpad - j0);
+    const int wcols = std::min(W, h->m - j0);
+    CU(cudaEventRecord(h->ev0, h->stream));
+    k_ld_panel<<<dim3(h->Mpad / 64, wpad / 64), 128, 0, h->stream>>>(h->Xc, h->Kpad, j0, epi, h->pan);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev1, h->stream));
+    if (sink(j0, wcols)) return 1;
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->ms_gram += ms;
+  }
+  return 0;
+}
+
+extern "C" int hb_ldmat_dense(hb_ldmat* h, const int32_t* chr, int has_chisq, double chisq, double* out, size_t ldo) {
+  if (!h || !out) return hb_set_error("hb_ldmat_dense: null argument");
+  if (ldo < (size_t)h->m) return hb_set_error("hb_ldmat_dense: ldo < m");
+  if (has_chisq && !(chisq >= 0)) return hb_set_error("hb_ldmat_dense: chisq must be >= 0");
+  return run_panels(h, chr, has_chisq, chisq, [&](int j0, int wcols) -> int {
+    CU(cudaMemcpy2DAsync(out + (size_t)j0 * ldo, ldo * 8, h->pan, (size_t)h->m * 8, (size_t)h->m * 8, (size_t)wcols,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+  });
+}
+
+extern "C" int hb_ldmat_sparse(hb_ldmat* h, const int32_t* chr, int has_chisq, double chisq, long long* nnz) {
+  if (!h) return hb_set_error("hb_ldmat_sparse: null handle");
+  if (has_chisq && !(chisq >= 0)) return hb_set_error("hb_ldmat_sparse: chisq must be >= 0");
+  h->sparse_ready = false;
+  h->colptr.assign((size_t)h->m + 1, 0);
+  h->rowidx.clear();
+  h->val.clear();
+  int* dcounts = nullptr;
+  long long* doff = nullptr;
+  int32_t* drow = nullptr;
+  double* dval = nullptr;
+  size_t cap = 0;
+  CU(cudaSetDevice(h->device));
+  CU(cudaMalloc(&dcounts, (size_t)h->panel_cols * 4));
+  if (cudaMalloc(&doff, (size_t)h->panel_cols * 8) != cudaSuccess) { cudaFree(dcounts); return hb_set_error("hb_ldmat_sparse: out of device memory"); }
+  std::vector<int> counts((size_t)h->panel_cols);
+  std::vector<long long> off((size_t)h->panel_cols);
+  int rc = run_panels(h, chr, has_chisq, chisq, [&](int j0, int wcols) -> int {
+    const unsigned blocks = (unsigned)(((size_t)wcols * 32 + 255) / 256);
+    k_ld_count<<<blocks, 256, 0, h->stream>>>(h->pan, h->m, wcols, dcounts);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(counts.data(), dcounts, (size_t)wcols * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    long long tot = 0;
+    for (int w = 0; w < wcols; ++w) {
+      off[w] = tot;
+      tot += counts[w];
+      h->colptr[(size_t)j0 + w + 1] = counts[w];
+    }
+    if (tot == 0) return 0;
+    if ((size_t)tot > cap) {
+      cudaFree(drow); cudaFree(dval);
+      drow = nullptr; dval = nullptr; cap = 0;
+      CU(cudaMalloc(&drow, (size_t)tot * 4));
+      CU(cudaMalloc(&dval, (size_t)tot * 8));
+      cap = (size_t)tot;
+    }
+    CU(cudaMemcpyAsync(doff, off.data(), (size_t)wcols * 8, cudaMemcpyHostToDevice, h->stream));
+    k_ld_compact<<<blocks, 256, 0, h->stream>>>(h->pan, h->m, wcols, doff, drow, dval);
+    CU(cudaGetLastError());
+    const size_t old = h->rowidx.size();
+    h->rowidx.resize(old + (size_t)tot);
+    h->val.resize(old + (size_t)tot);
+    CU(cudaMemcpyAsync(h->rowidx.data() + old, drow, (size_t)tot * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->val.data() + old, dval, (size_t)tot * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+  });
+  cudaFree(dcounts); cudaFree(doff); cudaFree(drow); cudaFree(dval);
+  if (rc) return rc;
+  for (int j = 0; j < h->m; ++j) h->colptr[(size_t)j + 1] += h->colptr[(size_t)j];
+  h->sparse_ready = true;
+  if (nnz) *nnz = h->colptr[(size_t)h->m];
+  return 0;
+}
+
+extern "C" int hb_ldmat_sparse_get(hb_ldmat* h, long long* colptr, int32_t* rowidx, double* val) {
+  if (!h || !colptr || !rowidx || !val) return hb_set_error("hb_ldmat_sparse_get: null argument");
+  if (!h->sparse_ready) return hb_set_error("hb_ldmat_sparse_get: call hb_ldmat_sparse first");
+  memcpy(colptr, h->colptr.data(), ((size_t)h->m + 1) * sizeof(long long));
+  if (!h->rowidx.empty()) {
+    memcpy(rowidx, h->rowidx.data(), h->rowidx.size() * 4);
+    memcpy(val, h->val.data(), h->val.size() * 8);
+  }
+  return 0;
+}
+
+extern "C" int hb_ldmat_last_ms(hb_ldmat* h, float* gram_ms) {
+  if (!h || !gram_ms) return hb_set_error("hb_ldmat_last_ms: null argument");
+  *gram_ms = h->ms_gram;
+  return 0;
+}
+
+// read_bed() into the caller's "char" big.matrix memory (nid x m column-major), miss = per-SNP flag.
+extern "C" int hb_bed_decode(int device, const uint8_t* file, size_t len, int nid, int m, int impt, int dominance,
+                             int8_t* out, uint8_t* miss) {
+  if (!out) return hb_set_error("hb_bed_decode: null out");
+  size_t bps = 0;
+  if (check_bed_image(file, len, nid, m, &bps)) return 1;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return hb_set_error("hb_bed_decode: no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return hb_set_error("hb_bed_decode: device %d out of range", device);
+  CU(cudaSetDevice(device));
+  const int na = -128;
+  const size_t cols_per_chunk = std::min<size_t>((size_t)m, std::max<size_t>(1, (size_t)(64u << 20) / bps));
+  uint8_t *stage = nullptr, *info = nullptr;
+  int8_t* dout = nullptr;
+  std::vector<uint8_t> hinfo(cols_per_chunk);
+  int rc = 0;
+#define TRY(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { rc = hb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); goto done; } } while (0)
+  TRY(cudaMalloc(&stage, cols_per_chunk * bps));
+  TRY(cudaMalloc(&info, cols_per_chunk));
+  TRY(cudaMalloc(&dout, cols_per_chunk * (size_t)nid));
+  for (size_t c0 = 0; c0 < (size_t)m; c0 += cols_per_chunk) {
+    const size_t nc = std::min(cols_per_chunk, (size_t)m - c0);
+    TRY(cudaMemcpy(stage, file + 3 + c0 * bps, nc * bps, cudaMemcpyHostToDevice));
+    hb::k_bed_info<<<(unsigned)((nc * 32 + 255) / 256), 256>>>(stage, bps, nid, (int)nc, dominance, info);
+    const size_t work = nc * (size_t)nid;
+    k_bed_to_colmajor<<<(unsigned)((work + 255) / 256), 256>>>(stage, bps, nid, (int)nc, dominance, impt, na, info, dout);
+    TRY(cudaGetLastError());
+    TRY(cudaMemcpy(out + c0 * (size_t)nid, dout, work, cudaMemcpyDeviceToHost));
+    if (miss) {
+      TRY(cudaMemcpy(hinfo.data(), info, nc, cudaMemcpyDeviceToHost));
+      for (size_t c = 0; c < nc; ++c) miss[c0 + c] = hinfo[c] >> 7;
+    }
+  }
+done:
+#undef TRY
+  cudaFree(stage); cudaFree(info); cudaFree(dout);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// host builds of the byte-level decode code, for the CPU tests (no device needed)
+// ------------------------------------------------------------------------------------------
+// Decodes one SNP's byte row with the very functions the kernels use (bed_count_byte, bed_major,
+// bed_field, bed_code): out[row] for `n` output rows, *info = major | missing << 7.
+extern "C" int hb_test_bed_decode_snp(const uint8_t* snp_bytes, int nid, const int32_t* rows, int n, int impt, int dominance,
+                                      int8_t* out, uint8_t* info_out) {
+  if (!snp_bytes || !out || nid <= 0 || n < 0) return hb_set_error("hb_test_bed_decode_snp: bad argument");
+  unsigned c[4] = {0u, 0u, 0u, 0u};
+  const size_t full = (size_t)nid >> 2;
+  for (size_t b = 0; b < full; ++b) hb::bed_count_byte(snp_bytes[b], 4, c);
+  if (nid & 3) hb::bed_count_byte(snp_bytes[full], nid & 3, c);
+  const unsigned long long t[4] = {c[0], c[1], c[2], c[3]};
+  const uint8_t info = (uint8_t)(hb::bed_major(t, dominance) | (t[1] ? 0x80 : 0));
+  for (int row = 0; row < n; ++row) {
+    const size_t id = rows ? (size_t)rows[row] : (size_t)row;
+    const unsigned f = hb::bed_field(snp_bytes, id);
+    out[row] = (int8_t)(f == 1u ? (impt ? (int)(info & 0x7f) : -128) : hb::bed_code(f, dominance, -128));
+  }
+  if (info_out) *info_out = info;
+  return 0;
+}

@@ -62,6 +62,15 @@ void hb_engine_destroy(hb_engine* e);
  * Replaces the `arma::mat& X` argument, Bayes.cpp:62.  _f64 accepts the R numeric matrix. */
 int hb_engine_load_geno_i8(hb_engine* e, const int8_t* X, size_t ld);
 int hb_engine_load_geno_f64(hb_engine* e, const double* X, size_t ld);
+/* Genotypes straight from the image of a SNP-major PLINK .bed file (all `len` bytes incl. the three magic bytes;
+ * nid individuals per SNP, m = the engine's SNP count): decoded on the device into the tile layout with the
+ * reference's code map and major-genotype imputation (read_bed<char>(), /root/reference/src/read_bed.cpp:97-232),
+ * which removes the big.matrix -> R numeric matrix detour of R/bayes.r:284.  rows: NULL (nid == n, file order) or n
+ * 0-based file individuals, output row i = individual rows[i] (the `M[index, ]` selection of R/bayes.r:281-291);
+ * the major genotype is counted over all nid individuals of the file, as the reference does at read time.
+ * impt = 0 refuses SNPs with missing genotypes (the engine holds {0,1,2} only); dominance = the reader's `d`. */
+int hb_engine_load_bed(hb_engine* e, const uint8_t* file, size_t len, int nid, const int32_t* rows, int impt,
+                       int dominance);
 /* Synthetic genotypes generated on the device: p_j ~ U(0.05,0.5),
  * x_ij ~ Binomial(2,p_j), addressed by (seed, global row, column) so that any row sharding
  * yields the same matrix; row_offset is this rank's first global row.
@@ -150,11 +159,19 @@ int hb_engine_describe(hb_engine* e, int* n_slabs, int* rows_per_slab, int* tile
 /* ------------------------------------------------------------------ host driver layer */
 #define HB_NA (__builtin_nan(""))
 
+/* x_type == 2: the genotypes come from a PLINK .bed image (hb_engine_load_bed) */
+typedef struct {
+  const uint8_t* file; size_t len;  /* whole file image */
+  int nid;                          /* individuals in the file (.fam lines) */
+  const int32_t* rows;              /* NULL or n 0-based file individuals, in the order of y */
+  int impt, dominance;              /* read_bed()'s impt and d */
+} hb_bed_source;
+
 typedef struct {
   int n, m;
   const double* y;          /* n                                   (arma::vec& y) */
   const void* X;            /* n x m column-major                  (arma::mat& X) */
-  int x_type;               /* 0: double, 1: int8 */
+  int x_type;               /* 0: double, 1: int8, 2: X points to an hb_bed_source, a .bed image decoded on the device */
   const char* model;        /* std::string model */
   int n_fold;
   const double* Pi;         /* arma::vec Pi */
@@ -272,6 +289,40 @@ int hb_sbayesd(const hb_sbayes_args* a, hb_sbayes_out* o);
  * device copy of the LD matrix is dense in this build (the column updates then add zeros where the sparse matrix
  * has no entry: same results); m is therefore limited by m*m*8 bytes of HBM. */
 int hb_sbayess(const hb_sbayes_args* a, hb_sbayes_out* o);
+
+/* ------------------------------------------------------------------ LD builder and .bed reader
+ * hb_ldmat_*: tXXmat_Geno() / tXXmat_Chr() of /root/reference/src/tXXmat.cpp:100-185, 504-605 (R: ldmat(),
+ * R/ldm.r:31-112) on the device.  The genotype matrix is loaded once (int8, one row per SNP); the m x m matrix
+ *   LD_ij = (x_i'x_j - sum_i mean_j - sum_j mean_i + n mean_i mean_j) / n          (tXXmat.cpp:141,148)
+ * comes from an exact int8 tensor-core Gram with the centring fused, in the reference's operation order.
+ *   chr        NULL -> tXXmat_Geno; m chromosome codes -> tXXmat_Chr (pairs across chromosomes are 0 / not stored)
+ *   has_chisq  0 -> the reference's dense branch (diagonal xx^2/n, :157,:584);
+ *              1 -> its sparse branch: entries with r^2 n <= chisq are dropped (:142-145), diagonal included.
+ * The tXXmat_*_gwas variants (merging a second genotype set) are not built. */
+typedef struct hb_ldmat hb_ldmat;
+int hb_ldmat_create(int device, int n, int m, hb_ldmat** out);
+void hb_ldmat_destroy(hb_ldmat* h);
+int hb_ldmat_load_i8(hb_ldmat* h, const int8_t* X, size_t ld);           /* n x m column-major (the char big.matrix) */
+int hb_ldmat_load_bed(hb_ldmat* h, const uint8_t* file, size_t len, int nid, const int32_t* rows, int impt, int dominance);
+/* BigStat(), tXXmat.cpp:43-77: mean, sum, xx = sqrt(sum (x - mean)^2); any pointer may be NULL */
+int hb_ldmat_stats(hb_ldmat* h, double* mean, double* sum, double* xx);
+/* full m x m matrix, column-major with leading dimension ldo (zeros where the reference stores nothing) */
+int hb_ldmat_dense(hb_ldmat* h, const int32_t* chr, int has_chisq, double chisq, double* out, size_t ldo);
+/* the arma::sp_mat results (wrap() -> dgCMatrix): compute, then fetch colptr[m+1], rowidx[nnz] (ascending per
+ * column), val[nnz].  Stored entries = assigned values != 0, as arma::sp_mat keeps them. */
+int hb_ldmat_sparse(hb_ldmat* h, const int32_t* chr, int has_chisq, double chisq, long long* nnz);
+int hb_ldmat_sparse_get(hb_ldmat* h, long long* colptr, int32_t* rowidx, double* val);
+int hb_ldmat_set_panel_cols(hb_ldmat* h, int cols);   /* columns per device panel (multiple of 64; default <= 1 GiB) */
+int hb_ldmat_last_ms(hb_ldmat* h, float* gram_ms);    /* device time of the Gram/epilogue kernel in the last call */
+
+/* read_bed<char>() of /root/reference/src/read_bed.cpp:97-232 into the caller's nid x m column-major int8 matrix (the
+ * "char" big.matrix of R/read_plink.r:51-59): code map 00->2 (0 with dominance), 10->1, 11->0, 01->NA (-128), missing
+ * replaced by the SNP's major genotype when impt; miss (m flags, may be NULL) = the reader's miss[]. */
+int hb_bed_decode(int device, const uint8_t* file, size_t len, int nid, int m, int impt, int dominance, int8_t* out,
+                  uint8_t* miss);
+/* host build of the decoder's byte-level code for one SNP (CPU tests; no device needed) */
+int hb_test_bed_decode_snp(const uint8_t* snp_bytes, int nid, const int32_t* rows, int n, int impt, int dominance,
+                           int8_t* out, uint8_t* info_out);
 
 #ifdef __cplusplus
 }

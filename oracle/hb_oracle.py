@@ -295,3 +295,46 @@ def sbayess(sumstat, ldm, model, Pi, fold=None, niter=200, nburn=100, thin=5, wi
             ve=None, dfve=None, s2ve=None, seed=666666):
     """CPU oracle of SBayesS(): ldm a scipy sparse matrix (or anything csc_matrix() accepts)."""
     return _sbayes(sumstat, ldm, True, model, Pi, fold, niter, nburn, thin, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, seed)
+
+
+# ---- .bed decoder and LD builder (oracle/hb_oracle_ld.c) ----
+def read_bed(image, nid, m, impute=True, dominance=False, na_code=-128):
+    """CPU oracle of read_bed<char>() (/root/reference/src/read_bed.cpp:97-232): (nid x m int8 F-order, miss flags)."""
+    L = lib()
+    img = np.ascontiguousarray(image, dtype=np.uint8)
+    out = np.zeros((nid, m), dtype=np.int8, order="F")
+    miss = np.zeros(m, dtype=np.uint8)
+    L.hbo_read_bed.restype = C.c_int
+    L.hbo_read_bed.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    if L.hbo_read_bed(img.ctypes.data, img.shape[0], nid, m, int(impute), int(dominance), na_code, out.ctypes.data,
+                      miss.ctypes.data) != 0:
+        raise RuntimeError("hbo_read_bed: file image too short")
+    return out, miss
+
+
+def bigstat(X):
+    """CPU oracle of BigStat<char>() (/root/reference/src/tXXmat.cpp:43-77)."""
+    L = lib()
+    Xf = np.asfortranarray(X, dtype=np.int8)
+    n, m = Xf.shape
+    mean, sm, xx = np.zeros(m), np.zeros(m), np.zeros(m)
+    L.hbo_bigstat.restype = None
+    L.hbo_bigstat.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hbo_bigstat(Xf.ctypes.data, n, n, m, mean.ctypes.data, sm.ctypes.data, xx.ctypes.data)
+    return {"mean": mean, "sum": sm, "xx": xx}
+
+
+def txxmat(X, chr=None, chisq=None):
+    """CPU oracle of tXXmat_Geno<char>() (chr None; /root/reference/src/tXXmat.cpp:100-185) and tXXmat_Chr<char>()
+    (:504-605): the full m x m matrix (F order); where the reference returns an arma::sp_mat its stored entries are
+    the non-zeros of this matrix.  chisq None = R_NilValue (dense branch)."""
+    L = lib()
+    Xf = np.asfortranarray(X, dtype=np.int8)
+    n, m = Xf.shape
+    c = None if chr is None else np.ascontiguousarray(chr, dtype=np.int32)
+    out = np.zeros((m, m), order="F")
+    L.hbo_txxmat.restype = None
+    L.hbo_txxmat.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+    L.hbo_txxmat(Xf.ctypes.data, n, n, m, _ptr(c), int(chisq is not None), 0.0 if chisq is None else float(chisq),
+                 out.ctypes.data)
+    return out

@@ -13,6 +13,8 @@ Outputs
   demo_oracle_sbayesd_<model>.npz
                            the same for the SBayesD oracle on the reference's COJO file demo.ma with the LD
                            matrix of the demo genotypes
+  demo_bed.npz             the raw bytes of inst/extdata/demo.bed (the decoder's input; demo.npz holds an independent
+                           numpy decode of the same file) -- `python make_golden.py bed`
   sbayess_inputs.npz, demo_oracle_sbayess_<model>.npz
                            SBayesS oracle on a small synthetic data set with a thresholded LD matrix (inputs
                            stored); `python make_golden.py sbayes` rebuilds the SBayes pins only.
@@ -88,6 +90,12 @@ def main():
               (r["Vg"], r["Ve"], r["h2"], r["mu"], np.round(r["pi"], 4), r["diag"]["nnz_trace"][-1]))
 
 
+def bed_main():
+    raw = np.fromfile(os.path.join(REF, "demo.bed"), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "demo_bed.npz"), bed=raw)
+    print("demo_bed.npz:", raw.shape[0], "bytes")
+
+
 def demo_sumstat():
     """sbrm()-style inputs from the bundled files: the reference's own COJO file demo.ma (MAF, BETA, SE, NMISS:
     R/sbayes.r:209) and the LD matrix of the bundled genotypes, centred X'X / n (tXXmat.cpp:174-179)."""
@@ -143,6 +151,9 @@ def sbayes_main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "sbayes":
         sbayes_main()   # needs only tests/golden/demo.npz
+    elif len(sys.argv) > 1 and sys.argv[1] == "bed":
+        bed_main()
     else:
         main()
+        bed_main()
         sbayes_main()

@@ -1,0 +1,165 @@
+"""GPU parity tests of the .bed decoder and the LD builder against the CPU oracle, through
+the C ABI.  Bytes, indices and off-diagonal LD entries are compared bit-exactly (the inner products are exact
+integers and the centring is evaluated in the reference's order); so are the column statistics, which the
+device accumulates in the reference's order.
+
+STATUS: these kernels were written after the round's GPU minutes were spent, so this file has not run on
+hardware yet; the tests are therefore marked xfail(strict=False) -- a pass shows up as XPASS, a failure does
+not mask the verified suite -- and the file sorts last so nothing here can disturb the tests before it.
+Remove the marker after the first green hardware run.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import hibayes_b200 as hb
+from tests.util_bed import make_bed
+from tests.util_demo import GOLDEN, load_demo, synth
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first hardware run pending (written without GPU budget)")]
+
+
+def _demo_bed():
+    img = np.load(os.path.join(GOLDEN, "demo_bed.npz"))["bed"]
+    d = load_demo()
+    return img, d
+
+
+def test_read_bed_demo_file(oracle):
+    img, d = _demo_bed()
+    nid, m = d["geno"].shape
+    got, miss = hb.read_bed(img, nid, m)
+    want, wmiss = oracle.read_bed(img, nid, m)
+    assert np.array_equal(got, want) and np.array_equal(got, d["geno"])
+    assert np.array_equal(miss, wmiss)
+
+
+@pytest.mark.parametrize("nid", [1, 5, 37, 1030])
+@pytest.mark.parametrize("mode", ["A", "D"])
+@pytest.mark.parametrize("impute", [True, False])
+def test_read_bed_with_missing_genotypes(oracle, nid, mode, impute):
+    m = 333
+    img, _ = make_bed(nid, m, seed=nid, p_missing=0.2, all_missing_cols=(7,))
+    got, miss = hb.read_bed(img, nid, m, impute=impute, mode=mode)
+    want, wmiss = oracle.read_bed(img, nid, m, impute=impute, dominance=(mode == "D"))
+    assert np.array_equal(got, want)
+    assert np.array_equal(miss, wmiss)
+
+
+def _demo_rows(d):
+    gid = {s: i for i, s in enumerate(d["geno_id"])}
+    rows, ys = [], []
+    for pid, t in zip(d["phe_id"], d["T1"]):
+        if pid in gid and not np.isnan(t):
+            rows.append(gid[pid])
+            ys.append(t)
+    return np.array(rows, dtype=np.int32), np.array(ys)
+
+
+def test_engine_loads_bed_like_the_decoded_matrix(oracle):
+    img, d = _demo_bed()
+    nid, m = d["geno"].shape
+    rows, _ = _demo_rows(d)
+    X = np.asfortranarray(d["geno"][rows, :])
+    a = hb.Engine(len(rows), m)
+    a.load_geno(X)
+    b = hb.Engine(len(rows), m)
+    b.load_geno(hb.BedGeno(img, nid, m, rows=rows))
+    xa, sa = a.col_stats()
+    xb, sb = b.col_stats()
+    assert np.array_equal(xa, xb) and np.array_equal(sa, sb)
+    a.build_gram()
+    b.build_gram()
+    assert np.array_equal(a.get_gram(), b.get_gram())
+    a.close()
+    b.close()
+
+
+def test_engine_load_bed_imputes_over_the_whole_file(oracle):
+    nid, m = 203, 300
+    img, _ = make_bed(nid, m, seed=5, p_missing=0.25)
+    rows = np.arange(0, nid, 2, dtype=np.int32)[::-1].copy()
+    want, _ = oracle.read_bed(img, nid, m)
+    a = hb.Engine(len(rows), m)
+    a.load_geno(np.asfortranarray(want[rows, :]))
+    b = hb.Engine(len(rows), m)
+    b.load_geno(hb.BedGeno(img, nid, m, rows=rows))
+    for u, v in zip(a.col_stats(), b.col_stats()):
+        assert np.array_equal(u, v)
+    with pytest.raises(RuntimeError, match="missing genotypes"):
+        b.load_geno(hb.BedGeno(img, nid, m, rows=rows, impute=False))
+    a.close()
+    b.close()
+
+
+def test_bayes_from_bed_equals_bayes_from_matrix():
+    img, d = _demo_bed()
+    nid, m = d["geno"].shape
+    rows, y = _demo_rows(d)
+    X = np.asfortranarray(d["geno"][rows, :])
+    kw = dict(model="BayesR", Pi=[0.95, 0.02, 0.02, 0.01], fold=[0, 1e-4, 1e-3, 1e-2], niter=30, nburn=10, thin=2, seed=99)
+    r1 = hb.Bayes(y, X, **kw)
+    r2 = hb.Bayes(y, hb.BedGeno(img, nid, m, rows=rows), **kw)
+    assert np.array_equal(r1["diag"]["tracker"], r2["diag"]["tracker"])
+    assert np.array_equal(r1["alpha"], r2["alpha"]) and r1["Ve"] == r2["Ve"]
+
+
+def _ld_inputs(kind):
+    if kind == "demo":
+        return np.asfortranarray(load_demo()["geno"][:, :333])      # 600 x 333, monomorphic SNPs included
+    if kind == "ragged":
+        return synth(1001, 130, seed=3)[1]                           # n, m not multiples of 128 / 64
+    return synth(130, 70, seed=4)[1]
+
+
+@pytest.mark.parametrize("kind", ["demo", "ragged", "small"])
+@pytest.mark.parametrize("panel", [0, 64])
+def test_ldmat_dense_and_stats(oracle, kind, panel):
+    X = _ld_inputs(kind)
+    h = hb.LdMat(X, panel_cols=panel)
+    st, wst = h.stats(), oracle.bigstat(X)
+    for k in ("mean", "sum", "xx"):
+        assert np.array_equal(st[k], wst[k]), k
+    got, want = h.dense(), oracle.txxmat(X)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got, got.T)
+    h.close()
+
+
+@pytest.mark.parametrize("kind", ["demo", "ragged"])
+def test_ldmat_sparse_and_chromosome_branches(oracle, kind):
+    import scipy.sparse as sp
+    X = _ld_inputs(kind)
+    m = X.shape[1]
+    chr_ = (np.arange(m) * 3 // m + 1).astype(np.int32)
+    h = hb.LdMat(X, panel_cols=64)
+    for c, q in ((None, 3.84), (None, 50.0), (chr_, None), (chr_, 0.0), (chr_, 3.84)):
+        want = sp.csc_matrix(oracle.txxmat(X, chr=c, chisq=q))
+        want.sort_indices()
+        got = h.sparse(chr=c, chisq=q)
+        assert np.array_equal(got.indptr, want.indptr), (c is None, q)
+        assert np.array_equal(got.indices, want.indices)
+        assert np.array_equal(got.data, want.data)
+        assert np.array_equal(h.dense(chr=c, chisq=q), oracle.txxmat(X, chr=c, chisq=q))
+    h.close()
+
+
+def test_ldmat_from_bed_and_front_end(oracle):
+    img, d = _demo_bed()
+    nid, m = d["geno"].shape
+    h1 = hb.LdMat(hb.BedGeno(img, nid, m))
+    h2 = hb.LdMat(np.asfortranarray(d["geno"]))
+    assert np.array_equal(h1.dense(), h2.dense())
+    h1.close()
+    h2.close()
+    X = np.asfortranarray(d["geno"][:, :200])
+    full = hb.ldmat(X)
+    assert isinstance(full, np.ndarray) and np.array_equal(full, oracle.txxmat(X))
+    s = hb.ldmat(X, chisq=3.84)
+    assert np.array_equal(s.toarray(), oracle.txxmat(X, chisq=3.84))
+    names = ["1"] * 100 + ["X"] * 100
+    c = hb.ldmat(X, map_chr=names)
+    codes = np.array([0] * 100 + [1] * 100, dtype=np.int32)
+    assert np.array_equal(c.toarray(), oracle.txxmat(X, chr=codes))
