@@ -506,6 +506,15 @@ class Engine:
         _lib.check(self.L.hb_engine_predict(self.h, alpha.ctypes.data, out.ctypes.data))
         return out
 
+    def predict_samples(self, alpha_samples):
+        """X @ alpha_samples (m x n_records) -> n x n_records: `M %*% res$MCMCsamples$alpha`, R/bayes.r:303-304."""
+        A = np.asfortranarray(alpha_samples, dtype=np.float64)
+        if A.ndim != 2 or A.shape[0] != self.m:
+            raise ValueError("alpha_samples must be m x n_records")
+        out = np.zeros((self.n, A.shape[1]), order="F")
+        _lib.check(self.L.hb_engine_predict_samples(self.h, A.ctypes.data, self.m, A.shape[1], out.ctypes.data, self.n))
+        return out
+
     def sweep(self, iter, model_index, vare, logpi, vara_fold, fold=None, dfvara=4.0, s2varg=0.0, lambda_=0.0, lambda2=0.0,
               mu_shift=0.0, rnorm2_bound=1.0):
         si = _lib.SweepIn()

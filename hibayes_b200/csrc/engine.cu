@@ -1249,6 +1249,19 @@ extern "C" int hb_engine_predict(hb_engine* e, const double* alpha, double* out)
   return 0;
 }
 
+// Genetic values of every stored MCMC sample, `M %*% res$MCMCsamples$alpha` of R/bayes.r:303-304:
+// out[:, c] = X alpha[:, c].  First path: one k_gemv_part pass over X per record (the kernel hb_engine_predict uses);
+// a batched kernel that reads X once for all records is the obvious next step.
+extern "C" int hb_engine_predict_samples(hb_engine* e, const double* alpha, size_t ld_alpha, int n_records, double* out,
+                                         size_t ld_out) {
+  if (!e || !alpha || !out) return hb_set_error("hb_engine_predict_samples: null argument");
+  if (n_records < 0 || ld_alpha < (size_t)e->m || ld_out < (size_t)e->n)
+    return hb_set_error("hb_engine_predict_samples: bad leading dimension or record count");
+  for (int c = 0; c < n_records; ++c)
+    if (hb_engine_predict(e, alpha + (size_t)c * ld_alpha, out + (size_t)c * ld_out)) return 1;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // row sharding over several GPUs (one process and one engine per GPU)
 // ------------------------------------------------------------------------------------------

@@ -135,6 +135,8 @@ int hb_engine_get_effect_sums(hb_engine* e, double* gsum);
 
 /* out[i] = sum_j X[i][j] * alpha[j] over the resident genotypes (the X*g of Bayes.cpp:971) */
 int hb_engine_predict(hb_engine* e, const double* alpha, double* out);
+/* `M %*% MCMCsamples$alpha` of R/bayes.r:303-304: out (n x n_records, ld_out) = X * alpha (m x n_records, ld_alpha) */
+int hb_engine_predict_samples(hb_engine* e, const double* alpha, size_t ld_alpha, int n_records, double* out, size_t ld_out);
 
 /* Row sharding over the GPUs of one node: one process and one engine per GPU, created with
  * (rank, world) and this rank's rows.  The x_j'r of Bayes.cpp:593 becomes a sum over ranks: inside the sweep

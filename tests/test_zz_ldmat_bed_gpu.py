@@ -163,3 +163,17 @@ def test_ldmat_from_bed_and_front_end(oracle):
     c = hb.ldmat(X, map_chr=names)
     codes = np.array([0] * 100 + [1] * 100, dtype=np.int32)
     assert np.array_equal(c.toarray(), oracle.txxmat(X, chr=codes))
+
+
+def test_gebv_samples_equal_matrix_product():
+    """`M %*% MCMCsamples$alpha` (R/bayes.r:303-304); fp64, summation order differs from a BLAS
+    dgemm, tolerance 1e-10 relative to the largest value."""
+    y, X = synth(1500, 3000, seed=8)
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(3000, 7)) * (rng.random((3000, 7)) < 0.1)
+    e = hb.Engine(1500, 3000)
+    e.load_geno(X)
+    got = e.predict_samples(A)
+    want = X.astype(np.float64) @ A
+    assert np.allclose(got, want, rtol=0, atol=1e-10 * np.abs(want).max())
+    e.close()
