@@ -96,23 +96,38 @@ struct LdEpi {
   double chisq;
 };
 
+// fp64 operations that must round exactly where the reference's expressions round: explicit round-to-nearest
+// intrinsics on the device (no FMA contraction), plain operators on the host (built with -ffp-contract=off)
+#ifdef __CUDA_ARCH__
+#define LD_MUL(a, b) __dmul_rn((a), (b))
+#define LD_ADD(a, b) __dadd_rn((a), (b))
+#define LD_SUB(a, b) __dsub_rn((a), (b))
+#define LD_DIV(a, b) __ddiv_rn((a), (b))
+#else
+#define LD_MUL(a, b) ((a) * (b))
+#define LD_ADD(a, b) ((a) + (b))
+#define LD_SUB(a, b) ((a) - (b))
+#define LD_DIV(a, b) ((a) / (b))
+#endif
+
 // One LD entry from the exact inner product (tXXmat.cpp:141-148 / :157): the statistics of the SNP
 // with the smaller index play the role of sum1/m1/p1 (outer loop variable j of the reference).
-__device__ __forceinline__ double ld_entry(const LdEpi& e, int i, int j, int G) {
+// __host__ __device__: tests/ run this very function on the CPU (hb_test_ld_entries below).
+__host__ __device__ __forceinline__ double ld_entry(const LdEpi& e, int i, int j, int G) {
   if (e.chr && e.chr[i] != e.chr[j]) return 0.0;
-  const int lo = min(i, j), hi = max(i, j);
+  const int lo = i < j ? i : j, hi = i < j ? j : i;
   const double ind = (double)e.n;
   const double p1 = e.xx[lo];
-  if (!e.has_chisq && lo == hi) return __ddiv_rn(__dmul_rn(p1, p1), ind);
+  if (!e.has_chisq && lo == hi) return LD_DIV(LD_MUL(p1, p1), ind);
   const double m1 = e.mean[lo], sum1 = e.sum[lo];
   const double p2 = e.xx[hi], m2 = e.mean[hi], sum2 = e.sum[hi];
-  const double t = __dsub_rn(__dadd_rn(__dmul_rn(sum1, m2), __dmul_rn(sum2, m1)), __dmul_rn(__dmul_rn(ind, m1), m2));
-  const double p12 = __dsub_rn((double)G, t);
+  const double t = LD_SUB(LD_ADD(LD_MUL(sum1, m2), LD_MUL(sum2, m1)), LD_MUL(LD_MUL(ind, m1), m2));
+  const double p12 = LD_SUB((double)G, t);
   if (e.has_chisq) {
-    const double r = __ddiv_rn(p12, __dmul_rn(p1, p2));
-    if (__dmul_rn(__dmul_rn(r, r), ind) <= e.chisq) return 0.0;
+    const double r = LD_DIV(p12, LD_MUL(p1, p2));
+    if (LD_MUL(LD_MUL(r, r), ind) <= e.chisq) return 0.0;
   }
-  return __ddiv_rn(p12, ind);
+  return LD_DIV(p12, ind);
 }
 
 constexpr int LD_RK = 128;              // individuals (bytes) per stage
@@ -601,5 +616,16 @@ extern "C" int hb_test_bed_decode_snp(const uint8_t* snp_bytes, int nid, const i
     out[row] = (int8_t)(f == 1u ? (impt ? (int)(info & 0x7f) : -128) : hb::bed_code(f, dominance, -128));
   }
   if (info_out) *info_out = info;
+  return 0;
+}
+
+// The epilogue's arithmetic on the host: out (m x m column-major) from an exact Gram matrix (int32, m x m) and the
+// column statistics, through ld_entry() -- the function k_ld_panel calls per accumulator element.
+extern "C" int hb_test_ld_entries(int n, int m, const int32_t* gram, const double* sum, const double* mean, const double* xx,
+                                  const int32_t* chr, int has_chisq, double chisq, double* out) {
+  if (!gram || !sum || !mean || !xx || !out || n <= 0 || m <= 0) return hb_set_error("hb_test_ld_entries: bad argument");
+  LdEpi e{sum, mean, xx, chr, n, m, has_chisq, chisq};
+  for (int j = 0; j < m; ++j)
+    for (int i = 0; i < m; ++i) out[(size_t)j * m + i] = ld_entry(e, i, j, gram[(size_t)j * m + i]);
   return 0;
 }

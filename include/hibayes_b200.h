@@ -323,6 +323,9 @@ int hb_ldmat_last_ms(hb_ldmat* h, float* gram_ms);    /* device time of the Gram
 int hb_bed_decode(int device, const uint8_t* file, size_t len, int nid, int m, int impt, int dominance, int8_t* out,
                   uint8_t* miss);
 /* host build of the decoder's byte-level code for one SNP (CPU tests; no device needed) */
+/* host build of the LD builder's epilogue: out (m x m) from an exact int32 Gram matrix and BigStat's vectors */
+int hb_test_ld_entries(int n, int m, const int32_t* gram, const double* sum, const double* mean, const double* xx,
+                       const int32_t* chr, int has_chisq, double chisq, double* out);
 int hb_test_bed_decode_snp(const uint8_t* snp_bytes, int nid, const int32_t* rows, int n, int impt, int dominance,
                            int8_t* out, uint8_t* info_out);
 

@@ -169,3 +169,25 @@ def test_bed_and_ldmat_entry_points_refuse_without_a_gpu():
         hb.read_bed(bad, 8, 4)
     with pytest.raises(RuntimeError, match="needed for"):
         hb.read_bed(img[:-1], 8, 4)
+
+
+@pytest.mark.parametrize("mode", ["dense", "sparse", "chr_dense", "chr_sparse0", "chr_sparse"])
+def test_device_ld_epilogue_on_the_host_is_bit_identical_to_the_oracle(oracle, mode):
+    """hb_test_ld_entries runs ld_entry() -- what k_ld_panel applies to every accumulator element -- on the host,
+    fed with the exact Gram matrix: every entry must equal the oracle's bit for bit (operation order of
+    tXXmat.cpp:141-148, smaller index in the role of the outer loop variable, diagonal rules of both branches)."""
+    L = hb.load_library()
+    X = _demo_slice(600, 160)          # includes monomorphic SNPs (0/0 -> NaN in r)
+    n, m = X.shape
+    st = oracle.bigstat(X)
+    G = np.asfortranarray((X.astype(np.int64).T @ X.astype(np.int64)).astype(np.int32))
+    chr_ = (np.arange(m) * 3 // m + 1).astype(np.int32)
+    c, q = {"dense": (None, None), "sparse": (None, 3.84), "chr_dense": (chr_, None), "chr_sparse0": (chr_, 0.0),
+            "chr_sparse": (chr_, 10.0)}[mode]
+    out = np.zeros((m, m), order="F")
+    _lib.check(L.hb_test_ld_entries(n, m, G.ctypes.data, st["sum"].ctypes.data, st["mean"].ctypes.data, st["xx"].ctypes.data,
+                                    None if c is None else c.ctypes.data, int(q is not None), 0.0 if q is None else q,
+                                    out.ctypes.data))
+    want = oracle.txxmat(X, chr=c, chisq=q)
+    assert np.array_equal(out, want)
+    assert (out != 0).sum() > m

@@ -15,7 +15,7 @@ It reports, per sweep: candidates per tile, rounds per tile of the CURRENT schem
 and classifies the misses of the first round (candidate changed class / non-candidate became non-zero).
 
     python tools/sim_rounds.py --n 50000 --m 5120 --sweeps 40
-    python tools/sim_rounds.py --n 400000 --m 5120 --sweeps 40      # the regime of 8 GPUs x 50k rows
+    python tools/sim_rounds.py --n 50000 --m 5120 --sweeps 40 --fold-scale 64   # HB_BENCH_FOLD_SCALE=64 of bench.py
 """
 import argparse
 import time
@@ -186,7 +186,11 @@ def main():
     ap.add_argument("--m-full", type=int, default=1000000, help="SNP count of the workload whose regime is imitated")
     ap.add_argument("--seed", type=int, default=20260101)
     ap.add_argument("--report-every", type=int, default=5)
+    ap.add_argument("--fold-scale", type=float, default=1.0,
+                    help="multiplies the variance folds like HB_BENCH_FOLD_SCALE of bench.py (64: the flip-heavy regime)")
     a = ap.parse_args()
+    global FOLD
+    FOLD = FOLD * a.fold_scale
     rng = np.random.default_rng(a.seed)
     n, m, B = a.n, a.m, a.tile
     T = m // B
