@@ -55,47 +55,6 @@ struct hb_ldmat {
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
-// BigStat (tXXmat.cpp:43-77).  One thread per SNP, individuals in file order: the second pass is a
-// sequential fp64 sum of (x - mean)^2 whose rounding depends on the order, and the sparse branch
-// thresholds on it (:142-143), so the order is kept.  The first pass sums integers (exact).
-__global__ void k_ld_stats(const int8_t* __restrict__ Xc, int Kpad, int n, int m, double* __restrict__ sum,
-                           double* __restrict__ mean, double* __restrict__ xx) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= m) return;
-  const int8_t* row = Xc + (size_t)j * Kpad;
-  long long s = 0;
-  for (int k0 = 0; k0 < Kpad; k0 += 16) {  // padding bytes are 0
-    const int4 v = *(const int4*)(row + k0);
-    const int w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) s += (int8_t)(w[q]) + (int8_t)(w[q] >> 8) + (int8_t)(w[q] >> 16) + (int8_t)(w[q] >> 24);
-  }
-  const double sm = (double)s;
-  const double mu = __ddiv_rn(sm, (double)n);
-  double p1 = 0.0;
-  for (int k0 = 0; k0 < n; k0 += 16) {
-    const int4 v = *(const int4*)(row + k0);
-    const int w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      if (k0 + q < n) {
-        const double dv = __dsub_rn((double)(int8_t)(w[q >> 2] >> (8 * (q & 3))), mu);
-        p1 = __dadd_rn(p1, __dmul_rn(dv, dv));
-      }
-    }
-  }
-  sum[j] = sm;
-  mean[j] = mu;
-  xx[j] = __dsqrt_rn(p1);
-}
-
-struct LdEpi {
-  const double *sum, *mean, *xx;
-  const int32_t* chr;  // may be null
-  int n, m, has_chisq;
-  double chisq;
-};
-
 // fp64 operations that must round exactly where the reference's expressions round: explicit round-to-nearest
 // intrinsics on the device (no FMA contraction), plain operators on the host (built with -ffp-contract=off)
 #ifdef __CUDA_ARCH__
@@ -109,6 +68,57 @@ struct LdEpi {
 #define LD_SUB(a, b) ((a) - (b))
 #define LD_DIV(a, b) ((a) / (b))
 #endif
+
+#ifdef __CUDA_ARCH__
+#define LD_SQRT(a) __dsqrt_rn(a)
+#else
+#define LD_SQRT(a) sqrt(a)
+#endif
+
+// BigStat (tXXmat.cpp:43-77) of one SNP row of Xc, individuals in file order: the second pass is a sequential fp64
+// sum of (x - mean)^2 whose rounding depends on the order, and the sparse branch thresholds on it (:142-143), so the
+// order is kept.  The first pass sums integers (exact).  __host__ __device__: the CPU tests run this function too.
+__host__ __device__ __forceinline__ void ld_stats_row(const int8_t* row, int Kpad, int n, double* sum, double* mean, double* xx) {
+  long long s = 0;
+  for (int k0 = 0; k0 < Kpad; k0 += 16) {  // padding bytes are 0
+    const int4 v = *(const int4*)(row + k0);
+    const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s += (int8_t)(w[q]) + (int8_t)(w[q] >> 8) + (int8_t)(w[q] >> 16) + (int8_t)(w[q] >> 24);
+  }
+  const double sm = (double)s;
+  const double mu = LD_DIV(sm, (double)n);
+  double p1 = 0.0;
+  for (int k0 = 0; k0 < n; k0 += 16) {
+    const int4 v = *(const int4*)(row + k0);
+    const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      if (k0 + q < n) {
+        const double dv = LD_SUB((double)(int8_t)(w[q >> 2] >> (8 * (q & 3))), mu);
+        p1 = LD_ADD(p1, LD_MUL(dv, dv));
+      }
+    }
+  }
+  *sum = sm;
+  *mean = mu;
+  *xx = LD_SQRT(p1);
+}
+
+// one thread per SNP
+__global__ void k_ld_stats(const int8_t* __restrict__ Xc, int Kpad, int n, int m, double* __restrict__ sum,
+                           double* __restrict__ mean, double* __restrict__ xx) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  ld_stats_row(Xc + (size_t)j * Kpad, Kpad, n, sum + j, mean + j, xx + j);
+}
+
+struct LdEpi {
+  const double *sum, *mean, *xx;
+  const int32_t* chr;  // may be null
+  int n, m, has_chisq;
+  double chisq;
+};
 
 // One LD entry from the exact inner product (tXXmat.cpp:141-148 / :157): the statistics of the SNP
 // with the smaller index play the role of sum1/m1/p1 (outer loop variable j of the reference).
@@ -627,5 +637,12 @@ extern "C" int hb_test_ld_entries(int n, int m, const int32_t* gram, const doubl
   LdEpi e{sum, mean, xx, chr, n, m, has_chisq, chisq};
   for (int j = 0; j < m; ++j)
     for (int i = 0; i < m; ++i) out[(size_t)j * m + i] = ld_entry(e, i, j, gram[(size_t)j * m + i]);
+  return 0;
+}
+
+// BigStat on the host through ld_stats_row(): Xc is m rows of Kpad bytes (16-byte aligned, zero padded beyond n).
+extern "C" int hb_test_ld_stats(const int8_t* Xc, int Kpad, int n, int m, double* sum, double* mean, double* xx) {
+  if (!Xc || !sum || !mean || !xx || Kpad % 16 || Kpad < n || ((uintptr_t)Xc & 15)) return hb_set_error("hb_test_ld_stats: bad argument");
+  for (int j = 0; j < m; ++j) ld_stats_row(Xc + (size_t)j * Kpad, Kpad, n, sum + j, mean + j, xx + j);
   return 0;
 }

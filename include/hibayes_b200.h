@@ -326,6 +326,8 @@ int hb_bed_decode(int device, const uint8_t* file, size_t len, int nid, int m, i
 /* host build of the LD builder's epilogue: out (m x m) from an exact int32 Gram matrix and BigStat's vectors */
 int hb_test_ld_entries(int n, int m, const int32_t* gram, const double* sum, const double* mean, const double* xx,
                        const int32_t* chr, int has_chisq, double chisq, double* out);
+/* host build of the LD builder's BigStat code: Xc = m rows of Kpad bytes, 16-byte aligned, zeros beyond n */
+int hb_test_ld_stats(const int8_t* Xc, int Kpad, int n, int m, double* sum, double* mean, double* xx);
 int hb_test_bed_decode_snp(const uint8_t* snp_bytes, int nid, const int32_t* rows, int n, int impt, int dominance,
                            int8_t* out, uint8_t* info_out);
 

@@ -191,3 +191,21 @@ def test_device_ld_epilogue_on_the_host_is_bit_identical_to_the_oracle(oracle, m
     want = oracle.txxmat(X, chr=c, chisq=q)
     assert np.array_equal(out, want)
     assert (out != 0).sum() > m
+
+
+@pytest.mark.parametrize("n,m", [(600, 240), (130, 70), (1001, 33)])
+def test_device_bigstat_code_on_the_host_is_bit_identical_to_the_oracle(oracle, n, m):
+    """hb_test_ld_stats runs ld_stats_row() -- the body of k_ld_stats -- on the host, on the device layout (one
+    zero-padded row of Kpad bytes per SNP)."""
+    L = hb.load_library()
+    from tests.util_demo import synth
+    X = _demo_slice(n, m) if n == 600 else synth(n, m, seed=n)[1]
+    Kpad = (n + 127) // 128 * 128
+    raw = np.zeros(m * Kpad + 16, dtype=np.int8)
+    off = (-raw.ctypes.data) % 16
+    Xc = raw[off:off + m * Kpad].reshape(m, Kpad)
+    Xc[:, :n] = X.T
+    sm, mean, xx = np.zeros(m), np.zeros(m), np.zeros(m)
+    _lib.check(L.hb_test_ld_stats(Xc.ctypes.data, Kpad, n, m, sm.ctypes.data, mean.ctypes.data, xx.ctypes.data))
+    st = oracle.bigstat(X)
+    assert np.array_equal(sm, st["sum"]) and np.array_equal(mean, st["mean"]) and np.array_equal(xx, st["xx"])
