@@ -106,10 +106,6 @@ double hbo_invgauss_literal_root(double mu, double lambda, double z);
  * each vector op.  Returns SNP-updates per second. */
 double hbo_time_sweep_fp64(int n, int m_cpu, int sweeps, int threads, uint64_t seed, double* checksum);
 
-#ifdef __cplusplus
-}
-#endif
-#endif
 
 /* ---- SBayesD: dense-LD summary-statistics Gibbs sampler (/root/reference/src/SBayesD.cpp:5-609) ---- */
 typedef struct {
@@ -144,3 +140,8 @@ typedef struct {
 int hbo_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o);
 /* SBayesS: sparse-LD variant (/root/reference/src/SBayesS.cpp:21-679) */
 int hbo_sbayess(const hbo_sbayes_args* a, hbo_sbayes_out* o);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -209,3 +209,21 @@ def test_device_bigstat_code_on_the_host_is_bit_identical_to_the_oracle(oracle, 
     _lib.check(L.hb_test_ld_stats(Xc.ctypes.data, Kpad, n, m, sm.ctypes.data, mean.ctypes.data, xx.ctypes.data))
     st = oracle.bigstat(X)
     assert np.array_equal(sm, st["sum"]) and np.array_equal(mean, st["mean"]) and np.array_equal(xx, st["xx"])
+
+
+@pytest.mark.parametrize("model,Pi,fold", [("BayesCpi", [0.95, 0.05], None),
+                                            ("BayesR", [0.95, 0.02, 0.02, 0.01], [0, 1e-4, 1e-3, 1e-2])])
+def test_oracle_pipeline_ldmat_into_sbayesd_reproduces_the_golden_pin(oracle, model, Pi, fold):
+    """ldmat() -> sbrm() as a user chains them (R/ldm.r -> R/sbayes.r:198-215): the LD oracle's matrix of the bundled
+    genotypes, fed to the SBayesD oracle with the reference's COJO file, lands on the committed pin (which was made
+    with a numpy X'X/n): same inclusion indicators, variance components to 1e-9."""
+    d = load_demo()
+    ld = oracle.txxmat(np.asfortranarray(d["geno"]))
+    ss = np.asfortranarray(np.column_stack([d["ma_maf"], d["ma_beta"], d["ma_se"], d["ma_n"]]))
+    r = oracle.sbayesd(ss, ld, model, Pi, fold=fold, niter=100, nburn=50, thin=5, seed=666666)
+    g = np.load(os.path.join(GOLDEN, "demo_oracle_sbayesd_%s.npz" % model))
+    assert np.array_equal(r["diag"]["tracker"], g["tracker"])
+    assert np.array_equal(r["diag"]["nnz_trace"], g["nnz_trace"])
+    for k in ("Vg", "Ve", "h2"):
+        assert abs(r[k] / float(g[k]) - 1) < 1e-9, k
+    assert np.allclose(r["alpha"], g["alpha"], rtol=1e-7, atol=1e-12)

@@ -177,3 +177,18 @@ def test_gebv_samples_equal_matrix_product():
     want = X.astype(np.float64) @ A
     assert np.allclose(got, want, rtol=0, atol=1e-10 * np.abs(want).max())
     e.close()
+
+
+def test_pipeline_ldmat_into_sbayesd_on_the_device(oracle):
+    """ldmat() -> sbrm() entirely through the C ABI against the same chain of oracles."""
+    d = load_demo()
+    X = np.asfortranarray(d["geno"])
+    ss = np.asfortranarray(np.column_stack([d["ma_maf"], d["ma_beta"], d["ma_se"], d["ma_n"]]))
+    ld = hb.ldmat(X)
+    assert np.array_equal(ld, oracle.txxmat(X))
+    kw = dict(fold=[0, 1e-4, 1e-3, 1e-2], niter=60, nburn=30, thin=5, seed=4)
+    got = hb.SBayesD(ss, ld, "BayesR", [0.95, 0.02, 0.02, 0.01], **kw)
+    want = oracle.sbayesd(ss, ld, "BayesR", [0.95, 0.02, 0.02, 0.01], **kw)
+    assert np.array_equal(got["diag"]["tracker"], want["diag"]["tracker"])
+    assert np.allclose(got["alpha"], want["alpha"], rtol=1e-5, atol=1e-12)
+    assert abs(got["Ve"] / want["Ve"] - 1) < 1e-5
