@@ -186,6 +186,10 @@ def main():
     ap.add_argument("--m-full", type=int, default=1000000, help="SNP count of the workload whose regime is imitated")
     ap.add_argument("--seed", type=int, default=20260101)
     ap.add_argument("--report-every", type=int, default=5)
+    ap.add_argument("--leads", type=str, default="",
+                    help="comma list of lead times in tiles, e.g. 0,1,2,4: how complete must the gathered candidate rows be "
+                         "when phase P runs that many tiles before phase S (DESIGN.md section 10, one serial CTA)")
+    ap.add_argument("--nears", type=str, default="0,0.1,0.3,0.5,1.0")
     ap.add_argument("--fold-scale", type=float, default=1.0,
                     help="multiplies the variance folds like HB_BENCH_FOLD_SCALE of bench.py (64: the flip-heavy regime)")
     a = ap.parse_args()
@@ -232,6 +236,10 @@ def main():
     dfg, s2g = 4.0, varg * 0.5
     g = np.zeros(m)
     r = y - y.mean()
+    leads = [int(v) for v in a.leads.split(",") if v != ""]
+    nears = [float(v) for v in a.nears.split(",") if v != ""]
+    lead_stats = {(ld, nr): [0, 0, 0.0, 0] for ld in leads for nr in nears}   # tiles, tiles with a miss, rows, missed SNPs
+    hist = []   # residual at the entry of the last max(leads) tiles
     for it in range(a.sweeps):
         ts = time.time()
         r -= rng.normal(r.mean(), np.sqrt(vare / n))
@@ -252,6 +260,28 @@ def main():
             z = rng.normal(size=B)
             gold = g[cols].copy()
             cls, gnew, delta = exact_tile(entry, Gl[t], gold, xpx[cols], u, z, vare, vara_fold, logpi)
+            if leads:
+                hist.append(r.copy())
+                if len(hist) > max(leads) + 1:
+                    hist.pop(0)
+                if it >= 10:
+                    act = xpx[cols] > 0
+                    xs = np.where(act, xpx[cols], 1.0)
+                    needed = act & ((gold != 0) | (cls != 0))
+                    Xt64 = Xt.T.astype(np.float64)
+                    for ld in leads:
+                        r_old = hist[max(0, len(hist) - 1 - ld)]
+                        rhs_old = Xt64 @ r_old + xpx[cols] * gold
+                        spec_old = classify(rhs_old, xs, u, vare, vara_fold, logpi)
+                        dist = boundary_distance(rhs_old, xs, u, vare, vara_fold, logpi)
+                        for nr in nears:
+                            pkg = act & ((gold != 0) | (spec_old != 0) | (dist <= nr))
+                            st = lead_stats[(ld, nr)]
+                            miss = needed & ~pkg
+                            st[0] += 1
+                            st[1] += int(miss.any())
+                            st[2] += int(pkg.sum())
+                            st[3] += int(miss.sum())
             stats.append(replay(entry, Gl[t], gold, xpx[cols], u, z, vare, vara_fold, logpi, cls, a.near))
             ch = np.flatnonzero(delta != 0)
             if ch.size:
@@ -273,6 +303,13 @@ def main():
                   % (it + 1, nnz, 100 * nnz / m, mean("k"), mean("cur"), mean("cond"),
                      max(s["cond_lanes"] for s in stats), mean("cond_near"), max(s["cond_near_lanes"] for s in stats),
                      mean("miss_cand"), mean("miss_non"), vare, varg, time.time() - ts), flush=True)
+    if leads:
+        print("package completeness when phase P runs `lead` tiles before phase S (tiles of sweeps > 10):")
+        print("  lead  near   tiles  tiles with a missing row  missing rows/tile  rows gathered/tile")
+        for (ld, nr), st in sorted(lead_stats.items()):
+            if st[0]:
+                print("  %4d  %4.2f  %6d  %8.2f %%               %8.4f           %6.1f"
+                      % (ld, nr, st[0], 100.0 * st[1] / st[0], st[3] / st[0], st[2] / st[0]))
 
 
 if __name__ == "__main__":
