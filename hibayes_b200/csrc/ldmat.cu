@@ -646,3 +646,37 @@ extern "C" int hb_test_ld_stats(const int8_t* Xc, int Kpad, int n, int m, double
   for (int j = 0; j < m; ++j) ld_stats_row(Xc + (size_t)j * Kpad, Kpad, n, sum + j, mean + j, xx + j);
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// host build of hb_limbs.h (a round-2 building block of the sweep's inner loop; CPU tests only)
+// ------------------------------------------------------------------------------------------
+#include "hb_limbs.h"
+// dot of one genotype column (n bytes in {0,1,2}, n a multiple of 4) with r through the limb scheme: returns x'q (exact
+// int64) with q_i = rint(r_i scale); *ok = 0 if some |q_i| >= 2^47.
+extern "C" int hb_test_limb_dot(const uint8_t* x, const double* r, int n, double scale, long long* dot_q, int* ok) {
+  if (!x || !r || !dot_q || !ok || n % 4) return hb_set_error("hb_test_limb_dot: bad argument");
+  std::vector<uint8_t> lim((size_t)HB_NLIMB * n);   // limb-major: lim[k][row]
+  *ok = 1;
+  for (int i = 0; i < n; ++i) {
+    uint8_t l6[HB_NLIMB];
+    if (!hb_limb_split(r[i], scale, l6)) { *ok = 0; l6[0] = l6[1] = l6[2] = l6[3] = l6[4] = l6[5] = 0; }
+    for (int k = 0; k < HB_NLIMB; ++k) lim[(size_t)k * n + i] = l6[k];
+  }
+  int acc[HB_NLIMB] = {0, 0, 0, 0, 0, 0};
+  long long total = 0;
+  for (int i = 0; i < n; i += 4) {
+    uint32_t xw;
+    memcpy(&xw, x + i, 4);
+    for (int k = 0; k < HB_NLIMB; ++k) {
+      uint32_t lw;
+      memcpy(&lw, &lim[(size_t)k * n + i], 4);
+      acc[k] = hb_limb_dp4a(xw, lw, k, acc[k]);
+    }
+    if ((i / 4) % 6 == 5 || i + 4 >= n) {   // merge every 24 rows, as a lane of the sweep kernel would
+      total += hb_limb_merge(acc);
+      for (int k = 0; k < HB_NLIMB; ++k) acc[k] = 0;
+    }
+  }
+  *dot_q = total;
+  return 0;
+}

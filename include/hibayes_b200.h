@@ -328,6 +328,8 @@ int hb_test_ld_entries(int n, int m, const int32_t* gram, const double* sum, con
                        const int32_t* chr, int has_chisq, double chisq, double* out);
 /* host build of the LD builder's BigStat code: Xc = m rows of Kpad bytes, 16-byte aligned, zeros beyond n */
 int hb_test_ld_stats(const int8_t* Xc, int Kpad, int n, int m, double* sum, double* mean, double* xx);
+/* host build of csrc/hb_limbs.h (fixed-point limb dot, a building block not yet used by the sweep): x'q, q = rint(r scale) */
+int hb_test_limb_dot(const uint8_t* x, const double* r, int n, double scale, long long* dot_q, int* ok);
 int hb_test_bed_decode_snp(const uint8_t* snp_bytes, int nid, const int32_t* rows, int n, int impt, int dominance,
                            int8_t* out, uint8_t* info_out);
 
