@@ -91,6 +91,8 @@ struct hb_engine {
   unsigned sweep_no = 0;
   unsigned long long* trace = nullptr;
   int KROW = 0;
+  int limbs = 0;      // HB_LIMBS=1 (experimental): integer-only dots in the streaming CTAs (k_sweep<..., LIMBS>)
+  double* absmax_dev = nullptr;
   int cluster2 = 0;   // HB_CLUSTER=1: scalar workers in clusters of 2 (hand-over through distributed shared memory)
   int scalar0 = 0;    // block index of the first scalar CTA
   int* ctrl = nullptr;  // [0] progress, [1] abort
@@ -552,6 +554,20 @@ __global__ void k_bayesl_post(int m, int iter, hb_key_t key, const uint8_t* __re
   double vargi = 1.0 / hb_invgauss_from_uz(sqrt(vare) * lambda / fabs(g[j]), lambda2, uu, zz);
   if (vargi >= 0) vargL[j] = vargi;
 }
+// max_i |r_i + shift| (one block): the bound behind the fixed-point scale of the LIMBS variant
+__global__ void __launch_bounds__(1024) k_absmax(const double* __restrict__ r, int n, double shift, double* out) {
+  __shared__ double sh[32];
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) v = fmax(v, fabs(r[i] + shift));
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = sh[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) *out = v;
+  }
+}
 __global__ void __launch_bounds__(1024) k_sum(const double* __restrict__ x, int n, double* out) {
   __shared__ double sh[1024];
   double a = 0;
@@ -704,6 +720,17 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, e->block_threads, e->smem_bytes));
     if (occ < 1) { delete e; return hb_set_error("sweep kernel does not fit an SM (threads %d, smem %zu)", e->block_threads, e->smem_bytes); }
   }
+  if (const char* lb = getenv("HB_LIMBS")) {
+    // experimental: only the bench's kernel shape is instantiated with integer dots
+    if (atoi(lb) && e->RL == 24) {
+      const void* fn = (const void*)k_sweep<512, 4, 24, false, true>;
+      CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+      CU(cudaMalloc(&e->absmax_dev, 8));
+      e->limbs = 1;
+    } else if (atoi(lb)) {
+      fprintf(stderr, "[hb] HB_LIMBS needs 384-row slabs (RL = 24); this engine has RL = %d: fp64 dots\n", e->RL);
+    }
+  }
   e->scalar0 = e->S;
   if (const char* cl = getenv("HB_CLUSTER")) {
     // experimental: the whole grid in clusters of 2 so that the scalar workers 2c, 2c+1 share distributed shared memory
@@ -754,7 +781,7 @@ extern "C" void hb_engine_destroy(hb_engine* e) {
   cudaFree(e->Xp); cudaFree(e->r); cudaFree(e->u); cudaFree(e->xpx); cudaFree(e->g); cudaFree(e->gsum);
   cudaFree(e->nzrate); cudaFree(e->wppa); cudaFree(e->vargL); cudaFree(e->active); cudaFree(e->tracker);
   cudaFree(e->gram); cudaFree(e->dacc); cudaFree(e->q_snp); cudaFree(e->q_delta);
-  cudaFree(e->tile_cnt); cudaFree(e->corr); cudaFree(e->trace);
+  cudaFree(e->tile_cnt); cudaFree(e->corr); cudaFree(e->trace); cudaFree(e->absmax_dev);
   for (int g = 0; g < 8; ++g) if (e->peer_acc2[g] && e->peer_acc2[g] != e->acc2) cudaIpcCloseMemHandle(e->peer_acc2[g]);
   cudaFree(e->acc2); cudaFree(e->ctrl); cudaFree(e->prm); cudaFree(e->out_dev); cudaFree(e->post_partial); cudaFree(e->fold_dev); cudaFree(e->wstart); cudaFree(e->wmem);
   for (int i = 0; i < 4; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -1071,6 +1098,23 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   CU(cudaEventRecord(e->ev[1], e->stream));
   {
     const void* fn = sweep_kernel_for(in->model_index == HB_MODEL_R ? F : 2, e->RL, dense_model);
+    const int nf_kernel = in->model_index == HB_MODEL_R ? F : 2;
+    if (e->limbs && !dense_model && nf_kernel > 2 && nf_kernel <= 4) {
+      // fixed-point scale of the residual limbs: |q| = |r| rscale must stay below 2^47 while the residual moves during
+      // the sweep (factor 4 of head-room over today's largest element; an overflow aborts the sweep with a message)
+      double amax = 0.0;
+      k_absmax<<<1, 1024, 0, e->stream>>>(e->r, e->n, in->mu_shift, e->absmax_dev);
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(&amax, e->absmax_dev, 8, cudaMemcpyDeviceToHost, e->stream));
+      CU(cudaStreamSynchronize(e->stream));
+      const double bound = 4.0 * std::max(amax, 1e-300);
+      int ex_r = (int)floor(log2(140737488355328.0 / bound));   // 2^47 / bound
+      const int ex_d = (int)lrint(log2(sp.dscale));
+      ex_r = std::max(ex_d - 40, std::min(ex_r, ex_d + 40));
+      sp.rscale = ldexp(1.0, ex_r);
+      sp.rshift = ex_r - ex_d;
+      fn = (const void*)k_sweep<512, 4, 24, false, true>;
+    }
     void* args[] = {(void*)&sp};
     bool launched = false;
     if (e->cluster2) {

@@ -49,9 +49,11 @@ HB_LIMB_FN int hb_limb_dp4a(uint32_t xword, uint32_t limbword, int k, int acc) {
 #endif
 }
 
-// x'q from the six int32 limb sums
+// x'q from the six int32 limb sums.  Valid while 0 <= acc[0..4] < 2^15 and |acc[5]| < 2^15, i.e. for sums over at
+// most 32 rows of genotypes in {0,1,2} (a lane of the sweep kernel merges after its 24 rows): the two halves then fit
+// 32-bit integers (lo < 2^31, |hi| < 2^31) and the merge costs a handful of integer multiply-adds.
 HB_LIMB_FN long long hb_limb_merge(const int acc[HB_NLIMB]) {
-  long long v = 0;
-  for (int k = HB_NLIMB - 1; k >= 0; --k) v = v * 256 + (long long)acc[k];
-  return v;
+  const int lo = acc[0] + acc[1] * 256 + acc[2] * 65536;
+  const int hi = acc[3] + acc[4] * 256 + acc[5] * 65536;
+  return (long long)hi * 16777216ll + (long long)lo;
 }

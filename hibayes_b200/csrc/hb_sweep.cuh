@@ -31,6 +31,7 @@
 
 #include "../../include/hibayes_b200.h"
 #include "hb_device.cuh"
+#include "hb_limbs.h"
 
 struct SweepOutDev {
   double count[HB_MAX_FOLD];
@@ -76,6 +77,10 @@ struct SweepParams {
   int dbg;       // timing experiments only (HB_DEBUG env): 1 skip AXPY, 2 skip dot FMAs, 16/32 streaming side alone
   int scalar0;   // block index of the first scalar CTA (>= S; blocks S .. scalar0-1 are idle padding)
   int cluster2;  // launched as clusters of 2 CTAs: worker pairs (0,1), (2,3), ... hand over through distributed shared memory
+  // LIMBS variant only (HB_LIMBS=1, experimental): the residual slab is handed to the compute warps as 48-bit fixed
+  // point, q = rint(r * rscale), in six 8-bit limbs (hb_limbs.h); rscale = dscale * 2^rshift
+  double rscale;
+  int rshift;
 };
 
 enum { HB_ABORT_TIMEOUT_STREAM = 1, HB_ABORT_TIMEOUT_SCALAR = 2, HB_ABORT_TIMEOUT_TMA = 3, HB_ABORT_OVERFLOW = 4,
@@ -222,7 +227,95 @@ __device__ __forceinline__ void post_corr(double* slot, double v) { st_relaxed_u
 //   columns 8w + 4h + {0..3} and keeps one running dot per column (16 per tile).  After the tile's four
 //   sub-stages the 16 lanes of a half-warp hold 16 x 16 partial dots; a transposed shuffle reduction (8+4+2+1
 //   exchanges, fixed tree) leaves lane l with the complete slab dot of accumulator l.
+// LIMBS variant of the compute warps (experimental, HB_LIMBS=1; written at the end of round 1 and NOT yet run on
+// hardware): integer-only dots.  The AXPY warps publish the residual slab as six 8-bit limbs of q = rint(r * rscale)
+// (hb_limbs.h; limb-major, lbuf[buffer][limb][row]); a lane keeps the limb words of its RL rows in registers for a whole
+// tile; four genotypes of a column -- one 32-bit word as it lies in shared memory, no PRMT -- cost six dp4a, the six
+// int32 sums of a lane's rows merge into one int64, and the half-warp reduction is exact.  The only rounding is the
+// quantisation of r (<= sum(x) / (2 rscale) per slab dot) and the shift to the accumulators' scale.
 template <int RL>
+__device__ void stream_compute_limbs(const SweepParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, uint64_t* rfull,
+                                     uint64_t* rempty) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NS = p.NS, B = p.B, T = p.T, R = p.R, SUBB = p.SUBB;
+  constexpr int Q = 4;
+  constexpr int NW = RL / 4;   // limb words per lane and limb
+  uint8_t* stage0 = smem;
+  const uint8_t* lbuf = smem + p.off_rbuf;   // 2 x HB_NLIMB x R bytes (inside the 2 x R doubles of the fp64 variant)
+  int* ctrl = p.ctrl;
+  const int h = lane >> 4, l = lane & 15;
+  const uint32_t lane_off = (uint32_t)((8 * warp + 4 * h) * R + RL * l);
+  const int my_col = (l >> 2) * SUBB + 8 * warp + 4 * h + (l & 3);
+  int st = 0;
+  uint32_t st_par = 0;
+  for (int t = 0; t < T; ++t) {
+    if (!mbar_wait(rfull + (t & 1), (uint32_t)((t >> 1) & 1), ctrl, HB_ABORT_TIMEOUT_PIPE)) return;
+    uint32_t lw[HB_NLIMB][NW];
+    {
+      const uint8_t* lb = lbuf + (size_t)(t & 1) * HB_NLIMB * R + RL * l;
+#pragma unroll
+      for (int k = 0; k < HB_NLIMB; ++k)
+#pragma unroll
+        for (int w = 0; w < NW; ++w) lw[k][w] = *(const uint32_t*)(lb + (size_t)k * R + 4 * w);
+    }
+    __syncwarp();
+    if (lane == 0) hb::mbar_arrive(rempty + (t & 1));
+    long long acc[16];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      if (!mbar_wait(full + st, st_par, ctrl, HB_ABORT_TIMEOUT_TMA)) return;
+      const uint8_t* sp = stage0 + (size_t)st * p.stage_bytes + lane_off;
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {   // two columns at a time: twelve independent dp4a chains
+        int a0[HB_NLIMB], a1[HB_NLIMB];
+#pragma unroll
+        for (int k = 0; k < HB_NLIMB; ++k) { a0[k] = 0; a1[k] = 0; }
+        const uint8_t* c0p = sp + (size_t)(2 * c2) * R;
+        const uint8_t* c1p = c0p + R;
+#pragma unroll
+        for (int wd = 0; wd < RL / 8; ++wd) {
+          const uint2 v0 = *(const uint2*)(c0p + 8 * wd), v1 = *(const uint2*)(c1p + 8 * wd);
+          if (!(p.dbg & 2)) {
+#pragma unroll
+            for (int k = 0; k < HB_NLIMB; ++k) {
+              a0[k] = hb_limb_dp4a(v0.x, lw[k][2 * wd], k, a0[k]);
+              a1[k] = hb_limb_dp4a(v1.x, lw[k][2 * wd], k, a1[k]);
+              a0[k] = hb_limb_dp4a(v0.y, lw[k][2 * wd + 1], k, a0[k]);
+              a1[k] = hb_limb_dp4a(v1.y, lw[k][2 * wd + 1], k, a1[k]);
+            }
+          }
+        }
+        acc[4 * q + 2 * c2] = hb_limb_merge(a0);
+        acc[4 * q + 2 * c2 + 1] = hb_limb_merge(a1);
+      }
+      __syncwarp();
+      if (lane == 0) hb::mbar_arrive(empty + st);
+      if (++st == NS) { st = 0; st_par ^= 1u; }
+    }
+    // transposed reduction over the 16 lanes of the half-warp (the tree of the fp64 variant; integer sums are exact)
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+      const bool up = (l & o) != 0;
+#pragma unroll
+      for (int i = 0; i < o; ++i) {
+        const long long keep = up ? acc[i + o] : acc[i];
+        const long long send = up ? acc[i] : acc[i + o];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    {
+      // x'q is in units of 1/rscale; the accumulators count units of 1/dscale, rscale = dscale * 2^rshift
+      long long fx = acc[0];
+      if (p.rshift > 0) fx = (fx + (1ll << (p.rshift - 1))) >> p.rshift;
+      else if (p.rshift < 0) fx = fx * (1ll << (-p.rshift));
+      if (!(fx > -(long long)kFixLimit && fx < (long long)kFixLimit)) atomicCAS(ctrl + 1, 0, HB_ABORT_OVERFLOW);
+      atomicAdd(p.dacc + (size_t)t * B + my_col, ((unsigned long long)fx << 8) + 1ull);
+      if (blockIdx.x == 0 && tid == 0) HB_TRACE(t, 7);
+    }
+  }
+}
+
+template <int RL, bool LIMBS = false>
 __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s = blockIdx.x;
@@ -251,6 +344,10 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
 
   if (warp < NCW) {
     // ---------------- compute warps
+    if constexpr (LIMBS) {
+      stream_compute_limbs<RL>(p, smem, full, empty, rfull, rempty);
+      return;
+    }
     const int h = lane >> 4, l = lane & 15;
     const uint32_t lane_off = (uint32_t)((8 * warp + 4 * h) * R + RL * l);
     // accumulator l = 4*q + k  <->  column q*SUBB + 8w + 4h + k of the tile
@@ -429,7 +526,28 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
       }
       if (t < T) {
         if (t >= 2 && !mbar_wait(rempty + (t & 1), (uint32_t)(((t >> 1) - 1) & 1), ctrl, HB_ABORT_TIMEOUT_PIPE)) return;
-        if (has) {
+        if constexpr (LIMBS) {
+          if (has) {
+            // the slab as fixed-point limbs: limb k of this thread's four rows is one 32-bit word
+            uint32_t w[HB_NLIMB];
+#pragma unroll
+            for (int k = 0; k < HB_NLIMB; ++k) w[k] = 0u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint8_t l6[HB_NLIMB];
+              if (!hb_limb_split(rm[i] * kTwo513, p.rscale, l6)) {
+                atomicCAS(ctrl + 1, 0, HB_ABORT_OVERFLOW);
+#pragma unroll
+                for (int k = 0; k < HB_NLIMB; ++k) l6[k] = 0;
+              }
+#pragma unroll
+              for (int k = 0; k < HB_NLIMB; ++k) w[k] |= (uint32_t)l6[k] << (8 * i);
+            }
+            uint8_t* lb = (uint8_t*)rbuf + (size_t)(t & 1) * HB_NLIMB * R + row0;
+#pragma unroll
+            for (int k = 0; k < HB_NLIMB; ++k) *(uint32_t*)(lb + (size_t)k * R) = w[k];
+          }
+        } else if (has) {
           double* rb = rbuf + (size_t)(t & 1) * R + row0;
 #pragma unroll
           for (int i = 0; i < 4; ++i) rb[i] = (rm[i] * kTwo513) * kTwo513;
@@ -1315,9 +1433,9 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
 
 }  // namespace hbk
 
-template <int MAXT, int NF, int RL, bool DENSE>
+template <int MAXT, int NF, int RL, bool DENSE, bool LIMBS = false>
 __global__ void __launch_bounds__(MAXT, 1) k_sweep(const __grid_constant__ SweepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   if ((int)blockIdx.x >= p.scalar0) hbk::scalar_role<NF, DENSE>(p, smem);
-  else if ((int)blockIdx.x < p.S) hbk::stream_role<RL>(p, smem);
+  else if ((int)blockIdx.x < p.S) hbk::stream_role<RL, LIMBS>(p, smem);
 }

@@ -192,3 +192,21 @@ def test_pipeline_ldmat_into_sbayesd_on_the_device(oracle):
     assert np.array_equal(got["diag"]["tracker"], want["diag"]["tracker"])
     assert np.allclose(got["alpha"], want["alpha"], rtol=1e-5, atol=1e-12)
     assert abs(got["Ve"] / want["Ve"] - 1) < 1e-5
+
+
+def test_integer_dot_variant_of_the_sweep_matches_the_oracle(oracle, monkeypatch):
+    """HB_LIMBS=1 (experimental): the streaming CTAs take the dots with dp4a on a 48-bit
+    fixed-point residual (csrc/hb_limbs.h).  Same bar as the fp64 kernel: class labels identical to the oracle,
+    effects within 1e-5 relative (observed tolerance of the fp64 path: 1e-10)."""
+    monkeypatch.setenv("HB_LIMBS", "1")
+    y, X = synth(3000, 2048, seed=21, n_causal=20)
+    kw = dict(model="BayesR", Pi=[0.95, 0.02, 0.02, 0.01], fold=[0, 1e-4, 1e-3, 1e-2], niter=12, nburn=4, thin=2, seed=77)
+    e = hb.Engine(3000, 2048, n_slabs=8)
+    assert e.describe()["rows_per_slab"] == 384        # the variant exists for 384-row slabs only
+    e.close()
+    got = hb.Bayes(y, X, n_slabs=8, **kw)
+    want = oracle.bayes(y, X, kw["model"], kw["Pi"], fold=kw["fold"], niter=12, nburn=4, thin=2, seed=77)
+    assert np.array_equal(got["diag"]["tracker"], want["diag"]["tracker"])
+    assert np.array_equal(got["diag"]["nnz_trace"], want["diag"]["nnz_trace"])
+    assert np.allclose(got["alpha"], want["alpha"], rtol=1e-5, atol=1e-12)
+    assert abs(got["Ve"] / want["Ve"] - 1) < 1e-5

@@ -15,5 +15,10 @@ tail -15 gpurun_out/memcheck_new.log
 timeout 600 python tools/bench_ldmat.py --n 5000 --m 30000 > gpurun_out/bench_ldmat_dense.json 2> gpurun_out/bench_ldmat.err
 timeout 600 python tools/bench_ldmat.py --n 5000 --m 30000 --chisq 3.84 > gpurun_out/bench_ldmat_sparse.json 2>> gpurun_out/bench_ldmat.err
 cat gpurun_out/bench_ldmat_dense.json gpurun_out/bench_ldmat_sparse.json; tail -5 gpurun_out/bench_ldmat.err
+# integer-dot variant of the streaming CTAs (HB_LIMBS=1): streaming side alone (HB_DEBUG=32), then coupled
+HB_DEBUG=32 timeout 600 python bench.py --no-cpu --steps 5 --warmup 3 > gpurun_out/bench_stream_fp64.json 2>> gpurun_out/bench.err
+HB_LIMBS=1 HB_DEBUG=32 timeout 600 python bench.py --no-cpu --steps 5 --warmup 3 > gpurun_out/bench_stream_limbs.json 2>> gpurun_out/bench.err
+HB_LIMBS=1 timeout 600 python bench.py --no-cpu --steps 10 --warmup 5 > gpurun_out/bench_limbs.json 2>> gpurun_out/bench.err
+for f in bench_stream_fp64 bench_stream_limbs bench_limbs; do python -c "import json,sys; d=json.loads(open('gpurun_out/$f.json').read().strip().splitlines()[-1]); print('$f', d['ms_per_step'], d['value'])"; done
 timeout 900 python bench.py --steps 10 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -c 2500 gpurun_out/bench.json
