@@ -398,6 +398,61 @@ def SBayesS(sumstat, ldm, model, Pi, niter=50000, nburn=20000, thin=5, fold=None
                    verbose, seed, device)
 
 
+
+SBRM_METHODS = ("BayesB", "BayesA", "BayesL", "BayesRR", "BayesBpi", "BayesC", "BayesCpi", "BayesR", "CG")
+
+
+def sbrm_plan(sumstat, ldm, method="BayesB", Pi=None, fold=None, niter=None, nburn=None, thin=5, windindx=None):
+    """The argument handling of sbrm() (R/sbayes.r:126-215) up to the call of SBayesD()/SBayesS(): which kernel
+    (dense or sparse LD), the method's default chain length and mixture, the COJO columns that become `sumstat`.
+    sumstat: the 8-column COJO table (SNP, A1, A2, MAF, BETA, SE, P, NMISS) as a 2-D array of floats (the three name
+    columns may hold anything numeric) or an m x 4 array already reduced to (MAF, BETA, SE, NMISS)."""
+    import scipy.sparse as sp
+    if isinstance(ldm, np.ndarray) and ldm.ndim == 2:
+        sparse = False                                             # :126-127
+    elif sp.issparse(ldm):
+        sparse = True                                              # :128-129 (dgCMatrix)
+    else:
+        raise RuntimeError("Unrecognized type of ldm.")            # :131
+    if method not in SBRM_METHODS:
+        raise ValueError("'arg' should be one of " + ", ".join(SBRM_METHODS))   # match.arg, :134
+    if windindx is not None and method in ("BayesA", "BayesRR", "BayesL"):
+        raise RuntimeError("can not implement GWAS analysis for the method: " + method)   # :136-137
+    if method == "CG":
+        raise NotImplementedError("the conjugate-gradient solver (conjgt_den/conjgt_spa) is not part of this build")
+    if niter is None:
+        niter = 50000 if method == "BayesR" else 20000             # :186-188
+    if nburn is None:
+        nburn = 30000 if method == "BayesR" else 12000             # :189-191
+    if thin >= niter - nburn:
+        raise RuntimeError("bad setting for collecting frequency 'thin'.")   # :192
+    if Pi is None:                                                 # :194-201
+        if method == "BayesR":
+            Pi = [0.95, 0.02, 0.02, 0.01]
+            if fold is None:
+                fold = [0, 0.0001, 0.001, 0.01]
+        else:
+            Pi = [0.95, 0.05]
+    ss = np.asarray(sumstat, dtype=np.float64)
+    if ss.ndim != 2 or ss.shape[1] not in (4, 8):
+        raise RuntimeError("Inappropriate summary data format.")
+    if ss.shape[1] == 8:
+        ss = ss[:, [3, 4, 5, 7]]                                   # :205: columns 4, 5, 6, 8
+    return dict(sparse=sparse, sumstat=np.asfortranarray(ss), model=method, Pi=list(Pi), fold=None if fold is None else list(fold),
+                niter=int(niter), nburn=int(nburn), thin=int(thin), windindx=windindx)
+
+
+def sbrm(sumstat, ldm, method="BayesB", Pi=None, fold=None, niter=None, nburn=None, thin=5, windindx=None, vg=None, dfvg=None,
+         s2vg=None, ve=None, dfve=None, s2ve=None, printfreq=100, seed=666666, verbose=False, device=0):
+    """sbrm() of the reference (R/sbayes.r:101-239) for the Bayesian methods, without the map/window bookkeeping
+    (pass `windindx` directly): dispatches to SBayesD() for a dense LD matrix and SBayesS() for a sparse one."""
+    a = sbrm_plan(sumstat, ldm, method, Pi, fold, niter, nburn, thin, windindx)
+    fn = SBayesS if a["sparse"] else SBayesD
+    return fn(a["sumstat"], ldm, a["model"], a["Pi"], niter=a["niter"], nburn=a["nburn"], thin=a["thin"], fold=a["fold"],
+              windindx=a["windindx"], vg=vg, dfvg=dfvg, s2vg=s2vg, ve=ve, dfve=dfve, s2ve=s2ve, outfreq=printfreq,
+              verbose=verbose and printfreq > 0, seed=seed, device=device)
+
+
 class Engine:
     """Thin handle on hb_engine_* (one per GPU)."""
 

@@ -227,3 +227,25 @@ def test_oracle_pipeline_ldmat_into_sbayesd_reproduces_the_golden_pin(oracle, mo
     for k in ("Vg", "Ve", "h2"):
         assert abs(r[k] / float(g[k]) - 1) < 1e-9, k
     assert np.allclose(r["alpha"], g["alpha"], rtol=1e-7, atol=1e-12)
+
+
+def test_sbrm_argument_handling_follows_the_reference():
+    import scipy.sparse as sp
+    m = 6
+    cojo = np.arange(m * 8, dtype=float).reshape(m, 8)
+    dense = np.eye(m)
+    a = hb.sbrm_plan(cojo, dense)
+    assert not a["sparse"] and a["model"] == "BayesB" and a["Pi"] == [0.95, 0.05] and a["fold"] is None
+    assert (a["niter"], a["nburn"]) == (20000, 12000)                       # R/sbayes.r:186-191
+    assert np.array_equal(a["sumstat"], cojo[:, [3, 4, 5, 7]])              # :205
+    b = hb.sbrm_plan(cojo, sp.csc_matrix(dense), method="BayesR")
+    assert b["sparse"] and b["Pi"] == [0.95, 0.02, 0.02, 0.01] and b["fold"] == [0, 0.0001, 0.001, 0.01]
+    assert (b["niter"], b["nburn"]) == (50000, 30000)
+    with pytest.raises(RuntimeError, match="Unrecognized type of ldm"):
+        hb.sbrm_plan(cojo, [[1.0]])
+    with pytest.raises(RuntimeError, match="bad setting for collecting frequency"):
+        hb.sbrm_plan(cojo, dense, niter=100, nburn=96, thin=5)
+    with pytest.raises(RuntimeError, match="can not implement GWAS analysis for the method: BayesA"):
+        hb.sbrm_plan(cojo, dense, method="BayesA", windindx=np.ones(m, dtype=np.int32))
+    with pytest.raises(NotImplementedError):
+        hb.sbrm_plan(cojo, dense, method="CG")

@@ -210,3 +210,19 @@ def test_integer_dot_variant_of_the_sweep_matches_the_oracle(oracle, monkeypatch
     assert np.array_equal(got["diag"]["nnz_trace"], want["diag"]["nnz_trace"])
     assert np.allclose(got["alpha"], want["alpha"], rtol=1e-5, atol=1e-12)
     assert abs(got["Ve"] / want["Ve"] - 1) < 1e-5
+
+
+def test_sbrm_front_end_dispatches_dense_and_sparse(oracle):
+    import scipy.sparse as sp
+    d = load_demo()
+    X = np.asfortranarray(d["geno"][:, :300])
+    cojo = np.zeros((300, 8))
+    cojo[:, 3], cojo[:, 4], cojo[:, 5], cojo[:, 7] = d["ma_maf"][:300], d["ma_beta"][:300], d["ma_se"][:300], d["ma_n"][:300]
+    ld = hb.ldmat(X)
+    r1 = hb.sbrm(cojo, ld, method="BayesCpi", niter=40, nburn=20, thin=5, seed=3)
+    w1 = oracle.sbayesd(cojo[:, [3, 4, 5, 7]], ld, "BayesCpi", [0.95, 0.05], niter=40, nburn=20, thin=5, seed=3)
+    assert np.array_equal(r1["diag"]["tracker"], w1["diag"]["tracker"])
+    lds = sp.csc_matrix(ld)
+    r2 = hb.sbrm(cojo, lds, method="BayesCpi", niter=40, nburn=20, thin=5, seed=3)
+    w2 = oracle.sbayess(cojo[:, [3, 4, 5, 7]], lds, "BayesCpi", [0.95, 0.05], niter=40, nburn=20, thin=5, seed=3)
+    assert np.array_equal(r2["diag"]["tracker"], w2["diag"]["tracker"])
