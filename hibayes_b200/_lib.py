@@ -23,7 +23,7 @@ SYMBOLS = [
     "hb_ld_engine_set_vargL", "hb_ld_engine_set_sparse_info", "hb_ld_engine_get", "hb_ld_engine_sweep", "hb_sbayesd", "hb_sbayess",
     "hb_engine_load_bed", "hb_ldmat_create", "hb_ldmat_destroy", "hb_ldmat_load_i8", "hb_ldmat_load_bed", "hb_ldmat_stats",
     "hb_ldmat_dense", "hb_ldmat_sparse", "hb_ldmat_sparse_get", "hb_ldmat_set_panel_cols", "hb_ldmat_last_ms", "hb_bed_decode",
-    "hb_test_bed_decode_snp", "hb_engine_predict_samples", "hb_test_ld_entries", "hb_test_ld_stats", "hb_test_limb_dot",
+    "hb_test_bed_decode_snp", "hb_engine_predict_samples", "hb_test_ld_entries", "hb_test_ld_stats", "hb_test_limb_dot", "hb_cutwind_by_bp", "hb_cutwind_by_num",
 ]
 
 
@@ -160,6 +160,8 @@ def load_library():
                                      C.c_void_p]
     L.hb_test_ld_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_test_limb_dot.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
+    L.hb_cutwind_by_bp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+    L.hb_cutwind_by_num.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.hb_engine_load_bed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int, C.c_int]
     L.hb_ldmat_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.hb_ldmat_destroy.argtypes = [C.c_void_p]

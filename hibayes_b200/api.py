@@ -399,6 +399,27 @@ def SBayesS(sumstat, ldm, model, Pi, niter=50000, nburn=20000, thin=5, fold=None
 
 
 
+
+def cutwind(chr, pos, windsize=None, windnum=None):
+    """Window ids per SNP for the WPPA counters: cutwind_by_bp / cutwind_by_num of the reference
+    (src/cutwind.cpp:13-65) with the checks of R/sbayes.r:176-182."""
+    L = _lib.load_library()
+    c = np.ascontiguousarray(chr, dtype=np.float64)
+    p_ = np.ascontiguousarray(pos, dtype=np.float64)
+    m = c.shape[0]
+    out = np.zeros(m, dtype=np.int32)
+    if windnum is not None:
+        if m < windnum:
+            raise RuntimeError("Number of markers specified in a window is larger than the total number of markers.")
+        _lib.check(L.hb_cutwind_by_num(c.ctypes.data, p_.ctypes.data, m, int(windnum), out.ctypes.data))
+    else:
+        if windsize is None:
+            raise ValueError("give windsize or windnum")
+        if p_.max() < windsize:
+            raise RuntimeError("Maximum of physical position is smaller than wind size.")
+        _lib.check(L.hb_cutwind_by_bp(c.ctypes.data, p_.ctypes.data, m, float(windsize), out.ctypes.data))
+    return out
+
 SBRM_METHODS = ("BayesB", "BayesA", "BayesL", "BayesRR", "BayesBpi", "BayesC", "BayesCpi", "BayesR", "CG")
 
 

@@ -323,6 +323,11 @@ int hb_ldmat_last_ms(hb_ldmat* h, float* gram_ms);    /* device time of the Gram
 int hb_bed_decode(int device, const uint8_t* file, size_t len, int nid, int m, int impt, int dominance, int8_t* out,
                   uint8_t* miss);
 /* host build of the decoder's byte-level code for one SNP (CPU tests; no device needed) */
+/* Window cutters behind `windindx` (/root/reference/src/cutwind.cpp:13-65; R/sbayes.r:176-182): chr and pos per SNP (numeric
+ * chromosome codes), 1-based window ids out; 0 = in no window (positions < 1, which the reference leaves undefined). */
+int hb_cutwind_by_bp(const double* chr, const double* pos, int m, double bp, int32_t* windindx);
+int hb_cutwind_by_num(const double* chr, const double* pos, int m, int fixN, int32_t* windindx);
+
 /* host build of the LD builder's epilogue: out (m x m) from an exact int32 Gram matrix and BigStat's vectors */
 int hb_test_ld_entries(int n, int m, const int32_t* gram, const double* sum, const double* mean, const double* xx,
                        const int32_t* chr, int has_chisq, double chisq, double* out);
