@@ -420,6 +420,99 @@ def cutwind(chr, pos, windsize=None, windnum=None):
         _lib.check(L.hb_cutwind_by_bp(c.ctypes.data, p_.ctypes.data, m, float(windsize), out.ctypes.data))
     return out
 
+
+IBRM_METHODS = ("BayesCpi", "BayesA", "BayesL", "BSLMM", "BayesR", "BayesB", "BayesC", "BayesBpi", "BayesRR")
+
+
+def ibrm_plan(method="BayesCpi", Pi=None, fold=None, niter=None, nburn=None, thin=5, windsize=None, windnum=None,
+              map_chr=None, map_pos=None):
+    """The argument handling of ibrm() (R/bayes.r:151-276) that decides what Bayes() is called with: the method's
+    default chain length and mixture, the thin check, and the windows (cutwind) when a window size or count is given."""
+    if method not in IBRM_METHODS:
+        raise ValueError("'arg' should be one of " + ", ".join(IBRM_METHODS))     # match.arg, :166
+    if method == "BSLMM":
+        raise NotImplementedError("BSLMM's polygenic term (make_grm + Kival/Ki) is not part of this build")
+    windindx = None
+    if windsize is not None or windnum is not None:
+        if method in ("BayesA", "BayesRR", "BayesL"):
+            raise RuntimeError("can not implement GWAS analysis for the method: " + method)   # :212-213
+        if map_chr is None or map_pos is None:
+            raise RuntimeError("map information must be provided.")              # :214-215
+        pos = np.asarray(map_pos, dtype=np.float64)
+        if np.isnan(pos).any():
+            raise RuntimeError("NAs are not allowed in physical position.")
+        if (pos == 0).any():
+            raise RuntimeError("0 is not allowed in physical position.")
+        names = [str(v) for v in np.asarray(map_chr).tolist()]
+        if any(v == "0" for v in names):
+            raise RuntimeError("0 is not allowed in chromosome.")
+        # numeric chromosome codes; names that are not numbers follow the largest number (:234-243)
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        vals = [num(v) for v in names]
+        mx = max([v for v in vals if v is not None], default=0.0)
+        extra = {}
+        for v, nm in zip(vals, names):
+            if v is None and nm not in extra:
+                extra[nm] = mx + len(extra) + 1
+        codes = np.array([extra[nm] if v is None else v for v, nm in zip(vals, names)], dtype=np.float64)
+        windindx = cutwind(codes, pos, windsize=windsize, windnum=windnum)
+    if niter is None:
+        niter = 50000 if method == "BayesR" else 20000                           # :262-264
+    if nburn is None:
+        nburn = 30000 if method == "BayesR" else 12000                           # :265-267
+    if thin >= niter - nburn:
+        raise RuntimeError("bad setting for collecting frequency 'thin'.")       # :268
+    if Pi is None:                                                               # :270-277
+        if method == "BayesR":
+            Pi = [0.95, 0.02, 0.02, 0.01]
+            if fold is None:
+                fold = [0, 0.0001, 0.001, 0.01]
+        else:
+            Pi = [0.95, 0.05]
+    return dict(model=method, Pi=list(Pi), fold=None if fold is None else list(fold), niter=int(niter), nburn=int(nburn),
+                thin=int(thin), windindx=windindx)
+
+
+def ibrm(y, M, method="BayesCpi", X=None, R=None, map_chr=None, map_pos=None, Pi=None, fold=None, niter=None, nburn=None,
+         thin=5, windsize=None, windnum=None, dfvr=None, s2vr=None, vg=None, dfvg=None, s2vg=None, ve=None, dfve=None,
+         s2ve=None, printfreq=100, seed=666666, verbose=False, device=0):
+    """ibrm() of the reference (R/bayes.r:121-320) after the formula has been resolved: y (NaN = no record) in the row
+    order of M (matrix or BedGeno), X fixed-effect design columns, R level codes of the environmental random effects.
+    Individuals without a record are predicted: g covers all rows of M (:303-308)."""
+    a = ibrm_plan(method, Pi, fold, niter, nburn, thin, windsize, windnum, map_chr, map_pos)
+    y = np.asarray(y, dtype=np.float64)
+    n_all = M.shape[0]
+    if y.shape[0] != n_all:
+        raise RuntimeError("number of individuals mismatched in 'M' and 'M.id'.")   # :157
+    has = ~np.isnan(y)
+    rows = np.flatnonzero(has).astype(np.int32)
+
+    def take(sel):
+        if isinstance(M, BedGeno):
+            base = np.arange(M.nid, dtype=np.int32) if M.rows is None else M.rows
+            return BedGeno(M.image, M.nid, M.m, rows=base[sel], impute=M.impute, mode="D" if M.dominance else "A")
+        return np.asfortranarray(np.asarray(M)[sel, :])
+
+    Mfit = M if has.all() else take(rows)
+    res = Bayes(y[has], Mfit, a["model"], a["Pi"], C_=None if X is None else np.asarray(X)[has], R=None if R is None else np.asarray(R)[has],
+                fold=a["fold"], niter=a["niter"], nburn=a["nburn"], thin=a["thin"], dfvr=dfvr, s2vr=s2vr, vg=vg, dfvg=dfvg,
+                s2vg=s2vg, ve=ve, dfve=dfve, s2ve=s2ve, windindx=a["windindx"], outfreq=printfreq,
+                verbose=verbose and printfreq > 0, seed=seed, device=device)
+    # gebv of every individual of M, with or without a record: the mean over the stored samples of M %*% alpha
+    # (R/bayes.r:303-308) is M times the posterior mean of alpha
+    e = Engine(n_all, M.shape[1], device=device)
+    try:
+        e.load_geno(M)
+        g = e.predict(res["alpha"])
+    finally:
+        e.close()
+    res["g"] = g
+    return res
+
 SBRM_METHODS = ("BayesB", "BayesA", "BayesL", "BayesRR", "BayesBpi", "BayesC", "BayesCpi", "BayesR", "CG")
 
 

@@ -61,3 +61,26 @@ def test_windows_unsorted_chromosomes_and_errors():
         hb.cutwind(chr_, pos, windnum=501)
     with pytest.raises(RuntimeError, match="smaller than wind size"):
         hb.cutwind(chr_, pos, windsize=1e6)
+
+
+def test_ibrm_argument_handling_follows_the_reference():
+    a = hb.ibrm_plan()
+    assert a["model"] == "BayesCpi" and a["Pi"] == [0.95, 0.05] and (a["niter"], a["nburn"]) == (20000, 12000) and a["windindx"] is None
+    b = hb.ibrm_plan("BayesR")
+    assert b["Pi"] == [0.95, 0.02, 0.02, 0.01] and b["fold"] == [0, 0.0001, 0.001, 0.01] and (b["niter"], b["nburn"]) == (50000, 30000)
+    d = load_demo()
+    c = hb.ibrm_plan("BayesCpi", windnum=50, map_chr=d["chr"], map_pos=d["pos"])
+    chr_ = np.array([float(v) for v in d["chr"]])
+    assert np.array_equal(c["windindx"], np_by_num(chr_, d["pos"].astype(np.float64), 50))
+    # a chromosome name that is not a number follows the largest number (R/bayes.r:234-243)
+    names = ["1"] * 5 + ["X"] * 5 + ["2"] * 5
+    e = hb.ibrm_plan("BayesC", windnum=5, map_chr=names, map_pos=np.arange(1, 16))
+    assert e["windindx"].tolist() == [1] * 5 + [3] * 5 + [2] * 5
+    with pytest.raises(RuntimeError, match="can not implement GWAS analysis"):
+        hb.ibrm_plan("BayesL", windnum=5, map_chr=names, map_pos=np.arange(1, 16))
+    with pytest.raises(RuntimeError, match="map information must be provided"):
+        hb.ibrm_plan("BayesC", windnum=5)
+    with pytest.raises(RuntimeError, match="bad setting for collecting frequency"):
+        hb.ibrm_plan(niter=10, nburn=6)
+    with pytest.raises(NotImplementedError):
+        hb.ibrm_plan("BSLMM")

@@ -226,3 +226,19 @@ def test_sbrm_front_end_dispatches_dense_and_sparse(oracle):
     r2 = hb.sbrm(cojo, lds, method="BayesCpi", niter=40, nburn=20, thin=5, seed=3)
     w2 = oracle.sbayess(cojo[:, [3, 4, 5, 7]], lds, "BayesCpi", [0.95, 0.05], niter=40, nburn=20, thin=5, seed=3)
     assert np.array_equal(r2["diag"]["tracker"], w2["diag"]["tracker"])
+
+
+def test_ibrm_front_end_predicts_individuals_without_a_record(oracle):
+    d = load_demo()
+    gid = {s: i for i, s in enumerate(d["geno_id"])}
+    y = np.full(len(d["geno_id"]), np.nan)
+    for pid, t in zip(d["phe_id"], d["T1"]):
+        if pid in gid:
+            y[gid[pid]] = t
+    M = np.asfortranarray(d["geno"])
+    r = hb.ibrm(y, M, method="BayesCpi", niter=40, nburn=20, thin=5, seed=11)
+    has = ~np.isnan(y)
+    w = oracle.bayes(y[has], np.asfortranarray(M[has]), "BayesCpi", [0.95, 0.05], niter=40, nburn=20, thin=5, seed=11)
+    assert np.array_equal(r["diag"]["tracker"], w["diag"]["tracker"])
+    assert np.allclose(r["alpha"], w["alpha"], rtol=1e-5, atol=1e-12)
+    assert np.allclose(r["g"], M.astype(np.float64) @ r["alpha"], rtol=1e-9, atol=1e-9)
