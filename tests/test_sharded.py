@@ -21,7 +21,7 @@ def test_collectives_and_sharding_arithmetic_gloo():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("model", ["BayesR", "BayesCpi"])
+@pytest.mark.parametrize("model", ["BayesR", "BayesCpi", "BayesB"])   # BayesB (BASELINE config 3) added after the last 2-GPU run
 def test_two_gpus_match_the_oracle(model):
     import hibayes_b200 as hb
     if hb.device_count() < 2:
