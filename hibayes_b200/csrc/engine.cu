@@ -91,6 +91,7 @@ struct hb_engine {
   unsigned sweep_no = 0;
   unsigned long long* trace = nullptr;
   int KROW = 0;
+  int lead = 0;       // HB_LEAD=1|2|4 (experiment): phase P speculates as if it ran that many tiles earlier
   int limbs = 0;      // HB_LIMBS=1 (experimental): integer-only dots in the streaming CTAs (k_sweep<..., LIMBS>)
   double* absmax_dev = nullptr;
   int cluster2 = 0;   // HB_CLUSTER=1: scalar workers in clusters of 2 (hand-over through distributed shared memory)
@@ -720,6 +721,17 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, e->block_threads, e->smem_bytes));
     if (occ < 1) { delete e; return hb_set_error("sweep kernel does not fit an SM (threads %d, smem %zu)", e->block_threads, e->smem_bytes); }
   }
+  if (const char* ld = getenv("HB_LEAD")) {
+    const int v = atoi(ld);
+    if ((v == 1 || v == 2 || v == 4) && e->RL == 24) {
+      const void* fn = v == 1 ? (const void*)k_sweep<512, 4, 24, false, false, 1>
+                     : v == 2 ? (const void*)k_sweep<512, 4, 24, false, false, 2> : (const void*)k_sweep<512, 4, 24, false, false, 4>;
+      CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+      e->lead = v;
+    } else if (v) {
+      fprintf(stderr, "[hb] HB_LEAD takes 1, 2 or 4 and needs 384-row slabs (RL = %d): ignored\n", e->RL);
+    }
+  }
   if (const char* lb = getenv("HB_LIMBS")) {
     // experimental: only the bench's kernel shape is instantiated with integer dots
     if (atoi(lb) && e->RL == 24) {
@@ -1099,7 +1111,10 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   {
     const void* fn = sweep_kernel_for(in->model_index == HB_MODEL_R ? F : 2, e->RL, dense_model);
     const int nf_kernel = in->model_index == HB_MODEL_R ? F : 2;
-    if (e->limbs && !dense_model && nf_kernel > 2 && nf_kernel <= 4) {
+    if (e->lead && !dense_model && nf_kernel > 2 && nf_kernel <= 4)
+      fn = e->lead == 1 ? (const void*)k_sweep<512, 4, 24, false, false, 1>
+         : e->lead == 2 ? (const void*)k_sweep<512, 4, 24, false, false, 2> : (const void*)k_sweep<512, 4, 24, false, false, 4>;
+    else if (e->limbs && !dense_model && nf_kernel > 2 && nf_kernel <= 4) {
       // fixed-point scale of the residual limbs: |q| = |r| rscale must stay below 2^47 while the residual moves during
       // the sweep (factor 4 of head-room over today's largest element; an overflow aborts the sweep with a message)
       double amax = 0.0;

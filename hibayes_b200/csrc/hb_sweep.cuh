@@ -972,7 +972,10 @@ __device__ __noinline__ int classify_exact(const double* __restrict__ prm, size_
   return class_from_cum<NF>(nf, __ldcg(prm + prm_idx(0, mp, j)), cum);
 }
 
-template <int NF, bool DENSE>
+// LEAD (experiment, HB_LEAD=1|2|4): the speculation of phase P ignores the corrections owed by the LEAD nearest tiles, as
+// if it had run that many tiles earlier; the sweep's `respec`/`rounds` counters then say how often a candidate list
+// built that early is incomplete (one serial CTA with packages).  LEAD = 0 is the product.
+template <int NF, bool DENSE, int LEAD = 0>
 __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
   // the parameters are read all along the serial phase: keep a copy in shared memory instead of going through the
   // constant cache, which the long code of a tile keeps evicting (a miss there costs a trip to L2)
@@ -1102,7 +1105,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
       for (int q = 0; q < 8; ++q) cw[q] = (q + 1 <= dmax) ? ld_relaxed_u64(p.corr + ((size_t)t * DC + q) * B + i) : kCorrEmpty;
 #pragma unroll
       for (int q = 7; q >= 0; --q)
-        if (cw[q] != kCorrEmpty) cspec += __longlong_as_double((long long)cw[q]);
+        if (cw[q] != kCorrEmpty && q >= LEAD) cspec += __longlong_as_double((long long)cw[q]);
     }
     // the dots: complete when the arrival count in the low byte equals the number of slabs.  Every primary thread
     // waits politely on its own accumulator (16 cache lines per tile, 8 workers: no hot spot), so that the tile
@@ -1433,9 +1436,9 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
 
 }  // namespace hbk
 
-template <int MAXT, int NF, int RL, bool DENSE, bool LIMBS = false>
+template <int MAXT, int NF, int RL, bool DENSE, bool LIMBS = false, int LEAD = 0>
 __global__ void __launch_bounds__(MAXT, 1) k_sweep(const __grid_constant__ SweepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  if ((int)blockIdx.x >= p.scalar0) hbk::scalar_role<NF, DENSE>(p, smem);
+  if ((int)blockIdx.x >= p.scalar0) hbk::scalar_role<NF, DENSE, LEAD>(p, smem);
   else if ((int)blockIdx.x < p.S) hbk::stream_role<RL, LIMBS>(p, smem);
 }

@@ -20,5 +20,11 @@ HB_DEBUG=32 timeout 600 python bench.py --no-cpu --steps 5 --warmup 3 > gpurun_o
 HB_LIMBS=1 HB_DEBUG=32 timeout 600 python bench.py --no-cpu --steps 5 --warmup 3 > gpurun_out/bench_stream_limbs.json 2>> gpurun_out/bench.err
 HB_LIMBS=1 timeout 600 python bench.py --no-cpu --steps 10 --warmup 5 > gpurun_out/bench_limbs.json 2>> gpurun_out/bench.err
 for f in bench_stream_fp64 bench_stream_limbs bench_limbs; do python -c "import json,sys; d=json.loads(open('gpurun_out/$f.json').read().strip().splitlines()[-1]); print('$f', d['ms_per_step'], d['value'])"; done
+# how complete is a candidate list built `lead` tiles early?: rebuilt lists and rounds per sweep
+for lead in 0 1 2 4; do
+  HB_LEAD=$lead HB_PHASES=1 timeout 600 python bench.py --no-cpu --steps 5 --warmup 25 > gpurun_out/bench_lead$lead.json 2> gpurun_out/bench_lead$lead.err
+  echo "lead $lead: $(grep -c 're-speculated' gpurun_out/bench_lead$lead.err) sweeps; last: $(grep 're-speculated' gpurun_out/bench_lead$lead.err | tail -1)"
+  python -c "import json; d=json.loads(open('gpurun_out/bench_lead$lead.json').read().strip().splitlines()[-1]); print('  ms/sweep', d['ms_per_step'], 'rounds/sweep', d['config'].get('scalar_rounds_per_sweep'))"
+done
 timeout 900 python bench.py --steps 10 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -c 2500 gpurun_out/bench.json
