@@ -391,6 +391,8 @@ extern "C" int hb_ldmat_load_bed(hb_ldmat* h, const uint8_t* file, size_t len, i
   size_t bps = 0;
   if (check_bed_image(file, len, nid, h->m, &bps)) return 1;
   if (!rows && nid != h->n) return hb_set_error("hb_ldmat_load_bed: the file has %d individuals, the handle %d; pass the row selection", nid, h->n);
+  if (!impt && (double)h->n * 16384.0 >= 2147483648.0)
+    return hb_set_error("hb_ldmat_load_bed: without imputation a missing genotype is -128, which overflows the exact int32 inner product over %d individuals", h->n);
   if (rows)
     for (int i = 0; i < h->n; ++i)
       if (rows[i] < 0 || rows[i] >= nid) return hb_set_error("hb_ldmat_load_bed: rows[%d] = %d outside the file's %d individuals", i, rows[i], nid);
