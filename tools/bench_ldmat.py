@@ -22,7 +22,20 @@ def main():
     ap.add_argument("--m", type=int, default=30000)
     ap.add_argument("--chisq", type=float, default=None)
     ap.add_argument("--seed", type=int, default=20260101)
+    ap.add_argument("--cpu-m", type=int, default=2000,
+                    help="SNPs of the CPU sample: the oracle's literal tXXmat loop (OpenMP) on the first columns, timed beside the device")
     a = ap.parse_args()
+    if a.cpu_m > 0:
+        # the reference's CPU path (oracle port of tXXmat_Geno: pairs x individuals scalar loop, OpenMP over SNPs)
+        from oracle import hb_oracle
+        mc = min(a.cpu_m, a.m)
+        Xc = hb.synth_geno_host(a.n, mc, a.seed)
+        t0 = time.perf_counter()
+        hb_oracle.txxmat(Xc)
+        tc = time.perf_counter() - t0
+        print(json.dumps({"stage": "ldmat_cpu_port", "n": a.n, "m_sample": mc, "seconds": tc, "cores": os.cpu_count(),
+                          "pair_updates_per_s": mc * (mc + 1) / 2 * a.n / tc,
+                          "note": "oracle/hb_oracle_ld.c, upper triangle only (as the reference); the device computes both triangles"}))
     X = hb.synth_geno_host(a.n, a.m, a.seed)
     t0 = time.perf_counter()
     h = hb.LdMat(X)
