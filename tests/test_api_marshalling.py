@@ -23,6 +23,10 @@ class Recorder:
             self.calls.append((name, args))
             if name in ("hb_engine_create", "hb_ldmat_create"):
                 args[-1]._obj.value = 0xBEEF          # a non-null handle
+            if name == "hb_bayes" and args[0]._obj.x_type == 2:
+                # the hb_bed_source lives for the duration of the call only: look at it now
+                src = C.cast(args[0]._obj.X, C.POINTER(_lib.BedSource)).contents
+                self.bed_seen = (src.nid, src.len, src.impt, src.dominance, bool(src.rows))
             if name == "hb_engine_describe":
                 for a, v in zip(args[1:5], (8, 384, 256, 5)):
                     a._obj.value = v
@@ -96,8 +100,7 @@ def test_bed_inputs_cross_the_abi_as_declared(rec):
     assert name == "hb_bayes"
     args = a[0]._obj
     assert args.x_type == 2 and args.n == 3 and args.m == 6
-    src = C.cast(args.X, C.POINTER(_lib.BedSource)).contents
-    assert src.nid == 10 and src.len == img.shape[0] and src.impt == 1 and src.dominance == 0
+    assert rec.bed_seen == (10, img.shape[0], 1, 0, True)
     with pytest.raises(RuntimeError, match="Number of individuals not equals"):
         hb.Bayes(np.arange(4, dtype=np.float64), g, "BayesCpi", [0.95, 0.05], niter=10, nburn=5)
 
