@@ -106,6 +106,7 @@ class BayesOut(C.Structure):
         ("varg_trace", C.c_void_p),
         ("n_records_done", C.c_int), ("nzct", C.c_int), ("iters_done", C.c_int),
         ("seconds_sweep", C.c_double), ("seconds_setup", C.c_double),
+        ("rounds_total", C.c_longlong), ("tiles_total", C.c_longlong),
     ]
 
 

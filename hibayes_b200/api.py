@@ -314,7 +314,8 @@ def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, nite
     res.update({"Vg": o.Vg, "Ve": o.Ve, "h2": o.h2, "mu": o.mu, "Veps": o.Veps, "J": o.J})
     res["MCMCsamples"] = mc
     dg.update({"n_records": o.n_records_done, "nzct": o.nzct, "iters_done": o.iters_done,
-               "seconds_sweep": o.seconds_sweep, "seconds_setup": o.seconds_setup})
+               "seconds_sweep": o.seconds_sweep, "seconds_setup": o.seconds_setup,
+               "rounds_total": o.rounds_total, "tiles_total": o.tiles_total})
     res["diag"] = dg
     return res
 

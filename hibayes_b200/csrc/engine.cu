@@ -95,6 +95,12 @@ struct hb_engine {
   int limbs = 0;      // HB_LIMBS=1 (experimental): integer-only dots in the streaming CTAs (k_sweep<..., LIMBS>)
   double* absmax_dev = nullptr;
   int cluster2 = 0;   // HB_CLUSTER=1: scalar workers in clusters of 2 (hand-over through distributed shared memory)
+  // serial mode (hb_serial.cuh; mixture models): one serial CTA + NH helper CTAs instead of the ring of NG workers
+  int serial = 0, NH = 0, KROW_S = 0;
+  uint32_t pkg_stride = 0;
+  uint8_t* pkg = nullptr;
+  int* pkg_flag = nullptr;
+  int* miss_tile = nullptr;
   int scalar0 = 0;    // block index of the first scalar CTA
   int* ctrl = nullptr;  // [0] progress, [1] abort
   double* prm = nullptr;  // per-SNP sweep parameters, SoA
@@ -393,14 +399,16 @@ __global__ void k_prep(PrepParams p, const double* __restrict__ xpx, const uint8
                        const double* __restrict__ g, const double* __restrict__ vargL, double* __restrict__ prm,
                        unsigned long long* __restrict__ dacc, int* __restrict__ ctrl, SweepOutDev* __restrict__ out,
                        int* __restrict__ tile_cnt, int* __restrict__ q_snp, unsigned long long* __restrict__ q_delta,
-                       unsigned long long* __restrict__ corr, int B, int DC, unsigned long long* __restrict__ acc2_next) {
+                       unsigned long long* __restrict__ corr, int B, int DC, unsigned long long* __restrict__ acc2_next,
+                       int* __restrict__ pkg_flag, int* __restrict__ miss_tile) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) {
     ctrl[0] = 0; ctrl[1] = 0;
+    if (miss_tile) *miss_tile = -(1 << 28);
     out->n_changed = 0; out->status = 0; out->rounds = 0; out->pad = 0; out->varg_acc = 0; out->sum_vargL = 0;
     for (int k = 0; k < HB_MAX_FOLD; ++k) out->count[k] = 0;
   }
-  if (j < p.T) tile_cnt[j] = -1;
+  if (j < p.T) { tile_cnt[j] = -1; if (pkg_flag) pkg_flag[j] = 0; }
   if (j >= p.m_pad) return;
   dacc[j] = 0ull;
   if (acc2_next) acc2_next[j] = 0ull;   // the buffer of the sweep after this one (see hb_engine_sweep)
@@ -468,6 +476,15 @@ static const void* sweep_kernel_rl(int nf, bool dense) {
 // kernel variants: rows per lane x number of mixture classes held in registers x dense/mixture chain
 static const void* sweep_kernel_for(int nf, int rl, bool dense) {
   return rl == 8 ? sweep_kernel_rl<8>(nf, dense) : rl == 16 ? sweep_kernel_rl<16>(nf, dense) : sweep_kernel_rl<24>(nf, dense);
+}
+// the mixture models with the serial CTA + helpers (hb_serial.cuh)
+template <int RL>
+static const void* serial_kernel_rl(int nf) {
+  return nf <= 2 ? (const void*)k_sweep<512, 2, RL, false, false, 0, true>
+       : nf <= 4 ? (const void*)k_sweep<512, 4, RL, false, false, 0, true> : (const void*)k_sweep<512, HB_MAX_FOLD, RL, false, false, 0, true>;
+}
+static const void* serial_kernel_for(int nf, int rl) {
+  return rl == 8 ? serial_kernel_rl<8>(nf) : rl == 16 ? serial_kernel_rl<16>(nf) : serial_kernel_rl<24>(nf);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -662,7 +679,12 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   e->n = cfg->n; e->m = cfg->m;
   e->nsm = prop.multiProcessorCount;
   e->B = cfg->tile_snps > 0 ? cfg->tile_snps : 256;
-  e->D = cfg->lag_tiles > 0 ? cfg->lag_tiles : 5;
+  // serial mode is the default for the mixture models; HB_RING=1 keeps the ring of workers for everything
+  e->serial = getenv("HB_RING") && atoi(getenv("HB_RING")) ? 0 : 1;
+  if (e->B != hbk::kSerialB) e->serial = 0;   // (compiled for tiles of 256 SNPs)
+  // tiles in flight between a tile's dots and its residual update: the loop publish -> AXPY -> dots -> phase P -> package
+  // takes ~17 us, i.e. 7-8 tiles at the chain's pace (serial mode); the ring of workers is paced by its hand-over (5)
+  e->D = cfg->lag_tiles > 0 ? cfg->lag_tiles : (e->serial ? 8 : 5);
   if (e->B != 64 && e->B != 128 && e->B != 256) { delete e; return hb_set_error("tile_snps must be 64, 128 or 256"); }
   if (e->D > 8) { delete e; return hb_set_error("lag_tiles must be <= 8"); }
   e->NG = 8;   // scalar CTAs (one worker each)
@@ -714,6 +736,13 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   const size_t scalar_smem = hbk::scalar_smem_bytes(e->B);
   e->KROW = hbk::scalar_krow(e->B);
   e->smem_bytes = std::max(stream_smem, scalar_smem);
+  if (e->serial) {
+    e->KROW_S = hbk::serial_krow(e->B);
+    e->pkg_stride = hbk::pkg_layout(e->B, e->KROW_S).stride;
+    e->smem_bytes = std::max(e->smem_bytes, hbk::serial_smem_bytes(e->B));
+    e->NH = std::max(1, std::min(16, e->nsm - e->S - 1));
+    if (const char* nh = getenv("HB_NH")) e->NH = std::max(1, std::min(e->NH, atoi(nh)));
+  }
   for (int v = 0; v < 4; ++v) {
     const void* fn = sweep_kernel_for(v == 0 ? 2 : v == 1 ? 4 : HB_MAX_FOLD, e->RL, v == 3);
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
@@ -721,6 +750,14 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, e->block_threads, e->smem_bytes));
     if (occ < 1) { delete e; return hb_set_error("sweep kernel does not fit an SM (threads %d, smem %zu)", e->block_threads, e->smem_bytes); }
   }
+  if (e->serial)
+    for (int v = 0; v < 3; ++v) {
+      const void* fn = serial_kernel_for(v == 0 ? 2 : v == 1 ? 4 : HB_MAX_FOLD, e->RL);
+      CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+      int occ = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, e->block_threads, e->smem_bytes));
+      if (occ < 1) { delete e; return hb_set_error("serial sweep kernel does not fit an SM (threads %d, smem %zu)", e->block_threads, e->smem_bytes); }
+    }
   if (const char* ld = getenv("HB_LEAD")) {
     const int v = atoi(ld);
     if ((v == 1 || v == 2 || v == 4) && e->RL == 24) {
@@ -779,6 +816,11 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   }
   CU(cudaMalloc(&e->corr, std::max<size_t>(1, (size_t)e->m_pad * (e->D - 1)) * 8));
   CU(cudaMalloc(&e->ctrl, 64)); CU(cudaMemsetAsync(e->ctrl, 0, 64, e->stream));
+  if (e->serial) {
+    CU(cudaMalloc(&e->pkg, (size_t)e->T * e->pkg_stride));
+    CU(cudaMalloc(&e->pkg_flag, (size_t)e->T * 4));
+    CU(cudaMalloc(&e->miss_tile, 64));
+  }
   CU(cudaMalloc(&e->out_dev, sizeof(SweepOutDev)));
   CU(cudaMalloc(&e->post_partial, (size_t)kPostBlocks * (HB_MAX_FOLD + 1) * 8));
   CU(cudaMalloc(&e->fold_dev, HB_MAX_FOLD * 8));
@@ -794,6 +836,7 @@ extern "C" void hb_engine_destroy(hb_engine* e) {
   cudaFree(e->nzrate); cudaFree(e->wppa); cudaFree(e->vargL); cudaFree(e->active); cudaFree(e->tracker);
   cudaFree(e->gram); cudaFree(e->dacc); cudaFree(e->q_snp); cudaFree(e->q_delta);
   cudaFree(e->tile_cnt); cudaFree(e->corr); cudaFree(e->trace); cudaFree(e->absmax_dev);
+  cudaFree(e->pkg); cudaFree(e->pkg_flag); cudaFree(e->miss_tile);
   for (int g = 0; g < 8; ++g) if (e->peer_acc2[g] && e->peer_acc2[g] != e->acc2) cudaIpcCloseMemHandle(e->peer_acc2[g]);
   cudaFree(e->acc2); cudaFree(e->ctrl); cudaFree(e->prm); cudaFree(e->out_dev); cudaFree(e->post_partial); cudaFree(e->fold_dev); cudaFree(e->wstart); cudaFree(e->wmem);
   for (int i = 0; i < 4; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -1069,7 +1112,7 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   memset(&sp, 0, sizeof sp);
   sp.Xp = e->Xp; sp.r = e->r; sp.u = e->u; sp.xpx = e->xpx; sp.active = e->active; sp.g = e->g; sp.tracker = e->tracker;
   sp.gram = e->gram; sp.dacc = e->dacc; sp.q_snp = e->q_snp; sp.q_delta = e->q_delta;
-  if (getenv("HB_TRACE") && !e->trace) { CU(cudaMalloc(&e->trace, (size_t)e->T * 64)); CU(cudaMemset(e->trace, 0, (size_t)e->T * 64)); }
+  if (getenv("HB_TRACE") && !e->trace) { CU(cudaMalloc(&e->trace, (size_t)e->T * 128)); CU(cudaMemset(e->trace, 0, (size_t)e->T * 128)); }
   sp.trace = e->trace;
   sp.world = std::max(1, e->cfg.world); sp.rank = e->cfg.rank;
   if (sp.world > 1) {
@@ -1100,17 +1143,28 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
     sp.inv_dscale = ldexp(1.0, -ex);
   }
   { const char* dbg = getenv("HB_DEBUG"); sp.dbg = dbg ? atoi(dbg) : 0; }
+  if (getenv("HB_PHASES")) sp.dbg |= 64;   // per-phase cycle counters of the serial CTA (they cost ~1 us per tile)
 
   const bool dense_model = in->model_index == HB_MODEL_RR || in->model_index == HB_MODEL_A || in->model_index == HB_MODEL_L;
   CU(cudaEventRecord(e->ev[0], e->stream));
   k_prep<<<(e->m_pad + 255) / 256, 256, 0, e->stream>>>(pp, e->xpx, e->active, e->g, e->vargL, e->prm, e->dacc, e->ctrl, e->out_dev,
                                                        e->tile_cnt, e->q_snp, (unsigned long long*)e->q_delta, (unsigned long long*)e->corr, e->B, e->D - 1,
-                                                       e->acc2 ? e->acc2 + (size_t)((e->sweep_no + 1) & 1) * e->m_pad : nullptr);
+                                                       e->acc2 ? e->acc2 + (size_t)((e->sweep_no + 1) & 1) * e->m_pad : nullptr,
+                                                       e->pkg_flag, e->miss_tile);
   CU(cudaGetLastError());
   CU(cudaEventRecord(e->ev[1], e->stream));
   {
     const void* fn = sweep_kernel_for(in->model_index == HB_MODEL_R ? F : 2, e->RL, dense_model);
     const int nf_kernel = in->model_index == HB_MODEL_R ? F : 2;
+    // serial CTA + helpers: mixture models whose classes are decided by thresholds
+    const bool serial = e->serial && !dense_model && pp.use_thr && !e->lead && !e->limbs && !e->cluster2;
+    int nscalar = e->NG;
+    if (serial) {
+      fn = serial_kernel_for(nf_kernel, e->RL);
+      sp.serial = 1; sp.NH = e->NH; sp.KROW_S = e->KROW_S; sp.pkg_stride = e->pkg_stride;
+      sp.pkg = e->pkg; sp.pkg_flag = e->pkg_flag; sp.miss_tile = e->miss_tile;
+      nscalar = 1 + e->NH;
+    }
     if (e->lead && !dense_model && nf_kernel > 2 && nf_kernel <= 4)
       fn = e->lead == 1 ? (const void*)k_sweep<512, 4, 24, false, false, 1>
          : e->lead == 2 ? (const void*)k_sweep<512, 4, 24, false, false, 2> : (const void*)k_sweep<512, 4, 24, false, false, 4>;
@@ -1165,7 +1219,7 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
     if (!launched) {
       sp.cluster2 = 0;
       sp.scalar0 = e->S;
-      CU(cudaLaunchCooperativeKernel(fn, dim3(e->S + e->NG), dim3(e->block_threads), args, e->smem_bytes, e->stream));
+      CU(cudaLaunchCooperativeKernel(fn, dim3(e->S + nscalar), dim3(e->block_threads), args, e->smem_bytes, e->stream));
     }
   }
   CU(cudaEventRecord(e->ev[2], e->stream));
@@ -1197,11 +1251,18 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   out->n_changed = h.n_changed; out->status = h.status; out->rounds = h.rounds; out->reserved = 0;
   if (e->trace && getenv("HB_TRACE")) {
     // event stamps of the tiles of this sweep -> file (ns): see tools/trace_report.py
-    std::vector<unsigned long long> tr((size_t)e->T * 8);
+    std::vector<unsigned long long> tr((size_t)e->T * 16);
     CU(cudaMemcpy(tr.data(), e->trace, tr.size() * 8, cudaMemcpyDeviceToHost));
     if (FILE* f = fopen(getenv("HB_TRACE"), "wb")) { fwrite(tr.data(), 8, tr.size(), f); fclose(f); }
   }
-  if (getenv("HB_PHASES")) {
+  if (getenv("HB_PHASES") && sp.serial) {
+    static const char* nm[13] = {"wait_pkg", "rhs0", "-", "bar_open", "chain", "final", "publish", "tail", "bar_chain", "loop", "bar_part",
+                                 "verify", "bar_bad"};
+    fprintf(stderr, "[hb] serial CTA: tiles repaired %d, generic %lld, rounds %d (tiles %d)\n[hb phases serial]", h.pad,
+            h.phase_clk[1][1], h.rounds, e->T);
+    for (int k = 0; k < 13; ++k) fprintf(stderr, " %s=%.0f", nm[k], (double)h.phase_clk[0][k] / std::max(1, e->T));
+    fprintf(stderr, " (cycles per tile)\n");
+  } else if (getenv("HB_PHASES")) {
     fprintf(stderr, "[hb] tiles re-speculated before the chain: %d, rounds %d (tiles %d)\n", h.pad, h.rounds, e->T);
     static const char* nm[16] = {"wait_dots", "guess", "wait_prev", "bar_rhs0", "chain", "first", "post", "commit",
                                  "bar_chain", "loop", "bar_part", "classify", "bar_bad", "-", "-", "-"};

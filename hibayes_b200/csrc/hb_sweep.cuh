@@ -62,7 +62,7 @@ struct SweepParams {
   int* tile_cnt;              // per tile: number of changes, -1 until known
   double* corr;               // [T][D-1][B] corrections owed to tile t by tile t-dt, kCorrEmpty = not yet written
   int* ctrl;                  // [1] abort code
-  unsigned long long* trace;  // diagnostics (HB_TRACE): [T][8] globaltimer stamps of a tile's events, or null
+  unsigned long long* trace;  // diagnostics (HB_TRACE): [T][16] globaltimer stamps of a tile's events, or null
   const double* prm;
   SweepOutDev* out;
   size_t slab_stride, m_pad;
@@ -81,6 +81,15 @@ struct SweepParams {
   // point, q = rint(r * rscale), in six 8-bit limbs (hb_limbs.h); rscale = dscale * 2^rshift
   double rscale;
   int rshift;
+  // serial mode (hb_serial.cuh): one serial CTA (block scalar0) runs phase S of every tile, NH helper CTAs (blocks
+  // scalar0+1 ..) prepare the tiles (phase P -> a package in global memory) and post the far corrections (phase C)
+  int serial;                 // 1: serial CTA + helpers; 0: ring of NG workers (scalar_role)
+  int NH;                     // helper CTAs
+  int KROW_S;                 // row slots (and candidates) of a package
+  uint32_t pkg_stride;        // bytes between the packages of consecutive tiles
+  uint8_t* pkg;               // [T] packages
+  int* pkg_flag;              // [T] 0 = not written yet, else 1 + number of row slots (| 1 << 20: no rows, generic path)
+  int* miss_tile;             // [1] last tile that needed a second round (the helpers widen their row sets after it)
 };
 
 enum { HB_ABORT_TIMEOUT_STREAM = 1, HB_ABORT_TIMEOUT_SCALAR = 2, HB_ABORT_TIMEOUT_TMA = 3, HB_ABORT_OVERFLOW = 4,
@@ -157,7 +166,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* c
   return true;
 }
 
-#define HB_TRACE(t, ev) do { if (p.trace) p.trace[(size_t)(t) * 8 + (ev)] = gtimer(); } while (0)
+#define HB_TRACE(t, ev) do { if (p.trace) p.trace[(size_t)(t) * 16 + (ev)] = gtimer(); } while (0)
 
 __device__ __forceinline__ double byte_as_scaled(uint32_t w, uint32_t sel) {
   // genotype byte -> mantissa bits 48..55 of a double: value = byte * 2^-1026 (exact, denormal)
@@ -763,7 +772,8 @@ __device__ __noinline__ void gather_rows(int32_t* dst, const int32_t* __restrict
 // ROWS: the candidates' Gram rows are in shared memory (doubles); otherwise they are read from global.
 template <bool ROWS>
 __device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const int32_t* __restrict__ G, const int32_t* rows, int B, int lane,
-                                                 const double* coef = nullptr) {
+                                                 const double* coef = nullptr, int rs = 0) {
+  if (rs == 0) rs = B;   // stride between the rows of the row buffer (the serial CTA interleaves two blocks: 2 B)
   for (int sb = 0; sb < k; sb += 32) {
     const int sidx = sb + lane;
     const bool valid = sidx < k;
@@ -772,7 +782,7 @@ __device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const
     const double niv = -iv;
     double e = valid ? fma(cs.rhs0[sidx], iv, cs.sdz[sidx]) - gold : 0.0;
     auto gval = [&](int sp) -> double {
-      return gram_as_double(ROWS ? rows[(size_t)cs.slot[sp] * B + ci] : __ldcg(G + (size_t)cs.idx[sp] * B + ci));
+      return gram_as_double(ROWS ? rows[(size_t)cs.slot[sp] * rs + ci] : __ldcg(G + (size_t)cs.idx[sp] * B + ci));
     };
     // candidates of earlier chunks: their changes are final
     for (int sp = 0; sp < sb; sp += 8) {
@@ -812,7 +822,7 @@ __device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const
           for (int q = 0; q < 16; ++q) {
             const int lp = 16 * hc + q;
             const int row = min(sb + lp, k - 1);
-            const double gv = gram_as_double(rows[(size_t)cs.slot[row] * B + ci]) * niv;
+            const double gv = gram_as_double(rows[(size_t)cs.slot[row] * rs + ci]) * niv;
             hreg[q] = (valid && lp < lane && lp < nl) ? gv : 0.0;
           }
 #pragma unroll
@@ -944,10 +954,8 @@ __device__ __forceinline__ double band_correction(const CandSet& cs, int k, cons
 
 // Tiles with more candidates than a row buffer holds (k > KROW): chain and sums straight from the Gram band in
 // global memory.  Rare and slow; kept out of line so that the common path stays compact in the instruction cache.
-__device__ __noinline__ double slow_chain_and_sums(int k, int myrank, const int32_t* __restrict__ G0, int B,
-                                                 int i, int h, bool has1, bool dense, int model, int nthreads) {
-  extern __shared__ __align__(128) uint8_t smem_slow[];
-  const CandSet cs = make_candset(smem_slow, B);
+__device__ __noinline__ double slow_chain_and_sums_cs(const CandSet& cs, int k, int myrank, const int32_t* __restrict__ G0, int B,
+                                                    int i, int h, bool has1, bool dense, int model, int nthreads) {
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < 32 && k > 0) {
     if (dense) solve_candidates<false>(cs, k, G0, nullptr, B, model, lane);
@@ -957,6 +965,12 @@ __device__ __noinline__ double slow_chain_and_sums(int k, int myrank, const int3
   // the primary half returns its right-hand-side sum, the secondary half the corrections for the next tile
   if (h == 0) return band_correction(cs, myrank, G0, B, i);
   return has1 ? band_correction(cs, k, G0 + (size_t)B * B, B, i) : 0.0;
+}
+__device__ __forceinline__ double slow_chain_and_sums(int k, int myrank, const int32_t* __restrict__ G0, int B,
+                                                    int i, int h, bool has1, bool dense, int model, int nthreads) {
+  extern __shared__ __align__(128) uint8_t smem_slow[];
+  const CandSet cs = make_candset(smem_slow, B);
+  return slow_chain_and_sums_cs(cs, k, myrank, G0, B, i, h, has1, dense, model, nthreads);
 }
 
 // exact class of SNP j given rr = rhs^2 (reads its a_k, c_k and uniform from the parameter table)
@@ -1436,9 +1450,19 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
 
 }  // namespace hbk
 
-template <int MAXT, int NF, int RL, bool DENSE, bool LIMBS = false, int LEAD = 0>
+#include "hb_serial.cuh"
+
+// SERIAL: the mixture models' scalar side as one serial CTA + helper CTAs (hb_serial.cuh) instead of the ring of
+// workers (scalar_role); the streaming CTAs are the same.
+template <int MAXT, int NF, int RL, bool DENSE, bool LIMBS = false, int LEAD = 0, bool SERIAL = false>
 __global__ void __launch_bounds__(MAXT, 1) k_sweep(const __grid_constant__ SweepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  if ((int)blockIdx.x >= p.scalar0) hbk::scalar_role<NF, DENSE, LEAD>(p, smem);
-  else if ((int)blockIdx.x < p.S) hbk::stream_role<RL, LIMBS>(p, smem);
+  if ((int)blockIdx.x < p.S) { hbk::stream_role<RL, LIMBS>(p, smem); return; }
+  if ((int)blockIdx.x < p.scalar0) return;
+  if constexpr (SERIAL) {
+    if ((int)blockIdx.x == p.scalar0) hbk::serial_role<NF>(p, smem);
+    else hbk::helper_role<NF>(p, smem);
+  } else {
+    hbk::scalar_role<NF, DENSE, LEAD>(p, smem);
+  }
 }

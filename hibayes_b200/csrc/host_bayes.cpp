@@ -71,6 +71,7 @@ double seconds_since(const std::chrono::steady_clock::time_point& t0) {
 
 extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
   if (!a || !o) return hb_set_error("hb_bayes: null argument");
+  o->rounds_total = 0; o->tiles_total = 0;
   const int n = a->n, m = a->m;
   const int world = a->world > 1 ? a->world : 1;
   const double ntot = world > 1 ? (double)a->n_total : (double)n;   // individuals over all ranks
@@ -358,6 +359,12 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
     hb_sweep_out so;
     HBCHK(hb_engine_sweep(E, &in, &so));
     { float a0, a1, a2; hb_engine_last_sweep_ms(E, &a0, &a1, &a2); t_sweep += 1e-3 * (a0 + a1 + a2); }
+    {
+      int tsz = 0;
+      hb_engine_describe(E, nullptr, nullptr, &tsz, nullptr, nullptr, nullptr);
+      o->rounds_total += so.rounds;
+      o->tiles_total += (m + tsz - 1) / std::max(1, tsz);
+    }
 
     switch (model_index) {
       case 1:

@@ -213,6 +213,9 @@ typedef struct {
   int n_records_done, nzct, iters_done;
   double seconds_sweep;     /* device time inside hb_engine_sweep, seconds */
   double seconds_setup;     /* load + stats + gram */
+  /* diagnostics of the scalar chain: speculation rounds and tiles summed over the sweeps (rounds > tiles means that
+   * classes had to be re-decided after a first look), and the sweeps' device time per kernel */
+  long long rounds_total, tiles_total;
 } hb_bayes_out;
 
 int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o);

@@ -1,9 +1,12 @@
-"""Reads an HB_TRACE dump ([T][8] globaltimer ns per tile) and prints where a tile's time goes.
+"""Reads an HB_TRACE dump ([T][16] globaltimer ns per tile) and prints where a tile's time goes.
 events: 0 dots seen by worker, 1 P done, 2 hand-over from t-1 arrived, 3 S done (hand-over posted), 4 updates published,
-5 C done, 6 AXPY warp of slab 0 fetched the tile's updates, 7 compute warp 0 of slab 0 added its dots of the tile."""
+5 C done, 6 AXPY warp of slab 0 fetched the tile's updates, 7 compute warp 0 of slab 0 added its dots of the tile.
+Serial mode (hb_serial.cuh): 0/1 = the helper's phase P (dots seen, package flagged), 2 = package in the serial CTA's shared
+memory, 3 = tile final, 4 = published, 5 = serial CTA done with the tile, 8/9/10 = the helper's phase C (changes seen, first far
+correction posted, done), 11 = the loader saw the package flag."""
 import sys
 import numpy as np
-a = np.fromfile(sys.argv[1], dtype=np.uint64).reshape(-1, 8).astype(np.int64)
+a = np.fromfile(sys.argv[1], dtype=np.uint64).reshape(-1, 16).astype(np.int64)
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 T = a.shape[0]
 lo, hi = T // 4, 3 * T // 4
@@ -38,3 +41,13 @@ for par, name in ((1, "odd tiles (cluster mode: local hand-over)"), (0, "even ti
     print("S done of t-1 -> hand-over arrived at t, %s: mean %.0f p10 %.0f p50 %.0f p90 %.0f" % (name, x.mean(), np.percentile(x, 10), np.percentile(x, 50), np.percentile(x, 90)))
 sd = (a[lo:hi, 3] - a[lo:hi, 2]).astype(np.float64)
 print("hand-over arrived -> S done: mean %.0f p10 %.0f p50 %.0f p90 %.0f" % (sd.mean(), np.percentile(sd, 10), np.percentile(sd, 50), np.percentile(sd, 90)))
+
+if a[lo:hi, 8].any():
+    print("-- serial mode")
+    print("package flagged (1) -> loader saw the flag (11): %.0f" % d(11, 1))
+    print("loader saw the flag (11) -> package in shared memory, tile started (2): %.0f" % d(2, 11))
+    print("published (4) -> helper saw the changes (8): %.0f" % d(8, 4))
+    print("helper saw the changes (8) -> first far correction posted (9): %.0f" % d(9, 8))
+    print("helper saw the changes (8) -> phase C done (10): %.0f" % d(10, 8))
+    print("tile final (3) -> serial CTA done with the tile (5): %.0f" % d(5, 3))
+    print("serial CTA done with t-1 (5) -> tile t started (2): %.0f" % float(np.median(a[lo + 1:hi, 2] - a[lo:hi - 1, 5])))
