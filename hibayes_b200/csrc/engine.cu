@@ -1143,6 +1143,7 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
     sp.inv_dscale = ldexp(1.0, -ex);
   }
   { const char* dbg = getenv("HB_DEBUG"); sp.dbg = dbg ? atoi(dbg) : 0; }
+  if (const char* xe = getenv("HB_XEVICT")) sp.xevict = atoi(xe);
   if (getenv("HB_PHASES")) sp.dbg |= 64;   // per-phase cycle counters of the serial CTA (they cost ~1 us per tile)
 
   const bool dense_model = in->model_index == HB_MODEL_RR || in->model_index == HB_MODEL_A || in->model_index == HB_MODEL_L;

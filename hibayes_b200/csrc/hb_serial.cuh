@@ -37,10 +37,10 @@ __host__ __device__ constexpr PkgLayout pkg_layout(int B, int KC) {
   PkgLayout L{};
   uint32_t o = 0;
   L.o_hdr = o; o += 64;
-  L.o_base0 = o; o += 8 * B;
-  L.o_addback = o; o += 8 * B;
-  L.o_lo = o; o += 8 * B;
-  L.o_hi = o; o += 8 * B;
+  L.o_base0 = o; o += 8 * B;          // x'r of the stale residual + xpx * g (the corrections are still to be subtracted)
+  L.o_addback = L.o_base0;
+  L.o_lo = o; o += 4 * B;             // interval of rhs^2 on which the speculated class holds, as floats rounded inwards
+  L.o_hi = o; o += 4 * B;
   L.o_info = o; o += 4 * B;
   L.o_slotof = o; o += 4 * B;
   const uint32_t kc8 = 8 * ((KC + 1) & ~1u), kc4 = 4 * ((KC + 3) & ~3u);
@@ -65,30 +65,35 @@ __host__ __device__ constexpr PkgLayout pkg_layout(int B, int KC) {
 enum { PK_K = 0, PK_NS = 1, PK_FAST = 2, PK_MOK = 3, PK_TILE = 4, PK_HAS1 = 5 };
 // info word of a SNP: class | candidate << 4 | active << 5 | exact-check << 6 | rank << 8
 constexpr int kPkgNoRows = 1 << 20;
-constexpr int kMaxDC = 11;   // serial mode: lag of at most 12 tiles (far-correction words a thread asks for one tile ahead)
+constexpr int kMaxDC = 7;    // serial mode: lag of at most 8 tiles (landing zone of a tile's far-correction slots)
 constexpr int kSerialB = 256;   // serial mode is compiled for tiles of 256 SNPs (every offset below is a constant)
 
 // private shared memory of the serial CTA behind the two package buffers (byte offsets from its start)
+constexpr int kNear2 = 33;   // changes of a tile whose Gram entries towards t+2 travel in registers (3 subsets of 11)
 struct PrivLayout {
-  uint32_t o_part_rhs, o_part_corr, o_c2buf, o_coef, o_dl2, o_ix2, o_new_snp, o_rank, o_g2land, o_wcnt, o_gctl, o_pc, o_full, o_empty, bytes;
+  uint32_t o_part_rhs, o_part_corr, o_coldbuf, o_c2part, o_coef, o_dl2, o_ix2, o_new_snp, o_rank, o_stage, o_wcnt, o_gctl, o_pc,
+      o_full, o_empty, o_farfull, o_stagefull, bytes;
 };
 __host__ __device__ constexpr PrivLayout priv_layout(int B) {
   PrivLayout P{};
   uint32_t o = 0;
-  P.o_part_rhs = o; o += 8 * B;
-  P.o_part_corr = o; o += 8 * B;
-  P.o_c2buf = o; o += 2 * 8 * B;      // [2][B] correction owed by tile t-2, by parity of the receiving tile
-  P.o_coef = o; o += 32 * 32 * 8;     // chain coefficients of the first 32 candidates (no solved matrix / repair rounds)
-  P.o_dl2 = o; o += 2 * 32 * 8;       // first 32 changes of the last two tiles ...
-  P.o_ix2 = o; o += 2 * 32 * 4;       // ... and their SNPs
+  P.o_part_rhs = o;                   // (unused: the primary threads keep their sums)
+  P.o_part_corr = o; o += 8 * B;      // corrections owed to the next tile, from the threads that summed them
+  P.o_c2part = o; o += 3 * 8 * B;     // [3][B] partial sums of the correction towards t+2 (three subsets of the changes)
+  P.o_coldbuf = o; o += 2 * 8 * B;    // [2][B] sum of the far corrections (dt >= 3) of a tile, by tile parity (input warp)
+  P.o_coef = 0;                       // (the chain coefficients live in the package's M area: never both in use)
+  P.o_dl2 = o; o += 2 * 36 * 8;       // first kNear2 changes of the last two tiles ...
+  P.o_ix2 = o; o += 2 * 36 * 4;       // ... and their SNPs
   P.o_new_snp = o; o += 4 * B;
   P.o_rank = o; o += 4 * B;           // candidates before SNP i (repair rounds: the secondary threads read it)
-  P.o_g2land = o; o += 32 * 32 * 4;   // landing zone of the last primary warp's Gram entries towards t+2
+  P.o_stage = o; o += (kMaxDC - 2) * 8 * B;   // landing zone of a tile's far-correction slots (input warp)
   P.o_wcnt = o; o += 64 * 4;
   P.o_gctl = o; o += 16 * 4;          // [1] k, [2] row slots, [8+b] k of the tile of parity b
   P.o_pc = o; o += 18 * 8;
   P.o_full = o; o += 2 * 8;
   P.o_empty = o; o += 2 * 8;
+  P.o_farfull = o; o += 2 * 8;
+  P.o_stagefull = o; o += 8;
   P.bytes = (o + 127) & ~127u;
   return P;
 }
@@ -127,7 +132,7 @@ __shared__ SweepParams g_serial_ps;
 // What a thread knows about its SNP while a tile is being decided (primary threads; the secondary threads use k, ns
 // and the flags only).
 struct SerialTile {
-  double rhs0, lo, hi, gold, myiv, mysdz, c1next, my_delta, my_gnew;
+  double rhs0, rhs1, lo, hi, gold, myiv, mysdz, c1next, my_delta, my_gnew;   // rhs1: exact right-hand side of the first round
   int cls, cls2, myrank, slot, k, ns, nrounds;
   bool act, cand, chk_exact, generic, m_ok, dead, has1;
 };
@@ -142,6 +147,156 @@ struct SerialGeo {
   static constexpr int NTS = 2 * B - 32;    // threads of the chain (the last warp of the block is the loader)
   static constexpr uint32_t priv0 = 2 * L.stride;
 };
+
+// Exact right-hand sides and the corrections owed to the next tile, from the row slots in shared memory:
+//   primary thread i     sum over the changes before SNP i of G0[c][i] * delta_c        (returned)
+//   secondary thread i   sum over all changes of G1[c][i] * delta_c -> part_corr[i]     (i < B - 32)
+//   primary warp 0       the same for the last 32 SNPs, which have no secondary thread (its own sums are the shortest:
+//                        hardly any change precedes the first 32 SNPs of a tile)
+// Four partial sums per thread (changes e, e+4, ... each), added at the end: the dependent chain of fmas is a quarter of
+// the list.
+template <bool PRIM, int B>
+__device__ __forceinline__ double tile_sums(const int32_t* rows, const double* c_delta, const int* c_slot, int k, int myrank,
+                                            bool has1, int i, int warp, int lane, double* part_corr) {
+  constexpr int RS = 2 * B;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if constexpr (PRIM) {
+    const int kw = __shfl_sync(0xffffffffu, myrank, 31);   // changes before the warp's last SNP: nobody needs more
+    int e = 0;
+    for (; e + 3 < kw; e += 4) {
+      const double d0 = c_delta[e], d1 = c_delta[e + 1], d2 = c_delta[e + 2], d3 = c_delta[e + 3];
+      const int s0 = c_slot[e], s1 = c_slot[e + 1], s2 = c_slot[e + 2], s3 = c_slot[e + 3];
+      a0 = fma(e < myrank ? gram_as_double(rows[s0 * RS + i]) : 0.0, d0, a0);
+      a1 = fma(e + 1 < myrank ? gram_as_double(rows[s1 * RS + i]) : 0.0, d1, a1);
+      a2 = fma(e + 2 < myrank ? gram_as_double(rows[s2 * RS + i]) : 0.0, d2, a2);
+      a3 = fma(e + 3 < myrank ? gram_as_double(rows[s3 * RS + i]) : 0.0, d3, a3);
+    }
+    for (; e < kw; ++e) a0 = fma(e < myrank ? gram_as_double(rows[c_slot[e] * RS + i]) : 0.0, c_delta[e], a0);
+    const double prhs = (a0 + a1) + (a2 + a3);
+    if (warp == 0 && has1) {
+      const int i2 = B - 32 + lane;
+      double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+      int f = 0;
+      for (; f + 3 < k; f += 4) {
+        b0 = fma(gram_as_double(rows[c_slot[f] * RS + B + i2]), c_delta[f], b0);
+        b1 = fma(gram_as_double(rows[c_slot[f + 1] * RS + B + i2]), c_delta[f + 1], b1);
+        b2 = fma(gram_as_double(rows[c_slot[f + 2] * RS + B + i2]), c_delta[f + 2], b2);
+        b3 = fma(gram_as_double(rows[c_slot[f + 3] * RS + B + i2]), c_delta[f + 3], b3);
+      }
+      for (; f < k; ++f) b0 = fma(gram_as_double(rows[c_slot[f] * RS + B + i2]), c_delta[f], b0);
+      part_corr[i2] = (b0 + b1) + (b2 + b3);
+    } else if (warp == 0) {
+      part_corr[B - 32 + lane] = 0.0;
+    }
+    return prhs;
+  } else {
+    if (has1) {
+      int f = 0;
+#pragma unroll 1
+      for (; f + 3 < k; f += 4) {
+        a0 = fma(gram_as_double(rows[c_slot[f] * RS + B + i]), c_delta[f], a0);
+        a1 = fma(gram_as_double(rows[c_slot[f + 1] * RS + B + i]), c_delta[f + 1], a1);
+        a2 = fma(gram_as_double(rows[c_slot[f + 2] * RS + B + i]), c_delta[f + 2], a2);
+        a3 = fma(gram_as_double(rows[c_slot[f + 3] * RS + B + i]), c_delta[f + 3], a3);
+      }
+#pragma unroll 1
+      for (; f < k; ++f) a0 = fma(gram_as_double(rows[c_slot[f] * RS + B + i]), c_delta[f], a0);
+    }
+    part_corr[i] = (a0 + a1) + (a2 + a3);
+    return 0.0;
+  }
+}
+
+// The same for a package as the helper ships it: the candidates' rows are slots 0 .. k-1 in order, so the slots need not be
+// looked up, and the changes are read two at a time (half as many shared-memory instructions: the chain's threads all run
+// this at once and the load/store unit is what bounds it).
+template <bool PRIM, int B>
+__device__ __forceinline__ double tile_sums_seq(const int32_t* rows, const double* c_delta, int k, int myrank, bool has1, int i,
+                                                int warp, int lane, double* part_corr) {
+  constexpr int RS = 2 * B;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if constexpr (PRIM) {
+    const int kw = __shfl_sync(0xffffffffu, myrank, 31);   // changes before the warp's last SNP: nobody needs more
+    const int32_t* r0 = rows + i;
+    int e = 0;
+#pragma unroll 1
+    for (; e + 3 < kw; e += 4) {
+      const double2 da = *(const double2*)(c_delta + e), db = *(const double2*)(c_delta + e + 2);
+      const int g0 = r0[e * RS], g1 = r0[(e + 1) * RS], g2 = r0[(e + 2) * RS], g3 = r0[(e + 3) * RS];
+      a0 = fma(e < myrank ? gram_as_double(g0) : 0.0, da.x, a0);
+      a1 = fma(e + 1 < myrank ? gram_as_double(g1) : 0.0, da.y, a1);
+      a2 = fma(e + 2 < myrank ? gram_as_double(g2) : 0.0, db.x, a2);
+      a3 = fma(e + 3 < myrank ? gram_as_double(g3) : 0.0, db.y, a3);
+    }
+#pragma unroll 1
+    for (; e < kw; ++e) a0 = fma(e < myrank ? gram_as_double(r0[e * RS]) : 0.0, c_delta[e], a0);
+    const double prhs = (a0 + a1) + (a2 + a3);
+    if (warp == 0) {
+      double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+      if (has1) {
+        const int32_t* r1 = rows + B + (B - 32 + lane);
+        int f = 0;
+#pragma unroll 1
+  #pragma unroll 1
+      for (; f + 3 < k; f += 4) {
+          const double2 da = *(const double2*)(c_delta + f), db = *(const double2*)(c_delta + f + 2);
+          b0 = fma(gram_as_double(r1[f * RS]), da.x, b0);
+          b1 = fma(gram_as_double(r1[(f + 1) * RS]), da.y, b1);
+          b2 = fma(gram_as_double(r1[(f + 2) * RS]), db.x, b2);
+          b3 = fma(gram_as_double(r1[(f + 3) * RS]), db.y, b3);
+        }
+#pragma unroll 1
+        for (; f < k; ++f) b0 = fma(gram_as_double(r1[f * RS]), c_delta[f], b0);
+      }
+      part_corr[B - 32 + lane] = (b0 + b1) + (b2 + b3);
+    }
+    return prhs;
+  } else {
+    if (has1) {
+      const int32_t* r1 = rows + B + i;
+      int f = 0;
+#pragma unroll 1
+      for (; f + 3 < k; f += 4) {
+        const double2 da = *(const double2*)(c_delta + f), db = *(const double2*)(c_delta + f + 2);
+        a0 = fma(gram_as_double(r1[f * RS]), da.x, a0);
+        a1 = fma(gram_as_double(r1[(f + 1) * RS]), da.y, a1);
+        a2 = fma(gram_as_double(r1[(f + 2) * RS]), db.x, a2);
+        a3 = fma(gram_as_double(r1[(f + 3) * RS]), db.y, a3);
+      }
+#pragma unroll 1
+      for (; f < k; ++f) a0 = fma(gram_as_double(r1[f * RS]), c_delta[f], a0);
+    }
+    part_corr[i] = (a0 + a1) + (a2 + a3);
+    return 0.0;
+  }
+}
+
+// Candidates beyond the first 32 of a package (the solved chain matrix covers 32): one after the other, each from the
+// changes of all candidates before it -- lane l multiplies the changes of candidates l and l + 32 with their Gram entries
+// towards candidate s, a shuffle tree adds the products.  A rolled loop: a few dozen instructions that ~7 % of the
+// tiles run for a handful of candidates (the step-by-step chain of scalar_role unrolls to 2000 instructions, which
+// would push the chain's loop out of the instruction cache).
+template <int B>
+__device__ __forceinline__ void chain_tail(const int32_t* rows, const int* c_idx, const int* c_cls, const double* c_rhs0,
+                                           const double* c_iv, const double* c_sdz, const double* c_gold, double* c_delta,
+                                           double* c_gnew, int k, int lane) {
+  constexpr int RS = 2 * B;
+  for (int s = 32; s < k; ++s) {
+    const int col = c_idx[s];
+    double part = 0.0;
+    if (lane < s) part = gram_as_double(rows[lane * RS + col]) * c_delta[lane];
+    if (lane + 32 < s) part = fma(gram_as_double(rows[(lane + 32) * RS + col]), c_delta[lane + 32], part);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) {
+      const double gold = c_gold[s];
+      const double e = fma(c_rhs0[s] - part, c_iv[s], c_sdz[s]) - gold;
+      c_delta[s] = e;
+      c_gnew[s] = (c_cls[s] > 0) ? gold + e : 0.0;
+    }
+    __syncwarp();
+  }
+}
 
 // The rare paths of a tile, kept out of the chain's instruction stream and registers: a package without rows (more
 // candidates than a package holds: the classes are decided here, chain and sums straight from the Gram band), and the
@@ -168,7 +323,7 @@ __device__ __noinline__ void serial_slow(SerialTile& st, int t, bool from_start)
   uint8_t* priv = smem + G::priv0;
   double* part_rhs = (double*)(priv + P.o_part_rhs);
   double* part_corr = (double*)(priv + P.o_part_corr);
-  double* coef = (double*)(priv + P.o_coef);
+  double* coef = (double*)(pk + L.o_M);   // chain coefficients of the first 32 candidates: in the (then unused) M area
   int* new_snp = (int*)(priv + P.o_new_snp);
   int* rank_sh = (int*)(priv + P.o_rank);
   int* wcnt = (int*)(priv + P.o_wcnt);
@@ -298,8 +453,11 @@ __device__ __noinline__ void serial_slow(SerialTile& st, int t, bool from_start)
     }
     compact_generic();
   } else {
-    // a class differed from its speculation in the first round
-    if (prim && st.cls2 != st.cls) { st.cls = st.cls2; load_draw(); }
+    // a class may differ from its speculation after the first round: every class from the round's exact right-hand side
+    if (prim && st.act) {
+      st.cls2 = classify_full(st.rhs1);
+      if (st.cls2 != st.cls) { st.cls = st.cls2; load_draw(); }
+    }
     if (!generic) compact_rows();
     if (generic) { hb::named_bar_sync(1, NTS); compact_generic(); }
   }
@@ -307,40 +465,21 @@ __device__ __noinline__ void serial_slow(SerialTile& st, int t, bool from_start)
     ++st.nrounds;
     if (st.cand && prim) cs.rhs0[st.myrank] = st.rhs0;
     hb::named_bar_sync(1, NTS);
-    double prhs = 0.0, pcorr = 0.0, prhs2 = 0.0, pcorr2 = 0.0;
+    double prhs = 0.0;
     if (!generic) {
       if (tid < 32 && k > 0) chain_candidates<true>(cs, k, G0, rows, B, lane, coef, RS);
       hb::named_bar_sync(1, NTS);
-#pragma unroll 4
-      for (int sidx = h; sidx < k; sidx += 2) {
-        const double d = cs.delta[sidx];
-        const int sl = cs.slot[sidx];
-        const double g0 = gram_as_double(rows[(size_t)sl * RS + i]), g1 = gram_as_double(rows[(size_t)sl * RS + B + i]);
-        prhs = fma(sidx < st.myrank ? g0 : 0.0, d, prhs);
-        pcorr = fma(has1 ? g1 : 0.0, d, pcorr);
-      }
-      if (tailw) {
-#pragma unroll 4
-        for (int sidx = 1; sidx < k; sidx += 2) {
-          const double d = cs.delta[sidx];
-          const int sl = cs.slot[sidx];
-          const double g0 = gram_as_double(rows[(size_t)sl * RS + i]), g1 = gram_as_double(rows[(size_t)sl * RS + B + i]);
-          prhs2 = fma(sidx < st.myrank ? g0 : 0.0, d, prhs2);
-          pcorr2 = fma(has1 ? g1 : 0.0, d, pcorr2);
-        }
-      }
+      prhs = tile_sums<PRIM, B>(rows, cs.delta, cs.slot, k, st.myrank, has1, i, warp, lane, part_corr);
     } else {
       const double sv = slow_chain_and_sums_cs(cs, k, st.myrank, G0, B, i, h, has1, false, model, NTS);
-      if (prim) prhs = sv; else pcorr = sv;
-      if (tailw) pcorr2 = has1 ? band_correction(cs, k, G0 + (size_t)B * B, B, i) : 0.0;
+      if (prim) prhs = sv; else part_corr[i] = sv;
+      if (tailw) part_corr[i] = has1 ? band_correction(cs, k, G0 + (size_t)B * B, B, i) : 0.0;
     }
-    if (!prim) { part_rhs[i] = prhs; part_corr[i] = pcorr; }
     hb::named_bar_sync(1, NTS);
     int cls2 = st.cls;
     if (prim) {
-      double rhs;
-      if (tailw) { rhs = st.rhs0 - (prhs + prhs2); st.c1next = pcorr + pcorr2; }
-      else { rhs = st.rhs0 - (prhs + part_rhs[i]); st.c1next = pcorr + part_corr[i]; }
+      const double rhs = st.rhs0 - prhs;
+      st.c1next = part_corr[i];
       if (st.act) cls2 = classify_full(rhs);
     }
     const bool bad = prim && st.act && (cls2 != st.cls);
@@ -352,18 +491,146 @@ __device__ __noinline__ void serial_slow(SerialTile& st, int t, bool from_start)
   }
   // the tile is final: this thread's change, and the first 32 changes for the correction towards t+2
   if (prim && st.cand) { st.my_delta = cs.delta[st.myrank]; st.my_gnew = cs.gnew[st.myrank]; }
-  if (tid < 32) {
-    ((double*)(priv + P.o_dl2))[(t & 1) * 32 + tid] = (tid < k) ? cs.delta[tid] : 0.0;
-    ((int*)(priv + P.o_ix2))[(t & 1) * 32 + tid] = (tid < k) ? cs.idx[tid] : 0;
+  if (tid < 36) {
+    ((double*)(priv + P.o_dl2))[(t & 1) * 36 + tid] = (tid < k) ? cs.delta[tid] : 0.0;
+    ((int*)(priv + P.o_ix2))[(t & 1) * 36 + tid] = (tid < k) ? cs.idx[tid] : 0;
   }
   st.k = k; st.ns = ns; st.generic = generic;
 }
 
-// The primary threads (one per SNP: inputs, classes, verification) and the secondary threads (odd candidates of the
-// sums, Gram entries towards t+2 in registers) run the same sequence of barriers from two instantiations of this
-// function, so that neither carries the other's registers.
+// Bounded wait on an mbarrier without a function call: a call inside the chain's loop would make the compiler park the
+// registers that live across it (the Gram words towards t+2, ...) in local memory, and with 225 KB of shared memory in use
+// local memory is an L2 round trip.
+__device__ __forceinline__ bool mbar_wait_nocall(uint64_t* bar, uint32_t parity, int* ctrl, int code) {
+  if (hb::mbar_try_wait(bar, parity)) return true;
+  unsigned spins = 0;
+  unsigned long long t0 = 0;
+  while (!hb::mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3f) == 0) {
+      if (*((volatile int*)(ctrl + 1)) != 0) return false;
+      const unsigned long long now = gtimer();
+      if (t0 == 0) t0 = now;
+      else if ((long long)(now - t0) > kTimeoutNs) { atomicCAS(ctrl + 1, 0, code); return false; }
+    }
+  }
+  return true;
+}
+
+// What a chain thread carries from tile to tile.
+constexpr int kNGA = 6, kNGB = 5;   // Gram words towards t+2 per thread: batch A (changes 0..17 of a tile), batch B (18..32)
+static_assert(3 * (kNGA + kNGB) == kNear2, "batches cover the near list");
+struct SerialCarry {
+  int t;              // next tile
+  bool dead;
+  double corr1;       // correction owed by the previous tile to this thread's SNP (never leaves the thread)
+  double corr2;       // correction owed by the tile before that (summed from c2part at the end of the previous tile)
+  int4 gA[kNGA], gB[kNGB];   // (secondary warps 0..5) Gram words towards t+2 on their way
+};
+
+// End of a tile, once it is final: effects, classes and the tile's changes for the AXPY warps and the helpers; the
+// correction towards t+2 (batch B of the previous tile's list summed, batch A of this tile's list asked for); the package
+// buffer handed back to the input warp.
+template <bool PRIM, int B>
+__device__ __forceinline__ void serial_tile_end(int t, int k, int nrounds, bool cand, bool act, int myrank, int cls, double my_delta,
+                                                double my_gnew, double& corr2, int4 (&gA)[kNGA], int4 (&gB)[kNGB], bool timing) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using G = SerialGeo<B>;
+  constexpr PrivLayout P = G::P;
+  constexpr int NTS = G::NTS;
+  constexpr int h = PRIM ? 0 : 1;
+  const SweepParams& p = g_serial_ps;
+  const int D = p.D, T = p.T;
+  const int tid = threadIdx.x, i = tid - h * B, warp = i >> 5, lane = i & 31;
+  const int b = t & 1, j = t * B + i;
+  const int abl = p.dbg;
+  uint8_t* priv = smem + G::priv0;
+  double* c2part = (double*)(priv + P.o_c2part);
+  const double* dl2 = (const double*)(priv + P.o_dl2);
+  const int* ix2 = (const int*)(priv + P.o_ix2);
+  volatile int* gctl = (volatile int*)(priv + P.o_gctl);
+  long long* pc = (long long*)(priv + P.o_pc);
+  uint64_t* empty = (uint64_t*)(priv + P.o_empty);
+  const bool g2on = !PRIM && warp < 6;
+  const int g2s = warp >> 1, g2j = (warp & 1) * 32 + lane;
+#define HB_SPHASE(n) do { if (timing) { const long long _now = clock64(); pc[n] += _now - pc[16]; pc[16] = _now; } } while (0)
+  if (tid == 0) {
+    gctl[10] += nrounds; gctl[11] += k;
+    if (nrounds > 1) { gctl[12]++; st_relaxed_s32(p.miss_tile, t); }
+  }
+  HB_SPHASE(5);
+  if (tid == 0) HB_TRACE(t, 3);
+  if constexpr (PRIM) {
+    if (cand) {
+      st_relaxed_u64(p.q_delta + (size_t)t * B + myrank, (unsigned long long)__double_as_longlong(my_delta));
+      st_relaxed_s32(p.q_snp + (size_t)t * B + myrank, j);
+      p.g[j] = my_gnew;
+    }
+    if (i == 0) { st_relaxed_s32(p.tile_cnt + t, k); HB_TRACE(t, 4); gctl[8 + b] = k; }
+    if (act) p.tracker[j] = cls;
+  }
+  HB_SPHASE(6);
+  const bool c2on = t >= 1 && t + 1 < T && D > 2 && !(abl & 256);
+  if constexpr (!PRIM) {
+    if (g2on && c2on && gctl[8 + (b ^ 1)] > 3 * kNGA) {
+      // batch B of tile t-1's list: added to the partial sums of batch A (same thread, same entries)
+      const int kp = min(gctl[8 + (b ^ 1)], kNear2);
+      const double* dprev = dl2 + (b ^ 1) * 36;
+      double* cp = c2part + g2s * B + 4 * g2j;
+      double a0 = cp[0], a1 = cp[1], a2 = cp[2], a3 = cp[3];
+#pragma unroll
+      for (int r = 0; r < kNGB; ++r) {
+        const int e = 3 * kNGA + g2s + 3 * r;
+        if (e < kp) {
+          const double d = dprev[e];
+          a0 = fma(gram_as_double(gB[r].x), d, a0); a1 = fma(gram_as_double(gB[r].y), d, a1);
+          a2 = fma(gram_as_double(gB[r].z), d, a2); a3 = fma(gram_as_double(gB[r].w), d, a3);
+        }
+      }
+      cp[0] = a0; cp[1] = a1; cp[2] = a2; cp[3] = a3;
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's accesses to the package buffer before its refill
+  hb::named_bar_sync(1, NTS);   // dl2 / ix2 / gctl[8+b] of this tile and the partial sums towards t+1 are visible
+  if constexpr (PRIM) {
+    if (c2on) {
+      corr2 = (c2part[i] + c2part[B + i]) + c2part[2 * B + i];
+      const int kp = gctl[8 + (b ^ 1)];
+      if (kp > kNear2) {
+        // rare: the rest of the list from the published queue of tile t-1
+        const int32_t* gb = p.gram + ((size_t)(t - 1) * D + 2) * B * B;
+        for (int e = kNear2; e < kp; ++e) {
+          const int sn = hb::ld_relaxed(p.q_snp + (size_t)(t - 1) * B + e) - (t - 1) * B;
+          const double d = __longlong_as_double((long long)ld_relaxed_u64(p.q_delta + (size_t)(t - 1) * B + e));
+          corr2 = fma(gram_as_double(__ldcg(gb + (size_t)sn * B + i)), d, corr2);
+        }
+      }
+    } else {
+      corr2 = 0.0;
+    }
+  } else {
+    // (every path assigns the words: a conditional assignment would keep the old values alive around the whole loop
+    // body and the compiler would park them in local memory)
+    const bool on = g2on && t + 2 < T && D > 2 && !(abl & 256);
+    const int32_t* gb = p.gram + ((size_t)t * D + 2) * B * B + 4 * g2j;
+    const int* ixp = ix2 + b * 36;
+    const int kk = on ? min(k, kNear2) : 0;
+#pragma unroll
+    for (int r = 0; r < kNGA; ++r) {
+      const int e = g2s + 3 * r;
+      gA[r] = (e < kk) ? __ldcg((const int4*)(gb + (size_t)ixp[e] * B)) : make_int4(0, 0, 0, 0);
+    }
+  }
+  if (tid == 0) { hb::mbar_arrive(empty + b); HB_TRACE(t, 5); }
+  HB_SPHASE(7);
+#undef HB_SPHASE
+}
+
+// The chain itself: tiles from c.t on, back to back, until the last tile or until a tile needs one of the rare paths
+// (returns 1 with the tile's state in st; the caller runs serial_slow and serial_tile_end for it and comes back).  No
+// function is called from here: a call inside the loop makes the compiler park whatever lives across it in local memory,
+// and with 225 KB of shared memory in use local memory is an L2 round trip.
 template <int NF, bool PRIM, int B>
-__device__ __noinline__ void serial_threads() {
+__device__ __noinline__ int serial_fast(SerialCarry& c, SerialTile& st) {
   extern __shared__ __align__(128) uint8_t smem[];
   using G = SerialGeo<B>;
   constexpr PkgLayout L = G::L;
@@ -371,276 +638,341 @@ __device__ __noinline__ void serial_threads() {
   constexpr int RS = G::RS, NTS = G::NTS;
   constexpr bool prim = PRIM;
   constexpr int h = PRIM ? 0 : 1;
-  constexpr int nwarp = B / 32;
   const SweepParams& p = g_serial_ps;
   const int D = p.D, T = p.T;
   const int tid = threadIdx.x;
   const int i = tid - h * B, warp = i >> 5, lane = i & 31;
-  const bool tailw = prim && warp == nwarp - 1;   // primary threads without a secondary partner
+  // secondary warps 0..5 carry the correction towards t+2: subset g2s of the tile's changes (e = g2s, g2s+3, ...), four
+  // SNPs 4*g2j .. 4*g2j+3 of the tile after next per thread (16-byte loads of the Gram rows)
+  const bool g2on = !prim && warp < 6;
+  const int g2s = warp >> 1, g2j = (warp & 1) * 32 + lane;
   int* ctrl = p.ctrl;
   uint8_t* priv = smem + G::priv0;
-  double* part_rhs = (double*)(priv + P.o_part_rhs);
   double* part_corr = (double*)(priv + P.o_part_corr);
-  double* c2buf = (double*)(priv + P.o_c2buf);
-  double* coef = (double*)(priv + P.o_coef);
+  const double* coldbuf = (const double*)(priv + P.o_coldbuf);
+  double* c2part = (double*)(priv + P.o_c2part);
   double* dl2 = (double*)(priv + P.o_dl2);
   int* ix2 = (int*)(priv + P.o_ix2);
-  int32_t* g2land = (int32_t*)(priv + P.o_g2land);
   volatile int* gctl = (volatile int*)(priv + P.o_gctl);
   long long* pc = (long long*)(priv + P.o_pc);
   uint64_t* full = (uint64_t*)(priv + P.o_full);
-  uint64_t* empty = (uint64_t*)(priv + P.o_empty);
+  uint64_t* farfull = (uint64_t*)(priv + P.o_farfull);
 
   const int DC = D - 1;
-  bool dead = false;
-  int rounds_total = 0, changed_total = 0, repaired = 0, generic_tiles = 0;
-  double corr1 = 0.0;               // correction owed by the previous tile to this thread's SNP (never leaves the thread)
-  unsigned long long cwn[PRIM ? kMaxDC : 1];   // far corrections of the next tile, asked for one tile ahead
-  int g2[PRIM ? 1 : 32];            // Gram entries towards the tile after next (secondary threads), asked for one tile ahead
+  bool dead = c.dead;
+  double corr1 = c.corr1, corr2 = c.corr2;
+  int4 gA[kNGA], gB[kNGB];
 #pragma unroll
-  for (int q = 0; q < (PRIM ? kMaxDC : 1); ++q) cwn[q] = kCorrEmpty;
+  for (int e = 0; e < kNGA; ++e) gA[e] = c.gA[e];
 #pragma unroll
-  for (int e = 0; e < (PRIM ? 1 : 32); ++e) g2[e] = 0;
+  for (int e = 0; e < kNGB; ++e) gB[e] = c.gB[e];
 
   const bool timing = PRIM && tid == 0 && (p.dbg & 64);
 #define HB_SPHASE(n) do { if (timing) { const long long _now = clock64(); pc[n] += _now - pc[16]; pc[16] = _now; } } while (0)
-  const int abl = p.dbg;   // timing experiments (results are wrong with them): 256 no t+2 correction, 512 no far corrections, 1024 no effect/class stores
-  for (int t = 0; t < T; ++t) {
+  const int abl = p.dbg;   // timing experiments (results are wrong with them): 256 no t+2 correction, 512 no far corrections
+  int ret = 0;
+  int t = c.t;
+  for (; t < T; ++t) {
     const int b = t & 1;
     const int j = t * B + i;
     uint8_t* pk = smem + (size_t)b * L.stride;
-    if (!mbar_wait(full + b, (uint32_t)((t >> 1) & 1), ctrl, HB_ABORT_TIMEOUT_SCALAR)) dead = true;
+    {
+      const uint32_t par = (uint32_t)((t >> 1) & 1);
+      if (!mbar_wait_nocall(full + b, par, ctrl, HB_ABORT_TIMEOUT_SCALAR)) dead = true;
+      if (tid == 0) HB_TRACE(t, 15);
+      if (PRIM && !dead && !mbar_wait_nocall(farfull + b, par, ctrl, HB_ABORT_TIMEOUT_SCALAR)) dead = true;
+    }
     HB_SPHASE(0);
     if (tid == 0) HB_TRACE(t, 2);
     const int* hdr = (const int*)(pk + L.o_hdr);
-    // (plain locals: everything the chain touches stays in registers; a SerialTile is filled only for the rare paths)
-    int k = dead ? 0 : hdr[PK_K];
+    const int k = dead ? 0 : hdr[PK_K];
     const int ns0 = dead ? 0 : hdr[PK_NS];
     const bool fast = !dead && hdr[PK_FAST] != 0;
     const bool m_ok = !dead && hdr[PK_MOK] != 0;
     const bool has1 = (D > 1 && t + 1 < T);
-    double rhs0 = 0.0, lo = -1.0, hi = HUGE_VAL, gold = 0.0, myiv = 0.0, mysdz = 0.0, c1next = 0.0, my_delta = 0.0, my_gnew = 0.0;
-    int cls = 0, cls2 = 0, myrank = 0, slot = -1, nrounds = 0;
+    double rhs0 = 0.0, rhs1 = 0.0, c1next = 0.0;
+    int cls = 0, myrank = 0;
     bool act = false, cand = false, chk_exact = false;
     double* c_rhs0 = (double*)(pk + L.o_rhs0);
     double* c_delta = (double*)(pk + L.o_delta);
     const int* c_slot = (const int*)(pk + L.o_slot);
     const int32_t* rows = (const int32_t*)(pk + L.o_rows);
+    double* coef = (double*)(pk + L.o_M);   // chain coefficients of the first 32 candidates: in the (then unused) M area
 
     // ---- this SNP's inputs
-    if constexpr (PRIM) if (!dead) {
-      const double base0 = ((const double*)(pk + L.o_base0))[i];
-      const double addback = ((const double*)(pk + L.o_addback))[i];
-      lo = ((const double*)(pk + L.o_lo))[i];
-      hi = ((const double*)(pk + L.o_hi))[i];
+    if (!dead) {
       const int info = ((const int*)(pk + L.o_info))[i];
-      slot = ((const int*)(pk + L.o_slotof))[i];
-      cls = info & 15; cand = (info >> 4) & 1; act = (info >> 5) & 1; chk_exact = (info >> 6) & 1;
-      myrank = info >> 8;
-      if (cand && fast) {
-        gold = ((const double*)(pk + L.o_gold))[myrank];
-        myiv = ((const double*)(pk + L.o_iv))[myrank];
-        mysdz = ((const double*)(pk + L.o_sdz))[myrank];
+      myrank = info >> 8;   // candidates before SNP i
+      if constexpr (PRIM) {
+        const double base = ((const double*)(pk + L.o_base0))[i];
+        cls = info & 15; cand = (info >> 4) & 1; act = (info >> 5) & 1; chk_exact = (info >> 6) & 1;
+        const int dmax = min(DC, t);
+        double cold = 0.0;
+        if (dmax >= 3 && !(abl & 512)) cold = coldbuf[b * B + i];   // far corrections, summed oldest first by the input warp
+        if (dmax >= 2 && !(abl & 256)) cold += corr2;
+        const double c1 = (dmax >= 1) ? corr1 : 0.0;
+        rhs0 = (base - cold) - c1;
       }
-      const int dmax = min(DC, t);
-      double cold = 0.0;
-#pragma unroll
-      for (int q = kMaxDC - 1; q >= 2; --q)
-        if (q + 1 <= dmax && !(abl & 512)) {
-          double v = __longlong_as_double((long long)cwn[q]);
-          if (cwn[q] == kCorrEmpty) {
-            if (!poll_corr_slow(p.corr + ((size_t)t * DC + q) * B + i, v, ctrl)) { dead = true; v = 0.0; }
-          }
-          cold += v;
-        }
-      if (dmax >= 2 && !(abl & 256)) cold += c2buf[b * B + i];
-      const double c1 = (dmax >= 1) ? corr1 : 0.0;
-      rhs0 = ((base0 - cold) - c1) + addback;
     }
-    if constexpr (!PRIM) if (!dead) myrank = ((const int*)(pk + L.o_info))[i] >> 8;   // candidates before SNP i
     HB_SPHASE(1);
 
     if (fast) {
-      if (!m_ok && k > 0) {
-        // more than 32 candidates: no solved chain matrix in the package; the coefficients of the first 32 for the
-        // step-by-step chain
-        const int* c_idx = (const int*)(pk + L.o_idx);
-        const double* c_iv = (const double*)(pk + L.o_iv);
-        for (int e = tid; e < 32 * 32; e += NTS) {
-          const int lp = e >> 5, sc = e & 31;
-          double v = 0.0;
-          if (lp < sc && sc < min(k, 32)) v = gram_as_double(rows[(size_t)c_slot[lp] * RS + c_idx[sc]]) * (-c_iv[sc]);
-          coef[e] = v;
-        }
-      }
-      if (prim && cand && !dead) c_rhs0[myrank] = rhs0;
+      if (prim && cand) c_rhs0[myrank] = rhs0;
     }
     if (hb::named_bar_or(1, NTS, dead)) { dead = true; break; }
+    // ---- (secondary warps, while the chain warp works) correction owed by tile t-1 to tile t+1: batch A of the Gram words
+    // was asked for at the end of the previous tile; partial sums of the three subsets (each in ascending order of the
+    // changes), added up by the receiving SNP's thread at the end of this tile; then batch B of the same list is asked for
+    if constexpr (!PRIM) {
+      const bool on = g2on && t >= 1 && t + 1 < T && D > 2 && !(abl & 256);
+      if (!on) {
+#pragma unroll
+        for (int r = 0; r < kNGB; ++r) gB[r] = make_int4(0, 0, 0, 0);
+      } else {
+        const int kp = min(gctl[8 + (b ^ 1)], kNear2);
+        const double* dprev = dl2 + (b ^ 1) * 36;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int r = 0; r < kNGA; ++r) {
+          const int e = g2s + 3 * r;
+          if (e < kp) {
+            const double d = dprev[e];
+            a0 = fma(gram_as_double(gA[r].x), d, a0); a1 = fma(gram_as_double(gA[r].y), d, a1);
+            a2 = fma(gram_as_double(gA[r].z), d, a2); a3 = fma(gram_as_double(gA[r].w), d, a3);
+          }
+        }
+        double* cp = c2part + g2s * B + 4 * g2j;
+        cp[0] = a0; cp[1] = a1; cp[2] = a2; cp[3] = a3;
+        const int32_t* gb = p.gram + ((size_t)(t - 1) * D + 2) * B * B + 4 * g2j;
+        const int* ixp = ix2 + (b ^ 1) * 36;
+#pragma unroll
+        for (int r = 0; r < kNGB; ++r) {
+          const int e = 3 * kNGA + g2s + 3 * r;
+          gB[r] = (e < kp) ? __ldcg((const int4*)(gb + (size_t)ixp[e] * B)) : make_int4(0, 0, 0, 0);
+        }
+      }
+    }
     bool slow = !fast;
     if (fast) {
       // ---- first round: the speculated candidate list
-      nrounds = 1;
       HB_SPHASE(3);
       if (tid < 32 && k > 0) {
         CandSet cs;
         cs.rhs0 = c_rhs0; cs.iv = (double*)(pk + L.o_iv); cs.sdz = (double*)(pk + L.o_sdz);
         cs.gold = (double*)(pk + L.o_gold); cs.delta = c_delta; cs.gnew = (double*)(pk + L.o_gnew);
         cs.idx = (int*)(pk + L.o_idx); cs.cls = (int*)(pk + L.o_cls); cs.slot = (int*)(pk + L.o_slot);
-        if (m_ok) chain_matvec(cs, k, (const double*)(pk + L.o_M), lane);
-        else chain_candidates<true>(cs, k, nullptr, rows, B, lane, coef, RS);
+        chain_matvec(cs, min(k, 32), (const double*)(pk + L.o_M), lane);   // (the package always has the matrix of the first 32)
+        if (k > 32) chain_tail<B>(rows, cs.idx, cs.cls, c_rhs0, cs.iv, cs.sdz, cs.gold, c_delta, cs.gnew, k, lane);
+        if (abl & 2048) chain_matvec(cs, min(k, 32), (const double*)(pk + L.o_M), lane);   // (timing: the chain twice, same result)
       }
       HB_SPHASE(4);
       hb::named_bar_sync(1, NTS);
       HB_SPHASE(8);
-      // exact right-hand side of every SNP, and the corrections owed to the next tile: the primary thread takes the
-      // even candidates, the secondary the odd ones (the last primary warp has no partner and takes both)
-      double prhs = 0.0, pcorr = 0.0, prhs2 = 0.0, pcorr2 = 0.0;
-#pragma unroll 4
-      for (int sidx = h; sidx < k; sidx += 2) {
-        const double d = c_delta[sidx];
-        const int sl = c_slot[sidx];
-        const double g0 = gram_as_double(rows[sl * RS + i]), g1 = gram_as_double(rows[sl * RS + B + i]);
-        prhs = fma(sidx < myrank ? g0 : 0.0, d, prhs);
-        pcorr = fma(has1 ? g1 : 0.0, d, pcorr);
-      }
-      if (tailw) {
-#pragma unroll 4
-        for (int sidx = 1; sidx < k; sidx += 2) {
-          const double d = c_delta[sidx];
-          const int sl = c_slot[sidx];
-          const double g0 = gram_as_double(rows[sl * RS + i]), g1 = gram_as_double(rows[sl * RS + B + i]);
-          prhs2 = fma(sidx < myrank ? g0 : 0.0, d, prhs2);
-          pcorr2 = fma(has1 ? g1 : 0.0, d, pcorr2);
-        }
-      }
-      if (!prim) { part_rhs[i] = prhs; part_corr[i] = pcorr; }
+      // exact right-hand side of every SNP, and the corrections owed to the next tile
+      double prhs = tile_sums_seq<PRIM, B>(rows, c_delta, k, myrank, has1, i, warp, lane, part_corr);
+      if (abl & 4096) prhs = tile_sums_seq<PRIM, B>(rows, c_delta, k, myrank, has1, i, warp, lane, part_corr);   // (timing: twice)
       HB_SPHASE(9);
       hb::named_bar_sync(1, NTS);
       HB_SPHASE(10);
-      cls2 = cls;
+      bool bad = false;
       if constexpr (PRIM) {
-        double rhs;
-        if (tailw) { rhs = rhs0 - (prhs + prhs2); c1next = pcorr + pcorr2; }
-        else { rhs = rhs0 - (prhs + part_rhs[i]); c1next = pcorr + part_corr[i]; }
+        rhs1 = rhs0 - prhs;
+        c1next = part_corr[i];
         if (act) {
-          const double rr = rhs * rhs;
-          if (chk_exact || !(rr >= lo && rr <= hi)) {
-            // outside the interval of the speculated class (or no certified interval): the class itself
-            const int nf = (p.model == HB_MODEL_R) ? p.F : 2;
-            double TL[NF - 1], TH[NF - 1];
-#pragma unroll
-            for (int q = 0; q < NF - 1; ++q) {
-              TL[q] = -1.0; TH[q] = -1.0;
-              if (q < nf - 1) {
-                TL[q] = __ldcg(p.prm + prm_idx(kThrField0 + 2 * q, p.m_pad, j));
-                TH[q] = __ldcg(p.prm + prm_idx(kThrField0 + 2 * q + 1, p.m_pad, j));
-              }
-            }
-            int c0 = thr_class<NF>(nf, rr, TL, TH);
-            if (c0 < 0) c0 = classify_exact<NF>(p.prm, p.m_pad, j, nf, rr, p.logpi0);
-            cls2 = c0;
-          }
+          // the class holds as long as rhs^2 stays inside the interval of the speculated class; outside it (or without a
+          // certified interval) the classes are re-decided in serial_slow
+          const double rr = rhs1 * rhs1;
+          const double lo = (double)((const float*)(pk + L.o_lo))[i], hi = (double)((const float*)(pk + L.o_hi))[i];
+          bad = chk_exact || !(rr >= lo && rr <= hi);
         }
       }
-      const bool bad = prim && act && (cls2 != cls);
       HB_SPHASE(11);
       slow = hb::named_bar_or(1, NTS, bad);
       HB_SPHASE(12);
-      if (!slow) {
-        if (prim && cand) { my_delta = c_delta[myrank]; my_gnew = ((const double*)(pk + L.o_gnew))[myrank]; }
-        if (tid < 32) {
-          dl2[b * 32 + tid] = (tid < k) ? c_delta[tid] : 0.0;
-          ix2[b * 32 + tid] = (tid < k) ? ((const int*)(pk + L.o_idx))[tid] : 0;
-        }
-      }
     }
     if (slow) {
-      // the rare paths (no rows in the package / a class differed): out of line, with their own registers
-      if (!fast) ++generic_tiles;
-      SerialTile st;
-      st.rhs0 = rhs0; st.lo = lo; st.hi = hi; st.gold = gold; st.myiv = myiv; st.mysdz = mysdz; st.c1next = c1next;
-      st.my_delta = 0.0; st.my_gnew = 0.0;
-      st.cls = cls; st.cls2 = cls2; st.myrank = myrank; st.slot = slot; st.k = k; st.ns = ns0; st.nrounds = nrounds;
-      st.act = act; st.cand = cand; st.chk_exact = chk_exact; st.generic = !fast; st.m_ok = m_ok; st.dead = false; st.has1 = has1;
-      serial_slow<NF, PRIM, B>(st, t, !fast);
-      c1next = st.c1next; my_delta = st.my_delta; my_gnew = st.my_gnew;
-      cls = st.cls; myrank = st.myrank; k = st.k; nrounds = st.nrounds; cand = st.cand;
-    }
-    corr1 = c1next;
-    rounds_total += nrounds;
-    changed_total += k;
-    if (nrounds > 1) { ++repaired; if (tid == 0) st_relaxed_s32(p.miss_tile, t); }
-    HB_SPHASE(5);
-    if (tid == 0) HB_TRACE(t, 3);
-    // ---- the tile is final: effects, classes, and the tile's changes for the AXPY warps and the helpers
-    if constexpr (PRIM) {
-      if (cand) {
-        st_relaxed_u64(p.q_delta + (size_t)t * B + myrank, (unsigned long long)__double_as_longlong(my_delta));
-        st_relaxed_s32(p.q_snp + (size_t)t * B + myrank, j);
-        if (!(abl & 1024)) p.g[j] = my_gnew;
-      }
-      if (i == 0) { st_relaxed_s32(p.tile_cnt + t, k); HB_TRACE(t, 4); gctl[8 + b] = k; }
-      if (act && !(abl & 1024)) p.tracker[j] = cls;
-    }
-    HB_SPHASE(6);
-    // ---- correction owed by tile t-1 to tile t+1: the Gram entries were asked for one tile ago
-    if ((!prim || tailw) && t >= 1 && t + 1 < T && D > 2 && !(abl & 256)) {
-      const int kp = gctl[8 + (b ^ 1)];
-      const double* dprev = dl2 + (b ^ 1) * 32;
-      double c = 0.0;
-      if constexpr (PRIM) {
-        // (last primary warp: its entries landed in shared memory)
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        for (int e = 0; e < min(kp, 32); ++e) c = fma(gram_as_double(g2land[e * 32 + lane]), dprev[e], c);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (e < kp) c = fma(gram_as_double(g2[e]), dprev[e], c);
-      }
-      if (kp > 32) {
-        // rare: the rest of the list from the published queue of tile t-1 (same order as band_correction_raw)
-        const int32_t* gb = p.gram + ((size_t)(t - 1) * D + 2) * B * B;
-        for (int e = 32; e < kp; ++e) {
-          const int sn = hb::ld_relaxed(p.q_snp + (size_t)(t - 1) * B + e) - (t - 1) * B;
-          const double d = __longlong_as_double((long long)ld_relaxed_u64(p.q_delta + (size_t)(t - 1) * B + e));
-          c = fma(gram_as_double(__ldcg(gb + (size_t)sn * B + i)), d, c);
+      // the rare paths (no rows in the package / a class may differ): out of line, from the caller
+      st.rhs0 = rhs0; st.rhs1 = rhs1; st.lo = 0.0; st.hi = 0.0; st.gold = 0.0; st.myiv = 0.0; st.mysdz = 0.0; st.c1next = c1next;
+      st.slot = -1;
+      if (PRIM && !dead) {
+        // (what the chain did not need: read from the package only now)
+        st.slot = ((const int*)(pk + L.o_slotof))[i];
+        if (cand && fast) {
+          st.gold = ((const double*)(pk + L.o_gold))[myrank];
+          st.myiv = ((const double*)(pk + L.o_iv))[myrank];
+          st.mysdz = ((const double*)(pk + L.o_sdz))[myrank];
         }
       }
-      c2buf[(b ^ 1) * B + i] = c;
+      st.my_delta = 0.0; st.my_gnew = 0.0;
+      st.cls = cls; st.cls2 = -1; st.myrank = myrank; st.k = k; st.ns = ns0; st.nrounds = fast ? 1 : 0;
+      st.act = act; st.cand = cand; st.chk_exact = chk_exact; st.generic = !fast; st.m_ok = m_ok; st.dead = false; st.has1 = has1;
+      ret = 1;
+      break;
     }
-    hb::named_bar_sync(1, NTS);   // dl2 / ix2 / gctl[8+b] of this tile are visible; c2buf for t+1 is complete
-    if ((!prim || tailw) && t + 2 < T && D > 2 && !(abl & 256)) {
-      const int32_t* gb = p.gram + ((size_t)t * D + 2) * B * B;
-      const int* ixp = ix2 + b * 32;
-      const int kk = min(k, 32);
-      if constexpr (PRIM) {
-        for (int e = 0; e < kk; ++e)
-          cp_async4((uint32_t)__cvta_generic_to_shared(g2land + e * 32 + lane), gb + (size_t)ixp[e] * B + i);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) g2[e] = (e < kk) ? __ldcg(gb + (size_t)ixp[e] * B + i) : 0;
-      }
+    double my_delta = 0.0, my_gnew = 0.0;
+    if (prim && cand) { my_delta = c_delta[myrank]; my_gnew = ((const double*)(pk + L.o_gnew))[myrank]; }
+    if (tid < 36) {
+      dl2[b * 36 + tid] = (tid < k) ? c_delta[tid] : 0.0;
+      ix2[b * 36 + tid] = (tid < k) ? ((const int*)(pk + L.o_idx))[tid] : 0;
     }
-    // far corrections of the next tile (posted by the helpers): asked for now, looked at when the tile starts
-    if constexpr (PRIM) if (t + 1 < T && !(abl & 512)) {
-      const int dmax1 = min(DC, t + 1);
-#pragma unroll
-      for (int q = 2; q < kMaxDC; ++q)
-        cwn[q] = (q + 1 <= dmax1) ? ld_relaxed_u64(p.corr + ((size_t)(t + 1) * DC + q) * B + i) : kCorrEmpty;
-    }
-    if (tid == 0) { hb::mbar_arrive(empty + b); HB_TRACE(t, 5); }
-    HB_SPHASE(7);
+    corr1 = c1next;
+    serial_tile_end<PRIM, B>(t, k, 1, cand, act, myrank, cls, my_delta, my_gnew, corr2, gA, gB, timing);
   }
 #undef HB_SPHASE
-  if (dead) atomicCAS(ctrl + 1, 0, HB_ABORT_TIMEOUT_SCALAR);
+  c.t = t; c.dead = dead; c.corr1 = corr1; c.corr2 = corr2;
+#pragma unroll
+  for (int e = 0; e < kNGA; ++e) c.gA[e] = gA[e];
+#pragma unroll
+  for (int e = 0; e < kNGB; ++e) c.gB[e] = gB[e];
+  return ret;
+}
+
+// The primary threads (one per SNP: inputs, classes, verification) and the secondary threads (the corrections owed to
+// the next tile, Gram words towards t+2 in registers) run the same sequence of barriers from two instantiations of these
+// functions, so that neither carries the other's registers.
+template <int NF, bool PRIM, int B>
+__device__ __noinline__ void serial_threads() {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using G = SerialGeo<B>;
+  constexpr PrivLayout P = G::P;
+  const SweepParams& p = g_serial_ps;
+  const int tid = threadIdx.x;
+  volatile int* gctl = (volatile int*)(smem + G::priv0 + P.o_gctl);
+  long long* pc = (long long*)(smem + G::priv0 + P.o_pc);
+  SerialCarry c;
+  c.t = 0; c.dead = false; c.corr1 = 0.0; c.corr2 = 0.0;
+  for (int e = 0; e < kNGA; ++e) c.gA[e] = make_int4(0, 0, 0, 0);
+  for (int e = 0; e < kNGB; ++e) c.gB[e] = make_int4(0, 0, 0, 0);
+  for (;;) {
+    SerialTile st;
+    if (serial_fast<NF, PRIM, B>(c, st) == 0) break;
+    const int t = c.t;
+    if (st.generic && tid == 0) gctl[13]++;
+    serial_slow<NF, PRIM, B>(st, t, st.generic);
+    c.corr1 = st.c1next;
+    serial_tile_end<PRIM, B>(t, st.k, st.nrounds, st.cand, st.act, st.myrank, st.cls, st.my_delta, st.my_gnew, c.corr2, c.gA, c.gB,
+                             PRIM && tid == 0 && (p.dbg & 64));
+    c.t = t + 1;
+  }
+  if (c.dead) atomicCAS(p.ctrl + 1, 0, HB_ABORT_TIMEOUT_SCALAR);
   if (tid == 0) {
     for (int k = 0; k < 16; ++k) p.out->phase_clk[0][k] = pc[k];
-    p.out->phase_clk[1][0] = repaired;
-    p.out->phase_clk[1][1] = generic_tiles;
-    atomicAdd(&p.out->rounds, rounds_total);
-    atomicAdd(&p.out->pad, repaired);
-    atomicAdd(&p.out->n_changed, changed_total);
+    p.out->phase_clk[1][0] = gctl[12];
+    p.out->phase_clk[1][1] = gctl[13];
+    atomicAdd(&p.out->rounds, gctl[10]);
+    atomicAdd(&p.out->pad, gctl[12]);
+    atomicAdd(&p.out->n_changed, gctl[11]);
+  }
+}
+
+// The input warp of the serial CTA (its last warp): per tile, in order, (1) the package -> buffer t & 1 with one bulk
+// copy as soon as the buffer is free and the helper's flag is up, (2) the tile's far corrections (dt >= 3, one slot of B
+// doubles per source tile, contiguous in global memory) -> landing zone with one bulk copy, summed oldest first into
+// coldbuf[t & 1]; a slot that had not been posted yet when the copy ran is polled word by word.
+template <int B>
+__device__ __noinline__ void serial_input_warp() {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using G = SerialGeo<B>;
+  constexpr PkgLayout L = G::L;
+  constexpr PrivLayout P = G::P;
+  const SweepParams& p = g_serial_ps;
+  const int T = p.T, DC = p.D - 1;
+  const int lane = threadIdx.x & 31;
+  int* ctrl = p.ctrl;
+  uint8_t* priv = smem + G::priv0;
+  double* coldbuf = (double*)(priv + P.o_coldbuf);
+  const unsigned long long* stage = (const unsigned long long*)(priv + P.o_stage);
+  uint64_t* full = (uint64_t*)(priv + P.o_full);
+  uint64_t* empty = (uint64_t*)(priv + P.o_empty);
+  uint64_t* farfull = (uint64_t*)(priv + P.o_farfull);
+  uint64_t* stagefull = (uint64_t*)(priv + P.o_stagefull);
+  // lane 0 keeps the flag of the next tile: read (acquire) and fenced towards the async proxy while this tile's far
+  // corrections are on their way, so that neither trip is on the path of the next package
+  int fnext = 0;
+  if (lane == 0) {
+    fnext = ld_acquire_s32(p.pkg_flag);
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+  }
+  for (int t = 0; t < T; ++t) {
+    const int b = t & 1;
+    if (t >= 2 && !mbar_wait(empty + b, (uint32_t)(((t >> 1) - 1) & 1), ctrl, HB_ABORT_TIMEOUT_PIPE)) return;
+    const int dmax = min(DC, t);
+    const int nfar = max(0, dmax - 2);   // slots q = 2 .. dmax-1
+    int f = 0;
+    if (lane == 0) {
+      f = fnext;
+      if (f == 0) {
+        Waiter w;
+        do {
+          __nanosleep(40);
+          if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) break;
+          f = ld_acquire_s32(p.pkg_flag + t);
+        } while (f == 0);
+        asm volatile("fence.proxy.async.global;" ::: "memory");   // the helper's (generic) stores before the bulk (async) reads
+      }
+      HB_TRACE(t, 11);
+    }
+    f = __shfl_sync(0xffffffffu, f, 0);
+    if (f == 0) return;   // abandoned
+    const int nrow = (f & kPkgNoRows) ? 0 : ((f & 0xffff) - 1);
+    const uint32_t bytes = L.fixed_bytes + (uint32_t)nrow * L.row_bytes;
+    // the package in pieces of 8 KB, one lane each: a bulk copy keeps only so many requests in flight (a single 75 KB copy
+    // took ~4 us here), several copies run side by side -- and so does their issue
+    if (lane == 0) {
+      hb::mbar_arrive_expect_tx(full + b, bytes);
+      if (nfar > 0) hb::mbar_arrive_expect_tx(stagefull, (uint32_t)nfar * B * 8);
+    }
+    __syncwarp();
+    for (uint32_t off = 8192u * lane; off < bytes; off += 8192u * 32)
+      hb::tma_load_1d(smem + (size_t)b * L.stride + off, p.pkg + (size_t)t * p.pkg_stride + off, min(8192u, bytes - off), full + b);
+    if (lane == 31 && nfar > 0) hb::tma_load_1d((void*)stage, p.corr + ((size_t)t * DC + 2) * B, (uint32_t)nfar * B * 8, stagefull);
+    if (lane == 0) {
+      HB_TRACE(t, 12);
+      fnext = 0;
+      if (t + 1 < T) {
+        fnext = ld_acquire_s32(p.pkg_flag + t + 1);   // consumed in the next iteration
+        if (fnext) asm volatile("fence.proxy.async.global;" ::: "memory");
+      }
+    }
+    __syncwarp();
+    if (nfar > 0) {
+      if (!mbar_wait(stagefull, (uint32_t)((t - 3) & 1), ctrl, HB_ABORT_TIMEOUT_SCALAR)) return;
+      if (lane == 0) HB_TRACE(t, 13);
+      // far corrections of SNP s, summed oldest first; a slot that had not been posted yet when the copy ran is polled.
+      // Four SNPs at a time, all their slot words asked for before the first is used (the loads are independent).
+      for (int s0 = lane; s0 < B; s0 += 128) {
+        unsigned long long w[4][kMaxDC - 2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int q = 0; q < kMaxDC - 2; ++q)
+            w[r][q] = (q < nfar && s0 + 32 * r < B) ? stage[(size_t)q * B + s0 + 32 * r] : 0ull;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int s = s0 + 32 * r;
+          if (s < B) {
+            double cold = 0.0;
+#pragma unroll
+            for (int q = kMaxDC - 3; q >= 0; --q)
+              if (q < nfar) {
+                unsigned long long v = w[r][q];
+                if (v == kCorrEmpty) {
+                  unsigned spins = 0;
+                  const unsigned long long* slot = (const unsigned long long*)(p.corr + ((size_t)t * DC + q + 2) * B + s);
+                  do {
+                    v = ld_relaxed_u64(slot);
+                    if ((++spins & 0xffff) == 0 && *((volatile int*)(ctrl + 1)) != 0) return;
+                  } while (v == kCorrEmpty);
+                }
+                cold += __longlong_as_double((long long)v);
+              }
+            coldbuf[b * B + s] = cold;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) { hb::mbar_arrive(farfull + b); HB_TRACE(t, 14); }   // (release at CTA scope: the sums are visible to the waiters)
   }
 }
 
@@ -651,54 +983,29 @@ __device__ void serial_role(const SweepParams& pin, uint8_t* smem) {
   for (int w = threadIdx.x; w < (int)(sizeof(SweepParams) / 4); w += blockDim.x) ((int*)&g_serial_ps)[w] = ((const int*)&pin)[w];
   __syncthreads();
   const SweepParams& p = g_serial_ps;
-  const int T = p.T;
   const int tid = threadIdx.x;
   if (tid >= 2 * B) return;
   if (p.dbg & 48) return;   // timing experiments of the streaming side: the helpers publish empty tiles
-  // threads: [0, B) primary (one per SNP), [B, 2B-32) secondary (odd candidates of SNP i < B-32), last warp = loader
+  // threads: [0, B) primary (one per SNP), [B, 2B-32) secondary (odd candidates of SNP i < B-32), last warp = input warp
   constexpr int NTS = G::NTS;
-  int* ctrl = p.ctrl;
-  constexpr PkgLayout L = G::L;
   constexpr PrivLayout P = G::P;
   uint8_t* priv = smem + G::priv0;
   volatile int* gctl = (volatile int*)(priv + P.o_gctl);
   long long* pc = (long long*)(priv + P.o_pc);
-  uint64_t* full = (uint64_t*)(priv + P.o_full);
-  uint64_t* empty = (uint64_t*)(priv + P.o_empty);
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) { hb::mbar_init(full + b, 1); hb::mbar_init(empty + b, 1); }
+    uint64_t* full = (uint64_t*)(priv + P.o_full);
+    uint64_t* empty = (uint64_t*)(priv + P.o_empty);
+    uint64_t* farfull = (uint64_t*)(priv + P.o_farfull);
+    for (int b = 0; b < 2; ++b) { hb::mbar_init(full + b, 1); hb::mbar_init(empty + b, 1); hb::mbar_init(farfull + b, 1); }
+    hb::mbar_init((uint64_t*)(priv + P.o_stagefull), 1);
     hb::mbar_fence_init();
     for (int k = 0; k < 16; ++k) gctl[k] = 0;
     for (int k = 0; k < 16; ++k) pc[k] = 0;
     pc[16] = clock64();
   }
   hb::named_bar_sync(5, 2 * B);
-  if (tid >= NTS) {
-    // ---------------- loader: package of tile t -> buffer t & 1, as soon as the buffer is free and the flag is up
-    if (tid == NTS) {
-      for (int t = 0; t < T; ++t) {
-        const int b = t & 1;
-        if (t >= 2 && !mbar_wait(empty + b, (uint32_t)(((t >> 1) - 1) & 1), ctrl, HB_ABORT_TIMEOUT_PIPE)) return;
-        int f = ld_acquire_s32(p.pkg_flag + t);
-        if (f == 0) {
-          Waiter w;
-          do {
-            __nanosleep(40);
-            if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) return;
-            f = ld_acquire_s32(p.pkg_flag + t);
-          } while (f == 0);
-        }
-        HB_TRACE(t, 11);
-        asm volatile("fence.proxy.async;" ::: "memory");   // the helpers' (generic) stores before the bulk (async) read
-        const int nrow = (f & kPkgNoRows) ? 0 : ((f & 0xffff) - 1);
-        const uint32_t bytes = L.fixed_bytes + (uint32_t)nrow * L.row_bytes;
-        hb::mbar_arrive_expect_tx(full + b, bytes);
-        hb::tma_load_1d(smem + (size_t)b * L.stride, p.pkg + (size_t)t * p.pkg_stride, bytes, full + b);
-      }
-    }
-    return;
-  }
-  if (tid < B) serial_threads<NF, true, B>();
+  if (tid >= NTS) serial_input_warp<B>();
+  else if (tid < B) serial_threads<NF, true, B>();
   else serial_threads<NF, false, B>();
 }
 
@@ -844,24 +1151,27 @@ __device__ __noinline__ void helper_role(const SweepParams& pin, uint8_t* smem) 
     // row set: every candidate, plus -- while the chain has recently needed repairs -- the SNPs within 30 % of their
     // first class boundary; trimmed to the candidates when the set would not fit a package
     const bool widen = (t - gctl[4]) < 16 * NH;   // (read by one thread before the last barrier: the same for all)
+    // Slots are numbered with the candidates first, in SNP order (slot of candidate e = e: the serial CTA then walks the
+    // rows of a tile's changes without looking the slots up), the other wanted rows after them.
     auto select_rows = [&](bool with_near) {
       if (prim) {
         const double rr_spec = rhs_spec * rhs_spec;
         const bool near = with_near && TH[0] > 0.0 && TH[0] < 1e300 && rr_spec >= 0.49 * TH[0];
-        const bool want = act && (gold != 0.0 || cls > 0 || near);
-        const unsigned bal = __ballot_sync(0xffffffffu, want);
-        if (lane == 0) wcnt[warp] = __popc(bal);
+        const bool isc = act && (gold != 0.0 || cls > 0);
+        const bool extra = act && !isc && near;
+        const unsigned bal = __ballot_sync(0xffffffffu, isc), bal2 = __ballot_sync(0xffffffffu, extra);
+        if (lane == 0) { wcnt[warp] = __popc(bal); wcnt[32 + warp] = __popc(bal2); }
         hb::named_bar_sync(4, B);
-        int pre = 0, tot = 0;
+        int pre = 0, tot = 0, pre2 = 0, tot2 = 0;
         for (int w = 0; w < nwarp; ++w) {
-          const int c = wcnt[w];
-          if (w < warp) pre += c;
-          tot += c;
+          const int c = wcnt[w], c2 = wcnt[32 + w];
+          if (w < warp) { pre += c; pre2 += c2; }
+          tot += c; tot2 += c2;
         }
-        const int sl = pre + __popc(bal & ((1u << lane) - 1u));
-        slot_of[i] = want ? sl : -1;
-        if (want) slot_snp[sl] = i;
-        if (i == 0) gctl[2] = tot;
+        const int sl = isc ? pre + __popc(bal & ((1u << lane) - 1u)) : tot + pre2 + __popc(bal2 & ((1u << lane) - 1u));
+        slot_of[i] = (isc || extra) ? sl : -1;
+        if (isc || extra) slot_snp[sl] = i;
+        if (i == 0) gctl[2] = tot + tot2;
       }
       hb::named_bar_sync(1, NT2);
       ns = gctl[2];
@@ -923,8 +1233,8 @@ __device__ __noinline__ void helper_role(const SweepParams& pin, uint8_t* smem) 
         coef[e] = v;
       }
       hb::named_bar_sync(1, NT2);
-      if (k > 0 && k <= 32 && !(p.dbg & 128)) {
-        if (!prim && warp == 0) chain_build_matrix(coef, cmat, k, lane);
+      if (k > 0) {
+        if (!prim && warp == 0) chain_build_matrix(coef, cmat, min(k, 32), lane);
         m_ok = true;
       }
       hb::named_bar_sync(1, NT2);
@@ -941,10 +1251,9 @@ __device__ __noinline__ void helper_role(const SweepParams& pin, uint8_t* smem) 
             if (q == cls && q < nf - 1) hi = TL[q];
           }
         }
-        ((double*)(pk + L.o_base0))[i] = base0;
-        ((double*)(pk + L.o_addback))[i] = addback;
-        ((double*)(pk + L.o_lo))[i] = lo;
-        ((double*)(pk + L.o_hi))[i] = hi;
+        ((double*)(pk + L.o_base0))[i] = base0 + addback;
+        ((float*)(pk + L.o_lo))[i] = __double2float_ru(lo);   // (inwards: a class is never accepted on a rounded bound)
+        ((float*)(pk + L.o_hi))[i] = __double2float_rd(hi);
         ((int*)(pk + L.o_info))[i] = cls | ((int)cand << 4) | ((int)act << 5) | ((int)(spec_exact && act) << 6) | (myrank << 8);
         ((int*)(pk + L.o_slotof))[i] = fast ? slot_of[i] : -1;
         if (i == 0) {
@@ -984,28 +1293,53 @@ __device__ __noinline__ void helper_role(const SweepParams& pin, uint8_t* smem) 
       }
     }
     if (hb::named_bar_or(1, NT2, dead)) { dead = true; break; }
-    // ================= phase C: the corrections this tile owes to the tiles t+3 .. t+D-1, once it is final
+    // ================= phase C: the corrections this tile owes to the tiles t+3 .. t+D-1, once it is final.
+    // While the tile waits for its turn in the chain, the far Gram rows of its speculated candidates (slot e = candidate e)
+    // are brought into shared memory (the row buffers are free once the package is written): when the changes arrive the
+    // corrections cost no trip to memory, and the first of them is posted ~1.5 us after the tile was published -- the
+    // serial CTA's input warp reads it one tile later.
     {
       int* fidx = cs.idx;        // the final list (the candidate arrays are free now)
       double* fdel = cs.delta;
+      int* fslot = cs.cls;       // row slot of a final change in the far buffers, -1: not there (read from the Gram band)
+      const int nblk = max(0, min(D, T - t) - 3);          // far blocks dt = 3 .. 3 + nblk - 1
+      const int kpre = fast ? min(k, KROW) : 0;            // candidates whose far rows are fetched ahead
+      const int cap = (2 * KROW) / max(1, kpre);           // blocks that fit the two row buffers
+      const int npre = min(nblk, cap);
+      int32_t* far = rows0;                                // [npre][kpre][B]
+      if (kpre > 0 && npre > 0) {
+        const int q4 = B / 4;   // 16-byte pieces per row
+        for (int e = tid; e < npre * kpre * q4; e += NT2) {
+          const int c = e % q4, r = (e / q4) % kpre, d = e / (q4 * kpre);
+          const int32_t* src = G0 + (size_t)(3 + d) * B * B + (size_t)slot_snp[r] * B + 4 * c;
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(far + ((size_t)d * kpre + r) * B + 4 * c);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+        cp_async_wait_all();
+      }
+      // the tile's changes: the count and the first 32 entries are asked for in the same trip to L2
       if (tid < 32) {
-        int cnt = -1;
+        int cnt = -1, jl0 = -1;
+        unsigned long long dw0 = kCorrEmpty;
         Waiter w;
         for (;;) {
           int c = -1;
           if (lane == 0) c = hb::ld_relaxed(p.tile_cnt + t);
+          if (jl0 < 0) jl0 = hb::ld_relaxed(p.q_snp + (size_t)t * B + lane);
+          if (dw0 == kCorrEmpty) dw0 = ld_relaxed_u64(p.q_delta + (size_t)t * B + lane);
           cnt = __shfl_sync(0xffffffffu, c, 0);
-          if (cnt >= 0) break;
-          __nanosleep(100);
+          if (cnt >= 0 && __all_sync(0xffffffffu, lane >= cnt || (jl0 >= 0 && dw0 != kCorrEmpty))) break;
+          if (cnt < 0) __nanosleep(100);
           if (!w.keep_waiting(ctrl, HB_ABORT_TIMEOUT_SCALAR)) { cnt = -2; break; }
         }
+        if (lane < cnt) { fidx[lane] = jl0 - t * B; fdel[lane] = __longlong_as_double((long long)dw0); }
         if (lane == 0) gctl[3] = cnt;
       }
       hb::named_bar_sync(1, NT2);
       const int kf = gctl[3];
       if (kf < 0) { dead = true; break; }
       if (tid == 0) HB_TRACE(t, 8);
-      for (int e = tid; e < kf; e += NT2) {
+      for (int e = 32 + tid; e < kf; e += NT2) {
         int jl = -1;
         unsigned long long dw = kCorrEmpty;
         Waiter w;
@@ -1018,10 +1352,26 @@ __device__ __noinline__ void helper_role(const SweepParams& pin, uint8_t* smem) 
         fidx[e] = jl - t * B;
         fdel[e] = __longlong_as_double((long long)dw);
       }
-      if (hb::named_bar_or(1, NT2, dead)) { dead = true; break; }
+      if (kf > 32 && hb::named_bar_or(1, NT2, dead)) { dead = true; break; }
+      // row slot of every final change (slot_of: candidates are slots 0 .. k-1)
+      bool all_pre = true;
+      for (int e = tid; e < kf; e += NT2) {
+        const int sl = slot_of[fidx[e]];
+        fslot[e] = (sl >= 0 && sl < kpre) ? sl : -1;
+      }
+      hb::named_bar_sync(1, NT2);
+      for (int e = 0; e < kf; ++e) all_pre = all_pre && (fslot[e] >= 0);
       for (int dt = 3 + h; dt < D; dt += 2) {
         if (t + dt >= T) break;
-        const double cv = band_correction_raw(fidx, fdel, kf, G0 + (size_t)dt * B * B, B, i);
+        double cv;
+        if (dt - 3 < npre && all_pre) {
+          // (ascending order of the changes, one fma each: the sum band_correction_raw forms)
+          const int32_t* fr = far + (size_t)(dt - 3) * kpre * B + i;
+          cv = 0.0;
+          for (int e = 0; e < kf; ++e) cv = fma(gram_as_double(fr[(size_t)fslot[e] * B]), fdel[e], cv);
+        } else {
+          cv = band_correction_raw(fidx, fdel, kf, G0 + (size_t)dt * B * B, B, i);
+        }
         post_corr(p.corr + ((size_t)(t + dt) * DC + (dt - 1)) * B + i, cv);
         if (tid == 0 && dt == 3) HB_TRACE(t, 9);
       }

@@ -90,6 +90,7 @@ struct SweepParams {
   uint8_t* pkg;               // [T] packages
   int* pkg_flag;              // [T] 0 = not written yet, else 1 + number of row slots (| 1 << 20: no rows, generic path)
   int* miss_tile;             // [1] last tile that needed a second round (the helpers widen their row sets after it)
+  int xevict;                 // genotype tiles are streamed with an L2 evict_first hint (HB_XEVICT)
 };
 
 enum { HB_ABORT_TIMEOUT_STREAM = 1, HB_ABORT_TIMEOUT_SCALAR = 2, HB_ABORT_TIMEOUT_TMA = 3, HB_ABORT_OVERFLOW = 4,
@@ -434,10 +435,12 @@ __device__ void stream_role(const SweepParams& p, uint8_t* smem) {
     if (lane == 0) {
       int st = 0;
       uint32_t par = 1;   // parity of the previous phase of empty[st]
+      const uint64_t pol = hb::l2_policy_evict_first();
       for (int gsub = 0; gsub < nsub; ++gsub) {
         if (gsub >= NS && !mbar_wait(empty + st, par, ctrl, HB_ABORT_TIMEOUT_TMA)) return;
         hb::mbar_arrive_expect_tx(full + st, p.stage_bytes);
-        hb::tma_load_1d(stage0 + (size_t)st * p.stage_bytes, Xs + (size_t)gsub * p.stage_bytes, p.stage_bytes, full + st);
+        if (p.xevict) hb::tma_load_1d_hint(stage0 + (size_t)st * p.stage_bytes, Xs + (size_t)gsub * p.stage_bytes, p.stage_bytes, full + st, pol);
+        else hb::tma_load_1d(stage0 + (size_t)st * p.stage_bytes, Xs + (size_t)gsub * p.stage_bytes, p.stage_bytes, full + st);
         if (++st == NS) { st = 0; par ^= 1u; }
       }
     }
@@ -858,38 +861,49 @@ __device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const
 // The chain of the first 32 candidates is the triangular system (I - H) e = e0 with H[s][lp] = coef[32 lp + s]
 // (strictly lower triangular).  Its inverse M depends only on the candidate list, so one idle warp solves it column
 // by column in phase P (lane c owns column c, forward substitution) ...
+// (M is stored column by column, M[c * 33 + s] = entry (row s, column c): lane c builds its own column, and in
+// chain_matvec lane s reads entry (s, lp) of consecutive lanes from consecutive words)
 __device__ __forceinline__ void chain_build_matrix(const double* coef, double* M, int kk, int c) {
   for (int sr = 0; sr < 32; ++sr) {
     double acc0 = (sr == c) ? 1.0 : 0.0, acc1 = 0.0;
     if (sr < kk) {
       int lp = 0;
       for (; lp + 1 < sr; lp += 2) {
-        acc0 = fma(coef[lp * 32 + sr], M[lp * 33 + c], acc0);
-        acc1 = fma(coef[(lp + 1) * 32 + sr], M[(lp + 1) * 33 + c], acc1);
+        acc0 = fma(coef[lp * 32 + sr], M[c * 33 + lp], acc0);
+        acc1 = fma(coef[(lp + 1) * 32 + sr], M[c * 33 + lp + 1], acc1);
       }
-      if (lp < sr) acc0 = fma(coef[lp * 32 + sr], M[lp * 33 + c], acc0);
+      if (lp < sr) acc0 = fma(coef[lp * 32 + sr], M[c * 33 + lp], acc0);
     }
-    M[sr * 33 + c] = (sr < kk) ? acc0 + acc1 : 0.0;
+    M[c * 33 + sr] = (sr < kk) ? acc0 + acc1 : 0.0;
   }
 }
 // ... and on the serial path the chain is one 32x32 matrix-vector product by one warp: lane s takes row s, the
 // right-hand sides e0 come by shuffle, four independent partial sums (no step waits for the one before).
+// The right-hand sides e0 go through shared memory (the candidates' delta array serves as the scratch: it is written
+// only at the end), so a step is two independent loads and one fma -- no shuffle on the way.
 __device__ __forceinline__ void chain_matvec(const CandSet& cs, int k, const double* M, int lane) {
   const bool valid = lane < k;
   const double iv = valid ? cs.iv[lane] : 0.0, gold = valid ? cs.gold[lane] : 0.0;
   const double e0 = valid ? fma(cs.rhs0[lane], iv, cs.sdz[lane]) - gold : 0.0;
-  const double* row = M + lane * 33;
+  const int cls = valid ? cs.cls[lane] : 0;
+  double* e0buf = cs.delta;
+  e0buf[lane] = e0;
+  __syncwarp();
+  const double* col = M + lane;   // entry (row lane, column lp) at col[33 * lp]
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
   for (int lp = 0; lp < 32; lp += 4) {
     if (lp >= k) break;
-    a0 = fma(row[lp], __shfl_sync(0xffffffffu, e0, lp), a0);
-    a1 = fma(row[lp + 1], __shfl_sync(0xffffffffu, e0, lp + 1), a1);
-    a2 = fma(row[lp + 2], __shfl_sync(0xffffffffu, e0, lp + 2), a2);
-    a3 = fma(row[lp + 3], __shfl_sync(0xffffffffu, e0, lp + 3), a3);
+    const double2 ea = *(const double2*)(e0buf + lp), eb = *(const double2*)(e0buf + lp + 2);
+    a0 = fma(col[33 * lp], ea.x, a0);
+    a1 = fma(col[33 * (lp + 1)], ea.y, a1);
+    a2 = fma(col[33 * (lp + 2)], eb.x, a2);
+    a3 = fma(col[33 * (lp + 3)], eb.y, a3);
   }
   const double e = (a0 + a1) + (a2 + a3);
+  __syncwarp();
   if (valid) { cs.delta[lane] = e; cs.gnew[lane] = (cs.cls[lane] > 0) ? gold + e : 0.0; }
+  (void)cls;
   __syncwarp();
 }
 template <bool ROWS>

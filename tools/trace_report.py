@@ -51,3 +51,10 @@ if a[lo:hi, 8].any():
     print("helper saw the changes (8) -> phase C done (10): %.0f" % d(10, 8))
     print("tile final (3) -> serial CTA done with the tile (5): %.0f" % d(5, 3))
     print("serial CTA done with t-1 (5) -> tile t started (2): %.0f" % float(np.median(a[lo + 1:hi, 2] - a[lo:hi - 1, 5])))
+    if a[lo:hi, 12].any():
+        print("loader saw the flag (11) -> bulk copies issued (12): %.0f" % d(12, 11))
+        print("bulk copies issued (12) -> far slots landed (13): %.0f" % d(13, 12))
+        print("far slots landed (13) -> far sums done (14): %.0f" % d(14, 13))
+        print("bulk copies issued (12) -> package landed, as seen by the chain (15): %.0f" % d(15, 12))
+        print("package seen (15) -> tile started (2; = far sums seen): %.0f" % d(2, 15))
+        print("serial CTA done with t-2 (5) -> loader saw the flag of t (11): %.0f" % float(np.median(a[lo + 2:hi, 11] - a[lo:hi - 2, 5])))
