@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- Gibbs SNP-updates/s of the BayesR sweep (BASELINE.json metric).
+"""bench.py -- Gibbs SNP-updates/s of the BayesR sweep (BASELINE.json metric) and the other BASELINE configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config metric|c2|c3] [--scaling weak|strong]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one MCMC iteration's SNP sweep over the whole synthetic genotype matrix (n = 50 000
-individuals x m = 1 000 000 SNPs, int8, generated on the device) followed by the per-iteration reductions -- what
-replaces Bayes.cpp:586-823 -- driven by the host-side scalar updates of a BayesR chain.
+A "step" is one MCMC iteration's SNP sweep over the whole synthetic genotype matrix followed by the per-iteration
+reductions -- what replaces Bayes.cpp:586-823 -- driven by the host-side scalar updates of the chain.
 
-`value`     K steps timed with inputs resident in HBM (barrier + synchronize on both sides, max over ranks).
-`e2e`       the same K steps through the host-facing C ABI with HOST buffers: every step uploads the residual
-            (what the host driver does after its non-SNP effects) and downloads residual and genetic values.
-N > 1       weak scaling over individuals: every rank holds n = 50 000 rows of an N x 50 000-row matrix (the
-            reference's C3 shape is 8 x 25 000); a unit of `value` is one SNP update over one rank's 50 000-row
-            shard, so N ranks sweeping m SNPs do N x m units per step.  The dots of a tile are exchanged inside the
-            sweep kernel (NVLink peer atomics), scalars of the iteration by one small all-reduce.
+--config metric (default; what the driver runs)  BayesR, n = 50 000 x m = 1 000 000 int8 genotypes generated on the device.
+    value   K steps timed with inputs resident in HBM (barrier + synchronize on both sides, max over ranks).
+    e2e     N = 1: the drop-in call hb_bayes() (what _hibayes_Bayes would forward to) with HOST y and X for W + K iterations;
+            the timed region is the whole call minus its set-up (X host->device + column statistics + Gram band, reported
+            as e2e.x_load_s), i.e. y upload, every sweep with its host-side scalar updates, and the download of the results.
+            N > 1 (and hosts too small for the 50 GB matrix): the engine steps with the residual crossing PCIe both ways.
+    N > 1   --scaling weak (default): every rank holds 50 000 rows of an N x 50 000-row matrix; a unit of `value` is one
+            SNP update over one rank's shard (config.snp_updates_per_s is the plain m x steps / time).
+            --scaling strong: the 50 000 rows are split over the ranks (last row).
+            `parity_check`: an untimed small row-sharded run against the CPU oracle on rank 0, and equality of the
+            class labels over the ranks after the timed run.
+--config c2   BASELINE configs[1]: ibrm() BayesR n = 50 000 x m = 500 000, 1000 iterations through hb_bayes() with host
+              buffers; ms per sweep and rounds per tile around iterations 10 / 100 / 500 / 1000.
+--config c3   BASELINE configs[2]: BayesB n = 200 000 x m = 1 000 000 row-sharded over 8 GPUs (25 000 rows per GPU).
 `--impl reference`  the reference's own CPU data path (per-SNP ddot + 2 daxpy on a column-major fp64 matrix,
             Bayes.cpp:751-802, all host threads) on a bounded column sample of the same workload (oracle port: the
             reference itself needs R/Rcpp/Armadillo and cannot be built here).
@@ -35,7 +41,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "gibbs_snp_updates_per_sec_bayesr_n50k"
 UNIT = "SNP-updates/s"
-PI0 = [0.95, 0.02, 0.02, 0.01]
+PI_R = [0.95, 0.02, 0.02, 0.01]
 FOLD = [0.0, 1e-4, 1e-3, 1e-2]
 if os.environ.get("HB_BENCH_FOLD_SCALE"):   # experiments only: stronger effects stress the speculation of the scalar chain
     FOLD = [f * float(os.environ["HB_BENCH_FOLD_SCALE"]) for f in FOLD]
@@ -53,12 +59,13 @@ def _peaks():
 
 
 def _traffic():
-    """dram bytes per k_sweep launch at the bench shape, from the committed ncu capture (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r01_sweep_traffic.json")
-    try:
-        return json.load(open(path))
-    except Exception:
-        return None
+    """dram bytes per k_sweep launch at the metric shape, from the committed ncu capture (profiles/); N = 1 only."""
+    for name in ("r02_sweep_traffic.json", "r01_sweep_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -97,70 +104,198 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+# ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_reference(n, m_cpu, sweeps, threads):
+    """The reference's CPU data path on an n x m_cpu fp64 column-major sample: the oracle's OpenMP level-1 loops
+    (hbo_time_sweep_fp64: one untimed warm-up sweep, then `sweeps` timed ones) and the same per-SNP ddot / 2 daxpy through
+    the bundled OpenBLAS (scipy.linalg.blas, multi-threaded), the stand-in for MKL; the faster of the two is reported
+    (BASELINE.md section 3)."""
     from oracle import hb_oracle
     hb_oracle.lib()
-    val, _ = hb_oracle.time_sweep_fp64(n, m_cpu, sweeps, threads)
-    return val
+    v_omp, _ = hb_oracle.time_sweep_fp64(n, m_cpu, sweeps, threads)
+    v_blas = None
+    try:
+        v_blas = _cpu_openblas(n, min(m_cpu, 4000), sweeps)
+    except Exception:
+        pass
+    if v_blas is not None and v_blas > v_omp:
+        return v_blas, "OpenBLAS ddot/daxpy (scipy.linalg.blas)", {"openmp": v_omp, "openblas": v_blas}
+    return v_omp, "OpenMP ddot/daxpy", {"openmp": v_omp, "openblas": v_blas}
 
 
+def _cpu_openblas(n, m_cpu, sweeps):
+    from scipy.linalg import blas
+    rng = np.random.default_rng(1)
+    X = np.asfortranarray(rng.integers(0, 3, size=(n, m_cpu)).astype(np.float64))
+    r = rng.standard_normal(n)
+    u = np.zeros(n)
+    g = np.zeros(m_cpu)
+    xpx = (X * X).sum(axis=0)
+    un = rng.uniform(size=(sweeps + 1, m_cpu))
+    zn = rng.standard_normal(size=(sweeps + 1, m_cpu))
+    t_total = 0.0
+    for sw in range(sweeps + 1):
+        t0 = time.perf_counter()
+        for j in range(m_cpu):
+            x = X[:, j]
+            rhs = blas.ddot(x, r) + xpx[j] * g[j]
+            inc = un[sw, j] < 0.05                         # (the class decision is negligible next to the three passes)
+            gn = (rhs / (xpx[j] + 1e3) + 1e-3 * zn[sw, j]) if inc else 0.0
+            d = g[j] - gn
+            if d != 0.0:
+                blas.daxpy(x, r, a=d)
+                blas.daxpy(x, u, a=-d)
+            g[j] = gn
+        if sw > 0:
+            t_total += time.perf_counter() - t0
+    return m_cpu * sweeps / t_total
+
+
+# ------------------------------------------------------------------------------------------------ chains
 class Chain:
-    """Host-side scalar updates of the BayesR chain around hb_engine_sweep (Bayes.cpp:480-482, 803-823); numpy's
+    """Host-side scalar updates of the chain around hb_engine_sweep (Bayes.cpp:480-482, 664-670, 803-823); numpy's
     generator stands in for the host draws (same seed on every rank) -- only the workload matters here."""
 
-    def __init__(self, n_total, vary, sumvx, seed):
+    def __init__(self, model, n_total, vary, sumvx, seed):
+        self.model = model
         self.n = n_total
         self.rng = np.random.default_rng(seed)
         self.df = 4.0
+        self.pi = np.array(PI_R if model == "BayesR" else [0.95, 0.05])
         vara = (self.df - 2) / self.df * vary * 0.5
         self.vare = vary * 0.5
-        self.varg = vara / ((1 - PI0[0]) * sumvx)
-        self.s2varg = vara * (self.df - 2) / self.df / ((1 - PI0[0]) * sumvx)
-        self.pi = np.array(PI0)
+        self.varg = vara / ((1 - self.pi[0]) * sumvx)
+        self.s2varg = vara * (self.df - 2) / self.df / ((1 - self.pi[0]) * sumvx)
         self.sum_r, self.sum_r2 = 0.0, vary * (n_total - 1)
         self.it = 0
 
     def sweep_args(self):
         mu_ = -(self.sum_r / self.n + math.sqrt(self.vare / self.n) * self.rng.standard_normal())
         rn2 = self.sum_r2 + 2 * mu_ * self.sum_r + self.n * mu_ * mu_
-        return dict(iter=self.it, model_index=6, vare=self.vare, logpi=list(np.log(self.pi)),
-                    vara_fold=[self.varg * f for f in FOLD], fold=FOLD, dfvara=self.df, s2varg=self.s2varg,
+        if self.model == "BayesR":
+            return dict(iter=self.it, model_index=6, vare=self.vare, logpi=list(np.log(self.pi)),
+                        vara_fold=[self.varg * f for f in FOLD], fold=FOLD, dfvara=self.df, s2varg=self.s2varg,
+                        mu_shift=mu_, rnorm2_bound=rn2)
+        # BayesB: per-SNP variances are drawn on the device from dfvara / s2varg (Bayes.cpp:636)
+        return dict(iter=self.it, model_index=3, vare=self.vare, logpi=list(np.log(self.pi)) + [0.0, 0.0],
+                    vara_fold=[0.0, self.varg, 0.0, 0.0], fold=[0.0, 1.0, 0.0, 0.0], dfvara=self.df, s2varg=self.s2varg,
                     mu_shift=mu_, rnorm2_bound=rn2)
 
     def update(self, so, sum_r, sum_r2):
-        cnt = np.array(so["count"][:4])
+        F = len(self.pi)
+        cnt = np.array(so["count"][:F])
         nnz = cnt[1:].sum()
-        self.varg = (so["varg_acc"] + self.s2varg * self.df) / self.rng.chisquare(self.df + nnz)
+        if self.model == "BayesR":
+            self.varg = (so["varg_acc"] + self.s2varg * self.df) / self.rng.chisquare(self.df + nnz)
         self.pi = self.rng.dirichlet(cnt + 1)
         self.vare = sum_r2 / self.rng.chisquare(self.n - 2)
         self.sum_r, self.sum_r2 = sum_r, sum_r2
         self.it += 1
 
 
+# ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     n, m_cpu = args.n, args.m_cpu
-    # each "step" = one sweep over the m_cpu-column sample; hbo_time_sweep_fp64 runs one untimed warm-up sweep
-    # itself, then `steps` timed sweeps
+    sweeps = max(3, min(args.steps, 5))   # each "step" = one sweep over the m_cpu-column sample; >= 3 timed sweeps
     t0 = time.time()
-    val = cpu_reference(n, m_cpu, max(1, args.steps), threads)
+    val, how, both = cpu_reference(n, m_cpu, sweeps, threads)
     wall = time.time() - t0
-    sample = ("n=%d x m=%d fp64 column-major, %d timed sweeps, OpenMP ddot/daxpy (oracle port; the reference needs "
-              "R/Rcpp/Armadillo and cannot be built here)" % (n, m_cpu, max(1, args.steps)))
+    sample = ("n=%d x m=%d fp64 column-major, 1 warm-up + %d timed sweeps, %s (oracle port; the reference needs "
+              "R/Rcpp/Armadillo and cannot be built here)" % (n, m_cpu, sweeps, how))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * m_cpu / val, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "ibrm() BayesR sweep, synthetic n=%d x m=%d (CPU sample: first %d columns)" % (n, args.m, m_cpu),
-                   "n": n, "m": args.m, "m_sample": m_cpu},
+                   "n": n, "m": args.m, "m_sample": m_cpu, "variants": both},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ host data
+def _mem_available():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) * 1024
+    except Exception:
+        pass
+    return 0
+
+
+def host_genotypes(n, m, seed, threads=None):
+    """The device generator's matrix on the host (column-major int8), blocks of columns on several threads."""
+    import hibayes_b200 as hb
+    X = np.empty((n, m), dtype=np.int8, order="F")
+    threads = threads or min(32, os.cpu_count() or 1)
+    step = max(1, -(-m // (4 * threads)))
+    blocks = [(c0, min(m, c0 + step)) for c0 in range(0, m, step)]
+
+    def work(b):
+        c0, c1 = b
+        hb.synth_geno_host_into(X[:, c0:c1], seed, col_offset=c0)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, blocks))
+    return X
+
+
+def product_call(n, m, niter, seed, device, comm=None):
+    """hb_bayes() with host buffers: synthetic y from 1000 causal SNPs (h2 = 0.5), BayesR defaults of R/bayes.r."""
+    import hibayes_b200 as hb
+    t0 = time.time()
+    X = host_genotypes(n, m, seed)
+    rng = np.random.default_rng(seed)
+    causal = rng.choice(m, size=min(1000, m), replace=False)
+    gv = X[:, causal].astype(np.float64) @ rng.standard_normal(causal.size)
+    y = gv * math.sqrt(0.5 / gv.var()) + np.random.default_rng(seed + 1).normal(scale=math.sqrt(0.5), size=n)
+    t_gen = time.time() - t0
+    t0 = time.perf_counter()
+    res = hb.Bayes(y, X, "BayesR", PI_R, fold=FOLD, niter=niter, nburn=niter // 2, thin=5, seed=seed, device=device, comm=comm)
+    wall = time.perf_counter() - t0
+    return res, wall, t_gen, X.nbytes
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def parity_check_sharded(comm, local_rank):
+    """Untimed: hb_bayes() on row shards of a small problem against the CPU oracle on the full data (rank 0), and the
+    same class labels on every rank.  Returns a dict for the JSON line."""
+    import torch
+    import hibayes_b200 as hb
+    from hibayes_b200.sharded import shard_rows
+    from tests.util_demo import synth
+    out = {}
+    y, X = synth(3001, 2500, seed=44, n_causal=25)
+    kw = dict(niter=12, nburn=4, thin=2, seed=909)
+    Pi = [0.9, 0.05, 0.03, 0.02]
+    lo, hi = shard_rows(len(y), comm.rank, comm.world)
+    got = hb.Bayes(y[lo:hi], X[lo:hi], "BayesR", Pi, fold=FOLD, device=local_rank, comm=comm, **kw)
+    ok = True
+    if comm.rank == 0:
+        from oracle import hb_oracle
+        ref = hb_oracle.bayes(y, X, "BayesR", Pi, fold=FOLD, **kw)
+        ok = bool(np.array_equal(got["diag"]["tracker"], ref["diag"]["tracker"])
+                  and np.array_equal(got["diag"]["nnz_trace"], ref["diag"]["nnz_trace"])
+                  and np.abs(got["alpha"] - ref["alpha"]).max() < 1e-5 * np.abs(ref["alpha"]).max()
+                  and abs(got["Ve"] / ref["Ve"] - 1) < 1e-5 and abs(got["Vg"] / ref["Vg"] - 1) < 1e-5)
+    t = torch.from_numpy(got["diag"]["tracker"].astype(np.int64)).cuda()
+    t0 = t.clone()
+    comm.dist.broadcast(t0, 0)
+    same = bool(torch.equal(t, t0))
+    flags = torch.tensor([int(ok), int(same)], device="cuda")
+    comm.dist.all_reduce(flags, op=comm.dist.ReduceOp.MIN)
+    out["small_sharded_vs_oracle"] = "ok" if int(flags[0]) else "MISMATCH"
+    out["small_sharded_labels_equal_across_ranks"] = bool(int(flags[1]))
+    out["shape"] = "BayesR n=3001 x m=2500, 12 iterations, rows over %d ranks" % comm.world
+    return out
 
 
 def run_gpu(args):
@@ -185,8 +320,22 @@ def run_gpu(args):
         if comm:
             comm.dist.barrier()
 
-    n_local, m = args.n, args.m
+    model = "BayesB" if args.config == "c3" else "BayesR"
+    m = args.m
+    if args.config == "c3":
+        n_local = 200000 // max(world, 1) if world > 1 else 25000
+        scaling = "strong"   # the configuration is fixed: 200 000 rows over the ranks
+    elif args.scaling == "strong" and world > 1:
+        n_local = -(-args.n // world)
+        n_local = -(-n_local // 4) * 4
+        scaling = "strong"
+    else:
+        n_local = args.n
+        scaling = "weak"
     n_total = n_local * world
+    parity = None
+    if comm:
+        parity = parity_check_sharded(comm, local_rank)
     t_setup = time.time()
     eng = hb.Engine(n_local, m, device=local_rank, tile_snps=args.tile, lag_tiles=args.lag, seed=args.seed, rank=rank, world=world)
     eng.synth_geno(args.seed, row_offset=rank * n_local)
@@ -216,7 +365,7 @@ def run_gpu(args):
     vary = (s2[1] - n_total * ymean * ymean) / (n_total - 1)
     r = y - ymean
     eng.set_residual(r)
-    chain = Chain(n_total, float(vary), float(vx.sum()), args.seed)
+    chain = Chain(model, n_total, float(vary), float(vx.sum()), args.seed)
     s3 = allsum(np.array([r.sum(), r @ r]))
     chain.sum_r, chain.sum_r2 = float(s3[0]), float(s3[1])
     t_setup = time.time() - t_setup
@@ -249,9 +398,18 @@ def run_gpu(args):
         wall = time.perf_counter() - t0
     wall = float(np.max(allsum_max(comm, wall)))
     m_active = int(active.sum())
-    value = world * m_active * args.steps / wall
-    # ---- end-to-end region: same steps through the host-facing ABI, residual over PCIe in both directions
-    r = eng.get_residual()                  # the chain's current residual (not the one from before the sweeps)
+    snp_updates = m_active * args.steps / wall                # plain SNP updates of the n_total-row model per second
+    value = (world if scaling == "weak" else 1) * snp_updates  # weak scaling: one unit = one SNP update over one rank's shard
+    if comm:
+        # every rank took the same decisions in the timed run
+        t = torch.from_numpy(eng.get_tracker().astype(np.int64)).cuda()
+        t0_ = t.clone()
+        comm.dist.broadcast(t0_, 0)
+        flag = torch.tensor([int(torch.equal(t, t0_))], device="cuda")
+        comm.dist.all_reduce(flag, op=comm.dist.ReduceOp.MIN)
+        parity["timed_run_labels_equal_across_ranks"] = bool(int(flag[0]))
+    # ---- end-to-end region through the engine: same steps, residual over PCIe in both directions
+    r = eng.get_residual()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -262,43 +420,107 @@ def run_gpu(args):
     torch.cuda.synchronize()
     barrier()
     e2e_s = float(np.max(allsum_max(comm, time.perf_counter() - t0)))
-    e2e = world * m_active * args.steps / e2e_s
+    e2e = {"value": (world if scaling == "weak" else 1) * m_active * args.steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": 8 * n_local, "d2h_bytes_per_step": 16 * n_local + 160,
+           "path": "hb_engine_* steps with host residual buffers (the residual crosses PCIe both ways every step)"}
+    eng.close()
+    del eng
+    # ---- end-to-end through the drop-in call (N = 1, metric shape, when the host can hold X)
+    if world == 1 and args.config == "metric" and not args.no_product:
+        need = int(1.7 * n_local * m)
+        if _mem_available() > need:
+            niter = args.warmup + args.steps
+            res, call_s, gen_s, xbytes = product_call(n_local, m, niter, args.seed, local_rank)
+            dg = res["diag"]
+            run_s = call_s - dg["seconds_setup"]
+            e2e = {"value": m_active * niter / run_s, "unit": UNIT,
+                   "h2d_bytes_per_step": int((8 * n_local) / niter), "d2h_bytes_per_step": int((3 * 8 * m + 16 * n_local) / niter),
+                   "path": "hb_bayes() with host y and X (int8), %d iterations; timed = the call minus its set-up" % niter,
+                   "x_load_s": dg["seconds_setup"], "x_bytes": int(xbytes), "call_s": call_s, "host_generation_s": gen_s,
+                   "value_incl_x_load": m_active * niter / call_s,
+                   "device_ms_per_sweep": float(np.mean(dg["sweep_ms_trace"][args.warmup:])),
+                   "rounds_per_tile": float(dg["rounds_total"]) / max(1, dg["tiles_total"])}
+        else:
+            e2e["note"] = "host memory too small for the %d GB int8 matrix: engine-level steps" % (n_local * m // 10**9)
     peak, peak_src = _peaks()
     kern_s = float(np.mean(sweep_ms)) * 1e-3
     achieved = n_local * m / kern_s / 1e9   # algorithmic bytes: n per SNP update (one read of the int8 column)
-    tr = _traffic()
+    tr = _traffic() if (world == 1 and args.config == "metric" and n_local == 50000 and m == 1000000) else None
+    workload = {"metric": "ibrm() BayesR sweep", "c3": "ibrm() BayesB sweep (BASELINE configs[2])", "c2": ""}[args.config]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "ibrm() BayesR sweep, synthetic int8 genotypes, n=%d individuals per GPU x m=%d SNPs, %d GPU(s)"
-                               % (n_local, m, world),
-                   "n_per_gpu": n_local, "n_total": n_total, "m": m, "m_active": m_active, "Pi": PI0, "fold": FOLD,
-                   "unit_of_value": "one SNP update over one rank's %d-row shard" % n_local,
+        "config": {"workload": "%s, synthetic int8 genotypes, n=%d individuals per GPU x m=%d SNPs, %d GPU(s), n_total=%d"
+                               % (workload, n_local, m, world, n_total),
+                   "n_per_gpu": n_local, "n_total": n_total, "m": m, "m_active": m_active, "model": model,
+                   "Pi": list(chain.pi) if False else (PI_R if model == "BayesR" else [0.95, 0.05]), "fold": FOLD,
+                   "unit_of_value": ("one SNP update over one rank's %d-row shard" % n_local) if scaling == "weak"
+                                    else "one SNP update of the %d-row model" % n_total,
+                   "snp_updates_per_s": snp_updates,
                    "layout": desc, "l2": "inputs (%.1f GB per GPU) larger than L2" % (desc["geno_bytes"] / 1e9),
                    "changed_snps_per_sweep": float(np.mean(changed)), "scalar_rounds_per_sweep": float(np.mean(rounds)),
+                   "rounds_per_tile": float(np.mean(rounds)) / max(1, -(-m // desc["tile_snps"])),
                    "device_ms_per_step": float(np.mean(dev_ms)), "setup_s": t_setup, "gram_s": t_gram,
                    "frac_of_8TBps": achieved / 8000.0},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_source": (tr or {}).get("source"),
                      "peak_source": peak_src, "kernel": "k_sweep", "kernel_ms": kern_s * 1e3,
                      "algorithmic_bytes_per_launch": n_local * m},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n_local, "d2h_bytes_per_step": 16 * n_local + 160},
+        "e2e": e2e,
         "gpu_launches": KERNELS_PER_STEP * args.steps,
         "clocks": clk.summary(),
     }
+    if parity is not None:
+        line["parity_check"] = parity
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        val = cpu_reference(n_local, args.m_cpu, 1, threads)
+        val, how, both = cpu_reference(n_local, args.m_cpu, 3, threads)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "n=%d x m=%d fp64 column-major (first columns of the workload), 1 warm + 1 timed sweep, "
-                                          "OpenMP ddot/daxpy" % (n_local, args.m_cpu)}
+                                "sample": "n=%d x m=%d fp64 column-major (first columns of the workload), 1 warm-up + 3 timed "
+                                          "sweeps, %s" % (n_local, args.m_cpu, how), "variants": both}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    eng.close()
     if comm:
         comm.dist.barrier()
         comm.dist.destroy_process_group()
+
+
+def run_c2(args):
+    """BASELINE configs[1]: the drop-in call on n = 50 000 x m = 500 000 for 1000 iterations."""
+    n, m, niter = args.n, 500000 if args.m == 1000000 else args.m, args.niter
+    res, call_s, gen_s, xbytes = product_call(n, m, niter, args.seed, 0)
+    dg = res["diag"]
+    T = dg["tiles_total"] // max(1, dg["iters_done"])
+    run_s = call_s - dg["seconds_setup"]
+
+    def around(it):
+        lo, hi = max(0, it - 10), min(niter, it)
+        return {"iteration": it, "device_ms_per_sweep": float(np.mean(dg["sweep_ms_trace"][lo:hi])),
+                "rounds_per_tile": float(np.mean(dg["rounds_trace"][lo:hi])) / max(1, T),
+                "nnz_snps": int(dg["nnz_trace"][hi - 1])}
+
+    peak, peak_src = _peaks()
+    ms_steady = float(np.mean(dg["sweep_ms_trace"][niter // 2:]))
+    line = {
+        "metric": METRIC, "value": m * niter / run_s, "unit": UNIT, "n_gpus": 1, "steps": niter, "warmup": 0,
+        "ms_per_step": 1e3 * run_s / niter, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: ibrm() BayesR, synthetic n=%d x m=%d int8, %d iterations through hb_bayes() "
+                               "with host y and X" % (n, m, niter),
+                   "n": n, "m": m, "niter": niter, "x_load_s": dg["seconds_setup"], "x_bytes": int(xbytes), "call_s": call_s,
+                   "host_generation_s": gen_s, "value_incl_x_load": m * niter / call_s,
+                   "at": [around(it) for it in (10, 100, 500, 1000) if it <= niter],
+                   "Vg": res["Vg"], "Ve": res["Ve"], "h2": res["h2"], "pi": list(res["pi"])},
+        "roofline": {"bound": "hbm", "achieved": n * m / (ms_steady * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": n * m / (ms_steady * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "k_prep + k_sweep + reductions (device time of an iteration, second half of the chain)",
+                     "kernel_ms": ms_steady, "algorithmic_bytes_per_launch": n * m},
+        "e2e": {"value": m * niter / run_s, "unit": UNIT, "h2d_bytes_per_step": int(8 * n / niter),
+                "d2h_bytes_per_step": int((3 * 8 * m + 16 * n) / niter), "path": "hb_bayes(), timed = the call minus its set-up"},
+        "gpu_launches": KERNELS_PER_STEP * niter,
+    }
+    print(json.dumps(line), flush=True)
 
 
 def allsum_max(comm, x):
@@ -317,17 +539,23 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", default="metric", choices=["metric", "c2", "c3"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--n", type=int, default=50000)
     ap.add_argument("--m", type=int, default=1000000)
+    ap.add_argument("--niter", type=int, default=1000)
     ap.add_argument("--m-cpu", dest="m_cpu", type=int, default=20000)
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--lag", type=int, default=0)
     ap.add_argument("--seed", type=int, default=20260101)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-product", action="store_true", help="skip the hb_bayes() end-to-end leg (engine-level e2e only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c2":
+        run_c2(args)
     else:
         run_gpu(args)
 

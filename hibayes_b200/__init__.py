@@ -5,4 +5,4 @@ libhibayes_b200.so (CUDA sm_100a kernels + C++ host driver).  There is no CPU fa
 fails loudly when the library or a CUDA device is missing.
 """
 from ._lib import load_library, last_error, device_count  # noqa: F401
-from .api import Bayes, BedGeno, cutwind, Engine, LdMat, SBayesD, SBayesS, ibrm, ibrm_plan, ldmat, ldmat_plan, read_bed, sbrm, sbrm_plan, synth_geno_host  # noqa: F401
+from .api import Bayes, BedGeno, cutwind, Engine, LdMat, SBayesD, SBayesS, ibrm, ibrm_plan, ldmat, ldmat_plan, read_bed, sbrm, sbrm_plan, synth_geno_host, synth_geno_host_into  # noqa: F401

@@ -12,7 +12,7 @@ MAX_FOLD = 8
 # every symbol include/hibayes_b200.h declares
 SYMBOLS = [
     "hb_last_error", "hb_device_count", "hb_engine_create", "hb_engine_destroy", "hb_engine_load_geno_i8",
-    "hb_engine_load_geno_f64", "hb_engine_synth_geno", "hb_synth_geno_host", "hb_engine_col_stats",
+    "hb_engine_load_geno_f64", "hb_engine_synth_geno", "hb_synth_geno_host", "hb_synth_geno_host_cols", "hb_engine_col_stats",
     "hb_engine_set_snp_info", "hb_engine_build_gram", "hb_engine_get_gram", "hb_engine_set_residual", "hb_engine_get_residual",
     "hb_engine_set_u", "hb_engine_get_u", "hb_engine_set_effects", "hb_engine_get_effects", "hb_engine_get_tracker",
     "hb_engine_set_vargL", "hb_engine_sweep", "hb_engine_set_windows", "hb_engine_accumulate_pip",
@@ -107,6 +107,7 @@ class BayesOut(C.Structure):
         ("n_records_done", C.c_int), ("nzct", C.c_int), ("iters_done", C.c_int),
         ("seconds_sweep", C.c_double), ("seconds_setup", C.c_double),
         ("rounds_total", C.c_longlong), ("tiles_total", C.c_longlong),
+        ("rounds_trace", C.c_void_p), ("sweep_ms_trace", C.c_void_p),
     ]
 
 
@@ -134,6 +135,7 @@ def load_library():
     L.hb_engine_load_geno_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.hb_engine_synth_geno.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
     L.hb_synth_geno_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int64]
+    L.hb_synth_geno_host_cols.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64]
     L.hb_engine_col_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_engine_set_snp_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_engine_build_gram.argtypes = [C.c_void_p]

@@ -31,6 +31,15 @@ def synth_geno_host(n, m, seed, row_offset=0):
     return X
 
 
+def synth_geno_host_into(Xblock, seed, col_offset=0, row_offset=0):
+    """Fills a column block (F-ordered int8 view, n x ncols) of the synthetic matrix: columns col_offset .. of the matrix
+    synth_geno_host() returns.  The call releases the GIL, so blocks can be filled from several threads."""
+    L = _lib.load_library()
+    n, nc = Xblock.shape
+    assert Xblock.dtype == np.int8 and Xblock.strides == (1, n)
+    _lib.check(L.hb_synth_geno_host_cols(Xblock.ctypes.data, n, col_offset, nc, seed, row_offset))
+
+
 class BedGeno:
     """Genotypes held as the image of a SNP-major PLINK .bed file; accepted by Bayes() and LdMat in place of
     a matrix, decoded on the device (hb_engine_load_bed / hb_ldmat_load_bed; read_bed<char>() of
@@ -299,7 +308,9 @@ def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, nite
         "tracker": np.zeros(m, dtype=np.int32), "nzrate_count": np.zeros(m), "wppa_count": np.zeros(nw),
         "nnz_trace": np.zeros(niter, dtype=np.int32), "vara_trace": np.zeros(niter),
         "vare_trace": np.zeros(niter), "varg_trace": np.zeros(niter),
+        "rounds_trace": np.zeros(niter, dtype=np.int32), "sweep_ms_trace": np.zeros(niter, dtype=np.float32),
     }
+    o.rounds_trace, o.sweep_ms_trace = _ptr(dg["rounds_trace"]), _ptr(dg["sweep_ms_trace"])
     o.beta, o.alpha, o.pi, o.pip = _ptr(res["beta"]), _ptr(res["alpha"]), _ptr(res["pi"]), _ptr(res["pip"])
     o.gwas = _ptr(res["gwas"]) if nw else None
     o.g, o.e, o.vr, o.estR, o.epsilon = _ptr(res["g"]), _ptr(res["e"]), _ptr(res["Vr"]), _ptr(res["r"]), _ptr(res["epsilon"])

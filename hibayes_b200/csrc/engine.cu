@@ -679,12 +679,13 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   e->n = cfg->n; e->m = cfg->m;
   e->nsm = prop.multiProcessorCount;
   e->B = cfg->tile_snps > 0 ? cfg->tile_snps : 256;
-  // serial mode is the default for the mixture models; HB_RING=1 keeps the ring of workers for everything
-  e->serial = getenv("HB_RING") && atoi(getenv("HB_RING")) ? 0 : 1;
+  // Scalar side of the mixture models: the ring of NG workers (default; 18.8 ms per sweep at the metric shape) or, with
+  // HB_SERIAL=1, one serial CTA + helper CTAs (hb_serial.cuh; 20.8 ms: its chain never leaves one SM, but the package
+  // traffic into that SM under the streaming load paces it -- DESIGN.md)
+  e->serial = getenv("HB_SERIAL") && atoi(getenv("HB_SERIAL")) ? 1 : 0;
   if (e->B != hbk::kSerialB) e->serial = 0;   // (compiled for tiles of 256 SNPs)
-  // tiles in flight between a tile's dots and its residual update: the loop publish -> AXPY -> dots -> phase P -> package
-  // takes ~17 us, i.e. 7-8 tiles at the chain's pace (serial mode); the ring of workers is paced by its hand-over (5)
-  e->D = cfg->lag_tiles > 0 ? cfg->lag_tiles : (e->serial ? 8 : 5);
+  // tiles in flight between a tile's dots and its residual update (measured: 5 -> 20.0, 6 -> 19.0, 7 -> 18.9, 8 -> 18.8 ms)
+  e->D = cfg->lag_tiles > 0 ? cfg->lag_tiles : 8;
   if (e->B != 64 && e->B != 128 && e->B != 256) { delete e; return hb_set_error("tile_snps must be 64, 128 or 256"); }
   if (e->D > 8) { delete e; return hb_set_error("lag_tiles must be <= 8"); }
   e->NG = 8;   // scalar CTAs (one worker each)
@@ -991,13 +992,17 @@ extern "C" int hb_engine_synth_geno(hb_engine* e, uint64_t seed, int64_t row_off
   return 0;
 }
 
+extern "C" int hb_synth_geno_host_cols(int8_t* X, int n, int col0, int ncols, uint64_t seed, int64_t row_offset);
 extern "C" int hb_synth_geno_host(int8_t* X, int n, int m, uint64_t seed, int64_t row_offset) {
-  if (!X || row_offset % 4 != 0) return hb_set_error("hb_synth_geno_host: bad argument");
+  return hb_synth_geno_host_cols(X, n, 0, m, seed, row_offset);
+}
+extern "C" int hb_synth_geno_host_cols(int8_t* X, int n, int col0, int ncols, uint64_t seed, int64_t row_offset) {
+  if (!X || row_offset % 4 != 0 || col0 < 0 || ncols < 0) return hb_set_error("hb_synth_geno_host: bad argument");
   hb_key_t key = hb_make_key(seed);
-  for (int j = 0; j < m; ++j) {
+  for (int j = col0; j < col0 + ncols; ++j) {
     double t0, t1;
     hb_synth_thresholds(key, (uint32_t)j, &t0, &t1);
-    int8_t* col = X + (size_t)j * n;
+    int8_t* col = X + (size_t)(j - col0) * n;
     for (int i = 0; i < n; i += 4) {
       uint32_t w = hb_synth_word(key, (uint32_t)j, (uint64_t)(row_offset + i) >> 2, t0, t1);
       for (int b = 0; b < 4 && i + b < n; ++b) col[i + b] = (int8_t)((w >> (8 * b)) & 0xff);
@@ -1143,6 +1148,9 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
     sp.inv_dscale = ldexp(1.0, -ex);
   }
   { const char* dbg = getenv("HB_DEBUG"); sp.dbg = dbg ? atoi(dbg) : 0; }
+  // the genotype tiles are streamed with an L2 evict_first hint, so that they do not push the scalar side's small working
+  // set (Gram rows, correction slots, parameters) out of L2: -3 % per sweep; HB_XEVICT=0 switches it off
+  sp.xevict = 1;
   if (const char* xe = getenv("HB_XEVICT")) sp.xevict = atoi(xe);
   if (getenv("HB_PHASES")) sp.dbg |= 64;   // per-phase cycle counters of the serial CTA (they cost ~1 us per tile)
 

@@ -1279,15 +1279,20 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
         }
       }
     };
+    // Solves the chain matrix of the current candidate list (first warp of the secondary half; everybody meets again at
+    // the next barrier of the worker).  In phase P this happens while the tile waits for its turn; a list rebuilt on the
+    // serial path gets its matrix too, so that a tile's changes come out of the same arithmetic (delta = M e0) whether
+    // or not its first speculation held -- which depends on timing -- and two runs agree bit for bit.
+    auto build_matrix = [&]() {
+      if (fast && !dense && k > 0 && k <= 32 && !(p.dbg & 128)) {
+        hb::named_bar_sync(1, NT2);
+        if (!prim && warp == 0) chain_build_matrix(coef, cmat, k, lane);
+        m_ok = true;
+      }
+    };
     select_rows(act ? ((base0 - cspec) + addback) * ((base0 - cspec) + addback) : 0.0);
     compact();
-    if (fast && !dense && k > 0 && k <= 32 && !(p.dbg & 128)) {
-      // solve the chain matrix while the tile waits for its turn (first warp of the secondary half; everybody
-      // meets again at the barrier that opens phase S)
-      hb::named_bar_sync(1, NT2);
-      if (!prim && warp == 0) chain_build_matrix(coef, cmat, k, lane);
-      m_ok = true;
-    }
+    build_matrix();
     HB_PHASE(1);
     if (tid == 0) HB_TRACE(t, 1);
     // ---- phase S: the previous tile is final once its corrections for this tile are here
@@ -1354,6 +1359,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
       if (hb::named_bar_or(1, NT2, cls0 != cls)) {
         cls = cls0;
         compact();
+        build_matrix();
         if (cand && prim) cs.rhs0[myrank] = rhs0;
         hb::named_bar_sync(1, NT2);
         ++respec;
@@ -1414,6 +1420,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
       if (hb::named_bar_or(1, NT2, dead)) { dead = true; break; }
       // a class differed: speculate again with the corrected classes
       compact();
+      build_matrix();
     }
     if (dead) break;
     rounds_total += nrounds;

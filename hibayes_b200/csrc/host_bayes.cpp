@@ -363,6 +363,8 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
       int tsz = 0;
       hb_engine_describe(E, nullptr, nullptr, &tsz, nullptr, nullptr, nullptr);
       o->rounds_total += so.rounds;
+      if (o->rounds_trace) o->rounds_trace[iter] = so.rounds;
+      if (o->sweep_ms_trace) { float a0, a1, a2; hb_engine_last_sweep_ms(E, &a0, &a1, &a2); o->sweep_ms_trace[iter] = a0 + a1 + a2; }
       o->tiles_total += (m + tsz - 1) / std::max(1, tsz);
     }
 

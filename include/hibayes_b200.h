@@ -77,6 +77,8 @@ int hb_engine_load_bed(hb_engine* e, const uint8_t* file, size_t len, int nid, c
  * hb_synth_geno_host() writes the same matrix on the host (column-major int8). */
 int hb_engine_synth_geno(hb_engine* e, uint64_t seed, int64_t row_offset);
 int hb_synth_geno_host(int8_t* X, int n, int m, uint64_t seed, int64_t row_offset);
+/* columns col0 .. col0 + ncols - 1 of the same matrix (X: n x ncols); lets a caller fill a large matrix from several threads */
+int hb_synth_geno_host_cols(int8_t* X, int n, int col0, int ncols, uint64_t seed, int64_t row_offset);
 
 /* Column statistics, Bayes.cpp:310-317: xpx_j = sum x^2, sumx_j = sum x (exact integers
  * returned as doubles; the caller forms var(x_j)).  Local rows only when world > 1. */
@@ -216,6 +218,9 @@ typedef struct {
   /* diagnostics of the scalar chain: speculation rounds and tiles summed over the sweeps (rounds > tiles means that
    * classes had to be re-decided after a first look), and the sweeps' device time per kernel */
   long long rounds_total, tiles_total;
+  /* optional per-iteration traces (niter entries each, NULL = not wanted): speculation rounds of the sweep and the
+   * device time of the iteration's kernels in milliseconds */
+  int32_t* rounds_trace; float* sweep_ms_trace;
 } hb_bayes_out;
 
 int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o);

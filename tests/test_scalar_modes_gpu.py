@@ -1,6 +1,7 @@
-"""GPU parity tests of the serial-CTA scalar side (csrc/hb_serial.cuh; the default for the mixture models at
-tiles of 256 SNPs) against the CPU oracle, against the ring of workers it replaces, in the flip-heavy regime where
-classes have to be re-decided tile after tile, and at the metric's number of rows (n = 50 000)."""
+"""GPU parity tests of the two scalar sides of the sweep -- the ring of workers (default) and the serial CTA + helpers
+(csrc/hb_serial.cuh, HB_SERIAL=1; tiles of 256 SNPs) -- against the CPU oracle and against each other: every lag, every
+mixture model, more candidates than a package holds, the flip-heavy regime where classes have to be re-decided tile
+after tile, and the metric's number of rows (n = 50 000, the production tiling)."""
 import os
 
 import numpy as np
@@ -11,6 +12,20 @@ from tests.test_gpu_parity import _compare
 from tests.util_demo import synth
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _serial_mode():
+    # the engine reads HB_SERIAL when it is created: every hb.Bayes() of this file runs the serial-CTA scalar side
+    # unless a test switches it off for a comparison
+    old = os.environ.get("HB_SERIAL")
+    os.environ["HB_SERIAL"] = "1"
+    yield
+    if old is None:
+        os.environ.pop("HB_SERIAL", None)
+    else:
+        os.environ["HB_SERIAL"] = old
+
 
 PI_R = [0.95, 0.02, 0.02, 0.01]
 FOLD_R = [0, 1e-4, 1e-3, 1e-2]
@@ -58,7 +73,7 @@ def test_serial_cta_and_ring_of_workers_agree():
     y, X = synth(3000, 4096, seed=5, n_causal=40)
     kw = dict(niter=8, nburn=2, thin=2, seed=2024)
     a = hb.Bayes(y, X, "BayesR", PI_R, fold=FOLD_R, **kw)
-    with _env(HB_RING=1):
+    with _env(HB_SERIAL=0):
         b = hb.Bayes(y, X, "BayesR", PI_R, fold=FOLD_R, **kw)
     # same classes; the effects agree to rounding (a repaired tile ends with the step-by-step chain, an unrepaired one with
     # the solved chain matrix, and the two modes do not repair the same tiles)
@@ -76,17 +91,21 @@ def test_many_candidates_per_tile(oracle):
     _compare(got, ref)
 
 
-def test_flip_heavy_chain_against_the_oracle(oracle):
+@pytest.mark.parametrize("mode", ["ring", "serial"])
+def test_flip_heavy_chain_against_the_oracle(oracle, mode):
     """Large effect variances (folds x 64) and h2 = 0.9 at n = 20 000: the changes inside a tile move the other SNPs of the
     tile across their class boundaries, so the speculation misses and tiles need repair rounds (rounds > tiles)."""
     y, X = synth(20000, 4096, seed=33, n_causal=400, h2=0.9)
     fold = [0.0] + [64 * f for f in FOLD_R[1:]]
     kw = dict(niter=30, nburn=10, thin=5, seed=808)
     ref = oracle.bayes(y, X, "BayesR", PI_R, fold=fold, **kw)
-    got = hb.Bayes(y, X, "BayesR", PI_R, fold=fold, **kw)
+    with _env(HB_SERIAL=int(mode == "serial")):
+        got = hb.Bayes(y, X, "BayesR", PI_R, fold=fold, **kw)
     _compare(got, ref)
     assert got["diag"]["rounds_total"] > got["diag"]["tiles_total"], (got["diag"]["rounds_total"], got["diag"]["tiles_total"])
-    with _env(HB_RING=1):
+    if mode == "ring":
+        return
+    with _env(HB_SERIAL=0):
         ring = hb.Bayes(y, X, "BayesR", PI_R, fold=fold, **kw)
     # (not bit for bit here: a repaired tile ends with the step-by-step chain, an unrepaired one with the solved chain
     # matrix, and the two modes do not repair the same tiles; the classes are the same, the effects agree to rounding)
@@ -94,7 +113,8 @@ def test_flip_heavy_chain_against_the_oracle(oracle):
     assert np.allclose(ring["alpha"], got["alpha"], rtol=1e-9, atol=1e-14)
 
 
-def test_metric_rows_against_the_oracle(oracle):
+@pytest.mark.parametrize("mode", ["ring", "serial"])
+def test_metric_rows_against_the_oracle(oracle, mode):
     """The production configuration of the metric (n = 50 000 rows: 131 slabs of 384 rows, tiles of 256, default lag)
     on m = 65 536 SNPs for three sweeps: classes bit-exact, effects to 1e-5."""
     n, m = 50000, 65536
@@ -105,6 +125,7 @@ def test_metric_rows_against_the_oracle(oracle):
     y = gv * np.sqrt(0.5 / gv.var()) + rng.normal(scale=np.sqrt(0.5), size=n)
     kw = dict(niter=3, nburn=1, thin=1, seed=20260101)
     ref = oracle.bayes(y, X, "BayesR", PI_R, fold=FOLD_R, **kw)
-    got = hb.Bayes(y, X, "BayesR", PI_R, fold=FOLD_R, **kw)
+    with _env(HB_SERIAL=int(mode == "serial")):
+        got = hb.Bayes(y, X, "BayesR", PI_R, fold=FOLD_R, **kw)
     _compare(got, ref)
     assert got["diag"]["tiles_total"] == 3 * 256
