@@ -24,6 +24,9 @@ SYMBOLS = [
     "hb_engine_load_bed", "hb_ldmat_create", "hb_ldmat_destroy", "hb_ldmat_load_i8", "hb_ldmat_load_bed", "hb_ldmat_stats",
     "hb_ldmat_dense", "hb_ldmat_sparse", "hb_ldmat_sparse_get", "hb_ldmat_set_panel_cols", "hb_ldmat_last_ms", "hb_bed_decode",
     "hb_test_bed_decode_snp", "hb_engine_predict_samples", "hb_test_ld_entries", "hb_test_ld_stats", "hb_test_limb_dot", "hb_cutwind_by_bp", "hb_cutwind_by_num",
+    "hb_engine_device_state", "hb_fx_create", "hb_fx_destroy", "hb_fx_dot", "hb_fx_self_dot", "hb_fx_axpy", "hb_fx_level_sums",
+    "hb_fx_level_apply", "hb_fx_eps_set_counts", "hb_fx_eps_rhs", "hb_fx_eps_set_rhs", "hb_fx_eps_sample", "hb_fx_eps_accumulate",
+    "hb_fx_eps_get", "hb_fx_describe",
 ]
 
 
@@ -108,6 +111,8 @@ class BayesOut(C.Structure):
         ("seconds_sweep", C.c_double), ("seconds_setup", C.c_double),
         ("rounds_total", C.c_longlong), ("tiles_total", C.c_longlong),
         ("rounds_trace", C.c_void_p), ("sweep_ms_trace", C.c_void_p),
+        ("vr_store", C.c_void_p), ("estR_store", C.c_void_p), ("veps_store", C.c_void_p), ("J_store", C.c_void_p),
+        ("epsilon_store", C.c_void_p),
     ]
 
 

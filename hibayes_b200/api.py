@@ -257,7 +257,12 @@ def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, nite
         if Rf.shape[0] != n:
             raise RuntimeError("Number of individuals does not match for environmental random effects.")
         nr = Rf.shape[1]
+        if Rf.size and Rf.min() < 0:
+            raise RuntimeError("level codes of the environmental random effects must be >= 0")
         nlev = np.ascontiguousarray(Rf.max(axis=0) + 1, dtype=np.int32)
+        if comm is not None and comm.world > 1:   # the levels of a term are the same set on every rank
+            allmax = np.frombuffer(comm.allgather_bytes(nlev.astype(np.int64).tobytes()), dtype=np.int64).reshape(comm.world, nr)
+            nlev = np.ascontiguousarray(allmax.max(axis=0), dtype=np.int32)
         n_levels = int(nlev.sum())
         a.Rlev, a.nlev = _ptr(Rf), _ptr(nlev)
         keep += [Rf, nlev]
@@ -268,6 +273,8 @@ def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, nite
     nw = 0
     if windindx is not None:
         w = np.ascontiguousarray(windindx, dtype=np.int32)
+        if w.shape[0] != m:
+            raise RuntimeError("windindx should have one entry per SNP.")
         nw = int(w.max())
         a.windindx = _ptr(w)
         keep.append(w)
@@ -283,6 +290,14 @@ def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, nite
         gv = np.ascontiguousarray(G.data, dtype=np.float64)
         yj = np.ascontiguousarray(epsl_y_J, dtype=np.float64)
         ne, qe = ei.shape[0], G.shape[0]
+        if G.shape[0] != G.shape[1]:
+            raise RuntimeError("variance-covariance matrix should be in square.")   # Bayes.cpp:263
+        if G.indptr[-1] >= 2 ** 31:
+            raise RuntimeError("epsl_Gi has too many stored entries for 32-bit column pointers")
+        if ne and (ei.min() < 1 or ei.max() > qe):
+            raise RuntimeError("epsl_index should be 1-based positions inside epsl_Gi")
+        if ne > n or yj.shape[0] != n:
+            raise RuntimeError("epsl_y_J / epsl_index do not match the number of individuals")
         a.epsl_y_J, a.epsl_index, a.Gi_colptr, a.Gi_rowidx, a.Gi_val = _ptr(yj), _ptr(ei), _ptr(cp), _ptr(ri), _ptr(gv)
         keep += [ei, cp, ri, gv, yj]
     a.ne, a.qe = ne, qe
@@ -311,6 +326,12 @@ def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, nite
         "rounds_trace": np.zeros(niter, dtype=np.int32), "sweep_ms_trace": np.zeros(niter, dtype=np.float32),
     }
     o.rounds_trace, o.sweep_ms_trace = _ptr(dg["rounds_trace"]), _ptr(dg["sweep_ms_trace"])
+    if nr:   # MCMCsamples of the other terms (Bayes.cpp:987-1020)
+        mc["Vr"], mc["r"] = np.zeros((nr, nrec), order="F"), np.zeros((n_levels, nrec), order="F")
+        o.vr_store, o.estR_store = _ptr(mc["Vr"]), _ptr(mc["r"])
+    if qe:
+        mc["Veps"], mc["J"], mc["epsilon"] = np.zeros(nrec), np.zeros(nrec), np.zeros((qe, nrec), order="F")
+        o.veps_store, o.J_store, o.epsilon_store = _ptr(mc["Veps"]), _ptr(mc["J"]), _ptr(mc["epsilon"])
     o.beta, o.alpha, o.pi, o.pip = _ptr(res["beta"]), _ptr(res["alpha"]), _ptr(res["pi"]), _ptr(res["pip"])
     o.gwas = _ptr(res["gwas"]) if nw else None
     o.g, o.e, o.vr, o.estR, o.epsilon = _ptr(res["g"]), _ptr(res["e"]), _ptr(res["Vr"]), _ptr(res["r"]), _ptr(res["epsilon"])

@@ -1076,6 +1076,15 @@ extern "C" int hb_engine_set_residual(hb_engine* e, const double* y) { if (!e ||
 extern "C" int hb_engine_get_residual(hb_engine* e, double* y) { if (!e || !y) return hb_set_error("null argument"); return fetch_vec(e, y, e->r, e->n); }
 extern "C" int hb_engine_set_u(hb_engine* e, const double* u) { if (!e || !u) return hb_set_error("null argument"); return copy_vec(e, e->u, u, e->n); }
 extern "C" int hb_engine_get_u(hb_engine* e, double* u) { if (!e || !u) return hb_set_error("null argument"); return fetch_vec(e, u, e->u, e->n); }
+extern "C" int hb_engine_device_state(hb_engine* e, double** r_dev, double** u_dev, void** cuda_stream, int* device, int* n) {
+  if (!e) return hb_set_error("hb_engine_device_state: null argument");
+  if (r_dev) *r_dev = e->r;
+  if (u_dev) *u_dev = e->u;
+  if (cuda_stream) *cuda_stream = (void*)e->stream;
+  if (device) *device = e->cfg.device;
+  if (n) *n = e->n;
+  return 0;
+}
 extern "C" int hb_engine_set_effects(hb_engine* e, const double* g) { if (!e || !g) return hb_set_error("null argument"); return copy_vec(e, e->g, g, e->m); }
 extern "C" int hb_engine_get_effects(hb_engine* e, double* g) { if (!e || !g) return hb_set_error("null argument"); return fetch_vec(e, g, e->g, e->m); }
 extern "C" int hb_engine_set_vargL(hb_engine* e, const double* v) { if (!e || !v) return hb_set_error("null argument"); return copy_vec(e, e->vargL, v, e->m); }

@@ -61,6 +61,11 @@ struct EngineGuard {
   ~EngineGuard() { hb_engine_destroy(e); }
 };
 
+struct FxGuard {
+  hb_fx* f = nullptr;
+  ~FxGuard() { hb_fx_destroy(f); }
+};
+
 double seconds_since(const std::chrono::steady_clock::time_point& t0) {
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
@@ -78,8 +83,6 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
   if (world > 1) {
     if (!a->allreduce_sum_f64 || !a->allreduce_sum_i32_dev || !a->allgather_bytes || a->n_total < n)
       return hb_set_error("hb_bayes: world = %d needs n_total and the three collectives", world);
-    if (a->nc || a->nr || a->ne)
-      return hb_set_error("hb_bayes: covariates, environmental random effects and the single-step term are not sharded in this build");
   }
   // sum over ranks, in place (no-op on one rank)
   auto allsum = [&](double* buf, size_t cnt) -> int {
@@ -141,17 +144,28 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
     R_off[i + 1] = n_levels;
   }
   std::vector<double> estR(n_levels, 0.0), estR_tmp(n_levels, 0.0), r_rhs(n_levels, 0.0), r_cnt(n_levels, 0.0),
-      estRsum(n_levels, 0.0), diff(nr ? n : 0);
+      estRsum(n_levels, 0.0), ldiff(n_levels, 0.0);
   for (int i = 0; i < nr; ++i)
     for (int k = 0; k < n; ++k) r_cnt[R_off[i] + a->Rlev[(size_t)i * n + k]] += 1.0;
   // ---- single-step term :235-275
-  const int ne = a->ne, qe = ne ? a->qe : 0;
+  const int ne = a->ne, qe = (a->Gi_colptr != nullptr || ne) ? a->qe : 0;
   double veps = 0, vepstmp = 0, JtJ = 0, epsl_J_beta = 0, vepssum = 0, Jsum = 0;
   std::vector<double> e_estR(qe, 0.0), e_tmp(qe, 0.0), e_rhs(qe, 0.0), e_cnt(qe, 0.0), e_sum(qe, 0.0);
-  if (ne) {
-    if (!a->Gi_colptr) return hb_set_error("variance-covariance matrix should be provided for epsilon term.");
+  const bool have_eps = (a->Gi_colptr != nullptr && qe > 0);   // (a rank of a sharded run may hold none of the ne rows)
+  if (ne && !a->Gi_colptr) return hb_set_error("variance-covariance matrix should be provided for epsilon term.");
+  if (have_eps) {
+    if (!a->epsl_y_J) return hb_set_error("epsl_y_J should be provided for epsilon term.");
     JtJ = ddot(n, a->epsl_y_J, a->epsl_y_J);
-    for (int i = 0; i < ne; ++i) e_cnt[a->epsl_index[i] - 1] += 1.0;
+    for (int i = 0; i < ne; ++i) {
+      if (a->epsl_index[i] < 1 || a->epsl_index[i] > qe) return hb_set_error("epsl_index out of range.");
+      e_cnt[a->epsl_index[i] - 1] += 1.0;
+    }
+  }
+  // with the individuals sharded over ranks these set-up sums run over all ranks' rows
+  if (world > 1) {
+    if (nc) HBCHK(allsum(cpc.data(), nc));
+    if (nr) HBCHK(allsum(r_cnt.data(), n_levels));
+    if (have_eps) { HBCHK(allsum(&JtJ, 1)); HBCHK(allsum(e_cnt.data(), qe)); }
   }
 
   int NnzSnp = 0;
@@ -242,11 +256,26 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
 
   // ---- state :469-471
   double mu_, mu = ymean;
-  std::vector<double> yadj(n), u_host;
+  std::vector<double> yadj(n);
   for (int i = 0; i < n; ++i) yadj[i] = a->y[i] - mu;
   HBCHK(hb_engine_set_residual(E, yadj.data()));
-  const bool host_effects = (nc > 0 || nr > 0 || ne > 0);
-  if (ne) u_host.assign(n, 0.0);
+  // non-SNP effects (covariates :484-494, env. random effects :496-516, single-step J + epsilon :554-584) run on the
+  // device on the engine's own residual and u (csrc/effects.cu): the vectors never cross PCIe inside the loop
+  const bool side_effects = (nc > 0 || nr > 0 || have_eps);
+  FxGuard fxg;
+  if (side_effects) {
+    hb_fx_desc fd;
+    memset(&fd, 0, sizeof fd);
+    fd.n = n; fd.nc = nc; fd.C = a->C; fd.nr = nr; fd.Rlev = a->Rlev; fd.nlev = a->nlev;
+    if (have_eps) {
+      fd.J = a->epsl_y_J; fd.ne = ne; fd.qe = qe; fd.epsl_index = a->epsl_index;
+      fd.Gi_colptr = a->Gi_colptr; fd.Gi_rowidx = a->Gi_rowidx; fd.Gi_val = a->Gi_val;
+    }
+    fd.seed = a->seed;
+    HBCHK(hb_fx_create(E, &fd, &fxg.f));
+    if (have_eps) HBCHK(hb_fx_eps_set_counts(fxg.f, e_cnt.data()));
+  }
+  hb_fx* FX = fxg.f;
   double sum_r = acc_sum(yadj.data(), n), sum_r2 = ddot(n, yadj.data(), yadj.data());
   if (world > 1) { double b2[2] = {sum_r, sum_r2}; HBCHK(allsum(b2, 2)); sum_r = b2[0]; sum_r2 = b2[1]; }
 
@@ -262,88 +291,64 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
     mu -= mu_;
     double mu_shift = mu_;
     double rnorm2 = sum_r2 + 2.0 * mu_ * sum_r + ntot * mu_ * mu_;
-    if (host_effects) {
-      HBCHK(hb_engine_get_residual(E, yadj.data()));
-      for (int i = 0; i < n; ++i) yadj[i] += mu_ * 1.0;
+    if (side_effects) {
+      HBCHK(hb_fx_axpy(FX, HB_FX_ONES, 0, mu_, 0.0));   // yadj += mu_ (:482)
       mu_shift = 0.0;
-      if (ne) HBCHK(hb_engine_get_u(E, u_host.data()));
       // covariates :484-494
       for (int i = 0; i < nc; ++i) {
-        const double* dci = a->C + (size_t)i * n;
         const double oldgi = beta[i], v = cpc[i];
-        double rhs = ddot(n, dci, yadj.data());
+        double rhs;
+        HBCHK(hb_fx_dot(FX, HB_FX_COV, i, &rhs));
+        HBCHK(allsum(&rhs, 1));
         rhs += v * oldgi;
         const double gi = rhs / v + sqrt(vare_ / v) * hb_draw_z(KEY, HB_DOM_COV, it, (uint32_t)i, 0, 0);
-        daxpy(n, oldgi - gi, dci, yadj.data());
+        HBCHK(hb_fx_axpy(FX, HB_FX_COV, i, oldgi - gi, 0.0));
         beta[i] = gi;
       }
       // environmental random effects :496-516
       for (int i = 0; i < nr; ++i) {
         const int off = R_off[i], qr = a->nlev[i];
-        const int32_t* lev = a->Rlev + (size_t)i * n;
-        for (int q = 0; q < qr; ++q) r_rhs[off + q] = 0.0;
-        for (int k = 0; k < n; ++k) r_rhs[off + lev[k]] += yadj[k];
-        for (int q = 0; q < qr; ++q) r_rhs[off + q] += r_cnt[off + q] * estR[off + q];
+        HBCHK(hb_fx_level_sums(FX, i, r_rhs.data() + off));                    // Z' yadj
+        HBCHK(allsum(r_rhs.data() + off, qr));
+        for (int q = 0; q < qr; ++q) r_rhs[off + q] += r_cnt[off + q] * estR[off + q];   // + Z'Z estR
         for (int q = 0; q < qr; ++q) {
           const double l = r_cnt[off + q] + vare_ / vrtmp[i];
           estR_tmp[off + q] = r_rhs[off + q] / l + sqrt(vare_ / l) * hb_draw_z(KEY, HB_DOM_RAND, it, (uint32_t)(off + q), 0, 0);
         }
-        for (int k = 0; k < n; ++k) diff[k] = estR[off + lev[k]] - estR_tmp[off + lev[k]];
-        daxpy(n, 1.0, diff.data(), yadj.data());
+        for (int q = 0; q < qr; ++q) ldiff[off + q] = estR[off + q] - estR_tmp[off + q];
+        HBCHK(hb_fx_level_apply(FX, i, ldiff.data() + off));
         vrtmp[i] = (ddot(qr, estR_tmp.data() + off, estR_tmp.data() + off) + s2r * dfr) /
                    hb_draw_chisq(KEY, HB_DOM_ITER, it, HB_IT_VR0 + (uint32_t)i, 0, qr + dfr);
         vrv[i] = arma_var(estR_tmp.data() + off, qr);
         for (int q = 0; q < qr; ++q) estR[off + q] = estR_tmp[off + q];
       }
       // single-step J + epsilon :554-584 (sparse Gauss-Seidel sampler, solver.cpp:131-140)
-      if (ne) {
-        double oldgi = epsl_J_beta, v = JtJ;
-        double rhs = ddot(n, a->epsl_y_J, yadj.data());
+      if (have_eps) {
+        const double oldgi = epsl_J_beta, v = JtJ;
+        double rhs;
+        HBCHK(hb_fx_dot(FX, HB_FX_J, 0, &rhs));
+        HBCHK(allsum(&rhs, 1));
         rhs += v * oldgi;
         const double gi = rhs / v + sqrt(vare_ / v) * hb_draw_z(KEY, HB_DOM_ITER, it, HB_IT_J, 0, 0);
-        double gi_ = oldgi - gi;
-        daxpy(n, gi_, a->epsl_y_J, yadj.data());
-        gi_ *= -1;
-        daxpy(n, gi_, a->epsl_y_J, u_host.data());
+        HBCHK(hb_fx_axpy(FX, HB_FX_J, 0, oldgi - gi, -(oldgi - gi)));
         epsl_J_beta = gi;
         const double ratio = vare_ / vepstmp;
-        for (int q = 0; q < qe; ++q) e_rhs[q] = 0.0;
-        for (int i = 0; i < ne; ++i) e_rhs[a->epsl_index[i] - 1] += yadj[n - ne + i];
-        for (int q = 0; q < qe; ++q) e_rhs[q] += e_cnt[q] * e_tmp[q];
-        for (int i = 0; i < qe; ++i) {
-          double aii = e_cnt[i], Ax = 0.0;
-          bool have_diag = false;
-          for (int p = a->Gi_colptr[i]; p < a->Gi_colptr[i + 1]; ++p) {
-            const int rix = a->Gi_rowidx[p];
-            const double aval = a->Gi_val[p] * ratio + (rix == i ? e_cnt[i] : 0.0);
-            if (rix == i) { aii = aval; have_diag = true; }
-            Ax += aval * e_tmp[rix];
-          }
-          if (!have_diag) Ax += e_cnt[i] * e_tmp[i];
-          const double invlhs = 1.0 / aii;
-          const double uu = invlhs * (e_rhs[i] - Ax) + e_tmp[i];
-          e_tmp[i] = uu + sqrt(invlhs * vare_) * hb_draw_z(KEY, HB_DOM_EPS, it, (uint32_t)i, 0, 0);
+        if (world > 1) {   // Z'yadj.tail(ne) over all ranks' records (every rank then runs the same sampler)
+          if (ne) HBCHK(hb_fx_eps_rhs(FX, e_rhs.data())); else std::fill(e_rhs.begin(), e_rhs.end(), 0.0);
+          HBCHK(allsum(e_rhs.data(), qe));
+          HBCHK(hb_fx_eps_set_rhs(FX, e_rhs.data()));
+        } else {
+          HBCHK(hb_fx_eps_rhs(FX, nullptr));
         }
-        for (int q = 0; q < qe; ++q) e_estR[q] -= e_tmp[q];
-        for (int i = 0; i < ne; ++i) {
-          const double d = e_estR[a->epsl_index[i] - 1];
-          yadj[n - ne + i] += d;
-          u_host[n - ne + i] -= d;
-        }
-        vepstmp = 0.0;
-        for (int c = 0; c < qe; ++c) {
-          double colsum = 0.0;
-          for (int p = a->Gi_colptr[c]; p < a->Gi_colptr[c + 1]; ++p) colsum += a->Gi_val[p] * e_tmp[a->Gi_rowidx[p]];
-          vepstmp += colsum * e_tmp[c];
-        }
-        vepstmp += s2vara_ * dfvara_;
-        vepstmp /= hb_draw_chisq(KEY, HB_DOM_ITER, it, HB_IT_VEPS, 0, dfvara_ + qe);
-        for (int q = 0; q < qe; ++q) e_estR[q] = e_tmp[q];
+        double quad;
+        HBCHK(hb_fx_eps_sample(FX, iter, vare_, ratio, &quad));
+        vepstmp = (quad + s2vara_ * dfvara_) / hb_draw_chisq(KEY, HB_DOM_ITER, it, HB_IT_VEPS, 0, dfvara_ + qe);
         veps = vepstmp;
-        HBCHK(hb_engine_set_u(E, u_host.data()));
       }
-      HBCHK(hb_engine_set_residual(E, yadj.data()));
-      rnorm2 = ddot(n, yadj.data(), yadj.data());
+      double rn2;
+      HBCHK(hb_fx_dot(FX, HB_FX_RESID, 0, &rn2));
+      HBCHK(allsum(&rn2, 1));
+      rnorm2 = rn2;
     }
 
     // SNP sweep :586-816 on the device
@@ -445,9 +450,16 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
       double vt = vara_ + vare_;
       for (int i = 0; i < nr; ++i) { vt += vrv[i]; vrsum[i] += vrv[i]; }
       for (int q = 0; q < n_levels; ++q) estRsum[q] += estR[q];
-      if (ne) {
+      if (have_eps) {
         vepssum += veps; Jsum += epsl_J_beta;
-        for (int q = 0; q < qe; ++q) e_sum[q] += e_estR[q];
+        HBCHK(hb_fx_eps_accumulate(FX));
+        if (o->veps_store) o->veps_store[count] = veps;
+        if (o->J_store) o->J_store[count] = epsl_J_beta;
+        if (o->epsilon_store) HBCHK(hb_fx_eps_get(FX, o->epsilon_store + (size_t)count * qe, nullptr));
+      }
+      if (nr) {
+        if (o->vr_store) for (int i = 0; i < nr; ++i) o->vr_store[(size_t)count * nr + i] = vrv[i];
+        if (o->estR_store) memcpy(o->estR_store + (size_t)count * n_levels, estR.data(), sizeof(double) * n_levels);
       }
       hsqsum += vara_ / vt;
       if (o->hsq_store) o->hsq_store[count] = vara_ / vt;
@@ -491,7 +503,8 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
   }
   if (fixpi && o->pi_store)
     for (int c = 0; c < count; ++c) { o->pi_store[(size_t)c * n_fold] = Pi[0]; o->pi_store[(size_t)c * n_fold + 1] = Pi[1]; }
-  if (ne) {
+  if (have_eps) {
+    HBCHK(hb_fx_eps_get(FX, nullptr, e_sum.data()));
     o->Veps = vepssum / rc; o->J = Jsum / rc;
     if (o->e) {
       for (int k = 0; k < n; ++k) o->e[k] -= o->J * a->epsl_y_J[k];

@@ -1,18 +1,26 @@
-// sbayes.cu -- device engine for the dense-LD summary-statistics sweep of SBayesD()
-// (/root/reference/src/SBayesD.cpp:253-456).
+// sbayes.cu -- device engine for the summary-statistics sweeps of SBayesD() (dense LD,
+// /root/reference/src/SBayesD.cpp:253-456) and SBayesS() (sparse LD, src/SBayesS.cpp:279-525).
 //
 // The reference walks the SNPs in order: rhs = r_hat[i] (+ xpx_i g_i), the same conditional draw as Bayes(), and,
-// only if the effect changed, r_hat += (g_old - g_new) * n * LD[:, i] (a length-m daxpy on column i, :351-356).
-// Here one cooperative launch does a whole sweep, tile by tile (B = 256 SNPs):
-//   phase A (CTA 0)   the tile's decisions.  The dependence of r_hat[i] on the earlier changes of the same tile is
-//                     n * LD[i, c] -- the LD block itself plays the role the Gram block plays in the genotype sweep
-//                     (hb_sweep.cuh): classes are speculated, the changed SNPs are chained by one warp in SNP order,
-//                     every SNP is re-evaluated with its exact right-hand side, a mismatch restarts the round.
-//   phase B (all CTAs) the column updates of the tile's changed SNPs, applied to every row of r_hat in SNP order
-//                     (coalesced over rows; deterministic).
-// Two grid barriers per tile.  This is the first correct path for this row of SURVEY.md 8(a14): HBM traffic is the
-// columns of the changed SNPs (m * 8 bytes each), the decisions of a tile are not yet overlapped with the updates
-// of the previous one.
+// only if the effect changed, r_hat += (g_old - g_new) * n * LD[:, i] -- a length-m daxpy on column i of the dense
+// matrix (SBayesD.cpp:351-356) or a walk over the stored entries of column i of the sp_mat (SBayesS.cpp:292-296,
+// 403-407).  Here one cooperative launch does a whole sweep, tile by tile (B = 256 SNPs), with ONE grid barrier per
+// tile:
+//   CTA 0, step t       first brings the rows of tile t up to date with the changes of tile t-1 (the 256 x 256 LD block
+//                       between the two tiles), then takes the tile's decisions: the dependence of r_hat[i] on the
+//                       earlier changes of the same tile is n * LD[i, c] -- the diagonal LD block plays the role the
+//                       Gram block plays in the genotype sweep (hb_sweep.cuh): classes are speculated, the changed
+//                       SNPs are chained by one warp in SNP order, every SNP is re-evaluated with its exact right-hand
+//                       side, a mismatch restarts the round.  The changed SNPs go to a double-buffered list.
+//   other CTAs, step t  the column updates of tile t-1's changed SNPs on every other row of r_hat, in SNP order
+//                       (deterministic, no atomics) -- overlapped with CTA 0's decisions for tile t.
+// Storage of LD on the device:
+//   dense (SBayesD)     the m x m fp64 matrix as given; a column update streams m * 8 bytes, coalesced over rows.
+//   CSC (SBayesS)       colptr / rowidx / val as given (8 + 4 bytes per stored entry, nothing for the zeros), plus, built
+//                       on the device at load, the dense 256 x 256 blocks CTA 0 needs (diagonal and first sub-diagonal
+//                       block of every tile: 4 KB per SNP) and, for every column, where each worker's row range starts
+//                       in it.  A worker owns a contiguous row range and walks the stored entries of a changed column
+//                       that fall into it -- the reference's `for (it = ldm.begin_col(i); ...) r_hat[it.row()] += ...`.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>

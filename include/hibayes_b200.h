@@ -160,6 +160,48 @@ int hb_engine_last_sweep_ms(hb_engine* e, float* prep_ms, float* sweep_ms, float
 int hb_engine_describe(hb_engine* e, int* n_slabs, int* rows_per_slab, int* tile_snps, int* lag_tiles,
                        uint64_t* geno_bytes, uint64_t* gram_bytes);
 
+/* ------------------------------------------------------------------ non-SNP effects on the device (csrc/effects.cu)
+ * The steps of an MCMC iteration of Bayes() around the SNP sweep, on the engine's own residual (yadj) and genetic values
+ * (u), so that neither vector leaves the device inside the loop:
+ *   covariates            /root/reference/src/Bayes.cpp:484-494
+ *   env. random effects   Bayes.cpp:496-516
+ *   single-step J         Bayes.cpp:555-562
+ *   single-step epsilon   Bayes.cpp:563-582 with the sparse Gauss-Seidel sampler Gibbs(sp_mat), src/solver.cpp:131-140
+ * The host driver (hb_bayes) owns the scalar draws and, when rows are sharded over ranks, all-reduces the returned sums. */
+int hb_engine_device_state(hb_engine* e, double** r_dev, double** u_dev, void** cuda_stream, int* device, int* n);
+
+typedef struct hb_fx hb_fx;
+typedef struct {
+  int n;                                             /* this rank's rows (= the engine's n) */
+  int nc; const double* C;                           /* n x nc column-major */
+  int nr; const int32_t* Rlev; const int32_t* nlev;  /* n x nr 0-based level codes, levels per term */
+  const double* J;                                   /* NULL or n (epsl_y_J) */
+  int ne, qe;                                        /* the LAST ne rows carry an epsilon; epsl_Gi is qe x qe (CSC) */
+  const int32_t* epsl_index;                         /* ne entries, 1-based */
+  const int32_t* Gi_colptr; const int32_t* Gi_rowidx; const double* Gi_val;
+  uint64_t seed;
+} hb_fx_desc;
+enum { HB_FX_COV = 0, HB_FX_J = 1, HB_FX_RESID = 2, HB_FX_ONES = 3 };
+int hb_fx_create(hb_engine* e, const hb_fx_desc* d, hb_fx** out);
+void hb_fx_destroy(hb_fx* f);
+/* x'yadj over this rank's rows, x = covariate idx / J / yadj itself; x'x */
+int hb_fx_dot(hb_fx* f, int kind, int idx, double* out);
+int hb_fx_self_dot(hb_fx* f, int kind, int idx, double* out);
+/* yadj += a_r x, u += a_u x  (HB_FX_ONES: x = 1, the intercept shift of Bayes.cpp:482) */
+int hb_fx_axpy(hb_fx* f, int kind, int idx, double a_r, double a_u);
+/* Z'yadj of random term `term` (nlev[term] sums, this rank's rows); yadj[k] += diff[level of row k] */
+int hb_fx_level_sums(hb_fx* f, int term, double* sums);
+int hb_fx_level_apply(hb_fx* f, int term, const double* diff);
+/* epsilon: records per entry (Z'Z, all ranks); RHS part Z'yadj.tail(ne) (host copy optional; set_rhs after an all-reduce);
+ * one Gauss-Seidel sampling pass + the update of yadj/u + eps' Gi eps (Bayes.cpp:565-577); record sums */
+int hb_fx_eps_set_counts(hb_fx* f, const double* cnt);
+int hb_fx_eps_rhs(hb_fx* f, double* rhs_host);
+int hb_fx_eps_set_rhs(hb_fx* f, const double* rhs_host);
+int hb_fx_eps_sample(hb_fx* f, int iter, double vare, double ratio, double* quad);
+int hb_fx_eps_accumulate(hb_fx* f);
+int hb_fx_eps_get(hb_fx* f, double* est, double* sum);
+int hb_fx_describe(hb_fx* f, int* eps_levels);
+
 /* ------------------------------------------------------------------ host driver layer */
 #define HB_NA (__builtin_nan(""))
 
@@ -221,6 +263,9 @@ typedef struct {
   /* optional per-iteration traces (niter entries each, NULL = not wanted): speculation rounds of the sweep and the
    * device time of the iteration's kernels in milliseconds */
   int32_t* rounds_trace; float* sweep_ms_trace;
+  /* MCMCsamples of the other terms (Bayes.cpp:867-876, 987-1020; optional, NULL = not wanted): Vr nr x records, r
+   * (all terms' levels) x records, Veps and J one per record, epsilon qe x records -- column-major like the reference's */
+  double* vr_store; double* estR_store; double* veps_store; double* J_store; double* epsilon_store;
 } hb_bayes_out;
 
 int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o);

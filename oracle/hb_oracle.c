@@ -632,10 +632,15 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
       if (nr) {
         for (int i = 0; i < nr; ++i) { vt += vrv[i]; vrsum[i] += vrv[i]; }
         for (int q = 0; q < n_levels; ++q) estRsum[q] += estR[q];
+        if (o->vr_store) memcpy(o->vr_store + (size_t)count * nr, vrv, sizeof(double) * nr);
+        if (o->estR_store) memcpy(o->estR_store + (size_t)count * n_levels, estR, sizeof(double) * n_levels);
       }
       if (ne) {
         vepssum += veps; Jsum += epsl_J_beta;
         for (int q = 0; q < qe; ++q) e_sum[q] += e_estR[q];
+        if (o->veps_store) o->veps_store[count] = veps;
+        if (o->J_store) o->J_store[count] = epsl_J_beta;
+        if (o->epsilon_store) memcpy(o->epsilon_store + (size_t)count * qe, e_estR, sizeof(double) * qe);
       }
       hsqsum += vara_ / vt;
       if (o->hsq_store) o->hsq_store[count] = vara_ / vt;

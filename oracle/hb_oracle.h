@@ -83,6 +83,9 @@ typedef struct {
   int nzct;
   int iters_done;
   double seconds_sweep;   /* wall seconds inside the SNP sweeps */
+  /* MCMCsamples of the other terms, Bayes.cpp:867-876 (NULL to skip): Vr nr x records, r levels x records, Veps, J per
+   * record, epsilon qe x records */
+  double* vr_store; double* estR_store; double* veps_store; double* J_store; double* epsilon_store;
 } hbo_bayes_out;
 
 /* returns 0 on success, else nonzero and hbo_last_error() holds the message

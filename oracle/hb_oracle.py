@@ -74,6 +74,8 @@ class Out(C.Structure):
         ("varg_trace", C.c_void_p),
         ("n_records_done", C.c_int), ("nzct", C.c_int), ("iters_done", C.c_int),
         ("seconds_sweep", C.c_double),
+        ("vr_store", C.c_void_p), ("estR_store", C.c_void_p), ("veps_store", C.c_void_p), ("J_store", C.c_void_p),
+        ("epsilon_store", C.c_void_p),
     ]
 
 
@@ -168,11 +170,19 @@ def bayes(y, X, model, Pi, fold=None, C_=None, R=None, niter=200, nburn=100, thi
     }
     if store_alpha:
         mc["alpha"] = np.zeros((m, nrec), order="F")
+    if nr:
+        mc["Vr"], mc["r"] = np.zeros((nr, nrec), order="F"), np.zeros((n_levels, nrec), order="F")
+    if ne:
+        mc["Veps"], mc["J"], mc["epsilon"] = np.zeros(nrec), np.zeros(nrec), np.zeros((qe, nrec), order="F")
     dg = {
         "tracker": np.zeros(m, dtype=np.int32), "nzrate_count": np.zeros(m), "wppa_count": np.zeros(nw),
         "nnz_trace": np.zeros(niter, dtype=np.int32), "vara_trace": np.zeros(niter),
         "vare_trace": np.zeros(niter), "varg_trace": np.zeros(niter),
     }
+    if nr:
+        o.vr_store, o.estR_store = _ptr(mc["Vr"]), _ptr(mc["r"])
+    if ne:
+        o.veps_store, o.J_store, o.epsilon_store = _ptr(mc["Veps"]), _ptr(mc["J"]), _ptr(mc["epsilon"])
     o.beta, o.alpha, o.pi, o.pip = _ptr(res["beta"]), _ptr(res["alpha"]), _ptr(res["pi"]), _ptr(res["pip"])
     o.gwas = _ptr(res["gwas"]) if nw else None
     o.g, o.e, o.vr, o.estR, o.epsilon = _ptr(res["g"]), _ptr(res["e"]), _ptr(res["Vr"]), _ptr(res["r"]), _ptr(res["epsilon"])

@@ -16,7 +16,7 @@ def main():
     import torch
     import torch.distributed as dist
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    if mode == "gpu":
+    if mode.startswith("gpu"):
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
         dist.init_process_group("nccl")
     else:
@@ -53,6 +53,39 @@ def main():
         assert ar64(None, buf.ctypes.data_as(C.POINTER(C.c_double)), 2) == 0
         assert np.allclose(buf, [sum(1.0 + r for r in range(world)), 2.0 * world])
         print("rank %d gloo ok" % rank, flush=True)
+    elif mode == "gpu_fx":
+        # covariates, an environmental random effect and the single-step term on row shards (csrc/effects.cu with the sums
+        # all-reduced): the epsilon rows are the tail of y, so rank 1 holds them all and rank 0 a few (uneven split)
+        import hibayes_b200 as hb
+        import scipy.sparse as sp
+        from oracle import hb_oracle
+        rng = np.random.default_rng(8)
+        n, m, ne, qe = 2400, 1800, 1500, 1700
+        X = rng.integers(0, 3, size=(n, m)).astype(np.int8)
+        J = np.concatenate([-np.ones(n - ne), rng.uniform(-1, 0, ne)])
+        y = X[:, :40].astype(np.float64) @ rng.normal(scale=0.3, size=40) + rng.normal(size=n) + 1.5
+        A = sp.random(qe, qe, density=0.004, random_state=5, format="csr")
+        G = sp.csc_matrix(A @ A.T + sp.diags(np.full(qe, 1.5)))
+        index1 = rng.permutation(qe)[:ne] + 1
+        Cm = np.column_stack([rng.normal(size=n), rng.integers(0, 2, n).astype(float)])
+        R = np.column_stack([rng.integers(0, 6, size=n), rng.integers(0, 40, size=n)])
+        kw = dict(niter=12, nburn=4, thin=2, seed=99)
+        lo, hi = shard_rows(n, rank, world)
+        ne_lo = max(lo, n - ne)           # first epsilon row of this shard
+        loc_idx = index1[ne_lo - (n - ne):hi - (n - ne)] if hi > ne_lo else index1[:0]
+        got = hb.Bayes(y[lo:hi], X[lo:hi], "BayesCpi", [0.9, 0.1], C_=Cm[lo:hi], R=R[lo:hi], epsl_y_J=J[lo:hi], epsl_Gi=G,
+                       epsl_index=loc_idx, device=torch.cuda.current_device(), comm=comm, **kw)
+        if rank == 0:
+            ref = hb_oracle.bayes(y, X.astype(np.float64), "BayesCpi", [0.9, 0.1], C_=Cm, R=R, epsl_y_J=J, epsl_Gi=G, epsl_index=index1, **kw)
+            assert np.array_equal(got["diag"]["tracker"], ref["diag"]["tracker"]), "class labels differ from the oracle"
+            assert np.array_equal(got["diag"]["nnz_trace"], ref["diag"]["nnz_trace"])
+            for k in ("Vg", "Ve", "h2", "mu", "Veps", "J"):
+                assert abs(got[k] / ref[k] - 1) < 1e-5, (k, got[k], ref[k])
+            for k in ("alpha", "beta", "epsilon", "r", "Vr"):
+                assert np.abs(got[k] - ref[k]).max() <= 1e-5 * np.abs(ref[k]).max(), k
+            assert np.allclose(got["e"], ref["e"][lo:hi], rtol=1e-5, atol=1e-5 * np.abs(ref["e"]).max())
+            assert np.allclose(got["MCMCsamples"]["epsilon"], ref["MCMCsamples"]["epsilon"], rtol=1e-5, atol=1e-8)
+        print("rank %d gpu_fx ok" % rank, flush=True)
     else:
         import hibayes_b200 as hb
         model = sys.argv[2] if len(sys.argv) > 2 else "BayesR"

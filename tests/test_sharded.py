@@ -29,3 +29,13 @@ def test_two_gpus_match_the_oracle(model):
     r = _launch("gpu", model, port=29612)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "rank 0 gpu %s ok" % model in r.stdout and "rank 1 gpu %s ok" % model in r.stdout
+
+
+@pytest.mark.gpu
+def test_two_gpus_covariates_random_effects_single_step():
+    import hibayes_b200 as hb
+    if hb.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    r = _launch("gpu_fx", port=29613)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "rank 0 gpu_fx ok" in r.stdout and "rank 1 gpu_fx ok" in r.stdout

@@ -176,10 +176,10 @@ def test_gpu_single_step_against_the_oracle(model, Pi, fold):
     y = X[:, :30].astype(np.float64) @ rng.normal(scale=0.3, size=30) + rng.normal(size=n) + 1.5
     A = sp.random(qe, qe, density=0.02, random_state=5, format="csr")
     G = (A @ A.T + sp.diags(np.full(qe, 1.5))).tolil()
-    G[7, 7] = 0.0
+    index1 = rng.permutation(qe)[:ne] + 1
+    G[index1[3] - 1, index1[3] - 1] = 0.0      # no stored diagonal: A(i, i) is the record count alone
     G = sp.csc_matrix(G)
     G.eliminate_zeros()
-    index1 = rng.permutation(qe)[:ne] + 1
     Cm = np.column_stack([rng.normal(size=n), rng.integers(0, 2, n).astype(float)])
     R = rng.integers(0, 5, size=(n, 1))
     kw = dict(niter=12, nburn=4, thin=2, seed=99, C_=Cm, R=R, epsl_y_J=J, epsl_Gi=G, epsl_index=index1)
@@ -194,3 +194,9 @@ def test_gpu_single_step_against_the_oracle(model, Pi, fold):
     assert np.abs(got["epsilon"] - ref["epsilon"]).max() <= 1e-5 * np.abs(ref["epsilon"]).max()
     assert np.abs(got["beta"] - ref["beta"]).max() <= 1e-5 * np.abs(ref["beta"]).max()
     assert np.abs(got["e"] - ref["e"]).max() <= 1e-5 * np.abs(ref["e"]).max()
+    # MCMCsamples of the other terms (Bayes.cpp:867-876, 987-1020)
+    for key in ("Veps", "J", "epsilon", "Vr", "r", "beta"):
+        a_, b_ = got["MCMCsamples"][key], ref["MCMCsamples"][key]
+        assert a_.shape == b_.shape and np.abs(a_ - b_).max() <= 1e-5 * np.abs(b_).max(), key
+    assert np.abs(got["r"] - ref["r"]).max() <= 1e-5 * np.abs(ref["r"]).max()
+    assert np.abs(got["Vr"] - ref["Vr"]).max() <= 1e-5 * np.abs(ref["Vr"]).max()
