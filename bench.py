@@ -21,6 +21,7 @@ reductions -- what replaces Bayes.cpp:586-823 -- driven by the host-side scalar 
 --config c2   BASELINE configs[1]: ibrm() BayesR n = 50 000 x m = 500 000, 1000 iterations through hb_bayes() with host
               buffers; ms per sweep and rounds per tile around iterations 10 / 100 / 500 / 1000.
 --config c3   BASELINE configs[2]: BayesB n = 200 000 x m = 1 000 000 row-sharded over 8 GPUs (25 000 rows per GPU).
+--config c4   BASELINE configs[3]: sbrm() SBayesD on a dense fp64 LD matrix of the largest m that fits (--m, default 100 000).
 `--impl reference`  the reference's own CPU data path (per-SNP ddot + 2 daxpy on a column-major fp64 matrix,
             Bayes.cpp:751-802, all host threads) on a bounded column sample of the same workload (oracle port: the
             reference itself needs R/Rcpp/Armadillo and cannot be built here).
@@ -523,6 +524,68 @@ def run_c2(args):
     print(json.dumps(line), flush=True)
 
 
+def run_c4(args):
+    """BASELINE configs[3]: sbrm() SBayesD, dense LD.  The reference's m = 300 000 fp64 matrix is 720 GB; the largest m this
+    run takes is --m (default 100 000: 80 GB of fp64 LD in HBM, and on the host while it is handed over).  LD = centred
+    X'X / n of a synthetic reference panel (n_ref = 5 000) built by the device LD builder (hb_ldmat_*), summary statistics
+    from marginal regressions at N = 50 000.  Reported: LD-column updates per second (one per changed SNP,
+    SBayesD.cpp:351-356), LD bytes those updates streamed / device time against the measured HBM peak."""
+    import hibayes_b200 as hb
+    m = 100000 if args.m == 1000000 else args.m
+    n_ref, N = 5000, 50000.0
+    niter = 50 if args.niter == 1000 else args.niter
+    t0 = time.time()
+    X = host_genotypes(n_ref, m, args.seed)
+    h = hb.LdMat(X)
+    ld = h.dense()
+    ld_ms = h.last_ms()
+    h.close()
+    rng = np.random.default_rng(args.seed)
+    beta = np.zeros(m)
+    causal = rng.choice(m, size=min(1000, m), replace=False)
+    beta[causal] = rng.standard_normal(causal.size)
+    vx = np.ascontiguousarray(np.diag(ld))
+    gvar = float(beta @ (ld @ beta))
+    beta *= math.sqrt(0.5 / gvar)
+    keep = vx > 0
+    bhat = np.zeros(m)
+    bhat[keep] = (ld @ beta)[keep] / vx[keep] + rng.standard_normal(int(keep.sum())) * np.sqrt(1.0 / (N * vx[keep]))
+    se = np.ones(m)
+    se[keep] = np.sqrt((1.0 - 0.0) / (N * vx[keep]))
+    ss = np.asfortranarray(np.column_stack([X.mean(axis=0) / 2, bhat, se, np.full(m, N)]))
+    ss[~keep, 1:3] = np.nan
+    del X
+    t_gen = time.time() - t0
+    t0 = time.perf_counter()
+    res = hb.SBayesD(ss, ld, "BayesR", PI_R, fold=FOLD, niter=niter, nburn=niter // 2, thin=5, seed=args.seed)
+    call_s = time.perf_counter() - t0
+    dg = res["diag"]
+    sweep_s = dg["seconds_sweep"]
+    cols, ent = dg["columns_total"], dg["ld_entries_total"]
+    peak, peak_src = _peaks()
+    ach = ent * 8 / sweep_s / 1e9
+    line = {
+        "metric": "sbayesd_ld_column_updates_per_sec", "value": cols / sweep_s, "unit": "LD-column-updates/s", "n_gpus": 1,
+        "steps": niter, "warmup": 0, "ms_per_step": 1e3 * sweep_s / niter, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[3]: sbrm() SBayesD BayesR, dense fp64 LD m=%d (%.0f GB; the reference's m=300000 "
+                               "is 720 GB and fits no single GPU), %d iterations through hb_sbayesd()" % (m, m * m * 8 / 1e9, niter),
+                   "m": m, "n_ref": n_ref, "N": N, "precision": "fp64", "ld_bytes_device": dg["ld_bytes_device"],
+                   "columns_per_sweep": cols / niter, "snp_updates_per_s": m * niter / sweep_s,
+                   "rounds_per_tile": dg["rounds_total"] / max(1, dg["tiles_total"]), "ld_builder_kernel_ms": ld_ms,
+                   "setup_s": t_gen, "call_s": call_s, "Vg": res["Vg"], "Ve": res["Ve"], "nnz_last": int(dg["nnz_trace"][-1])},
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "peak_source": peak_src, "kernel": "k_ld_sweep<dense>", "kernel_ms": 1e3 * sweep_s / niter,
+                     "algorithmic_bytes_per_launch": ent * 8 / niter,
+                     "note": "algorithmic bytes = m * 8 per changed SNP (SURVEY.md 8d); the tile decisions (one CTA) pace the sweep, "
+                             "the column updates of the other CTAs overlap them"},
+        "e2e": {"value": cols / (call_s), "unit": "LD-column-updates/s", "h2d_bytes_per_step": int(m * m * 8 / niter),
+                "d2h_bytes_per_step": int(4 * 8 * m / niter), "path": "hb_sbayesd() with host sumstat and LD (the LD upload is inside)"},
+        "gpu_launches": niter,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def allsum_max(comm, x):
     """max over ranks of a host scalar"""
     if not comm:
@@ -539,7 +602,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--config", default="metric", choices=["metric", "c2", "c3"])
+    ap.add_argument("--config", default="metric", choices=["metric", "c2", "c3", "c4"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--n", type=int, default=50000)
     ap.add_argument("--m", type=int, default=1000000)
@@ -556,6 +619,8 @@ def main():
         run_reference(args)
     elif args.config == "c2":
         run_c2(args)
+    elif args.config == "c4":
+        run_c4(args)
     else:
         run_gpu(args)
 

@@ -19,12 +19,12 @@ SYMBOLS = [
     "hb_engine_get_pip_counts", "hb_engine_accumulate_effects", "hb_engine_get_effect_sums", "hb_engine_predict",
     "hb_engine_last_sweep_ms", "hb_engine_describe", "hb_bayes",
     "hb_engine_ipc_handle", "hb_engine_set_peers", "hb_engine_gram_device", "hb_engine_u_centered_sums",
-    "hb_test_class_thresholds", "hb_test_class_of", "hb_ld_engine_create", "hb_ld_engine_destroy", "hb_ld_engine_load_dense", "hb_ld_engine_set_state",
+    "hb_test_class_thresholds", "hb_test_class_of", "hb_ld_engine_create", "hb_ld_engine_destroy", "hb_ld_engine_load_dense", "hb_ld_engine_load_csc", "hb_ld_engine_describe", "hb_ld_engine_set_state",
     "hb_ld_engine_set_vargL", "hb_ld_engine_set_sparse_info", "hb_ld_engine_get", "hb_ld_engine_sweep", "hb_sbayesd", "hb_sbayess",
     "hb_engine_load_bed", "hb_ldmat_create", "hb_ldmat_destroy", "hb_ldmat_load_i8", "hb_ldmat_load_bed", "hb_ldmat_stats",
     "hb_ldmat_dense", "hb_ldmat_sparse", "hb_ldmat_sparse_get", "hb_ldmat_set_panel_cols", "hb_ldmat_last_ms", "hb_bed_decode",
     "hb_test_bed_decode_snp", "hb_engine_predict_samples", "hb_test_ld_entries", "hb_test_ld_stats", "hb_test_limb_dot", "hb_cutwind_by_bp", "hb_cutwind_by_num",
-    "hb_engine_device_state", "hb_fx_create", "hb_fx_destroy", "hb_fx_dot", "hb_fx_self_dot", "hb_fx_axpy", "hb_fx_level_sums",
+    "hb_engine_last_predict_ms", "hb_engine_device_state", "hb_fx_create", "hb_fx_destroy", "hb_fx_dot", "hb_fx_self_dot", "hb_fx_axpy", "hb_fx_level_sums",
     "hb_fx_level_apply", "hb_fx_eps_set_counts", "hb_fx_eps_rhs", "hb_fx_eps_set_rhs", "hb_fx_eps_sample", "hb_fx_eps_accumulate",
     "hb_fx_eps_get", "hb_fx_describe",
 ]
@@ -51,7 +51,9 @@ class SBayesOut(C.Structure):
                 ("tracker_final", C.c_void_p), ("nzrate_count", C.c_void_p), ("wppa_count", C.c_void_p),
                 ("nnz_trace", C.c_void_p), ("vara_trace", C.c_void_p), ("vare_trace", C.c_void_p), ("varg_trace", C.c_void_p),
                 ("r_hat_final", C.c_void_p), ("n_records_done", C.c_int), ("nzct", C.c_int), ("iters_done", C.c_int),
-                ("n_used", C.c_int), ("seconds_sweep", C.c_double)]
+                ("n_used", C.c_int), ("seconds_sweep", C.c_double),
+                ("columns_total", C.c_longlong), ("ld_entries_total", C.c_longlong), ("ld_bytes_device", C.c_longlong),
+                ("rounds_total", C.c_longlong), ("tiles_total", C.c_longlong)]
 
 ALLREDUCE_F64 = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_size_t)
 ALLREDUCE_I32_DEV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)

@@ -409,7 +409,8 @@ def _sbayes(sparse, sumstat, ldm, model, Pi, niter, nburn, thin, fold, windindx,
     _lib.check((L.hb_sbayess if sparse else L.hb_sbayesd)(C.byref(a), C.byref(o)))
     res.update({"Vg": o.Vg, "Ve": o.Ve, "h2": o.h2, "MCMCsamples": mc})
     dg.update({"n_records": o.n_records_done, "nzct": o.nzct, "iters_done": o.iters_done, "n_used": o.n_used,
-               "seconds_sweep": o.seconds_sweep})
+               "seconds_sweep": o.seconds_sweep, "columns_total": o.columns_total, "ld_entries_total": o.ld_entries_total,
+               "ld_bytes_device": o.ld_bytes_device, "rounds_total": o.rounds_total, "tiles_total": o.tiles_total})
     res["diag"] = dg
     return res
 
@@ -716,6 +717,11 @@ class Engine:
         out = np.zeros((self.n, A.shape[1]), order="F")
         _lib.check(self.L.hb_engine_predict_samples(self.h, A.ctypes.data, self.m, A.shape[1], out.ctypes.data, self.n))
         return out
+
+    def last_predict_ms(self):
+        ms = C.c_float(0)
+        _lib.check(self.L.hb_engine_last_predict_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def sweep(self, iter, model_index, vare, logpi, vara_fold, fold=None, dfvara=4.0, s2varg=0.0, lambda_=0.0, lambda2=0.0,
               mu_shift=0.0, rnorm2_bound=1.0):

@@ -113,7 +113,7 @@ struct hb_engine {
   int *wstart = nullptr, *wmem = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  float ms_prep = 0, ms_sweep = 0, ms_tail = 0;
+  float ms_prep = 0, ms_sweep = 0, ms_tail = 0, ms_predict = 0;
 };
 
 
@@ -654,6 +654,92 @@ __global__ void k_gemv_sum(const double* __restrict__ partial, int nchunk, size_
   double v = 0.0;
   for (int c = 0; c < nchunk; ++c) v += partial[(size_t)c * Npad + i];
   out[i] = v;
+}
+
+// Genetic values of a block of MCMC samples, `M %*% MCMCsamples$alpha` (R/bayes.r:303-304): part[c][row][rec] = sum over
+// the SNPs of chunk c of x[row][j] * alpha[j][rec] for up to kGsRec records at once, so that X is read once per block of
+// records instead of once per record.  CTA (slab s, chunk c); warp w: row group w % RW (lane l owns rows 4 l .. 4 l + 3 of
+// it, the four genotype bytes of one 32-bit word) and records 16 (w / RW) .. + 15: 64 fp64 accumulators per thread, one
+// int8 -> fp64 conversion per 16 fused multiply-adds.  Sub-tiles of kGsSub SNPs (genotypes of the slab + their alpha rows)
+// are double-buffered in shared memory with cp.async.  fp64 FMA-bound: n * m * records / (64 per SM and clock).
+constexpr int kGsRec = 64, kGsSub = 32;   // (64 accumulators per thread: 12 warps of ~170 registers fill an SM's register file)
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__global__ void __launch_bounds__(384, 1) k_gemm_samples(const uint8_t* __restrict__ Xp, const double* __restrict__ at /* [m_pad][kGsRec] */,
+                                                         int m_pad, int R, int RW, int NG, size_t slab_stride, size_t Npad,
+                                                         double* __restrict__ part /* [nchunk][Npad][kGsRec] */) {
+  extern __shared__ __align__(16) uint8_t gs_smem[];
+  const int s = blockIdx.x, c = blockIdx.y, nchunk = gridDim.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
+  const int rw = warp % RW, rg = warp / RW;      // row group of 128 rows, record group of 16 records
+  const int nsub = m_pad / kGsSub;
+  const int sub_lo = (int)((long long)nsub * c / nchunk), sub_hi = (int)((long long)nsub * (c + 1) / nchunk);
+  const size_t xbytes = (size_t)kGsSub * R, abytes = (size_t)kGsSub * kGsRec * 8;
+  uint8_t* xb[2] = {gs_smem, gs_smem + xbytes + abytes};
+  const uint8_t* Xs = Xp + (size_t)s * slab_stride;
+  auto issue = [&](int sub, int b) {
+    const uint8_t* xg = Xs + (size_t)sub * kGsSub * R;                   // SNP columns of a slab are contiguous blocks of R bytes
+    const uint8_t* ag = (const uint8_t*)(at + (size_t)sub * kGsSub * kGsRec);
+    for (size_t o = (size_t)tid * 16; o < xbytes; o += (size_t)nthr * 16) cp_async16(xb[b] + o, xg + o);
+    for (size_t o = (size_t)tid * 16; o < abytes; o += (size_t)nthr * 16) cp_async16(xb[b] + xbytes + o, ag + o);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  double acc[4][16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[i][k] = 0.0;
+  if (sub_lo < sub_hi) issue(sub_lo, 0);
+  for (int sub = sub_lo; sub < sub_hi; ++sub) {
+    const int b = (sub - sub_lo) & 1;
+    if (sub + 1 < sub_hi) { issue(sub + 1, b ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (rg < NG) {
+      const uint8_t* xs = xb[b] + 128 * rw + 4 * lane;
+      const double* as = (const double*)(xb[b] + xbytes) + 16 * rg;
+#pragma unroll 2
+      for (int j = 0; j < kGsSub; ++j) {
+        const uint32_t w = *(const uint32_t*)(xs + (size_t)j * R);
+        const double x0 = (double)(w & 0xffu), x1 = (double)((w >> 8) & 0xffu), x2 = (double)((w >> 16) & 0xffu), x3 = (double)(w >> 24);
+        const double2* ap = (const double2*)(as + (size_t)j * kGsRec);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const double2 a = ap[k];
+          acc[0][2 * k] = fma(x0, a.x, acc[0][2 * k]); acc[0][2 * k + 1] = fma(x0, a.y, acc[0][2 * k + 1]);
+          acc[1][2 * k] = fma(x1, a.x, acc[1][2 * k]); acc[1][2 * k + 1] = fma(x1, a.y, acc[1][2 * k + 1]);
+          acc[2][2 * k] = fma(x2, a.x, acc[2][2 * k]); acc[2][2 * k + 1] = fma(x2, a.y, acc[2][2 * k + 1]);
+          acc[3][2 * k] = fma(x3, a.x, acc[3][2 * k]); acc[3][2 * k + 1] = fma(x3, a.y, acc[3][2 * k + 1]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (rg < NG) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double* o = part + ((size_t)c * Npad + (size_t)s * R + 128 * rw + 4 * lane + i) * kGsRec + 16 * rg;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) o[k] = acc[i][k];
+    }
+  }
+}
+// at[j][r] = alpha[r][j] (records r0 .. r0 + nrec - 1 of the caller's m x records matrix), zero beyond m / nrec
+__global__ void k_gs_transpose(const double* __restrict__ alpha, size_t ld, int m, int m_pad, int nrec, double* __restrict__ at) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)m_pad * kGsRec) return;
+  const int j = (int)(idx / kGsRec), r = (int)(idx % kGsRec);
+  at[idx] = (j < m && r < nrec) ? alpha[(size_t)r * ld + j] : 0.0;
+}
+// out[r][row] = sum over the chunks, in order (deterministic)
+__global__ void k_gs_sum(const double* __restrict__ part, int nchunk, size_t Npad, int n, int nrec, double* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * nrec) return;
+  const int r = (int)(idx / n), row = (int)(idx % n);
+  double v = 0.0;
+  for (int c = 0; c < nchunk; ++c) v += part[((size_t)c * Npad + row) * kGsRec + r];
+  out[idx] = v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1388,15 +1474,49 @@ extern "C" int hb_engine_predict(hb_engine* e, const double* alpha, double* out)
 }
 
 // Genetic values of every stored MCMC sample, `M %*% res$MCMCsamples$alpha` of R/bayes.r:303-304:
-// out[:, c] = X alpha[:, c].  First path: one k_gemv_part pass over X per record (the kernel hb_engine_predict uses);
-// a batched kernel that reads X once for all records is the obvious next step.
+// out[:, c] = X alpha[:, c].  Blocks of up to 64 records go through k_gemm_samples, which reads X once per block.
 extern "C" int hb_engine_predict_samples(hb_engine* e, const double* alpha, size_t ld_alpha, int n_records, double* out,
                                          size_t ld_out) {
   if (!e || !alpha || !out) return hb_set_error("hb_engine_predict_samples: null argument");
   if (n_records < 0 || ld_alpha < (size_t)e->m || ld_out < (size_t)e->n)
     return hb_set_error("hb_engine_predict_samples: bad leading dimension or record count");
-  for (int c = 0; c < n_records; ++c)
-    if (hb_engine_predict(e, alpha + (size_t)c * ld_alpha, out + (size_t)c * ld_out)) return 1;
+  if (!e->geno_ready) return hb_set_error("hb_engine_predict_samples: genotypes not loaded");
+  if (n_records == 0) return 0;
+  CU(cudaSetDevice(e->cfg.device));
+  const int RW = e->R / 128;   // R is 128, 256 or 384
+  const int nchunk = std::max(1, std::min(e->m_pad / kGsSub, (e->nsm + e->S - 1) / e->S));
+  struct Bufs { double *a = nullptr, *at = nullptr, *part = nullptr, *o = nullptr; ~Bufs() { cudaFree(a); cudaFree(at); cudaFree(part); cudaFree(o); } } b;
+  const int blk = std::min(n_records, kGsRec);
+  CU(cudaMalloc(&b.a, (size_t)e->m * blk * 8));
+  CU(cudaMalloc(&b.at, (size_t)e->m_pad * kGsRec * 8));
+  CU(cudaMalloc(&b.part, (size_t)nchunk * e->Npad * kGsRec * 8));
+  CU(cudaMalloc(&b.o, (size_t)e->n * blk * 8));
+  const size_t sh = 2 * ((size_t)kGsSub * e->R + (size_t)kGsSub * kGsRec * 8);
+  CU(cudaFuncSetAttribute(k_gemm_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+  float ms_total = 0.f;
+  for (int r0 = 0; r0 < n_records; r0 += kGsRec) {
+    const int nrec = std::min(kGsRec, n_records - r0), NG = (nrec + 15) / 16;
+    CU(cudaMemcpy2DAsync(b.a, (size_t)e->m * 8, alpha + (size_t)r0 * ld_alpha, ld_alpha * 8, (size_t)e->m * 8, nrec, cudaMemcpyHostToDevice, e->stream));
+    k_gs_transpose<<<(unsigned)(((size_t)e->m_pad * kGsRec + 255) / 256), 256, 0, e->stream>>>(b.a, (size_t)e->m, e->m, e->m_pad, nrec, b.at);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(e->ev[0], e->stream));
+    k_gemm_samples<<<dim3(e->S, nchunk), 32 * RW * NG, sh, e->stream>>>(e->Xp, b.at, e->m_pad, e->R, RW, NG, e->slab_stride, e->Npad, b.part);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(e->ev[1], e->stream));
+    k_gs_sum<<<(unsigned)(((size_t)e->n * nrec + 255) / 256), 256, 0, e->stream>>>(b.part, nchunk, e->Npad, e->n, nrec, b.o);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy2DAsync(out + (size_t)r0 * ld_out, ld_out * 8, b.o, (size_t)e->n * 8, (size_t)e->n * 8, nrec, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+    ms_total += ms;
+  }
+  e->ms_predict = ms_total;
+  return 0;
+}
+extern "C" int hb_engine_last_predict_ms(hb_engine* e, float* ms) {
+  if (!e || !ms) return hb_set_error("hb_engine_last_predict_ms: null argument");
+  *ms = e->ms_predict;
   return 0;
 }
 

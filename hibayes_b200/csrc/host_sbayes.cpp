@@ -35,6 +35,7 @@ struct LdGuard {
 
 static int sbayes_host(const hb_sbayes_args* a, hb_sbayes_out* o, bool sparse) {
   if (!a || !o) return hb_set_error("hb_sbayes: null argument");
+  o->columns_total = 0; o->ld_entries_total = 0; o->ld_bytes_device = 0; o->rounds_total = 0; o->tiles_total = 0;
   if (sparse ? !(a->ld_colptr && a->ld_rowidx && a->ld_val) : !a->ldm) return hb_set_error("hb_sbayes: LD matrix missing");
   const int m = a->m;
   const std::string model = a->model ? a->model : "";
@@ -75,16 +76,13 @@ static int sbayes_host(const hb_sbayes_args* a, hb_sbayes_out* o, bool sparse) {
   std::vector<double> xy(m, 0.0), r_hat(m, 0.0), yyi(m, 0.0), xpx(m), vx(m), g(m, 0.0), gsum(m, 0.0), nzrate(m, 0.0);
   std::vector<uint8_t> ifest(m, 1);
   std::vector<int32_t> tracker(m, 0);
-  std::vector<double> varediff(sparse ? m : 0), dense;
+  std::vector<double> varediff(sparse ? m : 0);
   if (sparse) {
-    // SBayesS.cpp:109-113, 131-141; the device engine works on a dense copy (zeros where nothing is stored)
-    dense.assign((size_t)m * m, 0.0);
+    // SBayesS.cpp:109-113, 131-141; the device engine keeps the compressed columns as they are (hb_ld_engine_load_csc)
     for (int i = 0; i < m; ++i) {
       vx[i] = 0.0;
-      for (int q = a->ld_colptr[i]; q < a->ld_colptr[i + 1]; ++q) {
-        dense[(size_t)i * m + a->ld_rowidx[q]] = a->ld_val[q];
+      for (int q = a->ld_colptr[i]; q < a->ld_colptr[i + 1]; ++q)
         if (a->ld_rowidx[q] == i) vx[i] = a->ld_val[q];
-      }
       varediff[i] = (m - (double)(a->ld_colptr[i + 1] - a->ld_colptr[i])) / m;
       xpx[i] = vx[i] * n;
     }
@@ -130,8 +128,12 @@ static int sbayes_host(const hb_sbayes_args* a, hb_sbayes_out* o, bool sparse) {
   LdGuard guard;
   HBCHK(hb_ld_engine_create(a->device, m, a->seed, &guard.e));
   hb_ld_engine* E = guard.e;
-  HBCHK(hb_ld_engine_load_dense(E, sparse ? dense.data() : a->ldm));
-  if (sparse) { HBCHK(hb_ld_engine_set_sparse_info(E, varediff.data(), vx.data())); std::vector<double>().swap(dense); }
+  if (sparse) {
+    HBCHK(hb_ld_engine_load_csc(E, a->ld_colptr, a->ld_rowidx, a->ld_val));
+    HBCHK(hb_ld_engine_set_sparse_info(E, varediff.data(), vx.data()));
+  } else {
+    HBCHK(hb_ld_engine_load_dense(E, a->ldm));
+  }
   HBCHK(hb_ld_engine_set_state(E, xpx.data(), ifest.data(), xy.data(), r_hat.data()));
   if (model_index == 5) { std::vector<double> vl(m, varg); HBCHK(hb_ld_engine_set_vargL(E, vl.data())); }
 
@@ -150,6 +152,8 @@ static int sbayes_host(const hb_sbayes_args* a, hb_sbayes_out* o, bool sparse) {
     hb_ld_sweep_out so;
     HBCHK(hb_ld_engine_sweep(E, &in, &so));
     t_sweep += 1e-3 * so.sweep_ms;
+    o->columns_total += so.n_changed; o->ld_entries_total += (long long)so.ld_entries; o->rounds_total += so.rounds;
+    o->tiles_total += (m + 255) / 256;
     switch (model_index) {
       case 1:
         varg = (so.varg_acc + s2varg_ * dfvara_) / hb_draw_chisq(KEY, HB_DOM_ITER, it, HB_IT_VARG, 0, dfvara_ + count_y);   // :269
@@ -228,6 +232,7 @@ static int sbayes_host(const hb_sbayes_args* a, hb_sbayes_out* o, bool sparse) {
     if (count == n_records) { ++iter; break; }   // :530
   }
   o->iters_done = iter; o->n_records_done = count; o->nzct = nzct; o->n_used = n; o->seconds_sweep = t_sweep;
+  { uint64_t lb = 0; hb_ld_engine_describe(E, nullptr, &lb, nullptr); o->ld_bytes_device = (long long)lb; }
   o->Vg = varasum / count; o->Ve = varesum / count; o->h2 = hsqsum / count;   // :535-545
   if (o->alpha) for (int i = 0; i < m; ++i) o->alpha[i] = gsum[i] / count;
   if (o->pi) for (int j = 0; j < n_fold; ++j) o->pi[j] = fixpi ? Pi[j] : pisum[j] / count;

@@ -49,10 +49,17 @@ struct LdOutDev {
   double count[HB_MAX_FOLD];
   double varg_acc, sum_vargL, d_minus, d_plus;
   int n_changed, rounds;
+  unsigned long long entries;   // LD entries streamed by the column updates (CSC: stored entries walked)
 };
 
 struct LdParams {
-  const double* ldm;
+  const double* ldm;            // dense storage: m x m column-major (nullptr with CSC storage)
+  // CSC storage (SBayesS)
+  const int *colptr, *rowidx;
+  const double* val;
+  const double *blk0, *blk1;    // [T][LB][LB]: blk0[t][c][r] = LD[LB t + r, LB t + c], blk1[t][c][r] = LD[LB (t+1) + r, LB t + c]
+  const int* rstart;            // [m][W + 1]: first stored entry of column c whose row is >= w * chunk
+  int chunk, W;                 // rows per worker range, number of workers
   int m;
   double nscale;
   double *r_hat, *g, *vargL;
@@ -63,16 +70,16 @@ struct LdParams {
   double logpi[HB_MAX_FOLD], vara_fold[HB_MAX_FOLD], fold[HB_MAX_FOLD];
   double vare, dfvara, s2varg, lambda, lambda2;
   hb_key_t key;
-  // SBayesS (sparse-LD variant): per-SNP residual variance varei = varediff_j * vara + vare, re-draws of too large
-  // effects for BayesC/Cpi and BayesR (SBayesS.cpp:131-141, 285, 388-398)
+  // SBayesS: per-SNP residual variance varei = varediff_j * vara + vare, re-draws of too large effects for BayesC/Cpi and
+  // BayesR (SBayesS.cpp:131-141, 285, 388-398)
   int sparse;
   const double *varediff, *vx;
   double vara, vary;
   uint8_t* looped;   // [m] the re-draw loop ran for this SNP in this sweep
   double* last2;     // [m] square of its last re-draw
-  int* q_idx;      // [LB] global SNP index of the tile's changed SNPs
-  double* q_dn;    // [LB] (g_old - g_new) * n
-  int* q_cnt;
+  int* q_idx;        // [2][LB] global SNP index of a tile's changed SNPs (lists of consecutive tiles alternate)
+  double* q_dn;      // [2][LB] (g_old - g_new) * n
+  int* q_cnt;        // [2]
   LdOutDev* out;
 };
 
@@ -103,10 +110,12 @@ __device__ double block_sum_256(double v, double* sh) {
   return r;
 }
 
+// CSC: the kernel is compiled for both storages; `CSC` selects where an LD entry comes from
+template <bool CSC>
 __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParams p) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double c_rhs0[LB], c_iv[LB], c_sdz[LB], c_gold[LB], c_delta[LB], c_gnew[LB], red[LB], c_sd[LB], c_vx[LB];
-  __shared__ int c_idx[LB], c_cls[LB], wcnt[LB / 32], s_flag;
+  __shared__ double c_rhs0[LB], c_iv[LB], c_sdz[LB], c_gold[LB], c_delta[LB], c_gnew[LB], red[LB], c_sd[LB], c_vx[LB], c_l2[LB];
+  __shared__ int c_idx[LB], c_cls[LB], c_loop[LB], wcnt[LB / 32], s_flag;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = p.m, model = p.model, F = p.F;
   const bool dense = (model == HB_MODEL_RR || model == HB_MODEL_A || model == HB_MODEL_L);
@@ -114,11 +123,63 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
   const int T = (m + LB - 1) / LB;
   const double nscale = p.nscale;
   const bool redraw = p.sparse && (model == HB_MODEL_C || model == HB_MODEL_R);
+  const bool solo = gridDim.x == 1;
   int rounds = 0, changed = 0;
-  for (int t = 0; t < T; ++t) {
-    if (blockIdx.x == 0) {
-      // ---------------- phase A: the tile's decisions
+  unsigned long long entries = 0;
+  // entry (row LB t + rl, column LB t + cl) of the diagonal block of tile t
+  auto diag = [&](int t, int cl, int rl) -> double {
+    if (CSC) return p.blk0[((size_t)t * LB + cl) * LB + rl];
+    return p.ldm[((size_t)t * LB + cl) * m + (size_t)t * LB + rl];
+  };
+  // the column updates of list `lt` (the changed SNPs of tile lt) on the rows of worker w, except the rows of the tiles
+  // lt and lt + 1, which CTA 0 updates itself (right after the decisions of lt / before those of lt + 1)
+  auto apply_columns = [&](int lt, int w) {
+    const int buf = lt & 1;
+    const int ku = *(volatile int*)(p.q_cnt + buf);
+    const int* qi = p.q_idx + buf * LB;
+    const double* qd = p.q_dn + buf * LB;
+    const int s0 = lt * LB, s1 = s0 + 2 * LB;
+    if (!CSC) {
+      for (int row = w * LB + tid; row < m; row += p.W * LB) {
+        if (row >= s0 && row < s1) continue;
+        double acc = __ldcg(p.r_hat + row);
+        for (int s = 0; s < ku; ++s) acc = fma(__ldcg(qd + s), p.ldm[(size_t)__ldcg(qi + s) * m + row], acc);
+        p.r_hat[row] = acc;
+      }
+      if (tid == 0) entries += (unsigned long long)ku * (unsigned long long)((m - w * LB + p.W * LB - 1) / (p.W * LB)) * LB;
+    } else {
+      // stored entries of every changed column inside this worker's row range, one column after the other (SNP order)
+      for (int s = 0; s < ku; ++s) {
+        const int c = __ldcg(qi + s);
+        const double dn = __ldcg(qd + s);
+        const int p0 = p.rstart[(size_t)c * (p.W + 1) + w], p1 = p.rstart[(size_t)c * (p.W + 1) + w + 1];
+        for (int q = p0 + tid; q < p1; q += LB) {
+          const int row = p.rowidx[q];
+          if (row >= s0 && row < s1) continue;
+          p.r_hat[row] = fma(dn, p.val[q], __ldcg(p.r_hat + row));
+        }
+        if (tid == 0) entries += (unsigned long long)(p1 - p0);
+        __syncthreads();   // the next column may hold the same rows
+      }
+    }
+  };
+  for (int t = 0; t <= T; ++t) {
+    if (blockIdx.x == 0 && t < T) {
       const int j = t * LB + tid;
+      // ---------------- the rows of this tile first: the changes of the previous tile (block between the two tiles)
+      if (t > 0 && j < m) {
+        const int buf = (t - 1) & 1;
+        const int ku = *(volatile int*)(p.q_cnt + buf);
+        double acc = __ldcg(p.r_hat + j);
+        for (int s = 0; s < ku; ++s) {
+          const int c = __ldcg(p.q_idx + buf * LB + s);
+          const double ld = CSC ? p.blk1[((size_t)(t - 1) * LB + (c - (t - 1) * LB)) * LB + tid] : p.ldm[(size_t)c * m + j];
+          acc = fma(__ldcg(p.q_dn + buf * LB + s), ld, acc);
+        }
+        p.r_hat[j] = acc;
+        if (tid == 0) entries += (unsigned long long)ku * LB;
+      }
+      // ---------------- the tile's decisions
       const bool act = j < m && p.ifest[j];
       double xx = 0, gold = 0, rbase = 0, uu = 0.5, zz = 0, vare = p.vare, vxj = 0;
       double sd[HB_MAX_FOLD];
@@ -171,7 +232,7 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
         for (int w = 0; w < LB / 32; ++w) { if (w < warp) pre += wcnt[w]; k += wcnt[w]; }
         myrank = pre + __popc(bal & ((1u << lane) - 1u));
         if (cand) {
-          c_idx[myrank] = j; c_gold[myrank] = gold; c_cls[myrank] = cls;
+          c_idx[myrank] = tid; c_gold[myrank] = gold; c_cls[myrank] = cls;
           c_iv[myrank] = iv[cls]; c_sdz[myrank] = sdz[cls]; c_rhs0[myrank] = rbase; c_sd[myrank] = sd[cls]; c_vx[myrank] = vxj;
         }
         __syncthreads();
@@ -180,15 +241,16 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
           for (int sb = 0; sb < k; sb += 32) {
             const int sidx = sb + lane;
             const bool valid = sidx < k;
-            const int ji = valid ? c_idx[sidx] : 0;
+            const int li = valid ? c_idx[sidx] : 0;   // position inside the tile
             double rhs = valid ? c_rhs0[sidx] : 0.0;
             const double siv = valid ? c_iv[sidx] : 0.0, ssdz = valid ? c_sdz[sidx] : 0.0, sgold = valid ? c_gold[sidx] : 0.0;
             const int scls = valid ? c_cls[sidx] : 0;
             const double ssd = valid ? c_sd[sidx] : 0.0, svx = valid ? c_vx[sidx] : 0.0;
             for (int sp = 0; sp < sb; ++sp)
-              if (valid) rhs = fma(-(nscale * p.ldm[(size_t)c_idx[sp] * m + ji]), c_delta[sp], rhs);
+              if (valid) rhs = fma(-(nscale * diag(t, c_idx[sp], li)), c_delta[sp], rhs);
             const int nl = min(32, k - sb);
-            double mydelta = 0.0, mygnew = sgold;
+            double mydelta = 0.0, mygnew = sgold, myl2 = 0.0;
+            int myloop = 0;
             for (int lp = 0; lp < nl; ++lp) {
               double gn = (scls > 0) ? fma(rhs, siv, ssdz) : 0.0;
               if (model == HB_MODEL_L && fabs(gn) < 1e-6) gn = 1e-6;   // :373
@@ -196,21 +258,22 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
                 int ii = 0;
                 double l2 = 0.0;
                 while (gn * gn * svx > p.vary) {
-                  gn = fma(rhs, siv, ssd * hb_draw_z(p.key, HB_DOM_SNP, (uint32_t)p.iter, (uint32_t)ji, HB_SL_RETRY, (uint32_t)(ii + 1)));
+                  gn = fma(rhs, siv, ssd * hb_draw_z(p.key, HB_DOM_SNP, (uint32_t)p.iter, (uint32_t)(t * LB + li), HB_SL_RETRY, (uint32_t)(ii + 1)));
                   l2 = gn * gn;
                   ++ii;
                   if (ii > 100) gn = 0.0;
                 }
-                p.looped[ji] = 1;
-                p.last2[ji] = l2;
+                myloop = 1;
+                myl2 = l2;
               }
               const double dl = gn - sgold;
               const double d = __shfl_sync(0xffffffffu, dl, lp);
-              const int jc = __shfl_sync(0xffffffffu, ji, lp);
+              const int lc = __shfl_sync(0xffffffffu, li, lp);
               if (lane == lp) { mydelta = dl; mygnew = gn; }
-              if (valid && lane > lp) rhs = fma(-(nscale * p.ldm[(size_t)jc * m + ji]), d, rhs);
+              if (valid && lane > lp) rhs = fma(-(nscale * diag(t, lc, li)), d, rhs);
             }
-            if (valid) { c_delta[sidx] = mydelta; c_gnew[sidx] = mygnew; }
+            // (the re-draw flags belong to this round only: a round that is redone must not leave its flag behind)
+            if (valid) { c_delta[sidx] = mydelta; c_gnew[sidx] = mygnew; c_loop[sidx] = myloop; c_l2[sidx] = myl2; }
             __syncwarp();
           }
         }
@@ -218,7 +281,7 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
         // exact right-hand side of every SNP of the tile and its class
         double rhs = rbase;
         if (act)
-          for (int s = 0; s < myrank; ++s) rhs = fma(-(nscale * p.ldm[(size_t)c_idx[s] * m + j]), c_delta[s], rhs);
+          for (int s = 0; s < myrank; ++s) rhs = fma(-(nscale * diag(t, c_idx[s], tid)), c_delta[s], rhs);
         const int cls2 = act ? classify(rhs) : 0;
         if (tid == 0) s_flag = 0;
         __syncthreads();
@@ -234,6 +297,7 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
       if (act) {
         p.g[j] = gnew;
         p.tracker[j] = cls;
+        if (redraw && cand && c_loop[myrank]) { p.looped[j] = 1; p.last2[j] = c_l2[myrank]; }
         if (model == HB_MODEL_L) {   // :374-375
           double u2, z2;
           hb_draw_uz(p.key, HB_DOM_SNP, (uint32_t)p.iter, (uint32_t)j, HB_SL_IG, 0, &u2, &z2);
@@ -241,35 +305,43 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
           if (vargi > 0) p.vargL[j] = vargi;
         }
       }
-      // the reference updates r_hat only when the effect changed (:351; models 1 and 2 always, :263, :284)
+      // the reference updates r_hat only when the effect changed (:351; models 1 and 2 always, :263, :284).  The
+      // changes inside the tile are applied to its own rows here, by their owners (diagonal block, SNP order).
       const bool upd = cand && (model == HB_MODEL_RR || model == HB_MODEL_A || gnew != gold);
       const unsigned balu = __ballot_sync(0xffffffffu, upd);
       if (lane == 0) wcnt[warp] = __popc(balu);
       __syncthreads();
       int pre = 0, ku = 0;
       for (int w = 0; w < LB / 32; ++w) { if (w < warp) pre += wcnt[w]; ku += wcnt[w]; }
+      const int buf = t & 1;
       if (upd) {
         const int r = pre + __popc(balu & ((1u << lane) - 1u));
-        p.q_idx[r] = j;
-        p.q_dn[r] = (gold - gnew) * nscale;   // gi_ = (g[i] - gi) * n
+        p.q_idx[buf * LB + r] = j;
+        p.q_dn[buf * LB + r] = (gold - gnew) * nscale;   // gi_ = (g[i] - gi) * n
+        c_idx[r] = tid; c_delta[r] = (gold - gnew) * nscale;
       }
-      if (tid == 0) *p.q_cnt = ku;
+      if (tid == 0) p.q_cnt[buf] = ku;
       changed += ku;
+      __syncthreads();
+      if (j < m) {
+        double acc = __ldcg(p.r_hat + j);
+        for (int s = 0; s < ku; ++s) acc = fma(c_delta[s], diag(t, c_idx[s], tid), acc);
+        p.r_hat[j] = acc;
+      }
+      if (tid == 0) entries += (unsigned long long)ku * LB;
+      __syncthreads();
       __threadfence();
     }
-    grid.sync();
-    // ---------------- phase B: r_hat += sum_s dn_s * LD[:, c_s], columns in SNP order
-    {
-      const int ku = *(volatile int*)p.q_cnt;
-      for (int row = blockIdx.x * LB + tid; row < m; row += gridDim.x * LB) {
-        double acc = __ldcg(p.r_hat + row);
-        for (int s = 0; s < ku; ++s) acc = fma(__ldcg(p.q_dn + s), p.ldm[(size_t)__ldcg(p.q_idx + s) * m + row], acc);
-        p.r_hat[row] = acc;
-      }
+    // ---------------- the column updates of the previous tile's changes on all other rows, overlapped with the decisions
+    if (t > 0) {
+      // rows of tile t-1 itself were updated by CTA 0 right after its decisions, rows of tile t at the start of this step
+      if (blockIdx.x > 0) apply_columns(t - 1, (int)blockIdx.x - 1);
+      else if (solo) apply_columns(t - 1, 0);
     }
     grid.sync();
   }
   // ---------------- end of the sweep: the sums the host needs (:269, :353, :445-447, :460-467)
+  if (tid == 0) atomicAdd(&p.out->entries, entries);
   if (blockIdx.x == 0) {
     double cnt[HB_MAX_FOLD], vacc = 0, sl = 0, dm = 0, dp = 0;
     for (int k = 0; k < HB_MAX_FOLD; ++k) cnt[k] = 0;
@@ -314,10 +386,41 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
 }
 
 // ------------------------------------------------------------------------------------------
+// CSC helpers (device, at load)
+// one warp per column: stored entries that fall into the tile's diagonal block or the block below it
+__global__ void k_csc_blocks(const int* __restrict__ colptr, const int* __restrict__ rowidx, const double* __restrict__ val, int m,
+                             double* __restrict__ blk0, double* __restrict__ blk1) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= m) return;
+  const int tc = c / LB, cl = c % LB;
+  for (int q = colptr[c] + lane; q < colptr[c + 1]; q += 32) {
+    const int r = rowidx[q], tr = r / LB;
+    if (tr == tc) blk0[((size_t)tc * LB + cl) * LB + (r % LB)] = val[q];
+    else if (tr == tc + 1) blk1[((size_t)tc * LB + cl) * LB + (r % LB)] = val[q];
+  }
+}
+// rstart[c][w] = first stored entry of column c with row >= w * chunk (w = 0 .. W)
+__global__ void k_csc_rstart(const int* __restrict__ colptr, const int* __restrict__ rowidx, int m, int W, int chunk, int* __restrict__ rstart) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)m * (W + 1)) return;
+  const int c = (int)(idx / (W + 1)), w = (int)(idx % (W + 1));
+  const long long target = (long long)w * chunk;
+  int lo = colptr[c], hi = colptr[c + 1];
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (rowidx[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  rstart[idx] = lo;
+}
+
 struct hb_ld_engine {
-  int device = 0, m = 0, grid = 1;
+  int device = 0, m = 0, grid = 1, W = 1, chunk = 0;
   uint64_t seed = 0;
   double *ldm = nullptr, *r_hat = nullptr, *g = nullptr, *vargL = nullptr, *xpx = nullptr, *xy = nullptr, *q_dn = nullptr;
+  int *colptr = nullptr, *rowidx = nullptr, *rstart = nullptr;
+  double *val = nullptr, *blk0 = nullptr, *blk1 = nullptr;
+  bool csc = false;
+  uint64_t ld_bytes = 0;
   uint8_t *ifest = nullptr, *looped = nullptr;
   double *varediff = nullptr, *vx = nullptr, *last2 = nullptr;
   bool sparse_ready = false;
@@ -341,26 +444,38 @@ extern "C" int hb_ld_engine_create(int device, int m, uint64_t seed, hb_ld_engin
   hb_ld_engine* e = new hb_ld_engine();
   e->device = device; e->m = m; e->seed = seed;
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ld_sweep, LB, 0));
-  e->grid = std::max(1, std::min(prop.multiProcessorCount * std::max(1, per_sm), (m + LB - 1) / LB));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ld_sweep<false>, LB, 0));
+  int per_sm2 = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_ld_sweep<true>, LB, 0));
+  per_sm = std::max(1, std::min(per_sm, per_sm2));
+  // CTA 0 decides, the others update: one CTA per 256 rows is enough, and never more than are co-resident
+  e->grid = std::max(1, std::min(prop.multiProcessorCount * per_sm, 1 + (m + LB - 1) / LB));
+  e->W = std::max(1, e->grid - 1);
+  e->chunk = (m + e->W - 1) / e->W;
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&e->ev[0])); CU(cudaEventCreate(&e->ev[1]));
   const size_t mm = (size_t)m;
-  CU(cudaMalloc(&e->ldm, mm * mm * 8));
   CU(cudaMalloc(&e->r_hat, mm * 8)); CU(cudaMalloc(&e->g, mm * 8)); CU(cudaMalloc(&e->vargL, mm * 8));
   CU(cudaMalloc(&e->xpx, mm * 8)); CU(cudaMalloc(&e->xy, mm * 8)); CU(cudaMalloc(&e->ifest, mm));
-  CU(cudaMalloc(&e->tracker, mm * 4)); CU(cudaMalloc(&e->q_idx, LB * 4)); CU(cudaMalloc(&e->q_dn, LB * 8));
-  CU(cudaMalloc(&e->q_cnt, 4)); CU(cudaMalloc(&e->out, sizeof(LdOutDev)));
+  CU(cudaMalloc(&e->tracker, mm * 4)); CU(cudaMalloc(&e->q_idx, 2 * LB * 4)); CU(cudaMalloc(&e->q_dn, 2 * LB * 8));
+  CU(cudaMalloc(&e->q_cnt, 2 * 4)); CU(cudaMalloc(&e->out, sizeof(LdOutDev)));
   CU(cudaMemsetAsync(e->g, 0, mm * 8, e->stream)); CU(cudaMemsetAsync(e->tracker, 0, mm * 4, e->stream));
   CU(cudaMemsetAsync(e->vargL, 0, mm * 8, e->stream));
+  CU(cudaMemsetAsync(e->q_cnt, 0, 2 * 4, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   *out = e;
   return 0;
 }
+static void free_ld(hb_ld_engine* e) {
+  cudaFree(e->ldm); cudaFree(e->colptr); cudaFree(e->rowidx); cudaFree(e->val); cudaFree(e->blk0); cudaFree(e->blk1); cudaFree(e->rstart);
+  e->ldm = nullptr; e->colptr = nullptr; e->rowidx = nullptr; e->val = nullptr; e->blk0 = nullptr; e->blk1 = nullptr; e->rstart = nullptr;
+  e->ld_ready = false;
+}
 extern "C" void hb_ld_engine_destroy(hb_ld_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  cudaFree(e->ldm); cudaFree(e->r_hat); cudaFree(e->g); cudaFree(e->vargL); cudaFree(e->xpx); cudaFree(e->xy);
+  free_ld(e);
+  cudaFree(e->r_hat); cudaFree(e->g); cudaFree(e->vargL); cudaFree(e->xpx); cudaFree(e->xy);
   cudaFree(e->looped); cudaFree(e->varediff); cudaFree(e->vx); cudaFree(e->last2);
   cudaFree(e->ifest); cudaFree(e->tracker); cudaFree(e->q_idx); cudaFree(e->q_dn); cudaFree(e->q_cnt); cudaFree(e->out);
   if (e->ev[0]) cudaEventDestroy(e->ev[0]);
@@ -371,8 +486,55 @@ extern "C" void hb_ld_engine_destroy(hb_ld_engine* e) {
 extern "C" int hb_ld_engine_load_dense(hb_ld_engine* e, const double* ldm) {
   if (!e || !ldm) return hb_set_error("hb_ld_engine_load_dense: null argument");
   CU(cudaSetDevice(e->device));
-  CU(cudaMemcpy(e->ldm, ldm, (size_t)e->m * e->m * 8, cudaMemcpyHostToDevice));
+  free_ld(e);
+  const size_t bytes = (size_t)e->m * e->m * 8;
+  if (cudaMalloc(&e->ldm, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return hb_set_error("hb_ld_engine_load_dense: the %d x %d fp64 LD matrix (%.1f GB) does not fit on the device", e->m, e->m, bytes / 1e9);
+  }
+  CU(cudaMemcpy(e->ldm, ldm, bytes, cudaMemcpyHostToDevice));
+  e->csc = false; e->ld_bytes = bytes;
   e->ld_ready = true;
+  return 0;
+}
+/* arma::sp_mat ldm of SBayesS() (SBayesS.cpp:21-40): compressed sparse columns, row indices ascending inside a column */
+extern "C" int hb_ld_engine_load_csc(hb_ld_engine* e, const int32_t* colptr, const int32_t* rowidx, const double* val) {
+  if (!e || !colptr || !rowidx || !val) return hb_set_error("hb_ld_engine_load_csc: null argument");
+  const int m = e->m;
+  if (colptr[0] != 0) return hb_set_error("hb_ld_engine_load_csc: colptr[0] must be 0");
+  for (int c = 0; c < m; ++c) {
+    if (colptr[c + 1] < colptr[c]) return hb_set_error("hb_ld_engine_load_csc: column pointers must not decrease");
+    for (int q = colptr[c]; q < colptr[c + 1]; ++q) {
+      if (rowidx[q] < 0 || rowidx[q] >= m) return hb_set_error("hb_ld_engine_load_csc: row index %d out of range in column %d", rowidx[q], c);
+      if (q > colptr[c] && rowidx[q] <= rowidx[q - 1]) return hb_set_error("hb_ld_engine_load_csc: row indices of column %d are not strictly ascending", c);
+    }
+  }
+  CU(cudaSetDevice(e->device));
+  free_ld(e);
+  const size_t nnz = (size_t)colptr[m], T = (size_t)(m + LB - 1) / LB;
+  CU(cudaMalloc(&e->colptr, ((size_t)m + 1) * 4)); CU(cudaMalloc(&e->rowidx, std::max<size_t>(nnz, 1) * 4));
+  CU(cudaMalloc(&e->val, std::max<size_t>(nnz, 1) * 8));
+  CU(cudaMalloc(&e->blk0, T * LB * LB * 8)); CU(cudaMalloc(&e->blk1, T * LB * LB * 8));
+  CU(cudaMalloc(&e->rstart, (size_t)m * (e->W + 1) * 4));
+  CU(cudaMemcpyAsync(e->colptr, colptr, ((size_t)m + 1) * 4, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->rowidx, rowidx, nnz * 4, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->val, val, nnz * 8, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemsetAsync(e->blk0, 0, T * LB * LB * 8, e->stream)); CU(cudaMemsetAsync(e->blk1, 0, T * LB * LB * 8, e->stream));
+  k_csc_blocks<<<(unsigned)(((size_t)m * 32 + 255) / 256), 256, 0, e->stream>>>(e->colptr, e->rowidx, e->val, m, e->blk0, e->blk1);
+  CU(cudaGetLastError());
+  const size_t nrs = (size_t)m * (e->W + 1);
+  k_csc_rstart<<<(unsigned)((nrs + 255) / 256), 256, 0, e->stream>>>(e->colptr, e->rowidx, m, e->W, e->chunk, e->rstart);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(e->stream));
+  e->csc = true; e->ld_bytes = nnz * 12 + ((size_t)m + 1) * 4;
+  e->ld_ready = true;
+  return 0;
+}
+extern "C" int hb_ld_engine_describe(hb_ld_engine* e, int* csc, uint64_t* ld_bytes, int* grid) {
+  if (!e) return hb_set_error("null engine");
+  if (csc) *csc = e->csc ? 1 : 0;
+  if (ld_bytes) *ld_bytes = e->ld_bytes;
+  if (grid) *grid = e->grid;
   return 0;
 }
 extern "C" int hb_ld_engine_set_state(hb_ld_engine* e, const double* xpx, const uint8_t* ifest, const double* xy, const double* r_hat) {
@@ -417,7 +579,9 @@ extern "C" int hb_ld_engine_sweep(hb_ld_engine* e, const hb_ld_sweep_in* in, hb_
   CU(cudaSetDevice(e->device));
   LdParams p;
   memset(&p, 0, sizeof p);
-  p.ldm = e->ldm; p.m = e->m; p.nscale = in->nscale; p.r_hat = e->r_hat; p.g = e->g; p.vargL = e->vargL; p.xpx = e->xpx;
+  p.ldm = e->ldm; p.colptr = e->colptr; p.rowidx = e->rowidx; p.val = e->val; p.blk0 = e->blk0; p.blk1 = e->blk1; p.rstart = e->rstart;
+  p.chunk = e->chunk; p.W = e->W;
+  p.m = e->m; p.nscale = in->nscale; p.r_hat = e->r_hat; p.g = e->g; p.vargL = e->vargL; p.xpx = e->xpx;
   p.xy = e->xy; p.ifest = e->ifest; p.tracker = e->tracker; p.iter = in->iter; p.model = in->model_index; p.F = in->n_fold;
   for (int k = 0; k < HB_MAX_FOLD; ++k) { p.logpi[k] = in->logpi[k]; p.vara_fold[k] = in->vara_fold[k]; p.fold[k] = in->fold[k]; }
   p.vare = in->vare; p.dfvara = in->dfvara; p.s2varg = in->s2varg; p.lambda = in->lambda; p.lambda2 = in->lambda2;
@@ -428,9 +592,11 @@ extern "C" int hb_ld_engine_sweep(hb_ld_engine* e, const hb_ld_sweep_in* in, hb_
     CU(cudaMemsetAsync(e->looped, 0, (size_t)e->m, e->stream));
   }
   p.key = hb_make_key(e->seed); p.q_idx = e->q_idx; p.q_dn = e->q_dn; p.q_cnt = e->q_cnt; p.out = e->out;
+  CU(cudaMemsetAsync(e->out, 0, sizeof(LdOutDev), e->stream));
   void* args[] = {(void*)&p};
   CU(cudaEventRecord(e->ev[0], e->stream));
-  CU(cudaLaunchCooperativeKernel((const void*)k_ld_sweep, dim3(e->grid), dim3(LB), args, 0, e->stream));
+  if (e->csc) CU(cudaLaunchCooperativeKernel((const void*)k_ld_sweep<true>, dim3(e->grid), dim3(LB), args, 0, e->stream));
+  else CU(cudaLaunchCooperativeKernel((const void*)k_ld_sweep<false>, dim3(e->grid), dim3(LB), args, 0, e->stream));
   CU(cudaEventRecord(e->ev[1], e->stream));
   LdOutDev h;
   CU(cudaMemcpyAsync(&h, e->out, sizeof h, cudaMemcpyDeviceToHost, e->stream));
@@ -439,5 +605,6 @@ extern "C" int hb_ld_engine_sweep(hb_ld_engine* e, const hb_ld_sweep_in* in, hb_
   for (int k = 0; k < HB_MAX_FOLD; ++k) out->count[k] = h.count[k];
   out->varg_acc = h.varg_acc; out->sum_vargL = h.sum_vargL; out->g_xy_minus_rhat = h.d_minus; out->g_xy_plus_rhat = h.d_plus;
   out->n_changed = h.n_changed; out->status = 0; out->rounds = h.rounds; out->sweep_ms = e->ms_sweep;
+  out->ld_entries = h.entries;
   return 0;
 }

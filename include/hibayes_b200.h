@@ -139,6 +139,8 @@ int hb_engine_get_effect_sums(hb_engine* e, double* gsum);
 int hb_engine_predict(hb_engine* e, const double* alpha, double* out);
 /* `M %*% MCMCsamples$alpha` of R/bayes.r:303-304: out (n x n_records, ld_out) = X * alpha (m x n_records, ld_alpha) */
 int hb_engine_predict_samples(hb_engine* e, const double* alpha, size_t ld_alpha, int n_records, double* out, size_t ld_out);
+/* device time of the batched kernel(s) of the last hb_engine_predict_samples() call, ms */
+int hb_engine_last_predict_ms(hb_engine* e, float* ms);
 
 /* Row sharding over the GPUs of one node: one process and one engine per GPU, created with
  * (rank, world) and this rank's rows.  The x_j'r of Bayes.cpp:593 becomes a sum over ranks: inside the sweep
@@ -284,6 +286,11 @@ typedef struct hb_ld_engine hb_ld_engine;
 int hb_ld_engine_create(int device, int m, uint64_t seed, hb_ld_engine** out);
 void hb_ld_engine_destroy(hb_ld_engine* e);
 int hb_ld_engine_load_dense(hb_ld_engine* e, const double* ldm);   /* m x m column-major (arma::mat ldm, :7) */
+/* arma::sp_mat ldm of SBayesS() (/root/reference/src/SBayesS.cpp:21-40; walked by column at :292-296, :403-407) as compressed
+ * sparse columns: colptr m + 1, rowidx / val nnz, row indices strictly ascending inside a column.  The device keeps the
+ * CSC arrays (12 bytes per stored entry), not a dense copy. */
+int hb_ld_engine_load_csc(hb_ld_engine* e, const int32_t* colptr, const int32_t* rowidx, const double* val);
+int hb_ld_engine_describe(hb_ld_engine* e, int* csc, uint64_t* ld_bytes, int* grid);
 /* xpx_j = n * LD_jj (:93-96), ifest (:100-103), xy (:104), initial r_hat (:105) */
 int hb_ld_engine_set_state(hb_ld_engine* e, const double* xpx, const uint8_t* ifest, const double* xy, const double* r_hat);
 int hb_ld_engine_set_vargL(hb_ld_engine* e, const double* vargL);
@@ -308,6 +315,7 @@ typedef struct {
   double g_xy_plus_rhat;       /* g'(xy + r_hat), :466 */
   int n_changed, status, rounds, reserved;
   float sweep_ms;              /* device time of the sweep kernel */
+  unsigned long long ld_entries;  /* LD entries the column updates streamed (dense: rows x changed columns; CSC: stored entries) */
 } hb_ld_sweep_out;
 int hb_ld_engine_sweep(hb_ld_engine* e, const hb_ld_sweep_in* in, hb_ld_sweep_out* out);
 
@@ -338,6 +346,9 @@ typedef struct {
   double* r_hat_final;
   int n_records_done, nzct, iters_done, n_used;
   double seconds_sweep;
+  /* diagnostics of the sweeps (bench): changed SNPs (= LD columns walked), LD entries streamed by their updates, bytes of
+   * LD held on the device, speculation rounds and tiles */
+  long long columns_total, ld_entries_total, ld_bytes_device, rounds_total, tiles_total;
 } hb_sbayes_out;
 int hb_sbayesd(const hb_sbayes_args* a, hb_sbayes_out* o);
 /* drop-in for the body of  Rcpp::List SBayesS(...)  (/root/reference/src/SBayesS.cpp:21-40): sparse LD matrix.  The

@@ -176,6 +176,24 @@ def test_gebv_samples_equal_matrix_product():
     e.close()
 
 
+def test_gebv_samples_batched_blocks_and_ragged_shapes():
+    """150 records (three blocks of the batched kernel, the last one partly filled), n and m not multiples of the slab /
+    tile sizes, two slab heights."""
+    rng = np.random.default_rng(5)
+    for n, m in ((2333, 5001), (300, 777)):
+        X = rng.integers(0, 3, size=(n, m)).astype(np.int8)
+        A = rng.normal(size=(m, 150)) * (rng.random((m, 150)) < 0.3)
+        e = hb.Engine(n, m)
+        e.load_geno(X)
+        got = e.predict_samples(A)
+        want = X.astype(np.float64) @ A
+        assert got.shape == want.shape and np.allclose(got, want, rtol=0, atol=1e-10 * np.abs(want).max())
+        one = e.predict(A[:, 17].copy())
+        assert np.allclose(one, want[:, 17], rtol=0, atol=1e-10 * np.abs(want).max())
+        assert e.last_predict_ms() > 0
+        e.close()
+
+
 def test_pipeline_ldmat_into_sbayesd_on_the_device(oracle):
     """ldmat() -> sbrm() entirely through the C ABI against the same chain of oracles."""
     d = load_demo()

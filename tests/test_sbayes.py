@@ -177,3 +177,55 @@ def test_sbayess_redraw_loop(oracle, model, Pi, fold):
     ref = oracle.sbayess(ss, sld, model, Pi, fold=fold, **kw)
     got = hb.SBayesS(ss, sld, model, Pi, fold=fold, **kw)
     _compare(got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,Pi,fold", [("BayesCpi", [0.9, 0.1], None), ("BayesR", [0.9, 0.05, 0.03, 0.02], [0, 1e-4, 1e-3, 1e-2]),
+                                           ("BayesRR", [0.0, 1.0], None)])
+def test_sbayess_csc_banded_many_tiles(oracle, model, Pi, fold):
+    """The CSC data path of the device (SBayesS.cpp:292-296, 403-407): a banded LD matrix over 12 tiles (m not a multiple of
+    256) whose stored pattern is NOT symmetric (entries dropped from one triangle only) and has an empty column; the device
+    holds the compressed columns, not a dense copy."""
+    import scipy.sparse as sp
+    import hibayes_b200 as hb
+    rng = np.random.default_rng(12)
+    n, m = 2500, 2900
+    # genotypes with local correlation: neighbouring SNPs share a latent block
+    base = rng.integers(0, 3, size=(n, m // 4 + 2))
+    X = np.empty((n, m), dtype=np.float64)
+    for j in range(m):
+        flip = rng.random(n) < 0.35
+        X[:, j] = np.where(flip, rng.integers(0, 3, size=n), base[:, j // 4])
+    y = X[:, rng.choice(m, 15, replace=False)] @ rng.normal(scale=0.4, size=15) + rng.normal(size=n)
+    ss, ld = make_sumstat(y, X)
+    i, j = np.indices((m, m))
+    band = np.abs(i - j) <= 300                                  # reaches the neighbouring tile and one beyond
+    d = np.sqrt(np.clip(np.diag(ld), 1e-300, None))
+    r2n = (ld / d[:, None] / d[None, :]) ** 2 * n
+    keep = (band & (r2n > 6.0)) | np.eye(m, dtype=bool)
+    keep &= ~((i > j) & ((i + 3 * j) % 11 == 0))                 # lower-triangle entries without their mirror image
+    keep[:, 1234] = False                                        # a column with nothing stored, not even the diagonal
+    ss[1234, 1] = np.nan                                         # (xpx = 0 there: the SNP is not estimated)
+    sld = sp.csc_matrix(np.where(keep, ld, 0.0))
+    assert sld.nnz < 0.05 * m * m
+    kw = dict(niter=25, nburn=10, thin=3, seed=515)
+    ref = oracle.sbayess(ss, sld, model, Pi, fold=fold, **kw)
+    assert np.all(np.isfinite(ref["alpha"])) and np.isfinite(ref["Ve"])
+    got = hb.SBayesS(ss, sld, model, Pi, fold=fold, **kw)
+    _compare(got, ref)
+    assert got["diag"]["ld_bytes_device"] == sld.nnz * 12 + (m + 1) * 4     # compressed columns, no dense copy
+    assert got["diag"]["columns_total"] > 0 and got["diag"]["ld_entries_total"] > 0
+
+
+@pytest.mark.gpu
+def test_sbayesd_many_tiles(oracle):
+    """Dense LD over 10 tiles: the decisions of a tile overlap the previous tile's column updates (one grid barrier per
+    tile), rows of the next tile are brought up to date by the deciding CTA itself."""
+    import hibayes_b200 as hb
+    y, X = synth(3000, 2500, seed=71, n_causal=30)
+    ss, ld = make_sumstat(y, X, n_na=15, seed=4)
+    kw = dict(niter=20, nburn=8, thin=3, seed=31)
+    ref = oracle.sbayesd(ss, ld, "BayesR", [0.9, 0.05, 0.03, 0.02], fold=[0, 1e-4, 1e-3, 1e-2], **kw)
+    got = hb.SBayesD(ss, ld, "BayesR", [0.9, 0.05, 0.03, 0.02], fold=[0, 1e-4, 1e-3, 1e-2], **kw)
+    _compare(got, ref)
+    assert got["diag"]["ld_bytes_device"] == 2500 * 2500 * 8

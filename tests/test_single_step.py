@@ -174,10 +174,13 @@ def test_gpu_single_step_against_the_oracle(model, Pi, fold):
     X = rng.integers(0, 3, size=(n, m)).astype(np.int8)
     J = np.concatenate([-np.ones(n - ne), rng.uniform(-1, 0, ne)])
     y = X[:, :30].astype(np.float64) @ rng.normal(scale=0.3, size=30) + rng.normal(size=n) + 1.5
-    A = sp.random(qe, qe, density=0.02, random_state=5, format="csr")
-    G = (A @ A.T + sp.diags(np.full(qe, 1.5))).tolil()
+    # an A^-1-like matrix: a few small off-diagonals per row, strictly diagonally dominant (the sampler's chain is stable)
+    A = sp.random(qe, qe, density=0.012, random_state=5, format="csr", data_rvs=lambda k: rng.uniform(-0.15, 0.15, k))
+    G = (A + A.T + sp.diags(np.full(qe, 2.0))).tolil()
     index1 = rng.permutation(qe)[:ne] + 1
-    G[index1[3] - 1, index1[3] - 1] = 0.0      # no stored diagonal: A(i, i) is the record count alone
+    k0 = index1[3] - 1                          # an entry with nothing stored at all, not even its diagonal: A(i, i) is the
+    G[k0, :] = 0.0                              # record count alone (Gibbs(sp_mat) reads A(i, i) of the sum, solver.cpp:134)
+    G[:, k0] = 0.0
     G = sp.csc_matrix(G)
     G.eliminate_zeros()
     Cm = np.column_stack([rng.normal(size=n), rng.integers(0, 2, n).astype(float)])

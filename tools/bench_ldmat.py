@@ -24,7 +24,29 @@ def main():
     ap.add_argument("--seed", type=int, default=20260101)
     ap.add_argument("--cpu-m", type=int, default=2000,
                     help="SNPs of the CPU sample: the oracle's literal tXXmat loop (OpenMP) on the first columns, timed beside the device")
+    ap.add_argument("--gebv", type=int, default=0, help="records of the GEBV sample product X %%*%% alpha (f4) to time instead (uses --n, --m)")
     a = ap.parse_args()
+    if a.gebv:
+        # `M %*% MCMCsamples$alpha` (R/bayes.r:303-304): batched fp64 kernel, X read once per 64 records
+        e = hb.Engine(a.n, a.m)
+        e.synth_geno(a.seed)
+        rng = np.random.default_rng(1)
+        A = np.asfortranarray(rng.normal(size=(a.m, a.gebv)))
+        t0 = time.perf_counter()
+        out = e.predict_samples(A)
+        wall = time.perf_counter() - t0
+        ms = e.last_predict_ms()
+        t0 = time.perf_counter()
+        for c in range(min(a.gebv, 4)):
+            e.predict(A[:, c].copy())
+        per_rec = (time.perf_counter() - t0) / min(a.gebv, 4)
+        flops = 2.0 * a.n * a.m * a.gebv
+        print(json.dumps({"stage": "gebv_samples", "n": a.n, "m": a.m, "records": a.gebv, "kernel_ms": ms, "call_s": wall,
+                          "fp64_TFLOPs": flops / (ms * 1e-3) / 1e12, "x_GBs": a.n * a.m * -(-a.gebv // 64) / (ms * 1e-3) / 1e9,
+                          "one_record_pass_s": per_rec, "speedup_vs_record_by_record": per_rec * a.gebv / wall,
+                          "checksum": float(out.sum())}))
+        e.close()
+        return
     if a.cpu_m > 0:
         # the reference's CPU path (oracle port of tXXmat_Geno: pairs x individuals scalar loop, OpenMP over SNPs)
         from oracle import hb_oracle
