@@ -13,7 +13,9 @@
 // operands), zero padded to Kpad = 128-multiple of n and Mpad = 64-multiple of m.  The m x m result is
 // produced in column panels of W columns (fp64, column-major, <= 1 GiB) that are either copied to the
 // caller's dense matrix or compacted on the device into CSC (dgCMatrix) pieces.
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <cudaTypedefs.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -46,6 +48,10 @@ struct hb_ldmat {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float ms_gram = 0.f;
+  CUtensorMap tmap;          // Xc as a 2-D tensor (individuals x SNP rows) for the TMA loads of k_ld_panel_tc
+  bool tmap_ready = false;
+  int use_tc = 1;            // tcgen05 panel kernel (default); HB_LD_MMA_SYNC=1 keeps the mma.sync kernel
+  int* status = nullptr;     // device word: a bounded wait of k_ld_panel_tc gave up
   std::vector<long long> colptr;
   std::vector<int32_t> rowidx;
   std::vector<double> val;
@@ -233,6 +239,140 @@ __global__ void __launch_bounds__(128) k_ld_panel(const int8_t* __restrict__ Xc,
       }
 }
 
+// ---- the same panel on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulator in tensor memory) ----
+// CTA = 128 x 128 entries: SNP rows [128 bx, +128) x panel columns [j0 + 128 by, +128).  Both operands are K-major
+// tiles of Xc (128 SNP rows x 128 individuals = 16 KB) that the TMA unit (cp.async.bulk.tensor.2d, 128-byte swizzle)
+// drops into a 4-stage shared-memory ring; one elected thread issues four tcgen05.mma (M = 128, N = 128, K = 32, s8 x s8 ->
+// s32, exact) per stage into a 128-lane x 128-column accumulator in tensor memory and commits the stage back to the
+// producer; four epilogue warps read their 32 lanes with tcgen05.ld (32 columns at a time) and turn every exact inner
+// product into the reference's fp64 value with ld_entry() -- the same function, the same bits, as the mma.sync kernel.
+// Warp roles: 0 TMA producer, 1 tensor-memory allocation + MMA issue, 2-5 epilogue (lane quadrant = warp % 4).
+// Every wait is bounded (2 s): a lost signal sets *status instead of hanging the device.
+constexpr int TC_TILE = 128, TC_KB = 128, TC_STAGES = 4;
+constexpr uint32_t TC_STAGE_BYTES = 2u * TC_TILE * TC_KB;   // A + B
+struct TcShared {
+  uint64_t full[TC_STAGES], empty[TC_STAGES], acc_full;
+  uint32_t tmem_base;
+  int dead;
+};
+__device__ __forceinline__ unsigned long long tc_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool tc_wait(uint64_t* bar, uint32_t parity, volatile int* dead) {
+  if (hb::mbar_try_wait(bar, parity)) return true;
+  const unsigned long long t0 = tc_now();
+  for (;;) {
+    for (int i = 0; i < 64; ++i)
+      if (hb::mbar_try_wait(bar, parity)) return true;
+    if (*dead || tc_now() - t0 > 2000000000ull) { *dead = 1; return false; }
+  }
+}
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+  // K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (stride byte offset),
+  // descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B; the leading byte offset is not used by this layout
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__global__ void __launch_bounds__(192, 1) k_ld_panel_tc(const __grid_constant__ CUtensorMap tmap, int Kpad, int j0, LdEpi epi,
+                                                        double* __restrict__ pan, int* __restrict__ status) {
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  uint8_t* tiles = (uint8_t*)(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
+  TcShared* sh = (TcShared*)(tiles + (size_t)TC_STAGES * TC_STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a0 = blockIdx.x * TC_TILE, b0 = j0 + blockIdx.y * TC_TILE;
+  const int nchunks = Kpad / TC_KB;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { hb::mbar_init(&sh->full[i], 1); hb::mbar_init(&sh->empty[i], 1); }
+    hb::mbar_init(&sh->acc_full, 1);
+    sh->dead = 0;
+    hb::mbar_fence_init();
+  }
+  if (warp == 1) {   // 128 columns of tensor memory: the 128 x 128 s32 accumulator
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hb::smem_u32(&sh->tmem_base)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sh->tmem_base;
+  volatile int* dead = &sh->dead;
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int st = ch % TC_STAGES;
+        if (ch >= TC_STAGES && !tc_wait(&sh->empty[st], (uint32_t)((ch / TC_STAGES - 1) & 1), dead)) break;
+        hb::mbar_arrive_expect_tx(&sh->full[st], TC_STAGE_BYTES);
+        uint8_t* A = tiles + (size_t)st * TC_STAGE_BYTES;
+        uint8_t* B = A + (size_t)TC_TILE * TC_KB;
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(hb::smem_u32(A)), "l"(&tmap), "r"(ch * TC_KB), "r"(a0), "r"(hb::smem_u32(&sh->full[st])) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(hb::smem_u32(B)), "l"(&tmap), "r"(ch * TC_KB), "r"(b0), "r"(hb::smem_u32(&sh->full[st])) : "memory");
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D = s32 (2 at bit 4), A and B signed 8-bit (1 at bits 7 and 10), both K-major, N / 8 at
+      // bit 17, M / 16 at bit 24
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TILE >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
+      bool ok = true;
+      for (int ch = 0; ch < nchunks && ok; ++ch) {
+        const int st = ch % TC_STAGES;
+        ok = tc_wait(&sh->full[st], (uint32_t)((ch / TC_STAGES) & 1), dead);
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t A = hb::smem_u32(tiles + (size_t)st * TC_STAGE_BYTES), B = A + TC_TILE * TC_KB;
+#pragma unroll
+        for (int k = 0; k < TC_KB / 32; ++k) {
+          const uint64_t da = tc_smem_desc(A + 32 * k), db = tc_smem_desc(B + 32 * k);
+          const uint32_t accum = (ch | k) ? 1u : 0u;
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+        }
+        // frees the stage for the producer once the four MMAs above have read it
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(hb::smem_u32(&sh->empty[st])) : "memory");
+      }
+      if (ok) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(hb::smem_u32(&sh->acc_full)) : "memory");
+    }
+  } else {
+    // ---- epilogue: thread = accumulator lane = SNP row; 32 panel columns per tcgen05.ld
+    const bool ok = tc_wait(&sh->acc_full, 0u, dead);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (ok) {
+      const int quad = warp & 3;
+      const int row = a0 + 32 * quad + lane;
+#pragma unroll 1
+      for (int cb = 0; cb < TC_TILE / 32; ++cb) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(32 * quad) << 16) + (uint32_t)(32 * cb);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+            "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+              "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < epi.m) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = b0 + 32 * cb + i;
+            if (col < epi.m) pan[(size_t)(col - j0) * epi.m + row] = ld_entry(epi, row, col, (int)v[i]);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+  if (threadIdx.x == 0 && sh->dead) *status = 1;
+}
+
 // Stored entries per panel column: what an arma::sp_mat keeps is every assigned value != 0.
 __global__ void k_ld_count(const double* __restrict__ pan, int m, int wcols, int* __restrict__ counts) {
   const int w = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -322,10 +462,10 @@ extern "C" int hb_ldmat_create(int device, int n, int m, hb_ldmat** out) {
   h->n = n;
   h->m = m;
   h->Kpad = (n + LD_RK - 1) / LD_RK * LD_RK;
-  h->Mpad = (m + 63) / 64 * 64;
+  h->Mpad = (m + 127) / 128 * 128;
   // panel of at most 1 GiB of fp64
-  long long W = ((1ll << 27) / m) / 64 * 64;
-  h->panel_cols = (int)std::min<long long>(h->Mpad, std::max<long long>(64, W));
+  long long W = ((1ll << 27) / m) / 128 * 128;
+  h->panel_cols = (int)std::min<long long>(h->Mpad, std::max<long long>(128, W));
 #define LDCK(call)                 \
   do {                             \
     if ((call) != cudaSuccess) {   \
@@ -342,7 +482,37 @@ extern "C" int hb_ldmat_create(int device, int n, int m, hb_ldmat** out) {
   LDCK(cudaMalloc(&h->mean, (size_t)m * 8));
   LDCK(cudaMalloc(&h->xx, (size_t)m * 8));
   LDCK(cudaMalloc(&h->chr, (size_t)m * 4));
+  LDCK(cudaMalloc(&h->status, 4));
+  LDCK(cudaMemset(h->status, 0, 4));
 #undef LDCK
+  if (const char* ev = getenv("HB_LD_MMA_SYNC")) h->use_tc = atoi(ev) ? 0 : 1;
+  if (h->use_tc) {
+    // Xc[Mpad][Kpad] as a 2-D tensor: dimension 0 = individuals (bytes, contiguous), dimension 1 = SNP rows
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      hb_ldmat_destroy(h);
+      return hb_set_error("hb_ldmat_create: cuTensorMapEncodeTiled not available from the driver");
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)h->Kpad, (cuuint64_t)h->Mpad};
+    const cuuint64_t gstr[1] = {(cuuint64_t)h->Kpad};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)TC_TILE};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = ((PFN_cuTensorMapEncodeTiled_v12000)fn)(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->Xc, gdim, gstr, box, estr,
+                                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      hb_ldmat_destroy(h);
+      return hb_set_error("hb_ldmat_create: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    }
+    h->tmap_ready = true;
+    const size_t shb = (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(TcShared) + 1024;
+    if (cudaFuncSetAttribute(k_ld_panel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb) != cudaSuccess) {
+      cudaError_t _e = cudaGetLastError();
+      hb_ldmat_destroy(h);
+      return hb_set_error("hb_ldmat_create: %s", cudaGetErrorString(_e));
+    }
+  }
   *out = h;
   return 0;
 }
@@ -350,7 +520,7 @@ extern "C" int hb_ldmat_create(int device, int n, int m, hb_ldmat** out) {
 extern "C" void hb_ldmat_destroy(hb_ldmat* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaFree(h->Xc); cudaFree(h->sum); cudaFree(h->mean); cudaFree(h->xx); cudaFree(h->chr); cudaFree(h->pan);
+  cudaFree(h->Xc); cudaFree(h->sum); cudaFree(h->mean); cudaFree(h->xx); cudaFree(h->chr); cudaFree(h->pan); cudaFree(h->status);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -360,6 +530,7 @@ extern "C" void hb_ldmat_destroy(hb_ldmat* h) {
 extern "C" int hb_ldmat_set_panel_cols(hb_ldmat* h, int cols) {
   if (!h) return hb_set_error("hb_ldmat_set_panel_cols: null handle");
   if (cols < 64 || cols % 64) return hb_set_error("hb_ldmat_set_panel_cols: need a positive multiple of 64");
+  cols = (cols + 127) / 128 * 128;   // (tiles of the tcgen05 kernel)
   h->panel_cols = std::min(cols, h->Mpad);
   return 0;
 }
@@ -473,10 +644,21 @@ static int run_panels(hb_ldmat* h, const int32_t* chr, int has_chisq, double chi
     const int wpad = std::min(W, h->Mpad - j0);
     const int wcols = std::min(W, h->m - j0);
     CU(cudaEventRecord(h->ev0, h->stream));
-    k_ld_panel<<<dim3(h->Mpad / 64, wpad / 64), 128, 0, h->stream>>>(h->Xc, h->Kpad, j0, epi, h->pan);
+    if (h->use_tc) {
+      const size_t shb = (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(TcShared) + 1024;
+      k_ld_panel_tc<<<dim3(h->Mpad / TC_TILE, wpad / TC_TILE), 192, shb, h->stream>>>(h->tmap, h->Kpad, j0, epi, h->pan, h->status);
+    } else {
+      k_ld_panel<<<dim3(h->Mpad / 64, wpad / 64), 128, 0, h->stream>>>(h->Xc, h->Kpad, j0, epi, h->pan);
+    }
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, h->stream));
     if (sink(j0, wcols)) return 1;
+    if (h->use_tc) {
+      int st = 0;
+      CU(cudaMemcpyAsync(&st, h->status, 4, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      if (st) return hb_set_error("hb_ldmat: the tcgen05 panel kernel gave up waiting on a pipeline barrier");
+    }
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->ms_gram += ms;

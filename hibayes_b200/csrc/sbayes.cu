@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
       for (int row = w * LB + tid; row < m; row += p.W * LB) {
         if (row >= s0 && row < s1) continue;
         double acc = __ldcg(p.r_hat + row);
+#pragma unroll 4
         for (int s = 0; s < ku; ++s) acc = fma(__ldcg(qd + s), p.ldm[(size_t)__ldcg(qi + s) * m + row], acc);
         p.r_hat[row] = acc;
       }
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
         const int buf = (t - 1) & 1;
         const int ku = *(volatile int*)(p.q_cnt + buf);
         double acc = __ldcg(p.r_hat + j);
+#pragma unroll 4
         for (int s = 0; s < ku; ++s) {
           const int c = __ldcg(p.q_idx + buf * LB + s);
           const double ld = CSC ? p.blk1[((size_t)(t - 1) * LB + (c - (t - 1) * LB)) * LB + tid] : p.ldm[(size_t)c * m + j];
@@ -246,12 +248,20 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
             const double siv = valid ? c_iv[sidx] : 0.0, ssdz = valid ? c_sdz[sidx] : 0.0, sgold = valid ? c_gold[sidx] : 0.0;
             const int scls = valid ? c_cls[sidx] : 0;
             const double ssd = valid ? c_sd[sidx] : 0.0, svx = valid ? c_vx[sidx] : 0.0;
+#pragma unroll 8
             for (int sp = 0; sp < sb; ++sp)
               if (valid) rhs = fma(-(nscale * diag(t, c_idx[sp], li)), c_delta[sp], rhs);
             const int nl = min(32, k - sb);
+            // the LD entries towards the earlier candidates of this block, all loads in flight at once: the chain below
+            // then waits for a shuffle and a fused multiply-add per step, not for a trip to L2
+            double ldv[32];
+#pragma unroll
+            for (int lp = 0; lp < 32; ++lp) ldv[lp] = (valid && lp < nl && lane > lp) ? nscale * diag(t, c_idx[sb + lp], li) : 0.0;
             double mydelta = 0.0, mygnew = sgold, myl2 = 0.0;
             int myloop = 0;
-            for (int lp = 0; lp < nl; ++lp) {
+#pragma unroll
+            for (int lp = 0; lp < 32; ++lp) {
+              if (lp >= nl) break;
               double gn = (scls > 0) ? fma(rhs, siv, ssdz) : 0.0;
               if (model == HB_MODEL_L && fabs(gn) < 1e-6) gn = 1e-6;   // :373
               if (redraw && lane == lp && scls > 0 && gn * gn * svx > p.vary) {   // SBayesS.cpp:388-398, 489-499
@@ -268,9 +278,8 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
               }
               const double dl = gn - sgold;
               const double d = __shfl_sync(0xffffffffu, dl, lp);
-              const int lc = __shfl_sync(0xffffffffu, li, lp);
               if (lane == lp) { mydelta = dl; mygnew = gn; }
-              if (valid && lane > lp) rhs = fma(-(nscale * diag(t, lc, li)), d, rhs);
+              rhs = fma(-ldv[lp], d, rhs);
             }
             // (the re-draw flags belong to this round only: a round that is redone must not leave its flag behind)
             if (valid) { c_delta[sidx] = mydelta; c_gnew[sidx] = mygnew; c_loop[sidx] = myloop; c_l2[sidx] = myl2; }
@@ -280,8 +289,10 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
         __syncthreads();
         // exact right-hand side of every SNP of the tile and its class
         double rhs = rbase;
-        if (act)
+        if (act) {
+#pragma unroll 8
           for (int s = 0; s < myrank; ++s) rhs = fma(-(nscale * diag(t, c_idx[s], tid)), c_delta[s], rhs);
+        }
         const int cls2 = act ? classify(rhs) : 0;
         if (tid == 0) s_flag = 0;
         __syncthreads();
@@ -325,6 +336,7 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
       __syncthreads();
       if (j < m) {
         double acc = __ldcg(p.r_hat + j);
+#pragma unroll 8
         for (int s = 0; s < ku; ++s) acc = fma(c_delta[s], diag(t, c_idx[s], tid), acc);
         p.r_hat[j] = acc;
       }
