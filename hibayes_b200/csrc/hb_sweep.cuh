@@ -730,9 +730,10 @@ __device__ __forceinline__ CandSet make_candset(uint8_t* smem, int B) {
   return cs;
 }
 
-// Shared memory of a scalar CTA: candidate arrays, two partial-sum arrays, and two buffers with the Gram rows of
-// the tile's candidates (exact int32, as stored): rows0 = diagonal block, rows1 = block
-// towards the next tile.
+// Shared memory of a scalar CTA: candidate arrays, two partial-sum arrays, and three buffers with the Gram rows of
+// the tile's candidates (exact int32, as stored): rows0 = diagonal block, rows1 = block towards the next tile, rows2 =
+// block towards the tile after that (its corrections are the next thing on the serial path after the hand-over: read
+// from L2/HBM in phase C they arrived after the hand-over of the tile in between and paced every second tile).
 // coefficients H (32x32) + solved chain matrix M (32x33, padded rows) + hand-over buffer of the cluster mode (2 x 256)
 constexpr size_t kChainCoefBytes = 32 * 32 * 8 + 32 * 33 * 8 + 2 * 256 * 8;
 __host__ __device__ inline size_t scalar_fixed_bytes(int B) {
@@ -743,11 +744,11 @@ __host__ __device__ inline size_t scalar_fixed_bytes(int B) {
 __host__ inline int scalar_krow(int B) {
   const size_t cap = 226 * 1024;
   const size_t fixed = scalar_fixed_bytes(B);
-  size_t rows = (cap - fixed) / (2 * (size_t)B * 4);
+  size_t rows = (cap - fixed) / (3 * (size_t)B * 4);
   if (rows > (size_t)B) rows = (size_t)B;
   return (int)rows;
 }
-__host__ inline size_t scalar_smem_bytes(int B) { return scalar_fixed_bytes(B) + 2 * (size_t)scalar_krow(B) * B * 4; }
+__host__ inline size_t scalar_smem_bytes(int B) { return scalar_fixed_bytes(B) + 3 * (size_t)scalar_krow(B) * B * 4; }
 
 // exact int32 -> double for 0 <= g < 2^31 on the full-rate pipe (one DADD instead of a quarter-rate I2F)
 __device__ __forceinline__ double gram_as_double(int g) {
@@ -946,6 +947,23 @@ __device__ void solve_candidates(const CandSet& cs, int k, const int32_t* __rest
   }
 }
 
+// the same for two band blocks at once (one wait for both)
+__device__ __noinline__ void gather_rows_2(int32_t* dst1, const int32_t* __restrict__ blk1, int32_t* dst2, const int32_t* __restrict__ blk2,
+                                          const int* idx, int k, int B, int i) {
+  for (int sb = 0; sb < k; ++sb) {
+    const size_t o = (size_t)idx[sb] * B + i;
+    if (blk1) {
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst1 + (size_t)sb * B + i);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(blk1 + o) : "memory");
+    }
+    if (blk2) {
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst2 + (size_t)sb * B + i);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(blk2 + o) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // corr_i = sum_s G[c_s][i] * delta_s over the k candidates (ascending s), read from global memory
 __device__ __noinline__ double band_correction_raw(const int* idx, const double* delta, int k, const int32_t* __restrict__ gb, int B, int i) {
   // 32 Gram entries in flight: one trip to L2 for most tiles.  The correction for tile t+2 is the next thing that
@@ -1035,7 +1053,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
   int *slot_of, *slot_snp;        // row buffers: slot of SNP i (-1: none), SNP of a slot
   volatile int* gctl;             // [0] abort flag, [1] number of candidates
   long long* phase;
-  int32_t *rows0, *rows1;
+  int32_t *rows0, *rows1, *rows2;
   double *coef, *cmat;            // [32][32] chain coefficients of the first 32 candidates, [32][33] solved chain matrix
   double* hbuf;                   // [2][256] cluster mode: corrections handed over by the other worker of the cluster
   {
@@ -1054,6 +1072,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     hbuf = cmat + 32 * 33;
     rows0 = (int32_t*)rb;
     rows1 = rows0 + (size_t)p.KROW * B;
+    rows2 = rows1 + (size_t)p.KROW * B;
   }
   const int KROW = p.KROW;
   const int NT2 = 2 * B;   // threads of the worker
@@ -1180,6 +1199,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     int k = 0, myrank = 0;
     bool cand = false, fast = false;
     const bool has1 = (D > 1 && t + 1 < T);
+    const bool has2 = (D > 2 && t + 2 < T);
     const int32_t* G0 = p.gram + ((size_t)t * D) * B * B;
     // Row buffers: the Gram rows of every SNP that is, or may soon become, a candidate (effect not zero, class not
     // zero, or right-hand side within 30 % of its first class boundary) are gathered once, as soon as the dots are
@@ -1215,15 +1235,15 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
         // miss to HBM under the streaming load costs several microseconds.
         {
           const int lpr = B / 32;   // 128-byte lines per row of a block
-          const int nfar = min(D, T - t) - 2;
+          const int nfar = min(D, T - t) - 3;
           for (int l = tid; l < ns * lpr * nfar; l += NT2) {
-            const int line = l % lpr, sl = (l / lpr) % ns, dt = 2 + l / (lpr * ns);
+            const int line = l % lpr, sl = (l / lpr) % ns, dt = 3 + l / (lpr * ns);
             const int32_t* a = G0 + (size_t)dt * B * B + (size_t)slot_snp[sl] * B + line * 32;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
           }
         }
         if (prim) gather_rows(rows0, G0, slot_snp, ns, B, i);
-        else if (has1) gather_rows(rows1, G0 + (size_t)B * B, slot_snp, ns, B, i);
+        else if (has1) gather_rows_2(rows1, G0 + (size_t)B * B, rows2, has2 ? G0 + (size_t)2 * B * B : nullptr, slot_snp, ns, B, i);
       }
     };
     bool m_ok = false;   // the solved chain matrix matches the current candidate list
@@ -1279,12 +1299,14 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
         }
       }
     };
-    // Solves the chain matrix of the current candidate list (first warp of the secondary half; everybody meets again at
-    // the next barrier of the worker).  In phase P this happens while the tile waits for its turn; a list rebuilt on the
-    // serial path gets its matrix too, so that a tile's changes come out of the same arithmetic (delta = M e0) whether
-    // or not its first speculation held -- which depends on timing -- and two runs agree bit for bit.
+    // Experiment (HB_DEBUG bit 256): the chain as a matrix-vector product delta = M e0 with the chain matrix of the current
+    // candidate list solved by the first warp of the secondary half -- in phase P while the tile waits for its turn, and
+    // again for a list rebuilt on the serial path, so that a tile's changes come out of the same arithmetic whether or
+    // not its first speculation held (which depends on timing).  It shortens phase S by 0.4 us without shortening the
+    // period, and a rebuild on the serial path costs ~7 us, which multiplies in the flip-heavy regime (many ranks, large
+    // n): the default is the step-by-step chain (chain_candidates) in every round -- same arithmetic, bit for bit, too.
     auto build_matrix = [&]() {
-      if (fast && !dense && k > 0 && k <= 32 && !(p.dbg & 128)) {
+      if (fast && !dense && k > 0 && k <= 32 && (p.dbg & 256)) {
         hb::named_bar_sync(1, NT2);
         if (!prim && warp == 0) chain_build_matrix(coef, cmat, k, lane);
         m_ok = true;
@@ -1436,6 +1458,24 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     }
     HB_PHASE(6);
     if (tid == 0) HB_TRACE(t, 3);
+    // ---- then what the tile after next waits for: its corrections (dt = 2), from the rows already in shared memory.
+    // Both halves sum their share of the candidates (even / odd, ascending) in the same order whether the rows are in
+    // shared memory or -- more candidates than row slots -- come from the band in global memory.
+    if (has2) {
+      double pc2 = 0.0;
+      if (fast) {
+#pragma unroll 4
+        for (int sidx = h; sidx < k; sidx += 2)
+          pc2 = fma(gram_as_double(rows2[(size_t)cs.slot[sidx] * B + i]), cs.delta[sidx], pc2);
+      } else {
+        const int32_t* gb = G0 + (size_t)2 * B * B;
+        for (int sidx = h; sidx < k; sidx += 2)
+          pc2 = fma(gram_as_double(__ldcg(gb + (size_t)cs.idx[sidx] * B + i)), cs.delta[sidx], pc2);
+      }
+      if (!prim) part_corr[i] = pc2;
+      hb::named_bar_sync(1, NT2);
+      if (prim) post_corr(p.corr + ((size_t)(t + 2) * DC + 1) * B + i, pc2 + part_corr[i]);
+    }
     // ---- phase C: commit.  The tile's residual updates go to the streaming CTAs first
     if (prim) {
       if (cand) {
@@ -1449,7 +1489,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     }
     // corrections owed to the tiles further ahead, whose dots were (or will be) taken before these updates
     // land: block dt goes to the half with the parity of dt
-    for (int dt = 2 + h; dt < D; dt += 2) {
+    for (int dt = 3 + h; dt < D; dt += 2) {
       if (t + dt >= T) break;
       const double cv = band_correction(cs, k, G0 + (size_t)dt * B * B, B, i);
       post_corr(p.corr + ((size_t)(t + dt) * DC + (dt - 1)) * B + i, cv);
