@@ -856,14 +856,19 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
       fprintf(stderr, "[hb] HB_LEAD takes 1, 2 or 4 and needs 384-row slabs (RL = %d): ignored\n", e->RL);
     }
   }
-  if (const char* lb = getenv("HB_LIMBS")) {
-    // experimental: only the bench's kernel shape is instantiated with integer dots
-    if (atoi(lb) && e->RL == 24) {
-      const void* fn = (const void*)k_sweep<512, 4, 24, false, true>;
-      CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+  {
+    // Integer dots in the streaming CTAs (dp4a on a 48-bit fixed-point residual, hb_limbs.h): the default for the mixture
+    // models with at most 4 classes on 384-row slabs (the shapes with enough rows for the streaming side to matter; the
+    // kernel is instantiated for those); HB_LIMBS=0 keeps the fp64 PRMT + DFMA loop.  Measured at the metric shape with
+    // the scalar side no longer pacing the sweep: 16.3 ms against 18.6 ms per sweep.
+    const char* lb = getenv("HB_LIMBS");
+    const bool want = lb ? atoi(lb) != 0 : true;
+    if (want && e->RL == 24) {
+      CU(cudaFuncSetAttribute((const void*)k_sweep<512, 4, 24, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+      CU(cudaFuncSetAttribute((const void*)k_sweep<512, 2, 24, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
       CU(cudaMalloc(&e->absmax_dev, 8));
       e->limbs = 1;
-    } else if (atoi(lb)) {
+    } else if (lb && want) {
       fprintf(stderr, "[hb] HB_LIMBS needs 384-row slabs (RL = 24); this engine has RL = %d: fp64 dots\n", e->RL);
     }
   }
@@ -1261,7 +1266,7 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
     const void* fn = sweep_kernel_for(in->model_index == HB_MODEL_R ? F : 2, e->RL, dense_model);
     const int nf_kernel = in->model_index == HB_MODEL_R ? F : 2;
     // serial CTA + helpers: mixture models whose classes are decided by thresholds
-    const bool serial = e->serial && !dense_model && pp.use_thr && !e->lead && !e->limbs && !e->cluster2;
+    const bool serial = e->serial && !dense_model && pp.use_thr && !e->lead && !e->cluster2;
     int nscalar = e->NG;
     if (serial) {
       fn = serial_kernel_for(nf_kernel, e->RL);
@@ -1272,7 +1277,7 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
     if (e->lead && !dense_model && nf_kernel > 2 && nf_kernel <= 4)
       fn = e->lead == 1 ? (const void*)k_sweep<512, 4, 24, false, false, 1>
          : e->lead == 2 ? (const void*)k_sweep<512, 4, 24, false, false, 2> : (const void*)k_sweep<512, 4, 24, false, false, 4>;
-    else if (e->limbs && !dense_model && nf_kernel > 2 && nf_kernel <= 4) {
+    else if (e->limbs && !dense_model && nf_kernel <= 4 && !serial) {
       // fixed-point scale of the residual limbs: |q| = |r| rscale must stay below 2^47 while the residual moves during
       // the sweep (factor 4 of head-room over today's largest element; an overflow aborts the sweep with a message)
       double amax = 0.0;
@@ -1286,7 +1291,7 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
       ex_r = std::max(ex_d - 40, std::min(ex_r, ex_d + 40));
       sp.rscale = ldexp(1.0, ex_r);
       sp.rshift = ex_r - ex_d;
-      fn = (const void*)k_sweep<512, 4, 24, false, true>;
+      fn = nf_kernel <= 2 ? (const void*)k_sweep<512, 2, 24, false, true> : (const void*)k_sweep<512, 4, 24, false, true>;
     }
     void* args[] = {(void*)&sp};
     bool launched = false;

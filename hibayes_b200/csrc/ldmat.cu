@@ -246,9 +246,10 @@ __global__ void __launch_bounds__(128) k_ld_panel(const int8_t* __restrict__ Xc,
 // s32, exact) per stage into a 128-lane x 128-column accumulator in tensor memory and commits the stage back to the
 // producer; four epilogue warps read their 32 lanes with tcgen05.ld (32 columns at a time) and turn every exact inner
 // product into the reference's fp64 value with ld_entry() -- the same function, the same bits, as the mma.sync kernel.
-// Warp roles: 0 TMA producer, 1 tensor-memory allocation + MMA issue, 2-5 epilogue (lane quadrant = warp % 4).
+// Warp roles: 0 TMA producer, 1 tensor-memory allocation + MMA issue, 2-9 epilogue (lane quadrant = warp % 4, two warps
+// per quadrant with 64 columns each; the fp64 epilogue -- two IEEE divisions per entry -- is what a tile spends its time on).
 // Every wait is bounded (2 s): a lost signal sets *status instead of hanging the device.
-constexpr int TC_TILE = 128, TC_KB = 128, TC_STAGES = 4;
+constexpr int TC_TILE = 128, TC_KB = 128, TC_STAGES = 3;   // 3 x 32 KB: two CTAs per SM, one's MMAs under the other's epilogue
 constexpr uint32_t TC_STAGE_BYTES = 2u * TC_TILE * TC_KB;   // A + B
 struct TcShared {
   uint64_t full[TC_STAGES], empty[TC_STAGES], acc_full;
@@ -274,7 +275,7 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
   // descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B; the leading byte offset is not used by this layout
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-__global__ void __launch_bounds__(192, 1) k_ld_panel_tc(const __grid_constant__ CUtensorMap tmap, int Kpad, int j0, LdEpi epi,
+__global__ void __launch_bounds__(320, 2) k_ld_panel_tc(const __grid_constant__ CUtensorMap tmap, int Kpad, int j0, LdEpi epi,
                                                         double* __restrict__ pan, int* __restrict__ status) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   uint8_t* tiles = (uint8_t*)(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
@@ -341,10 +342,10 @@ __global__ void __launch_bounds__(192, 1) k_ld_panel_tc(const __grid_constant__ 
     const bool ok = tc_wait(&sh->acc_full, 0u, dead);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (ok) {
-      const int quad = warp & 3;
+      const int quad = warp & 3, half = (warp - 2) >> 2;
       const int row = a0 + 32 * quad + lane;
 #pragma unroll 1
-      for (int cb = 0; cb < TC_TILE / 32; ++cb) {
+      for (int cb = 2 * half; cb < 2 * half + 2; ++cb) {
         uint32_t v[32];
         const uint32_t taddr = tmem + ((uint32_t)(32 * quad) << 16) + (uint32_t)(32 * cb);
         asm volatile(
@@ -646,7 +647,7 @@ static int run_panels(hb_ldmat* h, const int32_t* chr, int has_chisq, double chi
     CU(cudaEventRecord(h->ev0, h->stream));
     if (h->use_tc) {
       const size_t shb = (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(TcShared) + 1024;
-      k_ld_panel_tc<<<dim3(h->Mpad / TC_TILE, wpad / TC_TILE), 192, shb, h->stream>>>(h->tmap, h->Kpad, j0, epi, h->pan, h->status);
+      k_ld_panel_tc<<<dim3(h->Mpad / TC_TILE, wpad / TC_TILE), 320, shb, h->stream>>>(h->tmap, h->Kpad, j0, epi, h->pan, h->status);
     } else {
       k_ld_panel<<<dim3(h->Mpad / 64, wpad / 64), 128, 0, h->stream>>>(h->Xc, h->Kpad, j0, epi, h->pan);
     }
