@@ -1401,13 +1401,22 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
         // exact right-hand side of every SNP of the tile:  x_i'(r - sum_{c<i} x_c delta_c), and in the same pass
         // the corrections this tile owes to the next one (all k changes).  The primary thread takes the even
         // candidates, the secondary the odd ones.
+        // (a warp's 32 SNPs need the diagonal block only for the candidates before its last SNP: beyond that the loop
+        // reads the block towards the next tile alone -- the pass is bound by shared-memory bandwidth)
+        const int rank_hi = __shfl_sync(0xffffffffu, myrank, 31);
+        int sidx = h;
 #pragma unroll 4
-        for (int sidx = h; sidx < k; sidx += 2) {
+        for (; sidx < rank_hi; sidx += 2) {
           const double d = cs.delta[sidx];
           const int sl = cs.slot[sidx];
           const double g0 = gram_as_double(rows0[(size_t)sl * B + i]), g1 = gram_as_double(rows1[(size_t)sl * B + i]);
           prhs = fma(sidx < myrank ? g0 : 0.0, d, prhs);
           pcorr = fma(has1 ? g1 : 0.0, d, pcorr);
+        }
+        if (has1) {
+#pragma unroll 4
+          for (; sidx < k; sidx += 2)
+            pcorr = fma(gram_as_double(rows1[(size_t)cs.slot[sidx] * B + i]), cs.delta[sidx], pcorr);
         }
       } else {
         const double sv = slow_chain_and_sums(k, myrank, G0, B, i, h, has1, dense, model, NT2);
