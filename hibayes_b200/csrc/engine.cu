@@ -1252,8 +1252,6 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   // set (Gram rows, correction slots, parameters) out of L2: -3 % per sweep; HB_XEVICT=0 switches it off
   sp.xevict = 1;
   if (const char* xe = getenv("HB_XEVICT")) sp.xevict = atoi(xe);
-  sp.cond = 1;
-  if (const char* ce = getenv("HB_COND")) sp.cond = atoi(ce);
   if (getenv("HB_PHASES")) sp.dbg |= 64;   // per-phase cycle counters of the serial CTA (they cost ~1 us per tile)
 
   const bool dense_model = in->model_index == HB_MODEL_RR || in->model_index == HB_MODEL_A || in->model_index == HB_MODEL_L;

@@ -68,7 +68,6 @@ struct SweepParams {
   size_t slab_stride, m_pad;
   int n, m, S, R, T, B, D, NS;
   int NCW, NAW, SUBB, NG, KROW;
-  int cond;                   // chain with conditional lanes (mixture models, thresholds, <= 4 classes); HB_COND=0 switches it off
   uint32_t stage_bytes, off_rbuf, off_bar, off_qbuf;
   int model, F;
   double fold[HB_MAX_FOLD];
@@ -948,81 +947,6 @@ __device__ void solve_candidates(const CandSet& cs, int k, const int32_t* __rest
   }
 }
 
-template <int NF>
-__device__ __noinline__ int classify_exact(const double* __restrict__ prm, size_t mp, int j, int nf, double rr, double logpi0);
-// Candidate chain of the mixture models with CONDITIONAL lanes: every lane chains its right-hand side
-//   rhs_s = rhs0_s - sum_{s' < s} G[c_s'][c_s] delta_s'
-// and decides its own class at its turn from that exact right-hand side (thresholds of its SNP; the exact evaluation
-// inside a bracket), so a candidate -- or a near-candidate that was put on the list as a precaution -- never causes a
-// repair round whatever the changes before it do to its right-hand side: only a SNP that is NOT on the list and
-// crosses its first class boundary does.  cond[f * kCondStride + s]: per candidate TL_b, TH_b (b < NF-1), then 1/v_k and
-// sd_k z of the classes k = 1 .. NF-1.  A lane whose class comes out 0 with no old effect has delta = 0 and changes
-// nothing downstream (fma(-g, 0, rhs) = rhs exactly): the result does not depend on who else is on the list.
-constexpr int kCondStride = 64;
-template <int NF>
-__device__ __forceinline__ void chain_conditional(const CandSet& cs, int k, const int32_t* rows, int B, int lane, const double* cond,
-                                                  int nf, const double* __restrict__ prm, size_t mp, int j0, double logpi0) {
-  for (int sb = 0; sb < k; sb += 32) {
-    const int sidx = sb + lane;
-    const bool valid = sidx < k;
-    const int ci = valid ? cs.idx[sidx] : 0;
-    double rhs = valid ? cs.rhs0[sidx] : 0.0;
-    const double gold = valid ? cs.gold[sidx] : 0.0;
-    double TL[NF - 1], TH[NF - 1], iv[NF - 1], sdz[NF - 1];
-#pragma unroll
-    for (int b = 0; b < NF - 1; ++b) {
-      const int sx = valid ? sidx : 0;
-      TL[b] = cond[(size_t)b * kCondStride + sx];
-      TH[b] = cond[(size_t)(NF - 1 + b) * kCondStride + sx];
-      iv[b] = cond[(size_t)(2 * (NF - 1) + b) * kCondStride + sx];
-      sdz[b] = cond[(size_t)(3 * (NF - 1) + b) * kCondStride + sx];
-    }
-    auto gval = [&](int sp) -> double { return gram_as_double(rows[(size_t)cs.slot[sp] * B + ci]); };
-    // candidates of earlier blocks: their changes are final
-    for (int sp = 0; sp < sb; sp += 8) {
-      double gv[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) gv[q] = valid ? gval(sp + q) : 0.0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) rhs = fma(-gv[q], cs.delta[sp + q], rhs);
-    }
-    const int nl = min(32, k - sb);
-    int mycls = 0;
-    double mydelta = 0.0, mygnew = 0.0;
-#pragma unroll
-    for (int hc = 0; hc < 2; ++hc) {
-      if (16 * hc < nl) {
-        double greg[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int lp = 16 * hc + q;
-          const int row = min(sb + lp, k - 1);
-          greg[q] = (valid && lp < lane && lp < nl) ? gval(row) : 0.0;
-        }
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int lp = 16 * hc + q;
-          if (lp >= nl) break;
-          // the class and the change this lane would take with its present right-hand side; final for lane lp
-          int c = thr_class<NF>(nf, rhs * rhs, TL, TH);
-          if (c < 0) c = (lane == lp && valid) ? classify_exact<NF>(prm, mp, j0 + ci, nf, rhs * rhs, logpi0) : 0;
-          double civ = 0.0, csd = 0.0;
-#pragma unroll
-          for (int b = 0; b < NF - 1; ++b)
-            if (c == b + 1) { civ = iv[b]; csd = sdz[b]; }
-          const double gn = (c > 0) ? fma(rhs, civ, csd) : 0.0;
-          const double dl = gn - gold;
-          const double d = __shfl_sync(0xffffffffu, dl, lp);
-          if (lane == lp) { mycls = c; mydelta = dl; mygnew = gn; }
-          rhs = fma(-greg[q], d, rhs);   // greg = 0 for the lanes at or before lp: their right-hand side is final
-        }
-      }
-    }
-    if (valid) { cs.cls[sidx] = mycls; cs.delta[sidx] = mydelta; cs.gnew[sidx] = mygnew; }
-    __syncwarp();
-  }
-}
-
 // the same for two band blocks at once (one wait for both)
 __device__ __noinline__ void gather_rows_2(int32_t* dst1, const int32_t* __restrict__ blk1, int32_t* dst2, const int32_t* __restrict__ blk2,
                                           const int* idx, int k, int B, int i) {
@@ -1097,9 +1021,7 @@ __device__ __noinline__ int classify_exact(const double* __restrict__ prm, size_
 // LEAD (experiment, HB_LEAD=1|2|4): the speculation of phase P ignores the corrections owed by the LEAD nearest tiles, as
 // if it had run that many tiles earlier; the sweep's `respec`/`rounds` counters then say how often a candidate list
 // built that early is incomplete (one serial CTA with packages).  LEAD = 0 is the product.
-// COND: the mixture models' chain with conditional lanes (chain_conditional) -- every SNP on the candidate list decides its
-// class inside the chain; needs class thresholds (use_thr) and at most 4 classes.
-template <int NF, bool DENSE, int LEAD = 0, bool COND = false>
+template <int NF, bool DENSE, int LEAD = 0>
 __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
   // the parameters are read all along the serial phase: keep a copy in shared memory instead of going through the
   // constant cache, which the long code of a tile keeps evicting (a miss there costs a trip to L2)
@@ -1154,8 +1076,6 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
   }
   const int KROW = p.KROW;
   const int NT2 = 2 * B;   // threads of the worker
-  double* cond = cmat;   // (COND) per-candidate thresholds and draw constants: 4 (NF-1) x kCondStride doubles <= 32 x 33
-  const bool cond_mode = COND && p.cond && p.use_thr && !DENSE && (NF <= 4) && KROW <= kCondStride;
   if (tid < 8) gctl[tid] = 0;
   if (cl2) {
     for (int w = tid; w < 2 * 256; w += NT2) ((unsigned long long*)hbuf)[w] = kCorrEmpty;
@@ -1285,16 +1205,13 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     // zero, or right-hand side within 30 % of its first class boundary) are gathered once, as soon as the dots are
     // there; candidate lists are then rebuilt from these rows without touching memory again.
     bool extra = false;   // candidate that had no row yet
-    bool sticky = false;  // (COND) was on the candidate list in an earlier round of this tile: stays on it
-    bool nearc = false;   // (COND) near its first class boundary while speculation keeps missing: a conditional lane
     int ns = 0;
     // `widen`: the wider row set is only worth its gather while speculation keeps missing (chains far from
     // equilibrium, very large n); every tile that needed a second look switches it on for this worker's next 16 tiles
     auto select_rows = [&](double rr_spec) {
       if (prim) {
-        const bool near = widen > 0 && use_thr && TH[0] > 0.0 && TH[0] < 1e300 && rr_spec >= (cond_mode ? 0.36 : 0.49) * TH[0];
-        nearc = nearc || (cond_mode && act && near);
-        const bool want = act && (dense || gold != 0.0 || cls > 0 || near || extra || sticky || nearc);
+        const bool near = widen > 0 && use_thr && TH[0] > 0.0 && TH[0] < 1e300 && rr_spec >= 0.49 * TH[0];
+        const bool want = act && (dense || gold != 0.0 || cls > 0 || near || extra);
         const unsigned bal = __ballot_sync(0xffffffffu, want);
         if (lane == 0) wcnt[warp] = __popc(bal);
         hb::named_bar_sync(4, B);   // primary half only
@@ -1332,8 +1249,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     bool m_ok = false;   // the solved chain matrix matches the current candidate list
     // candidate list of the current classes
     auto compact = [&]() {
-      cand = act && (cls > 0 || gold != 0.0 || (cond_mode && (sticky || nearc)));
-      sticky = sticky || cand;
+      cand = act && (cls > 0 || gold != 0.0);
       bool missing = false;
       if (prim) {
         const unsigned bal = __ballot_sync(0xffffffffu, cand);
@@ -1361,17 +1277,6 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
             if (kk == cls) { iv = civ[kk - 1]; sdz = csdz[kk - 1]; }
           cs.iv[myrank] = iv;
           cs.sdz[myrank] = sdz;
-          if constexpr (COND && NF <= 4) {
-            if (cond_mode && myrank < kCondStride) {
-#pragma unroll
-              for (int b = 0; b < NF - 1; ++b) {
-                cond[(size_t)b * kCondStride + myrank] = TL[b];
-                cond[(size_t)(NF - 1 + b) * kCondStride + myrank] = TH[b];
-                cond[(size_t)(2 * (NF - 1) + b) * kCondStride + myrank] = civ[b];
-                cond[(size_t)(3 * (NF - 1) + b) * kCondStride + myrank] = csdz[b];
-              }
-            }
-          }
         }
       }
       if (hb::named_bar_or(1, NT2, missing && fast)) {
@@ -1384,7 +1289,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
       if (!prim) { k = gctl[1]; myrank = rank_sh[i]; }
       // coefficients of the chain's first 32 candidates (read by the chain warp after the next barrier)
       m_ok = false;
-      if (fast && !dense && !cond_mode) {
+      if (fast && !dense) {
         const int kk = min(k, 32);
         for (int e = tid; e < 32 * 32; e += NT2) {
           const int lp = e >> 5, sc = e & 31;
@@ -1472,7 +1377,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
       int cls0 = cls;
       // (only while speculation has recently missed on this worker: `widen`; otherwise the final check below is
       // enough and the serial path saves one classification)
-      if (nrounds == 1 && widen > 0 && prim && act && !(cond_mode && fast && cand)) cls0 = classify(rhs0);
+      if (nrounds == 1 && widen > 0 && prim && act) cls0 = classify(rhs0);
       if (hb::named_bar_or(1, NT2, cls0 != cls)) {
         cls = cls0;
         compact();
@@ -1486,12 +1391,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
       double prhs = 0.0, pcorr = 0.0;
       if (fast) {
         if (tid < 32 && k > 0) {
-          bool done = false;
-          if constexpr (COND && NF <= 4) {
-            if (cond_mode) { chain_conditional<NF>(cs, k, rows0, B, lane, cond, nf, p.prm, mp, t * B, p.logpi0); done = true; }
-          }
-          if (done) {}
-          else if (dense) solve_candidates<true>(cs, k, G0, rows0, B, model, lane);
+          if (dense) solve_candidates<true>(cs, k, G0, rows0, B, model, lane);
           else if (m_ok) chain_matvec(cs, k, cmat, lane);
           else chain_candidates<true>(cs, k, G0, rows0, B, lane, coef);
         }
@@ -1533,9 +1433,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
       }
       int cls2 = 0;
       double gnew2 = gold;
-      const bool decided = cond_mode && fast && cand && prim;   // class taken inside the chain from the exact right-hand side
-      if (decided) { cls = cs.cls[myrank]; cls2 = cls; }
-      else if (act && prim) {
+      if (act && prim) {
         cls2 = classify(rhs);
         if (dense) {
           gnew2 = fma(rhs, civ[0], csdz[0]);
@@ -1557,6 +1455,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     }
     if (dead) break;
     rounds_total += nrounds;
+    changed_total += k;
     widen = (nrounds > 1 || respec_tile) ? 16 : max(widen - 1, 0);
     // ---- the tile is final.  First what the next tile waits for: its corrections (dt = 1)
     if (has1 && prim) {
@@ -1588,34 +1487,14 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     }
     // ---- phase C: commit.  The tile's residual updates go to the streaming CTAs first
     if (prim) {
-      // (COND) list members whose class came out 0 with no old effect changed nothing: they are not published
-      bool pub = cand;
-      int kpub = k, prank = myrank;
-      if (cond_mode) {
-        pub = cand && cs.delta[myrank] != 0.0;
-        const unsigned balp = __ballot_sync(0xffffffffu, pub);
-        if (lane == 0) wcnt[warp] = __popc(balp);
-        hb::named_bar_sync(4, B);   // primary half only
-        int pre = 0;
-        kpub = 0;
-        for (int w = 0; w < nwarp; ++w) {
-          const int c = wcnt[w];
-          if (w < warp) pre += c;
-          kpub += c;
-        }
-        prank = pre + __popc(balp & ((1u << lane) - 1u));
-      }
       if (cand) {
         gnew = cs.gnew[myrank];
+        st_relaxed_u64(p.q_delta + (size_t)t * B + myrank, (unsigned long long)__double_as_longlong(cs.delta[myrank]));
+        st_relaxed_s32(p.q_snp + (size_t)t * B + myrank, j);
         p.g[j] = gnew;
       }
-      if (pub) {
-        st_relaxed_u64(p.q_delta + (size_t)t * B + prank, (unsigned long long)__double_as_longlong(cs.delta[myrank]));
-        st_relaxed_s32(p.q_snp + (size_t)t * B + prank, j);
-      }
-      if (i == 0) { st_relaxed_s32(p.tile_cnt + t, kpub); HB_TRACE(t, 4); }
+      if (i == 0) { st_relaxed_s32(p.tile_cnt + t, k); HB_TRACE(t, 4); }
       if (act) p.tracker[j] = cls;
-      changed_total += kpub;
     }
     // corrections owed to the tiles further ahead, whose dots were (or will be) taken before these updates
     // land: block dt goes to the half with the parity of dt
@@ -1654,6 +1533,6 @@ __global__ void __launch_bounds__(MAXT, 1) k_sweep(const __grid_constant__ Sweep
     if ((int)blockIdx.x == p.scalar0) hbk::serial_role<NF>(p, smem);
     else hbk::helper_role<NF>(p, smem);
   } else {
-    hbk::scalar_role<NF, DENSE, LEAD, (!DENSE && NF <= 4 && LEAD == 0)>(p, smem);
+    hbk::scalar_role<NF, DENSE, LEAD>(p, smem);
   }
 }

@@ -215,6 +215,10 @@ typedef struct {
   int impt, dominance;              /* read_bed()'s impt and d */
 } hb_bed_source;
 
+/* Argument list of Rcpp::List Bayes(...) (/root/reference/src/Bayes.cpp:60-88).  Two of its 27 arguments have no field
+ * here: Kival / Ki, the eigen-decomposition of the GRM for BSLMM's polygenic term (Bayes.cpp:518-552: two dense n x n
+ * products per iteration and arma::randn) -- that term is not offloaded; the Rcpp shim refuses a non-NULL Ki
+ *  and model "BSLMM" without it is the BayesCpi sweep, as in the reference (Bayes.cpp:97-106). */
 typedef struct {
   int n, m;
   const double* y;          /* n                                   (arma::vec& y) */
