@@ -46,7 +46,7 @@ PI_R = [0.95, 0.02, 0.02, 0.01]
 FOLD = [0.0, 1e-4, 1e-3, 1e-2]
 if os.environ.get("HB_BENCH_FOLD_SCALE"):   # experiments only: stronger effects stress the speculation of the scalar chain
     FOLD = [f * float(os.environ["HB_BENCH_FOLD_SCALE"]) for f in FOLD]
-KERNELS_PER_STEP = 5   # k_prep, k_sweep, k_post1, k_post2, k_tail
+KERNELS_PER_STEP = 6   # k_prep, k_absmax (scale of the integer dots), k_sweep, k_post1, k_post2, k_tail
 
 
 def _peaks():

@@ -822,6 +822,9 @@ extern "C" int hb_engine_create(const hb_engine_config* cfg, hb_engine** out) {
   const size_t stream_smem = e->off_qbuf + qbuf_bytes;
   const size_t scalar_smem = hbk::scalar_smem_bytes(e->B);
   e->KROW = hbk::scalar_krow(e->B);
+  // test hook: fewer row slots, so that tiles take the path that reads the Gram band from global memory (a tile's result
+  // must not depend on the path: tests/test_scalar_modes_gpu.py)
+  if (const char* kr = getenv("HB_KROW")) e->KROW = std::max(1, std::min(e->KROW, atoi(kr)));
   e->smem_bytes = std::max(stream_smem, scalar_smem);
   if (e->serial) {
     e->KROW_S = hbk::serial_krow(e->B);
@@ -1252,6 +1255,8 @@ extern "C" int hb_engine_sweep(hb_engine* e, const hb_sweep_in* in, hb_sweep_out
   // set (Gram rows, correction slots, parameters) out of L2: -3 % per sweep; HB_XEVICT=0 switches it off
   sp.xevict = 1;
   if (const char* xe = getenv("HB_XEVICT")) sp.xevict = atoi(xe);
+  sp.near_frac = 0.49;   // |rhs| within 30 % of the boundary
+  if (const char* nf_ = getenv("HB_NEAR")) sp.near_frac = atof(nf_);
   if (getenv("HB_PHASES")) sp.dbg |= 64;   // per-phase cycle counters of the serial CTA (they cost ~1 us per tile)
 
   const bool dense_model = in->model_index == HB_MODEL_RR || in->model_index == HB_MODEL_A || in->model_index == HB_MODEL_L;

@@ -91,6 +91,7 @@ struct SweepParams {
   int* pkg_flag;              // [T] 0 = not written yet, else 1 + number of row slots (| 1 << 20: no rows, generic path)
   int* miss_tile;             // [1] last tile that needed a second round (the helpers widen their row sets after it)
   int xevict;                 // genotype tiles are streamed with an L2 evict_first hint (HB_XEVICT)
+  double near_frac;           // rows are also gathered for SNPs with rhs^2 >= near_frac * (first class boundary) while speculation misses
 };
 
 enum { HB_ABORT_TIMEOUT_STREAM = 1, HB_ABORT_TIMEOUT_SCALAR = 2, HB_ABORT_TIMEOUT_TMA = 3, HB_ABORT_OVERFLOW = 4,
@@ -800,7 +801,8 @@ __device__ __forceinline__ void chain_candidates(const CandSet& cs, int k, const
     if (ROWS && sb == 0) {
       // first 32 candidates: the coefficients -G[c_lp][c_s]/v_s were laid out in shared memory when the candidate
       // list was built (phase P, off the serial path): coef[32 lp + s], zero for lp >= s.  Two halves of 16 steps,
-      // one shuffle and one fma each; steps beyond the last candidate are skipped.
+      // one shuffle and one fma each; steps beyond the last candidate are skipped.  (A rolled loop with the next
+      // coefficient fetched a step ahead was measured: 135 instead of 105 cycles per step.)
 #pragma unroll
       for (int hc = 0; hc < 2; ++hc) {
         if (16 * hc < nl) {
@@ -997,6 +999,20 @@ __device__ __noinline__ double slow_chain_and_sums_cs(const CandSet& cs, int k, 
   // the primary half returns its right-hand-side sum, the secondary half the corrections for the next tile
   if (h == 0) return band_correction(cs, myrank, G0, B, i);
   return has1 ? band_correction(cs, k, G0 + (size_t)B * B, B, i) : 0.0;
+}
+__device__ __noinline__ void slow_chain_only_cs(const CandSet& cs, int k, const int32_t* __restrict__ G0, int B, bool dense, int model,
+                                               int nthreads) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < 32 && k > 0) {
+    if (dense) solve_candidates<false>(cs, k, G0, nullptr, B, model, lane);
+    else chain_candidates<false>(cs, k, G0, nullptr, B, lane);
+  }
+  hb::named_bar_sync(1, nthreads);
+}
+__device__ __forceinline__ void slow_chain_only(int k, const int32_t* __restrict__ G0, int B, bool dense, int model, int nthreads) {
+  extern __shared__ __align__(128) uint8_t smem_slow2[];
+  const CandSet cs = make_candset(smem_slow2, B);
+  slow_chain_only_cs(cs, k, G0, B, dense, model, nthreads);
 }
 __device__ __forceinline__ double slow_chain_and_sums(int k, int myrank, const int32_t* __restrict__ G0, int B,
                                                     int i, int h, bool has1, bool dense, int model, int nthreads) {
@@ -1210,7 +1226,7 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
     // equilibrium, very large n); every tile that needed a second look switches it on for this worker's next 16 tiles
     auto select_rows = [&](double rr_spec) {
       if (prim) {
-        const bool near = widen > 0 && use_thr && TH[0] > 0.0 && TH[0] < 1e300 && rr_spec >= 0.49 * TH[0];
+        const bool near = widen > 0 && use_thr && TH[0] > 0.0 && TH[0] < 1e300 && rr_spec >= p.near_frac * TH[0];
         const bool want = act && (dense || gold != 0.0 || cls > 0 || near || extra);
         const unsigned bal = __ballot_sync(0xffffffffu, want);
         if (lane == 0) wcnt[warp] = __popc(bal);
@@ -1419,8 +1435,20 @@ __device__ void scalar_role(const SweepParams& pin, uint8_t* smem) {
             pcorr = fma(gram_as_double(rows1[(size_t)cs.slot[sidx] * B + i]), cs.delta[sidx], pcorr);
         }
       } else {
-        const double sv = slow_chain_and_sums(k, myrank, G0, B, i, h, has1, dense, model, NT2);
-        if (prim) prhs = sv; else pcorr = sv;
+        // more candidates than row slots: chain and sums straight from the band in global memory -- the SAME order of
+        // additions as above (even / odd candidates per half), so that a tile's result does not depend on which of the
+        // two paths it took: that depends on the row set, i.e. on `widen`, i.e. on timing, and ranks of a row-sharded
+        // run must not drift apart in the last bit (their decisions would follow)
+        slow_chain_only(k, G0, B, dense, model, NT2);
+        const int32_t* G1 = G0 + (size_t)B * B;
+        for (int sidx = h; sidx < k; sidx += 2) {
+          const double d = cs.delta[sidx];
+          const size_t o = (size_t)cs.idx[sidx] * B + i;
+          const double g0 = (sidx < myrank) ? gram_as_double(__ldcg(G0 + o)) : 0.0;
+          const double g1 = has1 ? gram_as_double(__ldcg(G1 + o)) : 0.0;
+          prhs = fma(g0, d, prhs);
+          pcorr = fma(g1, d, pcorr);
+        }
       }
       if (!prim) { part_rhs[i] = prhs; part_corr[i] = pcorr; }
       HB_PHASE(9);

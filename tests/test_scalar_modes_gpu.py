@@ -129,3 +129,22 @@ def test_metric_rows_against_the_oracle(oracle, mode):
         got = hb.Bayes(y, X, "BayesR", PI_R, fold=FOLD_R, **kw)
     _compare(got, ref)
     assert got["diag"]["tiles_total"] == 3 * 256
+
+
+@pytest.mark.parametrize("model,Pi,fold", [("BayesR", PI_R, FOLD_R), ("BayesCpi", [0.9, 0.1], None), ("BayesRR", [0.0, 1.0], None)])
+def test_result_does_not_depend_on_the_row_slot_path(model, Pi, fold):
+    """A tile whose candidates do not fit the row slots reads the Gram band from global memory instead of shared memory.
+    Which path a tile takes depends on the row set, i.e. on timing -- so both must give the same bits, or the ranks of a
+    row-sharded run drift apart (seen on 8 GPUs in the flip-heavy regime before the two paths summed in the same order)."""
+    y, X = synth(6000, 3072, seed=17, n_causal=120, h2=0.8)
+    fold_ = None if fold is None else [0.0] + [16 * f for f in fold[1:]]
+    kw = dict(niter=10, nburn=2, thin=2, seed=606)
+    with _env(HB_SERIAL=0):
+        a = hb.Bayes(y, X, model, Pi, fold=fold_, **kw)
+        with _env(HB_KROW=3):
+            b = hb.Bayes(y, X, model, Pi, fold=fold_, **kw)
+        with _env(HB_KROW=12):
+            c = hb.Bayes(y, X, model, Pi, fold=fold_, **kw)
+    for other in (b, c):
+        assert np.array_equal(a["diag"]["tracker"], other["diag"]["tracker"])
+        assert np.array_equal(a["alpha"], other["alpha"]) and np.array_equal(a["g"], other["g"]) and a["Ve"] == other["Ve"]
