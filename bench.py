@@ -22,6 +22,7 @@ reductions -- what replaces Bayes.cpp:586-823 -- driven by the host-side scalar 
               buffers; ms per sweep and rounds per tile around iterations 10 / 100 / 500 / 1000.
 --config c3   BASELINE configs[2]: BayesB n = 200 000 x m = 1 000 000 row-sharded over 8 GPUs (25 000 rows per GPU).
 --config c4   BASELINE configs[3]: sbrm() SBayesD on a dense fp64 LD matrix of the largest m that fits (--m, default 100 000).
+--config c5   BASELINE configs[4] surrogate: the single-step call of Bayes() (J + epsilon on the device) with integer rows, 1 GPU.
 `--impl reference`  the reference's own CPU data path (per-SNP ddot + 2 daxpy on a column-major fp64 matrix,
             Bayes.cpp:751-802, all host threads) on a bounded column sample of the same workload (oracle port: the
             reference itself needs R/Rcpp/Armadillo and cannot be built here).
@@ -586,6 +587,77 @@ def run_c4(args):
     print(json.dumps(line), flush=True)
 
 
+def random_pedigree_ainv(n_ped, n_founders, rng):
+    """A^-1 of a random pedigree by Henderson's rules without inbreeding (what make_Ainv builds, src/rm.cpp:173-206, up
+    to its integer-division quirk): animals 0 .. n_founders-1 have no parents, every later animal two random earlier ones."""
+    import scipy.sparse as sp
+    kids = np.arange(n_founders, n_ped)
+    sire = (rng.random(kids.size) * kids).astype(np.int64)
+    dam = (rng.random(kids.size) * kids).astype(np.int64)
+    dam = np.where(dam == sire, (dam + 1) % kids, dam)
+    rows = [np.arange(n_founders)]
+    cols = [np.arange(n_founders)]
+    vals = [np.ones(n_founders)]
+    for a, b, v in ((kids, kids, 2.0), (kids, sire, -1.0), (sire, kids, -1.0), (kids, dam, -1.0), (dam, kids, -1.0),
+                    (sire, sire, 0.5), (dam, dam, 0.5), (sire, dam, 0.5), (dam, sire, 0.5)):
+        rows.append(a); cols.append(b); vals.append(np.full(kids.size, v))
+    A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n_ped, n_ped))
+    return sp.csc_matrix(A)
+
+
+def run_c5(args):
+    """BASELINE configs[4] as far as this build goes: ssbrm()'s call of Bayes() -- BayesCpi with the single-step term (J,
+    sparse Gi = A^-1 block of the non-genotyped individuals, epsilon sampler) -- on ONE GPU with INTEGER rows for the
+    non-genotyped individuals too (the real-valued imputed rows of R/ssbayes.r:305 are not loadable: DESIGN.md section 8).
+    n = 30 000 genotyped + 20 000 non-genotyped individuals with records, pedigree of 200 000 (150 000 non-genotyped:
+    qe), m = --m (default 200 000)."""
+    import hibayes_b200 as hb
+    n_g, n_n, n_ped, qe = 30000, 20000, 200000, 150000
+    n = n_g + n_n
+    m = 200000 if args.m == 1000000 else args.m
+    niter = 60 if args.niter == 1000 else args.niter
+    rng = np.random.default_rng(args.seed)
+    t0 = time.time()
+    X = host_genotypes(n, m, args.seed)
+    causal = rng.choice(m, size=min(1000, m), replace=False)
+    gv = X[:, causal].astype(np.float64) @ rng.standard_normal(causal.size)
+    y = gv * math.sqrt(0.5 / gv.var()) + rng.normal(scale=math.sqrt(0.5), size=n)
+    Ainv = random_pedigree_ainv(n_ped, 20000, rng)
+    nongeno = np.sort(rng.choice(n_ped, size=qe, replace=False))      # the pedigree members without genotypes
+    Gi = Ainv[nongeno][:, nongeno].tocsc()
+    index1 = np.sort(rng.choice(qe, size=n_n, replace=False)) + 1      # the ones with a record: rows n_g .. n-1 of y
+    J = np.concatenate([-np.ones(n_g), -rng.uniform(0.2, 1.0, n_n)])
+    t_gen = time.time() - t0
+    t0 = time.perf_counter()
+    res = hb.Bayes(y, X, "BayesCpi", [0.95, 0.05], niter=niter, nburn=niter // 2, thin=5, seed=args.seed,
+                   epsl_y_J=J, epsl_Gi=Gi, epsl_index=index1)
+    call_s = time.perf_counter() - t0
+    dg = res["diag"]
+    run_s = call_s - dg["seconds_setup"]
+    sweep_ms = float(np.mean(dg["sweep_ms_trace"][niter // 2:]))
+    peak, peak_src = _peaks()
+    line = {
+        "metric": METRIC.replace("bayesr_n50k", "ssbayescpi_n50k"), "value": m * niter / run_s, "unit": UNIT, "n_gpus": 1, "steps": niter,
+        "warmup": 0, "ms_per_step": 1e3 * run_s / niter, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[4] surrogate: Bayes() as ssbrm() calls it, BayesCpi + single-step term, n=%d genotyped + %d "
+                               "non-genotyped records (INTEGER rows: the real-valued row class is not built), pedigree %d, qe=%d, m=%d, "
+                               "%d iterations through hb_bayes() on 1 GPU" % (n_g, n_n, n_ped, qe, m, niter),
+                   "n": n, "m": m, "qe": qe, "ne": n_n, "Gi_nnz": int(Gi.nnz), "device_sweep_ms": sweep_ms,
+                   "non_snp_ms_per_iteration": 1e3 * run_s / niter - sweep_ms, "x_load_s": dg["seconds_setup"], "setup_s": t_gen,
+                   "call_s": call_s, "Vg": res["Vg"], "Ve": res["Ve"], "Veps": res["Veps"], "J": res["J"],
+                   "rounds_per_tile": float(dg["rounds_total"]) / max(1, dg["tiles_total"])},
+        "roofline": {"bound": "hbm", "achieved": n * m / (sweep_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": n * m / (sweep_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "k_prep + k_sweep + reductions (device time of an iteration's SNP sweep)", "kernel_ms": sweep_ms,
+                     "algorithmic_bytes_per_launch": n * m},
+        "e2e": {"value": m * niter / run_s, "unit": UNIT, "h2d_bytes_per_step": int(8 * n / niter),
+                "d2h_bytes_per_step": int((3 * 8 * m + 16 * n + 8 * qe) / niter), "path": "hb_bayes(), timed = the call minus its set-up"},
+        "gpu_launches": (KERNELS_PER_STEP + 9) * niter,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def allsum_max(comm, x):
     """max over ranks of a host scalar"""
     if not comm:
@@ -602,7 +674,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--config", default="metric", choices=["metric", "c2", "c3", "c4"])
+    ap.add_argument("--config", default="metric", choices=["metric", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--n", type=int, default=50000)
     ap.add_argument("--m", type=int, default=1000000)
@@ -621,6 +693,8 @@ def main():
         run_c2(args)
     elif args.config == "c4":
         run_c4(args)
+    elif args.config == "c5":
+        run_c5(args)
     else:
         run_gpu(args)
 
