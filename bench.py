@@ -644,7 +644,8 @@ def run_c5(args):
                                "non-genotyped records (INTEGER rows: the real-valued row class is not built), pedigree %d, qe=%d, m=%d, "
                                "%d iterations through hb_bayes() on 1 GPU" % (n_g, n_n, n_ped, qe, m, niter),
                    "n": n, "m": m, "qe": qe, "ne": n_n, "Gi_nnz": int(Gi.nnz), "device_sweep_ms": sweep_ms,
-                   "non_snp_ms_per_iteration": 1e3 * run_s / niter - sweep_ms, "x_load_s": dg["seconds_setup"], "setup_s": t_gen,
+                   "other_ms_per_iteration": 1e3 * run_s / niter - sweep_ms,
+                   "other_is": "J + epsilon step, host draws, PIP / record stores, and the end-of-call summaries (X * alpha, downloads) spread over the iterations", "x_load_s": dg["seconds_setup"], "setup_s": t_gen,
                    "call_s": call_s, "Vg": res["Vg"], "Ve": res["Ve"], "Veps": res["Veps"], "J": res["J"],
                    "rounds_per_tile": float(dg["rounds_total"]) / max(1, dg["tiles_total"])},
         "roofline": {"bound": "hbm", "achieved": n * m / (sweep_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
