@@ -40,6 +40,20 @@ def synth_geno_host_into(Xblock, seed, col_offset=0, row_offset=0):
     _lib.check(L.hb_synth_geno_host_cols(Xblock.ctypes.data, n, col_offset, nc, seed, row_offset))
 
 
+def _is_zero_chromosome(v):
+    """"0" as a string, 0 / 0.0 as a number (R compares the values after as.character / as.numeric)."""
+    if isinstance(v, (bytes, str)):
+        t = v.decode() if isinstance(v, bytes) else v
+        try:
+            return float(t) == 0.0
+        except ValueError:
+            return False
+    try:
+        return float(v) == 0.0
+    except (TypeError, ValueError):
+        return False
+
+
 class BedGeno:
     """Genotypes held as the image of a SNP-major PLINK .bed file; accepted by Bayes() and LdMat in place of
     a matrix, decoded on the device (hb_engine_load_bed / hb_ldmat_load_bed; read_bed<char>() of
@@ -168,7 +182,7 @@ def ldmat_plan(m, map_chr=None, chisq=None, ldchr=False):
             chisq = None  # :53-55
         if any(v is None or (isinstance(v, float) and math.isnan(v)) for v in map_chr.tolist()):
             raise RuntimeError("NAs are not allowed in chromosome.")  # :60
-        if any(str(v) == "0" for v in map_chr.tolist()):
+        if any(_is_zero_chromosome(v) for v in map_chr.tolist()):
             raise RuntimeError("0 is not allowed in chromosome.")  # :63
     else:
         if chisq is not None and chisq == 0:
@@ -478,7 +492,7 @@ def ibrm_plan(method="BayesCpi", Pi=None, fold=None, niter=None, nburn=None, thi
         if (pos == 0).any():
             raise RuntimeError("0 is not allowed in physical position.")
         names = [str(v) for v in np.asarray(map_chr).tolist()]
-        if any(v == "0" for v in names):
+        if any(_is_zero_chromosome(v) for v in np.asarray(map_chr).tolist()):
             raise RuntimeError("0 is not allowed in chromosome.")
         # numeric chromosome codes; names that are not numbers follow the largest number (:234-243)
         def num(v):
