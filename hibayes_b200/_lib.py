@@ -26,7 +26,7 @@ SYMBOLS = [
     "hb_test_bed_decode_snp", "hb_engine_predict_samples", "hb_test_ld_entries", "hb_test_ld_stats", "hb_test_limb_dot", "hb_cutwind_by_bp", "hb_cutwind_by_num",
     "hb_engine_last_predict_ms", "hb_engine_device_state", "hb_fx_create", "hb_fx_destroy", "hb_fx_dot", "hb_fx_self_dot", "hb_fx_axpy", "hb_fx_level_sums",
     "hb_fx_level_apply", "hb_fx_eps_set_counts", "hb_fx_eps_rhs", "hb_fx_eps_set_rhs", "hb_fx_eps_sample", "hb_fx_eps_accumulate",
-    "hb_fx_eps_get", "hb_fx_describe",
+    "hb_fx_eps_get", "hb_fx_describe", "hb_fx_k_step", "hb_fx_k_accumulate", "hb_fx_k_ghat_vec", "hb_engine_xt_vec",
 ]
 
 
@@ -93,6 +93,7 @@ class BayesArgs(C.Structure):
         ("rank", C.c_int), ("world", C.c_int), ("n_total", C.c_longlong), ("comm_ctx", C.c_void_p),
         ("allreduce_sum_f64", ALLREDUCE_F64), ("allreduce_sum_i32_dev", ALLREDUCE_I32_DEV),
         ("allgather_bytes", ALLGATHER_BYTES),
+        ("nk", C.c_int), ("Kival", C.c_void_p), ("Ki", C.c_void_p),
     ]
 
 

@@ -225,8 +225,8 @@ def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, nite
     """GPU twin of hibayes' Bayes().  R: (n, nr) integer level codes (0-based) standing for the
     CharacterMatrix of environmental random effects; seed: the Philox run key the Rcpp shim
     derives from R's RNG state (the reference takes no seed argument, Bayes.cpp:60-88)."""
-    if Ki is not None or Kival is not None:
-        raise NotImplementedError("BSLMM polygenic term (Ki/Kival) is not part of this build")
+    if (Ki is None) != (Kival is None):
+        raise RuntimeError("Ki and Kival should be provided together.")
     L = _lib.load_library()
     y = np.ascontiguousarray(y, dtype=np.float64)
     n = y.shape[0]
@@ -315,6 +315,15 @@ def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, nite
         a.epsl_y_J, a.epsl_index, a.Gi_colptr, a.Gi_rowidx, a.Gi_val = _ptr(yj), _ptr(ei), _ptr(cp), _ptr(ri), _ptr(gv)
         keep += [ei, cp, ri, gv, yj]
     a.ne, a.qe = ne, qe
+    if Ki is not None:   # BSLMM: eigenvectors (n x n) and eigenvalues of the relationship matrix (Bayes.cpp:218-233)
+        Kf = np.asfortranarray(Ki, dtype=np.float64)
+        kv = np.ascontiguousarray(Kival, dtype=np.float64)
+        if Kf.ndim != 2 or Kf.shape[0] != Kf.shape[1]:
+            raise RuntimeError("variance-covariance matrix should be in square.")   # :221
+        if Kf.shape[0] != n or kv.shape[0] != Kf.shape[1]:
+            raise RuntimeError("Ki / Kival do not match the number of individuals")
+        a.nk, a.Ki, a.Kival = Kf.shape[1], _ptr(Kf), _ptr(kv)
+        keep += [Kf, kv]
     a.device, a.tile_snps, a.lag_tiles, a.n_slabs = device, tile_snps, lag_tiles, n_slabs
     if comm is not None and comm.world > 1:
         a.rank, a.world, a.n_total = comm.rank, comm.world, comm.total_rows(n)
@@ -479,7 +488,7 @@ def ibrm_plan(method="BayesCpi", Pi=None, fold=None, niter=None, nburn=None, thi
     if method not in IBRM_METHODS:
         raise ValueError("'arg' should be one of " + ", ".join(IBRM_METHODS))     # match.arg, :166
     if method == "BSLMM":
-        raise NotImplementedError("BSLMM's polygenic term (make_grm + Kival/Ki) is not part of this build")
+        raise NotImplementedError("ibrm(\"BSLMM\") builds the GRM and its eigen-decomposition in R (make_grm): pass Ki / Kival to Bayes() instead")
     windindx = None
     if windsize is not None or windnum is not None:
         if method in ("BayesA", "BayesRR", "BayesL"):

@@ -154,6 +154,63 @@ __global__ void k_eps_quad(EpsDev d, double* __restrict__ partial) {
   if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
+// ---- BSLMM (Bayes.cpp:518-552): dense products with the eigenvectors K (n x nk column-major)
+// out[j] = K[:, j] . v : one warp per column, lane-strided partial sums, fixed shuffle tree
+__global__ void k_gemv_t(const double* __restrict__ K, int n, int nk, const double* __restrict__ v, const double* __restrict__ v2,
+                         double* __restrict__ out) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (j >= nk) return;
+  const double* col = K + (size_t)j * n;
+  double s = 0.0;
+  for (int i = lane; i < n; i += 32) s = fma(col[i], v2 ? v[i] + v2[i] : v[i], s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) out[j] = s;
+}
+// out[i] = sum_j K[i, j] w[j] : one thread per row, columns in order
+__global__ void k_gemv_n(const double* __restrict__ K, int n, int nk, const double* __restrict__ w, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int j = 0; j < nk; ++j) s = fma(K[(size_t)j * n + i], w[j], s);
+  out[i] = s;
+}
+// w[j] = c1[j] * t[j] + c2[j] * z(iter, j)   (:532, :535)
+__global__ void k_k_weights(const double* __restrict__ c1, const double* __restrict__ c2, const double* __restrict__ t, int nk, hb_key_t key,
+                            uint32_t it, double* __restrict__ w) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nk) w[j] = c1[j] * t[j] + c2[j] * hb_draw_z(key, HB_DOM_K, it, (uint32_t)j, 0, 0);
+}
+// yadj += k_old - k_new, u -= k_old - k_new, k_old = k_new   (:537-540, :551)
+__global__ void k_k_apply(double* __restrict__ r, double* __restrict__ u, double* __restrict__ kcur, const double* __restrict__ knew, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double d = kcur[i] - knew[i];
+  r[i] += d;
+  u[i] -= d;
+  kcur[i] = knew[i];
+}
+// partial sums of t[j]^2 / kval[j]
+__global__ void k_k_quad(const double* __restrict__ t, const double* __restrict__ kval, int nk, double* __restrict__ partial) {
+  __shared__ double sh[kDotThreads];
+  double s = 0.0;
+  for (int j = blockIdx.x * kDotThreads + threadIdx.x; j < nk; j += kDotBlocks * kDotThreads) s += t[j] * ((1.0 / kval[j]) * t[j]);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = kDotThreads / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void k_k_scale(double* __restrict__ t, const double* __restrict__ kval, double a, int nk) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nk) t[j] = (t[j] / kval[j]) / a;
+}
+__global__ void k_vec_scale_to(const double* __restrict__ x, double a, double* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = x[i] / a;
+}
+
 __global__ void k_vec_add(double* __restrict__ acc, const double* __restrict__ x, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) acc[i] += x[i];
@@ -182,6 +239,10 @@ struct hb_fx {
   int *e_index0 = nullptr, *e_start = nullptr, *e_recs = nullptr, *g_colptr = nullptr, *g_rowidx = nullptr, *e_order = nullptr,
       *e_lstart = nullptr;
   double *g_val = nullptr, *e_cnt = nullptr, *e_x = nullptr, *e_rhs = nullptr, *e_est = nullptr, *e_sum = nullptr;
+  // BSLMM
+  int nk = 0;
+  double *K = nullptr, *k_cur = nullptr, *k_new = nullptr, *k_sum = nullptr, *k_t = nullptr, *k_w = nullptr, *k_c1 = nullptr, *k_c2 = nullptr,
+         *k_val = nullptr;
   double* partial = nullptr;                   // kDotBlocks
   double* h_partial = nullptr;                 // pinned
   hb_key_t key;
@@ -191,7 +252,8 @@ extern "C" void hb_fx_destroy(hb_fx* f) {
   if (!f) return;
   cudaSetDevice(f->device);
   void* p[] = {f->C, f->J, f->lev, f->lstart, f->lrows, f->lsum, f->ldiff, f->e_index0, f->e_start, f->e_recs, f->g_colptr,
-               f->g_rowidx, f->e_order, f->e_lstart, f->g_val, f->e_cnt, f->e_x, f->e_rhs, f->e_est, f->e_sum, f->partial};
+               f->g_rowidx, f->e_order, f->e_lstart, f->g_val, f->e_cnt, f->e_x, f->e_rhs, f->e_est, f->e_sum, f->partial,
+               f->K, f->k_cur, f->k_new, f->k_sum, f->k_t, f->k_w, f->k_c1, f->k_c2, f->k_val};
   for (void* q : p) if (q) cudaFree(q);
   if (f->h_partial) cudaFreeHost(f->h_partial);
   delete f;
@@ -296,6 +358,20 @@ extern "C" int hb_fx_create(hb_engine* e, const hb_fx_desc* d, hb_fx** out) {
     for (double** q : z) {
       CU(cudaMalloc((void**)q, qe * sizeof(double)));
       CU(cudaMemsetAsync(*q, 0, qe * sizeof(double), f->stream));
+    }
+  }
+  if (d->nk > 0) {
+    if (!d->Ki || d->nk != n) return hb_set_error("hb_fx_create: Ki must be n x n (nk = %d, n = %d)", d->nk, n);
+    f->nk = d->nk;
+    if (cudaMalloc((void**)&f->K, (size_t)n * f->nk * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError();
+      return hb_set_error("hb_fx_create: the %d x %d eigenvector matrix (%.1f GB) does not fit on the device", n, f->nk, (double)n * f->nk * 8 / 1e9);
+    }
+    CU(cudaMemcpyAsync(f->K, d->Ki, (size_t)n * f->nk * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+    double** z[] = {&f->k_cur, &f->k_new, &f->k_sum, &f->k_t, &f->k_w, &f->k_c1, &f->k_c2, &f->k_val};
+    for (double** q : z) {
+      CU(cudaMalloc((void**)q, (size_t)n * sizeof(double)));
+      CU(cudaMemsetAsync(*q, 0, (size_t)n * sizeof(double), f->stream));
     }
   }
   CU(cudaStreamSynchronize(f->stream));
@@ -441,5 +517,47 @@ extern "C" int hb_fx_eps_get(hb_fx* f, double* est, double* sum) {
 extern "C" int hb_fx_describe(hb_fx* f, int* eps_levels) {
   if (!f) return hb_set_error("hb_fx_describe: null argument");
   if (eps_levels) *eps_levels = f->eps_levels;
+  return 0;
+}
+
+extern "C" int hb_fx_k_step(hb_fx* f, int iter, const double* c1, const double* c2, const double* kival, double* quad) {
+  if (!f || !f->nk || !c1 || !c2 || !kival || !quad) return hb_set_error("hb_fx_k_step: bad argument");
+  CU(cudaSetDevice(f->device));
+  const int n = f->n, nk = f->nk;
+  CU(cudaMemcpyAsync(f->k_c1, c1, nk * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+  CU(cudaMemcpyAsync(f->k_c2, c2, nk * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+  CU(cudaMemcpyAsync(f->k_val, kival, nk * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+  const unsigned gw = (unsigned)(((size_t)nk * 32 + 255) / 256), gn = (unsigned)((n + 255) / 256), gk = (unsigned)((nk + 255) / 256);
+  k_gemv_t<<<gw, 256, 0, f->stream>>>(f->K, n, nk, f->r, f->k_cur, f->k_t);                 // K'(yadj + k_old)   :519, :532
+  k_k_weights<<<gk, 256, 0, f->stream>>>(f->k_c1, f->k_c2, f->k_t, nk, f->key, (uint32_t)iter, f->k_w);
+  k_gemv_n<<<gn, 256, 0, f->stream>>>(f->K, n, nk, f->k_w, f->k_new);                       // K (...)            :532, :535
+  k_k_apply<<<gn, 256, 0, f->stream>>>(f->r, f->u, f->k_cur, f->k_new, n);                  // :537-540, :551
+  k_gemv_t<<<gw, 256, 0, f->stream>>>(f->K, n, nk, f->k_cur, nullptr, f->k_t);              // Kg = K' k_new      :543
+  k_k_quad<<<kDotBlocks, kDotThreads, 0, f->stream>>>(f->k_t, f->k_val, nk, f->partial);    // :544
+  CU(cudaGetLastError());
+  return finish_partials(f, quad);
+}
+
+extern "C" int hb_fx_k_accumulate(hb_fx* f) {
+  if (!f || !f->nk) return hb_set_error("hb_fx_k_accumulate: no polygenic term");
+  CU(cudaSetDevice(f->device));
+  k_vec_add<<<(f->nk + 255) / 256, 256, 0, f->stream>>>(f->k_sum, f->k_cur, f->nk);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int hb_fx_k_ghat_vec(hb_fx* f, const double* kival, double sumvx, double count, double* v_host) {
+  if (!f || !f->nk || !kival || !v_host) return hb_set_error("hb_fx_k_ghat_vec: bad argument");
+  CU(cudaSetDevice(f->device));
+  const int n = f->n, nk = f->nk;
+  const unsigned gw = (unsigned)(((size_t)nk * 32 + 255) / 256), gn = (unsigned)((n + 255) / 256), gk = (unsigned)((nk + 255) / 256);
+  CU(cudaMemcpyAsync(f->k_val, kival, nk * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+  k_vec_scale_to<<<gk, 256, 0, f->stream>>>(f->k_sum, count, f->k_new, nk);           // k_estR_store /= count  :956
+  k_gemv_t<<<gw, 256, 0, f->stream>>>(f->K, n, nk, f->k_new, nullptr, f->k_t);              // K' k_mean              :957
+  k_k_scale<<<gk, 256, 0, f->stream>>>(f->k_t, f->k_val, sumvx, nk);                  // / Kval / sumvx         :958-959
+  k_gemv_n<<<gn, 256, 0, f->stream>>>(f->K, n, nk, f->k_t, f->k_w);                         // K * Kg                 :961
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(v_host, f->k_w, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
   return 0;
 }

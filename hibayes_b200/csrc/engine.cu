@@ -1483,6 +1483,44 @@ extern "C" int hb_engine_predict(hb_engine* e, const double* alpha, double* out)
   return 0;
 }
 
+// out[j] = sum_i x[i][j] v[i]  (X.t() * v, Bayes.cpp:961: the BSLMM polygenic values as SNP effects).  One warp per
+// SNP walks the slabs in order (a slab's rows of a column are contiguous: R bytes), lane-strided partial sums, fixed
+// shuffle tree: deterministic.  One pass over X, used once at the end of a run.
+__global__ void k_xt_vec(const uint8_t* __restrict__ Xp, const double* __restrict__ v, int m, int S, int R, size_t slab_stride,
+                         double* __restrict__ out) {
+  const int j = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (j >= m) return;
+  double s = 0.0;
+  for (int sl = 0; sl < S; ++sl) {
+    const uint8_t* col = Xp + (size_t)sl * slab_stride + (size_t)j * R;
+    const double* vs = v + (size_t)sl * R;
+    for (int r = 4 * lane; r < R; r += 128) {
+      const uint32_t w = *(const uint32_t*)(col + r);
+      s = fma((double)(w & 0xffu), vs[r], s);
+      s = fma((double)((w >> 8) & 0xffu), vs[r + 1], s);
+      s = fma((double)((w >> 16) & 0xffu), vs[r + 2], s);
+      s = fma((double)(w >> 24), vs[r + 3], s);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) out[j] = s;
+}
+extern "C" int hb_engine_xt_vec(hb_engine* e, const double* v, double* out) {
+  if (!e || !v || !out) return hb_set_error("hb_engine_xt_vec: null argument");
+  if (!e->geno_ready) return hb_set_error("hb_engine_xt_vec: genotypes not loaded");
+  CU(cudaSetDevice(e->cfg.device));
+  struct Bufs { double *v = nullptr, *o = nullptr; ~Bufs() { cudaFree(v); cudaFree(o); } } b;
+  CU(cudaMalloc(&b.v, e->Npad * 8));
+  CU(cudaMalloc(&b.o, (size_t)e->m * 8));
+  CU(cudaMemsetAsync(b.v, 0, e->Npad * 8, e->stream));   // padding rows: genotype 0 anyway
+  CU(cudaMemcpyAsync(b.v, v, (size_t)e->n * 8, cudaMemcpyHostToDevice, e->stream));
+  k_xt_vec<<<(unsigned)(((size_t)e->m * 32 + 255) / 256), 256, 0, e->stream>>>(e->Xp, b.v, e->m, e->S, e->R, e->slab_stride, b.o);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, b.o, (size_t)e->m * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
 // Genetic values of every stored MCMC sample, `M %*% res$MCMCsamples$alpha` of R/bayes.r:303-304:
 // out[:, c] = X alpha[:, c].  Blocks of up to 64 records go through k_gemm_samples, which reads X once per block.
 extern "C" int hb_engine_predict_samples(hb_engine* e, const double* alpha, size_t ld_alpha, int n_records, double* out,

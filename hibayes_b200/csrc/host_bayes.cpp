@@ -161,6 +161,15 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
       e_cnt[a->epsl_index[i] - 1] += 1.0;
     }
   }
+  // BSLMM polygenic term :203-233
+  const int nk = (a->Ki != nullptr) ? a->nk : 0;
+  double vbtmp = 0;
+  std::vector<double> k_c1(nk), k_c2(nk);
+  if (nk) {
+    if (!a->Kival) return hb_set_error("Ki and Kival should be provided together.");
+    if (nk != n) return hb_set_error("variance-covariance matrix should be in square.");   // :221 (and :519 needs nk == n)
+    if (world > 1) return hb_set_error("hb_bayes: the BSLMM polygenic term is not available with sharded individuals");
+  }
   // with the individuals sharded over ranks these set-up sums run over all ranks' rows
   if (world > 1) {
     if (nc) HBCHK(allsum(cpc.data(), nc));
@@ -236,6 +245,7 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
   // ---- priors :319-375
   double vara_ = isna(a->vg) ? ((dfvara_ - 2) / dfvara_) * vary * h2 : a->vg;
   vepstmp = vara_;
+  vbtmp = vara_;   // :333
   double vare_ = isna(a->ve) ? vary * (1 - h2) / (nr + 1) : a->ve;
   const double dfvare_ = isna(a->dfve) ? -2 : a->dfve;
   const double s2vara_ = isna(a->s2vg) ? vara_ * (dfvara_ - 2) / dfvara_ : a->s2vg;
@@ -261,7 +271,7 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
   HBCHK(hb_engine_set_residual(E, yadj.data()));
   // non-SNP effects (covariates :484-494, env. random effects :496-516, single-step J + epsilon :554-584) run on the
   // device on the engine's own residual and u (csrc/effects.cu): the vectors never cross PCIe inside the loop
-  const bool side_effects = (nc > 0 || nr > 0 || have_eps);
+  const bool side_effects = (nc > 0 || nr > 0 || have_eps || nk > 0);
   FxGuard fxg;
   if (side_effects) {
     hb_fx_desc fd;
@@ -272,6 +282,7 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
       fd.Gi_colptr = a->Gi_colptr; fd.Gi_rowidx = a->Gi_rowidx; fd.Gi_val = a->Gi_val;
     }
     fd.seed = a->seed;
+    fd.nk = nk; fd.Ki = nk ? a->Ki : nullptr;
     HBCHK(hb_fx_create(E, &fd, &fxg.f));
     if (have_eps) HBCHK(hb_fx_eps_set_counts(fxg.f, e_cnt.data()));
   }
@@ -321,6 +332,24 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
                    hb_draw_chisq(KEY, HB_DOM_ITER, it, HB_IT_VR0 + (uint32_t)i, 0, qr + dfr);
         vrv[i] = arma_var(estR_tmp.data() + off, qr);
         for (int q = 0; q < qr; ++q) estR[off + q] = estR_tmp[off + q];
+      }
+      // BSLMM polygenic term :518-552 (block Gibbs sampler on the eigen-decomposition; the dense products run on the device)
+      if (nk) {
+        double emax = 0.0;
+        for (int j = 0; j < nk; ++j) {
+          const double ev = (a->Kival[j] * vare_) / (a->Kival[j] + vare_ / vbtmp);   // :531
+          k_c2[j] = ev;
+          emax = std::max(emax, fabs(ev));
+        }
+        for (int j = 0; j < nk; ++j) {
+          if (!(k_c2[j] >= -1e-06 * emax))                                             // :533
+            return hb_set_error("matrix is not positive definite, try to specify parameter 'lambda' with a small value, eg: 0.001 or bigger");
+          k_c1[j] = k_c2[j] / vare_;
+          k_c2[j] = sqrt(k_c2[j] < 0 ? 0.0 : k_c2[j]);                                 // :534-535
+        }
+        double quad;
+        HBCHK(hb_fx_k_step(FX, iter, k_c1.data(), k_c2.data(), a->Kival, &quad));
+        vbtmp = (quad + s2vara_ * dfvara_) / hb_draw_chisq(KEY, HB_DOM_ITER, it, HB_IT_VB, 0, dfvara_ + nk);   // :546-547
       }
       // single-step J + epsilon :554-584 (sparse Gauss-Seidel sampler, solver.cpp:131-140)
       if (have_eps) {
@@ -450,6 +479,7 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
       double vt = vara_ + vare_;
       for (int i = 0; i < nr; ++i) { vt += vrv[i]; vrsum[i] += vrv[i]; }
       for (int q = 0; q < n_levels; ++q) estRsum[q] += estR[q];
+      if (nk) HBCHK(hb_fx_k_accumulate(FX));   // :858
       if (have_eps) {
         vepssum += veps; Jsum += epsl_J_beta;
         HBCHK(hb_fx_eps_accumulate(FX));
@@ -485,6 +515,17 @@ extern "C" int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o) {
   std::vector<double> alpha(m, 0.0);
   HBCHK(hb_engine_get_effect_sums(E, alpha.data()));
   for (int i = 0; i < m; ++i) alpha[i] /= rc;
+  if (nk) {   // :955-964: the polygenic values expressed as SNP effects and added to every stored sample
+    std::vector<double> kv(n), ghat(m);
+    HBCHK(hb_fx_k_ghat_vec(FX, a->Kival, sumvx, rc, kv.data()));
+    HBCHK(hb_engine_xt_vec(E, kv.data(), ghat.data()));
+    const double gm = acc_sum(ghat.data(), m) / (double)m;
+    for (int i = 0; i < m; ++i) ghat[i] -= gm;
+    for (int i = 0; i < m; ++i) alpha[i] += ghat[i];
+    if (o->alpha_store)
+      for (int c = 0; c < count; ++c)
+        for (int i = 0; i < m; ++i) o->alpha_store[(size_t)c * m + i] += ghat[i];
+  }
   if (o->alpha) memcpy(o->alpha, alpha.data(), sizeof(double) * m);
   if (o->e) {
     std::vector<double> xg(n);

@@ -182,6 +182,7 @@ typedef struct {
   const int32_t* epsl_index;                         /* ne entries, 1-based */
   const int32_t* Gi_colptr; const int32_t* Gi_rowidx; const double* Gi_val;
   uint64_t seed;
+  int nk; const double* Ki;                          /* BSLMM: n x nk eigenvectors (nk = n), or 0 / NULL */
 } hb_fx_desc;
 enum { HB_FX_COV = 0, HB_FX_J = 1, HB_FX_RESID = 2, HB_FX_ONES = 3 };
 int hb_fx_create(hb_engine* e, const hb_fx_desc* d, hb_fx** out);
@@ -203,6 +204,15 @@ int hb_fx_eps_sample(hb_fx* f, int iter, double vare, double ratio, double* quad
 int hb_fx_eps_accumulate(hb_fx* f);
 int hb_fx_eps_get(hb_fx* f, double* est, double* sum);
 int hb_fx_describe(hb_fx* f, int* eps_levels);
+/* BSLMM block Gibbs step, Bayes.cpp:519-544: k_new = K ((c1 % K'(yadj + k_old)) + c2 % z) with the host's c1 = eval / ve,
+ * c2 = sqrt(max(eval, 0)) (nk each) and z the position-addressed normals; yadj += k_old - k_new, u -= k_old - k_new;
+ * *quad = (K'k_new)' diag(1 / Kival) (K'k_new).  accumulate: the running sum of the records (:858).  ghat_vec: the n-vector
+ * K ((K' k_mean) / Kival / sumvx) whose X' product is added to the stored effects (:956-962). */
+int hb_fx_k_step(hb_fx* f, int iter, const double* c1, const double* c2, const double* kival, double* quad);
+int hb_fx_k_accumulate(hb_fx* f);
+int hb_fx_k_ghat_vec(hb_fx* f, const double* kival, double sumvx, double count, double* v_host);
+/* out[j] = sum_i X[i][j] v[i] over the resident genotypes (X.t() * v, Bayes.cpp:961) */
+int hb_engine_xt_vec(hb_engine* e, const double* v, double* out);
 
 /* ------------------------------------------------------------------ host driver layer */
 #define HB_NA (__builtin_nan(""))
@@ -215,10 +225,9 @@ typedef struct {
   int impt, dominance;              /* read_bed()'s impt and d */
 } hb_bed_source;
 
-/* Argument list of Rcpp::List Bayes(...) (/root/reference/src/Bayes.cpp:60-88).  Two of its 27 arguments have no field
- * here: Kival / Ki, the eigen-decomposition of the GRM for BSLMM's polygenic term (Bayes.cpp:518-552: two dense n x n
- * products per iteration and arma::randn) -- that term is not offloaded; the Rcpp shim refuses a non-NULL Ki
- *  and model "BSLMM" without it is the BayesCpi sweep, as in the reference (Bayes.cpp:97-106). */
+/* Argument list of Rcpp::List Bayes(...) (/root/reference/src/Bayes.cpp:60-88): every one of its 27 arguments has a field
+ * here (`threads` is ignored, `seed` replaces R's RNG state).  Model "BSLMM" without Ki is the BayesCpi sweep, as in the
+ * reference (Bayes.cpp:97-106). */
 typedef struct {
   int n, m;
   const double* y;          /* n                                   (arma::vec& y) */
@@ -250,6 +259,10 @@ typedef struct {
   int (*allreduce_sum_f64)(void* ctx, double* host_buf, size_t count);        /* in place, host memory */
   int (*allreduce_sum_i32_dev)(void* ctx, void* device_buf, size_t count);    /* in place, device memory */
   int (*allgather_bytes)(void* ctx, const void* mine, void* all, size_t bytes_per_rank); /* rank-ordered */
+  /* BSLMM polygenic term (Nullable<arma::vec> Kival, Nullable<arma::mat> Ki; Bayes.cpp:64-65, 203-233, 518-552, 955-964):
+   * Ki = eigenvectors of the relationship matrix, n x nk column-major with nk = n, Kival = its nk eigenvalues; nk = 0 /
+   * NULL = R_NilValue.  Runs on the device (csrc/effects.cu); not available with world > 1. */
+  int nk; const double* Kival; const double* Ki;
 } hb_bayes_args;
 
 typedef struct {

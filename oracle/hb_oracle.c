@@ -115,6 +115,7 @@ static int isna(double v) { return v != v; }
   free(R_off); free(snptracker); free(nzrate); free(g); free(u); free(xpx); free(vx); free(yadj); \
   free(scratch); free(vargL); free(Pi); free(fold_); free(fold_snp_num); free(logpi); free(s); free(stemp); \
   free(vara_fold); free(vare_vara_fold); free(wppai); free(wstart); free(wmembers); free(gsum); free(pisum); \
+  free(k_estR); free(k_tmp); free(k_sum); free(k_rhs); free(k_eval); free(k_t); free(k_w); \
   free(betasum); free(estRsum); free(e_estR); free(e_tmp); free(e_rhs); free(e_lhsdiag); free(e_cnt); free(e_sum); \
   free(diff); } while (0)
 
@@ -130,6 +131,7 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
   double *wppai = 0; int *wstart = 0, *wmembers = 0;
   double *gsum = 0, *pisum = 0, *betasum = 0, *estRsum = 0;
   double *e_estR = 0, *e_tmp = 0, *e_rhs = 0, *e_lhsdiag = 0, *e_cnt = 0, *e_sum = 0, *diff = 0;
+  double *k_estR = 0, *k_tmp = 0, *k_sum = 0, *k_rhs = 0, *k_eval = 0, *k_t = 0, *k_w = 0;   /* BSLMM */
 
   /* Bayes.cpp:92-117 argument checks */
   for (int i = 0; i < n; ++i) if (isna(a->y[i])) return fail("NAs are not allowed in y.");
@@ -207,6 +209,21 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
     for (int i = 0; i < ne; ++i) e_cnt[a->epsl_index[i] - 1] += 1.0;
   }
 
+  /* BSLMM polygenic term :203-233 */
+  const int nk = a->nk;
+  double vbtmp = 0;
+  if (nk) {
+    if (!a->Ki || !a->Kival) { FREE_ALL(); return fail("Ki and Kival should be provided together."); }
+    if (nk != n) { FREE_ALL(); return fail("variance-covariance matrix should be in square."); }   /* :221, and :519 needs nk == n */
+    k_estR = (double*)calloc(nk, sizeof(double));
+    k_tmp = (double*)calloc(nk, sizeof(double));
+    k_sum = (double*)calloc(nk, sizeof(double));
+    k_rhs = (double*)calloc(n, sizeof(double));
+    k_eval = (double*)calloc(nk, sizeof(double));
+    k_t = (double*)calloc(nk, sizeof(double));
+    k_w = (double*)calloc(nk, sizeof(double));
+  }
+
   int count = 0, nzct = 0, NnzSnp = 0, indistflag;
   double xx, oldgi, gi, gi_, rhs, lhs, logdetV, acceptProb, uhat, v;
   double vara_, dfvara_, s2vara_, vare_, dfvare_, s2vare_, vargi, s2varg_;
@@ -251,6 +268,7 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
   if (dfvara_ <= 2) { FREE_ALL(); return fail("dfvg should not be less than 2."); }
   vara_ = isna(a->vg) ? ((dfvara_ - 2) / dfvara_) * vary * h2 : a->vg;
   vepstmp = vara_;
+  vbtmp = vara_;   /* :333 */
   vare_ = isna(a->ve) ? vary * (1 - h2) / (nr + 1) : a->ve;
   dfvare_ = isna(a->dfve) ? -2 : a->dfve;
   s2vara_ = isna(a->s2vg) ? vara_ * (dfvara_ - 2) / dfvara_ : a->s2vg;
@@ -345,6 +363,44 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
                  chisq_at(HB_DOM_ITER, it, HB_IT_VR0 + (uint32_t)i, 0, qr + dfr);
       vrv[i] = hbo_var(estR_tmp + off, qr);
       for (int q = 0; q < qr; ++q) estR[off + q] = estR_tmp[off + q];
+    }
+
+    /* BSLMM polygenic term :518-552 (block Gibbs sampler on the eigen-decomposition K diag(Kval) K') */
+    if (nk) {
+      const double* K = a->Ki;
+      for (int i = 0; i < n; ++i) k_rhs[i] = yadj[i] + k_tmp[i];                                  /* :519 */
+      double emax = 0.0;
+      for (int j = 0; j < nk; ++j) {                                                              /* :531 */
+        k_eval[j] = (a->Kival[j] * vare_) / (a->Kival[j] + vare_ / vbtmp);
+        if (fabs(k_eval[j]) > emax) emax = fabs(k_eval[j]);
+      }
+      for (int j = 0; j < nk; ++j) k_t[j] = ddot(n, K + (size_t)j * n, k_rhs);                    /* K.t() * k_RHS */
+      for (int j = 0; j < nk; ++j) k_w[j] = (k_eval[j] / vare_) * k_t[j];
+      for (int i = 0; i < n; ++i) k_tmp[i] = 0.0;
+      for (int j = 0; j < nk; ++j) daxpy(n, k_w[j], K + (size_t)j * n, k_tmp);                    /* :532 */
+      for (int j = 0; j < nk; ++j)
+        if (!(k_eval[j] >= -1e-06 * emax)) {                                                      /* :533 */
+          FREE_ALL();
+          return fail("matrix is not positive definite, try to specify parameter 'lambda' with a small value, eg: 0.001 or bigger");
+        }
+      for (int j = 0; j < nk; ++j) {                                                              /* :534-535 */
+        if (k_eval[j] < 0) k_eval[j] = 0.0;
+        k_w[j] = sqrt(k_eval[j]) * hb_draw_z(KEY, HB_DOM_K, it, (uint32_t)j, 0, 0);
+      }
+      for (int i = 0; i < n; ++i) k_rhs[i] = 0.0;
+      for (int j = 0; j < nk; ++j) daxpy(n, k_w[j], K + (size_t)j * n, k_rhs);
+      for (int i = 0; i < n; ++i) k_tmp[i] += k_rhs[i];
+      daxpy(nk, -1.0, k_tmp, k_estR);                                                             /* :537-538 */
+      daxpy(n, 1.0, k_estR, yadj);                                                                /* :539 */
+      daxpy(n, -1.0, k_estR, u);                                                                  /* :540 */
+      vbtmp = 0.0;
+      for (int j = 0; j < nk; ++j) {                                                              /* :543-544 */
+        const double kg = ddot(n, K + (size_t)j * n, k_tmp);
+        vbtmp += kg * ((1 / a->Kival[j]) * kg);
+      }
+      vbtmp += s2vara_ * dfvara_;
+      vbtmp /= chisq_at(HB_DOM_ITER, it, HB_IT_VB, 0, dfvara_ + nk);                              /* :546-547 */
+      for (int j = 0; j < nk; ++j) k_estR[j] = k_tmp[j];                                          /* :551 */
     }
 
     /* single-step J + epsilon :554-584, solver.cpp:131-140 */
@@ -622,6 +678,7 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
       varasum += vara_; varesum += vare_;
       if (o->vara_store) o->vara_store[count] = vara_;
       if (o->vare_store) o->vare_store[count] = vare_;
+      if (nk) for (int j = 0; j < nk; ++j) k_sum[j] += k_estR[j];                                 /* :858 */
       for (int i = 0; i < m; ++i) gsum[i] += g[i];
       if (o->alpha_store) memcpy(o->alpha_store + (size_t)count * m, g, sizeof(double) * m);
       if (nc) {
@@ -667,6 +724,22 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
     }
   }
   for (int i = 0; i < m; ++i) gsum[i] /= rc;
+  if (nk) { /* :955-964: the polygenic values expressed as SNP effects and added to every stored sample */
+    const double* K = a->Ki;
+    for (int j = 0; j < nk; ++j) k_sum[j] /= rc;
+    for (int j = 0; j < nk; ++j) k_t[j] = (ddot(n, K + (size_t)j * n, k_sum) / a->Kival[j]) / sumvx;   /* Kg */
+    for (int i = 0; i < n; ++i) k_rhs[i] = 0.0;
+    for (int j = 0; j < nk; ++j) daxpy(n, k_t[j], K + (size_t)j * n, k_rhs);                          /* K * Kg */
+    double* ghat = (double*)malloc(sizeof(double) * m);
+    for (int i = 0; i < m; ++i) ghat[i] = ddot(n, xcol(a, i, scratch), k_rhs);                        /* X.t() * (K * Kg) */
+    const double gm = acc_mean(ghat, m);
+    for (int i = 0; i < m; ++i) ghat[i] -= gm;
+    for (int i = 0; i < m; ++i) gsum[i] += ghat[i];
+    if (o->alpha_store)
+      for (int c = 0; c < count; ++c)
+        for (int i = 0; i < m; ++i) o->alpha_store[(size_t)c * m + i] += ghat[i];
+    free(ghat);
+  }
   if (o->alpha) memcpy(o->alpha, gsum, sizeof(double) * m);
   if (o->e) {
     for (int i = 0; i < m; ++i) {

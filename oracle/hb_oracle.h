@@ -52,6 +52,11 @@ typedef struct {
   const int32_t* Gi_colptr;   /* qe+1, CSC of epsl_Gi */
   const int32_t* Gi_rowidx;
   const double* Gi_val;
+  /* BSLMM polygenic term (Bayes.cpp:203-233, 518-552, 955-964); nk = 0 disables.  Ki: n x nk column-major eigenvectors
+   * of the relationship matrix (nk must equal n: Bayes.cpp:519 adds an nk-vector to yadj), Kival: nk eigenvalues */
+  int nk;
+  const double* Kival;
+  const double* Ki;
 } hbo_bayes_args;
 
 typedef struct {

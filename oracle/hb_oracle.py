@@ -56,6 +56,7 @@ class Args(C.Structure):
         ("windindx", C.c_void_p), ("seed", C.c_uint64),
         ("ne", C.c_int), ("qe", C.c_int), ("epsl_y_J", C.c_void_p), ("epsl_index", C.c_void_p),
         ("Gi_colptr", C.c_void_p), ("Gi_rowidx", C.c_void_p), ("Gi_val", C.c_void_p),
+        ("nk", C.c_int), ("Kival", C.c_void_p), ("Ki", C.c_void_p),
     ]
 
 
@@ -90,7 +91,7 @@ def _nan(v):
 def bayes(y, X, model, Pi, fold=None, C_=None, R=None, niter=200, nburn=100, thin=5,
           dfvr=None, s2vr=None, vg=None, dfvg=None, s2vg=None, ve=None, dfve=None, s2ve=None,
           windindx=None, seed=666666, epsl_y_J=None, epsl_Gi=None, epsl_index=None,
-          store_alpha=False):
+          store_alpha=False, Kival=None, Ki=None):
     """Oracle twin of hibayes' C++ Bayes() (Bayes.cpp:60-88 argument list).
 
     X: (n, m) array, float64 or int8 (Fortran order is used internally).
@@ -157,6 +158,11 @@ def bayes(y, X, model, Pi, fold=None, C_=None, R=None, niter=200, nburn=100, thi
         a.epsl_y_J, a.epsl_index, a.Gi_colptr, a.Gi_rowidx, a.Gi_val = _ptr(yj), _ptr(ei), _ptr(cp), _ptr(ri), _ptr(gv)
         keep += [ei, cp, ri, gv, yj]
     a.ne, a.qe = ne, qe
+    if Ki is not None:   # BSLMM: eigenvectors (n x n) and eigenvalues of the relationship matrix
+        Kf = np.asfortranarray(Ki, dtype=np.float64)
+        kv = np.ascontiguousarray(Kival, dtype=np.float64)
+        a.nk, a.Ki, a.Kival = Kf.shape[1], _ptr(Kf), _ptr(kv)
+        keep += [Kf, kv]
     nrec = max((niter - nburn) // thin, 0)
     o = Out()
     res = {

@@ -30,7 +30,7 @@ int main(int argc, char** argv) {
     OFF(hb_bayes_args, y); OFF(hb_bayes_args, x_type); OFF(hb_bayes_args, model); OFF(hb_bayes_args, Pi); OFF(hb_bayes_args, C);
     OFF(hb_bayes_args, Rlev); OFF(hb_bayes_args, niter); OFF(hb_bayes_args, dfvr); OFF(hb_bayes_args, s2ve); OFF(hb_bayes_args, windindx);
     OFF(hb_bayes_args, seed); OFF(hb_bayes_args, ne); OFF(hb_bayes_args, epsl_y_J); OFF(hb_bayes_args, Gi_val); OFF(hb_bayes_args, device);
-    OFF(hb_bayes_args, rank); OFF(hb_bayes_args, n_total); OFF(hb_bayes_args, comm_ctx); OFF(hb_bayes_args, allgather_bytes);
+    OFF(hb_bayes_args, rank); OFF(hb_bayes_args, n_total); OFF(hb_bayes_args, comm_ctx); OFF(hb_bayes_args, allgather_bytes); OFF(hb_bayes_args, nk); OFF(hb_bayes_args, Kival); OFF(hb_bayes_args, Ki);
     OFF(hb_bayes_out, J); OFF(hb_bayes_out, beta); OFF(hb_bayes_out, epsilon); OFF(hb_bayes_out, mu_store); OFF(hb_bayes_out, beta_store);
     OFF(hb_bayes_out, tracker_final); OFF(hb_bayes_out, varg_trace); OFF(hb_bayes_out, n_records_done); OFF(hb_bayes_out, seconds_sweep);
     OFF(hb_bayes_out, rounds_total); OFF(hb_bayes_out, rounds_trace); OFF(hb_bayes_out, vr_store); OFF(hb_bayes_out, epsilon_store);

@@ -12,8 +12,8 @@ import scipy.sparse as sp
 from oracle import hb_oracle
 
 # addresses of the draws (hibayes_b200/csrc/hb_rng.h)
-DOM_ITER, DOM_SNP, DOM_EPS = 0, 1, 4
-IT_MU, IT_VARG, IT_VARE, IT_J, IT_VEPS = 0, 1, 2, 4, 5
+DOM_ITER, DOM_SNP, DOM_EPS, DOM_K = 0, 1, 4, 5
+IT_MU, IT_VARG, IT_VARE, IT_J, IT_VEPS, IT_VB = 0, 1, 2, 4, 5, 6
 SL_MAIN = 1
 
 
@@ -203,3 +203,122 @@ def test_gpu_single_step_against_the_oracle(model, Pi, fold):
         assert a_.shape == b_.shape and np.abs(a_ - b_).max() <= 1e-5 * np.abs(b_).max(), key
     assert np.abs(got["r"] - ref["r"]).max() <= 1e-5 * np.abs(ref["r"]).max()
     assert np.abs(got["Vr"] - ref["Vr"]).max() <= 1e-5 * np.abs(ref["Vr"]).max()
+
+
+def bayesrr_bslmm_numpy(y, X, Kval, K, niter, nburn, thin, seed):
+    """Bayes() for model "BayesRR" with the BSLMM polygenic term (Ki, Kival) and nothing else, restated from
+    Bayes.cpp:203-233, 518-552, 854-858, 955-964 with numpy's dense algebra."""
+    z, chisq, var = _draws(seed)
+    n, m = X.shape
+    nk = K.shape[1]
+    vary = var(y)
+    dfvara, h2 = 4.0, 0.5
+    vara = (dfvara - 2) / dfvara * vary * h2
+    vare = vary * (1 - h2)
+    s2vara = vara * (dfvara - 2) / dfvara
+    xpx = (X * X).sum(axis=0)
+    vx = np.array([var(X[:, j]) for j in range(m)])
+    sumvx = vx.sum()
+    nvar0 = int((vx == 0).sum())
+    varg = vara / sumvx
+    s2varg = s2vara / sumvx
+    dfvare, s2vare = -2.0, 0.0
+    vbtmp = vara                                                    # :333
+    mu = float(np.mean(y))
+    yadj = y - mu
+    u = np.zeros(n)
+    g = np.zeros(m)
+    k_estR, k_tmp, k_store = np.zeros(nk), np.zeros(nk), np.zeros(nk)
+    rec = dict(mu=[], vara=[], vare=[], g=[])
+    for it in range(niter):
+        mu_ = -(yadj.sum() / n + np.sqrt(vare / n) * z(DOM_ITER, it, IT_MU))
+        mu -= mu_
+        yadj = yadj + mu_
+        # ---- :518-552
+        k_rhs = yadj + k_tmp
+        ev = (Kval * vare) / (Kval + vare / vbtmp)
+        k_tmp = K @ ((ev / vare) * (K.T @ k_rhs))
+        assert np.all(ev >= -1e-6 * np.abs(ev).max())
+        ev = np.where(ev < 0, 0.0, ev)
+        rn = np.array([z(DOM_K, it, j) for j in range(nk)])
+        k_tmp = k_tmp + K @ (np.sqrt(ev) * rn)
+        k_estR = k_estR - k_tmp
+        yadj = yadj + k_estR
+        u = u - k_estR
+        Kg = K.T @ k_tmp
+        vbtmp = float(Kg @ ((1 / Kval) * Kg)) + s2vara * dfvara
+        vbtmp /= chisq(it, IT_VB, dfvara + nk)
+        k_estR = k_tmp.copy()
+        # ---- BayesRR sweep :588-603
+        for j in range(m):
+            if vx[j] == 0:
+                continue
+            x = X[:, j]
+            rhs = float(x @ yadj) + xpx[j] * g[j]
+            v = xpx[j] + vare / varg
+            gn = rhs / v + np.sqrt(vare / v) * z(DOM_SNP, it, j, SL_MAIN)
+            yadj = yadj + (g[j] - gn) * x
+            u = u - (g[j] - gn) * x
+            g[j] = gn
+        varg = (float(g @ g) + s2varg * dfvara) / chisq(it, IT_VARG, dfvara + m - nvar0)
+        vara = var(u)
+        vare = (float(yadj @ yadj) + s2vare * dfvare) / chisq(it, IT_VARE, n + dfvare)
+        if it >= nburn and (it + 1 - nburn) % thin == 0:
+            rec["mu"].append(mu); rec["vara"].append(vara); rec["vare"].append(vare); rec["g"].append(g.copy())
+            k_store += k_estR
+    k_store /= len(rec["mu"])
+    Kg = (K.T @ k_store) / Kval / sumvx
+    ghat = X.T @ (K @ Kg)
+    ghat -= ghat.mean()
+    alpha = np.mean(rec["g"], axis=0) + ghat
+    Mu = np.mean(rec["mu"])
+    return {"mu": Mu, "Vg": np.mean(rec["vara"]), "Ve": np.mean(rec["vare"]), "alpha": alpha, "u": u, "e": y - Mu - X @ alpha}
+
+
+def bslmm_case(seed, n=50, m=30):
+    rng = np.random.default_rng(seed)
+    X = rng.integers(0, 3, size=(n, m)).astype(np.float64)
+    X[:, 5] = 2.0
+    y = X @ rng.normal(scale=0.2, size=m) + rng.normal(size=n) + 1.0
+    Xc = X - X.mean(axis=0)
+    Kmat = Xc @ Xc.T / m + 0.05 * np.eye(n)          # a GRM with the ridge R/bayes.r adds (lambda)
+    Kval, K = np.linalg.eigh(Kmat)
+    return y, X, Kval, np.asfortranarray(K)
+
+
+def test_oracle_bslmm_against_a_dense_numpy_restatement():
+    y, X, Kval, K = bslmm_case(3)
+    kw = dict(niter=8, nburn=2, thin=2, seed=2024)
+    ref = bayesrr_bslmm_numpy(y, X, Kval, K, **kw)
+    got = hb_oracle.bayes(y, X, "BayesRR", [0.0, 1.0], Kival=Kval, Ki=K, **kw)
+    for key in ("mu", "Vg", "Ve"):
+        assert abs(got[key] - ref[key]) <= 1e-9 * abs(ref[key]), (key, got[key], ref[key])
+    assert np.allclose(got["alpha"], ref["alpha"], rtol=1e-8, atol=1e-11)
+    assert np.allclose(got["g"], ref["u"], rtol=1e-8, atol=1e-10)
+    assert np.allclose(got["e"], ref["e"], rtol=1e-8, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,Pi,fold", [("BSLMM", [0.9, 0.1], None), ("BayesR", [0.9, 0.05, 0.03, 0.02], [0, 1e-4, 1e-3, 1e-2])])
+def test_gpu_bslmm_against_the_oracle(model, Pi, fold):
+    """hb_bayes() with Ki / Kival (the polygenic term of BSLMM, Bayes.cpp:518-552, on the device) against the oracle."""
+    import hibayes_b200 as hb
+    rng = np.random.default_rng(12)
+    n, m = 640, 1200
+    X = rng.integers(0, 3, size=(n, m)).astype(np.int8)
+    y = X[:, :25].astype(np.float64) @ rng.normal(scale=0.3, size=25) + rng.normal(size=n) + 0.5
+    Xc = X.astype(np.float64) - X.mean(axis=0)
+    Kval, K = np.linalg.eigh(Xc @ Xc.T / m + 0.01 * np.eye(n))
+    K = np.asfortranarray(K)
+    kw = dict(niter=10, nburn=4, thin=2, seed=321, Kival=Kval, Ki=K, store_alpha=True)
+    ref = hb_oracle.bayes(y, X.astype(np.float64), model, Pi, fold=fold, **kw)
+    got = hb.Bayes(y, X, model, Pi, fold=fold, **kw)
+    assert np.array_equal(got["diag"]["tracker"], ref["diag"]["tracker"])
+    assert np.array_equal(got["diag"]["nnz_trace"], ref["diag"]["nnz_trace"])
+    for key in ("mu", "Vg", "Ve", "h2"):
+        assert abs(got[key] - ref[key]) <= 1e-5 * abs(ref[key]), (key, got[key], ref[key])
+    assert np.abs(got["alpha"] - ref["alpha"]).max() <= 1e-5 * np.abs(ref["alpha"]).max()
+    assert np.abs(got["g"] - ref["g"]).max() <= 1e-5 * np.abs(ref["g"]).max()
+    assert np.abs(got["e"] - ref["e"]).max() <= 1e-5 * np.abs(ref["e"]).max()
+    a_, b_ = got["MCMCsamples"]["alpha"], ref["MCMCsamples"]["alpha"]
+    assert np.abs(a_ - b_).max() <= 1e-5 * np.abs(b_).max()
