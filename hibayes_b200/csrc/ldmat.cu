@@ -51,6 +51,7 @@ struct hb_ldmat {
   CUtensorMap tmap;          // Xc as a 2-D tensor (individuals x SNP rows) for the TMA loads of k_ld_panel_tc
   bool tmap_ready = false;
   int use_tc = 1;            // tcgen05 panel kernel (default); HB_LD_MMA_SYNC=1 keeps the mma.sync kernel
+  bool panel_user = false;   // the caller fixed the panel width (hb_ldmat_set_panel_cols)
   int* status = nullptr;     // device word: a bounded wait of k_ld_panel_tc gave up
   std::vector<long long> colptr;
   std::vector<int32_t> rowidx;
@@ -276,7 +277,10 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 __global__ void __launch_bounds__(320, 2) k_ld_panel_tc(const __grid_constant__ CUtensorMap tmap, int Kpad, int j0, LdEpi epi,
-                                                        double* __restrict__ pan, int* __restrict__ status) {
+                                                        double* __restrict__ pan, int* __restrict__ status, int sym) {
+  // sym: the panel is the whole matrix -- only the tiles on and below the diagonal are computed (tXXmat.cpp:161-182 loops
+  // over i <= j and assigns both entries); a tile below the diagonal also writes its mirror image
+  if (sym && blockIdx.x < blockIdx.y) return;
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   uint8_t* tiles = (uint8_t*)(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
   TcShared* sh = (TcShared*)(tiles + (size_t)TC_STAGES * TC_STAGE_BYTES);
@@ -362,7 +366,11 @@ __global__ void __launch_bounds__(320, 2) k_ld_panel_tc(const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int col = b0 + 32 * cb + i;
-            if (col < epi.m) pan[(size_t)(col - j0) * epi.m + row] = ld_entry(epi, row, col, (int)v[i]);
+            if (col < epi.m) {
+              const double val = ld_entry(epi, row, col, (int)v[i]);
+              pan[(size_t)(col - j0) * epi.m + row] = val;
+              if (sym && blockIdx.x > blockIdx.y) pan[(size_t)row * epi.m + col] = val;   // (j0 = 0)
+            }
           }
         }
       }
@@ -533,6 +541,7 @@ extern "C" int hb_ldmat_set_panel_cols(hb_ldmat* h, int cols) {
   if (cols < 64 || cols % 64) return hb_set_error("hb_ldmat_set_panel_cols: need a positive multiple of 64");
   cols = (cols + 127) / 128 * 128;   // (tiles of the tcgen05 kernel)
   h->panel_cols = std::min(cols, h->Mpad);
+  h->panel_user = true;
   return 0;
 }
 
@@ -630,7 +639,15 @@ static int run_panels(hb_ldmat* h, const int32_t* chr, int has_chisq, double chi
   if (ensure_stats(h)) return 1;
   CU(cudaSetDevice(h->device));
   if (chr) CU(cudaMemcpyAsync(h->chr, chr, (size_t)h->m * 4, cudaMemcpyHostToDevice, h->stream));
-  const int W = h->panel_cols;
+  // With the tcgen05 kernel the whole matrix is one panel when it fits (<= 64 GB and half of the free memory): only the
+  // lower triangle is then computed, each tile writing its mirror image too (HB_LD_FULL=0 keeps the column panels).
+  int W = h->panel_cols;
+  int sym = 0;
+  if (h->use_tc && !h->panel_user && !(getenv("HB_LD_FULL") && !atoi(getenv("HB_LD_FULL")))) {
+    size_t fr = 0, tot = 0;
+    const size_t full = (size_t)h->Mpad * h->m * 8;
+    if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && full <= ((size_t)64 << 30) && full <= (fr + h->pan_elems * 8) / 2) { W = h->Mpad; sym = 1; }
+  }
   const size_t need = (size_t)W * h->m;
   if (h->pan_elems < need) {
     cudaFree(h->pan);
@@ -647,7 +664,7 @@ static int run_panels(hb_ldmat* h, const int32_t* chr, int has_chisq, double chi
     CU(cudaEventRecord(h->ev0, h->stream));
     if (h->use_tc) {
       const size_t shb = (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(TcShared) + 1024;
-      k_ld_panel_tc<<<dim3(h->Mpad / TC_TILE, wpad / TC_TILE), 320, shb, h->stream>>>(h->tmap, h->Kpad, j0, epi, h->pan, h->status);
+      k_ld_panel_tc<<<dim3(h->Mpad / TC_TILE, wpad / TC_TILE), 320, shb, h->stream>>>(h->tmap, h->Kpad, j0, epi, h->pan, h->status, sym);
     } else {
       k_ld_panel<<<dim3(h->Mpad / 64, wpad / 64), 128, 0, h->stream>>>(h->Xc, h->Kpad, j0, epi, h->pan);
     }
