@@ -376,7 +376,7 @@ def Bayes(y, X, model, Pi, Kival=None, Ki=None, C_=None, R=None, fold=None, nite
 
 
 def _sbayes(sparse, sumstat, ldm, model, Pi, niter, nburn, thin, fold, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, outfreq, verbose,
-            seed, device):
+            seed, device, store_alpha=False):
     L = _lib.load_library()
     ss = np.asfortranarray(sumstat, dtype=np.float64)
     a = _lib.SBayesArgs()
@@ -429,6 +429,9 @@ def _sbayes(sparse, sumstat, ldm, model, Pi, niter, nburn, thin, fold, windindx,
     o.nnz_trace, o.vara_trace, o.vare_trace, o.varg_trace = (_ptr(dg["nnz_trace"]), _ptr(dg["vara_trace"]),
                                                              _ptr(dg["vare_trace"]), _ptr(dg["varg_trace"]))
     o.r_hat_final = _ptr(dg["r_hat"])
+    if store_alpha:   # MCMCsamples$alpha (SBayesD.cpp:566), m x records
+        mc["alpha"] = np.zeros((m, nrec), order="F")
+        o.alpha_store = _ptr(mc["alpha"])
     _lib.check((L.hb_sbayess if sparse else L.hb_sbayesd)(C.byref(a), C.byref(o)))
     res.update({"Vg": o.Vg, "Ve": o.Ve, "h2": o.h2, "MCMCsamples": mc})
     dg.update({"n_records": o.n_records_done, "nzct": o.nzct, "iters_done": o.iters_done, "n_used": o.n_used,
@@ -439,20 +442,22 @@ def _sbayes(sparse, sumstat, ldm, model, Pi, niter, nburn, thin, fold, windindx,
 
 
 def SBayesD(sumstat, ldm, model, Pi, niter=50000, nburn=20000, thin=5, fold=None, windindx=None, vg=None, dfvg=None,
-            s2vg=None, ve=None, dfve=None, s2ve=None, outfreq=100, threads=0, verbose=False, seed=666666, device=0):
+            s2vg=None, ve=None, dfve=None, s2ve=None, outfreq=100, threads=0, verbose=False, seed=666666, device=0,
+            store_alpha=False):
     """GPU twin of hibayes' SBayesD() (/root/reference/src/SBayesD.cpp:5-24; what sbrm() calls at R/sbayes.r:215 for a
     dense LD matrix).  sumstat: m x 4 (MAF, BETA, SE, N = columns 4,5,6,8 of the COJO file, R/sbayes.r:209), NaN = NA;
     ldm: m x m.  Returns a dict named like the Rcpp::List (:532-578)."""
     return _sbayes(False, sumstat, ldm, model, Pi, niter, nburn, thin, fold, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, outfreq,
-                   verbose, seed, device)
+                   verbose, seed, device, store_alpha)
 
 
 def SBayesS(sumstat, ldm, model, Pi, niter=50000, nburn=20000, thin=5, fold=None, windindx=None, vg=None, dfvg=None,
-            s2vg=None, ve=None, dfve=None, s2ve=None, outfreq=100, threads=0, verbose=False, seed=666666, device=0):
+            s2vg=None, ve=None, dfve=None, s2ve=None, outfreq=100, threads=0, verbose=False, seed=666666, device=0,
+            store_alpha=False):
     """GPU twin of hibayes' SBayesS() (/root/reference/src/SBayesS.cpp:21-40; sbrm() with a sparse LD matrix,
     R/sbayes.r:213): ldm is a scipy sparse matrix (dgCMatrix in R)."""
     return _sbayes(True, sumstat, ldm, model, Pi, niter, nburn, thin, fold, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, outfreq,
-                   verbose, seed, device)
+                   verbose, seed, device, store_alpha)
 
 
 

@@ -75,11 +75,34 @@ static void daxpy(int n, double a, const double* x, double* y) {
 
 /* ---- sampler wrappers (stats.cpp) ------------------------------------------ */
 static hb_key_t KEY;
+/* tape of consumed variates (hb_oracle.h): every TAPE() sits where the reference makes the sampler call */
+static hbo_tape_entry* g_tape;
+static uint64_t g_tape_cap, g_tape_n;
+void hbo_tape_begin(hbo_tape_entry* buf, uint64_t cap) { g_tape = buf; g_tape_cap = cap; g_tape_n = 0; }
+uint64_t hbo_tape_end(void) { g_tape = 0; return g_tape_n; }
+static inline void TAPE(int kind, double value, double param) {
+  if (!g_tape) return;
+  if (g_tape_n < g_tape_cap) { g_tape[g_tape_n].kind = kind; g_tape[g_tape_n].pad = 0; g_tape[g_tape_n].value = value; g_tape[g_tape_n].param = param; }
+  g_tape_n++;
+}
+enum { TP_U = 0, TP_Z = 1, TP_GAMMA = 2, TP_CHISQ = 3 };
+static double z_at(uint32_t dom, uint32_t iter, uint32_t idx, uint32_t slot, uint32_t attempt) {
+  const double z = hb_draw_z(KEY, dom, iter, idx, slot, attempt);
+  TAPE(TP_Z, z, 0.0);
+  return z;
+}
 static double norm_at(uint32_t dom, uint32_t iter, uint32_t idx, uint32_t slot, double mean, double sd) {
-  return mean + sd * hb_draw_z(KEY, dom, iter, idx, slot, 0); /* stats.cpp:8-11 */
+  return mean + sd * z_at(dom, iter, idx, slot, 0); /* stats.cpp:8-11 */
 }
 static double chisq_at(uint32_t dom, uint32_t iter, uint32_t idx, uint32_t slot, double df) {
-  return hb_draw_chisq(KEY, dom, iter, idx, slot, df); /* stats.cpp:22-24 */
+  const double c = hb_draw_chisq(KEY, dom, iter, idx, slot, df); /* stats.cpp:22-24 */
+  TAPE(TP_CHISQ, c, df);
+  return c;
+}
+static double gamma_at(uint32_t dom, uint32_t iter, uint32_t idx, uint32_t slot, double shape) {
+  const double v = hb_draw_gamma(KEY, dom, iter, idx, slot, shape); /* stats.cpp:13-15, scale applied by the caller */
+  TAPE(TP_GAMMA, v, shape);
+  return v;
 }
 
 /* exposed helpers */
@@ -385,7 +408,7 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
         }
       for (int j = 0; j < nk; ++j) {                                                              /* :534-535 */
         if (k_eval[j] < 0) k_eval[j] = 0.0;
-        k_w[j] = sqrt(k_eval[j]) * hb_draw_z(KEY, HB_DOM_K, it, (uint32_t)j, 0, 0);
+        k_w[j] = sqrt(k_eval[j]) * z_at(HB_DOM_K, it, (uint32_t)j, 0, 0);
       }
       for (int i = 0; i < n; ++i) k_rhs[i] = 0.0;
       for (int j = 0; j < nk; ++j) daxpy(n, k_w[j], K + (size_t)j * n, k_rhs);
@@ -513,10 +536,12 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
             acceptProb = 1 / t; }
           double rval, zval;
           hb_draw_uz(KEY, HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, 0, &rval, &zval);
+          TAPE(TP_U, rval, 0.0);
           indistflag = rval < acceptProb ? 0 : 1;
           snptracker[i] = indistflag;
           if (indistflag) {
             v = xx + vare_ / varg;
+            TAPE(TP_Z, zval, 0.0);
             gi = rhs / v + sqrt(vare_ / v) * zval;
             gi_ = oldgi - gi;
             daxpy(n, gi_, dxi, yadj);
@@ -542,7 +567,7 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
         if (!fixpi) { /* rdirichlet_sample stats.cpp:69-76 */
           double tot = 0.0;
           for (int j = 0; j < n_fold; ++j) {
-            Pi[j] = hb_draw_gamma(KEY, HB_DOM_ITER, it, HB_IT_PI0 + (uint32_t)j, 0, fold_snp_num[j] + 1);
+            Pi[j] = gamma_at(HB_DOM_ITER, it, HB_IT_PI0 + (uint32_t)j, 0, fold_snp_num[j] + 1);
           }
           tot = acc_sum(Pi, n_fold);
           for (int j = 0; j < n_fold; ++j) Pi[j] /= tot;
@@ -561,6 +586,7 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
           if (fabs(gi) < 1e-6) gi = 1e-6;
           { double uu, zz;
             hb_draw_uz(KEY, HB_DOM_SNP, it, (uint32_t)i, HB_SL_IG, 0, &uu, &zz);
+            TAPE(TP_Z, zz, 0.0); TAPE(TP_U, uu, 0.0);
             vargi = 1 / hb_invgauss_from_uz(sqrt(vare_) * lambda / fabs(gi), lambda2, uu, zz); }
           if (vargi >= 0) vargL[i] = vargi;
           gi_ = oldgi - gi;
@@ -571,7 +597,7 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
         }
         shape = shape0 + m - nvar0;
         rate = rate0 + acc_sum(vargL, m) / 2;
-        lambda2 = hb_draw_gamma(KEY, HB_DOM_ITER, it, HB_IT_LAMBDA, 0, shape) * (1 / rate);
+        lambda2 = gamma_at(HB_DOM_ITER, it, HB_IT_LAMBDA, 0, shape) * (1 / rate);
         lambda = sqrt(lambda2);
         break;
       case 6: /* BayesR :743-815 */
@@ -601,6 +627,7 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
           indistflag = 0;
           double rval, zval;
           hb_draw_uz(KEY, HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, 0, &rval, &zval);
+          TAPE(TP_U, rval, 0.0);
           for (int j = 0; j < n_fold; ++j) {
             acceptProb += stemp[j];
             if (rval < acceptProb) { indistflag = j; break; }
@@ -608,6 +635,7 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
           snptracker[i] = indistflag;
           if (indistflag) {
             v = xx + vare_vara_fold[indistflag];
+            TAPE(TP_Z, zval, 0.0);
             gi = rhs / v + sqrt(vare_ / v) * zval;
             gi_ = oldgi - gi;
             daxpy(n, gi_, dxi, yadj);
@@ -636,7 +664,7 @@ int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o) {
         fold_snp_num[0] -= nvar0;
         if (!fixpi) {
           for (int j = 0; j < n_fold; ++j)
-            Pi[j] = hb_draw_gamma(KEY, HB_DOM_ITER, it, HB_IT_PI0 + (uint32_t)j, 0, fold_snp_num[j] + 1);
+            Pi[j] = gamma_at(HB_DOM_ITER, it, HB_IT_PI0 + (uint32_t)j, 0, fold_snp_num[j] + 1);
           double tot = acc_sum(Pi, n_fold);
           for (int j = 0; j < n_fold; ++j) Pi[j] /= tot;
         }
@@ -954,7 +982,7 @@ static int sbayes_impl(const hbo_sbayes_args* a, hbo_sbayes_out* o, int sparse) 
 #define VAREI(i) (sparse ? varediff[i] * vara_ + vare_ : vare_)
 /* SBayesS.cpp:388-398 / :489-499 */
 #define REDRAW_LOOP(i) do { if (sparse && (gi * gi * vx[i]) > vary) { int ii = 0; \
-    while ((gi * gi * vx[i]) > vary) { gi = rhs / v + sqrt(varei / v) * hb_draw_z(KEY, HB_DOM_SNP, it, (uint32_t)(i), HB_SL_RETRY, (uint32_t)(ii + 1)); \
+    while ((gi * gi * vx[i]) > vary) { gi = rhs / v + sqrt(varei / v) * z_at(HB_DOM_SNP, it, (uint32_t)(i), HB_SL_RETRY, (uint32_t)(ii + 1)); \
       vargi = gi * gi; ii++; if (ii > 100) gi = 0; } } } while (0)
   int count_y = 0, nvar0 = 0;
   for (int k = 0; k < m; ++k) {   /* :100-112 */
@@ -1048,11 +1076,13 @@ static int sbayes_impl(const hbo_sbayes_args* a, hbo_sbayes_out* o, int sparse) 
           acceptProb = 1 / (exp(s[0] - s[0]) + exp(s[1] - s[0]));
           double rval, zval;
           hb_draw_uz(KEY, HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, 0, &rval, &zval);
+          TAPE(TP_U, rval, 0.0);
           indistflag = rval < acceptProb ? 0 : 1;
           snptracker[i] = indistflag;
           if (indistflag == 0) gi = 0;
           else {
             v = xx + varei / varg;
+            TAPE(TP_Z, zval, 0.0);
             gi = rhs / v + sqrt(varei / v) * zval;
             if (model_index == 4) { REDRAW_LOOP(i); vargi += gi * gi; }
           }
@@ -1068,7 +1098,7 @@ static int sbayes_impl(const hbo_sbayes_args* a, hbo_sbayes_out* o, int sparse) 
         if (model_index == 4)
           varg = (vargi + s2varg_ * dfvara_) / chisq_at(HB_DOM_ITER, it, HB_IT_VARG, 0, dfvara_ + NnzSnp);
         if (!fixpi) {
-          for (int j = 0; j < n_fold; ++j) Pi[j] = hb_draw_gamma(KEY, HB_DOM_ITER, it, HB_IT_PI0 + (uint32_t)j, 0, fold_snp_num[j] + 1);
+          for (int j = 0; j < n_fold; ++j) Pi[j] = gamma_at(HB_DOM_ITER, it, HB_IT_PI0 + (uint32_t)j, 0, fold_snp_num[j] + 1);
           const double tot = acc_sum(Pi, n_fold);
           for (int j = 0; j < n_fold; ++j) Pi[j] /= tot;
         }
@@ -1084,6 +1114,7 @@ static int sbayes_impl(const hbo_sbayes_args* a, hbo_sbayes_out* o, int sparse) 
           if (fabs(gi) < 1e-6) gi = 1e-6;
           { double uu, zz;
             hb_draw_uz(KEY, HB_DOM_SNP, it, (uint32_t)i, HB_SL_IG, 0, &uu, &zz);
+            TAPE(TP_Z, zz, 0.0); TAPE(TP_U, uu, 0.0);
             vargi = 1 / hb_invgauss_from_uz(sqrt(varei) * lambda / fabs(gi), lambda2, uu, zz); }
           if (vargi > 0) vargL[i] = vargi;
           if (gi != g[i]) {
@@ -1093,7 +1124,7 @@ static int sbayes_impl(const hbo_sbayes_args* a, hbo_sbayes_out* o, int sparse) 
           }
         }
         { const double shape = shape0 + count_y, rate = rate0 + acc_sum(vargL, m) / 2;
-          lambda2 = hb_draw_gamma(KEY, HB_DOM_ITER, it, HB_IT_LAMBDA, 0, shape) * (1 / rate);
+          lambda2 = gamma_at(HB_DOM_ITER, it, HB_IT_LAMBDA, 0, shape) * (1 / rate);
           lambda = sqrt(lambda2); }
         break;
       default: /* 6: BayesR :390-455 */
@@ -1120,11 +1151,13 @@ static int sbayes_impl(const hbo_sbayes_args* a, hbo_sbayes_out* o, int sparse) 
           acceptProb = 0; indistflag = 0;
           double rval, zval;
           hb_draw_uz(KEY, HB_DOM_SNP, it, (uint32_t)i, HB_SL_MAIN, 0, &rval, &zval);
+          TAPE(TP_U, rval, 0.0);
           for (int j = 0; j < n_fold; ++j) { acceptProb += stemp[j]; if (rval < acceptProb) { indistflag = j; break; } }
           snptracker[i] = indistflag;
           if (indistflag == 0) gi = 0;
           else {
             v = xx + varei / vara_fold[indistflag];
+            TAPE(TP_Z, zval, 0.0);
             gi = rhs / v + sqrt(varei / v) * zval;
             REDRAW_LOOP(i);
             varg += (gi * gi / fold_[indistflag]);
@@ -1141,7 +1174,7 @@ static int sbayes_impl(const hbo_sbayes_args* a, hbo_sbayes_out* o, int sparse) 
         for (int j = 0; j < n_fold; ++j) vara_fold[j] = varg * fold_[j];
         fold_snp_num[0] -= nvar0;
         if (!fixpi) {
-          for (int j = 0; j < n_fold; ++j) Pi[j] = hb_draw_gamma(KEY, HB_DOM_ITER, it, HB_IT_PI0 + (uint32_t)j, 0, fold_snp_num[j] + 1);
+          for (int j = 0; j < n_fold; ++j) Pi[j] = gamma_at(HB_DOM_ITER, it, HB_IT_PI0 + (uint32_t)j, 0, fold_snp_num[j] + 1);
           const double tot = acc_sum(Pi, n_fold);
           for (int j = 0; j < n_fold; ++j) Pi[j] /= tot;
         }

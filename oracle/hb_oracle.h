@@ -98,6 +98,14 @@ typedef struct {
 int hbo_bayes(const hbo_bayes_args* a, hbo_bayes_out* o);
 const char* hbo_last_error(void);
 
+/* ---- tape of the random variates a run consumes, in the order of the REFERENCE's own sampler calls (stats.cpp) ----
+ * Recorded by hbo_bayes / hbo_sbayesd / hbo_sbayess between hbo_tape_begin() and hbo_tape_end(); replayed to the compiled
+ * reference (oracle/_ref/libhibayes_ref.so, oracle/ref_shim/) in place of libR's generator, so that both see the same
+ * numbers.  kind: 0 unif_rand(), 1 norm_rand() (a standard normal), 2 R::rgamma(shape = param, 1), 3 R::rchisq(df = param). */
+typedef struct { int32_t kind; int32_t pad; double value; double param; } hbo_tape_entry;
+void hbo_tape_begin(hbo_tape_entry* buf, uint64_t cap);
+uint64_t hbo_tape_end(void);   /* entries the run produced (may exceed cap: then the tape is incomplete) */
+
 /* helpers exposed for unit tests */
 double hbo_var(const double* x, int n);             /* Armadillo var(), norm_type 0 */
 double hbo_qnorm(double p);

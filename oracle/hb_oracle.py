@@ -80,6 +80,65 @@ class Out(C.Structure):
     ]
 
 
+_REF = None
+TAPE_DTYPE = np.dtype([("kind", np.int32), ("pad", np.int32), ("value", np.float64), ("param", np.float64)])
+
+
+def ref_lib():
+    """oracle/_ref/libhibayes_ref.so: the reference's own Bayes.cpp / SBayesD.cpp / SBayesS.cpp / stats.cpp / solver.cpp
+    compiled unmodified against the stand-in headers of oracle/ref_shim (oracle/Makefile).  Built here, where
+    /root/reference exists; on the GPU box the prebuilt file is used.  None when it is not there."""
+    global _REF
+    if _REF is None:
+        path = os.path.join(_HERE, "_ref", "libhibayes_ref.so")
+        if not os.path.exists(path) and os.path.exists("/root/reference/src/Bayes.cpp"):
+            build()
+        if not os.path.exists(path):
+            return None
+        _REF = C.CDLL(path)
+        _REF.hbref_last_error.restype = C.c_char_p
+        for f in (_REF.hbref_bayes, _REF.hbref_sbayesd, _REF.hbref_sbayess):
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    return _REF
+
+
+def _tape_begin(cap):
+    L = lib()
+    L.hbo_tape_begin.argtypes = [C.c_void_p, C.c_uint64]
+    L.hbo_tape_end.restype = C.c_uint64
+    buf = np.zeros(int(cap), dtype=TAPE_DTYPE)
+    L.hbo_tape_begin(buf.ctypes.data, buf.shape[0])
+    return buf
+
+
+def _tape_end(buf):
+    n = lib().hbo_tape_end()
+    if n > buf.shape[0]:
+        raise RuntimeError("tape buffer too small: %d draws, room for %d" % (n, buf.shape[0]))
+    return buf[:n].copy()
+
+
+def _run(oracle_fn, ref_fn, a, o, replay, record_cap):
+    """One call: the oracle (optionally recording its tape) or, with replay = a tape, the compiled reference."""
+    if replay is not None:
+        R = ref_lib()
+        if R is None:
+            raise RuntimeError("oracle/_ref/libhibayes_ref.so is not built")
+        tp = np.ascontiguousarray(replay, dtype=TAPE_DTYPE)
+        used = C.c_size_t(0)
+        rc = getattr(R, ref_fn)(C.addressof(a), C.addressof(o), tp.ctypes.data, tp.shape[0], C.byref(used))
+        if rc != 0:
+            raise RuntimeError("reference: " + R.hbref_last_error().decode())
+        return {"consumed": used.value, "tape_len": int(tp.shape[0])}
+    buf = _tape_begin(record_cap) if record_cap else None
+    rc = oracle_fn(C.byref(a), C.byref(o))
+    tape = _tape_end(buf) if record_cap else None
+    if rc != 0:
+        raise RuntimeError(lib().hbo_last_error().decode())
+    return {"tape": tape}
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data
 
@@ -91,13 +150,16 @@ def _nan(v):
 def bayes(y, X, model, Pi, fold=None, C_=None, R=None, niter=200, nburn=100, thin=5,
           dfvr=None, s2vr=None, vg=None, dfvg=None, s2vg=None, ve=None, dfve=None, s2ve=None,
           windindx=None, seed=666666, epsl_y_J=None, epsl_Gi=None, epsl_index=None,
-          store_alpha=False, Kival=None, Ki=None):
+          store_alpha=False, Kival=None, Ki=None, record_tape=False, replay_on_reference=None):
     """Oracle twin of hibayes' C++ Bayes() (Bayes.cpp:60-88 argument list).
 
     X: (n, m) array, float64 or int8 (Fortran order is used internally).
     R: (n, nr) integer level codes (0-based) for environmental random effects.
     epsl_Gi: scipy.sparse matrix (qe x qe); epsl_index 1-based.
     Returns a dict named like the reference's Rcpp::List plus diagnostics.
+    record_tape: also return res["tape"], the variates consumed in the order of the reference's sampler calls.
+    replay_on_reference: a tape -> the SAME arguments go to the compiled reference (ref_lib()) instead of the oracle;
+    the diagnostics the reference does not return stay zero, res["replay"] says how much of the tape it consumed.
     """
     L = lib()
     y = np.ascontiguousarray(y, dtype=np.float64)
@@ -199,9 +261,12 @@ def bayes(y, X, model, Pi, fold=None, C_=None, R=None, niter=200, nburn=100, thi
     o.wppa_count = _ptr(dg["wppa_count"]) if nw else None
     o.nnz_trace, o.vara_trace, o.vare_trace, o.varg_trace = (_ptr(dg["nnz_trace"]), _ptr(dg["vara_trace"]),
                                                              _ptr(dg["vare_trace"]), _ptr(dg["varg_trace"]))
-    rc = L.hbo_bayes(C.byref(a), C.byref(o))
-    if rc != 0:
-        raise RuntimeError(L.hbo_last_error().decode())
+    cap = niter * (3 * m + nc + n_levels + nr + qe + a.nk + F + 16) if record_tape else 0
+    info = _run(L.hbo_bayes, "hbref_bayes", a, o, replay_on_reference, cap)
+    if record_tape:
+        res["tape"] = info["tape"]
+    if replay_on_reference is not None:
+        res["replay"] = info
     res.update({"Vg": o.Vg, "Ve": o.Ve, "h2": o.h2, "mu": o.mu, "Veps": o.Veps, "J": o.J})
     res["MCMCsamples"] = mc
     dg.update({"n_records": o.n_records_done, "nzct": o.nzct, "iters_done": o.iters_done,
@@ -255,7 +320,8 @@ def sbayes_buffers(m, F, niter, nburn, thin, nw, out_struct):
     return res, mc, dg
 
 
-def _sbayes(sumstat, ldm, sparse, model, Pi, fold, niter, nburn, thin, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, seed):
+def _sbayes(sumstat, ldm, sparse, model, Pi, fold, niter, nburn, thin, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, seed,
+            record_tape=False, replay_on_reference=None, store_alpha=False):
     L = lib()
     ss = np.asfortranarray(sumstat, dtype=np.float64)
     keep = [ss]
@@ -293,8 +359,16 @@ def _sbayes(sumstat, ldm, sparse, model, Pi, fold, niter, nburn, thin, windindx,
     res, mc, dg = sbayes_buffers(m, F, niter, nburn, thin, nw, o)
     fn = L.hbo_sbayess if sparse else L.hbo_sbayesd
     fn.restype = C.c_int
-    if fn(C.byref(a), C.byref(o)) != 0:
-        raise RuntimeError(L.hbo_last_error().decode())
+    if store_alpha:
+        mc["alpha"] = np.zeros((m, max((niter - nburn) // thin, 0)), order="F")
+        o.alpha_store = mc["alpha"].ctypes.data
+    cap = niter * (103 * m + F + 16) if record_tape else 0   # (SBayesS may re-draw a SNP up to 101 times)
+    cap = min(cap, 50_000_000)
+    info = _run(fn, "hbref_sbayess" if sparse else "hbref_sbayesd", a, o, replay_on_reference, cap)
+    if record_tape:
+        res["tape"] = info["tape"]
+    if replay_on_reference is not None:
+        res["replay"] = info
     res.update({"Vg": o.Vg, "Ve": o.Ve, "h2": o.h2, "MCMCsamples": mc})
     dg.update({"n_records": o.n_records_done, "nzct": o.nzct, "iters_done": o.iters_done, "n_used": o.n_used})
     res["diag"] = dg
@@ -302,15 +376,15 @@ def _sbayes(sumstat, ldm, sparse, model, Pi, fold, niter, nburn, thin, windindx,
 
 
 def sbayesd(sumstat, ldm, model, Pi, fold=None, niter=200, nburn=100, thin=5, windindx=None, vg=None, dfvg=None, s2vg=None,
-            ve=None, dfve=None, s2ve=None, seed=666666):
+            ve=None, dfve=None, s2ve=None, seed=666666, **kw):
     """CPU oracle of SBayesD(): sumstat m x 4 (MAF, BETA, SE, N), ldm m x m dense."""
-    return _sbayes(sumstat, ldm, False, model, Pi, fold, niter, nburn, thin, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, seed)
+    return _sbayes(sumstat, ldm, False, model, Pi, fold, niter, nburn, thin, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, seed, **kw)
 
 
 def sbayess(sumstat, ldm, model, Pi, fold=None, niter=200, nburn=100, thin=5, windindx=None, vg=None, dfvg=None, s2vg=None,
-            ve=None, dfve=None, s2ve=None, seed=666666):
+            ve=None, dfve=None, s2ve=None, seed=666666, **kw):
     """CPU oracle of SBayesS(): ldm a scipy sparse matrix (or anything csc_matrix() accepts)."""
-    return _sbayes(sumstat, ldm, True, model, Pi, fold, niter, nburn, thin, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, seed)
+    return _sbayes(sumstat, ldm, True, model, Pi, fold, niter, nburn, thin, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, seed, **kw)
 
 
 # ---- .bed decoder and LD builder (oracle/hb_oracle_ld.c) ----
