@@ -4,7 +4,7 @@
  * (/root/reference/src/stats.cpp:3-28,55-76) and the sparse Gauss-Seidel
  * sampler used by the single-step model (/root/reference/src/solver.cpp:131-140).
  *
- * TEST INFRASTRUCTURE ONLY -- see hb_oracle.h ("parity unpinned").
+ * TEST INFRASTRUCTURE ONLY -- see hb_oracle.h (parity pinned against the compiled reference, oracle/_ref).
  *
  * Loop structure, operation order and quirks follow the reference line by line;
  * the only substitution is the random stream (hb_rng.h addresses instead of

@@ -428,3 +428,42 @@ def txxmat(X, chr=None, chisq=None):
     L.hbo_txxmat(Xf.ctypes.data, n, n, m, _ptr(c), int(chisq is not None), 0.0 if chisq is None else float(chisq),
                  out.ctypes.data)
     return out
+
+
+# ---- the same three through the compiled reference (oracle/_ref/libhibayes_ref.so: tXXmat.cpp, read_bed.cpp) ----
+def ref_bigstat(X):
+    """BigStat() of the reference itself (tXXmat.cpp:43-98) on a big.matrix of type char."""
+    R = ref_lib()
+    Xf = np.asfortranarray(X, dtype=np.int8)
+    n, m = Xf.shape
+    mean, sm, xx = np.zeros(m), np.zeros(m), np.zeros(m)
+    R.hbref_bigstat.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    if R.hbref_bigstat(Xf.ctypes.data, n, m, mean.ctypes.data, sm.ctypes.data, xx.ctypes.data) != 0:
+        raise RuntimeError("reference: " + R.hbref_last_error().decode())
+    return {"mean": mean, "sum": sm, "xx": xx}
+
+
+def ref_txxmat(X, chr=None, chisq=None):
+    """tXXmat_Geno() / tXXmat_Chr() of the reference itself (tXXmat.cpp:100-206, 504-626): (m x m matrix with zeros where
+    the returned arma::sp_mat stores nothing, number of stored entries)."""
+    R = ref_lib()
+    Xf = np.asfortranarray(X, dtype=np.int8)
+    n, m = Xf.shape
+    c = None if chr is None else np.ascontiguousarray(chr, dtype=np.int32)
+    out = np.zeros((m, m), order="F")
+    stored = C.c_longlong(0)
+    R.hbref_txxmat.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_longlong)]
+    if R.hbref_txxmat(Xf.ctypes.data, n, m, _ptr(c), int(chisq is not None), 0.0 if chisq is None else float(chisq),
+                      out.ctypes.data, C.byref(stored)) != 0:
+        raise RuntimeError("reference: " + R.hbref_last_error().decode())
+    return out, stored.value
+
+
+def ref_read_bed(path, nid, m, impute=True, dominance=False, max_line=10000):
+    """read_bed<char>() of the reference itself (read_bed.cpp:97-247) on a .bed file: nid x m int8 (F order)."""
+    R = ref_lib()
+    out = np.zeros((nid, m), dtype=np.int8, order="F")
+    R.hbref_read_bed.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, C.c_void_p]
+    if R.hbref_read_bed(path.encode(), nid, m, max_line, int(impute), int(dominance), out.ctypes.data) != 0:
+        raise RuntimeError("reference: " + R.hbref_last_error().decode())
+    return out

@@ -3,11 +3,11 @@
  * the PLINK .bed decoder and the LD / X'X builder.  TEST INFRASTRUCTURE ONLY: only tests/,
  * __graft_entry__.smoke() and bench.py's CPU arms may load this; hibayes_b200/ never links it.
  *
- * PARITY UNPINNED against the running reference (an R package: needs R, Rcpp, bigmemory, BH,
- * RcppProgress; cannot be built here and ships no tests).  Both functions are literal restatements of
- * the reference loops -- same operation order, so the results are what the reference computes on the
- * same inputs up to nothing at all for the decoder (bytes) and for the off-diagonal LD entries (the
- * inner product is an exact integer; the centring expression is evaluated in the reference's order).
+ * PARITY PINNED against the reference itself: tXXmat.cpp and read_bed.cpp compile unmodified against the stand-in
+ * Rcpp / Armadillo / bigmemory / RcppProgress headers of oracle/ref_shim/ into oracle/_ref/libhibayes_ref.so, and
+ * BigStat(), tXXmat_Geno(), tXXmat_Chr() and read_bed<char>() return the same bits as the functions below
+ * (tests/test_reference_pin.py: the bundled demo.bed, ragged files with missing genotypes, dense / sparse / per-chromosome
+ * LD with a monomorphic SNP).  Both functions are literal restatements of the reference loops -- same operation order.
  * The decoder is additionally pinned against an independent numpy decode of the reference's bundled
  * inst/extdata/demo.bed (tests/golden/demo_bed.npz, tests/test_ldmat_bed.py).
  */

@@ -13,6 +13,7 @@
 
 #include "../hb_oracle.h"
 #include "RcppArmadillo.h"
+#include "bigmemory/BigMatrix.h"
 
 using namespace Rcpp;
 using namespace arma;
@@ -32,6 +33,12 @@ Rcpp::List SBayesS(arma::mat sumstat, arma::sp_mat ldm, std::string model, arma:
                    const Nullable<arma::vec> fold, const Nullable<arma::uvec> windindx, const Nullable<double> vg, const Nullable<double> dfvg,
                    const Nullable<double> s2vg, const Nullable<double> ve, const Nullable<double> dfve, const Nullable<double> s2ve,
                    const int outfreq, const int threads, const bool verbose);
+
+// tXXmat.cpp:80, :188, :608 and read_bed.cpp:235 (the exported dispatchers on the big.matrix type)
+SEXP BigStat(SEXP pBigMat, const int threads);
+SEXP tXXmat_Geno(SEXP pBigMat, const Nullable<double> chisq, const int threads, const bool verbose);
+SEXP tXXmat_Chr(SEXP pBigMat, const NumericVector chr, const Nullable<double> chisq, const int threads, const bool verbose);
+void read_bed(std::string bfile, const SEXP pBigMat, const long maxLine, const bool impt, const bool d, const int threads);
 
 // ---- the tape -------------------------------------------------------------------------------------------------------
 static const hbo_tape_entry* g_tape = nullptr;
@@ -239,3 +246,49 @@ static int run_sbayes(int sparse, const hbo_sbayes_args* a, hbo_sbayes_out* o, c
 }
 extern "C" int hbref_sbayesd(const hbo_sbayes_args* a, hbo_sbayes_out* o, const hbo_tape_entry* tape, size_t ntape, size_t* consumed) { return run_sbayes(0, a, o, tape, ntape, consumed); }
 extern "C" int hbref_sbayess(const hbo_sbayes_args* a, hbo_sbayes_out* o, const hbo_tape_entry* tape, size_t ntape, size_t* consumed) { return run_sbayes(1, a, o, tape, ntape, consumed); }
+
+// ---- LD builder and .bed decoder (no random numbers) --------------------------------------------------------------------------
+// X: nid x m int8 column-major (a big.matrix of type char, what read_bed() fills and ldmat() hands over, R/ldm.r).
+extern "C" int hbref_bigstat(const int8_t* X, int nid, int m, double* mean, double* sum, double* xx) {
+  g_err[0] = 0;
+  try {
+    BigMatrix bm(const_cast<int8_t*>(X), nid, m, 1);
+    List st(BigStat(XPtr<BigMatrix>(&bm), 1));
+    const NumericVector a = st[0], b = st[1], c = st[2];
+    for (int j = 0; j < m; ++j) { mean[j] = a[j]; sum[j] = b[j]; xx[j] = c[j]; }
+    return 0;
+  } catch (const std::exception& e) { snprintf(g_err, sizeof g_err, "%s", e.what()); return 1; }
+}
+// out: m x m column-major, zero where the reference's arma::sp_mat stores nothing.  chr NULL -> tXXmat_Geno, else tXXmat_Chr.
+extern "C" int hbref_txxmat(const int8_t* X, int nid, int m, const int32_t* chr, int has_chisq, double chisq, double* out, long long* stored) {
+  g_err[0] = 0;
+  try {
+    BigMatrix bm(const_cast<int8_t*>(X), nid, m, 1);
+    XPtr<BigMatrix> xp(&bm);
+    Nullable<double> cs; if (has_chisq) cs = Nullable<double>(chisq);
+    SEXP res;
+    if (chr) { NumericVector c(m); for (int j = 0; j < m; ++j) c[j] = chr[j]; res = tXXmat_Chr(xp, c, cs, 1, false); }
+    else res = tXXmat_Geno(xp, cs, 1, false);
+    memset(out, 0, sizeof(double) * (size_t)m * m);
+    const bool is_sparse = chr != nullptr || (has_chisq && chisq > 0);   // (tXXmat.cpp:117-120, :520-523: which branch returns what)
+    if (is_sparse) {
+      const sp_mat& L = res->payload.get<sp_mat>();
+      for (uword j = 0; j < L.n_cols; ++j) for (uword p = L.col_ptrs[j]; p < L.col_ptrs[j + 1]; ++p) out[(size_t)j * m + L.row_indices[p]] = L.values[p];
+      if (stored) *stored = (long long)L.n_nonzero;
+    } else {
+      const mat& L = res->payload.get<mat>();
+      memcpy(out, L.mem.data(), sizeof(double) * (size_t)m * m);
+      if (stored) *stored = (long long)m * m;
+    }
+    return 0;
+  } catch (const std::exception& e) { snprintf(g_err, sizeof g_err, "%s", e.what()); return 1; }
+}
+// read_bed<char>() on a file: out nid x m int8 column-major
+extern "C" int hbref_read_bed(const char* bfile, int nid, int m, long maxLine, int impute, int dominance, int8_t* out) {
+  g_err[0] = 0;
+  try {
+    BigMatrix bm(out, nid, m, 1);
+    read_bed(std::string(bfile), XPtr<BigMatrix>(&bm), maxLine, impute != 0, dominance != 0, 1);
+    return 0;
+  } catch (const std::exception& e) { snprintf(g_err, sizeof g_err, "%s", e.what()); return 1; }
+}

@@ -267,3 +267,42 @@ def test_gpu_sbayes_against_the_reference_fixtures(kind, model, Pi, fold):
     ss, ld = _fixture_inputs(kind)
     got = (hb.SBayesD if kind == "sbayesd" else hb.SBayesS)(ss, ld, model, list(f["Pi"]), store_alpha=True, **_fixture_kw(f))
     _check_against_fixture(got, f, model, 1e-5)
+
+
+# ---- the stages in front of the sweeps: LD builder and .bed decoder (no random numbers: plain equality) -----------------------
+def test_bigstat_and_txxmat_are_the_references(ref):
+    """oracle/hb_oracle_ld.c against BigStat(), tXXmat_Geno(), tXXmat_Chr() of tXXmat.cpp as compiled: every entry the
+    same bits, the number of stored entries of the returned arma::sp_mat = the non-zeros of the oracle's matrix."""
+    y, X = synth(333, 90, seed=4)
+    X[:, 5] = 1                                         # a monomorphic SNP: xx = 0, r = NaN in the sparse branch
+    a, b = ref.bigstat(X), ref.ref_bigstat(X)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    chr_ = np.repeat([1, 2, 3], 30)
+    for c, q in [(None, None), (None, 3.84), (chr_, None), (chr_, 3.84), (chr_, 0.0)]:
+        o = ref.txxmat(X, chr=c, chisq=q)
+        r, stored = ref.ref_txxmat(X, chr=c, chisq=q)
+        assert np.array_equal(o, r, equal_nan=True), (c is not None, q)
+        if c is not None or q is not None:
+            assert stored == np.count_nonzero(o)
+    # tXXmat_Geno takes its sparse branch only for chisq > 0 (tXXmat.cpp:117-120); ldmat_plan() maps that before the ABI
+    r0, stored0 = ref.ref_txxmat(X, chisq=0.0)
+    assert stored0 == 90 * 90 and np.array_equal(r0, ref.txxmat(X))
+
+
+@pytest.mark.parametrize("impute,dominance", [(True, False), (False, False), (True, True)])
+def test_read_bed_is_the_references(ref, tmp_path, impute, dominance):
+    """oracle read_bed against read_bed<char>() of read_bed.cpp as compiled, on the reference's own demo.bed and on a file
+    with missing genotypes, a number of individuals that is not a multiple of 4, more SNPs than one buffer holds."""
+    from tests.util_bed import make_bed
+    d = np.load(os.path.join(GOLDEN, "demo_bed.npz"))
+    p = tmp_path / "demo.bed"
+    p.write_bytes(d["bed"].tobytes())
+    want, _ = ref.read_bed(d["bed"], 600, 1000, impute=impute, dominance=dominance)
+    assert np.array_equal(ref.ref_read_bed(str(p), 600, 1000, impute=impute, dominance=dominance), want)
+    img, _ = make_bed(203, 77, seed=5, p_missing=0.15, all_missing_cols=(9,))
+    q = tmp_path / "ragged.bed"
+    q.write_bytes(img.tobytes())
+    want, _ = ref.read_bed(img, 203, 77, impute=impute, dominance=dominance)
+    for max_line in (10000, 16):
+        assert np.array_equal(ref.ref_read_bed(str(q), 203, 77, impute=impute, dominance=dominance, max_line=max_line), want)
