@@ -24,8 +24,9 @@ reductions -- what replaces Bayes.cpp:586-823 -- driven by the host-side scalar 
 --config c4   BASELINE configs[3]: sbrm() SBayesD on a dense fp64 LD matrix of the largest m that fits (--m, default 100 000).
 --config c5   BASELINE configs[4] surrogate: the single-step call of Bayes() (J + epsilon on the device) with integer rows, 1 GPU.
 `--impl reference`  the reference's own CPU data path (per-SNP ddot + 2 daxpy on a column-major fp64 matrix,
-            Bayes.cpp:751-802, all host threads) on a bounded column sample of the same workload (oracle port: the
-            reference itself needs R/Rcpp/Armadillo and cannot be built here).
+            Bayes.cpp:751-802, all host threads) on a bounded column sample of the same workload: Bayes() of the
+            reference's own Bayes.cpp as compiled into oracle/_ref (stand-in R/Rcpp/Armadillo headers, OpenBLAS level 1),
+            with the oracle port's two variants of the bare data path listed beside it.
 """
 import argparse
 import json
@@ -125,6 +126,49 @@ def cpu_reference(n, m_cpu, sweeps, threads):
     return v_omp, "OpenMP ddot/daxpy", {"openmp": v_omp, "openblas": v_blas}
 
 
+def _openblas_path():
+    import glob
+    import scipy
+    hits = glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas-*.so"))
+    return (hits[0], "scipy_") if hits else (None, None)
+
+
+def cpu_reference_compiled(n, m_cpu, sweeps, blas=True):
+    """The reference ITSELF on the CPU: Bayes() of /root/reference/src/Bayes.cpp as compiled into
+    oracle/_ref/libhibayes_ref.so (oracle/Makefile, stand-in R/Rcpp/Armadillo headers), model BayesR on the first m_cpu
+    columns of the workload as an fp64 arma::mat (what ibrm() hands over), its ddot_/daxpy_ forwarded to the bundled
+    multi-threaded OpenBLAS (blas=True; an R linked against OpenBLAS) or run by reference-BLAS loops.  Its random draws
+    replay the oracle's tape for the same call; the timed region is iterations 2..1+sweeps of the MCMC loop, from the first
+    draw of iteration 2 to the last draw of the run (time stamps taken inside the library at those tape positions).
+    Returns SNP-updates/s or None when the library is not there."""
+    from oracle import hb_oracle
+    import ctypes as C
+    import hibayes_b200 as hb
+    R = hb_oracle.ref_lib()
+    if R is None:
+        return None
+    X = hb.synth_geno_host(n, m_cpu, 20260101)
+    rng = np.random.default_rng(7)
+    y = X[:, :50].astype(np.float64) @ rng.normal(scale=0.1, size=50) + rng.normal(size=n)
+    kw = dict(fold=FOLD, thin=1, seed=12345)
+    p1 = len(hb_oracle.bayes(y, X, "BayesR", PI_R, niter=1, nburn=0, record_tape=True, **kw)["tape"])
+    tape = hb_oracle.bayes(y, X, "BayesR", PI_R, niter=1 + sweeps, nburn=sweeps, record_tape=True, **kw)["tape"]
+    path, prefix = _openblas_path() if blas else (None, None)
+    R.hbref_use_blas.argtypes = [C.c_char_p, C.c_char_p]
+    if R.hbref_use_blas(path.encode() if path else None, prefix.encode() if prefix else None) != 0:
+        raise RuntimeError(R.hbref_last_error().decode())
+    marks = (C.c_uint64 * 2)(p1, len(tape) - 1)
+    R.hbref_set_time_marks(marks, 2)
+    try:
+        hb_oracle.bayes(y, X, "BayesR", PI_R, niter=1 + sweeps, nburn=sweeps, replay_on_reference=tape, **kw)
+    finally:
+        R.hbref_use_blas(None, None)
+    t = (C.c_double * 2)()
+    R.hbref_get_time_marks(t, 2)
+    R.hbref_set_time_marks(marks, 0)
+    return m_cpu * sweeps / (t[1] - t[0])
+
+
 def _cpu_openblas(n, m_cpu, sweeps):
     from scipy.linalg import blas
     rng = np.random.default_rng(1)
@@ -195,6 +239,31 @@ class Chain:
         self.it += 1
 
 
+def cpu_arm(n, m_cpu, sweeps, threads):
+    """(value, kind, sample, variants) of the CPU arm: the compiled reference (oracle/_ref, kind "reference") when the
+    library is there -- its own Bayes() with OpenBLAS level 1 -- else the oracle port of its data path (kind "port").
+    The port's two variants (the bare ddot / 2 daxpy data path, without the class probabilities) are measured in both
+    cases and listed under `variants`."""
+    v_port, how, both = cpu_reference(n, m_cpu, sweeps, threads)
+    both = dict(both)
+    v_ref = None
+    try:
+        m_ref = min(m_cpu, 8000)   # (the compiled reference holds X as fp64 and the oracle run that records its tape is serial)
+        v_ref = cpu_reference_compiled(n, m_ref, sweeps, blas=True)
+        both["compiled_reference_openblas"] = v_ref
+        both["compiled_reference_netlib_loops_1_thread"] = cpu_reference_compiled(n, min(m_cpu, 2000), 2, blas=False)
+    except Exception as e:   # noqa: BLE001 -- the arm must print a line in any case
+        both["compiled_reference_error"] = str(e)[:200]
+    if v_ref is not None:
+        note = "" if v_ref >= v_port else ("; the oracle port of the bare data path (no class probabilities) runs at %.0f/s, see variants" % v_port)
+        return v_ref, "reference", ("Bayes() of the reference's own Bayes.cpp compiled into oracle/_ref (BayesR, n=%d x m=%d fp64 "
+                                    "arma::mat = the first columns of the workload, ddot_/daxpy_ -> bundled multi-threaded OpenBLAS), "
+                                    "1 warm-up + %d timed iterations of its MCMC loop%s" % (n, m_ref, sweeps, note)), both
+    sample = ("n=%d x m=%d fp64 column-major, 1 warm-up + %d timed sweeps, %s (oracle port of Bayes.cpp:751-802; oracle/_ref not "
+              "built)" % (n, m_cpu, sweeps, how))
+    return v_port, "port", sample, both
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -204,17 +273,15 @@ def run_reference(args):
     n, m_cpu = args.n, args.m_cpu
     sweeps = max(3, min(args.steps, 5))   # each "step" = one sweep over the m_cpu-column sample; >= 3 timed sweeps
     t0 = time.time()
-    val, how, both = cpu_reference(n, m_cpu, sweeps, threads)
+    val, kind, sample, both = cpu_arm(n, m_cpu, sweeps, threads)
     wall = time.time() - t0
-    sample = ("n=%d x m=%d fp64 column-major, 1 warm-up + %d timed sweeps, %s (oracle port; the reference needs "
-              "R/Rcpp/Armadillo and cannot be built here)" % (n, m_cpu, sweeps, how))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * m_cpu / val, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "ibrm() BayesR sweep, synthetic n=%d x m=%d (CPU sample: first %d columns)" % (n, args.m, m_cpu),
                    "n": n, "m": args.m, "m_sample": m_cpu, "variants": both},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
     }
@@ -477,10 +544,8 @@ def run_gpu(args):
         line["parity_check"] = parity
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        val, how, both = cpu_reference(n_local, args.m_cpu, 3, threads)
-        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "n=%d x m=%d fp64 column-major (first columns of the workload), 1 warm-up + 3 timed "
-                                          "sweeps, %s" % (n_local, args.m_cpu, how), "variants": both}
+        val, kind, sample, both = cpu_arm(n_local, args.m_cpu, 3, threads)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample, "variants": both}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if comm:

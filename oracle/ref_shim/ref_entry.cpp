@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+#include <time.h>
 
 #include "../hb_oracle.h"
 #include "RcppArmadillo.h"
@@ -44,7 +46,18 @@ void read_bed(std::string bfile, const SEXP pBigMat, const long maxLine, const b
 static const hbo_tape_entry* g_tape = nullptr;
 static size_t g_tape_n = 0, g_tape_pos = 0;
 static const char* const KIND[] = {"uniform", "normal", "gamma", "chi-square"};
+// time stamps at chosen tape positions (bench.py's reference arm: the first draw of an iteration marks its start)
+static uint64_t g_mark_pos[16];
+static double g_mark_t[16];
+static int g_nmarks = 0, g_next_mark = 0;
+static double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+extern "C" void hbref_set_time_marks(const uint64_t* pos, int n) {
+  g_nmarks = n < 16 ? n : 16; g_next_mark = 0;
+  for (int i = 0; i < g_nmarks; ++i) { g_mark_pos[i] = pos[i]; g_mark_t[i] = 0.0; }
+}
+extern "C" void hbref_get_time_marks(double* t, int n) { for (int i = 0; i < n && i < g_nmarks; ++i) t[i] = g_mark_t[i]; }
 static double tape_pop(int kind, double param) {
+  if (g_next_mark < g_nmarks && g_tape_pos == g_mark_pos[g_next_mark]) g_mark_t[g_next_mark++] = now_s();
   if (!g_tape) throw Rcpp::exception("libhibayes_ref: a random draw was requested but no tape is set");
   char buf[256];
   if (g_tape_pos >= g_tape_n) {
@@ -79,13 +92,34 @@ double rexp(double) { return not_on_the_path("rexp"); }
 namespace arma { double mini_arma_randn() { return tape_pop(1, 0.0); } }
 
 // ---- reference BLAS level 1 (netlib ddot/daxpy with unit stride: one accumulator, ascending) ---------------------------
+// hbref_use_blas(path, prefix): forward both to a real BLAS (bench.py's reference arm: the bundled multi-threaded OpenBLAS,
+// what an R installation linked against OpenBLAS runs); the default loops are what the bit-for-bit pin tests use.
+typedef double (*ddot_fn)(const int*, const double*, const int*, const double*, const int*);
+typedef void (*daxpy_fn)(const int*, const double*, const double*, const int*, double*, const int*);
+static ddot_fn g_ddot = nullptr;
+static daxpy_fn g_daxpy = nullptr;
+extern "C" const char* hbref_last_error(void);
+static char g_err[600];
+extern "C" int hbref_use_blas(const char* path, const char* prefix) {
+  g_ddot = nullptr; g_daxpy = nullptr;
+  if (!path) return 0;
+  void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) { snprintf(g_err, sizeof g_err, "hbref_use_blas: %s", dlerror()); return 1; }
+  const std::string pre(prefix ? prefix : "");
+  g_ddot = (ddot_fn)dlsym(h, (pre + "ddot_").c_str());
+  g_daxpy = (daxpy_fn)dlsym(h, (pre + "daxpy_").c_str());
+  if (!g_ddot || !g_daxpy) { g_ddot = nullptr; g_daxpy = nullptr; snprintf(g_err, sizeof g_err, "hbref_use_blas: %sddot_ / %sdaxpy_ not found", pre.c_str(), pre.c_str()); return 1; }
+  return 0;
+}
 extern "C" double ddot_(const int* n, const double* x, const int* incx, const double* y, const int* incy) {
+  if (g_ddot) return g_ddot(n, x, incx, y, incy);
   double s = 0.0;
   const int ix = *incx, iy = *incy;
   for (int i = 0; i < *n; ++i) s += x[(size_t)i * ix] * y[(size_t)i * iy];
   return s;
 }
 extern "C" void daxpy_(const int* n, const double* a, const double* x, const int* incx, double* y, const int* incy) {
+  if (g_daxpy) { g_daxpy(n, a, x, incx, y, incy); return; }
   const int ix = *incx, iy = *incy;
   const double al = *a;
   if (al == 0.0) return;   // (netlib: quick return)
@@ -110,7 +144,6 @@ extern "C" void Rprintf(const char* fmt, ...) { if (!getenv("HB_REF_VERBOSE")) r
 extern "C" void REprintf(const char* fmt, ...) { if (!getenv("HB_REF_VERBOSE")) return; va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); }
 
 // ---- plain-buffer wrappers ----------------------------------------------------------------------------------------------
-static char g_err[600];
 extern "C" const char* hbref_last_error(void) { return g_err; }
 
 static Nullable<double> opt(double v) { return v == v ? Nullable<double>(v) : Nullable<double>(); }
