@@ -81,6 +81,7 @@ class Out(C.Structure):
 
 
 _REF = None
+_DROPIN = None
 TAPE_DTYPE = np.dtype([("kind", np.int32), ("pad", np.int32), ("value", np.float64), ("param", np.float64)])
 
 
@@ -103,6 +104,33 @@ def ref_lib():
     return _REF
 
 
+def dropin_lib():
+    """oracle/_ref/libhibayes_dropin.so: the same plain-buffer harness as ref_lib(), linked with the drop-in Rcpp bodies of
+    integration/rcpp/ (the reference's C++ signatures forwarding to libhibayes_b200.so) instead of the reference's files.
+    Needs a GPU at run time.  Its `tape` is two uniforms: what seed_from_r() draws to make the run key."""
+    global _DROPIN
+    if _DROPIN is None:
+        path = os.path.join(_HERE, "_ref", "libhibayes_dropin.so")
+        if not os.path.exists(path):
+            build()
+        if not os.path.exists(path):
+            return None
+        _DROPIN = C.CDLL(path)
+        _DROPIN.hbref_last_error.restype = C.c_char_p
+        for f in (_DROPIN.hbref_bayes, _DROPIN.hbref_sbayesd, _DROPIN.hbref_sbayess):
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    return _DROPIN
+
+
+def seed_tape(seed):
+    """The two unif_rand() values from which the drop-in bodies rebuild `seed` (integration/rcpp/hb_dropin.h)."""
+    t = np.zeros(2, dtype=TAPE_DTYPE)
+    t["value"][0] = float((seed >> 32) & 0xFFFFFFFF) / 4294967296.0
+    t["value"][1] = float(seed & 0xFFFFFFFF) / 4294967296.0
+    return t
+
+
 def _tape_begin(cap):
     L = lib()
     L.hbo_tape_begin.argtypes = [C.c_void_p, C.c_uint64]
@@ -119,17 +147,18 @@ def _tape_end(buf):
     return buf[:n].copy()
 
 
-def _run(oracle_fn, ref_fn, a, o, replay, record_cap):
-    """One call: the oracle (optionally recording its tape) or, with replay = a tape, the compiled reference."""
+def _run(oracle_fn, ref_fn, a, o, replay, record_cap, library="reference"):
+    """One call: the oracle (optionally recording its tape) or, with replay = a tape, the compiled reference
+    (library "reference") or the drop-in Rcpp bodies over the GPU library (library "dropin")."""
     if replay is not None:
-        R = ref_lib()
+        R = ref_lib() if library == "reference" else dropin_lib()
         if R is None:
-            raise RuntimeError("oracle/_ref/libhibayes_ref.so is not built")
+            raise RuntimeError("oracle/_ref/libhibayes_%s.so is not built" % ("ref" if library == "reference" else "dropin"))
         tp = np.ascontiguousarray(replay, dtype=TAPE_DTYPE)
         used = C.c_size_t(0)
         rc = getattr(R, ref_fn)(C.addressof(a), C.addressof(o), tp.ctypes.data, tp.shape[0], C.byref(used))
         if rc != 0:
-            raise RuntimeError("reference: " + R.hbref_last_error().decode())
+            raise RuntimeError(("reference: " if library == "reference" else "drop-in: ") + R.hbref_last_error().decode())
         return {"consumed": used.value, "tape_len": int(tp.shape[0])}
     buf = _tape_begin(record_cap) if record_cap else None
     rc = oracle_fn(C.byref(a), C.byref(o))
@@ -150,7 +179,7 @@ def _nan(v):
 def bayes(y, X, model, Pi, fold=None, C_=None, R=None, niter=200, nburn=100, thin=5,
           dfvr=None, s2vr=None, vg=None, dfvg=None, s2vg=None, ve=None, dfve=None, s2ve=None,
           windindx=None, seed=666666, epsl_y_J=None, epsl_Gi=None, epsl_index=None,
-          store_alpha=False, Kival=None, Ki=None, record_tape=False, replay_on_reference=None):
+          store_alpha=False, Kival=None, Ki=None, record_tape=False, replay_on_reference=None, library="reference"):
     """Oracle twin of hibayes' C++ Bayes() (Bayes.cpp:60-88 argument list).
 
     X: (n, m) array, float64 or int8 (Fortran order is used internally).
@@ -262,7 +291,7 @@ def bayes(y, X, model, Pi, fold=None, C_=None, R=None, niter=200, nburn=100, thi
     o.nnz_trace, o.vara_trace, o.vare_trace, o.varg_trace = (_ptr(dg["nnz_trace"]), _ptr(dg["vara_trace"]),
                                                              _ptr(dg["vare_trace"]), _ptr(dg["varg_trace"]))
     cap = niter * (3 * m + nc + n_levels + nr + qe + a.nk + F + 16) if record_tape else 0
-    info = _run(L.hbo_bayes, "hbref_bayes", a, o, replay_on_reference, cap)
+    info = _run(L.hbo_bayes, "hbref_bayes", a, o, replay_on_reference, cap, library)
     if record_tape:
         res["tape"] = info["tape"]
     if replay_on_reference is not None:
@@ -321,7 +350,7 @@ def sbayes_buffers(m, F, niter, nburn, thin, nw, out_struct):
 
 
 def _sbayes(sumstat, ldm, sparse, model, Pi, fold, niter, nburn, thin, windindx, vg, dfvg, s2vg, ve, dfve, s2ve, seed,
-            record_tape=False, replay_on_reference=None, store_alpha=False):
+            record_tape=False, replay_on_reference=None, store_alpha=False, library="reference"):
     L = lib()
     ss = np.asfortranarray(sumstat, dtype=np.float64)
     keep = [ss]
@@ -364,7 +393,7 @@ def _sbayes(sumstat, ldm, sparse, model, Pi, fold, niter, nburn, thin, windindx,
         o.alpha_store = mc["alpha"].ctypes.data
     cap = niter * (103 * m + F + 16) if record_tape else 0   # (SBayesS may re-draw a SNP up to 101 times)
     cap = min(cap, 50_000_000)
-    info = _run(fn, "hbref_sbayess" if sparse else "hbref_sbayesd", a, o, replay_on_reference, cap)
+    info = _run(fn, "hbref_sbayess" if sparse else "hbref_sbayesd", a, o, replay_on_reference, cap, library)
     if record_tape:
         res["tape"] = info["tape"]
     if replay_on_reference is not None:
@@ -431,9 +460,16 @@ def txxmat(X, chr=None, chisq=None):
 
 
 # ---- the same three through the compiled reference (oracle/_ref/libhibayes_ref.so: tXXmat.cpp, read_bed.cpp) ----
-def ref_bigstat(X):
+def _ldlib(library):
+    R = ref_lib() if library == "reference" else dropin_lib()
+    if R is None:
+        raise RuntimeError("oracle/_ref library '%s' is not built" % library)
+    return R
+
+
+def ref_bigstat(X, library="reference"):
     """BigStat() of the reference itself (tXXmat.cpp:43-98) on a big.matrix of type char."""
-    R = ref_lib()
+    R = _ldlib(library)
     Xf = np.asfortranarray(X, dtype=np.int8)
     n, m = Xf.shape
     mean, sm, xx = np.zeros(m), np.zeros(m), np.zeros(m)
@@ -443,10 +479,10 @@ def ref_bigstat(X):
     return {"mean": mean, "sum": sm, "xx": xx}
 
 
-def ref_txxmat(X, chr=None, chisq=None):
+def ref_txxmat(X, chr=None, chisq=None, library="reference"):
     """tXXmat_Geno() / tXXmat_Chr() of the reference itself (tXXmat.cpp:100-206, 504-626): (m x m matrix with zeros where
     the returned arma::sp_mat stores nothing, number of stored entries)."""
-    R = ref_lib()
+    R = _ldlib(library)
     Xf = np.asfortranarray(X, dtype=np.int8)
     n, m = Xf.shape
     c = None if chr is None else np.ascontiguousarray(chr, dtype=np.int32)
@@ -459,9 +495,9 @@ def ref_txxmat(X, chr=None, chisq=None):
     return out, stored.value
 
 
-def ref_read_bed(path, nid, m, impute=True, dominance=False, max_line=10000):
+def ref_read_bed(path, nid, m, impute=True, dominance=False, max_line=10000, library="reference"):
     """read_bed<char>() of the reference itself (read_bed.cpp:97-247) on a .bed file: nid x m int8 (F order)."""
-    R = ref_lib()
+    R = _ldlib(library)
     out = np.zeros((nid, m), dtype=np.int8, order="F")
     R.hbref_read_bed.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, C.c_void_p]
     if R.hbref_read_bed(path.encode(), nid, m, max_line, int(impute), int(dominance), out.ctypes.data) != 0:

@@ -323,6 +323,15 @@ template <class T> struct SpMat {
   std::vector<T> values;
   SpMat() {}
   SpMat(uword r, uword c) { resize0(r, c); }
+  // compressed columns as given (Armadillo's SpMat(rowind, colptr, values, n_rows, n_cols)); zeros are not stored
+  SpMat(const Mat<uword>& rowind, const Mat<uword>& colptr, const Mat<T>& vals, uword r, uword c) {
+    resize0(r, c);
+    for (uword j = 0; j < c; ++j) {
+      for (uword p = colptr.mem[j]; p < colptr.mem[j + 1]; ++p) if (vals.mem[p] != T(0)) { row_indices.push_back(rowind.mem[p]); values.push_back(vals.mem[p]); }
+      col_ptrs[j + 1] = row_indices.size();
+    }
+    n_nonzero = values.size();
+  }
   void resize0(uword r, uword c) { n_rows = r; n_cols = c; n_nonzero = 0; col_ptrs.assign(c + 1, 0); row_indices.clear(); values.clear(); }
   void resize(uword r, uword c) {
     if (n_nonzero) throw std::logic_error("mini_arma: SpMat::resize of a non-empty matrix is not provided");
