@@ -29,6 +29,8 @@
 #include <algorithm>
 #include <string>
 #include <vector>
+#include <thread>
+#include <atomic>
 
 #include "../../include/hibayes_b200.h"
 #include "hb_bed.cuh"
@@ -122,8 +124,9 @@ struct hb_engine {
 // ------------------------------------------------------------------------------------------
 // One thread per 16-row chunk of one column: gathers 16 int8 genotypes (0 beyond n) and stores
 // them as one 16-byte vector at Xp[slab][tile][col][16*rg ..].
+// bad (may be NULL): [0] = 1 + the first column seen with a value outside {0,1,2}, [1] = such a value
 __global__ void k_pack_i8(const int8_t* __restrict__ src, size_t ld, int n, int col0, int ncols, uint8_t* __restrict__ Xp,
-                          int S, int R, int NRG, int T, int B) {
+                          int S, int R, int NRG, int T, int B, int* __restrict__ bad = nullptr) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t per_col = (size_t)S * NRG;
   if (idx >= per_col * ncols) return;
@@ -140,6 +143,17 @@ __global__ void k_pack_i8(const int8_t* __restrict__ src, size_t ld, int n, int 
     w[i >> 2] |= x << (8 * (i & 3));
   }
   int j = col0 + c, t = j / B, cj = j % B;
+  if (bad) {
+    // a byte above 2 in any of the sixteen: (w & 0xfc...) catches 4 .. 255, the pair of low bits both set catches 3
+    uint32_t o = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o |= (w[q] & 0xfcfcfcfcu) | (w[q] & (w[q] >> 1) & 0x01010101u);
+    if (o && atomicCAS(bad, 0, j + 1) == 0) {
+      int v = 0;
+      for (int i = 0; i < 16; ++i) { const int x = (int)(int8_t)((w[i >> 2] >> (8 * (i & 3))) & 0xffu); if ((uint8_t)x > 2 && !v) v = x; }
+      bad[1] = v;
+    }
+  }
   uint4* dst = (uint4*)(Xp + ((((size_t)s * T + t) * B + cj) * R + 16 * rg));
   *dst = make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -951,58 +965,101 @@ extern "C" int hb_engine_describe(hb_engine* e, int* n_slabs, int* rows_per_slab
   return 0;
 }
 
+// Host matrix -> device tiles.  The matrix goes through two pinned bounce buffers in chunks of <= 256 MB: host threads
+// fill one (plain copies of int8 columns; fp64 columns converted and checked on the way) while the DMA engine drains the
+// other, and the range check of int8 input runs on the device inside the pack kernel -- the single-threaded host scan and the
+// pageable copies of the first version took 19 s for the 50 GB of the metric shape.
 static int load_chunked(hb_engine* e, const int8_t* X8, const double* X64, size_t ld) {
   CU(cudaSetDevice(e->cfg.device));
   const int n = e->n, m = e->m;
-  size_t cols_per_chunk = std::max<size_t>(1, (size_t)(256u << 20) / (size_t)n);
+  size_t budget = (size_t)256u << 20;
+  if (const char* cb = getenv("HB_LOAD_CHUNK")) budget = std::max<size_t>(1, (size_t)atoll(cb));   // (test hook: many small chunks)
+  size_t cols_per_chunk = std::max<size_t>(1, budget / (size_t)n);
   cols_per_chunk = std::min<size_t>(cols_per_chunk, (size_t)m);
-  int8_t* stage = nullptr;
-  CU(cudaMalloc(&stage, cols_per_chunk * (size_t)n));
-  std::vector<int8_t> hbuf;
-  if (X64 || ld != (size_t)n) hbuf.resize(cols_per_chunk * (size_t)n);
-  for (size_t c0 = 0; c0 < (size_t)m; c0 += cols_per_chunk) {
-    const size_t nc = std::min(cols_per_chunk, (size_t)m - c0);
-    const int8_t* src = nullptr;
-    if (X64) {
-      for (size_t c = 0; c < nc; ++c) {
-        const double* col = X64 + (c0 + c) * ld;
-        int8_t* dst = hbuf.data() + c * (size_t)n;
-        for (int i = 0; i < n; ++i) {
-          double v = col[i];
-          if (!(v == 0.0 || v == 1.0 || v == 2.0)) {
-            cudaFree(stage);
-            return hb_set_error("genotype (%d,%zu) = %g: this engine holds genotypes as int8 in {0,1,2}", i, c0 + c, v);
-          }
-          dst[i] = (int8_t)v;
-        }
-      }
-      src = hbuf.data();
-    } else if (ld != (size_t)n) {
-      for (size_t c = 0; c < nc; ++c) memcpy(hbuf.data() + c * (size_t)n, X8 + (c0 + c) * ld, (size_t)n);
-      src = hbuf.data();
-    } else {
-      src = X8 + c0 * ld;
-    }
-    if (!X64) {
-      // validate the value range once on the host: negative or > 2 bytes would silently change the model
-      const int8_t* p8 = src;
-      for (size_t q = 0; q < nc * (size_t)n; ++q)
-        if ((uint8_t)p8[q] > 2) {
-          cudaFree(stage);
-          return hb_set_error("genotype value %d outside {0,1,2} (column %zu)", (int)p8[q], c0 + q / n);
-        }
-    }
-    CU(cudaMemcpyAsync(stage, src, nc * (size_t)n, cudaMemcpyHostToDevice, e->stream));
-    const size_t work = (size_t)e->S * e->NRG * nc;
-    k_pack_i8<<<(unsigned)((work + 255) / 256), 256, 0, e->stream>>>(stage, (size_t)n, n, (int)c0, (int)nc, e->Xp, e->S, e->R,
-                                                                    e->NRG, e->T, e->B);
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(e->stream));
+  const size_t chunk_bytes = cols_per_chunk * (size_t)n;
+  int8_t* stage[2] = {nullptr, nullptr};
+  int8_t* pin[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int* d_bad = nullptr;
+  int rc = 0;
+  std::atomic<long long> bad64{-1};   // first fp64 entry (linear index inside its chunk) that is not 0, 1 or 2
+  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+#define TRYL(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { rc = hb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); goto done; } } while (0)
+  for (int b = 0; b < 2; ++b) {
+    TRYL(cudaMalloc(&stage[b], chunk_bytes));
+    TRYL(cudaHostAlloc(&pin[b], chunk_bytes, cudaHostAllocDefault));
+    TRYL(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
   }
-  CU(cudaFree(stage));
+  TRYL(cudaMalloc(&d_bad, 8));
+  TRYL(cudaMemsetAsync(d_bad, 0, 8, e->stream));
+  {
+    int b = 0;
+    for (size_t c0 = 0; c0 < (size_t)m; c0 += cols_per_chunk, b ^= 1) {
+      const size_t nc = std::min(cols_per_chunk, (size_t)m - c0);
+      TRYL(cudaEventSynchronize(ev[b]));   // the copy that last read this bounce buffer is through (no-op the first time)
+      // fill the bounce buffer: columns split over the host threads
+      const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, nc * (size_t)n >> 20));
+      auto fill = [&](unsigned w) {
+        const size_t ca = nc * w / nt, cb = nc * (w + 1) / nt;
+        if (X64) {
+          for (size_t c = ca; c < cb; ++c) {
+            const double* col = X64 + (c0 + c) * ld;
+            int8_t* dst = pin[b] + c * (size_t)n;
+            bool ok = true;
+            for (int i = 0; i < n; ++i) { const double v = col[i]; ok &= (v == 0.0) | (v == 1.0) | (v == 2.0); dst[i] = (int8_t)(int)v; }
+            if (!ok)
+              for (int i = 0; i < n; ++i) {
+                const double v = col[i];
+                if (!(v == 0.0 || v == 1.0 || v == 2.0)) {
+                  long long want = -1;
+                  bad64.compare_exchange_strong(want, (long long)(c * (size_t)n + i));
+                  break;
+                }
+              }
+          }
+        } else if (ld == (size_t)n) {
+          memcpy(pin[b] + ca * (size_t)n, X8 + (c0 + ca) * ld, (cb - ca) * (size_t)n);
+        } else {
+          for (size_t c = ca; c < cb; ++c) memcpy(pin[b] + c * (size_t)n, X8 + (c0 + c) * ld, (size_t)n);
+        }
+      };
+      if (nt <= 1) fill(0);
+      else {
+        std::vector<std::thread> th;
+        for (unsigned w = 1; w < nt; ++w) th.emplace_back(fill, w);
+        fill(0);
+        for (auto& t : th) t.join();
+      }
+      if (bad64.load() >= 0) {
+        const long long q = bad64.load();
+        const size_t c = (size_t)q / (size_t)n;
+        const int i = (int)((size_t)q % (size_t)n);
+        rc = hb_set_error("genotype (%d,%zu) = %g: this engine holds genotypes as int8 in {0,1,2}", i, c0 + c, X64[(c0 + c) * ld + i]);
+        goto done;
+      }
+      TRYL(cudaMemcpyAsync(stage[b], pin[b], nc * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+      TRYL(cudaEventRecord(ev[b], e->stream));
+      const size_t work = (size_t)e->S * e->NRG * nc;
+      k_pack_i8<<<(unsigned)((work + 255) / 256), 256, 0, e->stream>>>(stage[b], (size_t)n, n, (int)c0, (int)nc, e->Xp, e->S, e->R,
+                                                                      e->NRG, e->T, e->B, X64 ? nullptr : d_bad);
+      TRYL(cudaGetLastError());
+      // (stage[b] is next written two chunks later, behind this kernel on the same stream)
+    }
+  }
+  {
+    int hbad[2] = {0, 0};
+    TRYL(cudaMemcpyAsync(hbad, d_bad, 8, cudaMemcpyDeviceToHost, e->stream));
+    TRYL(cudaStreamSynchronize(e->stream));
+    if (hbad[0]) { rc = hb_set_error("genotype value %d outside {0,1,2} (column %d)", hbad[1], hbad[0] - 1); goto done; }
+  }
   e->geno_ready = true;
   e->gram_ready = false;
-  return 0;
+done:
+#undef TRYL
+  cudaStreamSynchronize(e->stream);
+  for (int b = 0; b < 2; ++b) { cudaFree(stage[b]); cudaFreeHost(pin[b]); if (ev[b]) cudaEventDestroy(ev[b]); }
+  cudaFree(d_bad);
+  return rc;
 }
 
 extern "C" int hb_engine_load_geno_i8(hb_engine* e, const int8_t* X, size_t ld) {

@@ -208,3 +208,29 @@ def test_large_shape_invariants():
     assert abs(o1[-1]["sum_r2"] - r1 @ r1) < 1e-9 * (r1 @ r1)
     assert np.all((g1 != 0) == (t1 > 0))
     e.close()
+
+
+@pytest.mark.gpu
+def test_loader_chunks_and_range_checks(monkeypatch):
+    """hb_engine_load_geno_i8 / _f64 (engine.cu, load_chunked): pinned double buffering over many small chunks gives the
+    same device tiles as one chunk (same chain, bit for bit); values outside {0,1,2} are refused -- int8 by the check inside
+    the pack kernel, fp64 by the converting host threads -- with the place named."""
+    import hibayes_b200 as hb
+    y, X = synth(700, 900, seed=31, n_causal=9)
+    kw = dict(model="BayesR", Pi=[0.95, 0.02, 0.02, 0.01], fold=[0, 1e-4, 1e-3, 1e-2], niter=8, nburn=2, thin=2, seed=77)
+    one = hb.Bayes(y, X, **kw)
+    monkeypatch.setenv("HB_LOAD_CHUNK", str(700 * 37))       # 37 columns per chunk: 25 chunks, both bounce buffers reused
+    many = hb.Bayes(y, X, **kw)
+    many64 = hb.Bayes(y, X.astype(np.float64), **kw)
+    for got in (many, many64):
+        assert np.array_equal(got["diag"]["tracker"], one["diag"]["tracker"])
+        assert np.array_equal(got["alpha"], one["alpha"]) and got["Ve"] == one["Ve"]
+    for bad_value in (3, -1, 100):
+        Xb = X.copy()
+        Xb[17, 523] = bad_value
+        with pytest.raises(RuntimeError, match=r"genotype value %d outside \{0,1,2\} \(column 523\)" % bad_value):
+            hb.Bayes(y, Xb, **kw)
+    Xf = X.astype(np.float64)
+    Xf[5, 877] = 0.5
+    with pytest.raises(RuntimeError, match=r"genotype \(5,877\) = 0\.5"):
+        hb.Bayes(y, Xf, **kw)
