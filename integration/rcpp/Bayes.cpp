@@ -104,68 +104,68 @@ Rcpp::List Bayes(
     arma::vec g = arma::zeros<arma::vec>(n), e = arma::zeros<arma::vec>(n), beta = arma::zeros<arma::vec>(a.nc);
     arma::vec gwas = arma::zeros<arma::vec>(nw), vr = arma::zeros<arma::vec>(a.nr), estR = arma::zeros<arma::vec>(n_levels);
     arma::vec epsilon = arma::zeros<arma::vec>(a.qe);
-    arma::mat mu_store = arma::zeros<arma::mat>(1, n_records), vara_store = arma::zeros<arma::mat>(1, n_records);
-    arma::mat vare_store = arma::zeros<arma::mat>(1, n_records), hsq_store = arma::zeros<arma::mat>(1, n_records);
-    arma::mat pi_store = arma::zeros<arma::mat>(n_fold, n_records), g_store = arma::zeros<arma::mat>(m, n_records);
-    arma::mat beta_store = arma::zeros<arma::mat>(a.nc, n_records), vr_store = arma::zeros<arma::mat>(a.nr, n_records);
-    arma::mat estR_store = arma::zeros<arma::mat>(n_levels, n_records), epsl_estR_store = arma::zeros<arma::mat>(a.qe, n_records);
-    arma::mat veps_store = arma::zeros<arma::mat>(1, n_records), epsl_J_beta_store = arma::zeros<arma::mat>(1, n_records);
+    arma::mat mu_rec = arma::zeros<arma::mat>(1, n_records), vg_rec = arma::zeros<arma::mat>(1, n_records);
+    arma::mat ve_rec = arma::zeros<arma::mat>(1, n_records), h2_rec = arma::zeros<arma::mat>(1, n_records);
+    arma::mat pi_rec = arma::zeros<arma::mat>(n_fold, n_records), alpha_rec = arma::zeros<arma::mat>(m, n_records);
+    arma::mat beta_rec = arma::zeros<arma::mat>(a.nc, n_records), vr_rec = arma::zeros<arma::mat>(a.nr, n_records);
+    arma::mat r_rec = arma::zeros<arma::mat>(n_levels, n_records), eps_rec = arma::zeros<arma::mat>(a.qe, n_records);
+    arma::mat veps_rec = arma::zeros<arma::mat>(1, n_records), J_rec = arma::zeros<arma::mat>(1, n_records);
     o.alpha = alpha.memptr();  o.pi = pi.memptr();  o.pip = pip.memptr();  o.g = g.memptr();  o.e = e.memptr();
     o.beta = beta.memptr();  o.gwas = nw ? gwas.memptr() : NULL;  o.vr = vr.memptr();  o.estR = estR.memptr();  o.epsilon = epsilon.memptr();
-    o.mu_store = mu_store.memptr();  o.vara_store = vara_store.memptr();  o.vare_store = vare_store.memptr();  o.hsq_store = hsq_store.memptr();
-    o.pi_store = pi_store.memptr();  o.alpha_store = g_store.memptr();  o.beta_store = beta_store.memptr();
-    o.vr_store = vr_store.memptr();  o.estR_store = estR_store.memptr();
-    o.veps_store = veps_store.memptr();  o.J_store = epsl_J_beta_store.memptr();  o.epsilon_store = epsl_estR_store.memptr();
+    o.mu_store = mu_rec.memptr();  o.vara_store = vg_rec.memptr();  o.vare_store = ve_rec.memptr();  o.hsq_store = h2_rec.memptr();
+    o.pi_store = pi_rec.memptr();  o.alpha_store = alpha_rec.memptr();  o.beta_store = beta_rec.memptr();
+    o.vr_store = vr_rec.memptr();  o.estR_store = r_rec.memptr();
+    o.veps_store = veps_rec.memptr();  o.J_store = J_rec.memptr();  o.epsilon_store = eps_rec.memptr();
 
     if(hb_bayes(&a, &o) != 0)  throw Rcpp::exception(hb_last_error());     // -> R's stop() through END_RCPP
 
     // the named list of Bayes.cpp:919-1040, in its order
-    List results;
-    List MCMCsample;
+    List out;
+    List samples;
     if(a.nr){
-        results["Vr"] = vr;
-        MCMCsample["Vr"] = vr_store;
+        out["Vr"] = vr;
+        samples["Vr"] = vr_rec;
     }
-    results["Vg"] = o.Vg;
-    results["Ve"] = o.Ve;
-    results["h2"] = o.h2;
-    MCMCsample["Vg"] = vara_store;
-    MCMCsample["Ve"] = vare_store;
-    MCMCsample["h2"] = hsq_store;
-    results["mu"] = o.mu;
-    MCMCsample["mu"] = mu_store;
+    out["Vg"] = o.Vg;
+    out["Ve"] = o.Ve;
+    out["h2"] = o.h2;
+    samples["Vg"] = vg_rec;
+    samples["Ve"] = ve_rec;
+    samples["h2"] = h2_rec;
+    out["mu"] = o.mu;
+    samples["mu"] = mu_rec;
     if(a.nc){
-        results["beta"] = beta;
-        MCMCsample["beta"] = beta_store;
+        out["beta"] = beta;
+        samples["beta"] = beta_rec;
     }
-    results["alpha"] = alpha;
-    MCMCsample["alpha"] = g_store;
-    results["pi"] = pi;
-    MCMCsample["pi"] = pi_store;
+    out["alpha"] = alpha;
+    samples["alpha"] = alpha_rec;
+    out["pi"] = pi;
+    samples["pi"] = pi_rec;
     if(a.ne){
-        results["Veps"] = o.Veps;
-        results["J"] = o.J;
-        results["epsilon"] = epsilon;
-        MCMCsample["Veps"] = veps_store;
-        MCMCsample["J"] = epsl_J_beta_store;
-        MCMCsample["epsilon"] = epsl_estR_store;
+        out["Veps"] = o.Veps;
+        out["J"] = o.J;
+        out["epsilon"] = epsilon;
+        samples["Veps"] = veps_rec;
+        samples["J"] = J_rec;
+        samples["epsilon"] = eps_rec;
     }
     if(a.nr){
-        List listr(2);
-        listr[0] = wrap(r_levels.begin(), r_levels.end());
-        listr[1] = wrap(estR);
-        DataFrame r = listr;
+        List lr(2);
+        lr[0] = wrap(r_levels.begin(), r_levels.end());
+        lr[1] = wrap(estR);
+        DataFrame r = lr;
         Rcpp::CharacterVector names(2);
         names[0] = "Levels";
         names[1] = "Estimation";
         r.attr("names") = names;
-        results["r"] = r;
-        MCMCsample["r"] = estR_store;
+        out["r"] = r;
+        samples["r"] = r_rec;
     }
-    results["g"] = g;
-    results["e"] = e;
-    results["pip"] = pip;
-    if(nw)  results["gwas"] = gwas;
-    results["MCMCsamples"] = MCMCsample;
-    return results;
+    out["g"] = g;
+    out["e"] = e;
+    out["pip"] = pip;
+    if(nw)  out["gwas"] = gwas;
+    out["MCMCsamples"] = samples;
+    return out;
 }

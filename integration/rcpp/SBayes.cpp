@@ -29,29 +29,29 @@ static Rcpp::List run(bool sparse, arma::mat &sumstat, const arma::mat *ldm_d, c
     a.outfreq = outfreq;  a.verbose = verbose;
     a.seed = hb_dropin::seed_from_r();
     const int n_records = (niter - nburn) / thin;
-    arma::vec g = arma::zeros<arma::vec>(m), pi = arma::zeros<arma::vec>(n_fold), nzrate = arma::zeros<arma::vec>(m), wppai = arma::zeros<arma::vec>(nw);
-    arma::mat vara_store = arma::zeros<arma::mat>(1, n_records), vare_store = arma::zeros<arma::mat>(1, n_records), hsq_store = arma::zeros<arma::mat>(1, n_records);
-    arma::mat pi_store = arma::zeros<arma::mat>(n_fold, n_records), g_store = arma::zeros<arma::mat>(m, n_records);
-    o.alpha = g.memptr();  o.pi = pi.memptr();  o.pip = nzrate.memptr();  o.gwas = nw ? wppai.memptr() : NULL;
-    o.vara_store = vara_store.memptr();  o.vare_store = vare_store.memptr();  o.hsq_store = hsq_store.memptr();
-    o.pi_store = pi_store.memptr();  o.alpha_store = g_store.memptr();
+    arma::vec alpha_v = arma::zeros<arma::vec>(m), pi = arma::zeros<arma::vec>(n_fold), pip_v = arma::zeros<arma::vec>(m), gwas_v = arma::zeros<arma::vec>(nw);
+    arma::mat vg_rec = arma::zeros<arma::mat>(1, n_records), ve_rec = arma::zeros<arma::mat>(1, n_records), h2_rec = arma::zeros<arma::mat>(1, n_records);
+    arma::mat pi_rec = arma::zeros<arma::mat>(n_fold, n_records), alpha_rec = arma::zeros<arma::mat>(m, n_records);
+    o.alpha = alpha_v.memptr();  o.pi = pi.memptr();  o.pip = pip_v.memptr();  o.gwas = nw ? gwas_v.memptr() : NULL;
+    o.vara_store = vg_rec.memptr();  o.vare_store = ve_rec.memptr();  o.hsq_store = h2_rec.memptr();
+    o.pi_store = pi_rec.memptr();  o.alpha_store = alpha_rec.memptr();
     if((sparse ? hb_sbayess(&a, &o) : hb_sbayesd(&a, &o)) != 0)  throw Rcpp::exception(hb_last_error());
-    List results;
-    List MCMCsample;
-    results["Vg"] = o.Vg;
-    results["Ve"] = o.Ve;
-    results["h2"] = o.h2;
-    MCMCsample["Vg"] = vara_store;
-    MCMCsample["Ve"] = vare_store;
-    MCMCsample["h2"] = hsq_store;
-    results["alpha"] = g;
-    MCMCsample["alpha"] = g_store;
-    results["pi"] = pi;
-    MCMCsample["pi"] = pi_store;
-    results["pip"] = nzrate;
-    if(nw)  results["gwas"] = wppai;
-    results["MCMCsamples"] = MCMCsample;
-    return results;
+    List out;
+    List samples;
+    out["Vg"] = o.Vg;
+    out["Ve"] = o.Ve;
+    out["h2"] = o.h2;
+    samples["Vg"] = vg_rec;
+    samples["Ve"] = ve_rec;
+    samples["h2"] = h2_rec;
+    out["alpha"] = alpha_v;
+    samples["alpha"] = alpha_rec;
+    out["pi"] = pi;
+    samples["pi"] = pi_rec;
+    out["pip"] = pip_v;
+    if(nw)  out["gwas"] = gwas_v;
+    out["MCMCsamples"] = samples;
+    return out;
 }
 
 // [[Rcpp::export]]
