@@ -19,7 +19,7 @@ SYMBOLS = [
     "hb_engine_get_pip_counts", "hb_engine_accumulate_effects", "hb_engine_get_effect_sums", "hb_engine_predict",
     "hb_engine_last_sweep_ms", "hb_engine_describe", "hb_bayes",
     "hb_engine_ipc_handle", "hb_engine_set_peers", "hb_engine_gram_device", "hb_engine_u_centered_sums",
-    "hb_test_class_thresholds", "hb_test_class_of", "hb_ld_engine_create", "hb_ld_engine_destroy", "hb_ld_engine_load_dense", "hb_ld_engine_load_csc", "hb_ld_engine_describe", "hb_ld_engine_set_state",
+    "hb_test_class_thresholds", "hb_test_class_of", "hb_test_class_batch_device", "hb_ld_engine_create", "hb_ld_engine_destroy", "hb_ld_engine_load_dense", "hb_ld_engine_load_csc", "hb_ld_engine_describe", "hb_ld_engine_set_state",
     "hb_ld_engine_set_vargL", "hb_ld_engine_set_sparse_info", "hb_ld_engine_get", "hb_ld_engine_sweep", "hb_sbayesd", "hb_sbayess",
     "hb_engine_load_bed", "hb_ldmat_create", "hb_ldmat_destroy", "hb_ldmat_load_i8", "hb_ldmat_load_bed", "hb_ldmat_stats",
     "hb_ldmat_dense", "hb_ldmat_sparse", "hb_ldmat_sparse_get", "hb_ldmat_set_panel_cols", "hb_ldmat_last_ms", "hb_bed_decode",

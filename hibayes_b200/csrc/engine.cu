@@ -1689,6 +1689,44 @@ extern "C" int hb_test_class_thresholds(int n_fold, double u, const double* a, c
   hbk::solve_thresholds<HB_MAX_FOLD>(n_fold, u, a, c, logpi0, TL, TH);
   return 0;
 }
+// The same two decisions ON THE DEVICE for `count` (rr, u) pairs of one SNP's parameters (test hook for the disagreement
+// count against the reference's literal form, tests/test_class_decisions_gpu.py): by_threshold[i] = thr_class after
+// solve_thresholds(u[i]) as k_prep / the sweep do it (-1 = inside a bracket), exact[i] = the soft-max evaluation they fall
+// back to.
+__global__ void k_test_class_batch(int nf, long long count, const double* __restrict__ rr, const double* __restrict__ u,
+                                   const double* __restrict__ a, const double* __restrict__ c, double logpi0,
+                                   int8_t* __restrict__ by_threshold, int8_t* __restrict__ exact) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double av[HB_MAX_FOLD], cv[HB_MAX_FOLD], TL[HB_MAX_FOLD], TH[HB_MAX_FOLD], cum[HB_MAX_FOLD];
+  for (int k = 0; k < nf - 1; ++k) { av[k] = a[k]; cv[k] = c[k]; }
+  hbk::solve_thresholds<HB_MAX_FOLD>(nf, u[i], av, cv, logpi0, TL, TH);
+  by_threshold[i] = (int8_t)hbk::thr_class<HB_MAX_FOLD>(nf, rr[i], TL, TH);
+  hbk::class_cum<HB_MAX_FOLD>(nf, rr[i], av, cv, logpi0, cum);
+  exact[i] = (int8_t)hbk::class_from_cum<HB_MAX_FOLD>(nf, u[i], cum);
+}
+extern "C" int hb_test_class_batch_device(int device, int n_fold, long long count, const double* rr, const double* u, const double* a,
+                                          const double* c, double logpi0, int8_t* by_threshold, int8_t* exact) {
+  if (n_fold < 2 || n_fold > HB_MAX_FOLD || count <= 0 || !rr || !u || !a || !c || !by_threshold || !exact)
+    return hb_set_error("hb_test_class_batch_device: bad argument");
+  CU(cudaSetDevice(device));
+  double *d_rr = nullptr, *d_u = nullptr, *d_a = nullptr, *d_c = nullptr;
+  int8_t *d_t = nullptr, *d_e = nullptr;
+  int rc = 0;
+#define TRYT(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { rc = hb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); goto done; } } while (0)
+  TRYT(cudaMalloc(&d_rr, count * 8)); TRYT(cudaMalloc(&d_u, count * 8));
+  TRYT(cudaMalloc(&d_a, HB_MAX_FOLD * 8)); TRYT(cudaMalloc(&d_c, HB_MAX_FOLD * 8));
+  TRYT(cudaMalloc(&d_t, count)); TRYT(cudaMalloc(&d_e, count));
+  TRYT(cudaMemcpy(d_rr, rr, count * 8, cudaMemcpyHostToDevice)); TRYT(cudaMemcpy(d_u, u, count * 8, cudaMemcpyHostToDevice));
+  TRYT(cudaMemcpy(d_a, a, (n_fold - 1) * 8, cudaMemcpyHostToDevice)); TRYT(cudaMemcpy(d_c, c, (n_fold - 1) * 8, cudaMemcpyHostToDevice));
+  k_test_class_batch<<<(unsigned)((count + 255) / 256), 256>>>(n_fold, count, d_rr, d_u, d_a, d_c, logpi0, d_t, d_e);
+  TRYT(cudaGetLastError());
+  TRYT(cudaMemcpy(by_threshold, d_t, count, cudaMemcpyDeviceToHost)); TRYT(cudaMemcpy(exact, d_e, count, cudaMemcpyDeviceToHost));
+done:
+#undef TRYT
+  cudaFree(d_rr); cudaFree(d_u); cudaFree(d_a); cudaFree(d_c); cudaFree(d_t); cudaFree(d_e);
+  return rc;
+}
 // class from the thresholds (-1 = inside a bracket) and from the exact cumulative probabilities
 extern "C" int hb_test_class_of(int n_fold, double rr, double u, const double* a, const double* c, double logpi0, const double* TL,
                                 const double* TH, int* by_threshold, int* exact) {

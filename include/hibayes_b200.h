@@ -294,6 +294,9 @@ int hb_bayes(const hb_bayes_args* a, hb_bayes_out* o);
 int hb_test_class_thresholds(int n_fold, double u, const double* a, const double* c, double logpi0, double* TL, double* TH);
 int hb_test_class_of(int n_fold, double rr, double u, const double* a, const double* c, double logpi0, const double* TL,
                      const double* TH, int* by_threshold, int* exact);
+/* the same two decisions taken on the device for `count` (rr, u) pairs (needs a GPU): int8 classes, -1 = inside a bracket */
+int hb_test_class_batch_device(int device, int n_fold, long long count, const double* rr, const double* u, const double* a,
+                               const double* c, double logpi0, int8_t* by_threshold, int8_t* exact);
 
 /* ------------------------------------------------------------------ SBayesD (dense LD, summary statistics) */
 /* Device engine for the LD-column sweep of SBayesD(), /root/reference/src/SBayesD.cpp:253-456: r_hat lives on the

@@ -122,6 +122,38 @@ void hbo_draw_uz(uint64_t seed, uint32_t dom, uint32_t iter, uint32_t idx, uint3
 double hbo_invgauss(double mu, double lambda, double u, double z) { return hb_invgauss_from_uz(mu, lambda, u, z); }
 double hbo_invgauss_literal_root(double mu, double lambda, double z) { return hb_invgauss_literal_root(mu, lambda, z); }
 
+/* The class draw of BayesR exactly as the reference writes it (Bayes.cpp:757-781) for `count` right-hand sides of one SNP:
+ * rhs already holds x'r (+ xx * oldgi), rval the uniform.  n_fold = 2 gives the BayesB/C form of :641-645 / :685-689
+ * (acceptProb = 1 / sum(exp(s - s[0])), class 1 unless rval < acceptProb) -- the same numbers in the same order. */
+void hbo_class_literal_batch(int n_fold, long long count, const double* rhs_v, const double* rval_v, double xx, double vare_,
+                             const double* vara_fold, const double* logpi, int8_t* out) {
+#pragma omp parallel for schedule(static)
+  for (long long q = 0; q < count; ++q) {
+    double s[8], stemp[8];
+    const double rhs = rhs_v[q], rval = rval_v[q];
+    const double lhs = xx / vare_;
+    s[0] = logpi[0];
+    for (int j = 1; j < n_fold; ++j) {
+      const double vare_vara = vare_ / vara_fold[j];
+      const double logdetV = log(vara_fold[j] * lhs + 1);
+      const double uhat = rhs / (xx + vare_vara);
+      s[j] = -0.5 * (logdetV - (rhs * uhat / vare_)) + logpi[j];
+    }
+    for (int j = 0; j < n_fold; ++j) {
+      double temp = 0.0;
+      for (int k = 0; k < n_fold; ++k) temp += exp(s[k] - s[j]);
+      stemp[j] = 1 / temp;
+    }
+    double acceptProb = 0;
+    int indistflag = 0;
+    for (int j = 0; j < n_fold; ++j) {
+      acceptProb += stemp[j];
+      if (rval < acceptProb) { indistflag = j; break; }
+    }
+    out[q] = (int8_t)indistflag;
+  }
+}
+
 /* column accessor: the reference holds X as arma::mat (fp64); an int8 source is
  * widened into a scratch column so the arithmetic is identical. */
 static const double* xcol(const hbo_bayes_args* a, int j, double* scratch) {

@@ -108,6 +108,10 @@ typedef struct { int32_t kind; int32_t pad; double value; double param; } hbo_ta
 void hbo_tape_begin(hbo_tape_entry* buf, uint64_t cap);
 uint64_t hbo_tape_end(void);   /* entries the run produced (may exceed cap: then the tape is incomplete) */
 
+/* the reference's literal class draw (Bayes.cpp:757-781) for `count` (rhs, uniform) pairs of one SNP */
+void hbo_class_literal_batch(int n_fold, long long count, const double* rhs, const double* rval, double xx, double vare_,
+                             const double* vara_fold, const double* logpi, int8_t* out);
+
 /* helpers exposed for unit tests */
 double hbo_var(const double* x, int n);             /* Armadillo var(), norm_type 0 */
 double hbo_qnorm(double p);
