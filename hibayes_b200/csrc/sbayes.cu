@@ -143,8 +143,14 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
       for (int row = w * LB + tid; row < m; row += p.W * LB) {
         if (row >= s0 && row < s1) continue;
         double acc = __ldcg(p.r_hat + row);
-#pragma unroll 4
-        for (int s = 0; s < ku; ++s) acc = fma(__ldcg(qd + s), p.ldm[(size_t)__ldcg(qi + s) * m + row], acc);
+        // sixteen LD entries in flight per row (a tile changes up to 256 SNPs: four at a time was 64 trips to memory)
+        for (int sq = 0; sq < ku; sq += 16) {
+          double lv[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) lv[q] = (sq + q < ku) ? p.ldm[(size_t)__ldcg(qi + sq + q) * m + row] : 0.0;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) if (sq + q < ku) acc = fma(__ldcg(qd + sq + q), lv[q], acc);
+        }
         p.r_hat[row] = acc;
       }
       if (tid == 0) entries += (unsigned long long)ku * (unsigned long long)((m - w * LB + p.W * LB - 1) / (p.W * LB)) * LB;
@@ -172,11 +178,15 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
         const int buf = (t - 1) & 1;
         const int ku = *(volatile int*)(p.q_cnt + buf);
         double acc = __ldcg(p.r_hat + j);
-#pragma unroll 4
-        for (int s = 0; s < ku; ++s) {
-          const int c = __ldcg(p.q_idx + buf * LB + s);
-          const double ld = CSC ? p.blk1[((size_t)(t - 1) * LB + (c - (t - 1) * LB)) * LB + tid] : p.ldm[(size_t)c * m + j];
-          acc = fma(__ldcg(p.q_dn + buf * LB + s), ld, acc);
+        for (int sq = 0; sq < ku; sq += 16) {   // (on the serial path: sixteen entries in flight)
+          double lv[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int c = (sq + q < ku) ? __ldcg(p.q_idx + buf * LB + sq + q) : (t - 1) * LB;
+            lv[q] = CSC ? p.blk1[((size_t)(t - 1) * LB + (c - (t - 1) * LB)) * LB + tid] : p.ldm[(size_t)c * m + j];
+          }
+#pragma unroll
+          for (int q = 0; q < 16; ++q) if (sq + q < ku) acc = fma(__ldcg(p.q_dn + buf * LB + sq + q), lv[q], acc);
         }
         p.r_hat[j] = acc;
         if (tid == 0) entries += (unsigned long long)ku * LB;
@@ -239,8 +249,11 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
         }
         __syncthreads();
         // chain of the candidates in SNP order (one warp): rhs_s = rhs0_s - sum_{s' < s} n LD[c_s, c_s'] delta_s'
-        if (warp == 0) {
-          for (int sb = 0; sb < k; sb += 32) {
+        // blocked forward substitution: warp 0 chains 32 candidates, then all threads take those 32 changes out of the
+        // right-hand sides of the later candidates (32 LD entries in flight per thread, same order of additions as a
+        // candidate-by-candidate sweep) -- the one warp used to fetch them itself, eight at a time, for every block again
+        for (int sb = 0; sb < k; sb += 32) {
+          if (warp == 0) {
             const int sidx = sb + lane;
             const bool valid = sidx < k;
             const int li = valid ? c_idx[sidx] : 0;   // position inside the tile
@@ -248,9 +261,6 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
             const double siv = valid ? c_iv[sidx] : 0.0, ssdz = valid ? c_sdz[sidx] : 0.0, sgold = valid ? c_gold[sidx] : 0.0;
             const int scls = valid ? c_cls[sidx] : 0;
             const double ssd = valid ? c_sd[sidx] : 0.0, svx = valid ? c_vx[sidx] : 0.0;
-#pragma unroll 8
-            for (int sp = 0; sp < sb; ++sp)
-              if (valid) rhs = fma(-(nscale * diag(t, c_idx[sp], li)), c_delta[sp], rhs);
             const int nl = min(32, k - sb);
             // the LD entries towards the earlier candidates of this block, all loads in flight at once: the chain below
             // then waits for a shuffle and a fused multiply-add per step, not for a trip to L2
@@ -285,13 +295,32 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
             if (valid) { c_delta[sidx] = mydelta; c_gnew[sidx] = mygnew; c_loop[sidx] = myloop; c_l2[sidx] = myl2; }
             __syncwarp();
           }
+          __syncthreads();
+          if (sb + 32 < k) {
+            const int sidx = sb + 32 + tid;   // (k <= LB: at most one later candidate per thread)
+            if (sidx < k) {
+              const int li = c_idx[sidx];
+              double r = c_rhs0[sidx];
+              double lq[32];
+#pragma unroll
+              for (int lp = 0; lp < 32; ++lp) lq[lp] = nscale * diag(t, c_idx[sb + lp], li);
+#pragma unroll
+              for (int lp = 0; lp < 32; ++lp) r = fma(-lq[lp], c_delta[sb + lp], r);
+              c_rhs0[sidx] = r;
+            }
+            __syncthreads();
+          }
         }
-        __syncthreads();
-        // exact right-hand side of every SNP of the tile and its class
+        // exact right-hand side of every SNP of the tile and its class (32 LD entries in flight)
         double rhs = rbase;
         if (act) {
-#pragma unroll 8
-          for (int s = 0; s < myrank; ++s) rhs = fma(-(nscale * diag(t, c_idx[s], tid)), c_delta[s], rhs);
+          for (int sq = 0; sq < myrank; sq += 32) {
+            double lq[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) lq[q] = (sq + q < myrank) ? nscale * diag(t, c_idx[sq + q], tid) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) if (sq + q < myrank) rhs = fma(-lq[q], c_delta[sq + q], rhs);
+          }
         }
         const int cls2 = act ? classify(rhs) : 0;
         if (tid == 0) s_flag = 0;
@@ -336,8 +365,13 @@ __global__ void __launch_bounds__(LB) k_ld_sweep(const __grid_constant__ LdParam
       __syncthreads();
       if (j < m) {
         double acc = __ldcg(p.r_hat + j);
-#pragma unroll 8
-        for (int s = 0; s < ku; ++s) acc = fma(c_delta[s], diag(t, c_idx[s], tid), acc);
+        for (int sq = 0; sq < ku; sq += 32) {
+          double lq[32];
+#pragma unroll
+          for (int q = 0; q < 32; ++q) lq[q] = (sq + q < ku) ? diag(t, c_idx[sq + q], tid) : 0.0;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) if (sq + q < ku) acc = fma(c_delta[sq + q], lq[q], acc);
+        }
         p.r_hat[j] = acc;
       }
       if (tid == 0) entries += (unsigned long long)ku * LB;
