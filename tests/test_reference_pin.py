@@ -306,3 +306,25 @@ def test_read_bed_is_the_references(ref, tmp_path, impute, dominance):
     want, _ = ref.read_bed(img, 203, 77, impute=impute, dominance=dominance)
     for max_line in (10000, 16):
         assert np.array_equal(ref.ref_read_bed(str(q), 203, 77, impute=impute, dominance=dominance, max_line=max_line), want)
+
+
+@pytest.mark.parametrize("model,Pi,fold", [("BayesR", [0.95, 0.02, 0.02, 0.01], [0, 1e-4, 1e-3, 1e-2]), ("BayesBpi", [0.9, 0.1], None),
+                                           ("BayesA", [0.9, 0.1], None)])
+def test_bayes_long_chain_stays_bit_identical(ref, model, Pi, fold):
+    """150 iterations on n = 1 500 x m = 2 500 (about 4e5 draws replayed, 3.75e5 SNP updates): oracle and compiled reference do
+    not drift apart -- every recorded effect still the same bits at the end."""
+    y, X = synth(1500, 2500, seed=77, n_causal=25)
+    o, r = _pair(ref.bayes, y, X, model, Pi, fold=fold, niter=150, nburn=50, thin=10, seed=909)
+    assert len(o["tape"]) > 150 * 2500
+    _same(o, r, keys=("alpha", "pip", "pi", "g", "e"), scalars=("Vg", "Ve", "h2", "mu"), rtol=1e-12)
+
+
+@pytest.mark.parametrize("model,Pi,fold", [("BayesCpi", [0.9, 0.1], None), ("BayesBpi", [0.9, 0.1], None), ("BayesL", [0.9, 0.1], None)])
+def test_bayes_single_step_real_valued_rows_other_models(ref, model, Pi, fold):
+    """The single-step call as ssbrm() makes it (R/ssbayes.r:305-321: real-valued imputed rows, J covariate, sparse Gi) for
+    more models, at a size where the imputed rows matter (a third of the records)."""
+    from tests.test_single_step import single_step_case
+    y, X, J, G, index1 = single_step_case(21, n=240, m=90, ne=80, qe=110)
+    o, r = _pair(ref.bayes, y, X, model, Pi, fold=fold, niter=24, nburn=8, thin=2, seed=4711, epsl_y_J=J, epsl_Gi=G, epsl_index=index1)
+    _same(o, r, exact=False, keys=("alpha", "pip", "g", "e", "epsilon"), scalars=("Vg", "Ve", "h2", "mu", "Veps", "J"),
+          rtol=BAYESL_RTOL if model == "BayesL" else 1e-9)
